@@ -1,0 +1,11 @@
+"""gym.spaces stand-in (see gym/__init__.py)."""
+
+
+class Box:
+    def __init__(self, low=None, high=None, shape=None, dtype=None):
+        self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
+
+
+class Discrete:
+    def __init__(self, n):
+        self.n = n
