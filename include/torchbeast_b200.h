@@ -1,0 +1,110 @@
+/* torchbeast_b200 C-ABI: the drop-in boundary of the B200-native IMPALA learner hot path.
+ *
+ * Plain C, raw device pointers + sizes + a cudaStream_t passed as void*; no torch types.
+ * The reference (facebookresearch/torchbeast) has NO FFI for this path - its boundary is
+ * the Python function surface - so every entry point below
+ * names the reference Python function (file:line under /root/reference) whose device-side
+ * work it replaces.  The Python mirror of that surface lives in torchbeast_b200/ and binds
+ * these symbols with ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; tb_last_error() returns a
+ *     thread-local message for the calling thread's last failure.
+ *   - all pointers are DEVICE pointers unless the name ends in _host; buffers are owned by
+ *     the caller (PyTorch caching allocator); outputs are written in place; nothing is
+ *     allocated or freed by the library on the data path.
+ *   - launches go to `stream` (the caller's current stream) and never synchronise.
+ *   - layouts are the reference's: time-major, element (t,b) at offset t*B+b
+ *     (logits: (t*B+b)*A + a), i.e. contiguous [T,B] / [T,B,A] tensors.
+ *   - clip thresholds: a negative or NaN value means Python `None` (no clipping).
+ *   - thread-safety: no global mutable state; reductions use the caller's `workspace`
+ *     (tb_workspace_bytes() bytes, zero-initialised ONCE by the caller, self-cleaning).
+ */
+#ifndef TORCHBEAST_B200_H_
+#define TORCHBEAST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB_ABI_VERSION 1
+
+int tb_abi_version(void);
+const char* tb_last_error(void);
+/* Number of SMs / compute capability of the current device (host query). */
+int tb_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+/* Bytes of zero-initialised scratch the reducing kernels need (counter + per-CTA partials). */
+size_t tb_workspace_bytes(void);
+
+/* ---- V-trace ----------------------------------------------------------------------- */
+
+/* torchbeast/core/vtrace.py:50-55  action_log_probs(policy_logits, actions)
+ * logits [N,A] f32, actions [N] i64 -> out [N] f32 = log_softmax(logits)[actions].       */
+int tb_action_log_probs_f32(const float* logits, const int64_t* actions, int64_t N, int64_t A,
+                            float* out, void* stream);
+int tb_action_log_probs_f64(const double* logits, const int64_t* actions, int64_t N, int64_t A,
+                            double* out, void* stream);
+
+/* torchbeast/core/vtrace.py:91-139  from_importance_weights(...) -> VTraceReturns(vs, pg_advantages)
+ * log_rhos/discounts/rewards/values [T,B], bootstrap [B]; outputs vs, pg_adv [T,B].
+ * One launch; reverse-time scan, T split over warps with an affine-map combine.          */
+int tb_vtrace_from_importance_weights_f32(const float* log_rhos, const float* discounts,
+                                          const float* rewards, const float* values,
+                                          const float* bootstrap, int64_t T, int64_t B,
+                                          float clip_rho, float clip_pg_rho, float* vs,
+                                          float* pg_adv, void* stream);
+int tb_vtrace_from_importance_weights_f64(const double* log_rhos, const double* discounts,
+                                          const double* rewards, const double* values,
+                                          const double* bootstrap, int64_t T, int64_t B,
+                                          double clip_rho, double clip_pg_rho, double* vs,
+                                          double* pg_adv, void* stream);
+
+/* Fused learner loss block: torchbeast/core/vtrace.py:58-88 (from_logits) +
+ * monobeast.py:107-125 / polybeast_learner.py:113-131 (three losses) +
+ * monobeast.py:245-277 / polybeast_learner.py:332-361 (reward clip, discounts, weighting)
+ * and their closed-form backward, ONE launch.
+ *
+ * inputs (already shifted: batch[1:], learner_outputs[:-1]):
+ *   behavior_logits, target_logits [T,B,A] f32; actions [T,B] i64; rewards [T,B] f32 (raw);
+ *   done [T,B] u8 (bool) if `discounts`==NULL, else discounts [T,B] f32 used as is;
+ *   values [T,B] f32; bootstrap [B] f32.
+ * flags: clip_rewards!=0 clamps rewards to [-1,1] (reward_clipping == "abs_one").
+ * outputs:
+ *   vs, pg_adv, log_rhos, behavior_alp, target_alp [T,B] f32 (all required);
+ *   losses_out [4] f32 = {pg_loss, baseline_cost*baseline_loss, entropy_cost*entropy_loss, total};
+ *   grad_logits [T(+1),B,A], grad_values [T(+1),B] f32 = d total / d target_logits, d values
+ *   (may both be NULL: forward only).  If zero_tail!=0 they have T+1 rows and row T is
+ *   zero-filled (the bootstrap row of the learner outputs gets no gradient, vtrace.py:91).
+ * workspace: tb_workspace_bytes() zero-initialised bytes (see conventions).                */
+int tb_impala_loss_fwd_bwd_f32(const float* behavior_logits, const float* target_logits,
+                               const int64_t* actions, const float* rewards,
+                               const uint8_t* done, const float* discounts, const float* values,
+                               const float* bootstrap, int64_t T, int64_t B, int64_t A,
+                               float discounting, float baseline_cost, float entropy_cost,
+                               int clip_rewards, float clip_rho, float clip_pg_rho, float* vs,
+                               float* pg_adv, float* log_rhos, float* behavior_alp,
+                               float* target_alp, float* losses_out, float* grad_logits,
+                               float* grad_values, int zero_tail, void* workspace, void* stream);
+
+/* ---- the three loss functions on their own (API mirror; tests pass float64) ---------- */
+
+/* monobeast.py:107-108 compute_baseline_loss: out[0] = 0.5*sum(adv^2); grad (nullable) = adv. */
+int tb_baseline_loss_f32(const float* adv, int64_t N, float* out, float* grad, void* workspace, void* stream);
+int tb_baseline_loss_f64(const double* adv, int64_t N, double* out, double* grad, void* workspace, void* stream);
+/* monobeast.py:111-115 compute_entropy_loss: out[0] = sum(p*log p) over [N,A]; grad nullable [N,A]. */
+int tb_entropy_loss_f32(const float* logits, int64_t N, int64_t A, float* out, float* grad, void* workspace, void* stream);
+int tb_entropy_loss_f64(const double* logits, int64_t N, int64_t A, double* out, double* grad, void* workspace, void* stream);
+/* monobeast.py:118-125 compute_policy_gradient_loss: out[0] = sum(-log pi(a)*adv); grad nullable
+ * [N,A] = adv*(p - onehot(a)) (advantages get no gradient).                               */
+int tb_pg_loss_f32(const float* logits, const int64_t* actions, const float* adv, int64_t N, int64_t A,
+                   float* out, float* grad, void* workspace, void* stream);
+int tb_pg_loss_f64(const double* logits, const int64_t* actions, const double* adv, int64_t N, int64_t A,
+                   double* out, double* grad, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TORCHBEAST_B200_H_ */
