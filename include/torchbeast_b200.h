@@ -104,6 +104,50 @@ int tb_pg_loss_f32(const float* logits, const int64_t* actions, const float* adv
 int tb_pg_loss_f64(const double* logits, const int64_t* actions, const double* adv, int64_t N, int64_t A,
                    double* out, double* grad, void* workspace, void* stream);
 
+/* ---- AtariNet (monobeast.py:545-635) forward / backward --------------------------------- */
+
+/* Parameters live in ONE flat f32 buffer in the reference's state_dict order and shapes
+ * (BASELINE.md section 5): conv1.weight (32,4,8,8), conv1.bias, conv2.weight (64,32,4,4), conv2.bias,
+ * conv3.weight (64,64,3,3), conv3.bias, fc.weight (512,3136), fc.bias, [core.weight_ih_l0,
+ * core.weight_hh_l0, core.bias_ih_l0, core.bias_hh_l0, ...l1 (2076 x 519 each)], policy.weight (A,519),
+ * policy.bias, baseline.weight (1,519), baseline.bias.  Gradients use the same layout.       */
+int64_t tb_atarinet_param_count(int num_actions, int use_lstm);
+/* Bytes of caller-owned workspace for a [T1,B] rollout (T1 = unroll_length + 1): patch matrices,
+ * activations kept for backward, packed weights, split-K scratch.                            */
+size_t tb_atarinet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm);
+
+/* monobeast.py:582-632 AtariNet.forward (without the action sampling, which the learner never
+ * uses - SURVEY.md K8).  frame u8 [T1,B,4,84,84]; reward f32 [T1,B]; last_action i64 [T1,B];
+ * notdone f32 [T1,B] = (~done).float() (LSTM only; multiplies the state before each step,
+ * monobeast.py:607-609); h0,c0 / hN,cN f32 [2,B,519] (LSTM only).
+ * -> policy_logits f32 [T1,B,A], baseline f32 [T1,B].  Activations stay in `workspace`.      */
+int tb_atarinet_forward(const uint8_t* frame, const float* reward, const float* notdone,
+                        const int64_t* last_action, const float* h0, const float* c0,
+                        const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
+                        void* workspace, float* policy_logits, float* baseline, float* hN, float* cN,
+                        void* stream);
+/* Backward of the above (replaces the autograd graph of total_loss.backward(), monobeast.py:290):
+ * grad_logits [T1,B,A], grad_baseline [T1,B] -> grads (flat, parameter layout, overwritten).
+ * Must follow a tb_atarinet_forward on the same workspace and parameters.                    */
+int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
+                         const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
+                         void* workspace, float* grads, void* stream);
+
+/* ---- flat-buffer optimizer step ------------------------------------------------------------ */
+
+/* out_sumsq[0] = sum(grads^2) (double accumulation, deterministic).  First half of
+ * nn.utils.clip_grad_norm_ (monobeast.py:291); grads must be 16-byte aligned.                */
+int tb_grad_sumsq_f32(const float* grads, int64_t n, float* out_sumsq, void* workspace, void* stream);
+/* Second half of clip_grad_norm_ fused with torch.optim.RMSprop.step() (monobeast.py:292,388-394):
+ *   coef = min(1, max_norm/(sqrt(sumsq)+1e-6)) (max_norm < 0: no clipping); grads *= coef (left
+ *   clipped in place like the reference); square_avg = alpha*square_avg + (1-alpha)*g^2;
+ *   params -= lr * g/(sqrt(square_avg)+eps)   (momentum != 0: buf = momentum*buf + g/avg; params -= lr*buf).
+ * lr_device (nullable) overrides `lr` with a device scalar; grad_norm_out (nullable) receives the
+ * pre-clip norm.  No host synchronisation.                                                   */
+int tb_clip_rmsprop_step_f32(float* params, float* grads, float* square_avg, float* momentum_buf, int64_t n,
+                             const float* sumsq, float max_norm, const float* lr_device, float lr, float alpha,
+                             float eps, float momentum, float* grad_norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

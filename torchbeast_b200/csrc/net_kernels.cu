@@ -1,0 +1,245 @@
+// Data-movement / pointwise kernels of the network path (see net_kernels.cuh).
+// All of these are HBM-bound byte/float shuffles: coalesced 128-bit accesses, grid-stride
+// loops sized in multiples of the SM count, no tensor cores.
+#include "net_kernels.cuh"
+
+namespace tb {
+
+static inline unsigned grid_for(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = int64_t(kNumSMsB200) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// ---------------------------------------------------------------------------------------
+// uint8 NCHW frames -> uint8 patch matrix.  One thread moves one kernel row (KW bytes).
+// ---------------------------------------------------------------------------------------
+__global__ void im2col_u8_nchw_kernel(const uint8_t* __restrict__ frame, uint8_t* __restrict__ col, int64_t N, int C,
+                                      int H, int W, int KH, int KW, int S, int OH, int OW, int aligned4) {
+  const int64_t rows_k = int64_t(C) * KH;               // kernel rows per patch
+  const int64_t total = N * OH * OW * rows_k;
+  const int64_t K = rows_k * KW;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t row = i / rows_k;
+    const int ck = int(i % rows_k);
+    const int c = ck / KH, kh = ck % KH;
+    const int64_t n = row / (OH * OW);
+    const int rem = int(row % (OH * OW));
+    const int oy = rem / OW, ox = rem % OW;
+    const uint8_t* src = frame + ((n * C + c) * H + (oy * S + kh)) * W + ox * S;
+    uint8_t* dst = col + row * K + int64_t(ck) * KW;
+    if (aligned4) {
+      // 4-byte aligned source (ox*S, W multiples of 4), 8-byte aligned destination
+      const uint32_t lo = __ldg(reinterpret_cast<const uint32_t*>(src));
+      const uint32_t hi = __ldg(reinterpret_cast<const uint32_t*>(src) + 1);
+      *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+    } else {
+      for (int kw = 0; kw < KW; ++kw) dst[kw] = __ldg(src + kw);
+    }
+  }
+}
+
+int im2col_u8_nchw(const uint8_t* frame, uint8_t* col, int64_t N, int C, int H, int W, int KH, int KW, int S,
+                   cudaStream_t stream) {
+  const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
+  const int64_t total = N * OH * OW * C * KH;
+  if (total == 0) return 0;
+  const int aligned4 = (KW == 8 && (S & 3) == 0 && (W & 3) == 0 && (reinterpret_cast<uintptr_t>(frame) & 3) == 0 &&
+                        (reinterpret_cast<uintptr_t>(col) & 7) == 0);
+  im2col_u8_nchw_kernel<<<grid_for(total, 256), 256, 0, stream>>>(frame, col, N, C, H, W, KH, KW, S, OH, OW, aligned4);
+  return check_launch("im2col_u8_nchw_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// f32 NHWC activation -> f32 patch matrix, one float4 per thread (C % 4 == 0).
+// ---------------------------------------------------------------------------------------
+__global__ void im2col_f32_nhwc_kernel(const float4* __restrict__ act, float4* __restrict__ col, int64_t N, int H,
+                                       int W, int C4, int KH, int KW, int S, int OH, int OW) {
+  const int64_t K4 = int64_t(KH) * KW * C4;
+  const int64_t total = N * OH * OW * K4;
+  const int rowlen = KW * C4;  // contiguous float4s per kernel row in the source
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t row = i / K4;
+    const int k4 = int(i % K4);
+    const int kh = k4 / rowlen, r = k4 % rowlen;
+    const int64_t n = row / (OH * OW);
+    const int rem = int(row % (OH * OW));
+    const int oy = rem / OW, ox = rem % OW;
+    col[i] = __ldg(act + ((n * H + (oy * S + kh)) * W + ox * S) * C4 + r);
+  }
+}
+
+int im2col_f32_nhwc(const float* act, float* col, int64_t N, int H, int W, int C, int KH, int KW, int S,
+                    cudaStream_t stream) {
+  TB_REQUIRE(C % 4 == 0, "im2col_f32_nhwc: C must be a multiple of 4");
+  const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
+  const int64_t total = N * OH * OW * KH * KW * (C / 4);
+  if (total == 0) return 0;
+  im2col_f32_nhwc_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(act), reinterpret_cast<float4*>(col), N, H, W, C / 4, KH, KW, S, OH, OW);
+  return check_launch("im2col_f32_nhwc_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// col2im (gather): d_act[n,iy,ix,c] = sum over (kh,kw) with oy*S+kh == iy, ox*S+kw == ix.
+// ---------------------------------------------------------------------------------------
+__global__ void col2im_f32_nhwc_kernel(const float4* __restrict__ dcol, const float4* __restrict__ act,
+                                       float4* __restrict__ dact, int64_t N, int H, int W, int C4, int KH, int KW,
+                                       int S, int OH, int OW) {
+  const int64_t total = N * H * W * C4;
+  const int64_t K4 = int64_t(KH) * KW * C4;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c4 = int(i % C4);
+    int64_t t = i / C4;
+    const int ix = int(t % W); t /= W;
+    const int iy = int(t % H);
+    const int64_t n = t / H;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kh = iy % S; kh < KH; kh += S) {
+      const int oy = (iy - kh) / S;
+      if (iy - kh < 0) break;
+      if (oy >= OH) continue;
+      for (int kw = ix % S; kw < KW; kw += S) {
+        const int ox = (ix - kw) / S;
+        if (ix - kw < 0) break;
+        if (ox >= OW) continue;
+        const float4 v = __ldg(dcol + ((n * OH + oy) * OW + ox) * K4 + (kh * KW + kw) * C4 + c4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+    }
+    if (act) {
+      const float4 a = __ldg(act + i);
+      s.x = a.x > 0.f ? s.x : 0.f; s.y = a.y > 0.f ? s.y : 0.f;
+      s.z = a.z > 0.f ? s.z : 0.f; s.w = a.w > 0.f ? s.w : 0.f;
+    }
+    dact[i] = s;
+  }
+}
+
+int col2im_f32_nhwc(const float* dcol, const float* act, float* dact, int64_t N, int H, int W, int C, int KH, int KW,
+                    int S, cudaStream_t stream) {
+  TB_REQUIRE(C % 4 == 0, "col2im_f32_nhwc: C must be a multiple of 4");
+  const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
+  const int64_t total = N * H * W * (C / 4);
+  if (total == 0) return 0;
+  col2im_f32_nhwc_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(dcol), reinterpret_cast<const float4*>(act), reinterpret_cast<float4*>(dact), N,
+      H, W, C / 4, KH, KW, S, OH, OW);
+  return check_launch("col2im_f32_nhwc_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void permute_pq_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t O, int P, int Q) {
+  const int64_t total = O * P * Q;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t o = i / (int64_t(P) * Q);
+    const int r = int(i % (int64_t(P) * Q));
+    const int p = r / Q, q = r % Q;
+    out[i] = __ldg(in + o * P * Q + int64_t(q) * P + p);
+  }
+}
+
+int permute_pq(const float* in, float* out, int64_t O, int P, int Q, cudaStream_t stream) {
+  const int64_t total = O * P * Q;
+  if (total == 0) return 0;
+  permute_pq_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, out, O, P, Q);
+  return check_launch("permute_pq_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+// column sums: block (32 x 8) covers 32 columns x a slab of rows; slabs reduced in a second pass.
+// ---------------------------------------------------------------------------------------
+constexpr int kColsumSlabs = 256;
+
+int64_t colsum_scratch_floats(int64_t ncols) { return int64_t(kColsumSlabs) * ncols; }
+
+__global__ void colsum_partial_kernel(const float* __restrict__ X, float* __restrict__ part, int64_t M, int64_t ncols,
+                                      int64_t ld, int64_t rows_per_slab) {
+  __shared__ float sm[8][33];
+  const int64_t n = int64_t(blockIdx.x) * 32 + threadIdx.x;
+  const int64_t r0 = int64_t(blockIdx.y) * rows_per_slab;
+  int64_t r1 = r0 + rows_per_slab;
+  if (r1 > M) r1 = M;
+  float s = 0.0f;
+  if (n < ncols)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += __ldg(X + r * ld + n);
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < ncols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += sm[y][threadIdx.x];
+    part[int64_t(blockIdx.y) * ncols + n] = t;
+  }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t ncols, int slabs) {
+  const int64_t n = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (n >= ncols) return;
+  float t = 0.0f;
+  for (int s = 0; s < slabs; ++s) t += part[int64_t(s) * ncols + n];
+  out[n] = t;
+}
+
+int colsum(const float* X, float* out, int64_t M, int64_t ncols, int64_t ld, float* scratch, cudaStream_t stream) {
+  if (ncols == 0) return 0;
+  TB_REQUIRE(X && out && scratch, "colsum: null pointer");
+  int slabs = kColsumSlabs;
+  if (M < slabs * 8) slabs = int((M + 7) / 8);
+  if (slabs < 1) slabs = 1;
+  const int64_t rows_per_slab = (M + slabs - 1) / slabs;
+  dim3 grid((unsigned)((ncols + 31) / 32), (unsigned)slabs);
+  colsum_partial_kernel<<<grid, dim3(32, 8), 0, stream>>>(X, scratch, M, ncols, ld, rows_per_slab);
+  int rc = check_launch("colsum_partial_kernel");
+  if (rc) return rc;
+  colsum_final_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, stream>>>(scratch, out, ncols, slabs);
+  return check_launch("colsum_final_kernel");
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void core_extras_kernel(float* __restrict__ core, int64_t ld, int64_t N, int F,
+                                   const float* __restrict__ reward, const int64_t* __restrict__ last_action, int A) {
+  const int64_t total = N * (A + 1);
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t n = i / (A + 1);
+    const int j = int(i % (A + 1));
+    float v;
+    if (j == 0) v = fminf(fmaxf(reward[n], -1.0f), 1.0f);
+    else v = (last_action[n] == int64_t(j - 1)) ? 1.0f : 0.0f;
+    core[n * ld + F + j] = v;
+  }
+}
+
+int core_extras(float* core, int64_t ld, int64_t N, int F, const float* reward, const int64_t* last_action, int A,
+                cudaStream_t stream) {
+  if (N == 0) return 0;
+  // A == 0: reward column only (polybeast Net has no last-action one-hot)
+  core_extras_kernel<<<grid_for(N * (A + 1), 256), 256, 0, stream>>>(core, ld, N, F, reward, last_action, A);
+  return check_launch("core_extras_kernel");
+}
+
+__global__ void relu_mask_kernel(float* __restrict__ X, const float* __restrict__ Y, int64_t M, int64_t ncols,
+                                 int64_t ldx, int64_t ldy) {
+  const int64_t total = M * ncols;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t m = i / ncols, n = i % ncols;
+    if (!(Y[m * ldy + n] > 0.0f)) X[m * ldx + n] = 0.0f;
+  }
+}
+
+int relu_mask_inplace(float* X, const float* Y, int64_t M, int64_t ncols, int64_t ldx, int64_t ldy,
+                      cudaStream_t stream) {
+  if (M * ncols == 0) return 0;
+  relu_mask_kernel<<<grid_for(M * ncols, 256), 256, 0, stream>>>(X, Y, M, ncols, ldx, ldy);
+  return check_launch("relu_mask_kernel");
+}
+
+}  // namespace tb

@@ -71,3 +71,68 @@ def impala_loss_fwd_bwd(
         "tb_impala_loss_fwd_bwd_f32")
     vs, pg, lr, blp, tlp = outs
     return ImpalaLoss(vs, pg, lr, blp, tlp, losses, gl, gv)
+
+
+def _all_reduce_grads(flat_grad):
+    """Batch-column data parallelism: losses are sums over (t, b), so one
+    SUM all-reduce of the flat gradient over NCCL/NVLink reproduces the single-GPU gradient;
+    every rank then clips and steps on the reduced gradient and replicas stay identical."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
+        return True
+    return False
+
+
+def optimizer_step(model, optimizer, max_grad_norm):
+    from torchbeast_b200 import optim as _optim
+
+    if isinstance(optimizer, _optim.RMSprop):
+        optimizer.step(max_grad_norm=max_grad_norm)  # fused clip + RMSprop, 2 launches
+    else:
+        # foreign optimizer object: gradients are already in .grad (views of the flat buffer)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
+        optimizer.step()
+
+
+def learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer, scheduler,
+               behavior_logits=None, actions=None, stats_sync=True):
+    """One optimisation step on a [T+1, B, ...] rollout batch (dict of CUDA tensors).
+
+    Launch sequence (no autograd graph, no host sync until the stats read-back):
+      network forward -> fused V-trace + 3 losses + their gradients (1 launch) -> network
+      backward into the flat gradient -> [NCCL all-reduce] -> fused clip + RMSprop -> actor copy.
+    """
+    out = model.learner_forward(batch, initial_agent_state)
+    blogits = batch["policy_logits"] if behavior_logits is None else behavior_logits
+    acts = batch["action"] if actions is None else actions
+    loss = impala_loss_fwd_bwd(
+        blogits[1:], out.policy_logits[:-1], acts[1:], batch["reward"][1:], batch["done"][1:],
+        out.baseline[:-1], out.baseline[-1],
+        discounting=flags.discounting, baseline_cost=flags.baseline_cost, entropy_cost=flags.entropy_cost,
+        reward_clipping=flags.reward_clipping)
+    flat_grad = model.learner_backward(loss.grad_logits, loss.grad_values)
+    _all_reduce_grads(flat_grad)
+    optimizer_step(model, optimizer, flags.grad_norm_clipping)
+    if scheduler is not None:
+        scheduler.step()
+    if actor_model is not None and actor_model is not model:
+        if hasattr(actor_model, "copy_params_from") and hasattr(model, "flat_params"):
+            actor_model.copy_params_from(model)
+        else:
+            actor_model.load_state_dict(model.state_dict())
+    if not stats_sync:
+        return dict(losses=loss.losses, vtrace=loss)
+    done = batch["done"][1:]
+    episode_returns = batch["episode_return"][1:][done.bool()]
+    host = loss.losses.cpu()  # the step's one blocking read-back
+    ep = episode_returns.cpu()
+    return {
+        "episode_returns": tuple(ep.numpy()),
+        "mean_episode_return": torch.mean(ep).item(),
+        "total_loss": host[3].item(),
+        "pg_loss": host[0].item(),
+        "baseline_loss": host[1].item(),
+        "entropy_loss": host[2].item(),
+    }

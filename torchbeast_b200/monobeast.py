@@ -11,3 +11,30 @@ from torchbeast_b200.losses import (  # noqa: F401
     compute_entropy_loss,
     compute_policy_gradient_loss,
 )
+
+import threading  # noqa: E402
+
+import torch  # noqa: E402
+
+from torchbeast_b200 import learner as _learner  # noqa: E402
+from torchbeast_b200.nets import AtariNet  # noqa: E402,F401
+
+Net = AtariNet
+
+
+def learn(
+    flags,
+    actor_model,
+    model,
+    batch,
+    initial_agent_state,
+    optimizer,
+    scheduler,
+    lock=threading.Lock(),  # noqa: B008
+):
+    """Performs a learning (optimization) step - reference monobeast.py:226-296.
+
+    Same arguments and returned stats dict.  `model` is a torchbeast_b200 network, `batch`
+    the dict of [T+1, B, ...] CUDA tensors get_batch() produces (monobeast.py:194-223)."""
+    with lock:
+        return _learner.learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer, scheduler)

@@ -1,0 +1,293 @@
+"""Network modules whose forward/backward are the hand-written sm_100a kernels.
+
+`AtariNet` keeps the reference's constructor, `initial_state`, `forward` contract and
+state_dict keys/shapes (/root/reference/torchbeast/monobeast.py:545-635) so
+reference checkpoints load, but its parameters are views into ONE flat device buffer (and its
+gradients into one flat gradient buffer): that is what the C-ABI kernels, the fused
+clip+RMSprop step and the single NCCL all-reduce operate on.
+"""
+import collections
+
+import torch
+from torch import nn
+
+from torchbeast_b200 import _lib
+
+LearnerOutputs = collections.namedtuple("LearnerOutputs", "policy_logits baseline core_state")
+
+
+class _ParamGroup(nn.Module):
+    """Namespace module so parameters get the reference's dotted names (conv1.weight, ...)."""
+
+
+def atarinet_param_spec(num_actions, use_lstm, in_channels=4):
+    core = 512 + num_actions + 1
+    spec = [
+        ("conv1.weight", (32, in_channels, 8, 8)), ("conv1.bias", (32,)),
+        ("conv2.weight", (64, 32, 4, 4)), ("conv2.bias", (64,)),
+        ("conv3.weight", (64, 64, 3, 3)), ("conv3.bias", (64,)),
+        ("fc.weight", (512, 3136)), ("fc.bias", (512,)),
+    ]
+    if use_lstm:
+        for layer in range(2):
+            spec += [
+                ("core.weight_ih_l%d" % layer, (4 * core, core)), ("core.weight_hh_l%d" % layer, (4 * core, core)),
+                ("core.bias_ih_l%d" % layer, (4 * core,)), ("core.bias_hh_l%d" % layer, (4 * core,)),
+            ]
+    spec += [
+        ("policy.weight", (num_actions, core)), ("policy.bias", (num_actions,)),
+        ("baseline.weight", (1, core)), ("baseline.bias", (1,)),
+    ]
+    return spec
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
+class FlatParamModule(nn.Module):
+    """nn.Module whose Parameters alias one flat fp32 buffer (`flat_params`) in spec order."""
+
+    def _build_flat(self, spec, device):
+        self._spec = list(spec)
+        total = sum(_numel(s) for _, s in self._spec)
+        self._flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self._flat_grad = None
+        self._views = []
+        off = 0
+        for name, shape in self._spec:
+            group, leaf = name.split(".")
+            if not hasattr(self, group):
+                setattr(self, group, _ParamGroup())
+            n = _numel(shape)
+            p = nn.Parameter(self._flat[off:off + n].view(shape))
+            getattr(self, group).register_parameter(leaf, p)
+            self._views.append((p, off, n, shape))
+            off += n
+        self._total = total
+
+    # keep the aliasing across .to()/.cuda()/.float(): move the flat buffer, re-point the views
+    def _apply(self, fn, recurse=True):
+        new_flat = fn(self._flat)
+        if new_flat.dtype != torch.float32:
+            raise _lib.TorchBeastB200Error("torchbeast_b200 networks are float32 only")
+        self._flat = new_flat.contiguous()
+        self._flat_grad = None
+        for p, off, n, shape in self._views:
+            p.data = self._flat[off:off + n].view(shape)
+            p.grad = None
+        for key, buf in list(self._buffers.items()):
+            if buf is not None:
+                self._buffers[key] = fn(buf)
+        return self
+
+    @property
+    def flat_params(self):
+        return self._flat
+
+    @property
+    def flat_grad(self):
+        """Flat gradient buffer; every Parameter's .grad is (re)pointed at its slice."""
+        if self._flat_grad is None or self._flat_grad.device != self._flat.device:
+            self._flat_grad = torch.zeros_like(self._flat)
+        return self._flat_grad
+
+    def attach_grads(self):
+        fg = self.flat_grad
+        for p, off, n, shape in self._views:
+            if p.grad is None or p.grad.data_ptr() != fg.data_ptr() + 4 * off:
+                p.grad = fg[off:off + n].view(shape)
+        return fg
+
+    def copy_params_from(self, other):
+        """actor_model.load_state_dict(model.state_dict()) as ONE device copy (monobeast.py:295)."""
+        self._flat.copy_(other._flat, non_blocking=True)
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        src = getattr(state_dict, "_tb_flat_source", None)
+        if src is not None and src._total == self._total and [s for s in src._spec] == [s for s in self._spec]:
+            self.copy_params_from(src)
+            return torch.nn.modules.module._IncompatibleKeys([], [])
+        return super().load_state_dict(state_dict, strict=strict)
+
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        if not args and not kwargs.get("prefix"):
+            sd._tb_flat_source = self  # lets a sibling FlatParamModule take the one-copy path
+        return sd
+
+    def reset_parameters_like_torch(self, seed=None):
+        """Same init distributions as the reference modules (nn.Conv2d / nn.Linear / nn.LSTM
+        defaults: U(-1/sqrt(fan_in), 1/sqrt(fan_in)); LSTM: U(-1/sqrt(H), 1/sqrt(H)))."""
+        gen = torch.Generator(device="cpu")
+        if seed is not None:
+            gen.manual_seed(seed)
+        else:
+            gen.manual_seed(int(torch.randint(0, 2 ** 31 - 1, (1,)).item()))
+        hidden = None
+        for name, shape in self._spec:
+            if name.startswith("core.weight_hh"):
+                hidden = shape[1]
+        with torch.no_grad():
+            for (name, shape), (p, off, n, _) in zip(self._spec, self._views):
+                if name.startswith("core."):
+                    bound = 1.0 / (hidden ** 0.5)
+                else:
+                    wshape = dict(self._spec)[name.rsplit(".", 1)[0] + ".weight"]
+                    bound = 1.0 / (_numel(wshape[1:]) ** 0.5)
+                vals = (torch.rand(n, generator=gen, dtype=torch.float32) * 2 - 1) * bound
+                self._flat[off:off + n].copy_(vals)
+
+
+class _AtariNetFunction(torch.autograd.Function):
+    """Autograd bridge for users who call model(...) and loss.backward() themselves.
+    learn() does not go through autograd (it calls learner_forward/learner_backward)."""
+
+    @staticmethod
+    def forward(ctx, module, frame, reward, notdone, last_action, h0, c0, *params):
+        logits, baseline, hN, cN = module._launch_forward(frame, reward, notdone, last_action, h0, c0)
+        ctx.module = module
+        ctx.notdone = notdone
+        ctx.shape = frame.shape[:2]
+        ctx.mark_non_differentiable(hN, cN)
+        return logits, baseline, hN, cN
+
+    @staticmethod
+    def backward(ctx, g_logits, g_baseline, _ghn, _gcn):
+        module = ctx.module
+        T1, B = ctx.shape
+        if g_logits is None:
+            g_logits = torch.zeros(T1, B, module.num_actions, device=module._flat.device)
+        if g_baseline is None:
+            g_baseline = torch.zeros(T1, B, device=module._flat.device)
+        grads = torch.empty_like(module._flat)
+        module._launch_backward(g_logits.contiguous(), g_baseline.contiguous(), ctx.notdone, grads)
+        outs = tuple(grads[off:off + n].view(shape) for _, off, n, shape in module._views)
+        return (None,) * 7 + outs
+
+
+class AtariNet(FlatParamModule):
+    """CUDA AtariNet (reference monobeast.py:545-635).  conv 8/4 -> 4/2 -> 3/1 -> fc 512 ->
+    cat[reward, one-hot last action] -> optional 2-layer LSTM(519) -> policy / baseline heads."""
+
+    def __init__(self, observation_shape, num_actions, use_lstm=False, device=None):
+        super().__init__()
+        if tuple(observation_shape) != (4, 84, 84):
+            raise _lib.TorchBeastB200Error(
+                "torchbeast_b200.AtariNet is specialised for (4, 84, 84) uint8 frames, got %r" % (tuple(observation_shape),))
+        self.observation_shape = tuple(observation_shape)
+        self.num_actions = num_actions
+        self.use_lstm = use_lstm
+        self.core_size = 512 + num_actions + 1
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self._build_flat(atarinet_param_spec(num_actions, use_lstm), device)
+        self.reset_parameters_like_torch()
+        if use_lstm:
+            self.core.num_layers = 2
+            self.core.hidden_size = self.core_size
+            self.core.input_size = self.core_size
+        self._ws = None
+        self._ws_key = None
+        count = _lib.lib().tb_atarinet_param_count(num_actions, int(use_lstm))
+        assert count == self._total, "parameter layout disagrees with the C-ABI (%d vs %d)" % (count, self._total)
+
+    def initial_state(self, batch_size):
+        if not self.use_lstm:
+            return tuple()
+        return tuple(torch.zeros(2, batch_size, self.core_size, device=self._flat.device) for _ in range(2))
+
+    # ---- raw launches ---------------------------------------------------------------------
+    def _workspace(self, T1, B):
+        key = (T1, B, self._flat.device)
+        if self._ws_key != key:
+            nbytes = _lib.lib().tb_atarinet_workspace_bytes(T1, B, self.num_actions, int(self.use_lstm))
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self._flat.device)
+            self._ws_key = key
+        return self._ws
+
+    def _launch_forward(self, frame, reward, notdone, last_action, h0, c0):
+        _lib.require_cuda(frame, reward, last_action, self._flat)
+        T1, B = frame.shape[:2]
+        if frame.dtype != torch.uint8 or tuple(frame.shape[2:]) != self.observation_shape:
+            raise _lib.TorchBeastB200Error("frame must be uint8 [T,B,4,84,84], got %s %r" % (frame.dtype, tuple(frame.shape)))
+        dev = self._flat.device
+        frame = frame.contiguous()
+        reward = reward.to(torch.float32).contiguous()
+        last_action = last_action.to(torch.int64).contiguous()
+        logits = torch.empty(T1, B, self.num_actions, dtype=torch.float32, device=dev)
+        baseline = torch.empty(T1, B, dtype=torch.float32, device=dev)
+        if self.use_lstm:
+            hN = torch.empty(2, B, self.core_size, dtype=torch.float32, device=dev)
+            cN = torch.empty_like(hN)
+            h0 = h0.to(torch.float32).contiguous(); c0 = c0.to(torch.float32).contiguous()
+        else:
+            hN = cN = torch.empty(0, device=dev)
+            h0 = c0 = notdone = None
+        ws = self._workspace(T1, B)
+        p = _lib.ptr
+        _lib.check(
+            _lib.lib().tb_atarinet_forward(
+                p(frame), p(reward), p(notdone), p(last_action), p(h0), p(c0), p(self._flat), T1, B,
+                self.num_actions, int(self.use_lstm), p(ws), p(logits), p(baseline),
+                p(hN) if self.use_lstm else None, p(cN) if self.use_lstm else None, _lib.stream_ptr()),
+            "tb_atarinet_forward")
+        return logits, baseline, hN, cN
+
+    def _launch_backward(self, g_logits, g_baseline, notdone, grads_out):
+        T1, B = g_baseline.shape
+        ws = self._workspace(T1, B)
+        p = _lib.ptr
+        _lib.check(
+            _lib.lib().tb_atarinet_backward(
+                p(g_logits), p(g_baseline), p(notdone) if self.use_lstm else None, p(self._flat), T1, B,
+                self.num_actions, int(self.use_lstm), p(ws), p(grads_out), _lib.stream_ptr()),
+            "tb_atarinet_backward")
+
+    @staticmethod
+    def _notdone(done):
+        # `(~done).float()`: logical for bool, bitwise for uint8 - exactly the reference's expression
+        return (~done).float().contiguous()
+
+    # ---- learner fast path (no autograd graph) ----------------------------------------------
+    @torch.no_grad()
+    def learner_forward(self, inputs, core_state=()):
+        notdone = self._notdone(inputs["done"]) if self.use_lstm else None
+        h0, c0 = core_state if self.use_lstm else (None, None)
+        logits, baseline, hN, cN = self._launch_forward(
+            inputs["frame"], inputs["reward"], notdone, inputs["last_action"], h0, c0)
+        self._saved_notdone = notdone
+        return LearnerOutputs(logits, baseline, (hN, cN) if self.use_lstm else tuple())
+
+    @torch.no_grad()
+    def learner_backward(self, grad_logits, grad_baseline):
+        """Writes d loss / d params into flat_grad (and points every .grad at its slice)."""
+        fg = self.attach_grads()
+        self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg)
+        return fg
+
+    # ---- reference-compatible forward ---------------------------------------------------------
+    def forward(self, inputs, core_state=()):
+        frame = inputs["frame"]
+        T, B = frame.shape[:2]
+        notdone = self._notdone(inputs["done"]) if self.use_lstm else None
+        h0, c0 = core_state if self.use_lstm else (None, None)
+        params = [v[0] for v in self._views]
+        if torch.is_grad_enabled() and any(q.requires_grad for q in params):
+            logits, baseline, hN, cN = _AtariNetFunction.apply(
+                self, frame, inputs["reward"], notdone, inputs["last_action"], h0, c0, *params)
+        else:
+            logits, baseline, hN, cN = self._launch_forward(frame, inputs["reward"], notdone, inputs["last_action"], h0, c0)
+        flat_logits = logits.detach().view(T * B, self.num_actions)
+        if self.training:
+            action = torch.multinomial(torch.softmax(flat_logits, dim=1), num_samples=1)
+        else:
+            action = torch.argmax(flat_logits, dim=1)  # don't sample when testing
+        out = dict(policy_logits=logits, baseline=baseline, action=action.view(T, B))
+        return out, ((hN, cN) if self.use_lstm else tuple())
+
+
+Net = AtariNet

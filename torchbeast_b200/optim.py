@@ -1,0 +1,56 @@
+"""Flat-buffer RMSprop with fused global-norm clipping (two kernel launches per step).
+
+Drop-in for `torch.optim.RMSprop(model.parameters(), lr, momentum, eps, alpha)` as the
+reference builds it (/root/reference/torchbeast/monobeast.py:388-394,
+polybeast_learner.py:472-478) for a FlatParamModule: same constructor arguments,
+`param_groups[0]["lr"]` is honoured so `torch.optim.lr_scheduler.LambdaLR` works unchanged,
+`state_dict()` carries square_avg (and momentum_buffer) per parameter like torch's.
+"""
+import torch
+
+from torchbeast_b200 import _lib
+
+
+class RMSprop(torch.optim.Optimizer):
+    def __init__(self, model, lr=0.01, alpha=0.99, eps=1e-8, weight_decay=0, momentum=0, centered=False):
+        if weight_decay != 0 or centered:
+            raise _lib.TorchBeastB200Error("torchbeast_b200.optim.RMSprop: weight_decay/centered are not supported")
+        if not hasattr(model, "flat_params"):
+            raise _lib.TorchBeastB200Error("torchbeast_b200.optim.RMSprop needs a FlatParamModule (e.g. AtariNet)")
+        self.model = model
+        defaults = dict(lr=lr, alpha=alpha, eps=eps, momentum=momentum, weight_decay=0, centered=False)
+        super().__init__(list(model.parameters()), defaults)
+        flat = model.flat_params
+        self.square_avg = torch.zeros_like(flat)
+        self.momentum_buffer = torch.zeros_like(flat) if momentum != 0 else None
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=flat.device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=flat.device)
+        self._steps = 0
+        # per-parameter views so state_dict() looks like torch.optim.RMSprop's
+        for p, off, n, shape in model._views:
+            st = self.state[p]
+            st["step"] = torch.tensor(0.0)
+            st["square_avg"] = self.square_avg[off:off + n].view(shape)
+            if self.momentum_buffer is not None:
+                st["momentum_buffer"] = self.momentum_buffer[off:off + n].view(shape)
+
+    @torch.no_grad()
+    def step(self, closure=None, max_grad_norm=None):
+        """clip_grad_norm_(max_grad_norm) (skipped when None) + RMSprop on the flat buffers."""
+        if closure is not None:
+            raise _lib.TorchBeastB200Error("closure is not supported")
+        model = self.model
+        flat, grad = model.flat_params, model.attach_grads()
+        group = self.param_groups[0]
+        lib, p = _lib.lib(), _lib.ptr
+        st = _lib.stream_ptr()
+        _lib.check(lib.tb_grad_sumsq_f32(p(grad), grad.numel(), p(self._sumsq), p(_lib.workspace()), st),
+                   "tb_grad_sumsq_f32")
+        _lib.check(
+            lib.tb_clip_rmsprop_step_f32(
+                p(flat), p(grad), p(self.square_avg), p(self.momentum_buffer), flat.numel(), p(self._sumsq),
+                -1.0 if max_grad_norm is None else float(max_grad_norm), None, float(group["lr"]),
+                float(group["alpha"]), float(group["eps"]), float(group["momentum"]), p(self.grad_norm), st),
+            "tb_clip_rmsprop_step_f32")
+        self._steps += 1
+        return None
