@@ -1,0 +1,396 @@
+"""bench.py - learner frames/sec of the B200-native IMPALA learner hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full learn() step (AtariNet forward, fused V-trace + losses + their gradients,
+network backward, [NCCL all-reduce of the flat gradient], global-norm clip + RMSprop, actor-weight
+publication) on one synthetic [T+1, B, 4, 84, 84] uint8 rollout batch per GPU (BASELINE.json
+configs[1]: T=80, B=32 per GPU; weak scaling: the global batch is 32*N columns).
+
+Printed JSON (one line, rank 0):
+  value   frames/s with the rollout batches already resident in HBM (T*B*N / step time, the
+          reference's own accounting, polybeast_learner.py:372), CUDA events, max over ranks.
+  e2e     same metric through the public API (torchbeast_b200.monobeast.learn) with HOST pinned
+          buffers: every step's inputs are copied host->device and the step's stats are read back
+          inside the timed region.
+  roofline / roofline_ops / vtrace / cpu_baseline / clocks / gpu_launches: see DESIGN.md section 5.
+`--impl reference` times the CPU restatement of the reference's learner step (oracle/, kind
+"port") on the host cores: the reference itself is PyTorch-on-CPU code that cannot travel to the box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--T", type=int, default=80)
+    ap.add_argument("--B", type=int, default=32, help="batch columns per GPU")
+    ap.add_argument("--use_lstm", type=int, default=1)
+    ap.add_argument("--num_actions", type=int, default=6)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_profile", action="store_true")
+    return ap.parse_args()
+
+
+def flags_ns(T, B):
+    return types.SimpleNamespace(
+        reward_clipping="abs_one", discounting=0.99, baseline_cost=0.5, entropy_cost=0.0006,
+        grad_norm_clipping=40.0, unroll_length=T, batch_size=B)
+
+
+def synthetic_host_batch(T, B, A, seed, pin):
+    """SURVEY.md 8(d) M2 synthetic rollout (numpy RandomState), host tensors (pinned if asked)."""
+    rs = np.random.RandomState(seed)
+    b = dict(
+        frame=torch.from_numpy(rs.randint(0, 256, size=(T + 1, B, 4, 84, 84), dtype=np.uint8)),
+        reward=torch.from_numpy(rs.randn(T + 1, B).astype(np.float32)),
+        done=torch.from_numpy(rs.rand(T + 1, B) < 0.01),
+        episode_return=torch.from_numpy(rs.randn(T + 1, B).astype(np.float32)),
+        policy_logits=torch.from_numpy(rs.randn(T + 1, B, A).astype(np.float32)),
+        action=torch.from_numpy(rs.randint(0, A, size=(T + 1, B)).astype(np.int64)),
+        last_action=torch.from_numpy(rs.randint(0, A, size=(T + 1, B)).astype(np.int64)),
+    )
+    if pin:
+        b = {k: v.pin_memory() for k, v in b.items()}
+    return b
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while a timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return None
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=p["hbm_gbs"], tensor=p["bf16_tflops_sustained"], tensor_burst=p["bf16_tflops"], source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, source="fallback")
+
+
+def gemm_flops_table(N, A, use_lstm):
+    """2*M*N*K of every tagged GEMM op per step (N = (T+1)*B frames) - DESIGN.md section 4."""
+    M1, M2, M3 = N * 400, N * 81, N * 49
+    core = 512 + 1 + A
+    t = {
+        "conv1_fwd": 2 * M1 * 32 * 256, "conv2_fwd": 2 * M2 * 64 * 512, "conv3_fwd": 2 * M3 * 64 * 576,
+        "fc_fwd": 2 * N * 512 * 3136, "heads_fwd": 2 * N * (A + 1) * core,
+        "conv1_wgrad": 2 * M1 * 32 * 256, "conv2_wgrad": 2 * M2 * 64 * 512, "conv3_wgrad": 2 * M3 * 64 * 576,
+        "fc_wgrad": 2 * N * 512 * 3136, "heads_wgrad": 2 * N * (A + 1) * core,
+        "conv2_dgrad": 2 * M2 * 64 * 512, "conv3_dgrad": 2 * M3 * 64 * 576, "fc_dgrad": 2 * N * 512 * 3136,
+        "heads_dgrad": 2 * N * (A + 1) * core,
+    }
+    if use_lstm:
+        H = core
+        t.update({
+            "lstm_xproj_fwd": 2 * 2 * N * 4 * H * H, "lstm_recurrence_fwd": 2 * 2 * N * 4 * H * H,
+            "lstm_recurrence_bwd": 2 * 2 * N * 4 * H * H, "lstm_wgrad": 2 * 2 * 2 * N * 4 * H * H,
+            "lstm_xproj_dgrad": 2 * 2 * N * 4 * H * H,
+        })
+    return t
+
+
+def hbm_bytes_table(N, T, B, A, use_lstm, nparams):
+    """Algorithmic bytes of the bandwidth-bound ops per step."""
+    M1, M2, M3 = N * 400, N * 81, N * 49
+    return {
+        "im2col_u8": N * 28224 + M1 * 256,                       # read frames once, write the patch matrix
+        "im2col_f32": 4 * (M1 * 32 + M2 * 512) + 4 * (M2 * 64 + M3 * 576),
+        "col2im": 4 * (M3 * 576 + 2 * M2 * 64) + 4 * (M2 * 512 + 2 * M1 * 32),
+        "impala_loss_fwd_bwd": (12 * A + 32 + 12 - 3) * T * B + 4 * B + 16,
+        "clip_rmsprop": 4 * nparams * 5, "grad_sumsq": 4 * nparams,
+    }
+
+
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's learn step on the host cores."""
+    from oracle import learner_torch as LT
+    T, B, A = args.T, args.B, args.num_actions
+    torch.set_num_threads(os.cpu_count() or 1)
+    shapes = LT.atarinet_param_shapes(A, bool(args.use_lstm))
+    p = LT.random_params(shapes, seed=0)
+    batch = synthetic_host_batch(T, B, A, seed=1, pin=False)
+    state = tuple(torch.zeros(2, B, 512 + A + 1) for _ in range(2)) if args.use_lstm else ()
+    sq = None
+    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    for _ in range(warm):
+        o = LT.learner_step(p, batch, state, net="atari", square_avg=sq, num_actions=A)
+        p, sq = o["params"], o["square_avg"]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o = LT.learner_step(p, batch, state, net="atari", square_avg=sq, num_actions=A)
+        p, sq = o["params"], o["square_avg"]
+    dt = (time.perf_counter() - t0) / steps
+    return dict(value=T * B / dt, ms_per_step=dt * 1e3, steps=steps, warmup=warm, cores=torch.get_num_threads())
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    T, B, A = args.T, args.B, args.num_actions
+    workload = "AtariNet(84x84x4 u8)%s + V-trace learner step, T=%d B=%d per GPU, synthetic frames" % (
+        "+LSTM(2x519)" if args.use_lstm else "", T, B)
+    config = dict(workload=workload, T=T, B_per_gpu=B, global_batch=B * max(world, 1), num_actions=A,
+                  use_lstm=bool(args.use_lstm), parallelism="dp%d over batch columns, one NCCL all-reduce of the flat gradient" % world)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_reference(args)
+        line = dict(
+            impl="reference", metric="learner_frames_per_sec", value=r["value"], unit="frames/s", n_gpus=args.gpus,
+            steps=r["steps"], warmup=r["warmup"], ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak",
+            vs_baseline=None, dtype="f32", data="synthetic", config=config,
+            cpu_baseline=dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port",
+                              sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py on CPU" % (r["steps"], T, B)),
+            e2e=dict(value=r["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from torchbeast_b200 import _lib, learner, monobeast, optim
+
+    dev = torch.device("cuda", local_rank)
+    model = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm))
+    actor = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm))
+    model.reset_parameters_like_torch(seed=0)  # identical replicas on every rank
+    actor.copy_params_from(model)
+    opt = optim.RMSprop(model, lr=0.00048, momentum=0, eps=0.01, alpha=0.99)
+    total_steps = 30_000_000
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 1 - min(e * T * B * world, total_steps) / total_steps)
+    flags = flags_ns(T, B)
+    state = model.initial_state(B)
+    NROT = 4  # distinct input batches: 4 x 73 MB > 126 MB L2
+    host = [synthetic_host_batch(T, B, A, seed=1000 * rank + i, pin=True) for i in range(NROT)]
+    devb = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    lib = _lib.lib()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident throughput ----------------------------------------------------
+    for i in range(args.warmup):
+        learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = lib.tb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        out = learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
+    e1.record()
+    barrier()
+    launches = lib.tb_launch_count() - launches0
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    final_loss = float(out["losses"][3])
+    assert np.isfinite(final_loss), "non-finite loss"
+
+    # ---- end to end: pinned host buffers -> H2D -> learn() -> stats D2H, every step ------
+    copy_stream = torch.cuda.Stream()
+    slots = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def stage(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            for k, v in host[i % NROT].items():
+                slots[s][k].copy_(v, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    for s in range(2):
+        freed[s].record()
+    barrier()
+    e2e_steps = args.steps
+    t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_e0.record()
+    stage(0)
+    stats = None
+    for i in range(e2e_steps):
+        if i + 1 < e2e_steps:
+            stage(i + 1)  # prefetch the next rollout while this one trains
+        s = i % 2
+        torch.cuda.current_stream().wait_event(ready[s])
+        stats = monobeast.learn(flags, actor, model, slots[s], state, opt, sched)  # includes the stats read-back
+        freed[s].record()
+    t_e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t_e0.elapsed_time(t_e1)) / e2e_steps
+    d2h_bytes = 4 * 4 + int(sum(1 for _ in stats["episode_returns"])) * 4
+
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    frames = T * B * world
+    line = dict(
+        metric="learner_frames_per_sec", value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=args.steps,
+        warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+        data="synthetic", config=dict(config, l2="4 rotating input batches per rank (%.0f MB) > 126 MB L2; ~2.3 GB of "
+                                      "activations written per step" % (NROT * h2d_bytes / 1e6)),
+        e2e=dict(value=frames / (e2e_ms * 1e-3), unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes,
+                 d2h_bytes_per_step=d2h_bytes, note="pinned host rollout -> async H2D (double-buffered, overlapped with "
+                 "the previous step) -> monobeast.learn -> stats read-back, all inside the timed region"),
+        gpu_launches=int(launches), clocks=clocks, final_total_loss=final_loss,
+    )
+
+    # ---- per-op device timing (separate steps; CUDA events around every op on its stream) ---
+    if not args.no_profile:
+        lib.tb_profile_enable(1)
+        PSTEPS = 3
+        for i in range(PSTEPS):
+            learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
+        recs = _lib.profile_collect()
+        lib.tb_profile_enable(0)
+        agg = {}
+        for name, t in recs:
+            a = agg.setdefault(name, [0.0, 0])
+            a[0] += t; a[1] += 1
+        N = (T + 1) * B
+        flops = gemm_flops_table(N, A, args.use_lstm)
+        nbytes = hbm_bytes_table(N, T, B, A, args.use_lstm, model.flat_params.numel())
+        ops = []
+        for name, (tot, cnt) in agg.items():
+            per_step = tot / PSTEPS
+            o = dict(op=name, ms_per_step=per_step, launches_per_step=cnt / PSTEPS)
+            if name in flops:
+                o.update(bound="tensor", achieved=flops[name] / (per_step * 1e-3) / 1e12, peak=pk["tensor"], unit="TFLOP/s")
+            elif name in nbytes:
+                o.update(bound="hbm", achieved=nbytes[name] / (per_step * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s")
+            if "achieved" in o:
+                o["frac"] = o["achieved"] / o["peak"]
+            ops.append(o)
+        ops.sort(key=lambda o: -o["ms_per_step"])
+        prof_total = sum(o["ms_per_step"] for o in ops)
+        line["roofline_ops"] = [dict(o, share=o["ms_per_step"] / prof_total) for o in ops[:12]]
+        dom = next((o for o in ops if "achieved" in o), None)
+        if dom is not None:
+            line["roofline"] = dict(kernel=dom["op"], bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"],
+                                    unit=dom["unit"], frac=dom["frac"], traffic=None, peak_source=pk["source"],
+                                    note="fp32 SIMT GEMM backend measured against the bf16 tensor-core peak")
+        # the V-trace kernels on their own (BASELINE.json metric: V-trace GB/s vs HBM peak)
+        line["vtrace"] = vtrace_numbers(pk, T, B, A)
+
+    if not args.no_cpu_baseline and world == 1:
+        r = run_reference(types.SimpleNamespace(**dict(vars(args), steps=3, warmup=1)))
+        line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port",
+                                    sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py" % (r["steps"], T, B))
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def vtrace_numbers(pk, T, B, A):
+    """Scan-only and fused-loss kernels: achieved algorithmic GB/s at the bench size (launch-latency
+    bound) and on a wide batch (HBM bound).  20 back-to-back launches per event pair."""
+    from torchbeast_b200 import _lib
+    lib, p, st = _lib.lib(), _lib.ptr, _lib.stream_ptr()
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(0)
+    flush = torch.zeros(64 * 1024 * 1024, device="cuda")
+    for tag, (t, b) in (("bench_size", (T, B)), ("wide", (T, 1 << 20))):
+        lr = 0.5 * torch.randn(t, b, device="cuda", generator=g)
+        dc = 0.99 * (torch.rand(t, b, device="cuda", generator=g) > 0.01).float()
+        rw = torch.randn(t, b, device="cuda", generator=g).clamp(-1, 1)
+        va = torch.randn(t, b, device="cuda", generator=g); bs = torch.randn(b, device="cuda", generator=g)
+        vs = torch.empty_like(va); pg = torch.empty_like(va)
+        reps = 20 if tag == "bench_size" else 3
+        times = []
+        for it in range(6):
+            if tag == "wide":
+                flush.add_(1)
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                lib.tb_vtrace_from_importance_weights_f32(p(lr), p(dc), p(rw), p(va), p(bs), t, b, 1.0, 1.0, p(vs), p(pg), st)
+            z.record(); torch.cuda.synchronize()
+            times.append(a.elapsed_time(z) / reps)
+        us = sorted(times[1:])[len(times[1:]) // 2] * 1e3
+        nbytes = 24 * t * b + 4 * b
+        out[tag] = dict(T=t, B=b, us=us, bytes=nbytes, gbs=nbytes / us / 1e3, frac=nbytes / us / 1e3 / pk["hbm"], peak=pk["hbm"])
+        del lr, dc, rw, va, vs, pg
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,14 @@ const char* tb_last_error(void);
 int tb_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 /* Bytes of zero-initialised scratch the reducing kernels need (counter + per-CTA partials). */
 size_t tb_workspace_bytes(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t tb_launch_count(void);
+/* Optional per-op device timing: tb_profile_enable(1) clears and starts recording a CUDA event pair
+ * around every op (GEMM, im2col, scan, ...) on its stream; tb_profile_collect synchronises the
+ * device and returns the number of records, writing newline-separated op names to names_host and
+ * the elapsed milliseconds to ms_host.  Off by default.                                      */
+int tb_profile_enable(int on);
+int tb_profile_collect(char* names_host, size_t names_cap, float* ms_host, int max_records);
 
 /* ---- V-trace ----------------------------------------------------------------------- */
 

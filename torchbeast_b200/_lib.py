@@ -20,6 +20,9 @@ _SIGNATURES = {
     "tb_last_error": ([], _c.c_char_p),
     "tb_device_info": ([_vp, _vp, _vp], _int),
     "tb_workspace_bytes": ([], _c.c_size_t),
+    "tb_launch_count": ([], _c.c_uint64),
+    "tb_profile_enable": ([_int], _int),
+    "tb_profile_collect": ([_c.c_char_p, _c.c_size_t, _vp, _int], _int),
     "tb_action_log_probs_f32": ([_vp, _vp, _i64, _i64, _vp, _vp], _int),
     "tb_action_log_probs_f64": ([_vp, _vp, _i64, _i64, _vp, _vp], _int),
     "tb_vtrace_from_importance_weights_f32": ([_vp] * 5 + [_i64, _i64, _f32, _f32, _vp, _vp, _vp], _int),
@@ -109,3 +112,14 @@ def workspace():
 
 def clip_arg(c):
     return -1.0 if c is None else float(c)
+
+
+def profile_collect(max_records=65536):
+    """Return [(op_name, milliseconds), ...] recorded since tb_profile_enable(1)."""
+    names = ctypes.create_string_buffer(max_records * 48)
+    ms = (ctypes.c_float * max_records)()
+    n = lib().tb_profile_collect(names, len(names), ctypes.cast(ms, ctypes.c_void_p), max_records)
+    if n < 0:
+        raise TorchBeastB200Error("tb_profile_collect failed: %s" % lib().tb_last_error().decode())
+    nm = names.value.decode().split("\n")[:n]
+    return list(zip(nm, [ms[i] for i in range(n)]))

@@ -147,21 +147,21 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
   TB_TRY(permute_pq(P + pp.fc_w, w.wfcp, G::FC_OUT, G::H3 * G::W3, G::C3, st));
   // conv1 (uint8 patch matrix; x/255 applied when the operand is read)
   TB_TRY(im2col_u8_nchw(frame, w.col1, N, G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, st));
-  ep = GemmEpilogue(); ep.bias = P + pp.conv1_b; ep.relu = 1;
+  ep = GemmEpilogue(); ep.bias = P + pp.conv1_b; ep.relu = 1; ep.tag = "conv1_fwd";
   TB_TRY((gemm_simt<uint8_t, float, false, true>(w.col1, P + pp.conv1_w, w.act1, M1, G::C1, G::KD1, G::KD1, G::KD1,
                                                   G::C1, ep, 1, nullptr, st)));
   // conv2
   TB_TRY(im2col_f32_nhwc(w.act1, w.col2, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
-  ep = GemmEpilogue(); ep.bias = P + pp.conv2_b; ep.relu = 1;
+  ep = GemmEpilogue(); ep.bias = P + pp.conv2_b; ep.relu = 1; ep.tag = "conv2_fwd";
   TB_TRY((gemm_simt<float, float, false, true>(w.col2, w.w2p, w.act2, M2, G::C2, G::KD2, G::KD2, G::KD2, G::C2, ep, 1,
                                                 nullptr, st)));
   // conv3
   TB_TRY(im2col_f32_nhwc(w.act2, w.col3, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
-  ep = GemmEpilogue(); ep.bias = P + pp.conv3_b; ep.relu = 1;
+  ep = GemmEpilogue(); ep.bias = P + pp.conv3_b; ep.relu = 1; ep.tag = "conv3_fwd";
   TB_TRY((gemm_simt<float, float, false, true>(w.col3, w.w3p, w.act3, M3, G::C3, G::KD3, G::KD3, G::KD3, G::C3, ep, 1,
                                                 nullptr, st)));
   // fc -> first 512 columns of the core input; then reward / one-hot columns
-  ep = GemmEpilogue(); ep.bias = P + pp.fc_b; ep.relu = 1;
+  ep = GemmEpilogue(); ep.bias = P + pp.fc_b; ep.relu = 1; ep.tag = "fc_fwd";
   TB_TRY((gemm_simt<float, float, false, true>(w.act3, w.wfcp, w.core_in, N, G::FC_OUT, G::FC_IN, G::FC_IN, G::FC_IN,
                                                 pp.core, ep, 1, nullptr, st)));
   TB_TRY(core_extras(w.core_in, pp.core, N, G::FC_OUT, reward, last_action, A, st));
@@ -175,10 +175,10 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
                         w.splitk, st));
   }
   // heads
-  ep = GemmEpilogue(); ep.bias = P + pp.policy_b;
+  ep = GemmEpilogue(); ep.bias = P + pp.policy_b; ep.tag = "heads_fwd";
   TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.policy_w, policy_logits, N, A, pp.core, pp.core,
                                                 pp.core, A, ep, 1, nullptr, st)));
-  ep = GemmEpilogue(); ep.bias = P + pp.baseline_b;
+  ep = GemmEpilogue(); ep.bias = P + pp.baseline_b; ep.tag = "heads_fwd";
   TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.baseline_w, baseline, N, 1, pp.core, pp.core,
                                                 pp.core, 1, ep, 1, nullptr, st)));
   return 0;
@@ -188,10 +188,10 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
 // backward: consumes the activations the forward left in the workspace
 // ---------------------------------------------------------------------------------------
 static int wgrad(const float* dY, int64_t ldy, const void* X, bool x_is_u8, int64_t ldx, float* dW, int64_t rows,
-                 int64_t nout, int64_t kin, int permP, int permQ, AtariWs& w, cudaStream_t st) {
+                 int64_t nout, int64_t kin, int permP, int permQ, AtariWs& w, cudaStream_t st, const char* tag) {
   // dW[nout, kin] = dY[rows, nout]^T . X[rows, kin]
   GemmEpilogue ep;
-  ep.permP = permP; ep.permQ = permQ;
+  ep.permP = permP; ep.permQ = permQ; ep.tag = tag;
   const int splits = pick_splits(nout, kin, rows);
   if (x_is_u8)
     return gemm_simt<float, uint8_t, true, false>(dY, static_cast<const uint8_t*>(X), dW, nout, kin, rows, ldy, ldx,
@@ -210,14 +210,14 @@ static int atarinet_backward(const float* grad_logits, const float* grad_baselin
   const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
   GemmEpilogue ep;
   // heads: dcore_out = dlogits . Wp + dbaseline . Wb ; dWp, dbp, dWb, dbb
-  ep = GemmEpilogue();
+  ep = GemmEpilogue(); ep.tag = "heads_dgrad";
   TB_TRY((gemm_simt<float, float, false, false>(grad_logits, P + pp.policy_w, w.dcore_out, N, pp.core, A, A, pp.core,
                                                  pp.core, ep, 1, nullptr, st)));
   ep.accumulate = 1;
   TB_TRY((gemm_simt<float, float, false, false>(grad_baseline, P + pp.baseline_w, w.dcore_out, N, pp.core, 1, 1,
                                                  pp.core, pp.core, ep, 1, nullptr, st)));
-  TB_TRY(wgrad(grad_logits, A, w.core_out, false, pp.core, G_ + pp.policy_w, N, A, pp.core, 1, 1, w, st));
-  TB_TRY(wgrad(grad_baseline, 1, w.core_out, false, pp.core, G_ + pp.baseline_w, N, 1, pp.core, 1, 1, w, st));
+  TB_TRY(wgrad(grad_logits, A, w.core_out, false, pp.core, G_ + pp.policy_w, N, A, pp.core, 1, 1, w, st, "heads_wgrad"));
+  TB_TRY(wgrad(grad_baseline, 1, w.core_out, false, pp.core, G_ + pp.baseline_w, N, 1, pp.core, 1, 1, w, st, "heads_wgrad"));
   TB_TRY(colsum(grad_logits, G_ + pp.policy_b, N, A, A, w.colsum_scratch, st));
   TB_TRY(colsum(grad_baseline, G_ + pp.baseline_b, N, 1, 1, w.colsum_scratch, st));
   if (use_lstm) {
@@ -234,26 +234,27 @@ static int atarinet_backward(const float* grad_logits, const float* grad_baselin
   // fc: ReLU mask on the first 512 columns, wgrad (un-packed into [o, c, (h,w)]), bias, dgrad (+ReLU mask of act3)
   TB_TRY(relu_mask_inplace(w.dcore_in, w.core_in, N, G::FC_OUT, pp.core, pp.core, st));
   TB_TRY(wgrad(w.dcore_in, pp.core, w.act3, false, G::FC_IN, G_ + pp.fc_w, N, G::FC_OUT, G::FC_IN, G::H3 * G::W3,
-               G::C3, w, st));
+               G::C3, w, st, "fc_wgrad"));
   TB_TRY(colsum(w.dcore_in, G_ + pp.fc_b, N, G::FC_OUT, pp.core, w.colsum_scratch, st));
-  ep = GemmEpilogue(); ep.mask = w.act3; ep.ldmask = G::FC_IN;
+  ep = GemmEpilogue(); ep.mask = w.act3; ep.ldmask = G::FC_IN; ep.tag = "fc_dgrad";
   TB_TRY((gemm_simt<float, float, false, false>(w.dcore_in, w.wfcp, w.dact3, N, G::FC_IN, G::FC_OUT, pp.core,
                                                  G::FC_IN, G::FC_IN, ep, 1, nullptr, st)));
   // conv3: dact3 viewed as [M3, 64]
-  TB_TRY(wgrad(w.dact3, G::C3, w.col3, false, G::KD3, G_ + pp.conv3_w, M3, G::C3, G::KD3, G::K3 * G::K3, G::C2, w, st));
+  TB_TRY(wgrad(w.dact3, G::C3, w.col3, false, G::KD3, G_ + pp.conv3_w, M3, G::C3, G::KD3, G::K3 * G::K3, G::C2, w, st, "conv3_wgrad"));
   TB_TRY(colsum(w.dact3, G_ + pp.conv3_b, M3, G::C3, G::C3, w.colsum_scratch, st));
-  ep = GemmEpilogue();
+  ep = GemmEpilogue(); ep.tag = "conv3_dgrad";
   TB_TRY((gemm_simt<float, float, false, false>(w.dact3, w.w3p, w.dcol3, M3, G::KD3, G::C3, G::C3, G::KD3, G::KD3, ep,
                                                  1, nullptr, st)));
   TB_TRY(col2im_f32_nhwc(w.dcol3, w.act2, w.dact2, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
   // conv2
-  TB_TRY(wgrad(w.dact2, G::C2, w.col2, false, G::KD2, G_ + pp.conv2_w, M2, G::C2, G::KD2, G::K2 * G::K2, G::C1, w, st));
+  TB_TRY(wgrad(w.dact2, G::C2, w.col2, false, G::KD2, G_ + pp.conv2_w, M2, G::C2, G::KD2, G::K2 * G::K2, G::C1, w, st, "conv2_wgrad"));
   TB_TRY(colsum(w.dact2, G_ + pp.conv2_b, M2, G::C2, G::C2, w.colsum_scratch, st));
+  ep.tag = "conv2_dgrad";
   TB_TRY((gemm_simt<float, float, false, false>(w.dact2, w.w2p, w.dcol2, M2, G::KD2, G::C2, G::C2, G::KD2, G::KD2, ep,
                                                  1, nullptr, st)));
   TB_TRY(col2im_f32_nhwc(w.dcol2, w.act1, w.dact1, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
   // conv1 (no input gradient needed)
-  TB_TRY(wgrad(w.dact1, G::C1, w.col1, true, G::KD1, G_ + pp.conv1_w, M1, G::C1, G::KD1, 1, 1, w, st));
+  TB_TRY(wgrad(w.dact1, G::C1, w.col1, true, G::KD1, G_ + pp.conv1_w, M1, G::C1, G::KD1, 1, 1, w, st, "conv1_wgrad"));
   TB_TRY(colsum(w.dact1, G_ + pp.conv1_b, M1, G::C1, G::C1, w.colsum_scratch, st));
   return 0;
 }

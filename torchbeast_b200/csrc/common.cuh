@@ -10,7 +10,16 @@ namespace tb {
 
 // ---- error plumbing (thread-local, see header conventions) --------------------------
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);
+int check_launch(const char* what);  // cudaGetLastError + launch counter
+
+// Optional per-op device timing (tb_profile_*): when enabled, every ProfScope records a CUDA
+// event pair on the op's stream; off by default (zero overhead beyond one branch).
+struct ProfScope {
+  ProfScope(const char* name, cudaStream_t stream);
+  ~ProfScope();
+  int slot;
+  cudaStream_t stream;
+};
 
 #define TB_REQUIRE(cond, ...)      \
   do {                             \

@@ -40,6 +40,7 @@ int gemm_simt(const AT* A, const BT* B, float* C, int64_t M, int64_t N, int64_t 
   if (splits > ktiles) splits = int(ktiles > 0 ? ktiles : 1);
   const bool via_scratch = splits > 1 || ep.permP > 1 || ep.permQ > 1;
   TB_REQUIRE(!via_scratch || splitk_scratch, "gemm: split-K / permuted output needs scratch");
+  ProfScope prof(ep.tag, stream);
   GemmArgs g;
   g.A = A; g.B = B; g.C = C; g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldb = ldb; g.ldc = ldc;
   g.partial = via_scratch ? splitk_scratch : nullptr; g.splits = splits; g.ep = ep;

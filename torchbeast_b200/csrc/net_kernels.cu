@@ -44,6 +44,7 @@ __global__ void im2col_u8_nchw_kernel(const uint8_t* __restrict__ frame, uint8_t
 
 int im2col_u8_nchw(const uint8_t* frame, uint8_t* col, int64_t N, int C, int H, int W, int KH, int KW, int S,
                    cudaStream_t stream) {
+  ProfScope prof("im2col_u8", stream);
   const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
   const int64_t total = N * OH * OW * C * KH;
   if (total == 0) return 0;
@@ -75,6 +76,7 @@ __global__ void im2col_f32_nhwc_kernel(const float4* __restrict__ act, float4* _
 
 int im2col_f32_nhwc(const float* act, float* col, int64_t N, int H, int W, int C, int KH, int KW, int S,
                     cudaStream_t stream) {
+  ProfScope prof("im2col_f32", stream);
   TB_REQUIRE(C % 4 == 0, "im2col_f32_nhwc: C must be a multiple of 4");
   const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
   const int64_t total = N * OH * OW * KH * KW * (C / 4);
@@ -123,6 +125,7 @@ __global__ void col2im_f32_nhwc_kernel(const float4* __restrict__ dcol, const fl
 
 int col2im_f32_nhwc(const float* dcol, const float* act, float* dact, int64_t N, int H, int W, int C, int KH, int KW,
                     int S, cudaStream_t stream) {
+  ProfScope prof("col2im", stream);
   TB_REQUIRE(C % 4 == 0, "col2im_f32_nhwc: C must be a multiple of 4");
   const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
   const int64_t total = N * H * W * (C / 4);
@@ -146,6 +149,7 @@ __global__ void permute_pq_kernel(const float* __restrict__ in, float* __restric
 }
 
 int permute_pq(const float* in, float* out, int64_t O, int P, int Q, cudaStream_t stream) {
+  ProfScope prof("weight_pack", stream);
   const int64_t total = O * P * Q;
   if (total == 0) return 0;
   permute_pq_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, out, O, P, Q);
@@ -188,6 +192,7 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* __res
 }
 
 int colsum(const float* X, float* out, int64_t M, int64_t ncols, int64_t ld, float* scratch, cudaStream_t stream) {
+  ProfScope prof("bias_grad_colsum", stream);
   if (ncols == 0) return 0;
   TB_REQUIRE(X && out && scratch, "colsum: null pointer");
   int slabs = kColsumSlabs;
@@ -219,6 +224,7 @@ __global__ void core_extras_kernel(float* __restrict__ core, int64_t ld, int64_t
 
 int core_extras(float* core, int64_t ld, int64_t N, int F, const float* reward, const int64_t* last_action, int A,
                 cudaStream_t stream) {
+  ProfScope prof("core_extras", stream);
   if (N == 0) return 0;
   // A == 0: reward column only (polybeast Net has no last-action one-hot)
   core_extras_kernel<<<grid_for(N * (A + 1), 256), 256, 0, stream>>>(core, ld, N, F, reward, last_action, A);
@@ -237,6 +243,7 @@ __global__ void relu_mask_kernel(float* __restrict__ X, const float* __restrict_
 
 int relu_mask_inplace(float* X, const float* Y, int64_t M, int64_t ncols, int64_t ldx, int64_t ldy,
                       cudaStream_t stream) {
+  ProfScope prof("relu_mask", stream);
   if (M * ncols == 0) return 0;
   relu_mask_kernel<<<grid_for(M * ncols, 256), 256, 0, stream>>>(X, Y, M, ncols, ldx, ldy);
   return check_launch("relu_mask_kernel");

@@ -1,0 +1,110 @@
+// Library runtime: error plumbing, launch counter, optional per-op event profiler, misc C ABI.
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return 2;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return 0;
+}
+
+// ---- profiler ---------------------------------------------------------------------------
+struct ProfRecord { const char* name; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRecord> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+ProfScope::ProfScope(const char* name, cudaStream_t st) : slot(-1), stream(st) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRecord r;
+  r.name = name;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof.push_back(r);
+  slot = int(g_prof.size()) - 1;
+}
+
+ProfScope::~ProfScope() {
+  if (slot < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (slot < int(g_prof.size())) cudaEventRecord(g_prof[slot].b, stream);
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int tb_abi_version(void) { return TB_ABI_VERSION; }
+const char* tb_last_error(void) { return g_err; }
+size_t tb_workspace_bytes(void) { return kWorkspaceBytes; }
+uint64_t tb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int tb_device_info(int* sm, int* major, int* minor) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { set_error("tb_device_info: %s", cudaGetErrorString(e)); return 2; }
+  if (sm) *sm = prop.multiProcessorCount;
+  if (major) *major = prop.major;
+  if (minor) *minor = prop.minor;
+  return 0;
+}
+
+int tb_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (on) {
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+  }
+  g_prof_on.store(on ? 1 : 0);
+  return 0;
+}
+
+int tb_profile_collect(char* names_host, size_t names_cap, float* ms_host, int max_records) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { set_error("tb_profile_collect: %s", cudaGetErrorString(e)); return -1; }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int n = 0;
+  size_t off = 0;
+  for (auto& r : g_prof) {
+    if (n >= max_records) break;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    const size_t len = strlen(r.name);
+    if (off + len + 2 > names_cap) break;
+    memcpy(names_host + off, r.name, len);
+    names_host[off + len] = '\n';
+    off += len + 1;
+    ms_host[n++] = ms;
+  }
+  if (names_cap) names_host[off < names_cap ? off : names_cap - 1] = '\0';
+  return n;
+}
+
+}  // extern "C"

@@ -24,27 +24,6 @@
 
 namespace tb {
 
-// ----------------------------------------------------------------------------------------
-// error plumbing
-// ----------------------------------------------------------------------------------------
-static thread_local char g_err[512] = "";
-
-void set_error(const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
-  va_end(ap);
-}
-
-int check_launch(const char* what) {
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
-    set_error("%s: %s", what, cudaGetErrorString(e));
-    return 2;
-  }
-  return 0;
-}
-
 static int g_sm_count = 0;
 static int sm_count() {
   if (g_sm_count == 0) {
@@ -197,6 +176,7 @@ static int launch_scan(const F* log_rhos, const F* discounts, const F* rewards, 
   dim3 block(kWarp, W);
   dim3 grid(pick_grid(tiles));
   size_t smem = size_t(2) * W * kWarp * sizeof(F);
+  ProfScope prof("vtrace_scan", (cudaStream_t)stream);
   vtrace_scan_kernel<F, 8><<<grid, block, smem, (cudaStream_t)stream>>>(a);
   return check_launch("vtrace_scan_kernel");
 }
@@ -511,22 +491,6 @@ using namespace tb;
 
 extern "C" {
 
-int tb_abi_version(void) { return TB_ABI_VERSION; }
-const char* tb_last_error(void) { return g_err; }
-size_t tb_workspace_bytes(void) { return kWorkspaceBytes; }
-
-int tb_device_info(int* sm, int* major, int* minor) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  cudaDeviceProp prop;
-  if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
-  if (e != cudaSuccess) { set_error("tb_device_info: %s", cudaGetErrorString(e)); return 2; }
-  if (sm) *sm = prop.multiProcessorCount;
-  if (major) *major = prop.major;
-  if (minor) *minor = prop.minor;
-  return 0;
-}
-
 int tb_action_log_probs_f32(const float* l, const int64_t* a, int64_t N, int64_t A, float* o, void* s) {
   return launch_alp<float>(l, a, N, A, o, s);
 }
@@ -581,6 +545,7 @@ int tb_impala_loss_fwd_bwd_f32(const float* blogits, const float* tlogits, const
   dim3 block(kWarp, W);
   dim3 grid(pick_grid(tiles));
   const size_t smem = size_t(2) * W * kWarp * sizeof(float);
+  ProfScope prof("impala_loss_fwd_bwd", (cudaStream_t)stream);
   TB_DISPATCH_A(A, (impala_loss_kernel<kA><<<grid, block, smem, (cudaStream_t)stream>>>(p)));
   return check_launch("impala_loss_kernel");
 }
