@@ -112,6 +112,43 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so the pinned rollout
+    staging buffers are allocated next to the GPU's PCIe root (first touch) - H2D bandwidth on a
+    2-socket host depends on it.  Returns the node id or None."""
+    try:
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = torch.cuda.get_device_properties(index).pci_domain_id
+        dev = torch.cuda.get_device_properties(index).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, dev)
+        node = int(open(path + "/numa_node").read())
+        cpus = open(path + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return node
+    except Exception:
+        return None
+
+
+def measure_h2d_gbs(dev):
+    """Pinned-host -> device copy bandwidth of this process (256 MB, best of 3)."""
+    src = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    best = 0.0
+    for _ in range(3):
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); dst.copy_(src, non_blocking=True); z.record(); torch.cuda.synchronize()
+        best = max(best, src.numel() / (a.elapsed_time(z) * 1e-3) / 1e9)
+    return best
+
+
 def peaks():
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -158,16 +195,37 @@ def run_reference(args):
     """CPU arm: the oracle port of the reference's learn step on the host cores."""
     from oracle import learner_torch as LT
     T, B, A = args.T, args.B, args.num_actions
-    torch.set_num_threads(os.cpu_count() or 1)
+    budget_s = float(os.environ.get("TB_CPU_BASELINE_BUDGET_S", "60"))
     shapes = LT.atarinet_param_shapes(A, bool(args.use_lstm))
     p = LT.random_params(shapes, seed=0)
+    # Thread count: the op-by-op CPU path is dispatch-bound and gets SLOWER with many threads
+    # (measured on the 128-thread B200 host: 250 s/step at 128 threads; SURVEY.md section 6), so pick
+    # the fastest of a few counts on a small calibration rollout and report it as `cores`.
+    ncpu = os.cpu_count() or 1
+    cal = synthetic_host_batch(8, 8, A, seed=2, pin=False)
+    cal_state = tuple(torch.zeros(2, 8, 512 + A + 1) for _ in range(2)) if args.use_lstm else ()
+    best = None
+    for nt in sorted({min(ncpu, n) for n in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(nt)
+        LT.learner_step(p, cal, cal_state, net="atari", num_actions=A)
+        t0 = time.perf_counter()
+        LT.learner_step(p, cal, cal_state, net="atari", num_actions=A)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+        if dt > 4 * best[0]:
+            break
+    torch.set_num_threads(best[1])
     batch = synthetic_host_batch(T, B, A, seed=1, pin=False)
     state = tuple(torch.zeros(2, B, 512 + A + 1) for _ in range(2)) if args.use_lstm else ()
     sq = None
-    steps, warm = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    steps, warm = max(1, min(args.steps, 10)), 1
+    tw = time.perf_counter()
     for _ in range(warm):
         o = LT.learner_step(p, batch, state, net="atari", square_avg=sq, num_actions=A)
         p, sq = o["params"], o["square_avg"]
+    tw = time.perf_counter() - tw
+    steps = max(1, min(steps, int(budget_s / max(tw, 1e-3))))  # bounded sample: ~budget_s of CPU work
     t0 = time.perf_counter()
     for _ in range(steps):
         o = LT.learner_step(p, batch, state, net="atari", square_avg=sq, num_actions=A)
@@ -203,6 +261,7 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)  # before any pinned allocation (first-touch placement)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -222,6 +281,7 @@ def main():
     host = [synthetic_host_batch(T, B, A, seed=1000 * rank + i, pin=True) for i in range(NROT)]
     devb = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
     h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    h2d_gbs = measure_h2d_gbs(dev)
     lib = _lib.lib()
 
     def barrier():
@@ -307,7 +367,7 @@ def main():
         data="synthetic", config=dict(config, l2="4 rotating input batches per rank (%.0f MB) > 126 MB L2; ~2.3 GB of "
                                       "activations written per step" % (NROT * h2d_bytes / 1e6)),
         e2e=dict(value=frames / (e2e_ms * 1e-3), unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes,
-                 d2h_bytes_per_step=d2h_bytes, note="pinned host rollout -> async H2D (double-buffered, overlapped with "
+                 d2h_bytes_per_step=d2h_bytes, h2d_gbs_measured=h2d_gbs, numa_node=numa, note="pinned host rollout -> async H2D (double-buffered, overlapped with "
                  "the previous step) -> monobeast.learn -> stats read-back, all inside the timed region"),
         gpu_launches=int(launches), clocks=clocks, final_total_loss=final_loss,
     )
@@ -350,6 +410,7 @@ def main():
         line["vtrace"] = vtrace_numbers(pk, T, B, A)
 
     if not args.no_cpu_baseline and world == 1:
+        os.environ.setdefault("TB_CPU_BASELINE_BUDGET_S", "20")
         r = run_reference(types.SimpleNamespace(**dict(vars(args), steps=3, warmup=1)))
         line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port",
                                     sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py" % (r["steps"], T, B))

@@ -38,14 +38,18 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers) {
   for (int l = 0; l < kLstmMaxLayers; ++l) {
     LstmLayerWs& L = w.layer[l];
     if (l < layers) {
-      L.gates = takef(N * 4 * H); L.hs = takef(N * H); L.cs = takef(N * H); L.hm = takef(N * H);
-      L.cm = takef(N * H); L.dgates = takef(N * 4 * H); L.bsum = takef(4 * H); L.w_hh_t = takef(int64_t(H) * 4 * H);
+      const int Hp = padded_h(H);
+      L.gates = takef(N * 4 * H); L.hs = takef(N * H); L.cs = takef(N * H); L.hm = takef(N * Hp);
+      L.cm = takef(N * H); L.dgates = takef(N * 4 * H); L.bsum = takef(4 * H); L.w_hh_t = takef(int64_t(H + 4) * 4 * Hp);
+      L.wp = takef(int64_t(4 * H + 4) * Hp);
     } else {
       L = LstmLayerWs();
     }
   }
   w.dh = takef(B * H); w.dc = takef(B * H);
   w.dx_mid = takef(N * (H > In ? H : In));
+  w.dgp = takef(int64_t(4) * B * padded_h(H));
+  w.Hp = padded_h(H);
   w.bytes = off;
   return w;
 }
@@ -60,62 +64,101 @@ __global__ void add2_kernel(const float* __restrict__ a, const float* __restrict
 // ---------------------------------------------------------------------------------------
 // forward step: one CTA = 4 hidden units (x 4 gates = 16 rows of W_hh) x a 32-row batch tile.
 // 128 threads: lane = batch row, warp q = gate; each thread owns gate q of 4 units.
+// Operands are staged by the bulk-copy engine (cp.async.bulk -> UBLKCP, mbarrier complete_tx):
+// four 8 KB W_hh gate slices - issued BEFORE griddepcontrol.wait, so with programmatic
+// dependent launch they stream in while the previous time step is still finishing - and the
+// 67 KB masked-h tile the previous step produced.
 // ---------------------------------------------------------------------------------------
 constexpr int kStepUnits = 4;
 constexpr int kStepThreads = 128;
 
 struct StepArgs {
-  const float* h_prev; const float* c_prev;  // [B,H] (previous step's h/c or the initial state)
-  const float* nd;                           // [B] notdone_t
-  const float* w_hh;                         // [4H,H]
-  float* gates;                              // [B,4H] in: x-projection + biases; out: activated gates
-  float* hs; float* cs; float* hm; float* cm;  // [B,H] this step's outputs
+  const float* hm;      // [B,Hp] masked recurrent input of this step (h_{t-1} * nd_t), zero padded
+  const float* cm;      // [B,H]  masked previous cell state
+  const float* nd_next; // [B] notdone_{t+1} or nullptr at the last step
+  const float* wp;      // [4H+4,Hp] padded W_hh
+  float* gates;         // [B,4H] in: x-projection + biases; out: activated gates
+  float* hs; float* cs; // [B,H] this step's outputs
+  float* hm_next; float* cm_next;  // [B,Hp] / [B,H] masked state for step t+1 (nullptr at the last step)
   int B, H, Hp;
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE_%=;\n"
+      "bra LAB_WAIT_%=;\n"
+      "LAB_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __global__ void __launch_bounds__(kStepThreads) lstm_step_fwd_kernel(StepArgs a) {
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* Ws = smem;                                  // [16][Hp]
   float* Xs = smem + 16 * a.Hp;                      // [32][Hp]  masked h_prev tile
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 48 * a.Hp);  // [0]: W slices, [1]: h tile
   __shared__ float act_s[4][kStepUnits][33];
   const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
   const int H = a.H, Hp = a.Hp;
   const int j0 = blockIdx.x * kStepUnits;
   const int b0 = blockIdx.y * 32;
-  // stage W_hh rows (g*H + j0 + u) and the masked recurrent input
-  for (int idx = tid; idx < 16 * Hp; idx += kStepThreads) {
-    const int r = idx / Hp, k = idx % Hp;
-    const int g = r >> 2, u = r & 3;
-    float v = 0.0f;
-    if (k < H && j0 + u < H) v = __ldg(a.w_hh + (int64_t(g) * H + j0 + u) * H + k);
-    Ws[idx] = v;
+  const int rows = (a.B - b0 < 32) ? (a.B - b0) : 32;
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t wbytes = uint32_t(kStepUnits) * Hp * sizeof(float);
+    mbar_expect_tx(&bar[0], 4 * wbytes);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)  // rows g*H + j0 .. +3 are contiguous in the padded matrix
+      bulk_g2s(Ws + g * kStepUnits * Hp, a.wp + (int64_t(g) * H + j0) * Hp, wbytes, &bar[0]);
+    // everything above is independent of the previous step; the h tile is not
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const uint32_t xbytes = uint32_t(rows) * Hp * sizeof(float);
+    mbar_expect_tx(&bar[1], xbytes);
+    bulk_g2s(Xs, a.hm + int64_t(b0) * Hp, xbytes, &bar[1]);
   }
-  for (int idx = tid; idx < 32 * Hp; idx += kStepThreads) {
-    const int r = idx / Hp, k = idx % Hp;
-    float v = 0.0f;
-    if (k < H && b0 + r < a.B) v = a.h_prev[int64_t(b0 + r) * H + k] * a.nd[b0 + r];
-    Xs[idx] = v;
-  }
-  __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __syncthreads();  // barrier inits visible to the waiting threads
+  mbar_wait(&bar[0], 0);
+  mbar_wait(&bar[1], 0);
   float acc[kStepUnits] = {0.f, 0.f, 0.f, 0.f};
   const float4* x4 = reinterpret_cast<const float4*>(Xs + lane * Hp);
   const float4* w4 = reinterpret_cast<const float4*>(Ws + (q * 4) * Hp);
   const int k4n = Hp / 4;
+  if (lane < rows) {
 #pragma unroll 2
-  for (int k4 = 0; k4 < k4n; ++k4) {
-    const float4 x = x4[k4];
+    for (int k4 = 0; k4 < k4n; ++k4) {
+      const float4 x = x4[k4];
 #pragma unroll
-    for (int u = 0; u < kStepUnits; ++u) {
-      const float4 w = w4[u * k4n + k4];
-      acc[u] = fmaf(x.x, w.x, acc[u]); acc[u] = fmaf(x.y, w.y, acc[u]);
-      acc[u] = fmaf(x.z, w.z, acc[u]); acc[u] = fmaf(x.w, w.w, acc[u]);
+      for (int u = 0; u < kStepUnits; ++u) {
+        const float4 w = w4[u * k4n + k4];
+        acc[u] = fmaf(x.x, w.x, acc[u]); acc[u] = fmaf(x.y, w.y, acc[u]);
+        acc[u] = fmaf(x.z, w.z, acc[u]); acc[u] = fmaf(x.w, w.w, acc[u]);
+      }
     }
   }
   const int b = b0 + lane;
 #pragma unroll
   for (int u = 0; u < kStepUnits; ++u) {
     float v = 0.0f;
-    if (b < a.B && j0 + u < H) {
+    if (lane < rows && j0 + u < H) {
       float* gp = a.gates + int64_t(b) * 4 * H + int64_t(q) * H + j0 + u;
       const float pre = *gp + acc[u];
       v = (q == 2) ? tanhf(pre) : sigmoidf_(pre);
@@ -126,16 +169,46 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_fwd_kernel(StepArgs a)
   __syncthreads();
   // state update: thread = (batch row lane, unit q)
   const int u = q;
-  if (b < a.B && j0 + u < H) {
+  if (lane < rows && j0 + u < H) {
     const int64_t o = int64_t(b) * H + j0 + u;
-    const float nd = a.nd[b];
-    const float cmv = a.c_prev[o] * nd;
+    const float cmv = a.cm[o];
     const float ig = act_s[0][u][lane], fg = act_s[1][u][lane], gg = act_s[2][u][lane], og = act_s[3][u][lane];
     const float c = fg * cmv + ig * gg;
+    const float h = og * tanhf(c);
     a.cs[o] = c;
-    a.hs[o] = og * tanhf(c);
-    a.cm[o] = cmv;
-    a.hm[o] = a.h_prev[o] * nd;
+    a.hs[o] = h;
+    if (a.hm_next) {
+      const float ndn = a.nd_next[b];
+      a.hm_next[int64_t(b) * Hp + j0 + u] = h * ndn;
+      a.cm_next[o] = c * ndn;
+    }
+  }
+}
+
+// padded copies: wp[r, :H] = w_hh[r, :], zero elsewhere (incl. 4 extra rows)
+__global__ void lstm_pack_whh_kernel(const float* __restrict__ w, float* __restrict__ wp, int H, int Hp) {
+  const int64_t total = int64_t(4 * H + 4) * Hp;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / Hp;
+    const int k = int(i % Hp);
+    wp[i] = (r < 4 * H && k < H) ? w[r * H + k] : 0.0f;
+  }
+}
+
+// hm[0] = h0 * nd_0 (zero padded), cm[0] = c0 * nd_0
+__global__ void lstm_init_state_kernel(const float* __restrict__ h0, const float* __restrict__ c0,
+                                       const float* __restrict__ nd, float* __restrict__ hm, float* __restrict__ cm,
+                                       int B, int H, int Hp) {
+  const int64_t total = int64_t(B) * Hp;
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = int(i / Hp), k = int(i % Hp);
+  if (k < H) {
+    hm[i] = h0[int64_t(b) * H + k] * nd[b];
+    cm[int64_t(b) * H + k] = c0[int64_t(b) * H + k] * nd[b];
+  } else {
+    hm[i] = 0.0f;
   }
 }
 
@@ -149,6 +222,7 @@ struct BwdPointArgs {
   const float* gates; const float* cs; const float* cm;        // forward saves at t
   float* dc;                                                   // [B,H] carry in/out (dL/dc_t in, dL/dc_{t-1} out)
   float* dgates;                                               // [B,4H]
+  float* dgp; int Hp;                                          // [4,B,Hp] gate-major padded copy
   int B, H; int first;                                         // first != 0: carries are zero (t = T1-1)
 };
 
@@ -169,24 +243,136 @@ __global__ void lstm_step_bwd_point_kernel(BwdPointArgs a) {
   const float d_o = dh * tc;
   dc += dh * og * (1.0f - tc * tc);
   const float d_i = dc * gg, d_f = dc * a.cm[i], d_g = dc * ig;
-  a.dgates[g0] = d_i * ig * (1.0f - ig);
-  a.dgates[g0 + a.H] = d_f * fg * (1.0f - fg);
-  a.dgates[g0 + 2 * a.H] = d_g * (1.0f - gg * gg);
-  a.dgates[g0 + 3 * a.H] = d_o * og * (1.0f - og);
+  const float p_i = d_i * ig * (1.0f - ig), p_f = d_f * fg * (1.0f - fg);
+  const float p_g = d_g * (1.0f - gg * gg), p_o = d_o * og * (1.0f - og);
+  a.dgates[g0] = p_i; a.dgates[g0 + a.H] = p_f; a.dgates[g0 + 2 * a.H] = p_g; a.dgates[g0 + 3 * a.H] = p_o;
+  const int64_t gs = int64_t(a.B) * a.Hp, gp = int64_t(b) * a.Hp + j;
+  a.dgp[gp] = p_i; a.dgp[gs + gp] = p_f; a.dgp[2 * gs + gp] = p_g; a.dgp[3 * gs + gp] = p_o;
   a.dc[i] = dc * fg * a.nd[b];
+}
+
+
+// ---------------------------------------------------------------------------------------
+// backward step, recurrent product: dh_raw[b,k] = sum_g sum_j dgates_g[b,j] * W_hh[g*H+j][k].
+// One CTA = 4 output columns k x a 32-row batch tile; lane = batch row, warp = column.  The
+// 4 x 4*Hp slice of W_hh^T arrives by one bulk copy before griddepcontrol.wait; the four
+// [32,Hp] gate-gradient tiles stream through a 2-deep shared-memory ring (bulk copies).
+// ---------------------------------------------------------------------------------------
+struct DhArgs {
+  const float* dgp;   // [4,B,Hp]
+  const float* wtp;   // [H+4, 4*Hp]
+  float* dh_raw;      // [B,H]
+  int B, H, Hp;
+};
+
+__global__ void __launch_bounds__(kStepThreads) lstm_step_bwd_dh_kernel(DhArgs a) {
+  extern __shared__ __align__(128) float smem[];
+  const int Hp = a.Hp, H = a.H;
+  float* Ws = smem;                       // [4][4*Hp]
+  float* Xs = smem + 16 * Hp;             // [2][32][Hp]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 80 * Hp);  // [0]: W, [1],[2]: ring slots
+  const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+  const int k0 = blockIdx.x * 4;
+  const int b0 = blockIdx.y * 32;
+  const int rows = (a.B - b0 < 32) ? (a.B - b0) : 32;
+  const uint32_t xbytes = uint32_t(rows) * Hp * sizeof(float);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t wbytes = uint32_t(16) * Hp * sizeof(float);
+    mbar_expect_tx(&bar[0], wbytes);
+    bulk_g2s(Ws, a.wtp + int64_t(k0) * 4 * Hp, wbytes, &bar[0]);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    for (int g = 0; g < 2; ++g) {
+      mbar_expect_tx(&bar[1 + g], xbytes);
+      bulk_g2s(Xs + g * 32 * Hp, a.dgp + (int64_t(g) * a.B + b0) * Hp, xbytes, &bar[1 + g]);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  __syncthreads();
+  mbar_wait(&bar[0], 0);
+  float acc = 0.0f;
+  const int k4n = Hp / 4;
+  for (int g = 0; g < 4; ++g) {
+    const int slot = g & 1;
+    mbar_wait(&bar[1 + slot], (g >> 1) & 1);
+    if (lane < rows) {
+      const float4* x4 = reinterpret_cast<const float4*>(Xs + (slot * 32 + lane) * Hp);
+      const float4* w4 = reinterpret_cast<const float4*>(Ws + (q * 4 + g) * Hp);
+#pragma unroll 4
+      for (int k4 = 0; k4 < k4n; ++k4) {
+        const float4 x = x4[k4];
+        const float4 w = w4[k4];
+        acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+      }
+    }
+    __syncthreads();  // everyone is done with this ring slot
+    if (tid == 0 && g + 2 < 4) {
+      mbar_expect_tx(&bar[1 + slot], xbytes);
+      bulk_g2s(Xs + slot * 32 * Hp, a.dgp + (int64_t(g + 2) * a.B + b0) * Hp, xbytes, &bar[1 + slot]);
+    }
+  }
+  if (lane < rows && k0 + q < H) a.dh_raw[int64_t(b0 + lane) * H + k0 + q] = acc;
+}
+
+// wtp[k][g*Hp + j] = W_hh[g*H + j][k], zero padded (j >= H, k >= H)
+__global__ void lstm_pack_whh_t_kernel(const float* __restrict__ w, float* __restrict__ wtp, int H, int Hp) {
+  const int64_t total = int64_t(H + 4) * 4 * Hp;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t k = i / (4 * Hp);
+    const int r = int(i % (4 * Hp));
+    const int g = r / Hp, j = r % Hp;
+    wtp[i] = (k < H && j < H) ? w[(int64_t(g) * H + j) * H + k] : 0.0f;
+  }
+}
+
+static int launch_step_bwd_dh(const DhArgs& a, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = size_t(80) * a.Hp * sizeof(float) + 32;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(lstm_step_bwd_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    TB_REQUIRE(e == cudaSuccess, "lstm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  TB_REQUIRE(smem <= 220 * 1024, "lstm: hidden size %d too large for the backward step kernel", a.H);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((a.H + 3) / 4, (a.B + 31) / 32);
+  cfg.blockDim = dim3(kStepThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_step_bwd_dh_kernel, a);
+  TB_REQUIRE(e == cudaSuccess, "lstm_step_bwd_dh_kernel: %s", cudaGetErrorString(e));
+  return check_launch("lstm_step_bwd_dh_kernel");
 }
 
 static int launch_step_fwd(const StepArgs& a, cudaStream_t st) {
   static bool attr_set = false;
-  const size_t smem = size_t(48) * a.Hp * sizeof(float);
+  const size_t smem = size_t(48) * a.Hp * sizeof(float) + 16;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(lstm_step_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     TB_REQUIRE(e == cudaSuccess, "lstm: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   TB_REQUIRE(smem <= 200 * 1024, "lstm: hidden size %d too large for the step kernel", a.H);
-  dim3 grid((a.H + kStepUnits - 1) / kStepUnits, (a.B + 31) / 32);
-  lstm_step_fwd_kernel<<<grid, kStepThreads, smem, st>>>(a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((a.H + kStepUnits - 1) / kStepUnits, (a.B + 31) / 32);
+  cfg.blockDim = dim3(kStepThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: overlap W staging with the previous step
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_step_fwd_kernel, a);
+  TB_REQUIRE(e == cudaSuccess, "lstm_step_fwd_kernel: %s", cudaGetErrorString(e));
   return check_launch("lstm_step_fwd_kernel");
 }
 
@@ -211,16 +397,30 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
     GemmEpilogue ep; ep.bias = L.bsum; ep.tag = "lstm_xproj_fwd";
     TB_TRY((gemm_simt<float, float, false, true>(xin, p.w_ih[l], L.gates, N, 4 * H, in_dim, in_dim, in_dim, 4 * H, ep, 1,
                                                   nullptr, st)));
+    const int Hp = padded_h(H);
+    {
+      const int64_t tot = int64_t(4 * H + 4) * Hp;
+      lstm_pack_whh_kernel<<<(unsigned)((tot + 255) / 256 > 1184 ? 1184 : (tot + 255) / 256), 256, 0, st>>>(p.w_hh[l], L.wp, H, Hp);
+      TB_TRY(check_launch("lstm_pack_whh_kernel"));
+      cudaError_t em = cudaMemsetAsync(L.hm, 0, sizeof(float) * N * Hp, st);  // zero the row padding
+      TB_REQUIRE(em == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(em));
+      lstm_init_state_kernel<<<(unsigned)((B * Hp + 255) / 256), 256, 0, st>>>(
+          h0 + int64_t(l) * B * H, c0 + int64_t(l) * B * H, notdone, L.hm, L.cm, int(B), H, Hp);
+      TB_TRY(check_launch("lstm_init_state_kernel"));
+    }
     ProfScope prof("lstm_recurrence_fwd", st);
     for (int64_t t = 0; t < T1; ++t) {
       StepArgs a;
-      a.h_prev = (t == 0) ? h0 + int64_t(l) * B * H : hs + (t - 1) * B * H;
-      a.c_prev = (t == 0) ? c0 + int64_t(l) * B * H : L.cs + (t - 1) * B * H;
-      a.nd = notdone + t * B;
-      a.w_hh = p.w_hh[l];
+      a.hm = L.hm + t * B * Hp;
+      a.cm = L.cm + t * B * H;
+      const bool last = (t == T1 - 1);
+      a.nd_next = last ? nullptr : notdone + (t + 1) * B;
+      a.wp = L.wp;
       a.gates = L.gates + t * B * 4 * H;
-      a.hs = hs + t * B * H; a.cs = L.cs + t * B * H; a.hm = L.hm + t * B * H; a.cm = L.cm + t * B * H;
-      a.B = int(B); a.H = H; a.Hp = padded_h(H);
+      a.hs = hs + t * B * H; a.cs = L.cs + t * B * H;
+      a.hm_next = last ? nullptr : L.hm + (t + 1) * B * Hp;
+      a.cm_next = last ? nullptr : L.cm + (t + 1) * B * H;
+      a.B = int(B); a.H = H; a.Hp = Hp;
       TB_TRY(launch_step_fwd(a, st));
     }
     cudaError_t e = cudaMemcpyAsync(hN + int64_t(l) * B * H, hs + (T1 - 1) * B * H, sizeof(float) * B * H,
@@ -259,6 +459,14 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     const float* xin = (l == 0) ? x : ws.layer[l - 1].hs;
     const int in_dim = (l == 0) ? In : H;
     float* dxl = (l == 0) ? dx : ws.dx_mid;
+    const int Hp = padded_h(H);
+    {
+      const int64_t tot = int64_t(H + 4) * 4 * Hp;
+      lstm_pack_whh_t_kernel<<<(unsigned)((tot + 255) / 256 > 1184 ? 1184 : (tot + 255) / 256), 256, 0, st>>>(p.w_hh[l], L.w_hh_t, H, Hp);
+      TB_TRY(check_launch("lstm_pack_whh_t_kernel"));
+      cudaError_t em = cudaMemsetAsync(ws.dgp, 0, sizeof(float) * 4 * B * Hp, st);  // zero the row padding
+      TB_REQUIRE(em == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(em));
+    }
     {
     ProfScope prof("lstm_recurrence_bwd", st);
     for (int64_t t = T1 - 1; t >= 0; --t) {
@@ -268,23 +476,23 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       a.dh_raw = ws.dh; a.nd_next = a.first ? nullptr : notdone + (t + 1) * B;
       a.nd = notdone + t * B;
       a.gates = L.gates + t * B * 4 * H; a.cs = L.cs + t * B * H; a.cm = L.cm + t * B * H;
-      a.dc = ws.dc; a.dgates = L.dgates + t * B * 4 * H; a.B = int(B); a.H = H;
+      a.dc = ws.dc; a.dgates = L.dgates + t * B * 4 * H; a.B = int(B); a.H = H; a.dgp = ws.dgp; a.Hp = Hp;
       const int64_t total = B * H;
       lstm_step_bwd_point_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a);
       TB_TRY(check_launch("lstm_step_bwd_point_kernel"));
       if (t > 0) {
         // dh_raw[B,H] = dgates_t[B,4H] . W_hh[4H,H]   (masked by notdone_t when consumed at t-1)
-        GemmEpilogue ep; ep.tag = "lstm_step_dh";
-        const int s = splits_for(B, H, 4 * H, scratch);
-        TB_TRY((gemm_simt<float, float, false, false>(a.dgates, p.w_hh[l], ws.dh, B, H, 4 * H, 4 * H, H, H, ep, s,
-                                                       splitk, st)));
+        DhArgs d;
+        d.dgp = ws.dgp; d.wtp = L.w_hh_t; d.dh_raw = ws.dh; d.B = int(B); d.H = H; d.Hp = Hp;
+        TB_TRY(launch_step_bwd_dh(d, st));
       }
     }
     }
     // parameter gradients over all steps at once
     GemmEpilogue ep; ep.tag = "lstm_wgrad";
     int s = splits_for(4 * H, H, N, scratch);
-    TB_TRY((gemm_simt<float, float, true, false>(L.dgates, L.hm, g.w_hh[l], 4 * H, H, N, 4 * H, H, H, ep, s, splitk, st)));
+    TB_TRY((gemm_simt<float, float, true, false>(L.dgates, L.hm, g.w_hh[l], 4 * H, H, N, 4 * H, padded_h(H), H, ep, s, splitk,
+                                                  st)));
     s = splits_for(4 * H, in_dim, N, scratch);
     TB_TRY((gemm_simt<float, float, true, false>(L.dgates, xin, g.w_ih[l], 4 * H, in_dim, N, 4 * H, in_dim, in_dim, ep, s,
                                                   splitk, st)));

@@ -20,11 +20,12 @@ struct LstmLayerWs {
   float* gates;   // [T1*B, 4H]  pre-activations, overwritten by activated i,f,g,o
   float* hs;      // [T1*B, H]   h_t
   float* cs;      // [T1*B, H]   c_t
-  float* hm;      // [T1*B, H]   h_{t-1} * notdone_t  (recurrent input actually used at step t)
+  float* hm;      // [T1*B, Hp]  h_{t-1} * notdone_t (recurrent input used at step t), rows zero-padded to Hp
   float* cm;      // [T1*B, H]   c_{t-1} * notdone_t
+  float* wp;      // [4H+4, Hp]  W_hh with rows zero-padded to Hp floats (16-byte multiples for bulk copies)
   float* dgates;  // [T1*B, 4H]  backward: d pre-activations
   float* bsum;    // [4H]        b_ih + b_hh
-  float* w_hh_t;  // [H, 4H]     W_hh^T (backward recurrent product)
+  float* w_hh_t;  // [H+4, 4*Hp] W_hh^T, gate segments zero-padded to Hp: wt[k][g*Hp+j] = W_hh[g*H+j][k]
 };
 
 struct LstmWs {
@@ -32,6 +33,8 @@ struct LstmWs {
   float* dh;      // [B, H] carry
   float* dc;      // [B, H] carry
   float* dx_mid;  // [T1*B, H] gradient w.r.t. the output of layer 0 (input of layer 1)
+  float* dgp;     // [4, B, Hp] this step's gate gradients, gate-major and zero padded (recurrent product operand)
+  int Hp = 0;     // padded row length of hm / wp
   size_t bytes = 0;
 };
 

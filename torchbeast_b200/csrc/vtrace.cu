@@ -48,6 +48,8 @@ static int pick_warps(int64_t T, int64_t tiles) {
   return int(w);
 }
 
+constexpr int kWideWarps = 8;
+
 static int pick_grid(int64_t tiles) {
   int64_t g = int64_t(sm_count()) * 8;
   if (g > kMaxPartialCtas) g = kMaxPartialCtas;
@@ -64,6 +66,7 @@ struct ScanArgs {
   int64_t T, B;
   F clip_rho, clip_pg; int has_clip_rho, has_clip_pg;
   F* vs; F* pg_adv;
+  int wide;  // 1: every warp owns its own column tile and the whole unroll (no T split, no smem)
 };
 
 template <typename F, int U>
@@ -71,14 +74,17 @@ __global__ void __launch_bounds__(512) vtrace_scan_kernel(ScanArgs<F> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   F* sA = reinterpret_cast<F*>(smem_raw);
   F* sB = sA + blockDim.y * kWarp;
-  const int lane = threadIdx.x, w = threadIdx.y, W = blockDim.y;
+  const int lane = threadIdx.x;
+  const int w = p.wide ? 0 : threadIdx.y, W = p.wide ? 1 : blockDim.y;
   const int64_t T = p.T, B = p.B;
   const int64_t tiles = (B + kWarp - 1) / kWarp;
   const int64_t chunk = (T + W - 1) / W;
   const int64_t t0 = (int64_t(w) * chunk < T) ? int64_t(w) * chunk : T;
   const int64_t t1 = (t0 + chunk < T) ? t0 + chunk : T;
+  const int64_t tile0 = p.wide ? int64_t(blockIdx.x) * blockDim.y + threadIdx.y : blockIdx.x;
+  const int64_t tile_step = p.wide ? int64_t(gridDim.x) * blockDim.y : gridDim.x;
 
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (int64_t tile = tile0; tile < tiles; tile += tile_step) {
     const int64_t b = tile * kWarp + lane;
     const bool active = b < B;
     F acc_in = F(0);
@@ -172,9 +178,15 @@ static int launch_scan(const F* log_rhos, const F* discounts, const F* rewards, 
   a.has_clip_pg = (clip_pg >= F(0));
   a.clip_rho = clip_rho; a.clip_pg = clip_pg; a.vs = vs; a.pg_adv = pg_adv;
   const int64_t tiles = (B + kWarp - 1) / kWarp;
-  const int W = pick_warps(T, tiles);
-  dim3 block(kWarp, W);
+  int W = pick_warps(T, tiles);
+  a.wide = (W == 1);
   dim3 grid(pick_grid(tiles));
+  if (a.wide) {  // wide batch: 8 warps per CTA, one column tile each, enough CTAs for every tile
+    W = kWideWarps;
+    int64_t g = (tiles + W - 1) / W;
+    grid = dim3((unsigned)(g < 1 ? 1 : g));
+  }
+  dim3 block(kWarp, W);
   size_t smem = size_t(2) * W * kWarp * sizeof(F);
   ProfScope prof("vtrace_scan", (cudaStream_t)stream);
   vtrace_scan_kernel<F, 8><<<grid, block, smem, (cudaStream_t)stream>>>(a);
@@ -288,6 +300,7 @@ struct LossArgs {
   float* vs; float* pg_adv; float* log_rhos; float* balp; float* talp; float* losses;
   float* grad_logits; float* grad_values; int zero_tail;
   void* workspace;
+  int wide;  // see ScanArgs
 };
 
 __device__ __forceinline__ float reward_of(const LossArgs& p, int64_t i) {
@@ -304,16 +317,19 @@ __global__ void __launch_bounds__(512) impala_loss_kernel(LossArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sA = reinterpret_cast<float*>(smem_raw);
   float* sB = sA + blockDim.y * kWarp;
-  const int lane = threadIdx.x, w = threadIdx.y, W = blockDim.y;
+  const int lane = threadIdx.x;
+  const int w = p.wide ? 0 : threadIdx.y, W = p.wide ? 1 : blockDim.y;
   const int64_t T = p.T, B = p.B;
   const int64_t Ause = A ? A : p.A;
   const int64_t tiles = (B + kWarp - 1) / kWarp;
   const int64_t chunk = (T + W - 1) / W;
   const int64_t t0 = (int64_t(w) * chunk < T) ? int64_t(w) * chunk : T;
   const int64_t t1 = (t0 + chunk < T) ? t0 + chunk : T;
+  const int64_t tile0 = p.wide ? int64_t(blockIdx.x) * blockDim.y + threadIdx.y : blockIdx.x;
+  const int64_t tile_step = p.wide ? int64_t(gridDim.x) * blockDim.y : gridDim.x;
   double s_pg = 0.0, s_bl = 0.0, s_en = 0.0;
 
-  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (int64_t tile = tile0; tile < tiles; tile += tile_step) {
     const int64_t b = tile * kWarp + lane;
     const bool active = b < B;
     float acc_in = 0.0f;
@@ -541,9 +557,16 @@ int tb_impala_loss_fwd_bwd_f32(const float* blogits, const float* tlogits, const
   p.losses = losses_out; p.grad_logits = grad_logits; p.grad_values = grad_values; p.zero_tail = zero_tail;
   p.workspace = workspace;
   const int64_t tiles = (B + kWarp - 1) / kWarp;
-  const int W = pick_warps(T, tiles);
-  dim3 block(kWarp, W);
+  int W = pick_warps(T, tiles);
+  p.wide = (W == 1);
   dim3 grid(pick_grid(tiles));
+  if (p.wide) {
+    W = kWideWarps;
+    int64_t g = (tiles + W - 1) / W;
+    if (g > kMaxPartialCtas) g = kMaxPartialCtas;  // per-CTA loss partials live in the workspace
+    grid = dim3((unsigned)(g < 1 ? 1 : g));
+  }
+  dim3 block(kWarp, W);
   const size_t smem = size_t(2) * W * kWarp * sizeof(float);
   ProfScope prof("impala_loss_fwd_bwd", (cudaStream_t)stream);
   TB_DISPATCH_A(A, (impala_loss_kernel<kA><<<grid, block, smem, (cudaStream_t)stream>>>(p)));

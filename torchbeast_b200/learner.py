@@ -136,3 +136,23 @@ def learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer,
         "baseline_loss": host[1].item(),
         "entropy_loss": host[2].item(),
     }
+
+
+def shard_rollout(batch, initial_agent_state, rank, world_size):
+    """Batch-column partition for data-parallel learners: rank g of G takes
+    columns [g*B/G, (g+1)*B/G) of every [T+1, B, ...] leaf and of the [layers, B, H] LSTM state.
+    V-trace, the LSTM and the convs are per-column and the losses are sums, so the SUM all-reduce
+    of the shards' gradients equals the full-batch gradient."""
+    def cols(t, dim):
+        B = t.shape[dim]
+        if B % world_size:
+            raise ValueError("batch size %d is not divisible by world size %d" % (B, world_size))
+        n = B // world_size
+        return t.narrow(dim, rank * n, n).contiguous()
+
+    if isinstance(batch, dict):
+        shard = {k: cols(v, 1) for k, v in batch.items()}
+    else:
+        shard = type(batch)(cols(v, 1) for v in batch)
+    state = tuple(cols(s, 1) for s in initial_agent_state)
+    return shard, state
