@@ -156,6 +156,18 @@ int tb_clip_rmsprop_step_f32(float* params, float* grads, float* square_avg, flo
                              const float* sumsq, float max_norm, const float* lr_device, float lr, float alpha,
                              float eps, float momentum, float* grad_norm_out, void* stream);
 
+/* ---- bf16 tensor-core GEMM (tcgen05 + TMEM + TMA), the throughput backend of the network -------- */
+
+/* C[M,N] = relu?( scale * (A[M,K] . B[N,K]^T) + bias[N] );  A, B bf16 with K contiguous ("K-major"),
+ * lda/ldb multiples of 8, 16-byte aligned; outputs fp32 C (ldc) and/or bf16 C_bf16 (ldc16), either may
+ * be NULL.  Replaces the cuBLAS/cuDNN calls behind F.linear / F.conv2d-as-GEMM (monobeast.py:587-591). */
+int tb_gemm_bf16_tn(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, int64_t lda,
+                    int64_t ldb, float* C, int64_t ldc, void* C_bf16, int64_t ldc16, const float* bias,
+                    float scale, int relu, void* stream);
+/* out_bf16[r, c] = bf16(in[r*ld + c]) for c < cols, 0 for cols <= c < ld16 (operand staging). */
+int tb_f32_to_bf16(const float* in, void* out_bf16, int64_t rows, int64_t cols, int64_t ld, int64_t ld16,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

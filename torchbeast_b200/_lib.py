@@ -35,6 +35,8 @@ _SIGNATURES = {
     "tb_entropy_loss_f64": ([_vp, _i64, _i64, _vp, _vp, _vp, _vp], _int),
     "tb_pg_loss_f32": ([_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp], _int),
     "tb_pg_loss_f64": ([_vp, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp], _int),
+    "tb_gemm_bf16_tn": ([_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _f32, _int, _vp], _int),
+    "tb_f32_to_bf16": ([_vp, _vp, _i64, _i64, _i64, _i64, _vp], _int),
     "tb_atarinet_param_count": ([_int, _int], _i64),
     "tb_atarinet_workspace_bytes": ([_i64, _i64, _int, _int], _c.c_size_t),
     "tb_atarinet_forward": ([_vp] * 7 + [_i64, _i64, _int, _int] + [_vp] * 6, _int),

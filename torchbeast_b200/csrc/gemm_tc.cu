@@ -1,0 +1,318 @@
+// bf16 tensor-core GEMM for sm_100a: tcgen05.mma + TMEM accumulators + TMA-staged operands.
+//
+//   C[M,N] = epilogue( sum_k A[m,k] * B[n,k] )     A [M,K], B [N,K] bf16, K contiguous ("K-major")
+//
+// One CTA computes a 128 x BLOCK_N tile.  Warp roles (192 threads):
+//   warp 0  TMA producer : cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 64 bf16 = 128 B) into a
+//                          4-stage shared-memory ring, mbarrier expect_tx / complete_tx
+//   warp 1  MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128,
+//                          N=BLOCK_N, K=16) x4 per 64-wide k-block, accumulating in TMEM;
+//                          tcgen05.commit frees the ring slot / signals the epilogue
+//   warps 2-5 epilogue   : tcgen05.ld 32x32b (each warp owns its 32 TMEM lanes = 32 output rows),
+//                          scale / bias / ReLU / ReLU-mask, fp32 and/or bf16 stores
+// M/N/K tails are handled by TMA out-of-bounds zero fill plus guarded stores.  Shared-memory
+// matrix descriptors: K-major, SWIZZLE_128B, SBO = 1024 B (8 rows x 128 B), advanced by 32 B per
+// K=16 step inside the swizzle atom (the CUTLASS/DeepGEMM canonical layout).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "gemm_tc.cuh"
+
+namespace tb {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;           // 64 bf16 = 128 bytes = one swizzle atom row
+constexpr int kStages = 4;
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KB
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LAB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LAB_DONE_%=;\n"
+      "bra LAB_WAIT_%=;\n"
+      "LAB_DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_128B: start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 | version(1)<<46 | layout(2)<<61
+  return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep, int M,
+               int N, int K) {
+  constexpr uint32_t B_BYTES = BLOCK_N * kBlockK * 2;
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  const uint32_t sA = base, sB = base + kStages * kABytes;
+  const uint32_t bars = sB + kStages * B_BYTES;                  // full[4], empty[4], tmem_full
+  const uint32_t tmem_slot = bars + 8 * (2 * kStages + 1);
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (kStages + s); };
+  const uint32_t tmem_full = bars + 8u * (2 * kStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * kBlockM;
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty(stage), phase ^ 1);
+        mbar_expect_tx(full(stage), kABytes + B_BYTES);
+        tma_load_2d(sA + stage * kABytes, &tmA, full(stage), kb * kBlockK, m0);
+        tma_load_2d(sB + stage * B_BYTES, &tmB, full(stage), kb * kBlockK, n0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3, M>>4
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(kBlockM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full(stage), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t da = make_smem_desc(sA + stage * kABytes + k * 32);
+          const uint64_t db = make_smem_desc(sB + stage * B_BYTES + k * 32);
+          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty(stage));  // slot free once these MMAs have read it
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);       // accumulator complete
+    }
+  } else {
+    const int quarter = warp & 3;   // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int64_t r = int64_t(m0) + quarter * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), v);
+      if (r < M) {
+        const int nbase = n0 + c0;
+        float o[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) * ep.scale;
+          const int n = nbase + j;
+          if (ep.bias && n < N) x += ep.bias[n];
+          if (ep.relu) x = fmaxf(x, 0.0f);
+          if (ep.mask && n < N) x = (ep.mask[r * ep.ldmask + n] > 0.0f) ? x : 0.0f;
+          o[j] = x;
+        }
+        if (ep.C) {
+          float* c = ep.C + r * ep.ldc + nbase;
+          if (nbase + 32 <= N && (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (nbase + j < N) c[j] = o[j];
+          }
+        }
+        if (ep.C16) {
+          __nv_bfloat16* c = ep.C16 + r * ep.ldc16 + nbase;
+          if (nbase + 32 <= N && (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+              *reinterpret_cast<uint4*>(c + j) = pk;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (nbase + j < N) c[j] = __float2bfloat16_rn(o[j]);
+          }
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  TB_REQUIRE(fn, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+  TB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0,
+             "gemm_tc: operand must be 16-byte aligned with a leading dimension that is a multiple of 8 (ld=%lld)",
+             (long long)ld);
+  cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t gstride[1] = {cuuint64_t(ld) * 2};
+  cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TB_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", int(r),
+             (long long)rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K,
+           cudaStream_t stream) {
+  constexpr size_t smem = 1024 + kStages * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kStages + 1) + 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((unsigned)((N + BLOCK_N - 1) / BLOCK_N), (unsigned)((M + kBlockM - 1) / kBlockM));
+  gemm_tc_kernel<BLOCK_N><<<grid, kThreads, smem, stream>>>(a, b, ep, int(M), int(N), int(K));
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace
+
+int gemm_tc_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                 const TcEpilogue& ep, cudaStream_t stream) {
+  TB_REQUIRE(M >= 0 && N >= 0 && K >= 1, "gemm_tc: bad sizes M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  if (M == 0 || N == 0) return 0;
+  TB_REQUIRE(A && B && (ep.C || ep.C16), "gemm_tc: null pointer");
+  TB_REQUIRE(M < (int64_t(1) << 31) && N < (int64_t(1) << 31) && K < (int64_t(1) << 31), "gemm_tc: size overflow");
+  ProfScope prof(ep.tag, stream);
+  const int bn = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, M, K, lda, kBlockM);
+  if (rc) return rc;
+  rc = make_map(&mb, B, N, K, ldb, bn);
+  if (rc) return rc;
+  if (bn == 32) return launch<32>(ma, mb, ep, M, N, K, stream);
+  if (bn == 64) return launch<64>(ma, mb, ep, M, N, K, stream);
+  return launch<128>(ma, mb, ep, M, N, K, stream);
+}
+
+// fp32 [rows, cols] (ld) -> bf16 [rows, cols16] (ld16), optional ReLU-free straight convert
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows,
+                                   int64_t cols, int64_t ld, int64_t ld16) {
+  const int64_t total = rows * ld16;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / ld16, c = i % ld16;
+    out[i] = __float2bfloat16_rn(c < cols ? in[r * ld + c] : 0.0f);
+  }
+}
+
+int f32_to_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, cudaStream_t stream) {
+  const int64_t total = rows * ld16;
+  if (total == 0) return 0;
+  ProfScope prof("f32_to_bf16", stream);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMsB200 * 16) blocks = kNumSMsB200 * 16;
+  f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), rows, cols, ld, ld16);
+  return check_launch("f32_to_bf16_kernel");
+}
+
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int tb_gemm_bf16_tn(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                    float* C, int64_t ldc, void* C_bf16, int64_t ldc16, const float* bias, float scale, int relu,
+                    void* stream) {
+  TcEpilogue ep;
+  ep.C = C; ep.ldc = ldc; ep.C16 = static_cast<__nv_bfloat16*>(C_bf16); ep.ldc16 = ldc16; ep.bias = bias;
+  ep.scale = scale; ep.relu = relu; ep.tag = "gemm_bf16_tn";
+  return gemm_tc_bf16(A_bf16, B_bf16, M, N, K, lda, ldb, ep, (cudaStream_t)stream);
+}
+
+int tb_f32_to_bf16(const float* in, void* out_bf16, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, void* stream) {
+  TB_REQUIRE(in && out_bf16, "tb_f32_to_bf16: null pointer");
+  return f32_to_bf16(in, out_bf16, rows, cols, ld, ld16, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,26 @@
+// bf16 tcgen05 GEMM (see gemm_tc.cu): host interface.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace tb {
+
+struct TcEpilogue {
+  float* C = nullptr; int64_t ldc = 0;               // fp32 output (nullable)
+  __nv_bfloat16* C16 = nullptr; int64_t ldc16 = 0;   // bf16 output (nullable) - next GEMM's operand
+  const float* bias = nullptr;                       // [N]
+  float scale = 1.0f;                                // applied to the accumulator first (1/255 for uint8 frames)
+  int relu = 0;
+  const float* mask = nullptr; int64_t ldmask = 0;   // out = (mask > 0) ? out : 0   (ReLU backward)
+  const char* tag = "gemm_tc";
+};
+
+// C[M,N] = epilogue(A[M,K] . B[N,K]^T); A, B bf16 with K contiguous, lda/ldb multiples of 8,
+// 16-byte aligned bases.
+int gemm_tc_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                 const TcEpilogue& ep, cudaStream_t stream);
+
+int f32_to_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, cudaStream_t stream);
+
+}  // namespace tb
