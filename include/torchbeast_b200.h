@@ -122,24 +122,27 @@ int tb_pg_loss_f64(const double* logits, const int64_t* actions, const double* a
 int64_t tb_atarinet_param_count(int num_actions, int use_lstm);
 /* Bytes of caller-owned workspace for a [T1,B] rollout (T1 = unroll_length + 1): patch matrices,
  * activations kept for backward, packed weights, split-K scratch.                            */
-size_t tb_atarinet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm);
+size_t tb_atarinet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm, int precision);
 
 /* monobeast.py:582-632 AtariNet.forward (without the action sampling, which the learner never
  * uses - SURVEY.md K8).  frame u8 [T1,B,4,84,84]; reward f32 [T1,B]; last_action i64 [T1,B];
  * notdone f32 [T1,B] = (~done).float() (LSTM only; multiplies the state before each step,
  * monobeast.py:607-609); h0,c0 / hN,cN f32 [2,B,519] (LSTM only).
- * -> policy_logits f32 [T1,B,A], baseline f32 [T1,B].  Activations stay in `workspace`.      */
+ * -> policy_logits f32 [T1,B,A], baseline f32 [T1,B].  Activations stay in `workspace`.
+ * precision: 0 = fp32 SIMT GEMMs (bit-comparable with the reference's fp32 CPU arithmetic);
+ *            1 = bf16 operands on tcgen05 tensor cores with fp32 accumulation (conv/fc trunk and the
+ *                LSTM projections; recurrence, heads, losses, optimizer stay fp32).              */
 int tb_atarinet_forward(const uint8_t* frame, const float* reward, const float* notdone,
                         const int64_t* last_action, const float* h0, const float* c0,
                         const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
-                        void* workspace, float* policy_logits, float* baseline, float* hN, float* cN,
-                        void* stream);
+                        int precision, void* workspace, float* policy_logits, float* baseline, float* hN,
+                        float* cN, void* stream);
 /* Backward of the above (replaces the autograd graph of total_loss.backward(), monobeast.py:290):
  * grad_logits [T1,B,A], grad_baseline [T1,B] -> grads (flat, parameter layout, overwritten).
  * Must follow a tb_atarinet_forward on the same workspace and parameters.                    */
 int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
                          const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
-                         void* workspace, float* grads, void* stream);
+                         int precision, void* workspace, float* grads, void* stream);
 
 /* ---- flat-buffer optimizer step ------------------------------------------------------------ */
 
@@ -164,6 +167,13 @@ int tb_clip_rmsprop_step_f32(float* params, float* grads, float* square_avg, flo
 int tb_gemm_bf16_tn(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, int64_t lda,
                     int64_t ldb, float* C, int64_t ldc, void* C_bf16, int64_t ldc16, const float* bias,
                     float scale, int relu, void* stream);
+/* General operand layouts of the same kernel: a_mn / b_mn != 0 mark an operand stored with the
+ * REDUCTION index as its row index (A as [K,M], B as [K,N], row-major) - the dgrad (b_mn) and wgrad
+ * (a_mn and b_mn) forms, so no transposed copies are needed.  splits > 1 reduces K over grid.z through
+ * `partial` (splits*M*N floats) with a fixed-order second pass.  C fp32 [M,N] (ldc).            */
+int tb_gemm_bf16_ex(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, int64_t lda,
+                    int64_t ldb, int a_mn, int b_mn, float* C, int64_t ldc, int splits, float* partial,
+                    void* stream);
 /* out_bf16[r, c] = bf16(in[r*ld + c]) for c < cols, 0 for cols <= c < ld16 (operand staging). */
 int tb_f32_to_bf16(const float* in, void* out_bf16, int64_t rows, int64_t cols, int64_t ld, int64_t ld16,
                    void* stream);

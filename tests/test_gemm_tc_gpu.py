@@ -56,3 +56,29 @@ def test_f32_to_bf16_padding():
     out = torch.full((37, 520), 7.0, device="cuda", dtype=torch.bfloat16)
     _lib.check(_lib.lib().tb_f32_to_bf16(_lib.ptr(x), _lib.ptr(out), 37, 519, 519, 520, _lib.stream_ptr()), "cvt")
     assert torch.equal(out[:, :519], x.to(torch.bfloat16)) and float(out[:, 519].abs().sum()) == 0.0
+
+
+EX_SHAPES = [(128, 64, 64), (128, 128, 128), (256, 64, 512), (1000, 512, 64), (300, 576, 64), (64, 256, 4096),
+             (32, 256, 20000), (512, 3136, 2592), (2076, 520, 2592), (6, 520, 2592), (129, 70 * 8, 200)]
+
+
+@pytest.mark.parametrize("M,N,K", EX_SHAPES)
+@pytest.mark.parametrize("mode", ["dgrad", "wgrad", "wgrad_splitk"])
+def test_gemm_tc_mn_major_operands(M, N, K, mode):
+    """dgrad form (A K-major, B stored [K,N]) and wgrad form (A stored [K,M], B stored [K,N])."""
+    from torchbeast_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a_mn = mode != "dgrad"
+    if (N % 8) or (a_mn and M % 8) or ((not a_mn) and K % 8):
+        pytest.skip("leading dimensions must be multiples of 8")
+    A = torch.randn((K, M) if a_mn else (M, K), device="cuda", generator=g).to(torch.bfloat16)
+    B = torch.randn(K, N, device="cuda", generator=g).to(torch.bfloat16)
+    C = torch.full((M, N), float("nan"), device="cuda")
+    splits = 7 if mode == "wgrad_splitk" else 1
+    part = torch.empty(splits * M * N, device="cuda") if splits > 1 else None
+    p = _lib.ptr
+    rc = _lib.lib().tb_gemm_bf16_ex(p(A), p(B), M, N, K, A.shape[1], N, int(a_mn), 1, p(C), N, splits, p(part), _lib.stream_ptr())
+    _lib.check(rc, "tb_gemm_bf16_ex")
+    torch.cuda.synchronize()
+    ref = (A.float().t() if a_mn else A.float()) @ B.float()
+    torch.testing.assert_close(C, ref, rtol=1e-4, atol=1e-4 * np.sqrt(K))

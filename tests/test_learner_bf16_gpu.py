@@ -1,0 +1,61 @@
+"""GPU: the bf16 tensor-core backend (precision="bf16": tcgen05 GEMMs with bf16 operands and fp32
+accumulation for the conv/fc trunk and the LSTM projections) against the fp64 oracle.
+bf16 carries 8 mantissa bits (unit roundoff 2^-9 ~ 2e-3), so this is a mixed-precision tolerance,
+stated per quantity: learner outputs relative L2 error < 1e-2, losses rtol 2e-2, every parameter
+gradient relative L2 error < 6e-2 and cosine similarity > 0.998 (the fp32 backend holds the tight
+parity contract in test_learner_gpu.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import learner_torch as LT
+from tests.test_learner_gpu import build_case, flags_for, to_cuda
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["learn_atari_T4_B2.npz", "learn_atari_T20_B4.npz", "learn_atari_lstm_T4_B2.npz", "learn_atari_lstm_T20_B4.npz"]
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("fname", CASES)
+def test_bf16_forward_and_gradients_vs_oracle(fname):
+    from torchbeast_b200 import learner
+    g, model, actor, batch, params, state, opt, sched = build_case(fname, precision="bf16")
+    p64 = {k: v.double() for k, v in params.items()}
+    o = LT.learner_step(p64, batch, tuple(s.double() for s in state), net="atari", update=False)
+    cb = to_cuda(batch)
+    out = model.learner_forward(cb, tuple(s.cuda() for s in state))
+    assert rel(out.policy_logits.cpu().double(), o["policy_logits"]) < 1e-2
+    assert rel(out.baseline.cpu().double(), o["baseline"]) < 1e-2
+    loss = learner.impala_loss_fwd_bwd(cb["policy_logits"][1:], out.policy_logits[:-1], cb["action"][1:], cb["reward"][1:],
+                                       cb["done"][1:], out.baseline[:-1], out.baseline[-1])
+    model.learner_backward(loss.grad_logits, loss.grad_values)
+    np.testing.assert_allclose(float(loss.losses[1]), float(o["baseline_loss"]), rtol=2e-2)
+    np.testing.assert_allclose(float(loss.losses[2]), float(o["entropy_loss"]), rtol=2e-2)
+    np.testing.assert_allclose(float(loss.losses[3]), float(o["total_loss"]), rtol=2e-2, atol=2e-2 * float(o["baseline_loss"]))
+    for n, p in model.named_parameters():
+        ref = o["grads"][n]
+        got = p.grad.cpu().double()
+        cos = float((got * ref).sum() / (got.norm() * ref.norm()).clamp_min(1e-30))
+        assert rel(got, ref) < 6e-2, (n, rel(got, ref))
+        assert cos > 0.998, (n, cos)
+
+
+@pytest.mark.parametrize("fname", ["learn_atari_T20_B4.npz", "learn_atari_lstm_T20_B4.npz"])
+def test_bf16_learn_step_runs_and_is_deterministic(fname):
+    from torchbeast_b200 import monobeast
+    outs = []
+    for _ in range(2):
+        g, model, actor, batch, params, state, opt, sched = build_case(fname, precision="bf16")
+        flags = flags_for(g)
+        cb = to_cuda(batch)
+        st = tuple(s.cuda() for s in state)
+        s1 = monobeast.learn(flags, actor, model, cb, st, opt, sched)
+        s2 = monobeast.learn(flags, actor, model, cb, st, opt, sched)
+        np.testing.assert_allclose(s1["total_loss"], float(g["total_loss"]), rtol=3e-2, atol=0.5)
+        outs.append((s1["total_loss"], s2["total_loss"], model.flat_params.clone()))
+        assert torch.equal(actor.flat_params, model.flat_params)
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and torch.equal(outs[0][2], outs[1][2])

@@ -1,7 +1,8 @@
 """GPU parity of the network + full learn() step (torchbeast_b200.monobeast) against
  (a) golden fixtures produced by the reference's own monobeast.learn (tests/golden/learn_*.npz),
  (b) the torch-CPU oracle (oracle/learner_torch.py) tensor by tensor.
-Tolerances (fp32 backend): forward outputs rtol 1e-4 / atol 1e-4 (north_star 1e-4 fp32); scalar
+All cases here run the fp32 backend (precision="fp32"); the bf16 tensor-core backend has its own file
+(test_learner_bf16_gpu.py).  Tolerances (fp32 backend): forward outputs rtol 1e-4 / atol 1e-4 (north_star 1e-4 fp32); scalar
 losses rtol 2e-5; gradients rtol 2e-3 with an absolute floor of 2e-4 x the tensor's norm (different
 summation order over up to 1e6-term reductions)."""
 import types
@@ -30,14 +31,14 @@ def flags_for(g):
         grad_norm_clipping=float(g["clip"]), unroll_length=int(g["meta"][0]), batch_size=int(g["meta"][1]))
 
 
-def build_case(fname):
+def build_case(fname, precision="fp32"):
     from torchbeast_b200 import monobeast, optim
     g = golden(fname)
     T, B, A, seed, use_lstm = [int(x) for x in g["meta"]]
     batch = LT.synthetic_batch(T, B, A, seed=seed)
     params = LT.random_params(LT.atarinet_param_shapes(A, bool(use_lstm)), seed=seed + 100)
-    model = monobeast.AtariNet((4, 84, 84), A, bool(use_lstm))
-    actor = monobeast.AtariNet((4, 84, 84), A, bool(use_lstm))
+    model = monobeast.AtariNet((4, 84, 84), A, bool(use_lstm), precision=precision)
+    actor = monobeast.AtariNet((4, 84, 84), A, bool(use_lstm), precision=precision)
     res = model.load_state_dict(params, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
     state = ()

@@ -11,6 +11,7 @@
 // buffer and are re-packed per step into GEMM order (tiny); weight gradients are un-packed into
 // the same flat layout by the split-K reduction so a flat optimizer / all-reduce can run on them.
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "lstm.cuh"
 #include "net_kernels.cuh"
 
@@ -70,11 +71,14 @@ struct AtariWs {  // bump-carved view of the caller's workspace
   float *w2p, *w3p, *wfcp;
   float *dcore_out, *dcore_in, *dact3, *dcol3, *dact2, *dcol2, *dact1;
   float *splitk, *colsum_scratch;
+  // bf16 tensor-core backend (precision 1): operands / activations in bf16
+  void *col1b, *act1b, *col2b, *act2b, *col3b, *act3b, *w1b, *w2b, *w3b, *wfcb;
+  void *dfcb, *dact3b, *dcol3b, *dact2b, *dcol2b, *dact1b;
   LstmWs lstm;
   size_t bytes;
 };
 
-static AtariWs atari_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lstm) {
+static AtariWs atari_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lstm, int precision) {
   using G = AtariGeom;
   AtariWs w;
   size_t off = 0;
@@ -85,23 +89,34 @@ static AtariWs atari_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int
   };
   const AtariParams pp = atari_params(A, use_lstm);
   const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
-  w.col1 = static_cast<uint8_t*>(take(size_t(M1) * G::KD1));
   auto takef = [&](int64_t n) { return static_cast<float*>(take(size_t(n) * sizeof(float))); };
-  w.act1 = takef(M1 * G::C1); w.col2 = takef(M2 * G::KD2); w.act2 = takef(M2 * G::C2);
-  w.col3 = takef(M3 * G::KD3); w.act3 = takef(N * G::FC_IN);
+  auto takeh = [&](int64_t n) { return take(size_t(n) * 2); };  // bf16
+  w = AtariWs();
   w.core_in = takef(N * pp.core);
   w.core_out = use_lstm ? takef(N * pp.core) : w.core_in;
-  w.w2p = takef(int64_t(G::C2) * G::KD2); w.w3p = takef(int64_t(G::C3) * G::KD3);
-  w.wfcp = takef(int64_t(G::FC_OUT) * G::FC_IN);
   w.dcore_out = takef(N * pp.core);
   w.dcore_in = use_lstm ? takef(N * pp.core) : w.dcore_out;
-  w.dact3 = takef(N * G::FC_IN); w.dcol3 = takef(M3 * G::KD3); w.dact2 = takef(M2 * G::C2);
-  w.dcol2 = takef(M2 * G::KD2); w.dact1 = takef(M1 * G::C1);
+  if (!precision) {
+    w.col1 = static_cast<uint8_t*>(take(size_t(M1) * G::KD1));
+    w.act1 = takef(M1 * G::C1); w.col2 = takef(M2 * G::KD2); w.act2 = takef(M2 * G::C2);
+    w.col3 = takef(M3 * G::KD3); w.act3 = takef(N * G::FC_IN);
+    w.w2p = takef(int64_t(G::C2) * G::KD2); w.w3p = takef(int64_t(G::C3) * G::KD3);
+    w.wfcp = takef(int64_t(G::FC_OUT) * G::FC_IN);
+    w.dact3 = takef(N * G::FC_IN); w.dcol3 = takef(M3 * G::KD3); w.dact2 = takef(M2 * G::C2);
+    w.dcol2 = takef(M2 * G::KD2); w.dact1 = takef(M1 * G::C1);
+  } else {
+    w.col1b = takeh(M1 * G::KD1); w.act1b = takeh(M1 * G::C1); w.col2b = takeh(M2 * G::KD2); w.act2b = takeh(M2 * G::C2);
+    w.col3b = takeh(M3 * G::KD3); w.act3b = takeh(N * G::FC_IN);
+    w.w1b = takeh(int64_t(G::C1) * G::KD1); w.w2b = takeh(int64_t(G::C2) * G::KD2); w.w3b = takeh(int64_t(G::C3) * G::KD3);
+    w.wfcb = takeh(int64_t(G::FC_OUT) * G::FC_IN);
+    w.dfcb = takeh(N * G::FC_OUT); w.dact3b = takeh(N * G::FC_IN); w.dcol3b = takeh(M3 * G::KD3);
+    w.dact2b = takeh(M2 * G::C2); w.dcol2b = takeh(M2 * G::KD2); w.dact1b = takeh(M1 * G::C1);
+  }
   w.splitk = takef(kSplitKScratchFloats);
   w.colsum_scratch = takef(colsum_scratch_floats(4 * int64_t(pp.core) > 512 ? 4 * int64_t(pp.core) : 512));
   if (use_lstm) {
-    size_t lbytes = lstm_ws_bytes(T1, B, pp.core, pp.core, 2);
-    w.lstm = lstm_ws(take(lbytes), T1, B, pp.core, pp.core, 2);
+    size_t lbytes = lstm_ws_bytes(T1, B, pp.core, pp.core, 2, precision);
+    w.lstm = lstm_ws(take(lbytes), T1, B, pp.core, pp.core, 2, precision);
   } else {
     w.lstm = LstmWs();
   }
@@ -133,14 +148,36 @@ static int pick_splits(int64_t M, int64_t N, int64_t K) {
 // ---------------------------------------------------------------------------------------
 static int atarinet_forward(const uint8_t* frame, const float* reward, const float* notdone,
                             const int64_t* last_action, const float* h0, const float* c0, const float* P,
-                            int64_t T1, int64_t B, int A, int use_lstm, void* workspace, float* policy_logits,
-                            float* baseline, float* hN, float* cN, cudaStream_t st) {
+                            int64_t T1, int64_t B, int A, int use_lstm, int precision, void* workspace,
+                            float* policy_logits, float* baseline, float* hN, float* cN, cudaStream_t st) {
   using G = AtariGeom;
   const int64_t N = T1 * B;
   const AtariParams pp = atari_params(A, use_lstm);
-  AtariWs w = atari_ws(workspace, N, T1, B, A, use_lstm);
+  AtariWs w = atari_ws(workspace, N, T1, B, A, use_lstm, precision);
   const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
   GemmEpilogue ep;
+  if (precision) {
+    // ---- bf16 tensor-core trunk: tcgen05 GEMMs, bf16 activations, fp32 accumulation ----
+    TB_TRY(pack_weights_bf16(P + pp.conv1_w, w.w1b, G::C1, 1, G::KD1, G::KD1, st));
+    TB_TRY(pack_weights_bf16(P + pp.conv2_w, w.w2b, G::C2, G::K2 * G::K2, G::C1, G::KD2, st));
+    TB_TRY(pack_weights_bf16(P + pp.conv3_w, w.w3b, G::C3, G::K3 * G::K3, G::C2, G::KD3, st));
+    TB_TRY(pack_weights_bf16(P + pp.fc_w, w.wfcb, G::FC_OUT, G::H3 * G::W3, G::C3, G::FC_IN, st));
+    TB_TRY(im2col_u8_nchw_bf16(frame, w.col1b, N, G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, st));
+    TcEpilogue te;
+    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act1b); te.ldc16 = G::C1; te.bias = P + pp.conv1_b;
+    te.scale = 1.0f / 255.0f; te.relu = 1; te.tag = "conv1_fwd";
+    TB_TRY(gemm_tc_bf16(w.col1b, w.w1b, M1, G::C1, G::KD1, G::KD1, G::KD1, te, st));
+    TB_TRY(im2col_bf16_nhwc(w.act1b, w.col2b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
+    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act2b); te.ldc16 = G::C2; te.bias = P + pp.conv2_b;
+    te.relu = 1; te.tag = "conv2_fwd";
+    TB_TRY(gemm_tc_bf16(w.col2b, w.w2b, M2, G::C2, G::KD2, G::KD2, G::KD2, te, st));
+    TB_TRY(im2col_bf16_nhwc(w.act2b, w.col3b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
+    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act3b); te.ldc16 = G::C3; te.bias = P + pp.conv3_b;
+    te.relu = 1; te.tag = "conv3_fwd";
+    TB_TRY(gemm_tc_bf16(w.col3b, w.w3b, M3, G::C3, G::KD3, G::KD3, G::KD3, te, st));
+    te = TcEpilogue(); te.C = w.core_in; te.ldc = pp.core; te.bias = P + pp.fc_b; te.relu = 1; te.tag = "fc_fwd";
+    TB_TRY(gemm_tc_bf16(w.act3b, w.wfcb, N, G::FC_OUT, G::FC_IN, G::FC_IN, G::FC_IN, te, st));
+  } else {
   // weight pack: [o, c, kh, kw] -> [o, (kh,kw), c];  fc: [o, c, (h,w)] -> [o, (h,w), c]
   TB_TRY(permute_pq(P + pp.conv2_w, w.w2p, G::C2, G::K2 * G::K2, G::C1, st));
   TB_TRY(permute_pq(P + pp.conv3_w, w.w3p, G::C3, G::K3 * G::K3, G::C2, st));
@@ -164,6 +201,7 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
   ep = GemmEpilogue(); ep.bias = P + pp.fc_b; ep.relu = 1; ep.tag = "fc_fwd";
   TB_TRY((gemm_simt<float, float, false, true>(w.act3, w.wfcp, w.core_in, N, G::FC_OUT, G::FC_IN, G::FC_IN, G::FC_IN,
                                                 pp.core, ep, 1, nullptr, st)));
+  }
   TB_TRY(core_extras(w.core_in, pp.core, N, G::FC_OUT, reward, last_action, A, st));
   if (use_lstm) {
     LstmParams lp;
@@ -172,7 +210,7 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
       lp.b_ih[l] = P + pp.lstm[l][2]; lp.b_hh[l] = P + pp.lstm[l][3];
     }
     TB_TRY(lstm_forward(w.core_in, notdone, h0, c0, lp, T1, B, pp.core, pp.core, 2, w.lstm, w.core_out, hN, cN,
-                        w.splitk, st));
+                        w.splitk, precision, st));
   }
   // heads
   ep = GemmEpilogue(); ep.bias = P + pp.policy_b; ep.tag = "heads_fwd";
@@ -200,13 +238,71 @@ static int wgrad(const float* dY, int64_t ldy, const void* X, bool x_is_u8, int6
                                                ep, splits, w.splitk, st);
 }
 
+
+// bf16 tensor-core backward of the conv/fc trunk.  dgrad: B operand = the packed weights as stored
+// (MN-major); wgrad: A = dY, B = patch matrix, both as stored (MN-major), split-K over grid.z with the
+// fixed-order reduce un-packing into the state_dict layout.
+static int tc_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t bn = N <= 64 ? 64 : 128;
+  const int64_t tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  const int64_t kb = (K + 63) / 64;
+  int64_t s = (2 * kNumSMsB200 + tiles - 1) / tiles;
+  if (s > kb / 4) s = kb / 4;
+  if (s * M * N > kSplitKScratchFloats) s = kSplitKScratchFloats / (M * N);
+  if (s > 148) s = 148;
+  if (s < 1) s = 1;
+  return int(s);
+}
+
+static int tc_wgrad(const void* dYb, int64_t ldy, const void* Xb, int64_t ldx, float* dW, int64_t rows, int64_t nout,
+                    int64_t kin, int permP, int permQ, float scale, AtariWs& w, cudaStream_t st, const char* tag) {
+  TcEpilogue te;
+  te.C = dW; te.ldc = kin; te.permP = permP; te.permQ = permQ; te.scale = scale; te.tag = tag;
+  return gemm_tc_bf16_ex(dYb, Xb, nout, kin, rows, ldy, ldx, true, true, te, tc_splits(nout, kin, rows), w.splitk, st);
+}
+
+static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariParams& pp, AtariWs& w, int64_t N,
+                                        cudaStream_t st) {
+  using G = AtariGeom;
+  const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
+  // fc: ReLU mask (fp32, in place), bias grad, bf16 copy of dY
+  TB_TRY(relu_mask_inplace(w.dcore_in, w.core_in, N, G::FC_OUT, pp.core, pp.core, st));
+  TB_TRY(colsum(w.dcore_in, G_ + pp.fc_b, N, G::FC_OUT, pp.core, w.colsum_scratch, st));
+  TB_TRY(f32_to_bf16(w.dcore_in, w.dfcb, N, G::FC_OUT, pp.core, G::FC_OUT, st));
+  TB_TRY(tc_wgrad(w.dfcb, G::FC_OUT, w.act3b, G::FC_IN, G_ + pp.fc_w, N, G::FC_OUT, G::FC_IN, G::H3 * G::W3, G::C3, 1.0f, w,
+                  st, "fc_wgrad"));
+  TcEpilogue te;
+  te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dact3b); te.ldc16 = G::FC_IN;
+  te.mask16 = static_cast<const __nv_bfloat16*>(w.act3b); te.ldmask = G::FC_IN; te.tag = "fc_dgrad";
+  TB_TRY(gemm_tc_bf16_ex(w.dfcb, w.wfcb, N, G::FC_IN, G::FC_OUT, G::FC_OUT, G::FC_IN, false, true, te, 1, nullptr, st));
+  // conv3 (dact3b viewed as [M3, 64])
+  TB_TRY(tc_wgrad(w.dact3b, G::C3, w.col3b, G::KD3, G_ + pp.conv3_w, M3, G::C3, G::KD3, G::K3 * G::K3, G::C2, 1.0f, w, st,
+                  "conv3_wgrad"));
+  TB_TRY(colsum_bf16(w.dact3b, G_ + pp.conv3_b, M3, G::C3, G::C3, w.colsum_scratch, st));
+  te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol3b); te.ldc16 = G::KD3; te.tag = "conv3_dgrad";
+  TB_TRY(gemm_tc_bf16_ex(w.dact3b, w.w3b, M3, G::KD3, G::C3, G::C3, G::KD3, false, true, te, 1, nullptr, st));
+  TB_TRY(col2im_bf16_nhwc(w.dcol3b, w.act2b, w.dact2b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
+  // conv2
+  TB_TRY(tc_wgrad(w.dact2b, G::C2, w.col2b, G::KD2, G_ + pp.conv2_w, M2, G::C2, G::KD2, G::K2 * G::K2, G::C1, 1.0f, w, st,
+                  "conv2_wgrad"));
+  TB_TRY(colsum_bf16(w.dact2b, G_ + pp.conv2_b, M2, G::C2, G::C2, w.colsum_scratch, st));
+  te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol2b); te.ldc16 = G::KD2; te.tag = "conv2_dgrad";
+  TB_TRY(gemm_tc_bf16_ex(w.dact2b, w.w2b, M2, G::KD2, G::C2, G::C2, G::KD2, false, true, te, 1, nullptr, st));
+  TB_TRY(col2im_bf16_nhwc(w.dcol2b, w.act1b, w.dact1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
+  // conv1: the patch matrix holds raw pixel values, so the weight gradient carries the 1/255
+  TB_TRY(tc_wgrad(w.dact1b, G::C1, w.col1b, G::KD1, G_ + pp.conv1_w, M1, G::C1, G::KD1, 1, 1, 1.0f / 255.0f, w, st,
+                  "conv1_wgrad"));
+  TB_TRY(colsum_bf16(w.dact1b, G_ + pp.conv1_b, M1, G::C1, G::C1, w.colsum_scratch, st));
+  return 0;
+}
+
 static int atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
-                             const float* P, int64_t T1, int64_t B, int A, int use_lstm, void* workspace, float* G_,
-                             cudaStream_t st) {
+                             const float* P, int64_t T1, int64_t B, int A, int use_lstm, int precision,
+                             void* workspace, float* G_, cudaStream_t st) {
   using G = AtariGeom;
   const int64_t N = T1 * B;
   const AtariParams pp = atari_params(A, use_lstm);
-  AtariWs w = atari_ws(workspace, N, T1, B, A, use_lstm);
+  AtariWs w = atari_ws(workspace, N, T1, B, A, use_lstm, precision);
   const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
   GemmEpilogue ep;
   // heads: dcore_out = dlogits . Wp + dbaseline . Wb ; dWp, dbp, dWb, dbb
@@ -229,8 +325,9 @@ static int atarinet_backward(const float* grad_logits, const float* grad_baselin
       lg.b_ih[l] = G_ + pp.lstm[l][2]; lg.b_hh[l] = G_ + pp.lstm[l][3];
     }
     TB_TRY(lstm_backward(w.dcore_out, w.core_in, notdone, lp, lg, T1, B, pp.core, pp.core, 2, w.lstm, w.dcore_in,
-                         w.splitk, w.colsum_scratch, st));
+                         w.splitk, w.colsum_scratch, precision, st));
   }
+  if (precision) return atarinet_backward_trunk_bf16(P, G_, pp, w, N, st);
   // fc: ReLU mask on the first 512 columns, wgrad (un-packed into [o, c, (h,w)]), bias, dgrad (+ReLU mask of act3)
   TB_TRY(relu_mask_inplace(w.dcore_in, w.core_in, N, G::FC_OUT, pp.core, pp.core, st));
   TB_TRY(wgrad(w.dcore_in, pp.core, w.act3, false, G::FC_IN, G_ + pp.fc_w, N, G::FC_OUT, G::FC_IN, G::H3 * G::W3,
@@ -272,31 +369,32 @@ int64_t tb_atarinet_param_count(int num_actions, int use_lstm) {
   return atari_params(num_actions, use_lstm).total;
 }
 
-size_t tb_atarinet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm) {
-  return atari_ws(nullptr, T1 * B, T1, B, num_actions, use_lstm).bytes;
+size_t tb_atarinet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm, int precision) {
+  return atari_ws(nullptr, T1 * B, T1, B, num_actions, use_lstm, precision).bytes;
 }
 
 int tb_atarinet_forward(const uint8_t* frame, const float* reward, const float* notdone, const int64_t* last_action,
                         const float* h0, const float* c0, const float* params, int64_t T1, int64_t B,
-                        int num_actions, int use_lstm, void* workspace, float* policy_logits, float* baseline,
-                        float* hN, float* cN, void* stream) {
+                        int num_actions, int use_lstm, int precision, void* workspace, float* policy_logits,
+                        float* baseline, float* hN, float* cN, void* stream) {
   TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "atarinet_forward: bad sizes T1=%lld B=%lld A=%d", (long long)T1,
              (long long)B, num_actions);
   TB_REQUIRE(frame && reward && last_action && params && workspace && policy_logits && baseline,
              "atarinet_forward: null pointer");
   TB_REQUIRE(!use_lstm || (notdone && h0 && c0 && hN && cN), "atarinet_forward: LSTM needs notdone/h0/c0/hN/cN");
-  return atarinet_forward(frame, reward, notdone, last_action, h0, c0, params, T1, B, num_actions, use_lstm, workspace,
-                          policy_logits, baseline, hN, cN, (cudaStream_t)stream);
+  TB_REQUIRE(precision == 0 || precision == 1, "atarinet_forward: precision must be 0 (fp32) or 1 (bf16 tensor cores)");
+  return atarinet_forward(frame, reward, notdone, last_action, h0, c0, params, T1, B, num_actions, use_lstm, precision,
+                          workspace, policy_logits, baseline, hN, cN, (cudaStream_t)stream);
 }
 
 int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
-                         const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm, void* workspace,
-                         float* grads, void* stream) {
+                         const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm, int precision,
+                         void* workspace, float* grads, void* stream) {
   TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "atarinet_backward: bad sizes");
   TB_REQUIRE(grad_logits && grad_baseline && params && workspace && grads, "atarinet_backward: null pointer");
   TB_REQUIRE(!use_lstm || notdone, "atarinet_backward: LSTM needs notdone");
-  return atarinet_backward(grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm, workspace, grads,
-                           (cudaStream_t)stream);
+  return atarinet_backward(grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm, precision, workspace,
+                           grads, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* _
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     float v = 0.0f;
     for (int z = 0; z < splits; ++z) v += partial[int64_t(z) * total + i];
+    v *= ep.scale;
     const int64_t m = i / N, n = i % N;
     if (ep.bias) v += ep.bias[n];
     if (ep.relu) v = fmaxf(v, 0.0f);

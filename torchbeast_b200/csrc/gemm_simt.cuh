@@ -25,6 +25,7 @@ struct GemmEpilogue {
   int accumulate = 0;            // C += acc
   // split-K reduce only: output column permutation n = p*Q + q  ->  q*P + p (weight-grad unpack)
   int permP = 1, permQ = 1;
+  float scale = 1.0f;            // (split-K reduce only) multiplies the reduced sum
   const char* tag = "gemm";    // op name reported by the profiler
 };
 

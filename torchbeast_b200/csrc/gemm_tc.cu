@@ -13,10 +13,18 @@
 // M/N/K tails are handled by TMA out-of-bounds zero fill plus guarded stores.  Shared-memory
 // matrix descriptors: K-major, SWIZZLE_128B, SBO = 1024 B (8 rows x 128 B), advanced by 32 B per
 // K=16 step inside the swizzle atom (the CUTLASS/DeepGEMM canonical layout).
+// Operands may also be "MN-major" (the reduction index is the ROW index in memory, A_MN / B_MN):
+// the tile is then loaded as 64(k) x 64(mn) boxes, described with LBO = 8192 B between 64-wide mn
+// groups and SBO = 1024 B between 8-row k groups, advanced by 2048 B per K=16 step.  That gives
+//   forward  act = col . W^T      : A K-major,  B K-major
+//   dgrad    dcol = dY . W        : A K-major,  B MN-major (W [n', k'] as stored)
+//   wgrad    dW   = dY^T . col    : A MN-major, B MN-major (no transposed copies), split-K over grid.z
 #include <cuda.h>
 #include <cuda_bf16.h>
 
 #include "gemm_tc.cuh"
+
+#include "gemm_simt.cuh"  // splitk_reduce_kernel / GemmEpilogue
 
 namespace tb {
 
@@ -58,6 +66,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
          (uint64_t(2) << 61);
 }
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  // MN-major, SWIZZLE_128B: LBO = 8192 B (next 64-wide mn group), SBO = 1024 B (next 8 k rows)
+  return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(8192 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -83,10 +96,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep, int M,
-               int N, int K) {
+               int N, int K, float* partial) {
   constexpr uint32_t B_BYTES = BLOCK_N * kBlockK * 2;
   constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
@@ -100,7 +113,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * kBlockM;
-  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  // split-K: this CTA reduces k-blocks [kb0, kb1)
+  const int total_kb = (K + kBlockK - 1) / kBlockK;
+  const int per = (total_kb + gridDim.z - 1) / gridDim.z;
+  const int kb0 = blockIdx.z * per;
+  const int kb1 = (kb0 + per < total_kb) ? kb0 + per : total_kb;
+  const int num_kb = kb1 > kb0 ? kb1 - kb0 : 0;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
@@ -119,26 +137,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int kc = (kb0 + i) * kBlockK;
         mbar_wait(empty(stage), phase ^ 1);
         mbar_expect_tx(full(stage), kABytes + B_BYTES);
-        tma_load_2d(sA + stage * kABytes, &tmA, full(stage), kb * kBlockK, m0);
-        tma_load_2d(sB + stage * B_BYTES, &tmB, full(stage), kb * kBlockK, n0);
+        if (A_MN) {  // two 64(k) x 64(m) boxes
+          tma_load_2d(sA + stage * kABytes, &tmA, full(stage), m0, kc);
+          tma_load_2d(sA + stage * kABytes + 8192, &tmA, full(stage), m0 + 64, kc);
+        } else {
+          tma_load_2d(sA + stage * kABytes, &tmA, full(stage), kc, m0);
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_2d(sB + stage * B_BYTES + j * 8192, &tmB, full(stage), n0 + 64 * j, kc);
+        } else {
+          tma_load_2d(sB + stage * B_BYTES, &tmB, full(stage), kc, n0);
+        }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3, M>>4
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(kBlockM >> 4) << 24);
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) |
+                                 (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(kBlockM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t da = make_smem_desc(sA + stage * kABytes + k * 32);
-          const uint64_t db = make_smem_desc(sB + stage * B_BYTES + k * 32);
+          const uint64_t da = A_MN ? make_smem_desc_mn(sA + stage * kABytes + k * 2048) : make_smem_desc(sA + stage * kABytes + k * 32);
+          const uint64_t db = B_MN ? make_smem_desc_mn(sB + stage * B_BYTES + k * 2048) : make_smem_desc(sB + stage * B_BYTES + k * 32);
           umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit(empty(stage));  // slot free once these MMAs have read it
@@ -155,6 +186,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), v);
+      if (num_kb == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0u;  // nothing was accumulated (empty split)
+      }
+      if (partial) {  // split-K: raw partial tile [z][M][N]; splitk_reduce_kernel applies the epilogue
+        if (r < M) {
+          float* pz = partial + (int64_t(blockIdx.z) * M + r) * N + n0 + c0;
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + j < N) pz[j] = __uint_as_float(v[j]);
+        }
+        continue;
+      }
       if (r < M) {
         const int nbase = n0 + c0;
         float o[32];
@@ -165,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ep.bias && n < N) x += ep.bias[n];
           if (ep.relu) x = fmaxf(x, 0.0f);
           if (ep.mask && n < N) x = (ep.mask[r * ep.ldmask + n] > 0.0f) ? x : 0.0f;
+          if (ep.mask16 && n < N) x = (__bfloat162float(ep.mask16[r * ep.ldmask + n]) > 0.0f) ? x : 0.0f;
           o[j] = x;
         }
         if (ep.C) {
@@ -221,7 +265,7 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols = kBlockK) {
   EncodeTiledFn fn = encode_fn();
   TB_REQUIRE(fn, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
   TB_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0,
@@ -229,7 +273,7 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int6
              (long long)ld);
   cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   cuuint64_t gstride[1] = {cuuint64_t(ld) * 2};
-  cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(box_rows)};
+  cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -239,18 +283,18 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int6
   return 0;
 }
 
-template <int BLOCK_N>
-int launch(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K,
-           cudaStream_t stream) {
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
+           float* partial, cudaStream_t stream) {
   constexpr size_t smem = 1024 + kStages * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kStages + 1) + 16;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
   }
-  dim3 grid((unsigned)((N + BLOCK_N - 1) / BLOCK_N), (unsigned)((M + kBlockM - 1) / kBlockM));
-  gemm_tc_kernel<BLOCK_N><<<grid, kThreads, smem, stream>>>(a, b, ep, int(M), int(N), int(K));
+  dim3 grid((unsigned)((N + BLOCK_N - 1) / BLOCK_N), (unsigned)((M + kBlockM - 1) / kBlockM), (unsigned)splits);
+  gemm_tc_kernel<BLOCK_N, A_MN, B_MN><<<grid, kThreads, smem, stream>>>(a, b, ep, int(M), int(N), int(K), partial);
   return check_launch("gemm_tc_kernel");
 }
 
@@ -258,20 +302,51 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int
 
 int gemm_tc_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                  const TcEpilogue& ep, cudaStream_t stream) {
+  return gemm_tc_bf16_ex(A, B, M, N, K, lda, ldb, false, false, ep, 1, nullptr, stream);
+}
+
+int gemm_tc_bf16_ex(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, bool a_mn,
+                    bool b_mn, const TcEpilogue& ep, int splits, float* partial, cudaStream_t stream) {
   TB_REQUIRE(M >= 0 && N >= 0 && K >= 1, "gemm_tc: bad sizes M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   if (M == 0 || N == 0) return 0;
-  TB_REQUIRE(A && B && (ep.C || ep.C16), "gemm_tc: null pointer");
+  TB_REQUIRE(A && B && (ep.C || ep.C16 || partial), "gemm_tc: null pointer");
   TB_REQUIRE(M < (int64_t(1) << 31) && N < (int64_t(1) << 31) && K < (int64_t(1) << 31), "gemm_tc: size overflow");
+  TB_REQUIRE(!a_mn || b_mn, "gemm_tc: A MN-major requires B MN-major (wgrad form)");
+  if (splits < 1) splits = 1;
+  TB_REQUIRE(splits == 1 || partial, "gemm_tc: split-K needs a partial buffer");
   ProfScope prof(ep.tag, stream);
-  const int bn = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
+  int bn = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
+  if (b_mn && bn < 64) bn = 64;  // MN-major tiles are built from 64-wide boxes
   CUtensorMap ma, mb;
-  int rc = make_map(&ma, A, M, K, lda, kBlockM);
+  // K-major operand [rows = mn, cols = k]: box {64 k, mn rows}.  MN-major operand [rows = k, cols = mn]: box {64 mn, 64 k}.
+  int rc = a_mn ? make_map(&ma, A, K, M, lda, kBlockK, 64) : make_map(&ma, A, M, K, lda, kBlockM);
   if (rc) return rc;
-  rc = make_map(&mb, B, N, K, ldb, bn);
+  rc = b_mn ? make_map(&mb, B, K, N, ldb, kBlockK, 64) : make_map(&mb, B, N, K, ldb, bn);
   if (rc) return rc;
-  if (bn == 32) return launch<32>(ma, mb, ep, M, N, K, stream);
-  if (bn == 64) return launch<64>(ma, mb, ep, M, N, K, stream);
-  return launch<128>(ma, mb, ep, M, N, K, stream);
+  float* part = splits > 1 || partial ? partial : nullptr;
+  if (splits == 1 && !(ep.permP > 1 || ep.permQ > 1)) part = nullptr;
+#define TB_TC_LAUNCH(BN, AM, BM) rc = launch<BN, AM, BM>(ma, mb, ep, M, N, K, splits, part, stream)
+  if (!a_mn && !b_mn) {
+    if (bn == 32) TB_TC_LAUNCH(32, false, false);
+    else if (bn == 64) TB_TC_LAUNCH(64, false, false);
+    else TB_TC_LAUNCH(128, false, false);
+  } else if (!a_mn && b_mn) {
+    if (bn == 64) TB_TC_LAUNCH(64, false, true);
+    else TB_TC_LAUNCH(128, false, true);
+  } else {
+    if (bn == 64) TB_TC_LAUNCH(64, true, true);
+    else TB_TC_LAUNCH(128, true, true);
+  }
+#undef TB_TC_LAUNCH
+  if (rc || !part) return rc;
+  TB_REQUIRE(ep.C, "gemm_tc: split-K reduce needs an fp32 output");
+  GemmEpilogue rep;
+  rep.bias = ep.bias; rep.relu = ep.relu; rep.permP = ep.permP; rep.permQ = ep.permQ; rep.scale = ep.scale;
+  const int64_t total = M * N;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;
+  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(part, ep.C, M, N, ep.ldc, splits, rep);
+  return check_launch("splitk_reduce_kernel");
 }
 
 // fp32 [rows, cols] (ld) -> bf16 [rows, cols16] (ld16), optional ReLU-free straight convert
@@ -308,6 +383,13 @@ int tb_gemm_bf16_tn(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N
   ep.C = C; ep.ldc = ldc; ep.C16 = static_cast<__nv_bfloat16*>(C_bf16); ep.ldc16 = ldc16; ep.bias = bias;
   ep.scale = scale; ep.relu = relu; ep.tag = "gemm_bf16_tn";
   return gemm_tc_bf16(A_bf16, B_bf16, M, N, K, lda, ldb, ep, (cudaStream_t)stream);
+}
+
+int tb_gemm_bf16_ex(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                    int a_mn, int b_mn, float* C, int64_t ldc, int splits, float* partial, void* stream) {
+  TcEpilogue ep;
+  ep.C = C; ep.ldc = ldc; ep.tag = "gemm_bf16_ex";
+  return gemm_tc_bf16_ex(A_bf16, B_bf16, M, N, K, lda, ldb, a_mn != 0, b_mn != 0, ep, splits, partial, (cudaStream_t)stream);
 }
 
 int tb_f32_to_bf16(const float* in, void* out_bf16, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, void* stream) {

@@ -13,6 +13,8 @@ struct TcEpilogue {
   float scale = 1.0f;                                // applied to the accumulator first (1/255 for uint8 frames)
   int relu = 0;
   const float* mask = nullptr; int64_t ldmask = 0;   // out = (mask > 0) ? out : 0   (ReLU backward)
+  const __nv_bfloat16* mask16 = nullptr;             // same, mask stored in bf16 (uses ldmask)
+  int permP = 1, permQ = 1;                          // (split-K reduce only) weight-grad column un-pack
   const char* tag = "gemm_tc";
 };
 
@@ -20,6 +22,12 @@ struct TcEpilogue {
 // 16-byte aligned bases.
 int gemm_tc_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                  const TcEpilogue& ep, cudaStream_t stream);
+
+// General form: a_mn / b_mn mark operands whose ROW index is the reduction index
+//   (a_mn: A is [K, M] row-major; b_mn: B is [K, N] row-major).  splits > 1 (or partial != nullptr)
+//   writes raw fp32 partial tiles [z][M][N] to `partial` for splitk_reduce_kernel.
+int gemm_tc_bf16_ex(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, bool a_mn,
+                    bool b_mn, const TcEpilogue& ep, int splits, float* partial, cudaStream_t stream);
 
 int f32_to_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, cudaStream_t stream);
 

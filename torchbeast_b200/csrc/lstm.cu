@@ -12,6 +12,7 @@
 #include "lstm.cuh"
 
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "net_kernels.cuh"
 
 namespace tb {
@@ -22,11 +23,13 @@ static inline int padded_h(int H) {
   return hp;
 }
 
-size_t lstm_ws_bytes(int64_t T1, int64_t B, int In, int H, int layers) {
-  return lstm_ws(nullptr, T1, B, In, H, layers).bytes;
+static inline int64_t ld16(int64_t n) { return (n + 7) & ~int64_t(7); }
+
+size_t lstm_ws_bytes(int64_t T1, int64_t B, int In, int H, int layers, int precision) {
+  return lstm_ws(nullptr, T1, B, In, H, layers, precision).bytes;
 }
 
-LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers) {
+LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int precision) {
   LstmWs w;
   size_t off = 0;
   auto takef = [&](int64_t n) {
@@ -42,6 +45,12 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers) {
       L.gates = takef(N * 4 * H); L.hs = takef(N * H); L.cs = takef(N * H); L.hm = takef(N * Hp);
       L.cm = takef(N * H); L.dgates = takef(N * 4 * H); L.bsum = takef(4 * H); L.w_hh_t = takef(int64_t(H + 4) * 4 * Hp);
       L.wp = takef(int64_t(4 * H + 4) * Hp);
+      L.xb = L.wihb = L.dgb = L.hmb = nullptr;
+      if (precision) {  // bf16 operand copies (2 bytes per element: take half the float count, rounded up)
+        const int64_t in_l = (l == 0) ? In : H;
+        L.xb = takef((N * ld16(in_l) + 1) / 2); L.wihb = takef((int64_t(4) * H * ld16(in_l) + 1) / 2);
+        L.dgb = takef((N * ld16(4 * H) + 1) / 2); L.hmb = takef((N * ld16(H) + 1) / 2);
+      }
     } else {
       L = LstmLayerWs();
     }
@@ -384,7 +393,7 @@ static int launch_step_fwd(const StepArgs& a, cudaStream_t st) {
 
 int lstm_forward(const float* x, const float* notdone, const float* h0, const float* c0, const LstmParams& p,
                  int64_t T1, int64_t B, int In, int H, int layers, LstmWs& ws, float* y, float* hN, float* cN,
-                 float* splitk, cudaStream_t st) {
+                 float* splitk, int precision, cudaStream_t st) {
   TB_REQUIRE(layers >= 1 && layers <= kLstmMaxLayers, "lstm: 1..%d layers", kLstmMaxLayers);
   const int64_t N = T1 * B;
   const float* xin = x;
@@ -394,9 +403,17 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
     float* hs = (l == layers - 1) ? y : L.hs;
     add2_kernel<<<(4 * H + 255) / 256, 256, 0, st>>>(p.b_ih[l], p.b_hh[l], L.bsum, 4 * H);
     TB_TRY(check_launch("add2_kernel"));
-    GemmEpilogue ep; ep.bias = L.bsum; ep.tag = "lstm_xproj_fwd";
-    TB_TRY((gemm_simt<float, float, false, true>(xin, p.w_ih[l], L.gates, N, 4 * H, in_dim, in_dim, in_dim, 4 * H, ep, 1,
-                                                  nullptr, st)));
+    if (precision) {
+      const int64_t l16 = ld16(in_dim);
+      TB_TRY(f32_to_bf16(xin, L.xb, N, in_dim, in_dim, l16, st));
+      TB_TRY(pack_weights_bf16(p.w_ih[l], L.wihb, 4 * H, 1, in_dim, l16, st));
+      TcEpilogue te; te.C = L.gates; te.ldc = 4 * H; te.bias = L.bsum; te.tag = "lstm_xproj_fwd";
+      TB_TRY(gemm_tc_bf16(L.xb, L.wihb, N, 4 * H, in_dim, l16, l16, te, st));
+    } else {
+      GemmEpilogue ep; ep.bias = L.bsum; ep.tag = "lstm_xproj_fwd";
+      TB_TRY((gemm_simt<float, float, false, true>(xin, p.w_ih[l], L.gates, N, 4 * H, in_dim, in_dim, in_dim, 4 * H, ep, 1,
+                                                    nullptr, st)));
+    }
     const int Hp = padded_h(H);
     {
       const int64_t tot = int64_t(4 * H + 4) * Hp;
@@ -450,7 +467,7 @@ static int splits_for(int64_t M, int64_t N, int64_t K, int64_t scratch_floats) {
 
 int lstm_backward(const float* dy, const float* x, const float* notdone, const LstmParams& p, const LstmGrads& g,
                   int64_t T1, int64_t B, int In, int H, int layers, LstmWs& ws, float* dx, float* splitk,
-                  float* colsum_scratch, cudaStream_t st) {
+                  float* colsum_scratch, int precision, cudaStream_t st) {
   const int64_t N = T1 * B;
   const int64_t scratch = int64_t(8) << 20;  // == kSplitKScratchFloats (atarinet.cu)
   const float* dyl = dy;
@@ -489,6 +506,24 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     }
     }
     // parameter gradients over all steps at once
+    if (precision) {
+      const int64_t lg = ld16(4 * H), lh = ld16(H), li = ld16(in_dim);
+      TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st));
+      TB_TRY(f32_to_bf16(L.hm, L.hmb, N, H, padded_h(H), lh, st));
+      const int64_t kb = (N + 63) / 64;
+      int sp = int(kb / 8); if (sp < 1) sp = 1; if (sp > 4) sp = 4;
+      TcEpilogue te; te.tag = "lstm_wgrad";
+      te.C = g.w_hh[l]; te.ldc = H;      // dW_hh[4H,H] = dgates^T . hm   (both operands stored [N, .]: MN-major)
+      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.hmb, 4 * H, H, N, lg, lh, true, true, te, sp, splitk, st));
+      te.C = g.w_ih[l]; te.ldc = in_dim;  // dW_ih[4H,in] = dgates^T . x
+      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.xb, 4 * H, in_dim, N, lg, li, true, true, te, sp, splitk, st));
+      TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));
+      cudaError_t e = cudaMemcpyAsync(g.b_hh[l], g.b_ih[l], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st);
+      TB_REQUIRE(e == cudaSuccess, "lstm: bias grad copy: %s", cudaGetErrorString(e));
+      // dx[N,in] = dgates[N,4H] . W_ih[4H,in]   (W_ih as stored: reduction index is its row index)
+      TcEpilogue td; td.tag = "lstm_xproj_dgrad"; td.C = dxl; td.ldc = in_dim;
+      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.wihb, N, in_dim, 4 * H, lg, li, false, true, td, 1, nullptr, st));
+    } else {
     GemmEpilogue ep; ep.tag = "lstm_wgrad";
     int s = splits_for(4 * H, H, N, scratch);
     TB_TRY((gemm_simt<float, float, true, false>(L.dgates, L.hm, g.w_hh[l], 4 * H, H, N, 4 * H, padded_h(H), H, ep, s, splitk,
@@ -503,6 +538,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     ep.tag = "lstm_xproj_dgrad";
     TB_TRY((gemm_simt<float, float, false, false>(L.dgates, p.w_ih[l], dxl, N, in_dim, 4 * H, 4 * H, in_dim, in_dim, ep, 1,
                                                    nullptr, st)));
+    }
     dyl = dxl;
   }
   return 0;

@@ -22,6 +22,10 @@ struct LstmLayerWs {
   float* cs;      // [T1*B, H]   c_t
   float* hm;      // [T1*B, Hp]  h_{t-1} * notdone_t (recurrent input used at step t), rows zero-padded to Hp
   float* cm;      // [T1*B, H]   c_{t-1} * notdone_t
+  void* xb;       // bf16 [T1*B, ld16(In)]   this layer's input (tensor-core backend)
+  void* wihb;     // bf16 [4H, ld16(In)]     W_ih
+  void* dgb;      // bf16 [T1*B, ld16(4H)]   gate gradients
+  void* hmb;      // bf16 [T1*B, ld16(H)]    masked recurrent inputs
   float* wp;      // [4H+4, Hp]  W_hh with rows zero-padded to Hp floats (16-byte multiples for bulk copies)
   float* dgates;  // [T1*B, 4H]  backward: d pre-activations
   float* bsum;    // [4H]        b_ih + b_hh
@@ -38,18 +42,20 @@ struct LstmWs {
   size_t bytes = 0;
 };
 
-size_t lstm_ws_bytes(int64_t T1, int64_t B, int In, int H, int layers);
-LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers);
+size_t lstm_ws_bytes(int64_t T1, int64_t B, int In, int H, int layers, int precision);
+LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int precision);
 
+// precision: 0 = fp32 SIMT GEMMs, 1 = bf16 tcgen05 GEMMs for the hoisted projections (the recurrence
+// itself is fp32 either way).
 // x [T1*B, In] -> y [T1*B, H]; h0/c0/hN/cN [layers, B, H]; notdone [T1*B] (float, multiplies the state
 // before each step).  splitk: GEMM scratch (kSplitKScratchFloats).
 int lstm_forward(const float* x, const float* notdone, const float* h0, const float* c0, const LstmParams& p,
                  int64_t T1, int64_t B, int In, int H, int layers, LstmWs& ws, float* y, float* hN, float* cN,
-                 float* splitk, cudaStream_t stream);
+                 float* splitk, int precision, cudaStream_t stream);
 
 // dy [T1*B, H] -> dx [T1*B, In]; parameter gradients written (overwritten) into g.
 int lstm_backward(const float* dy, const float* x, const float* notdone, const LstmParams& p, const LstmGrads& g,
                   int64_t T1, int64_t B, int In, int H, int layers, LstmWs& ws, float* dx, float* splitk,
-                  float* colsum_scratch, cudaStream_t stream);
+                  float* colsum_scratch, int precision, cudaStream_t stream);
 
 }  // namespace tb

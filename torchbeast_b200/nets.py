@@ -173,7 +173,9 @@ class AtariNet(FlatParamModule):
     """CUDA AtariNet (reference monobeast.py:545-635).  conv 8/4 -> 4/2 -> 3/1 -> fc 512 ->
     cat[reward, one-hot last action] -> optional 2-layer LSTM(519) -> policy / baseline heads."""
 
-    def __init__(self, observation_shape, num_actions, use_lstm=False, device=None):
+    PRECISIONS = {"fp32": 0, "bf16": 1}
+
+    def __init__(self, observation_shape, num_actions, use_lstm=False, device=None, precision=None):
         super().__init__()
         if tuple(observation_shape) != (4, 84, 84):
             raise _lib.TorchBeastB200Error(
@@ -190,6 +192,12 @@ class AtariNet(FlatParamModule):
             self.core.num_layers = 2
             self.core.hidden_size = self.core_size
             self.core.input_size = self.core_size
+        # "bf16": conv/fc/LSTM-projection GEMMs on tcgen05 tensor cores (bf16 operands, fp32
+        # accumulation, fp32 master weights/gradients); "fp32": exact SIMT GEMMs (parity anchor).
+        import os
+        self.precision = precision or os.environ.get("TB_PRECISION", "bf16")
+        if self.precision not in self.PRECISIONS:
+            raise _lib.TorchBeastB200Error("precision must be 'fp32' or 'bf16'")
         self._ws = None
         self._ws_key = None
         count = _lib.lib().tb_atarinet_param_count(num_actions, int(use_lstm))
@@ -202,9 +210,10 @@ class AtariNet(FlatParamModule):
 
     # ---- raw launches ---------------------------------------------------------------------
     def _workspace(self, T1, B):
-        key = (T1, B, self._flat.device)
+        key = (T1, B, self._flat.device, self.precision)
         if self._ws_key != key:
-            nbytes = _lib.lib().tb_atarinet_workspace_bytes(T1, B, self.num_actions, int(self.use_lstm))
+            nbytes = _lib.lib().tb_atarinet_workspace_bytes(T1, B, self.num_actions, int(self.use_lstm),
+                                                            self.PRECISIONS[self.precision])
             self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self._flat.device)
             self._ws_key = key
         return self._ws
@@ -232,7 +241,7 @@ class AtariNet(FlatParamModule):
         _lib.check(
             _lib.lib().tb_atarinet_forward(
                 p(frame), p(reward), p(notdone), p(last_action), p(h0), p(c0), p(self._flat), T1, B,
-                self.num_actions, int(self.use_lstm), p(ws), p(logits), p(baseline),
+                self.num_actions, int(self.use_lstm), self.PRECISIONS[self.precision], p(ws), p(logits), p(baseline),
                 p(hN) if self.use_lstm else None, p(cN) if self.use_lstm else None, _lib.stream_ptr()),
             "tb_atarinet_forward")
         return logits, baseline, hN, cN
@@ -244,7 +253,8 @@ class AtariNet(FlatParamModule):
         _lib.check(
             _lib.lib().tb_atarinet_backward(
                 p(g_logits), p(g_baseline), p(notdone) if self.use_lstm else None, p(self._flat), T1, B,
-                self.num_actions, int(self.use_lstm), p(ws), p(grads_out), _lib.stream_ptr()),
+                self.num_actions, int(self.use_lstm), self.PRECISIONS[self.precision], p(ws), p(grads_out),
+                _lib.stream_ptr()),
             "tb_atarinet_backward")
 
     @staticmethod
