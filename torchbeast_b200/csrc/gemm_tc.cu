@@ -32,7 +32,6 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;           // 64 bf16 = 128 bytes = one swizzle atom row
-constexpr int kStages = 4;
 constexpr int kThreads = 192;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;  // 16 KB
 
@@ -96,7 +95,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int kStages>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep, int M,
                int N, int K, float* partial) {
@@ -283,19 +282,30 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int6
   return 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
-           float* partial, cudaStream_t stream) {
+template <int BLOCK_N, bool A_MN, bool B_MN, int kStages>
+int launch_s(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
+             float* partial, cudaStream_t stream) {
   constexpr size_t smem = 1024 + kStages * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kStages + 1) + 16;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
   }
   dim3 grid((unsigned)((N + BLOCK_N - 1) / BLOCK_N), (unsigned)((M + kBlockM - 1) / kBlockM), (unsigned)splits);
-  gemm_tc_kernel<BLOCK_N, A_MN, B_MN><<<grid, kThreads, smem, stream>>>(a, b, ep, int(M), int(N), int(K), partial);
+  gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages><<<grid, kThreads, smem, stream>>>(a, b, ep, int(M), int(N), int(K), partial);
   return check_launch("gemm_tc_kernel");
+}
+
+// Few k-blocks per CTA (dgrad: K = 64 channels): a 2-stage ring keeps 3 CTAs resident per SM so the
+// per-CTA prologue (TMEM alloc, barrier init) of one tile overlaps the epilogue of another.
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
+           float* partial, cudaStream_t stream) {
+  const int64_t kb_per_cta = ((K + kBlockK - 1) / kBlockK + splits - 1) / splits;
+  if (kb_per_cta <= 2) return launch_s<BLOCK_N, A_MN, B_MN, 2>(a, b, ep, M, N, K, splits, partial, stream);
+  return launch_s<BLOCK_N, A_MN, B_MN, 4>(a, b, ep, M, N, K, splits, partial, stream);
 }
 
 }  // namespace
