@@ -37,12 +37,14 @@ def test_bf16_forward_and_gradients_vs_oracle(fname):
     np.testing.assert_allclose(float(loss.losses[1]), float(o["baseline_loss"]), rtol=2e-2)
     np.testing.assert_allclose(float(loss.losses[2]), float(o["entropy_loss"]), rtol=2e-2)
     np.testing.assert_allclose(float(loss.losses[3]), float(o["total_loss"]), rtol=2e-2, atol=2e-2 * float(o["baseline_loss"]))
+    report = {}
     for n, p in model.named_parameters():
         ref = o["grads"][n]
         got = p.grad.cpu().double()
         cos = float((got * ref).sum() / (got.norm() * ref.norm()).clamp_min(1e-30))
-        assert rel(got, ref) < 1e-1, (n, rel(got, ref))
-        assert cos > 0.995, (n, cos)
+        report[n] = (round(rel(got, ref), 4), round(cos, 5))
+    bad = {n: v for n, v in report.items() if v[0] >= 1e-1 or v[1] <= 0.995}
+    assert not bad, (bad, report)
 
 
 @pytest.mark.parametrize("fname", ["learn_atari_T20_B4.npz", "learn_atari_lstm_T20_B4.npz"])

@@ -72,14 +72,17 @@ __global__ void add2_kernel(const float* __restrict__ a, const float* __restrict
 
 // ---------------------------------------------------------------------------------------
 // forward step: one CTA = 4 hidden units (x 4 gates = 16 rows of W_hh) x a 32-row batch tile.
-// 128 threads: lane = batch row, warp q = gate; each thread owns gate q of 4 units.
+// 512 threads: lane = batch row, warp = (gate q, k-quarter ks); each thread accumulates gate q of the
+// 4 units over a quarter of the reduction, partial sums are combined through shared memory (16 warps
+// per SM hide the LDS/FMA latency that a 4-warp CTA exposed: ncu 'No Eligible' 86% -> see profiles/).
 // Operands are staged by the bulk-copy engine (cp.async.bulk -> UBLKCP, mbarrier complete_tx):
 // four 8 KB W_hh gate slices - issued BEFORE griddepcontrol.wait, so with programmatic
 // dependent launch they stream in while the previous time step is still finishing - and the
 // 67 KB masked-h tile the previous step produced.
 // ---------------------------------------------------------------------------------------
 constexpr int kStepUnits = 4;
-constexpr int kStepThreads = 128;
+constexpr int kStepThreads = 512;
+constexpr int kStepKSplit = 4;
 
 struct StepArgs {
   const float* hm;      // [B,Hp] masked recurrent input of this step (h_{t-1} * nd_t), zero padded
@@ -122,7 +125,8 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_fwd_kernel(StepArgs a)
   float* Xs = smem + 16 * a.Hp;                      // [32][Hp]  masked h_prev tile
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 48 * a.Hp);  // [0]: W slices, [1]: h tile
   __shared__ float act_s[4][kStepUnits][33];
-  const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+  __shared__ float part_s[kStepKSplit][4][kStepUnits][33];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, q = wrp & 3, ks = wrp >> 2;
   const int H = a.H, Hp = a.Hp;
   const int j0 = blockIdx.x * kStepUnits;
   const int b0 = blockIdx.y * 32;
@@ -151,9 +155,11 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_fwd_kernel(StepArgs a)
   const float4* x4 = reinterpret_cast<const float4*>(Xs + lane * Hp);
   const float4* w4 = reinterpret_cast<const float4*>(Ws + (q * 4) * Hp);
   const int k4n = Hp / 4;
+  const int kper = (k4n + kStepKSplit - 1) / kStepKSplit;
+  const int k4a = ks * kper, k4b = (k4a + kper < k4n) ? k4a + kper : k4n;
   if (lane < rows) {
-#pragma unroll 2
-    for (int k4 = 0; k4 < k4n; ++k4) {
+#pragma unroll 4
+    for (int k4 = k4a; k4 < k4b; ++k4) {
       const float4 x = x4[k4];
 #pragma unroll
       for (int u = 0; u < kStepUnits; ++u) {
@@ -163,22 +169,28 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_fwd_kernel(StepArgs a)
       }
     }
   }
-  const int b = b0 + lane;
 #pragma unroll
-  for (int u = 0; u < kStepUnits; ++u) {
-    float v = 0.0f;
-    if (lane < rows && j0 + u < H) {
-      float* gp = a.gates + int64_t(b) * 4 * H + int64_t(q) * H + j0 + u;
-      const float pre = *gp + acc[u];
-      v = (q == 2) ? tanhf(pre) : sigmoidf_(pre);
-      *gp = v;
+  for (int u = 0; u < kStepUnits; ++u) part_s[ks][q][u][lane] = acc[u];
+  __syncthreads();
+  const int b = b0 + lane;
+  if (ks == 0) {
+#pragma unroll
+    for (int u = 0; u < kStepUnits; ++u) {
+      float v = 0.0f;
+      if (lane < rows && j0 + u < H) {
+        const float dot = (part_s[0][q][u][lane] + part_s[1][q][u][lane]) + (part_s[2][q][u][lane] + part_s[3][q][u][lane]);
+        float* gp = a.gates + int64_t(b) * 4 * H + int64_t(q) * H + j0 + u;
+        const float pre = *gp + dot;
+        v = (q == 2) ? tanhf(pre) : sigmoidf_(pre);
+        *gp = v;
+      }
+      act_s[q][u][lane] = v;
     }
-    act_s[q][u][lane] = v;
   }
   __syncthreads();
-  // state update: thread = (batch row lane, unit q)
+  // state update: thread = (batch row lane, unit u) on the first four warps
   const int u = q;
-  if (lane < rows && j0 + u < H) {
+  if (ks == 0 && lane < rows && j0 + u < H) {
     const int64_t o = int64_t(b) * H + j0 + u;
     const float cmv = a.cm[o];
     const float ig = act_s[0][u][lane], fg = act_s[1][u][lane], gg = act_s[2][u][lane], og = act_s[3][u][lane];
@@ -280,7 +292,8 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_bwd_dh_kernel(DhArgs a
   float* Ws = smem;                       // [4][4*Hp]
   float* Xs = smem + 16 * Hp;             // [2][32][Hp]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 80 * Hp);  // [0]: W, [1],[2]: ring slots
-  const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
+  __shared__ float part_s[kStepKSplit][4][33];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, q = wrp & 3, ks = wrp >> 2;
   const int k0 = blockIdx.x * 4;
   const int b0 = blockIdx.y * 32;
   const int rows = (a.B - b0 < 32) ? (a.B - b0) : 32;
@@ -303,6 +316,8 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_bwd_dh_kernel(DhArgs a
   mbar_wait(&bar[0], 0);
   float acc = 0.0f;
   const int k4n = Hp / 4;
+  const int kper = (k4n + kStepKSplit - 1) / kStepKSplit;
+  const int k4a = ks * kper, k4b = (k4a + kper < k4n) ? k4a + kper : k4n;
   for (int g = 0; g < 4; ++g) {
     const int slot = g & 1;
     mbar_wait(&bar[1 + slot], (g >> 1) & 1);
@@ -310,7 +325,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_bwd_dh_kernel(DhArgs a
       const float4* x4 = reinterpret_cast<const float4*>(Xs + (slot * 32 + lane) * Hp);
       const float4* w4 = reinterpret_cast<const float4*>(Ws + (q * 4 + g) * Hp);
 #pragma unroll 4
-      for (int k4 = 0; k4 < k4n; ++k4) {
+      for (int k4 = k4a; k4 < k4b; ++k4) {
         const float4 x = x4[k4];
         const float4 w = w4[k4];
         acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
@@ -322,7 +337,10 @@ __global__ void __launch_bounds__(kStepThreads) lstm_step_bwd_dh_kernel(DhArgs a
       bulk_g2s(Xs + slot * 32 * Hp, a.dgp + (int64_t(g + 2) * a.B + b0) * Hp, xbytes, &bar[1 + slot]);
     }
   }
-  if (lane < rows && k0 + q < H) a.dh_raw[int64_t(b0 + lane) * H + k0 + q] = acc;
+  part_s[ks][q][lane] = acc;
+  __syncthreads();
+  if (ks == 0 && lane < rows && k0 + q < H)
+    a.dh_raw[int64_t(b0 + lane) * H + k0 + q] = (part_s[0][q][lane] + part_s[1][q][lane]) + (part_s[2][q][lane] + part_s[3][q][lane]);
 }
 
 // wtp[k][g*Hp + j] = W_hh[g*H + j][k], zero padded (j >= H, k >= H)
