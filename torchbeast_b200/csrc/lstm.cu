@@ -11,6 +11,8 @@
 // torch.nn.LSTM conventions: gate order i,f,g,o; weight_ih [4H,In], weight_hh [4H,H]; two biases.
 #include "lstm.cuh"
 
+#include <stdlib.h>
+
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "net_kernels.cuh"
@@ -57,7 +59,8 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
   }
   w.dh = takef(B * H); w.dc = takef(B * H);
   w.dx_mid = takef(N * (H > In ? H : In));
-  w.dgp = takef(int64_t(4) * B * padded_h(H));
+  w.dgp = takef(int64_t(2) * 4 * B * padded_h(H));
+  w.sync = reinterpret_cast<unsigned*>(takef(64));
   w.Hp = padded_h(H);
   w.bytes = off;
   return w;
@@ -415,6 +418,304 @@ static int launch_step_fwd(const StepArgs& a, cudaStream_t st) {
   return check_launch("lstm_step_fwd_kernel");
 }
 
+
+// =========================================================================================
+// Persistent recurrence kernels: ONE cooperative launch runs all T+1 steps of a layer.
+// The CTA's W_hh slice is staged once and stays in shared memory; the steps are separated by a
+// grid-wide barrier (release add / acquire spin on a global counter) instead of kernel
+// boundaries, and the only data that crosses CTAs per step (the masked h tile forward, the gate
+// gradients backward) is pulled by bulk copies right after the barrier.
+// =========================================================================================
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) {
+  while (ld_acquire_u32(ctr) < target) __nanosleep(32);
+  asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other CTAs -> our bulk copies
+}
+
+struct PersistFwdArgs {
+  const float* wp; float* gates; float* hs; float* cs; float* hm; float* cm; const float* nd;
+  unsigned* counter;
+  int T1, B, H, Hp; unsigned nctas;
+};
+
+__global__ void __launch_bounds__(kStepThreads) lstm_fwd_persistent_kernel(PersistFwdArgs a) {
+  extern __shared__ __align__(128) float smem[];
+  float* Ws = smem;
+  float* Xs = smem + 16 * a.Hp;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 48 * a.Hp);
+  __shared__ float act_s[4][kStepUnits][33];
+  __shared__ float part_s[kStepKSplit][4][kStepUnits][33];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, q = wrp & 3, ks = wrp >> 2;
+  const int H = a.H, Hp = a.Hp, B = a.B;
+  const int j0 = blockIdx.x * kStepUnits;
+  const int b0 = blockIdx.y * 32;
+  const int rows = (B - b0 < 32) ? (B - b0) : 32;
+  const uint32_t xbytes = uint32_t(rows) * Hp * sizeof(float);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t wbytes = uint32_t(kStepUnits) * Hp * sizeof(float);
+    mbar_expect_tx(&bar[0], 4 * wbytes);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      bulk_g2s(Ws + g * kStepUnits * Hp, a.wp + (int64_t(g) * H + j0) * Hp, wbytes, &bar[0]);
+  }
+  __syncthreads();
+  mbar_wait(&bar[0], 0);
+  const int b = b0 + lane;
+  const int k4n = Hp / 4;
+  const int kper = (k4n + kStepKSplit - 1) / kStepKSplit;
+  const int k4a = ks * kper, k4b = (k4a + kper < k4n) ? k4a + kper : k4n;
+  const float4* x4 = reinterpret_cast<const float4*>(Xs + lane * Hp);
+  const float4* w4 = reinterpret_cast<const float4*>(Ws + (q * 4) * Hp);
+  for (int t = 0; t < a.T1; ++t) {
+    const int64_t row0 = int64_t(t) * B;
+    if (tid == 0) {
+      if (t > 0) grid_wait(a.counter, unsigned(t) * a.nctas);  // every CTA finished step t-1
+      mbar_expect_tx(&bar[1], xbytes);
+      bulk_g2s(Xs, a.hm + (row0 + b0) * Hp, xbytes, &bar[1]);
+    }
+    float pre_in[kStepUnits] = {0.f, 0.f, 0.f, 0.f};
+    float cm_in = 0.f, ndn_in = 0.f;
+    const bool last = (t == a.T1 - 1);
+    if (ks == 0 && lane < rows) {
+#pragma unroll
+      for (int u = 0; u < kStepUnits; ++u)
+        if (j0 + u < H) pre_in[u] = a.gates[(row0 + b) * 4 * H + int64_t(q) * H + j0 + u];
+      if (j0 + q < H) {
+        cm_in = a.cm[(row0 + b) * H + j0 + q];  // written by this same thread one step earlier
+        if (!last) ndn_in = a.nd[row0 + B + b];
+      }
+    }
+    mbar_wait(&bar[1], t & 1);
+    float acc[kStepUnits] = {0.f, 0.f, 0.f, 0.f};
+    if (lane < rows) {
+#pragma unroll 4
+      for (int k4 = k4a; k4 < k4b; ++k4) {
+        const float4 x = x4[k4];
+#pragma unroll
+        for (int u = 0; u < kStepUnits; ++u) {
+          const float4 w = w4[u * k4n + k4];
+          acc[u] = fmaf(x.x, w.x, acc[u]); acc[u] = fmaf(x.y, w.y, acc[u]);
+          acc[u] = fmaf(x.z, w.z, acc[u]); acc[u] = fmaf(x.w, w.w, acc[u]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kStepUnits; ++u) part_s[ks][q][u][lane] = acc[u];
+    __syncthreads();
+    if (ks == 0) {
+#pragma unroll
+      for (int u = 0; u < kStepUnits; ++u) {
+        float v = 0.0f;
+        if (lane < rows && j0 + u < H) {
+          const float dot = (part_s[0][q][u][lane] + part_s[1][q][u][lane]) + (part_s[2][q][u][lane] + part_s[3][q][u][lane]);
+          const float pre = pre_in[u] + dot;
+          v = (q == 2) ? tanhf(pre) : sigmoidf_(pre);
+          a.gates[(row0 + b) * 4 * H + int64_t(q) * H + j0 + u] = v;
+        }
+        act_s[q][u][lane] = v;
+      }
+    }
+    __syncthreads();
+    const int u = q;
+    if (ks == 0 && lane < rows && j0 + u < H) {
+      const int64_t o = (row0 + b) * H + j0 + u;
+      const float ig = act_s[0][u][lane], fg = act_s[1][u][lane], gg = act_s[2][u][lane], og = act_s[3][u][lane];
+      const float c = fg * cm_in + ig * gg;
+      const float h = og * tanhf(c);
+      a.cs[o] = c;
+      a.hs[o] = h;
+      if (!last) {
+        a.hm[(row0 + B + b) * Hp + j0 + u] = h * ndn_in;
+        a.cm[o + int64_t(B) * H] = c * ndn_in;
+      }
+    }
+    __syncthreads();  // all of this CTA's step-t writes are issued; smem scratch is free again
+    if (tid == 0 && !last) red_release_add(a.counter, 1u);
+  }
+}
+
+struct PersistBwdArgs {
+  const float* wtp; const float* dy; const float* nd;
+  const float* gates; const float* cs; const float* cm;
+  float* dgates; float* dgp;
+  unsigned* counter;
+  int T1, B, H, Hp; unsigned nctas;
+};
+
+__global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_kernel(PersistBwdArgs a) {
+  extern __shared__ __align__(128) float smem[];
+  const int Hp = a.Hp, H = a.H, B = a.B;
+  float* Ws = smem;               // [4][4*Hp]
+  float* Xs = smem + 16 * Hp;     // [2][32][Hp]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 80 * Hp);
+  __shared__ float part_s[kStepKSplit][4][33];
+  __shared__ float dh_s[4][33];   // dL/dh_{t} contribution from step t+1 for this CTA's 4 units (unmasked)
+  __shared__ float dc_s[4][33];   // dL/dc_t carry
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, q = wrp & 3, ks = wrp >> 2;
+  const int k0 = blockIdx.x * 4;
+  const int rows = B < 32 ? B : 32;  // single batch tile (host guarantees B <= 32)
+  const uint32_t xbytes = uint32_t(rows) * Hp * sizeof(float);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_init(&bar[2], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t wbytes = uint32_t(16) * Hp * sizeof(float);
+    mbar_expect_tx(&bar[0], wbytes);
+    bulk_g2s(Ws, a.wtp + int64_t(k0) * 4 * Hp, wbytes, &bar[0]);
+  }
+  if (tid < 128) { dh_s[q][lane] = 0.0f; dc_s[q][lane] = 0.0f; }
+  __syncthreads();
+  mbar_wait(&bar[0], 0);
+  const int k4n = Hp / 4;
+  const int kper = (k4n + kStepKSplit - 1) / kStepKSplit;
+  const int k4a = ks * kper, k4b = (k4a + kper < k4n) ? k4a + kper : k4n;
+  const int64_t gs = int64_t(B) * Hp;
+  int it = 0;
+  for (int t = a.T1 - 1; t >= 0; --t, ++it) {
+    const int64_t row0 = int64_t(t) * B;
+    float* dgp_t = a.dgp + int64_t(it & 1) * 4 * gs;
+    // ---- phase A: gate gradients of this CTA's 4 units (thread = batch row x unit) ----
+    if (ks == 0 && lane < rows && k0 + q < H) {
+      const int j = k0 + q;
+      const int64_t i = (row0 + lane) * H + j;
+      const int64_t g0 = (row0 + lane) * 4 * H + j;
+      const float ig = a.gates[g0], fg = a.gates[g0 + H], gg = a.gates[g0 + 2 * H], og = a.gates[g0 + 3 * H];
+      float dh = a.dy[i];
+      float dc = 0.0f;
+      if (it > 0) {
+        dh += dh_s[q][lane] * a.nd[row0 + B + lane];
+        dc = dc_s[q][lane];
+      }
+      const float tc = tanhf(a.cs[i]);
+      const float d_o = dh * tc;
+      dc += dh * og * (1.0f - tc * tc);
+      const float d_i = dc * gg, d_f = dc * a.cm[i], d_g = dc * ig;
+      const float p_i = d_i * ig * (1.0f - ig), p_f = d_f * fg * (1.0f - fg);
+      const float p_g = d_g * (1.0f - gg * gg), p_o = d_o * og * (1.0f - og);
+      a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o;
+      const int64_t gp = int64_t(lane) * Hp + j;
+      dgp_t[gp] = p_i; dgp_t[gs + gp] = p_f; dgp_t[2 * gs + gp] = p_g; dgp_t[3 * gs + gp] = p_o;
+      dc_s[q][lane] = dc * fg * a.nd[row0 + lane];
+    }
+    if (t == 0) break;  // uniform: no earlier step needs dh
+    __syncthreads();
+    // ---- grid barrier: every CTA's gate gradients of step t are visible ----
+    if (tid == 0) {
+      red_release_add(a.counter, 1u);
+      grid_wait(a.counter, unsigned(it + 1) * a.nctas);
+      for (int g = 0; g < 2; ++g) {
+        mbar_expect_tx(&bar[1 + g], xbytes);
+        bulk_g2s(Xs + g * 32 * Hp, dgp_t + int64_t(g) * gs, xbytes, &bar[1 + g]);
+      }
+    }
+    // ---- phase B: dh_raw[b, k0+q] = sum_g dgates_g[b,:] . W_hh[g*H + :, k0+q] ----
+    float acc = 0.0f;
+    for (int g = 0; g < 4; ++g) {
+      const int slot = g & 1;
+      mbar_wait(&bar[1 + slot], (g >> 1) & 1);
+      if (lane < rows) {
+        const float4* x4 = reinterpret_cast<const float4*>(Xs + (slot * 32 + lane) * Hp);
+        const float4* w4 = reinterpret_cast<const float4*>(Ws + (q * 4 + g) * Hp);
+#pragma unroll 4
+        for (int k4 = k4a; k4 < k4b; ++k4) {
+          const float4 x = x4[k4];
+          const float4 w = w4[k4];
+          acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+        }
+      }
+      __syncthreads();
+      if (tid == 0 && g + 2 < 4) {
+        mbar_expect_tx(&bar[1 + slot], xbytes);
+        bulk_g2s(Xs + slot * 32 * Hp, dgp_t + int64_t(g + 2) * gs, xbytes, &bar[1 + slot]);
+      }
+    }
+    part_s[ks][q][lane] = acc;
+    __syncthreads();
+    if (ks == 0) dh_s[q][lane] = (part_s[0][q][lane] + part_s[1][q][lane]) + (part_s[2][q][lane] + part_s[3][q][lane]);
+    __syncthreads();
+  }
+}
+
+// returns 0 = ran, -1 = not applicable (caller falls back to the per-step kernels), > 0 = error
+static int persistent_ok(const void* kernel, dim3 grid, size_t smem) {
+  int dev = 0, sms = 0, coop = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStepThreads, smem) != cudaSuccess) return 0;
+  return int64_t(per_sm) * sms >= int64_t(grid.x) * grid.y;
+}
+
+static bool persistent_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TB_LSTM_PERSISTENT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int lstm_fwd_persistent(const LstmLayerWs& L, float* hs, const float* notdone, int64_t T1, int64_t B, int H,
+                               unsigned* counter, cudaStream_t st) {
+  if (!persistent_enabled() || B > 64) return -1;
+  const int Hp = padded_h(H);
+  const size_t smem = size_t(48) * Hp * sizeof(float) + 16;
+  if (smem > 200 * 1024) return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(lstm_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+      return -1;
+    attr_set = true;
+  }
+  dim3 grid((H + kStepUnits - 1) / kStepUnits, (unsigned)((B + 31) / 32));
+  if (!persistent_ok((const void*)lstm_fwd_persistent_kernel, grid, smem)) return -1;
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+  TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
+  PersistFwdArgs a;
+  a.wp = L.wp; a.gates = L.gates; a.hs = hs; a.cs = L.cs; a.hm = L.hm; a.cm = L.cm; a.nd = notdone; a.counter = counter;
+  a.T1 = int(T1); a.B = int(B); a.H = H; a.Hp = Hp; a.nctas = grid.x * grid.y;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)lstm_fwd_persistent_kernel, grid, dim3(kStepThreads), args, smem, st);
+  TB_REQUIRE(e == cudaSuccess, "lstm_fwd_persistent_kernel: %s", cudaGetErrorString(e));
+  return check_launch("lstm_fwd_persistent_kernel");
+}
+
+static int lstm_bwd_persistent(const LstmLayerWs& L, const LstmWs& ws, const float* dy, const float* notdone, int64_t T1,
+                               int64_t B, int H, unsigned* counter, cudaStream_t st) {
+  if (!persistent_enabled() || B > 32) return -1;
+  const int Hp = padded_h(H);
+  const size_t smem = size_t(80) * Hp * sizeof(float) + 32;
+  if (smem > 220 * 1024) return -1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(lstm_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+      return -1;
+    attr_set = true;
+  }
+  dim3 grid((H + 3) / 4, 1);
+  if (!persistent_ok((const void*)lstm_bwd_persistent_kernel, grid, smem)) return -1;
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ws.dgp, 0, sizeof(float) * 2 * 4 * B * Hp, st);
+  TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
+  PersistBwdArgs a;
+  a.wtp = L.w_hh_t; a.dy = dy; a.nd = notdone; a.gates = L.gates; a.cs = L.cs; a.cm = L.cm; a.dgates = L.dgates;
+  a.dgp = ws.dgp; a.counter = counter; a.T1 = int(T1); a.B = int(B); a.H = H; a.Hp = Hp; a.nctas = grid.x;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)lstm_bwd_persistent_kernel, grid, dim3(kStepThreads), args, smem, st);
+  TB_REQUIRE(e == cudaSuccess, "lstm_bwd_persistent_kernel: %s", cudaGetErrorString(e));
+  return check_launch("lstm_bwd_persistent_kernel");
+}
+
 #define TB_TRY(expr)        \
   do {                      \
     int _rc = (expr);       \
@@ -456,7 +757,9 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
       TB_TRY(check_launch("lstm_init_state_kernel"));
     }
     ProfScope prof("lstm_recurrence_fwd", st);
-    for (int64_t t = 0; t < T1; ++t) {
+    const int prc = lstm_fwd_persistent(L, hs, notdone, T1, B, H, ws.sync, st);
+    if (prc > 0) return prc;
+    for (int64_t t = 0; prc < 0 && t < T1; ++t) {
       StepArgs a;
       a.hm = L.hm + t * B * Hp;
       a.cm = L.cm + t * B * H;
@@ -516,7 +819,9 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     }
     {
     ProfScope prof("lstm_recurrence_bwd", st);
-    for (int64_t t = T1 - 1; t >= 0; --t) {
+    const int prc = lstm_bwd_persistent(L, ws, dyl, notdone, T1, B, H, ws.sync + 16, st);
+    if (prc > 0) return prc;
+    for (int64_t t = T1 - 1; prc < 0 && t >= 0; --t) {
       BwdPointArgs a;
       a.dy = dyl + t * B * H;
       a.first = (t == T1 - 1);

@@ -37,7 +37,9 @@ struct LstmWs {
   float* dh;      // [B, H] carry
   float* dc;      // [B, H] carry
   float* dx_mid;  // [T1*B, H] gradient w.r.t. the output of layer 0 (input of layer 1)
-  float* dgp;     // [4, B, Hp] this step's gate gradients, gate-major and zero padded (recurrent product operand)
+  unsigned* sync; // [64] grid-barrier counters of the persistent recurrence kernels (zeroed per launch)
+  float* dgp;     // [2][4, B, Hp] (double-buffered for the persistent backward)
+  //               this step's gate gradients, gate-major and zero padded (recurrent product operand)
   int Hp = 0;     // padded row length of hm / wp
   size_t bytes = 0;
 };
