@@ -446,21 +446,23 @@ struct PersistFwdArgs {
 };
 
 __global__ void __launch_bounds__(kStepThreads) lstm_fwd_persistent_kernel(PersistFwdArgs a) {
+  // 16 warps; warp = k-slice (1/16 of the reduction), lane = batch row, every thread accumulates all
+  // 16 outputs (4 gates x 4 units) of its row over its k-slice: one 4-wavefront LDS.128 of the h tile
+  // feeds 64 FMAs (W comes by broadcast LDS.128), which roughly halves shared-memory traffic per FMA
+  // against the per-step kernel (ncu: FFMA issue was short-scoreboard/LDS bound).
   extern __shared__ __align__(128) float smem[];
   float* Ws = smem;
   float* Xs = smem + 16 * a.Hp;
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 48 * a.Hp);
   __shared__ float act_s[4][kStepUnits][33];
-  __shared__ float part_s[kStepKSplit][4][kStepUnits][33];
-  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, q = wrp & 3, ks = wrp >> 2;
+  __shared__ float part_s[16][16][33];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int H = a.H, Hp = a.Hp, B = a.B;
   const int j0 = blockIdx.x * kStepUnits;
   const int b0 = blockIdx.y * 32;
   const int rows = (B - b0 < 32) ? (B - b0) : 32;
-  const uint32_t xbytes = uint32_t(rows) * Hp * sizeof(float);
   if (tid == 0) {
     mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t wbytes = uint32_t(kStepUnits) * Hp * sizeof(float);
     mbar_expect_tx(&bar[0], 4 * wbytes);
@@ -472,62 +474,61 @@ __global__ void __launch_bounds__(kStepThreads) lstm_fwd_persistent_kernel(Persi
   mbar_wait(&bar[0], 0);
   const int b = b0 + lane;
   const int k4n = Hp / 4;
-  const int kper = (k4n + kStepKSplit - 1) / kStepKSplit;
-  const int k4a = ks * kper, k4b = (k4a + kper < k4n) ? k4a + kper : k4n;
+  const int kper = (k4n + 15) / 16;
+  const int k4a = wrp * kper, k4b = (k4a + kper < k4n) ? k4a + kper : k4n;
   const float4* x4 = reinterpret_cast<const float4*>(Xs + lane * Hp);
-  const float4* w4 = reinterpret_cast<const float4*>(Ws + (q * 4) * Hp);
+  const float4* w4 = reinterpret_cast<const float4*>(Ws);
+  float4* Xs4 = reinterpret_cast<float4*>(Xs);
+  const int oq = wrp >> 2, ou = wrp & 3;  // the output (gate oq, unit ou) this thread finalises
   for (int t = 0; t < a.T1; ++t) {
     const int64_t row0 = int64_t(t) * B;
-    if (tid == 0) {
-      if (t > 0) grid_wait(a.counter, unsigned(t) * a.nctas);  // every CTA finished step t-1
-      mbar_expect_tx(&bar[1], xbytes);
-      bulk_g2s(Xs, a.hm + (row0 + b0) * Hp, xbytes, &bar[1]);
-    }
-    float pre_in[kStepUnits] = {0.f, 0.f, 0.f, 0.f};
-    float cm_in = 0.f, ndn_in = 0.f;
     const bool last = (t == a.T1 - 1);
-    if (ks == 0 && lane < rows) {
-#pragma unroll
-      for (int u = 0; u < kStepUnits; ++u)
-        if (j0 + u < H) pre_in[u] = a.gates[(row0 + b) * 4 * H + int64_t(q) * H + j0 + u];
-      if (j0 + q < H) {
-        cm_in = a.cm[(row0 + b) * H + j0 + q];  // written by this same thread one step earlier
-        if (!last) ndn_in = a.nd[row0 + B + b];
+    if (tid == 0 && t > 0) grid_wait(a.counter, unsigned(t) * a.nctas);  // every CTA finished step t-1
+    __syncthreads();
+    // cooperative L2 -> smem copy of the masked h tile (written by all CTAs in the previous step)
+    const float4* src = reinterpret_cast<const float4*>(a.hm + (row0 + b0) * Hp);
+    for (int i = tid; i < rows * k4n; i += kStepThreads) Xs4[i] = __ldcg(src + i);
+    float pre_in = 0.f, cm_in = 0.f, ndn_in = 0.f;
+    if (lane < rows && j0 + ou < H) {
+      pre_in = a.gates[(row0 + b) * 4 * H + int64_t(oq) * H + j0 + ou];
+      if (wrp < 4 && j0 + wrp < H) {
+        cm_in = a.cm[(row0 + b) * H + j0 + wrp];
+        if (!last) ndn_in = __ldg(a.nd + row0 + B + b);
       }
     }
-    mbar_wait(&bar[1], t & 1);
-    float acc[kStepUnits] = {0.f, 0.f, 0.f, 0.f};
+    __syncthreads();
+    float acc[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) acc[o] = 0.f;
     if (lane < rows) {
-#pragma unroll 4
       for (int k4 = k4a; k4 < k4b; ++k4) {
         const float4 x = x4[k4];
 #pragma unroll
-        for (int u = 0; u < kStepUnits; ++u) {
-          const float4 w = w4[u * k4n + k4];
-          acc[u] = fmaf(x.x, w.x, acc[u]); acc[u] = fmaf(x.y, w.y, acc[u]);
-          acc[u] = fmaf(x.z, w.z, acc[u]); acc[u] = fmaf(x.w, w.w, acc[u]);
+        for (int o = 0; o < 16; ++o) {
+          const float4 w = w4[o * k4n + k4];
+          acc[o] = fmaf(x.x, w.x, acc[o]); acc[o] = fmaf(x.y, w.y, acc[o]);
+          acc[o] = fmaf(x.z, w.z, acc[o]); acc[o] = fmaf(x.w, w.w, acc[o]);
         }
       }
     }
 #pragma unroll
-    for (int u = 0; u < kStepUnits; ++u) part_s[ks][q][u][lane] = acc[u];
+    for (int o = 0; o < 16; ++o) part_s[wrp][o][lane] = acc[o];
     __syncthreads();
-    if (ks == 0) {
+    {
+      float v = 0.0f;
+      if (lane < rows && j0 + ou < H) {
+        float dot = 0.f;
 #pragma unroll
-      for (int u = 0; u < kStepUnits; ++u) {
-        float v = 0.0f;
-        if (lane < rows && j0 + u < H) {
-          const float dot = (part_s[0][q][u][lane] + part_s[1][q][u][lane]) + (part_s[2][q][u][lane] + part_s[3][q][u][lane]);
-          const float pre = pre_in[u] + dot;
-          v = (q == 2) ? tanhf(pre) : sigmoidf_(pre);
-          a.gates[(row0 + b) * 4 * H + int64_t(q) * H + j0 + u] = v;
-        }
-        act_s[q][u][lane] = v;
+        for (int sidx = 0; sidx < 16; ++sidx) dot += part_s[sidx][wrp][lane];
+        const float pre = pre_in + dot;
+        v = (oq == 2) ? tanhf(pre) : sigmoidf_(pre);
+        a.gates[(row0 + b) * 4 * H + int64_t(oq) * H + j0 + ou] = v;
       }
+      act_s[oq][ou][lane] = v;
     }
     __syncthreads();
-    const int u = q;
-    if (ks == 0 && lane < rows && j0 + u < H) {
+    if (wrp < 4 && lane < rows && j0 + wrp < H) {
+      const int u = wrp;
       const int64_t o = (row0 + b) * H + j0 + u;
       const float ig = act_s[0][u][lane], fg = act_s[1][u][lane], gg = act_s[2][u][lane], og = act_s[3][u][lane];
       const float c = fg * cm_in + ig * gg;
@@ -539,7 +540,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_fwd_persistent_kernel(Persi
         a.cm[o + int64_t(B) * H] = c * ndn_in;
       }
     }
-    __syncthreads();  // all of this CTA's step-t writes are issued; smem scratch is free again
+    __syncthreads();  // all of this CTA's step-t writes are issued
     if (tid == 0 && !last) red_release_add(a.counter, 1u);
   }
 }
@@ -558,7 +559,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_kernel(Persi
   float* Ws = smem;               // [4][4*Hp]
   float* Xs = smem + 16 * Hp;     // [2][32][Hp]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 80 * Hp);
-  __shared__ float part_s[kStepKSplit][4][33];
+  __shared__ float part16_s[16][4][33];
   __shared__ float dh_s[4][33];   // dL/dh_{t} contribution from step t+1 for this CTA's 4 units (unmasked)
   __shared__ float dc_s[4][33];   // dL/dc_t carry
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, q = wrp & 3, ks = wrp >> 2;
@@ -576,8 +577,6 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_kernel(Persi
   __syncthreads();
   mbar_wait(&bar[0], 0);
   const int k4n = Hp / 4;
-  const int kper = (k4n + kStepKSplit - 1) / kStepKSplit;
-  const int k4a = ks * kper, k4b = (k4a + kper < k4n) ? k4a + kper : k4n;
   const int64_t gs = int64_t(B) * Hp;
   int it = 0;
   for (int t = a.T1 - 1; t >= 0; --t, ++it) {
@@ -617,19 +616,25 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_kernel(Persi
         bulk_g2s(Xs + g * 32 * Hp, dgp_t + int64_t(g) * gs, xbytes, &bar[1 + g]);
       }
     }
-    // ---- phase B: dh_raw[b, k0+q] = sum_g dgates_g[b,:] . W_hh[g*H + :, k0+q] ----
-    float acc = 0.0f;
+    // ---- phase B: dh_raw[b, k0+c] = sum_g dgates_g[b,:] . W_hh[g*H + :, k0+c], c = 0..3 ----
+    // warp = k-slice (1/16), every thread accumulates all 4 columns of its batch row
+    float acc4[4] = {0.f, 0.f, 0.f, 0.f};
+    const int kper16 = (k4n + 15) / 16;
+    const int ka = wrp * kper16, kb = (ka + kper16 < k4n) ? ka + kper16 : k4n;
     for (int g = 0; g < 4; ++g) {
       const int slot = g & 1;
       mbar_wait(&bar[1 + slot], (g >> 1) & 1);
       if (lane < rows) {
         const float4* x4 = reinterpret_cast<const float4*>(Xs + (slot * 32 + lane) * Hp);
-        const float4* w4 = reinterpret_cast<const float4*>(Ws + (q * 4 + g) * Hp);
-#pragma unroll 4
-        for (int k4 = k4a; k4 < k4b; ++k4) {
+        const float4* w4 = reinterpret_cast<const float4*>(Ws + g * Hp);
+        for (int k4 = ka; k4 < kb; ++k4) {
           const float4 x = x4[k4];
-          const float4 w = w4[k4];
-          acc = fmaf(x.x, w.x, acc); acc = fmaf(x.y, w.y, acc); acc = fmaf(x.z, w.z, acc); acc = fmaf(x.w, w.w, acc);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 w = w4[c * 4 * k4n + k4];
+            acc4[c] = fmaf(x.x, w.x, acc4[c]); acc4[c] = fmaf(x.y, w.y, acc4[c]);
+            acc4[c] = fmaf(x.z, w.z, acc4[c]); acc4[c] = fmaf(x.w, w.w, acc4[c]);
+          }
         }
       }
       __syncthreads();
@@ -638,9 +643,15 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_kernel(Persi
         bulk_g2s(Xs + slot * 32 * Hp, dgp_t + int64_t(g + 2) * gs, xbytes, &bar[1 + slot]);
       }
     }
-    part_s[ks][q][lane] = acc;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) part16_s[wrp][c][lane] = acc4[c];
     __syncthreads();
-    if (ks == 0) dh_s[q][lane] = (part_s[0][q][lane] + part_s[1][q][lane]) + (part_s[2][q][lane] + part_s[3][q][lane]);
+    if (wrp < 4) {
+      float d = 0.f;
+#pragma unroll
+      for (int sidx = 0; sidx < 16; ++sidx) d += part16_s[sidx][wrp][lane];
+      dh_s[wrp][lane] = d;
+    }
     __syncthreads();
   }
 }
