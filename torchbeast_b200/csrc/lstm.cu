@@ -663,7 +663,10 @@ static int persistent_ok(const void* kernel, dim3 grid, size_t smem) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   if (!coop) return 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStepThreads, smem) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kStepThreads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
   return int64_t(per_sm) * sms >= int64_t(grid.x) * grid.y;
 }
 
@@ -682,11 +685,13 @@ static int lstm_fwd_persistent(const LstmLayerWs& L, float* hs, const float* not
   const int Hp = padded_h(H);
   const size_t smem = size_t(48) * Hp * sizeof(float) + 16;
   if (smem > 200 * 1024) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(lstm_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+  static size_t attr_smem = 0;
+  if (attr_smem < smem) {
+    if (cudaFuncSetAttribute(lstm_fwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
+      cudaGetLastError();  // not applicable on this device: clear and fall back
       return -1;
-    attr_set = true;
+    }
+    attr_smem = smem;
   }
   dim3 grid((H + kStepUnits - 1) / kStepUnits, (unsigned)((B + 31) / 32));
   if (!persistent_ok((const void*)lstm_fwd_persistent_kernel, grid, smem)) return -1;
@@ -707,11 +712,13 @@ static int lstm_bwd_persistent(const LstmLayerWs& L, const LstmWs& ws, const flo
   const int Hp = padded_h(H);
   const size_t smem = size_t(80) * Hp * sizeof(float) + 32;
   if (smem > 220 * 1024) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(lstm_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess)
+  static size_t attr_smem = 0;
+  if (attr_smem < smem) {
+    if (cudaFuncSetAttribute(lstm_bwd_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
+      cudaGetLastError();
       return -1;
-    attr_set = true;
+    }
+    attr_smem = smem;
   }
   dim3 grid((H + 3) / 4, 1);
   if (!persistent_ok((const void*)lstm_bwd_persistent_kernel, grid, smem)) return -1;
