@@ -144,6 +144,25 @@ int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, c
                          const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
                          int precision, void* workspace, float* grads, void* stream);
 
+/* ---- IMPALA ResNet (polybeast_learner.py:134-266 `Net`) forward / backward ------------------------- */
+
+/* Flat parameter layout = the reference's state_dict order: feat_convs.{0,1,2}.0.{weight,bias}
+ * ((16,4,3,3) (32,16,3,3) (32,32,3,3)), resnet1.{0,1,2}.{1,3}.{weight,bias}, resnet2.{0,1,2}.{1,3}.{weight,bias},
+ * fc.{weight (256,3872), bias}, [core.weight_ih_l0 (1024,257), core.weight_hh_l0 (1024,256), core.bias_ih_l0,
+ * core.bias_hh_l0], policy.{weight (A,257|256), bias}, baseline.{weight, bias}.                       */
+int64_t tb_resnet_param_count(int num_actions, int use_lstm);
+size_t tb_resnet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm, int precision);
+/* polybeast_learner.py:214-266 Net.forward without the action sampling: frame u8 [T1,B,4,84,84], reward f32
+ * [T1,B], notdone f32 [T1,B] and h0,c0/hN,cN f32 [1,B,256] (LSTM only) -> policy_logits [T1,B,A], baseline [T1,B]. */
+int tb_resnet_forward(const uint8_t* frame, const float* reward, const float* notdone, const float* h0,
+                      const float* c0, const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
+                      int precision, void* workspace, float* policy_logits, float* baseline, float* hN, float* cN,
+                      void* stream);
+/* Backward (patch matrices are recomputed from `frame` and the stored activations). */
+int tb_resnet_backward(const uint8_t* frame, const float* grad_logits, const float* grad_baseline,
+                       const float* notdone, const float* params, int64_t T1, int64_t B, int num_actions,
+                       int use_lstm, int precision, void* workspace, float* grads, void* stream);
+
 /* ---- flat-buffer optimizer step ------------------------------------------------------------ */
 
 /* out_sumsq[0] = sum(grads^2) (double accumulation, deterministic).  First half of

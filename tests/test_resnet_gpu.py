@@ -1,0 +1,117 @@
+"""GPU parity of the IMPALA ResNet path (torchbeast_b200.polybeast_learner: Net + learn) against the
+golden fixtures produced by the reference's own polybeast_learner.learn (tests/golden/learn_resnet_*.npz)
+and the torch-CPU oracle; mirrors /root/reference/tests/polybeast_learn_function_test.py and
+polybeast_net_test.py.  fp32 backend: tight tolerances; bf16 tensor-core backend: the mixed-precision
+tolerances explained in test_learner_bf16_gpu.py."""
+import types
+import unittest.mock as mock
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import learner_torch as LT
+from tests.common import golden
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["learn_resnet_T4_B2.npz", "learn_resnet_lstm_T4_B2.npz"]
+
+
+def build(fname, precision="fp32"):
+    from torchbeast_b200 import optim, polybeast_learner
+    g = golden(fname)
+    T, B, A, seed, use_lstm = [int(x) for x in g["meta"]]
+    batch = LT.synthetic_batch(T, B, A, seed=seed, with_last_action=False)
+    params = LT.random_params(LT.resnet_param_shapes(A, bool(use_lstm)), seed=seed + 100)
+    model = polybeast_learner.Net(A, bool(use_lstm), precision=precision)
+    actor = polybeast_learner.Net(A, bool(use_lstm), precision=precision)
+    res = model.load_state_dict(params, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    state = ()
+    if use_lstm:
+        rs = np.random.RandomState(seed + 7)
+        state = tuple(torch.from_numpy(rs.randn(1, B, 256).astype(np.float32) * 0.1) for _ in range(2))
+    opt = optim.RMSprop(model, lr=0.00048, momentum=0, eps=0.01, alpha=0.99)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 1.0)
+    flags = types.SimpleNamespace(reward_clipping="abs_one", discounting=0.99, baseline_cost=0.5, entropy_cost=0.0006,
+                                  grad_norm_clipping=float(g["clip"]), unroll_length=T, batch_size=B, learner_device="cuda")
+    return g, model, actor, batch, params, state, opt, sched, flags
+
+
+def queue_of(batch, state):
+    env = (batch["frame"], batch["reward"], batch["done"], batch["episode_step"], batch["episode_return"])
+    agent = (batch["action"], batch["policy_logits"], batch["baseline"])
+    q = mock.MagicMock()
+    q.__iter__.return_value = iter([((env, agent), state)])
+    q.size.return_value = 0
+    return q
+
+
+@pytest.mark.parametrize("fname", CASES)
+def test_net_forward_matches_reference(fname):
+    g, model, actor, batch, params, state, opt, sched, flags = build(fname)
+    model.eval()
+    cb = {k: v.cuda() for k, v in batch.items()}
+    with torch.no_grad():
+        (action, logits, baseline), new_state = model(dict(frame=cb["frame"], reward=cb["reward"], done=cb["done"]),
+                                                      tuple(s.cuda() for s in state))
+    np.testing.assert_allclose(logits.cpu().numpy(), g["policy_logits"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(baseline.cpu().numpy(), g["baseline"], rtol=1e-4, atol=1e-4)
+    T1, B = batch["frame"].shape[:2]
+    assert tuple(action.shape) == (T1, B) and tuple(logits.shape) == (T1, B, 6) and tuple(baseline.shape) == (T1, B)
+    ol, ob, ostate = LT.resnet_forward(params, batch["frame"], batch["reward"], batch["done"], state)
+    for a, b in zip(new_state, ostate):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("fname", CASES)
+def test_learn_matches_reference(fname):
+    from torchbeast_b200 import polybeast_learner
+    g, model, actor, batch, params, state, opt, sched, flags = build(fname)
+    stats, plogger = {}, mock.Mock()
+    polybeast_learner.learn(flags, queue_of(batch, state), model, actor, opt, sched, stats, plogger)
+    plogger.log.assert_called_once()
+    assert stats["step"] == flags.unroll_length * flags.batch_size
+    for k in ("total_loss", "pg_loss", "baseline_loss", "entropy_loss"):
+        np.testing.assert_allclose(stats[k], float(g[k]), rtol=5e-5, atol=5e-5, err_msg=k)
+        assert stats[k] != 0.0
+    total = 0.0
+    for n, p in model.named_parameters():
+        gr = p.grad.detach().cpu()
+        total += float((gr.double() ** 2).sum())
+        scale = max(float(g["grad_stats/" + n][2]), 1e-6)
+        np.testing.assert_allclose(gr.flatten()[:16].numpy(), g["grad_head/" + n], rtol=5e-3, atol=5e-4 * scale, err_msg=n)
+        np.testing.assert_allclose(float(gr.double().norm()), float(g["grad_stats/" + n][2]), rtol=2e-3, atol=1e-6, err_msg=n)
+        np.testing.assert_allclose(p.detach().cpu().flatten()[:16].numpy(), g["param_head/" + n], rtol=1e-4, atol=1e-5, err_msg=n)
+        assert float(gr.abs().sum()) > 0, n  # every gradient non-zero (reference test :157-179)
+    np.testing.assert_allclose(np.sqrt(total), float(g["clipped_grad_norm"]), rtol=1e-3)
+    for (n, a), (_, b) in zip(actor.named_parameters(), model.named_parameters()):
+        assert torch.equal(a, b), n  # actor weights == learner weights (reference test :108-119)
+
+
+@pytest.mark.parametrize("fname", CASES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_backward_vs_oracle_fixed_cotangents(fname, precision):
+    g, model, actor, batch, params, state, opt, sched, flags = build(fname, precision)
+    p64 = {k: v.double().requires_grad_(True) for k, v in params.items()}
+    ol, ob, _ = LT.resnet_forward(p64, batch["frame"], batch["reward"], batch["done"], tuple(s.double() for s in state))
+    rs = np.random.RandomState(0)
+    w1 = torch.from_numpy(rs.randn(*ol.shape)); w2 = torch.from_numpy(rs.randn(*ob.shape))
+    names = list(p64)
+    ref = dict(zip(names, torch.autograd.grad((ol * w1).sum() + (ob * w2).sum(), [p64[n] for n in names])))
+    cb = {k: v.cuda() for k, v in batch.items()}
+    out = model.learner_forward(cb, tuple(s.cuda() for s in state))
+    rel = lambda a, b: float((a - b).norm() / b.norm().clamp_min(1e-30))
+    ftol = 1e-5 if precision == "fp32" else 2e-2
+    assert rel(out.policy_logits.cpu().double(), ol.detach()) < ftol
+    assert rel(out.baseline.cpu().double(), ob.detach()) < ftol
+    model.learner_backward(w1.float().cuda().contiguous(), w2.float().cuda().contiguous())
+    report = {}
+    for n, p in model.named_parameters():
+        got = p.grad.cpu().double()
+        cos = float((got * ref[n]).sum() / (got.norm() * ref[n].norm()).clamp_min(1e-30))
+        report[n] = (round(rel(got, ref[n]), 5), round(cos, 6))
+    lim = (1e-4, 0.999999) if precision == "fp32" else (0.2, 0.98)
+    bad = {n: v for n, v in report.items() if v[0] >= lim[0] or v[1] <= lim[1]}
+    assert not bad, (bad, report)

@@ -41,6 +41,10 @@ _SIGNATURES = {
     "tb_atarinet_param_count": ([_int, _int], _i64),
     "tb_atarinet_workspace_bytes": ([_i64, _i64, _int, _int, _int], _c.c_size_t),
     "tb_atarinet_forward": ([_vp] * 7 + [_i64, _i64, _int, _int, _int] + [_vp] * 6, _int),
+    "tb_resnet_param_count": ([_int, _int], _i64),
+    "tb_resnet_workspace_bytes": ([_i64, _i64, _int, _int, _int], _c.c_size_t),
+    "tb_resnet_forward": ([_vp] * 6 + [_i64, _i64, _int, _int, _int] + [_vp] * 6, _int),
+    "tb_resnet_backward": ([_vp] * 5 + [_i64, _i64, _int, _int, _int, _vp, _vp, _vp], _int),
     "tb_grad_sumsq_f32": ([_vp, _i64, _vp, _vp, _vp], _int),
     "tb_clip_rmsprop_step_f32": ([_vp] * 4 + [_i64, _vp, _f32, _vp, _f32, _f32, _f32, _f32, _vp, _vp], _int),
     "tb_atarinet_backward": ([_vp] * 4 + [_i64, _i64, _int, _int, _int, _vp, _vp, _vp], _int),

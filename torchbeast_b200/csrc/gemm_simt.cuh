@@ -23,6 +23,8 @@ struct GemmEpilogue {
   const float* mask = nullptr;   // [M, ldmask]: C = acc * (mask > 0)   (ReLU backward)
   int64_t ldmask = 0;
   int accumulate = 0;            // C += acc
+  const float* addend = nullptr; // [M, ldadd]: C = acc + bias + addend (residual connection), applied last
+  int64_t ldadd = 0;
   // split-K reduce only: output column permutation n = p*Q + q  ->  q*P + p (weight-grad unpack)
   int permP = 1, permQ = 1;
   float scale = 1.0f;            // (split-K reduce only) multiplies the reduced sum
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_simt_kernel(GemmArgs g) {
       if (g.ep.bias) v += g.ep.bias[n];
       if (g.ep.relu) v = fmaxf(v, 0.0f);
       if (g.ep.mask) v = (g.ep.mask[m * g.ep.ldmask + n] > 0.0f) ? v : 0.0f;
+      if (g.ep.addend) v += g.ep.addend[m * g.ep.ldadd + n];
       float* c = g.C + m * g.ldc + n;
       *c = g.ep.accumulate ? (*c + v) : v;
     }

@@ -208,6 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ep.relu) x = fmaxf(x, 0.0f);
           if (ep.mask && n < N) x = (ep.mask[r * ep.ldmask + n] > 0.0f) ? x : 0.0f;
           if (ep.mask16 && n < N) x = (__bfloat162float(ep.mask16[r * ep.ldmask + n]) > 0.0f) ? x : 0.0f;
+          if (ep.addend16 && n < N) x += __bfloat162float(ep.addend16[r * ep.ldadd + n]);
           o[j] = x;
         }
         if (ep.C) {

@@ -14,6 +14,7 @@ struct TcEpilogue {
   int relu = 0;
   const float* mask = nullptr; int64_t ldmask = 0;   // out = (mask > 0) ? out : 0   (ReLU backward)
   const __nv_bfloat16* mask16 = nullptr;             // same, mask stored in bf16 (uses ldmask)
+  const __nv_bfloat16* addend16 = nullptr; int64_t ldadd = 0;  // out += addend (residual connection), applied last
   int permP = 1, permQ = 1;                          // (split-K reduce only) weight-grad column un-pack
   const char* tag = "gemm_tc";
 };

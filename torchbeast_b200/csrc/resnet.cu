@@ -1,0 +1,393 @@
+// IMPALA "deep" ResNet (polybeast_learner.Net) forward / backward for the learner, behind the C ABI.
+//
+// Replaces /root/reference/torchbeast/polybeast_learner.py:214-266 (Net.forward) and its autograd graph:
+//   for ch in (16, 32, 32):  x = maxpool3x3/2(conv3x3(x));  x += conv(relu(conv(relu(x))));  x += conv(relu(conv(relu(x))))
+//   x = relu(x) -> fc 3872->256 -> relu -> cat[x, clip(reward)] -> [LSTM(257->256)] -> policy / baseline
+// Same construction as atarinet.cu: NHWC activations, every conv a patch-matrix GEMM through the shared
+// GEMM backends (fp32 SIMT for parity, bf16 tcgen05 for throughput - the activation element type T
+// follows the backend), residual adds fused into the GEMM epilogue, ReLU-on-read fused into the patch
+// gather, ReLU masks and skip-gradients fused into the gather-form col2im, weights/gradients in ONE
+// flat buffer in state_dict order.  Patch matrices are recomputed in the backward pass (a gather is
+// cheaper than keeping 15 of them resident).
+#include <type_traits>
+
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "lstm.cuh"
+#include "net_kernels.cuh"
+#include "resnet_kernels.cuh"
+
+namespace tb {
+
+namespace {
+
+constexpr int kSections = 3;
+constexpr int kSecCh[kSections] = {16, 32, 32};
+constexpr int kSecCin[kSections] = {4, 16, 32};
+constexpr int kSecS[kSections] = {84, 42, 21};     // spatial size of the section's feat conv
+constexpr int kSecSo[kSections] = {42, 21, 11};    // after the max-pool
+constexpr int kFcIn = 32 * 11 * 11;                // 3872
+constexpr int kFcOut = 256;
+constexpr int kLstmH = 256;
+constexpr int64_t kScratchFloats = int64_t(8) << 20;
+
+struct ConvP { int64_t w, b; };
+struct ResParams {
+  ConvP feat[kSections], blk[kSections][4];  // blk: r1a, r1b, r2a, r2b
+  int64_t fc_w, fc_b, lstm[4], policy_w, policy_b, baseline_w, baseline_b, total;
+  int core_in, core_out;
+};
+
+ResParams res_params(int A, int use_lstm) {
+  ResParams p;
+  int64_t o = 0;
+  auto take = [&](int64_t n) { int64_t r = o; o += n; return r; };
+  for (int i = 0; i < kSections; ++i) { p.feat[i].w = take(int64_t(kSecCh[i]) * kSecCin[i] * 9); p.feat[i].b = take(kSecCh[i]); }
+  for (int blk = 0; blk < 2; ++blk)     // resnet1.{0,1,2}.{1,3} then resnet2.{0,1,2}.{1,3}
+    for (int i = 0; i < kSections; ++i)
+      for (int j = 0; j < 2; ++j) {
+        p.blk[i][blk * 2 + j].w = take(int64_t(kSecCh[i]) * kSecCh[i] * 9);
+        p.blk[i][blk * 2 + j].b = take(kSecCh[i]);
+      }
+  p.fc_w = take(int64_t(kFcOut) * kFcIn); p.fc_b = take(kFcOut);
+  p.core_in = kFcOut + 1;
+  p.core_out = use_lstm ? kLstmH : p.core_in;
+  for (int k = 0; k < 4; ++k) p.lstm[k] = -1;
+  if (use_lstm) {
+    p.lstm[0] = take(int64_t(4) * kLstmH * p.core_in); p.lstm[1] = take(int64_t(4) * kLstmH * kLstmH);
+    p.lstm[2] = take(4 * kLstmH); p.lstm[3] = take(4 * kLstmH);
+  }
+  p.policy_w = take(int64_t(A) * p.core_out); p.policy_b = take(A);
+  p.baseline_w = take(p.core_out); p.baseline_b = take(1);
+  p.total = o;
+  return p;
+}
+
+template <typename T> struct Sec { T *P, *X0, *Y1, *X1, *Y2, *X2; };
+
+template <typename T>
+struct ResWs {
+  Sec<T> s[kSections];
+  T *fcin, *dfc, *dfcin, *g[3], *col, *dcol;
+  T *wfeat[kSections], *wblk[kSections][4], *wfc;
+  float *core_in, *core_out, *dcore_out, *dcore_in, *splitk, *colsum_scratch;
+  LstmWs lstm;
+  size_t bytes;
+};
+
+inline int64_t ldk_of(int cin, bool bf16) { const int64_t k = int64_t(cin) * 9; return bf16 ? ((k + 7) & ~int64_t(7)) : k; }
+
+template <typename T>
+ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lstm) {
+  constexpr bool kBf16 = !std::is_same<T, float>::value;
+  ResWs<T> w;
+  size_t off = 0;
+  auto take = [&](size_t nbytes) { void* p = base ? static_cast<char*>(base) + off : nullptr; off += (nbytes + 255) & ~size_t(255); return p; };
+  auto takeT = [&](int64_t n) { return static_cast<T*>(take(size_t(n) * sizeof(T))); };
+  auto takef = [&](int64_t n) { return static_cast<float*>(take(size_t(n) * sizeof(float))); };
+  const ResParams pp = res_params(A, use_lstm);
+  int64_t maxact = 0;
+  for (int i = 0; i < kSections; ++i) {
+    const int64_t big = N * kSecS[i] * kSecS[i] * kSecCh[i], small = N * kSecSo[i] * kSecSo[i] * kSecCh[i];
+    w.s[i].P = takeT(big); w.s[i].X0 = takeT(small); w.s[i].Y1 = takeT(small); w.s[i].X1 = takeT(small);
+    w.s[i].Y2 = takeT(small); w.s[i].X2 = takeT(small);
+    if (big > maxact) maxact = big;
+  }
+  w.fcin = takeT(N * kFcIn); w.dfc = takeT(N * kFcOut); w.dfcin = takeT(N * kFcIn);
+  for (int k = 0; k < 3; ++k) w.g[k] = takeT(maxact);
+  int64_t maxcol = 0;
+  for (int i = 0; i < kSections; ++i) {
+    const int64_t a = N * kSecS[i] * kSecS[i] * ldk_of(kSecCin[i], kBf16), b = N * kSecSo[i] * kSecSo[i] * ldk_of(kSecCh[i], kBf16);
+    if (a > maxcol) maxcol = a;
+    if (b > maxcol) maxcol = b;
+  }
+  w.col = takeT(maxcol); w.dcol = takeT(maxcol);
+  for (int i = 0; i < kSections; ++i) {
+    w.wfeat[i] = takeT(int64_t(kSecCh[i]) * ldk_of(kSecCin[i], kBf16));
+    for (int j = 0; j < 4; ++j) w.wblk[i][j] = takeT(int64_t(kSecCh[i]) * ldk_of(kSecCh[i], kBf16));
+  }
+  w.wfc = takeT(int64_t(kFcOut) * kFcIn);
+  w.core_in = takef(N * pp.core_in);
+  w.core_out = use_lstm ? takef(N * pp.core_out) : w.core_in;
+  w.dcore_out = takef(N * (pp.core_in > pp.core_out ? pp.core_in : pp.core_out));
+  w.dcore_in = use_lstm ? takef(N * pp.core_in) : w.dcore_out;
+  w.splitk = takef(kScratchFloats);
+  w.colsum_scratch = takef(colsum_scratch_floats(4 * kLstmH));
+  if (use_lstm) {
+    const size_t lb = lstm_ws_bytes(T1, B, pp.core_in, kLstmH, 1, kBf16 ? 1 : 0);
+    w.lstm = lstm_ws(take(lb), T1, B, pp.core_in, kLstmH, 1, kBf16 ? 1 : 0);
+  } else {
+    w.lstm = LstmWs();
+  }
+  w.bytes = off;
+  return w;
+}
+
+#define TB_TRY(expr)        \
+  do {                      \
+    int _rc = (expr);       \
+    if (_rc) return _rc;    \
+  } while (0)
+
+int splits_simt(int64_t M, int64_t N, int64_t K) {
+  const int64_t bm = (N <= 32) ? 128 : (M <= 64 ? 64 : 128), bn = (N <= 32) ? 32 : 64;
+  const int64_t tiles = ((M + bm - 1) / bm) * ((N + bn - 1) / bn);
+  int64_t s = (2 * kNumSMsB200 + tiles - 1) / tiles;
+  const int64_t kt = (K + kGemmBK - 1) / kGemmBK;
+  if (s > kt / 4) s = kt / 4;
+  if (s * M * N > kScratchFloats) s = kScratchFloats / (M * N);
+  if (s > 128) s = 128;
+  return int(s < 1 ? 1 : s);
+}
+int splits_tc(int64_t M, int64_t N, int64_t K) {
+  const int64_t bn = N <= 64 ? 64 : 128;
+  const int64_t tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  int64_t s = (2 * kNumSMsB200 + tiles - 1) / tiles;
+  const int64_t kb = (K + 63) / 64;
+  if (s > kb / 4) s = kb / 4;
+  if (s * M * N > kScratchFloats) s = kScratchFloats / (M * N);
+  if (s > 148) s = 148;
+  return int(s < 1 ? 1 : s);
+}
+
+// ---- backend-generic GEMM wrappers ------------------------------------------------------------
+// forward: out[M,cout] = scale * col[M,K] . W[cout,K]^T + bias (+relu) (+addend)
+int conv_fwd(const float* col, const float* W, float* out, int64_t M, int cout, int64_t K, int64_t ldk, const float* bias,
+             int relu, const float* addend, float /*scale*/, int64_t ldc, const char* tag, cudaStream_t st) {
+  GemmEpilogue ep; ep.bias = bias; ep.relu = relu; ep.addend = addend; ep.ldadd = cout; ep.tag = tag;
+  return gemm_simt<float, float, false, true>(col, W, out, M, cout, K, ldk, ldk, ldc, ep, 1, nullptr, st);
+}
+int conv_fwd_u8(const uint8_t* col, const float* W, float* out, int64_t M, int cout, int64_t K, int64_t ldk, const float* bias,
+                const char* tag, cudaStream_t st) {
+  GemmEpilogue ep; ep.bias = bias; ep.tag = tag;
+  return gemm_simt<uint8_t, float, false, true>(col, W, out, M, cout, K, ldk, ldk, cout, ep, 1, nullptr, st);
+}
+int conv_fwd(const __nv_bfloat16* col, const __nv_bfloat16* W, __nv_bfloat16* out, int64_t M, int cout, int64_t K, int64_t ldk,
+             const float* bias, int relu, const __nv_bfloat16* addend, float scale, int64_t ldc, const char* tag, cudaStream_t st) {
+  TcEpilogue te; te.C16 = out; te.ldc16 = ldc; te.bias = bias; te.relu = relu; te.addend16 = addend; te.ldadd = cout;
+  te.scale = scale; te.tag = tag;
+  return gemm_tc_bf16(col, W, M, cout, K, ldk, ldk, te, st);
+}
+// dgrad: dcol[M,K] = dY[M,cout] . W[cout,K]
+int conv_dgrad(const float* dY, const float* W, float* dcol, int64_t M, int cout, int64_t K, int64_t ldk, const char* tag,
+               cudaStream_t st) {
+  GemmEpilogue ep; ep.tag = tag;
+  return gemm_simt<float, float, false, false>(dY, W, dcol, M, K, cout, cout, ldk, ldk, ep, 1, nullptr, st);
+}
+int conv_dgrad(const __nv_bfloat16* dY, const __nv_bfloat16* W, __nv_bfloat16* dcol, int64_t M, int cout, int64_t K, int64_t ldk,
+               const char* tag, cudaStream_t st) {
+  TcEpilogue te; te.C16 = dcol; te.ldc16 = ldk; te.tag = tag;
+  return gemm_tc_bf16_ex(dY, W, M, K, cout, cout, ldk, false, true, te, 1, nullptr, st);
+}
+// wgrad: dW[cout,K] (fp32, un-packed by the split-K reduce) = scale * dY[M,cout]^T . col[M,K]
+int conv_wgrad(const float* dY, const void* col, bool col_u8, float* dW, int64_t M, int cout, int64_t K, int64_t ldk, int permP,
+               int permQ, float /*scale: the u8 operand is read as x/255*/, float* scratch, const char* tag, cudaStream_t st) {
+  GemmEpilogue ep; ep.permP = permP; ep.permQ = permQ; ep.tag = tag;
+  const int s = splits_simt(cout, K, M);
+  if (col_u8)
+    return gemm_simt<float, uint8_t, true, false>(dY, static_cast<const uint8_t*>(col), dW, cout, K, M, cout, ldk, K, ep, s, scratch, st);
+  return gemm_simt<float, float, true, false>(dY, static_cast<const float*>(col), dW, cout, K, M, cout, ldk, K, ep, s, scratch, st);
+}
+int conv_wgrad(const __nv_bfloat16* dY, const void* col, bool, float* dW, int64_t M, int cout, int64_t K, int64_t ldk, int permP,
+               int permQ, float scale, float* scratch, const char* tag, cudaStream_t st) {
+  TcEpilogue te; te.C = dW; te.ldc = K; te.permP = permP; te.permQ = permQ; te.scale = scale; te.tag = tag;
+  return gemm_tc_bf16_ex(dY, col, cout, K, M, cout, ldk, true, true, te, splits_tc(cout, K, M), scratch, st);
+}
+int pack_w(const float* in, float* out, int64_t O, int P, int Q, int64_t, cudaStream_t st) { return permute_pq(in, out, O, P, Q, st); }
+int pack_w(const float* in, __nv_bfloat16* out, int64_t O, int P, int Q, int64_t ld, cudaStream_t st) {
+  return pack_weights_bf16(in, out, O, P, Q, ld, st);
+}
+// fc forward into the fp32 core buffer
+int fc_fwd(const float* x, const float* W, float* core, int64_t N, int64_t ldc, const float* bias, cudaStream_t st) {
+  GemmEpilogue ep; ep.bias = bias; ep.relu = 1; ep.tag = "fc_fwd";
+  return gemm_simt<float, float, false, true>(x, W, core, N, kFcOut, kFcIn, kFcIn, kFcIn, ldc, ep, 1, nullptr, st);
+}
+int fc_fwd(const __nv_bfloat16* x, const __nv_bfloat16* W, float* core, int64_t N, int64_t ldc, const float* bias, cudaStream_t st) {
+  TcEpilogue te; te.C = core; te.ldc = ldc; te.bias = bias; te.relu = 1; te.tag = "fc_fwd";
+  return gemm_tc_bf16(x, W, N, kFcOut, kFcIn, kFcIn, kFcIn, te, st);
+}
+
+template <typename T>
+struct Impl {
+  static constexpr bool kBf16 = !std::is_same<T, float>::value;
+  using ColFirst = typename std::conditional<kBf16, __nv_bfloat16, uint8_t>::type;
+
+  static int forward(const uint8_t* frame, const float* reward, const float* notdone, const float* h0, const float* c0,
+                     const float* P, int64_t T1, int64_t B, int A, int use_lstm, void* workspace, float* policy_logits,
+                     float* baseline, float* hN, float* cN, cudaStream_t st) {
+    const int64_t N = T1 * B;
+    const ResParams pp = res_params(A, use_lstm);
+    ResWs<T> w = res_ws<T>(workspace, N, T1, B, A, use_lstm);
+    // weight pack: [o, c, kh, kw] -> [o, (kh,kw), c]; first conv keeps (c,kh,kw); fc: [o, c, (h,w)] -> [o, (h,w), c]
+    TB_TRY(pack_w(P + pp.feat[0].w, w.wfeat[0], kSecCh[0], 1, 36, ldk_of(4, kBf16), st));
+    for (int i = 0; i < kSections; ++i) {
+      if (i > 0) TB_TRY(pack_w(P + pp.feat[i].w, w.wfeat[i], kSecCh[i], 9, kSecCin[i], ldk_of(kSecCin[i], kBf16), st));
+      for (int j = 0; j < 4; ++j) TB_TRY(pack_w(P + pp.blk[i][j].w, w.wblk[i][j], kSecCh[i], 9, kSecCh[i], ldk_of(kSecCh[i], kBf16), st));
+    }
+    TB_TRY(pack_w(P + pp.fc_w, w.wfc, kFcOut, 121, 32, kFcIn, st));
+    const T* xin = nullptr;
+    for (int i = 0; i < kSections; ++i) {
+      const int S = kSecS[i], So = kSecSo[i], ch = kSecCh[i], cin = kSecCin[i];
+      const int64_t M = N * S * S, Mo = N * So * So;
+      const int64_t ldk_in = ldk_of(cin, kBf16), ldk = ldk_of(ch, kBf16);
+      if (i == 0) {
+        TB_TRY(im2col3x3_u8_nchw<ColFirst>(frame, reinterpret_cast<ColFirst*>(w.col), N, 4, S, S, ldk_in, st));
+        if constexpr (kBf16) {
+          TB_TRY(conv_fwd(w.col, w.wfeat[0], w.s[0].P, M, ch, 36, ldk_in, P + pp.feat[0].b, 0, nullptr, 1.0f / 255.0f, ch, "feat_conv_fwd", st));
+        } else {
+          TB_TRY(conv_fwd_u8(reinterpret_cast<const uint8_t*>(w.col), w.wfeat[0], w.s[0].P, M, ch, 36, ldk_in, P + pp.feat[0].b,
+                             "feat_conv_fwd", st));
+        }
+      } else {
+        TB_TRY(im2col3x3<T>(xin, w.col, N, S, S, cin, ldk_in, 0, st));
+        TB_TRY(conv_fwd(w.col, w.wfeat[i], w.s[i].P, M, ch, int64_t(cin) * 9, ldk_in, P + pp.feat[i].b, 0, nullptr, 1.0f, ch,
+                        "feat_conv_fwd", st));
+      }
+      TB_TRY(maxpool3x3s2_fwd<T>(w.s[i].P, w.s[i].X0, N, S, S, ch, st));
+      const T* ins[4] = {w.s[i].X0, w.s[i].Y1, w.s[i].X1, w.s[i].Y2};
+      T* outs[4] = {w.s[i].Y1, w.s[i].X1, w.s[i].Y2, w.s[i].X2};
+      const T* adds[4] = {nullptr, w.s[i].X0, nullptr, w.s[i].X1};
+      for (int j = 0; j < 4; ++j) {
+        TB_TRY(im2col3x3<T>(ins[j], w.col, N, So, So, ch, ldk, 1, st));
+        TB_TRY(conv_fwd(w.col, w.wblk[i][j], outs[j], Mo, ch, int64_t(ch) * 9, ldk, P + pp.blk[i][j].b, 0, adds[j], 1.0f, ch,
+                        "res_conv_fwd", st));
+      }
+      xin = w.s[i].X2;
+    }
+    TB_TRY(relu_fwd<T>(w.s[2].X2, w.fcin, N * kFcIn, st));
+    TB_TRY(fc_fwd(w.fcin, w.wfc, w.core_in, N, pp.core_in, P + pp.fc_b, st));
+    TB_TRY(core_extras(w.core_in, pp.core_in, N, kFcOut, reward, nullptr, 0, st));
+    if (use_lstm) {
+      LstmParams lp;
+      lp.w_ih[0] = P + pp.lstm[0]; lp.w_hh[0] = P + pp.lstm[1]; lp.b_ih[0] = P + pp.lstm[2]; lp.b_hh[0] = P + pp.lstm[3];
+      lp.w_ih[1] = lp.w_hh[1] = lp.b_ih[1] = lp.b_hh[1] = nullptr;
+      TB_TRY(lstm_forward(w.core_in, notdone, h0, c0, lp, T1, B, pp.core_in, kLstmH, 1, w.lstm, w.core_out, hN, cN, w.splitk,
+                          kBf16 ? 1 : 0, st));
+    }
+    GemmEpilogue ep; ep.bias = P + pp.policy_b; ep.tag = "heads_fwd";
+    TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.policy_w, policy_logits, N, A, pp.core_out, pp.core_out,
+                                                  pp.core_out, A, ep, 1, nullptr, st)));
+    ep = GemmEpilogue(); ep.bias = P + pp.baseline_b; ep.tag = "heads_fwd";
+    TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.baseline_w, baseline, N, 1, pp.core_out, pp.core_out,
+                                                  pp.core_out, 1, ep, 1, nullptr, st)));
+    return 0;
+  }
+
+  // one 3x3 conv backward: bias grad, weight grad (patch matrix recomputed from the stored input), and - if dx - the
+  // input gradient dx = col2im(dY . W) * (relu_in ? x > 0 : 1) + addend
+  static int conv_bwd(const T* x, bool relu_in, const T* dY, const T* Wp, float* dW, float* db, T* dx, const T* addend, int64_t N,
+                      int S, int cin, int cout, ResWs<T>& w, cudaStream_t st) {
+    const int64_t M = N * S * S, K = int64_t(cin) * 9, ldk = ldk_of(cin, kBf16);
+    TB_TRY(colsum_t<T>(dY, db, M, cout, cout, w.colsum_scratch, st));
+    TB_TRY(im2col3x3<T>(x, w.col, N, S, S, cin, ldk, relu_in ? 1 : 0, st));
+    TB_TRY(conv_wgrad(dY, w.col, false, dW, M, cout, K, ldk, 9, cin, 1.0f, w.splitk, "res_conv_wgrad", st));
+    if (dx) {
+      TB_TRY(conv_dgrad(dY, Wp, w.dcol, M, cout, K, ldk, "res_conv_dgrad", st));
+      TB_TRY(col2im3x3<T>(w.dcol, relu_in ? x : nullptr, addend, dx, N, S, S, cin, ldk, st));
+    }
+    return 0;
+  }
+
+  static int backward(const uint8_t* frame, const float* grad_logits, const float* grad_baseline, const float* notdone,
+                      const float* P, int64_t T1, int64_t B, int A, int use_lstm, void* workspace, float* G, cudaStream_t st) {
+    const int64_t N = T1 * B;
+    const ResParams pp = res_params(A, use_lstm);
+    ResWs<T> w = res_ws<T>(workspace, N, T1, B, A, use_lstm);
+    GemmEpilogue ep;
+    // heads
+    ep = GemmEpilogue(); ep.tag = "heads_dgrad";
+    TB_TRY((gemm_simt<float, float, false, false>(grad_logits, P + pp.policy_w, w.dcore_out, N, pp.core_out, A, A, pp.core_out,
+                                                   pp.core_out, ep, 1, nullptr, st)));
+    ep.accumulate = 1;
+    TB_TRY((gemm_simt<float, float, false, false>(grad_baseline, P + pp.baseline_w, w.dcore_out, N, pp.core_out, 1, 1,
+                                                   pp.core_out, pp.core_out, ep, 1, nullptr, st)));
+    ep = GemmEpilogue(); ep.tag = "heads_wgrad";
+    TB_TRY((gemm_simt<float, float, true, false>(grad_logits, w.core_out, G + pp.policy_w, A, pp.core_out, N, A, pp.core_out,
+                                                  pp.core_out, ep, splits_simt(A, pp.core_out, N), w.splitk, st)));
+    TB_TRY((gemm_simt<float, float, true, false>(grad_baseline, w.core_out, G + pp.baseline_w, 1, pp.core_out, N, 1, pp.core_out,
+                                                  pp.core_out, ep, splits_simt(1, pp.core_out, N), w.splitk, st)));
+    TB_TRY(colsum(grad_logits, G + pp.policy_b, N, A, A, w.colsum_scratch, st));
+    TB_TRY(colsum(grad_baseline, G + pp.baseline_b, N, 1, 1, w.colsum_scratch, st));
+    if (use_lstm) {
+      LstmParams lp; LstmGrads lg;
+      lp.w_ih[0] = P + pp.lstm[0]; lp.w_hh[0] = P + pp.lstm[1]; lp.b_ih[0] = P + pp.lstm[2]; lp.b_hh[0] = P + pp.lstm[3];
+      lg.w_ih[0] = G + pp.lstm[0]; lg.w_hh[0] = G + pp.lstm[1]; lg.b_ih[0] = G + pp.lstm[2]; lg.b_hh[0] = G + pp.lstm[3];
+      lp.w_ih[1] = lp.w_hh[1] = lp.b_ih[1] = lp.b_hh[1] = nullptr;
+      lg.w_ih[1] = lg.w_hh[1] = lg.b_ih[1] = lg.b_hh[1] = nullptr;
+      TB_TRY(lstm_backward(w.dcore_out, w.core_in, notdone, lp, lg, T1, B, pp.core_in, kLstmH, 1, w.lstm, w.dcore_in, w.splitk,
+                           w.colsum_scratch, kBf16 ? 1 : 0, st));
+    }
+    // fc
+    TB_TRY(relu_mask_inplace(w.dcore_in, w.core_in, N, kFcOut, pp.core_in, pp.core_in, st));
+    TB_TRY(colsum(w.dcore_in, G + pp.fc_b, N, kFcOut, pp.core_in, w.colsum_scratch, st));
+    TB_TRY(convert_from_f32<T>(w.dcore_in, w.dfc, N, kFcOut, pp.core_in, kFcOut, st));
+    TB_TRY(conv_wgrad(w.dfc, w.fcin, false, G + pp.fc_w, N, kFcOut, kFcIn, kFcIn, 121, 32, 1.0f, w.splitk, "fc_wgrad", st));
+    TB_TRY(conv_dgrad(w.dfc, w.wfc, w.dfcin, N, kFcOut, kFcIn, kFcIn, "fc_dgrad", st));
+    T* g0 = w.g[0]; T* g1 = w.g[1]; T* g2 = w.g[2];
+    TB_TRY(relu_bwd<T>(w.s[2].X2, w.dfcin, g0, N * kFcIn, st));  // dL/dX2 of the last section
+    for (int i = kSections - 1; i >= 0; --i) {
+      const int S = kSecS[i], So = kSecSo[i], ch = kSecCh[i], cin = kSecCin[i];
+      Sec<T>& s = w.s[i];
+      // block 2: X2 = X1 + conv_b(relu(Y2)), Y2 = conv_a(relu(X1))
+      TB_TRY(conv_bwd(s.Y2, true, g0, w.wblk[i][3], G + pp.blk[i][3].w, G + pp.blk[i][3].b, g1, nullptr, N, So, ch, ch, w, st));
+      TB_TRY(conv_bwd(s.X1, true, g1, w.wblk[i][2], G + pp.blk[i][2].w, G + pp.blk[i][2].b, g2, g0, N, So, ch, ch, w, st));
+      // block 1: X1 = X0 + conv_b(relu(Y1)), Y1 = conv_a(relu(X0))
+      TB_TRY(conv_bwd(s.Y1, true, g2, w.wblk[i][1], G + pp.blk[i][1].w, G + pp.blk[i][1].b, g0, nullptr, N, So, ch, ch, w, st));
+      TB_TRY(conv_bwd(s.X0, true, g0, w.wblk[i][0], G + pp.blk[i][0].w, G + pp.blk[i][0].b, g1, g2, N, So, ch, ch, w, st));
+      TB_TRY(maxpool3x3s2_bwd<T>(s.P, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
+      const int64_t M = N * S * S;
+      if (i == 0) {
+        const int64_t ldk_in = ldk_of(4, kBf16);
+        TB_TRY(colsum_t<T>(g2, G + pp.feat[0].b, M, ch, ch, w.colsum_scratch, st));
+        TB_TRY(im2col3x3_u8_nchw<ColFirst>(frame, reinterpret_cast<ColFirst*>(w.col), N, 4, S, S, ldk_in, st));
+        TB_TRY(conv_wgrad(g2, w.col, !kBf16, G + pp.feat[0].w, M, ch, 36, ldk_in, 1, 1, 1.0f / 255.0f, w.splitk, "feat_conv_wgrad", st));
+      } else {
+        TB_TRY(conv_bwd(w.s[i - 1].X2, false, g2, w.wfeat[i], G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S, cin, ch, w, st));
+      }
+    }
+    return 0;
+  }
+};
+
+}  // namespace
+}  // namespace tb
+
+using namespace tb;
+
+extern "C" {
+
+int64_t tb_resnet_param_count(int num_actions, int use_lstm) { return res_params(num_actions, use_lstm).total; }
+
+size_t tb_resnet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm, int precision) {
+  return precision ? res_ws<__nv_bfloat16>(nullptr, T1 * B, T1, B, num_actions, use_lstm).bytes
+                   : res_ws<float>(nullptr, T1 * B, T1, B, num_actions, use_lstm).bytes;
+}
+
+int tb_resnet_forward(const uint8_t* frame, const float* reward, const float* notdone, const float* h0, const float* c0,
+                      const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm, int precision, void* workspace,
+                      float* policy_logits, float* baseline, float* hN, float* cN, void* stream) {
+  TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "resnet_forward: bad sizes");
+  TB_REQUIRE(frame && reward && params && workspace && policy_logits && baseline, "resnet_forward: null pointer");
+  TB_REQUIRE(!use_lstm || (notdone && h0 && c0 && hN && cN), "resnet_forward: LSTM needs notdone/h0/c0/hN/cN");
+  TB_REQUIRE(precision == 0 || precision == 1, "resnet_forward: precision must be 0 or 1");
+  if (precision)
+    return Impl<__nv_bfloat16>::forward(frame, reward, notdone, h0, c0, params, T1, B, num_actions, use_lstm, workspace,
+                                        policy_logits, baseline, hN, cN, (cudaStream_t)stream);
+  return Impl<float>::forward(frame, reward, notdone, h0, c0, params, T1, B, num_actions, use_lstm, workspace, policy_logits,
+                              baseline, hN, cN, (cudaStream_t)stream);
+}
+
+int tb_resnet_backward(const uint8_t* frame, const float* grad_logits, const float* grad_baseline, const float* notdone,
+                       const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm, int precision,
+                       void* workspace, float* grads, void* stream) {
+  TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "resnet_backward: bad sizes");
+  TB_REQUIRE(frame && grad_logits && grad_baseline && params && workspace && grads, "resnet_backward: null pointer");
+  TB_REQUIRE(!use_lstm || notdone, "resnet_backward: LSTM needs notdone");
+  if (precision)
+    return Impl<__nv_bfloat16>::backward(frame, grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm,
+                                         workspace, grads, (cudaStream_t)stream);
+  return Impl<float>::backward(frame, grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm, workspace,
+                               grads, (cudaStream_t)stream);
+}
+
+}  // extern "C"

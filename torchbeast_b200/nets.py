@@ -59,12 +59,15 @@ class FlatParamModule(nn.Module):
         self._views = []
         off = 0
         for name, shape in self._spec:
-            group, leaf = name.split(".")
-            if not hasattr(self, group):
-                setattr(self, group, _ParamGroup())
+            *groups, leaf = name.split(".")
+            mod = self
+            for gname in groups:  # nested namespaces: "feat_convs.0.0.weight" -> feat_convs -> "0" -> "0"
+                if gname not in mod._modules:
+                    mod.add_module(gname, _ParamGroup())
+                mod = mod._modules[gname]
             n = _numel(shape)
             p = nn.Parameter(self._flat[off:off + n].view(shape))
-            getattr(self, group).register_parameter(leaf, p)
+            mod.register_parameter(leaf, p)
             self._views.append((p, off, n, shape))
             off += n
         self._total = total
@@ -298,6 +301,165 @@ class AtariNet(FlatParamModule):
             action = torch.argmax(flat_logits, dim=1)  # don't sample when testing
         out = dict(policy_logits=logits, baseline=baseline, action=action.view(T, B))
         return out, ((hN, cN) if self.use_lstm else tuple())
+
+
+
+
+def resnet_param_spec(num_actions, use_lstm):
+    """State_dict order/shapes of the reference's polybeast_learner.Net (pl:134-204)."""
+    spec = []
+    cin = 4
+    for i, ch in enumerate([16, 32, 32]):
+        spec += [("feat_convs.%d.0.weight" % i, (ch, cin, 3, 3)), ("feat_convs.%d.0.bias" % i, (ch,))]
+        cin = ch
+    for blk in ("resnet1", "resnet2"):
+        for i, ch in enumerate([16, 32, 32]):
+            for j in (1, 3):
+                spec += [("%s.%d.%d.weight" % (blk, i, j), (ch, ch, 3, 3)), ("%s.%d.%d.bias" % (blk, i, j), (ch,))]
+    spec += [("fc.weight", (256, 3872)), ("fc.bias", (256,))]
+    head_in = 257
+    if use_lstm:
+        spec += [("core.weight_ih_l0", (1024, 257)), ("core.weight_hh_l0", (1024, 256)),
+                 ("core.bias_ih_l0", (1024,)), ("core.bias_hh_l0", (1024,))]
+        head_in = 256
+    spec += [("policy.weight", (num_actions, head_in)), ("policy.bias", (num_actions,)),
+             ("baseline.weight", (1, head_in)), ("baseline.bias", (1,))]
+    return spec
+
+
+class _ResNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, frame, reward, notdone, h0, c0, *params):
+        logits, baseline, hN, cN = module._launch_forward(frame, reward, notdone, h0, c0)
+        ctx.module, ctx.notdone, ctx.frame = module, notdone, frame
+        ctx.mark_non_differentiable(hN, cN)
+        return logits, baseline, hN, cN
+
+    @staticmethod
+    def backward(ctx, g_logits, g_baseline, _ghn, _gcn):
+        module = ctx.module
+        T1, B = ctx.frame.shape[:2]
+        dev = module._flat.device
+        if g_logits is None:
+            g_logits = torch.zeros(T1, B, module.num_actions, device=dev)
+        if g_baseline is None:
+            g_baseline = torch.zeros(T1, B, device=dev)
+        grads = torch.empty_like(module._flat)
+        module._launch_backward(ctx.frame, g_logits.contiguous(), g_baseline.contiguous(), ctx.notdone, grads)
+        return (None,) * 6 + tuple(grads[off:off + n].view(shape) for _, off, n, shape in module._views)
+
+
+class ResNet(FlatParamModule):
+    """CUDA IMPALA ResNet (reference polybeast_learner.py:134-266 `Net`): three sections of
+    conv3x3 + maxpool3/2 + two residual blocks, fc 3872->256, cat[reward], optional LSTM(257->256), heads.
+    forward(inputs, core_state) returns ((action, policy_logits, baseline), core_state) like the reference."""
+
+    PRECISIONS = {"fp32": 0, "bf16": 1}
+
+    def __init__(self, num_actions, use_lstm=False, device=None, precision=None):
+        super().__init__()
+        import os
+        self.num_actions = num_actions
+        self.use_lstm = use_lstm
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self._build_flat(resnet_param_spec(num_actions, use_lstm), device)
+        self._fix_module_names()
+        self.reset_parameters_like_torch()
+        if use_lstm:
+            self.core.num_layers, self.core.hidden_size, self.core.input_size = 1, 256, 257
+        self.precision = precision or os.environ.get("TB_PRECISION", "bf16")
+        if self.precision not in self.PRECISIONS:
+            raise _lib.TorchBeastB200Error("precision must be 'fp32' or 'bf16'")
+        self._ws = None
+        self._ws_key = None
+        count = _lib.lib().tb_resnet_param_count(num_actions, int(use_lstm))
+        assert count == self._total, "parameter layout disagrees with the C-ABI (%d vs %d)" % (count, self._total)
+
+    def _fix_module_names(self):
+        pass  # names with more than one dot are handled by _build_flat (see FlatParamModule._register)
+
+    def initial_state(self, batch_size=1):
+        if not self.use_lstm:
+            return tuple()
+        return tuple(torch.zeros(1, batch_size, 256, device=self._flat.device) for _ in range(2))
+
+    def _workspace(self, T1, B):
+        key = (T1, B, self._flat.device, self.precision)
+        if self._ws_key != key:
+            nbytes = _lib.lib().tb_resnet_workspace_bytes(T1, B, self.num_actions, int(self.use_lstm),
+                                                          self.PRECISIONS[self.precision])
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self._flat.device)
+            self._ws_key = key
+        return self._ws
+
+    def _launch_forward(self, frame, reward, notdone, h0, c0):
+        _lib.require_cuda(frame, reward, self._flat)
+        T1, B = frame.shape[:2]
+        if frame.dtype != torch.uint8 or tuple(frame.shape[2:]) != (4, 84, 84):
+            raise _lib.TorchBeastB200Error("frame must be uint8 [T,B,4,84,84], got %s %r" % (frame.dtype, tuple(frame.shape)))
+        dev = self._flat.device
+        frame = frame.contiguous()
+        reward = reward.to(torch.float32).contiguous()
+        logits = torch.empty(T1, B, self.num_actions, dtype=torch.float32, device=dev)
+        baseline = torch.empty(T1, B, dtype=torch.float32, device=dev)
+        if self.use_lstm:
+            hN = torch.empty(1, B, 256, dtype=torch.float32, device=dev)
+            cN = torch.empty_like(hN)
+            h0 = h0.to(torch.float32).contiguous(); c0 = c0.to(torch.float32).contiguous()
+        else:
+            hN = cN = torch.empty(0, device=dev)
+            h0 = c0 = notdone = None
+        p = _lib.ptr
+        _lib.check(
+            _lib.lib().tb_resnet_forward(
+                p(frame), p(reward), p(notdone), p(h0), p(c0), p(self._flat), T1, B, self.num_actions, int(self.use_lstm),
+                self.PRECISIONS[self.precision], p(self._workspace(T1, B)), p(logits), p(baseline),
+                p(hN) if self.use_lstm else None, p(cN) if self.use_lstm else None, _lib.stream_ptr()),
+            "tb_resnet_forward")
+        return logits, baseline, hN, cN
+
+    def _launch_backward(self, frame, g_logits, g_baseline, notdone, grads_out):
+        T1, B = g_baseline.shape
+        p = _lib.ptr
+        _lib.check(
+            _lib.lib().tb_resnet_backward(
+                p(frame.contiguous()), p(g_logits), p(g_baseline), p(notdone) if self.use_lstm else None, p(self._flat),
+                T1, B, self.num_actions, int(self.use_lstm), self.PRECISIONS[self.precision], p(self._workspace(T1, B)),
+                p(grads_out), _lib.stream_ptr()),
+            "tb_resnet_backward")
+
+    @torch.no_grad()
+    def learner_forward(self, inputs, core_state=()):
+        notdone = (~inputs["done"]).float().contiguous() if self.use_lstm else None
+        h0, c0 = core_state if self.use_lstm else (None, None)
+        logits, baseline, hN, cN = self._launch_forward(inputs["frame"], inputs["reward"], notdone, h0, c0)
+        self._saved = (inputs["frame"], notdone)
+        return LearnerOutputs(logits, baseline, (hN, cN) if self.use_lstm else tuple())
+
+    @torch.no_grad()
+    def learner_backward(self, grad_logits, grad_baseline):
+        fg = self.attach_grads()
+        frame, notdone = self._saved
+        self._launch_backward(frame, grad_logits, grad_baseline, notdone, fg)
+        return fg
+
+    def forward(self, inputs, core_state=()):
+        frame = inputs["frame"]
+        T, B = frame.shape[:2]
+        notdone = (~inputs["done"]).float().contiguous() if self.use_lstm else None
+        h0, c0 = core_state if self.use_lstm else (None, None)
+        params = [v[0] for v in self._views]
+        if torch.is_grad_enabled() and any(q.requires_grad for q in params):
+            logits, baseline, hN, cN = _ResNetFunction.apply(self, frame, inputs["reward"], notdone, h0, c0, *params)
+        else:
+            logits, baseline, hN, cN = self._launch_forward(frame, inputs["reward"], notdone, h0, c0)
+        flat_logits = logits.detach().view(T * B, self.num_actions)
+        if self.training:
+            action = torch.multinomial(torch.softmax(flat_logits, dim=1), num_samples=1)
+        else:
+            action = torch.argmax(flat_logits, dim=1)  # don't sample when testing
+        return (action.view(T, B), logits, baseline), ((hN, cN) if self.use_lstm else tuple())
 
 
 Net = AtariNet

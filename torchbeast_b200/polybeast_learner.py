@@ -12,3 +12,62 @@ from torchbeast_b200.losses import (  # noqa: F401
     compute_entropy_loss,
     compute_policy_gradient_loss,
 )
+
+import collections  # noqa: E402
+import threading  # noqa: E402
+
+import torch  # noqa: E402
+
+from torchbeast_b200 import learner as _learner  # noqa: E402
+from torchbeast_b200.nets import ResNet as Net  # noqa: E402,F401
+
+EnvOutput = collections.namedtuple("EnvOutput", "frame rewards done episode_step episode_return")
+AgentOutput = collections.namedtuple("AgentOutput", "action policy_logits baseline")
+Batch = collections.namedtuple("Batch", "env agent")
+
+
+def _to_device(t, device):
+    return t.to(device, non_blocking=True) if isinstance(t, torch.Tensor) else t
+
+
+def learn(
+    flags,
+    learner_queue,
+    model,
+    actor_model,
+    optimizer,
+    scheduler,
+    stats,
+    plogger,
+    lock=threading.Lock(),  # noqa: B008
+):
+    """The learner thread body - reference polybeast_learner.py:295-389.
+
+    Consumes the same nest the reference's BatchingQueue yields:
+    ((env_outputs, actor_outputs), initial_agent_state) with [T+1, B, ...] CPU (or CUDA) leaves,
+    env_outputs = (frame u8, reward, done, episode_step, episode_return), actor_outputs =
+    (action, policy_logits, baseline); fills `stats` with the reference's keys and calls plogger.log."""
+    device = getattr(flags, "learner_device", None) or model.flat_params.device
+    for tensors in learner_queue:
+        batch, initial_agent_state = tensors
+        env_outputs, actor_outputs = batch
+        env = EnvOutput._make(_to_device(t, device) for t in list(env_outputs)[:5])
+        agent = AgentOutput._make(_to_device(t, device) for t in list(actor_outputs)[:3])
+        state = tuple(_to_device(t, device) for t in initial_agent_state)
+        rollout = dict(frame=env.frame, reward=env.rewards, done=env.done, episode_return=env.episode_return,
+                       policy_logits=agent.policy_logits, action=agent.action)
+        lock.acquire()  # only one thread learning at a time (the H2D copies above overlap the previous step)
+        try:
+            out = _learner.learn_step(flags, model, actor_model, rollout, state, optimizer, scheduler)
+            stats["step"] = stats.get("step", 0) + flags.unroll_length * flags.batch_size
+            stats["episode_returns"] = out["episode_returns"]
+            stats["mean_episode_return"] = out["mean_episode_return"]
+            stats["mean_episode_step"] = torch.mean(env.episode_step[1:].float()).item()
+            for k in ("total_loss", "pg_loss", "baseline_loss", "entropy_loss"):
+                stats[k] = out[k]
+            stats["learner_queue_size"] = learner_queue.size()
+            plogger.log(stats)
+            if not len(out["episode_returns"]):
+                stats["mean_episode_return"] = None  # hide the mean-of-empty NaN, like the reference
+        finally:
+            lock.release()
