@@ -43,6 +43,9 @@ def parse():
     ap.add_argument("--T", type=int, default=80)
     ap.add_argument("--B", type=int, default=32, help="batch columns per GPU")
     ap.add_argument("--use_lstm", type=int, default=1)
+    ap.add_argument("--net", default="atari", choices=["atari", "resnet"],
+                    help="atari: monobeast AtariNet (BASELINE configs[1]); resnet: polybeast IMPALA ResNet (configs[3])")
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
     ap.add_argument("--num_actions", type=int, default=6)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_profile", action="store_true")
@@ -169,6 +172,8 @@ def gemm_flops_table(N, A, use_lstm):
         "conv2_dgrad": 2 * M2 * 64 * 512, "conv3_dgrad": 2 * M3 * 64 * 576, "fc_dgrad": 2 * N * 512 * 3136,
         "heads_dgrad": 2 * N * (A + 1) * core,
     }
+    if use_lstm == "resnet":
+        return resnet_flops_table(N, A)
     if use_lstm:
         H = core
         t.update({
@@ -177,6 +182,17 @@ def gemm_flops_table(N, A, use_lstm):
             "lstm_xproj_dgrad": 2 * 2 * N * 4 * H * H,
         })
     return t
+
+
+def resnet_flops_table(N, A):
+    """2*M*N*K per tagged op of the IMPALA ResNet trunk (aggregated over the 15 convs)."""
+    secs = [(84, 42, 4, 16), (42, 21, 16, 32), (21, 11, 32, 32)]
+    feat = sum(2 * N * S * S * ch * cin * 9 for S, So, cin, ch in secs)
+    feat_d = sum(2 * N * S * S * ch * cin * 9 for S, So, cin, ch in secs[1:])
+    res = sum(4 * 2 * N * So * So * ch * ch * 9 for S, So, cin, ch in secs)
+    fc = 2 * N * 256 * 3872
+    return {"feat_conv_fwd": feat, "feat_conv_wgrad": 2 * N * 84 * 84 * 16 * 36, "res_conv_fwd": res,
+            "res_conv_wgrad": res + feat_d, "res_conv_dgrad": res + feat_d, "fc_fwd": fc, "fc_wgrad": fc, "fc_dgrad": fc}
 
 
 def hbm_bytes_table(N, T, B, A, use_lstm, nparams):
@@ -196,20 +212,22 @@ def run_reference(args):
     from oracle import learner_torch as LT
     T, B, A = args.T, args.B, args.num_actions
     budget_s = float(os.environ.get("TB_CPU_BASELINE_BUDGET_S", "60"))
-    shapes = LT.atarinet_param_shapes(A, bool(args.use_lstm))
+    net = getattr(args, "net", "atari")
+    shapes = (LT.resnet_param_shapes if net == "resnet" else LT.atarinet_param_shapes)(A, bool(args.use_lstm))
     p = LT.random_params(shapes, seed=0)
     # Thread count: the op-by-op CPU path is dispatch-bound and gets SLOWER with many threads
     # (measured on the 128-thread B200 host: 250 s/step at 128 threads), so pick
     # the fastest of a few counts on a small calibration rollout and report it as `cores`.
     ncpu = os.cpu_count() or 1
     cal = synthetic_host_batch(8, 8, A, seed=2, pin=False)
-    cal_state = tuple(torch.zeros(2, 8, 512 + A + 1) for _ in range(2)) if args.use_lstm else ()
+    st_shape = (lambda b: (1, b, 256)) if net == "resnet" else (lambda b: (2, b, 512 + A + 1))
+    cal_state = tuple(torch.zeros(*st_shape(8)) for _ in range(2)) if args.use_lstm else ()
     best = None
     for nt in sorted({min(ncpu, n) for n in (8, 16, 32, 64, ncpu)}):
         torch.set_num_threads(nt)
-        LT.learner_step(p, cal, cal_state, net="atari", num_actions=A)
+        LT.learner_step(p, cal, cal_state, net=net, num_actions=A)
         t0 = time.perf_counter()
-        LT.learner_step(p, cal, cal_state, net="atari", num_actions=A)
+        LT.learner_step(p, cal, cal_state, net=net, num_actions=A)
         dt = time.perf_counter() - t0
         if best is None or dt < best[0]:
             best = (dt, nt)
@@ -217,18 +235,18 @@ def run_reference(args):
             break
     torch.set_num_threads(best[1])
     batch = synthetic_host_batch(T, B, A, seed=1, pin=False)
-    state = tuple(torch.zeros(2, B, 512 + A + 1) for _ in range(2)) if args.use_lstm else ()
+    state = tuple(torch.zeros(*st_shape(B)) for _ in range(2)) if args.use_lstm else ()
     sq = None
     steps, warm = max(1, min(args.steps, 10)), 1
     tw = time.perf_counter()
     for _ in range(warm):
-        o = LT.learner_step(p, batch, state, net="atari", square_avg=sq, num_actions=A)
+        o = LT.learner_step(p, batch, state, net=net, square_avg=sq, num_actions=A)
         p, sq = o["params"], o["square_avg"]
     tw = time.perf_counter() - tw
     steps = max(1, min(steps, int(budget_s / max(tw, 1e-3))))  # bounded sample: ~budget_s of CPU work
     t0 = time.perf_counter()
     for _ in range(steps):
-        o = LT.learner_step(p, batch, state, net="atari", square_avg=sq, num_actions=A)
+        o = LT.learner_step(p, batch, state, net=net, square_avg=sq, num_actions=A)
         p, sq = o["params"], o["square_avg"]
     dt = (time.perf_counter() - t0) / steps
     return dict(value=T * B / dt, ms_per_step=dt * 1e3, steps=steps, warmup=warm, cores=torch.get_num_threads())
@@ -240,8 +258,12 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     T, B, A = args.T, args.B, args.num_actions
-    workload = "AtariNet(84x84x4 u8)%s + V-trace learner step, T=%d B=%d per GPU, synthetic frames" % (
-        "+LSTM(2x519)" if args.use_lstm else "", T, B)
+    if args.net == "resnet":
+        workload = "IMPALA ResNet(84x84x4 u8)%s + V-trace learner step, T=%d B=%d per GPU, synthetic frames" % (
+            "+LSTM(257->256)" if args.use_lstm else "", T, B)
+    else:
+        workload = "AtariNet(84x84x4 u8)%s + V-trace learner step, T=%d B=%d per GPU, synthetic frames" % (
+            "+LSTM(2x519)" if args.use_lstm else "", T, B)
     config = dict(workload=workload, T=T, B_per_gpu=B, global_batch=B * max(world, 1), num_actions=A,
                   use_lstm=bool(args.use_lstm), parallelism="dp%d over batch columns, one NCCL all-reduce of the flat gradient" % world)
 
@@ -268,8 +290,13 @@ def main():
     from torchbeast_b200 import _lib, learner, monobeast, optim
 
     dev = torch.device("cuda", local_rank)
-    model = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm))
-    actor = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm))
+    if args.net == "resnet":
+        from torchbeast_b200 import polybeast_learner
+        model = polybeast_learner.Net(A, bool(args.use_lstm), precision=args.precision)
+        actor = polybeast_learner.Net(A, bool(args.use_lstm), precision=args.precision)
+    else:
+        model = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm), precision=args.precision)
+        actor = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm), precision=args.precision)
     model.reset_parameters_like_torch(seed=0)  # identical replicas on every rank
     actor.copy_params_from(model)
     opt = optim.RMSprop(model, lr=0.00048, momentum=0, eps=0.01, alpha=0.99)
@@ -363,7 +390,8 @@ def main():
     frames = T * B * world
     line = dict(
         metric="learner_frames_per_sec", value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=args.steps,
-        warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+        warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype=("bf16" if model.precision == "bf16" else "f32"),
         data="synthetic", config=dict(config, l2="4 rotating input batches per rank (%.0f MB) > 126 MB L2; ~2.3 GB of "
                                       "activations written per step" % (NROT * h2d_bytes / 1e6)),
         e2e=dict(value=frames / (e2e_ms * 1e-3), unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes,
@@ -385,7 +413,7 @@ def main():
             a = agg.setdefault(name, [0.0, 0])
             a[0] += t; a[1] += 1
         N = (T + 1) * B
-        flops = gemm_flops_table(N, A, args.use_lstm)
+        flops = gemm_flops_table(N, A, "resnet" if args.net == "resnet" else args.use_lstm)
         nbytes = hbm_bytes_table(N, T, B, A, args.use_lstm, model.flat_params.numel())
         ops = []
         for name, (tot, cnt) in agg.items():
@@ -405,7 +433,8 @@ def main():
         if dom is not None:
             line["roofline"] = dict(kernel=dom["op"], bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"],
                                     unit=dom["unit"], frac=dom["frac"], traffic=None, peak_source=pk["source"],
-                                    note="fp32 SIMT GEMM backend measured against the bf16 tensor-core peak")
+                                    note=("bf16 tcgen05 GEMM" if model.precision == "bf16" else "fp32 SIMT GEMM backend") +
+                                    " measured against the sustained bf16 tensor-core peak")
         # the V-trace kernels on their own (BASELINE.json metric: V-trace GB/s vs HBM peak)
         line["vtrace"] = vtrace_numbers(pk, T, B, A)
 
