@@ -26,7 +26,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* _
 
 template <typename AT, typename BT, bool TA, bool TB, int BM, int BN>
 static void launch_tile(const GemmArgs& g, cudaStream_t stream) {
-  dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM), (unsigned)g.splits);
+  dim3 grid((unsigned)((g.M + BM - 1) / BM), (unsigned)((g.N + BN - 1) / BN), (unsigned)g.splits);
   gemm_simt_kernel<AT, BT, TA, TB, BM, BN><<<grid, kGemmThreads, 0, stream>>>(g);
 }
 

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_simt_kernel(GemmArgs g) {
   const BT* __restrict__ B = reinterpret_cast<const BT*>(g.B);
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
-  const int64_t m0 = int64_t(blockIdx.y) * BM, n0 = int64_t(blockIdx.x) * BN;
+  const int64_t m0 = int64_t(blockIdx.x) * BM, n0 = int64_t(blockIdx.y) * BN;  // M tiles on grid.x (no 65535 limit)
   // K range of this split (multiple of BK except the last)
   const int64_t ktiles = (g.K + BK - 1) / BK;
   const int64_t per = (ktiles + g.splits - 1) / g.splits;

@@ -111,7 +111,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_full = bars + 8u * (2 * kStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BLOCK_N, m0 = blockIdx.y * kBlockM;
+  const int n0 = blockIdx.y * BLOCK_N, m0 = blockIdx.x * kBlockM;  // M tiles on grid.x (no 65535 limit)
   // split-K: this CTA reduces k-blocks [kb0, kb1)
   const int total_kb = (K + kBlockK - 1) / kBlockK;
   const int per = (total_kb + gridDim.z - 1) / gridDim.z;
@@ -294,7 +294,7 @@ int launch_s(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, i
     TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
   }
-  dim3 grid((unsigned)((N + BLOCK_N - 1) / BLOCK_N), (unsigned)((M + kBlockM - 1) / kBlockM), (unsigned)splits);
+  dim3 grid((unsigned)((M + kBlockM - 1) / kBlockM), (unsigned)((N + BLOCK_N - 1) / BLOCK_N), (unsigned)splits);
   gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages><<<grid, kThreads, smem, stream>>>(a, b, ep, int(M), int(N), int(K), partial);
   return check_launch("gemm_tc_kernel");
 }
