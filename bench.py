@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--num_actions", type=int, default=6)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_profile", action="store_true")
+    ap.add_argument("--graph", type=int, default=1, help="e2e path: replay the step as one CUDA graph (falls back to eager)")
     return ap.parse_args()
 
 
@@ -359,6 +360,14 @@ def main():
                 slots[s][k].copy_(v, non_blocking=True)
             ready[s].record(copy_stream)
 
+    graphed = None
+    if args.graph:
+        try:
+            graphed = learner.GraphedLearner(flags, model, actor, opt, slots[0], state)
+        except Exception as exc:  # capture not possible on this setup: report and run eagerly
+            sys.stderr.write("CUDA graph capture failed (%s); e2e runs eagerly\n" % (exc,))
+            graphed = None
+            opt.lr_from_device = False
     for s in range(2):
         freed[s].record()
     barrier()
@@ -372,8 +381,13 @@ def main():
             stage(i + 1)  # prefetch the next rollout while this one trains
         s = i % 2
         torch.cuda.current_stream().wait_event(ready[s])
-        stats = monobeast.learn(flags, actor, model, slots[s], state, opt, sched)  # includes the stats read-back
-        freed[s].record()
+        if graphed is not None:
+            graphed.step(slots[s], state, sched)
+            freed[s].record()  # inputs were copied into the graph's static buffers
+            stats = graphed.stats()  # the step's blocking stats read-back
+        else:
+            stats = monobeast.learn(flags, actor, model, slots[s], state, opt, sched)  # includes the stats read-back
+            freed[s].record()
     t_e1.record()
     barrier()
     e2e_ms = max_over_ranks(t_e0.elapsed_time(t_e1)) / e2e_steps
@@ -395,7 +409,7 @@ def main():
         data="synthetic", config=dict(config, l2="4 rotating input batches per rank (%.0f MB) > 126 MB L2; ~2.3 GB of "
                                       "activations written per step" % (NROT * h2d_bytes / 1e6)),
         e2e=dict(value=frames / (e2e_ms * 1e-3), unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes,
-                 d2h_bytes_per_step=d2h_bytes, h2d_gbs_measured=h2d_gbs, numa_node=numa, note="pinned host rollout -> async H2D (double-buffered, overlapped with "
+                 d2h_bytes_per_step=d2h_bytes, h2d_gbs_measured=h2d_gbs, numa_node=numa, cuda_graph=graphed is not None, note="pinned host rollout -> async H2D (double-buffered, overlapped with "
                  "the previous step) -> monobeast.learn -> stats read-back, all inside the timed region"),
         gpu_launches=int(launches), clocks=clocks, final_total_loss=final_loss,
     )

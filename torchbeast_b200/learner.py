@@ -156,3 +156,70 @@ def shard_rollout(batch, initial_agent_state, rank, world_size):
         shard = type(batch)(cols(v, 1) for v in batch)
     state = tuple(cols(s, 1) for s in initial_agent_state)
     return shard, state
+
+
+class GraphedLearner:
+    """The whole device side of learn() captured ONCE into a CUDA graph and replayed per step.
+
+    One replay = network forward, fused V-trace/loss/grad kernel, network backward, [NCCL all-reduce],
+    fused clip + RMSprop, actor-weight publication: ~150 kernel launches become one cudaGraphLaunch, so
+    a learner that reads its stats back every step (like the reference, monobeast.py:279-287) is no longer
+    exposed to per-launch CPU latency.  Inputs are copied into static device buffers before each replay;
+    the learning rate is read from a device scalar so LambdaLR keeps working; stats are computed from the
+    graph's static outputs after the replay."""
+
+    KEYS = ("frame", "reward", "done", "policy_logits", "action", "last_action", "episode_return")
+
+    def __init__(self, flags, model, actor_model, optimizer, example_batch, initial_agent_state=()):
+        from torchbeast_b200 import optim as _optim
+        if not isinstance(optimizer, _optim.RMSprop):
+            raise _lib.TorchBeastB200Error("GraphedLearner needs torchbeast_b200.optim.RMSprop")
+        self.flags, self.model, self.actor, self.opt = flags, model, actor_model, optimizer
+        self.static = {k: torch.empty_like(v) for k, v in example_batch.items() if k in self.KEYS}
+        self.static_state = tuple(torch.empty_like(s) for s in initial_agent_state)
+        for k, v in self.static.items():
+            v.copy_(example_batch[k])
+        for d, s in zip(self.static_state, initial_agent_state):
+            d.copy_(s)
+        optimizer.lr_from_device = True
+        optimizer.sync_lr_to_device()
+        # warm up on a side stream (allocations, one-time attribute calls), then capture
+        snapshot = (model.flat_params.clone(), optimizer.square_avg.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                learn_step(flags, model, actor_model, self.static, self.static_state, optimizer, None, stats_sync=False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = learn_step(flags, model, actor_model, self.static, self.static_state, optimizer, None,
+                                  stats_sync=False)
+        # undo the warm-up / capture-time updates so training starts from the caller's weights
+        model.flat_params.copy_(snapshot[0])
+        optimizer.square_avg.copy_(snapshot[1])
+        if actor_model is not None and hasattr(actor_model, "copy_params_from"):
+            actor_model.copy_params_from(model)
+
+    def step(self, batch, initial_agent_state=(), scheduler=None):
+        for k, v in self.static.items():
+            v.copy_(batch[k], non_blocking=True)
+        for d, s in zip(self.static_state, initial_agent_state):
+            d.copy_(s, non_blocking=True)
+        self.opt.sync_lr_to_device()
+        self.graph.replay()
+        if scheduler is not None:
+            scheduler.step()
+        return self.out
+
+    def stats(self):
+        """Same keys as monobeast.learn()'s return value; one blocking read-back."""
+        done = self.static["done"][1:]
+        ep = self.static["episode_return"][1:][done.bool()].cpu()
+        host = self.out["losses"].cpu()
+        return {
+            "episode_returns": tuple(ep.numpy()), "mean_episode_return": torch.mean(ep).item(),
+            "total_loss": host[3].item(), "pg_loss": host[0].item(), "baseline_loss": host[1].item(),
+            "entropy_loss": host[2].item(),
+        }

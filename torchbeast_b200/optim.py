@@ -26,6 +26,9 @@ class RMSprop(torch.optim.Optimizer):
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=flat.device)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=flat.device)
         self._steps = 0
+        # learning rate as a device scalar: lets a captured CUDA graph see scheduler updates
+        self._lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=flat.device)
+        self.lr_from_device = False
         # per-parameter views so state_dict() looks like torch.optim.RMSprop's
         for p, off, n, shape in model._views:
             st = self.state[p]
@@ -49,8 +52,13 @@ class RMSprop(torch.optim.Optimizer):
         _lib.check(
             lib.tb_clip_rmsprop_step_f32(
                 p(flat), p(grad), p(self.square_avg), p(self.momentum_buffer), flat.numel(), p(self._sumsq),
-                -1.0 if max_grad_norm is None else float(max_grad_norm), None, float(group["lr"]),
+                -1.0 if max_grad_norm is None else float(max_grad_norm),
+                p(self._lr_dev) if self.lr_from_device else None, float(group["lr"]),
                 float(group["alpha"]), float(group["eps"]), float(group["momentum"]), p(self.grad_norm), st),
             "tb_clip_rmsprop_step_f32")
         self._steps += 1
         return None
+
+    def sync_lr_to_device(self):
+        """Publish param_groups[0]['lr'] to the device scalar a captured graph reads (async fill)."""
+        self._lr_dev.fill_(float(self.param_groups[0]["lr"]))
