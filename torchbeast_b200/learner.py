@@ -196,6 +196,8 @@ class GraphedLearner:
         with torch.cuda.graph(self.graph):
             self.out = learn_step(flags, model, actor_model, self.static, self.static_state, optimizer, None,
                                   stats_sync=False)
+        self.graph.replay()  # first replay uploads the graph to the device; keep that out of the training loop
+        torch.cuda.synchronize()
         # undo the warm-up / capture-time updates so training starts from the caller's weights
         model.flat_params.copy_(snapshot[0])
         optimizer.square_avg.copy_(snapshot[1])
