@@ -376,7 +376,9 @@ def main():
     t_e0.record()
     stage(0)
     stats = None
+    _dbg = os.environ.get("TB_BENCH_DEBUG")
     for i in range(e2e_steps):
+        _t0 = time.perf_counter()
         if i + 1 < e2e_steps:
             stage(i + 1)  # prefetch the next rollout while this one trains
         s = i % 2
@@ -388,6 +390,8 @@ def main():
         else:
             stats = monobeast.learn(flags, actor, model, slots[s], state, opt, sched)  # includes the stats read-back
             freed[s].record()
+        if _dbg:
+            sys.stderr.write("e2e step %d: %.2f ms\n" % (i, (time.perf_counter() - _t0) * 1e3))
     t_e1.record()
     barrier()
     e2e_ms = max_over_ranks(t_e0.elapsed_time(t_e1)) / e2e_steps
