@@ -454,11 +454,19 @@ def main():
         prof_total = sum(o["ms_per_step"] for o in ops)
         line["roofline_ops"] = [dict(o, share=o["ms_per_step"] / prof_total) for o in ops[:12]]
         dom = next((o for o in ops if "achieved" in o), None)
+        try:
+            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+        except Exception:
+            traffic_tab = {}
         if dom is not None:
             line["roofline"] = dict(kernel=dom["op"], bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"],
-                                    unit=dom["unit"], frac=dom["frac"], traffic=None, peak_source=pk["source"],
-                                    note=("bf16 tcgen05 GEMM" if model.precision == "bf16" else "fp32 SIMT GEMM backend") +
-                                    " measured against the sustained bf16 tensor-core peak")
+                                    unit=dom["unit"], frac=dom["frac"],
+                                    traffic=(traffic_tab.get(dom["op"], {}).get("dram_bytes_per_launch")),
+                                    launches_per_step=dom["launches_per_step"], peak_source=pk["source"],
+                                    note=("latency-bound fp32 recurrence (grid barrier per time step), flops of the recurrent "
+                                          "products against the sustained bf16 tensor peak" if dom["op"].startswith("lstm_recurrence")
+                                          else ("bf16 tcgen05 GEMM" if model.precision == "bf16" else "fp32 SIMT GEMM backend") +
+                                          " against the sustained bf16 tensor-core peak"))
         # the V-trace kernels on their own (BASELINE.json metric: V-trace GB/s vs HBM peak)
         line["vtrace"] = vtrace_numbers(pk, T, B, A)
 

@@ -423,10 +423,39 @@ __global__ void colsum_partial_bf16_kernel(const __nv_bfloat16* __restrict__ X, 
   }
 }
 
+// Dense [M, ncols] bf16 with ncols in {8,16,32,64}: every thread streams 16-byte vectors whose column
+// group never changes (the grid stride is a multiple of the row length), so the kernel is a plain
+// coalesced read of the whole matrix followed by a small shared-memory fold.
+__global__ void colsum_dense_bf16_kernel(const uint4* __restrict__ X, float* __restrict__ part, int64_t nvec, int cg) {
+  __shared__ float sm[256][9];
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;  // multiple of cg (cg | 256)
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) acc_bf16x8(__ldg(X + i), s);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[threadIdx.x][j] = s[j];
+  __syncthreads();
+  if (threadIdx.x < cg * 8) {
+    const int g = threadIdx.x / 8, j = threadIdx.x % 8;
+    float t = 0.f;
+    for (int k = g; k < 256; k += cg) t += sm[k][j];
+    part[int64_t(blockIdx.x) * cg * 8 + g * 8 + j] = t;
+  }
+}
+
 int colsum_bf16(const void* X, float* out, int64_t M, int64_t ncols, int64_t ld, float* scratch, cudaStream_t stream) {
   ProfScope prof("bias_grad_colsum", stream);
   if (ncols == 0) return 0;
   TB_REQUIRE(X && out && scratch, "colsum_bf16: null pointer");
+  if (ld == ncols && (ncols == 8 || ncols == 16 || ncols == 32 || ncols == 64) && M >= 4096 &&
+      (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    const int cg = int(ncols / 8);
+    const int blocks = kColsumSlabs;  // partials [blocks][ncols] fit the caller's scratch
+    colsum_dense_bf16_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(X), scratch, M * cg, cg);
+    int rc = check_launch("colsum_dense_bf16_kernel");
+    if (rc) return rc;
+    colsum_final_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, stream>>>(scratch, out, ncols, blocks);
+    return check_launch("colsum_final_kernel");
+  }
   int slabs = kColsumSlabs;
   if (M < slabs * 8) slabs = int((M + 7) / 8);
   if (slabs < 1) slabs = 1;
