@@ -95,33 +95,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent: each CTA walks the work list (m tile, n tile, k split) with stride gridDim.x; the TMEM
+// accumulator is double-buffered so the epilogue of work item i overlaps the TMA/MMA main loop of item
+// i+1, and the per-CTA prologue (barrier init, TMEM alloc, descriptor fetch) is paid once.
 template <int BLOCK_N, bool A_MN, bool B_MN, int kStages>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep, int M,
-               int N, int K, float* partial) {
+               int N, int K, float* partial, int tiles_m, int tiles_n, int splits) {
   constexpr uint32_t B_BYTES = BLOCK_N * kBlockK * 2;
-  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulator buffers (power of two)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   const uint32_t sA = base, sB = base + kStages * kABytes;
-  const uint32_t bars = sB + kStages * B_BYTES;                  // full[4], empty[4], tmem_full
-  const uint32_t tmem_slot = bars + 8 * (2 * kStages + 1);
+  const uint32_t bars = sB + kStages * B_BYTES;  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+  const uint32_t tmem_slot = bars + 8 * (2 * kStages + 4);
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (kStages + s); };
-  const uint32_t tmem_full = bars + 8u * (2 * kStages);
+  auto tmem_full = [&](int b) { return bars + 8u * (2 * kStages + b); };
+  auto tmem_empty = [&](int b) { return bars + 8u * (2 * kStages + 2 + b); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BLOCK_N, m0 = blockIdx.x * kBlockM;  // M tiles on grid.x (no 65535 limit)
-  // split-K: this CTA reduces k-blocks [kb0, kb1)
   const int total_kb = (K + kBlockK - 1) / kBlockK;
-  const int per = (total_kb + gridDim.z - 1) / gridDim.z;
-  const int kb0 = blockIdx.z * per;
-  const int kb1 = (kb0 + per < total_kb) ? kb0 + per : total_kb;
-  const int num_kb = kb1 > kb0 ? kb1 - kb0 : 0;
+  const int per = (total_kb + splits - 1) / splits;
+  const int tiles_mn = tiles_m * tiles_n;
+  const int total_work = tiles_mn * splits;
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
@@ -133,114 +138,160 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
+  // work item -> tile coordinates (n fastest so that co-running CTAs share A tiles in L2)
+  auto decode = [&](int w, int& m0, int& n0, int& kb0, int& num_kb, int& z) {
+    z = w / tiles_mn;
+    const int rem = w - z * tiles_mn;
+    m0 = (rem / tiles_n) * kBlockM;
+    n0 = (rem % tiles_n) * BLOCK_N;
+    kb0 = z * per;
+    const int kb1 = (kb0 + per < total_kb) ? kb0 + per : total_kb;
+    num_kb = kb1 > kb0 ? kb1 - kb0 : 0;
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int i = 0; i < num_kb; ++i) {
-        const int kc = (kb0 + i) * kBlockK;
-        mbar_wait(empty(stage), phase ^ 1);
-        mbar_expect_tx(full(stage), kABytes + B_BYTES);
-        if (A_MN) {  // two 64(k) x 64(m) boxes
-          tma_load_2d(sA + stage * kABytes, &tmA, full(stage), m0, kc);
-          tma_load_2d(sA + stage * kABytes + 8192, &tmA, full(stage), m0 + 64, kc);
-        } else {
-          tma_load_2d(sA + stage * kABytes, &tmA, full(stage), kc, m0);
-        }
-        if (B_MN) {
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        int m0, n0, kb0, num_kb, z;
+        decode(w, m0, n0, kb0, num_kb, z);
+        for (int i = 0; i < num_kb; ++i) {
+          const int kc = (kb0 + i) * kBlockK;
+          mbar_wait(empty(stage), phase ^ 1);
+          mbar_expect_tx(full(stage), kABytes + B_BYTES);
+          if (A_MN) {  // two 64(k) x 64(m) boxes
+            tma_load_2d(sA + stage * kABytes, &tmA, full(stage), m0, kc);
+            tma_load_2d(sA + stage * kABytes + 8192, &tmA, full(stage), m0 + 64, kc);
+          } else {
+            tma_load_2d(sA + stage * kABytes, &tmA, full(stage), kc, m0);
+          }
+          if (B_MN) {
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_2d(sB + stage * B_BYTES + j * 8192, &tmB, full(stage), n0 + 64 * j, kc);
-        } else {
-          tma_load_2d(sB + stage * B_BYTES, &tmB, full(stage), kc, n0);
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sB + stage * B_BYTES + j * 8192, &tmB, full(stage), n0 + 64 * j, kc);
+          } else {
+            tma_load_2d(sB + stage * B_BYTES, &tmB, full(stage), kc, n0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3, M>>4
+      // instruction descriptor: D=f32, A=B=bf16, majorness bits, N>>3, M>>4
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(A_MN) << 15) | (uint32_t(B_MN) << 16) |
                                  (uint32_t(BLOCK_N >> 3) << 17) | (uint32_t(kBlockM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full(stage), phase);
+      int it = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        int m0, n0, kb0, num_kb, z;
+        decode(w, m0, n0, kb0, num_kb, z);
+        const int ab = it & 1;
+        mbar_wait(tmem_empty(ab), ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator buffer
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + uint32_t(ab * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full(stage), phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t da = A_MN ? make_smem_desc_mn(sA + stage * kABytes + k * 2048) : make_smem_desc(sA + stage * kABytes + k * 32);
-          const uint64_t db = B_MN ? make_smem_desc_mn(sB + stage * B_BYTES + k * 2048) : make_smem_desc(sB + stage * B_BYTES + k * 32);
-          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc_mn(sA + stage * kABytes + k * 2048) : make_smem_desc(sA + stage * kABytes + k * 32);
+            const uint64_t db = B_MN ? make_smem_desc_mn(sB + stage * B_BYTES + k * 2048) : make_smem_desc(sB + stage * B_BYTES + k * 32);
+            umma_bf16(tacc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty(stage));  // slot free once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(empty(stage));  // slot free once these MMAs have read it
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        umma_commit(tmem_full(ab));   // accumulator complete
       }
-      umma_commit(tmem_full);       // accumulator complete
     }
   } else {
     const int quarter = warp & 3;   // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t r = int64_t(m0) + quarter * 32 + lane;
+    int it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      int m0, n0, kb0, num_kb, z;
+      decode(w, m0, n0, kb0, num_kb, z);
+      const int ab = it & 1;
+      mbar_wait(tmem_full(ab), (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t r = int64_t(m0) + quarter * 32 + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), v);
-      if (num_kb == 0) {
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(ab * BLOCK_N + c0), v);
+        if (num_kb == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0u;  // nothing was accumulated (empty split)
-      }
-      if (partial) {  // split-K: raw partial tile [z][M][N]; splitk_reduce_kernel applies the epilogue
-        if (r < M) {
-          float* pz = partial + (int64_t(blockIdx.z) * M + r) * N + n0 + c0;
-          for (int j = 0; j < 32; ++j)
-            if (n0 + c0 + j < N) pz[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = 0u;  // nothing was accumulated (empty split)
         }
-        continue;
-      }
-      if (r < M) {
-        const int nbase = n0 + c0;
-        float o[32];
+        if (partial) {  // split-K: raw partial tile [z][M][N]; splitk_reduce_kernel applies the epilogue
+          if (r < M) {
+            float* pz = partial + (int64_t(z) * M + r) * N + n0 + c0;
+            if (n0 + c0 + 32 <= N && (N & 3) == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(v[j]) * ep.scale;
-          const int n = nbase + j;
-          if (ep.bias && n < N) x += ep.bias[n];
-          if (ep.relu) x = fmaxf(x, 0.0f);
-          if (ep.mask && n < N) x = (ep.mask[r * ep.ldmask + n] > 0.0f) ? x : 0.0f;
-          if (ep.mask16 && n < N) x = (__bfloat162float(ep.mask16[r * ep.ldmask + n]) > 0.0f) ? x : 0.0f;
-          if (ep.addend16 && n < N) x += __bfloat162float(ep.addend16[r * ep.ldadd + n]);
-          o[j] = x;
-        }
-        if (ep.C) {
-          float* c = ep.C + r * ep.ldc + nbase;
-          if (nbase + 32 <= N && (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (nbase + j < N) c[j] = o[j];
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(pz + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+              for (int j = 0; j < 32; ++j)
+                if (n0 + c0 + j < N) pz[j] = __uint_as_float(v[j]);
+            }
           }
+          continue;
         }
-        if (ep.C16) {
-          __nv_bfloat16* c = ep.C16 + r * ep.ldc16 + nbase;
-          if (nbase + 32 <= N && (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+        if (r < M) {
+          const int nbase = n0 + c0;
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(v[j]) * ep.scale;
+            const int n = nbase + j;
+            if (ep.bias && n < N) x += ep.bias[n];
+            if (ep.relu) x = fmaxf(x, 0.0f);
+            if (ep.mask && n < N) x = (ep.mask[r * ep.ldmask + n] > 0.0f) ? x : 0.0f;
+            if (ep.mask16 && n < N) x = (__bfloat162float(ep.mask16[r * ep.ldmask + n]) > 0.0f) ? x : 0.0f;
+            if (ep.addend16 && n < N) x += __bfloat162float(ep.addend16[r * ep.ldadd + n]);
+            o[j] = x;
+          }
+          if (ep.C) {
+            float* c = ep.C + r * ep.ldc + nbase;
+            const bool vec = (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (vec && nbase + j + 4 <= N) {
+                *reinterpret_cast<float4*>(c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                  if (nbase + j + jj < N) c[j + jj] = o[j + jj];
+              }
+            }
+          }
+          if (ep.C16) {
+            __nv_bfloat16* c = ep.C16 + r * ep.ldc16 + nbase;
+            const bool vec = (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-              __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-              pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-              *reinterpret_cast<uint4*>(c + j) = pk;
+              if (vec && nbase + j + 8 <= N) {
+                uint4 pk;
+                __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+                __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                *reinterpret_cast<uint4*>(c + j) = pk;
+              } else {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                  if (nbase + j + jj < N) c[j + jj] = __float2bfloat16_rn(o[j + jj]);
+              }
             }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (nbase + j < N) c[j] = __float2bfloat16_rn(o[j]);
           }
         }
       }
+      // this warp is done reading the accumulator buffer: hand it back to the MMA issuer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty(ab));
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 2) {
@@ -286,7 +337,7 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int6
 template <int BLOCK_N, bool A_MN, bool B_MN, int kStages>
 int launch_s(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
              float* partial, cudaStream_t stream) {
-  constexpr size_t smem = 1024 + kStages * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kStages + 1) + 16;
+  constexpr size_t smem = 1024 + kStages * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kStages + 4) + 16;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages>,
@@ -294,8 +345,19 @@ int launch_s(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, i
     TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
   }
-  dim3 grid((unsigned)((M + kBlockM - 1) / kBlockM), (unsigned)((N + BLOCK_N - 1) / BLOCK_N), (unsigned)splits);
-  gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages><<<grid, kThreads, smem, stream>>>(a, b, ep, int(M), int(N), int(K), partial);
+  const int64_t tiles_m = (M + kBlockM - 1) / kBlockM, tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t total = tiles_m * tiles_n * splits;
+  TB_REQUIRE(total < (int64_t(1) << 31), "gemm_tc: too many tiles");
+  // persistent grid: as many CTAs as fit at once (shared memory and 512 TMEM columns per SM)
+  int per_sm = int((220 * 1024) / smem);
+  const int tmem_cols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 3) per_sm = 3;
+  int64_t grid = int64_t(kNumSMsB200) * per_sm;
+  if (grid > total) grid = total;
+  gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages><<<(unsigned)grid, kThreads, smem, stream>>>(
+      a, b, ep, int(M), int(N), int(K), partial, int(tiles_m), int(tiles_n), splits);
   return check_launch("gemm_tc_kernel");
 }
 
