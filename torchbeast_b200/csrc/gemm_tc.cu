@@ -102,7 +102,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // Persistent: each CTA walks the work list (m tile, n tile, k split) with stride gridDim.x; the TMEM
 // accumulator is double-buffered so the epilogue of work item i overlaps the TMA/MMA main loop of item
 // i+1, and the per-CTA prologue (barrier init, TMEM alloc, descriptor fetch) is paid once.
-template <int BLOCK_N, bool A_MN, bool B_MN, int kStages>
+// EPI: 0 = store the accumulator as is; 1 = scale / bias / ReLU; 2 = + ReLU-mask / residual loads.
+// (compile-time so the common epilogues carry no predicated per-element loads - ncu showed the generic
+//  epilogue, not the MMA pipe, bounding the K=64 dgrad products)
+template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep, int M,
                int N, int K, float* partial, int tiles_m, int tiles_n, int splits) {
@@ -241,15 +244,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (r < M) {
           const int nbase = n0 + c0;
           float o[32];
+          const bool full_cols = nbase + 32 <= N;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) * ep.scale;
-            const int n = nbase + j;
-            if (ep.bias && n < N) x += ep.bias[n];
-            if (ep.relu) x = fmaxf(x, 0.0f);
-            if (ep.mask && n < N) x = (ep.mask[r * ep.ldmask + n] > 0.0f) ? x : 0.0f;
-            if (ep.mask16 && n < N) x = (__bfloat162float(ep.mask16[r * ep.ldmask + n]) > 0.0f) ? x : 0.0f;
-            if (ep.addend16 && n < N) x += __bfloat162float(ep.addend16[r * ep.ldadd + n]);
+            float x = __uint_as_float(v[j]);
+            if constexpr (EPI >= 1) {
+              x *= ep.scale;
+              const int n = nbase + j;
+              if (ep.bias && (full_cols || n < N)) x += __ldg(ep.bias + n);
+              if (ep.relu) x = fmaxf(x, 0.0f);
+            }
+            if constexpr (EPI >= 2) {
+              const int n = nbase + j;
+              if (full_cols || n < N) {
+                if (ep.mask) x = (ep.mask[r * ep.ldmask + n] > 0.0f) ? x : 0.0f;
+                if (ep.mask16) x = (__bfloat162float(ep.mask16[r * ep.ldmask + n]) > 0.0f) ? x : 0.0f;
+                if (ep.addend16) x += __bfloat162float(ep.addend16[r * ep.ldadd + n]);
+              }
+            }
             o[j] = x;
           }
           if (ep.C) {
@@ -334,13 +346,13 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int6
   return 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int kStages>
-int launch_s(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
+template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI>
+int launch_e(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
              float* partial, cudaStream_t stream) {
   constexpr size_t smem = 1024 + kStages * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kStages + 4) + 16;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
@@ -356,9 +368,19 @@ int launch_s(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, i
   if (per_sm > 3) per_sm = 3;
   int64_t grid = int64_t(kNumSMsB200) * per_sm;
   if (grid > total) grid = total;
-  gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages><<<(unsigned)grid, kThreads, smem, stream>>>(
+  gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages, EPI><<<(unsigned)grid, kThreads, smem, stream>>>(
       a, b, ep, int(M), int(N), int(K), partial, int(tiles_m), int(tiles_n), splits);
   return check_launch("gemm_tc_kernel");
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int kStages>
+int launch_s(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
+             float* partial, cudaStream_t stream) {
+  const bool loads = ep.mask || ep.mask16 || ep.addend16;
+  const bool arith = ep.bias || ep.relu || ep.scale != 1.0f;
+  if (loads) return launch_e<BLOCK_N, A_MN, B_MN, kStages, 2>(a, b, ep, M, N, K, splits, partial, stream);
+  if (arith && !partial) return launch_e<BLOCK_N, A_MN, B_MN, kStages, 1>(a, b, ep, M, N, K, splits, partial, stream);
+  return launch_e<BLOCK_N, A_MN, B_MN, kStages, 0>(a, b, ep, M, N, K, splits, partial, stream);
 }
 
 // Few k-blocks per CTA (dgrad: K = 64 channels): a 2-stage ring keeps 3 CTAs resident per SM so the
