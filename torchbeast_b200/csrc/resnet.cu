@@ -63,7 +63,7 @@ ResParams res_params(int A, int use_lstm) {
   return p;
 }
 
-template <typename T> struct Sec { T *P, *X0, *Y1, *X1, *Y2, *X2; };
+template <typename T> struct Sec { T *P, *X0, *Y1, *X1, *Y2, *X2; uint8_t* arg; };
 
 template <typename T>
 struct ResWs {
@@ -91,6 +91,7 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
     const int64_t big = N * kSecS[i] * kSecS[i] * kSecCh[i], small = N * kSecSo[i] * kSecSo[i] * kSecCh[i];
     w.s[i].P = takeT(big); w.s[i].X0 = takeT(small); w.s[i].Y1 = takeT(small); w.s[i].X1 = takeT(small);
     w.s[i].Y2 = takeT(small); w.s[i].X2 = takeT(small);
+    w.s[i].arg = static_cast<uint8_t*>(take(size_t(small)));
     if (big > maxact) maxact = big;
   }
   w.fcin = takeT(N * kFcIn); w.dfc = takeT(N * kFcOut); w.dfcin = takeT(N * kFcIn);
@@ -243,7 +244,7 @@ struct Impl {
         TB_TRY(conv_fwd(w.col, w.wfeat[i], w.s[i].P, M, ch, int64_t(cin) * 9, ldk_in, P + pp.feat[i].b, 0, nullptr, 1.0f, ch,
                         "feat_conv_fwd", st));
       }
-      TB_TRY(maxpool3x3s2_fwd<T>(w.s[i].P, w.s[i].X0, N, S, S, ch, st));
+      TB_TRY(maxpool3x3s2_fwd<T>(w.s[i].P, w.s[i].X0, w.s[i].arg, N, S, S, ch, st));
       const T* ins[4] = {w.s[i].X0, w.s[i].Y1, w.s[i].X1, w.s[i].Y2};
       T* outs[4] = {w.s[i].Y1, w.s[i].X1, w.s[i].Y2, w.s[i].X2};
       const T* adds[4] = {nullptr, w.s[i].X0, nullptr, w.s[i].X1};
@@ -334,7 +335,7 @@ struct Impl {
       // block 1: X1 = X0 + conv_b(relu(Y1)), Y1 = conv_a(relu(X0))
       TB_TRY(conv_bwd(s.Y1, true, g2, w.wblk[i][1], G + pp.blk[i][1].w, G + pp.blk[i][1].b, g0, nullptr, N, So, ch, ch, w, st));
       TB_TRY(conv_bwd(s.X0, true, g0, w.wblk[i][0], G + pp.blk[i][0].w, G + pp.blk[i][0].b, g1, g2, N, So, ch, ch, w, st));
-      TB_TRY(maxpool3x3s2_bwd<T>(s.P, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
+      TB_TRY(maxpool3x3s2_bwd<T>(s.arg, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
       const int64_t M = N * S * S;
       if (i == 0) {
         const int64_t ldk_in = ldk_of(4, kBf16);

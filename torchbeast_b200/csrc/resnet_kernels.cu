@@ -63,37 +63,59 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_u8<__nv_bfloat16>(uint
 template <typename TOut>
 __global__ void im2col3x3_u8_nchw_kernel(const uint8_t* __restrict__ frame, TOut* __restrict__ col, int64_t N, int C, int H,
                                          int W, int64_t ldk) {
-  // one thread = one output pixel x one channel: writes its 9 taps (contiguous in k)
-  const int64_t total = N * H * W * C;
+  // one thread = one output pixel: gathers its C x 3 x 3 neighbourhood (neighbouring threads share cache
+  // lines) and writes its whole patch row with wide stores
+  const int64_t total = N * H * W;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int ox = int(i % W);
     int64_t t = i / W;
-    const int oy = int(t % H); t /= H;
-    const int c = int(t % C);
-    const int64_t n = t / C;
-    const uint8_t* src = frame + (n * C + c) * H * W;
-    TOut* dst = col + ((n * H + oy) * W + ox) * ldk + c * 9;
+    const int oy = int(t % H);
+    const int64_t n = t / H;
+    uint8_t v[40];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
-      uint8_t v = 0;
-      if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = __ldg(src + iy * W + ix);
-      dst[tap] = from_u8<TOut>(v);
+    for (int k = 0; k < 40; ++k) v[k] = 0;
+    for (int c = 0; c < C && c < 4; ++c) {
+      const uint8_t* src = frame + (n * C + c) * H * W;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[c * 9 + tap] = __ldg(src + iy * W + ix);
+      }
     }
+    TOut* dst = col + i * ldk;
+    if constexpr (sizeof(TOut) == 2) {
+      if (ldk == 40) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          uint4 o;
+          uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 p = __floats2bfloat162_rn(float(v[q * 8 + 2 * e]), float(v[q * 8 + 2 * e + 1]));
+            ow[e] = *reinterpret_cast<uint32_t*>(&p);
+          }
+          d4[q] = o;
+        }
+        continue;
+      }
+    }
+    for (int k = 0; k < C * 9; ++k) dst[k] = from_u8<TOut>(v[k]);
   }
 }
 
 template <typename TOut>
 int im2col3x3_u8_nchw(const uint8_t* frame, TOut* col, int64_t N, int C, int H, int W, int64_t ldk, cudaStream_t stream) {
   ProfScope prof("im2col3x3_u8", stream);
-  const int64_t total = N * H * W * C;
+  TB_REQUIRE(C <= 4, "im2col3x3_u8_nchw: at most 4 input channels");
+  const int64_t total = N * H * W;
   if (total == 0) return 0;
-  if (ldk > int64_t(C) * 9) {  // zero the k padding once (columns [9C, ldk))
+  if (ldk > int64_t(C) * 9 && !(sizeof(TOut) == 2 && ldk == 40)) {  // zero the k padding (the vector path writes it itself)
     cudaError_t e = cudaMemsetAsync(col, 0, size_t(N) * H * W * ldk * sizeof(TOut), stream);
     TB_REQUIRE(e == cudaSuccess, "im2col3x3_u8: memset: %s", cudaGetErrorString(e));
   }
-  im2col3x3_u8_nchw_kernel<TOut><<<rgrid(total, 256), 256, 0, stream>>>(frame, col, N, C, H, W, ldk);
+  im2col3x3_u8_nchw_kernel<TOut><<<rgrid(total, 128), 128, 0, stream>>>(frame, col, N, C, H, W, ldk);
   return check_launch("im2col3x3_u8_nchw_kernel");
 }
 template int im2col3x3_u8_nchw<uint8_t>(const uint8_t*, uint8_t*, int64_t, int, int, int, int64_t, cudaStream_t);
@@ -159,8 +181,9 @@ template int col2im3x3<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*
                                       int, int, int, int64_t, cudaStream_t);
 
 template <typename T>
-__global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t N, int H, int W, int OH, int OW,
-                                   int CV) {
+__global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint8_t* __restrict__ arg, int64_t N,
+                                   int H, int W, int OH, int OW, int CV) {
+  // also records, per output element, which of the 9 window taps held the FIRST maximum (torch's rule)
   constexpr int V = Vec16<T>::N;
   const int64_t total = N * OH * OW * CV;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -171,8 +194,9 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restric
     const int oy = int(t % OH);
     const int64_t n = t / OH;
     float m[V];
+    uint8_t a[V];
 #pragma unroll
-    for (int j = 0; j < V; ++j) m[j] = -INFINITY;
+    for (int j = 0; j < V; ++j) { m[j] = -INFINITY; a[j] = 0; }
     for (int kh = 0; kh < 3; ++kh) {
       const int iy = oy * 2 + kh - 1;
       if (iy < 0 || iy >= H) continue;
@@ -182,18 +206,20 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restric
         float f[V];
         Vec16<T>::unpack(__ldg(x + ((n * H + iy) * W + ix) * CV + cv), f);
 #pragma unroll
-        for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], f[j]);
+        for (int j = 0; j < V; ++j)
+          if (f[j] > m[j]) { m[j] = f[j]; a[j] = uint8_t(kh * 3 + kw); }
       }
     }
     y[i] = Vec16<T>::pack(m);
+#pragma unroll
+    for (int j = 0; j < V; ++j) arg[i * V + j] = a[j];
   }
 }
 
 template <typename T>
-__global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx, int64_t N,
-                                   int H, int W, int OH, int OW, int CV) {
-  // gather form: input pixel (iy, ix) receives dy of every window whose FIRST maximum (row-major scan,
-  // torch's rule) is this pixel.
+__global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ arg, const uint4* __restrict__ dy, uint4* __restrict__ dx,
+                                   int64_t N, int H, int W, int OH, int OW, int CV) {
+  // gather form: input pixel (iy, ix) sums dy of the (at most 4) windows whose recorded argmax tap is this pixel
   constexpr int V = Vec16<T>::N;
   const int64_t total = N * H * W * CV;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
@@ -203,38 +229,23 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __r
     const int ix = int(t % W); t /= W;
     const int iy = int(t % H);
     const int64_t n = t / H;
-    float self[V], g[V];
-    Vec16<T>::unpack(__ldg(x + i), self);
+    float g[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) g[j] = 0.0f;
-    // windows containing (iy, ix): oy*2 - 1 <= iy <= oy*2 + 1
-    for (int oy = (iy) / 2; oy <= (iy + 1) / 2; ++oy) {
-      if (oy < 0 || oy >= OH) continue;
-      for (int ox = (ix) / 2; ox <= (ix + 1) / 2; ++ox) {
-        if (ox < 0 || ox >= OW) continue;
-        // is (iy, ix) the first maximum of window (oy, ox)?
-        bool first[V];
-#pragma unroll
-        for (int j = 0; j < V; ++j) first[j] = true;
-        for (int kh = 0; kh < 3; ++kh) {
-          const int yy = oy * 2 + kh - 1;
-          if (yy < 0 || yy >= H) continue;
-          for (int kw = 0; kw < 3; ++kw) {
-            const int xx = ox * 2 + kw - 1;
-            if (xx < 0 || xx >= W || (yy == iy && xx == ix)) continue;
-            float f[V];
-            Vec16<T>::unpack(__ldg(x + ((n * H + yy) * W + xx) * CV + cv), f);
-            const bool before = (yy < iy) || (yy == iy && xx < ix);
-#pragma unroll
-            for (int j = 0; j < V; ++j)
-              if (before ? (f[j] >= self[j]) : (f[j] > self[j])) first[j] = false;
-          }
-        }
+    for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {
+      if (oy >= OH) continue;
+      const int kh = iy - (oy * 2 - 1);
+      for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
+        if (ox >= OW) continue;
+        const int kw = ix - (ox * 2 - 1);
+        const uint8_t tap = uint8_t(kh * 3 + kw);
+        const int64_t o = ((n * OH + oy) * OW + ox) * CV + cv;
         float d[V];
-        Vec16<T>::unpack(__ldg(dy + ((n * OH + oy) * OW + ox) * CV + cv), d);
+        Vec16<T>::unpack(__ldg(dy + o), d);
+        const uint8_t* ap = arg + o * V;
 #pragma unroll
         for (int j = 0; j < V; ++j)
-          if (first[j]) g[j] += d[j];
+          if (ap[j] == tap) g[j] += d[j];
       }
     }
     dx[i] = Vec16<T>::pack(g);
@@ -242,32 +253,32 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ x, const uint4* __r
 }
 
 template <typename T>
-int maxpool3x3s2_fwd(const T* x, T* y, int64_t N, int H, int W, int C, cudaStream_t stream) {
+int maxpool3x3s2_fwd(const T* x, T* y, uint8_t* argmax, int64_t N, int H, int W, int C, cudaStream_t stream) {
   ProfScope prof("maxpool_fwd", stream);
   constexpr int V = Vec16<T>::N;
   TB_REQUIRE(C % V == 0, "maxpool: C must be a multiple of %d", V);
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
   const int64_t total = N * OH * OW * (C / V);
   if (total == 0) return 0;
-  maxpool_fwd_kernel<T><<<rgrid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), N, H,
-                                                                W, OH, OW, C / V);
+  maxpool_fwd_kernel<T><<<rgrid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y),
+                                                                argmax, N, H, W, OH, OW, C / V);
   return check_launch("maxpool_fwd_kernel");
 }
 template <typename T>
-int maxpool3x3s2_bwd(const T* x, const T* dy, T* dx, int64_t N, int H, int W, int C, cudaStream_t stream) {
+int maxpool3x3s2_bwd(const uint8_t* argmax, const T* dy, T* dx, int64_t N, int H, int W, int C, cudaStream_t stream) {
   ProfScope prof("maxpool_bwd", stream);
   constexpr int V = Vec16<T>::N;
   const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
   const int64_t total = N * H * W * (C / V);
   if (total == 0) return 0;
-  maxpool_bwd_kernel<T><<<rgrid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<const uint4*>(dy),
+  maxpool_bwd_kernel<T><<<rgrid(total, 256), 256, 0, stream>>>(argmax, reinterpret_cast<const uint4*>(dy),
                                                                 reinterpret_cast<uint4*>(dx), N, H, W, OH, OW, C / V);
   return check_launch("maxpool_bwd_kernel");
 }
-template int maxpool3x3s2_fwd<float>(const float*, float*, int64_t, int, int, int, cudaStream_t);
-template int maxpool3x3s2_fwd<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int64_t, int, int, int, cudaStream_t);
-template int maxpool3x3s2_bwd<float>(const float*, const float*, float*, int64_t, int, int, int, cudaStream_t);
-template int maxpool3x3s2_bwd<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, int64_t, int, int, int,
+template int maxpool3x3s2_fwd<float>(const float*, float*, uint8_t*, int64_t, int, int, int, cudaStream_t);
+template int maxpool3x3s2_fwd<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, uint8_t*, int64_t, int, int, int, cudaStream_t);
+template int maxpool3x3s2_bwd<float>(const uint8_t*, const float*, float*, int64_t, int, int, int, cudaStream_t);
+template int maxpool3x3s2_bwd<__nv_bfloat16>(const uint8_t*, const __nv_bfloat16*, __nv_bfloat16*, int64_t, int, int, int,
                                              cudaStream_t);
 
 template <typename T>

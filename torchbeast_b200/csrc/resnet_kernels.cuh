@@ -51,10 +51,11 @@ int col2im3x3(const T* dcol, const T* relu_src, const T* addend, T* dx, int64_t 
               cudaStream_t stream);
 
 // nn.MaxPool2d(kernel_size=3, stride=2, padding=1) forward / backward (first-maximum tie rule)
+// forward also records the argmax tap (0..8) of every output element; backward gathers through it
 template <typename T>
-int maxpool3x3s2_fwd(const T* x, T* y, int64_t N, int H, int W, int C, cudaStream_t stream);
+int maxpool3x3s2_fwd(const T* x, T* y, uint8_t* argmax, int64_t N, int H, int W, int C, cudaStream_t stream);
 template <typename T>
-int maxpool3x3s2_bwd(const T* x, const T* dy, T* dx, int64_t N, int H, int W, int C, cudaStream_t stream);
+int maxpool3x3s2_bwd(const uint8_t* argmax, const T* dy, T* dx, int64_t N, int H, int W, int C, cudaStream_t stream);
 
 // y = relu(x) (elementwise, n elements); dx = dy * (x > 0) + (addend ? addend : 0)
 template <typename T>
