@@ -435,7 +435,7 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) {
-  while (ld_acquire_u32(ctr) < target) __nanosleep(32);
+  while (ld_acquire_u32(ctr) < target) {}
   asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other CTAs -> our bulk copies
 }
 
@@ -514,34 +514,38 @@ __global__ void __launch_bounds__(kStepThreads) lstm_fwd_persistent_kernel(Persi
 #pragma unroll
     for (int o = 0; o < 16; ++o) part_s[wrp][o][lane] = acc[o];
     __syncthreads();
+    float gate_v = 0.0f;
     {
-      float v = 0.0f;
       if (lane < rows && j0 + ou < H) {
         float dot = 0.f;
 #pragma unroll
         for (int sidx = 0; sidx < 16; ++sidx) dot += part_s[sidx][wrp][lane];
         const float pre = pre_in + dot;
-        v = (oq == 2) ? tanhf(pre) : sigmoidf_(pre);
-        a.gates[(row0 + b) * 4 * H + int64_t(oq) * H + j0 + ou] = v;
+        gate_v = (oq == 2) ? tanhf(pre) : sigmoidf_(pre);
       }
-      act_s[oq][ou][lane] = v;
+      act_s[oq][ou][lane] = gate_v;
     }
     __syncthreads();
-    if (wrp < 4 && lane < rows && j0 + wrp < H) {
+    float c_new = 0.f, h_new = 0.f;
+    const bool upd = (wrp < 4 && lane < rows && j0 + wrp < H);
+    if (upd) {
       const int u = wrp;
-      const int64_t o = (row0 + b) * H + j0 + u;
       const float ig = act_s[0][u][lane], fg = act_s[1][u][lane], gg = act_s[2][u][lane], og = act_s[3][u][lane];
-      const float c = fg * cm_in + ig * gg;
-      const float h = og * tanhf(c);
-      a.cs[o] = c;
-      a.hs[o] = h;
-      if (!last) {
-        a.hm[(row0 + B + b) * Hp + j0 + u] = h * ndn_in;
-        a.cm[o + int64_t(B) * H] = c * ndn_in;
-      }
+      c_new = fg * cm_in + ig * gg;
+      h_new = og * tanhf(c_new);
+      // the only value other CTAs wait for: next step's masked recurrent input
+      if (!last) a.hm[(row0 + B + b) * Hp + j0 + u] = h_new * ndn_in;
     }
-    __syncthreads();  // all of this CTA's step-t writes are issued
+    __syncthreads();
     if (tid == 0 && !last) red_release_add(a.counter, 1u);
+    // everything below is consumed by this CTA (cm) or after the kernel (gates, cs, hs): off the critical path
+    if (lane < rows && j0 + ou < H) a.gates[(row0 + b) * 4 * H + int64_t(oq) * H + j0 + ou] = gate_v;
+    if (upd) {
+      const int64_t o = (row0 + b) * H + j0 + wrp;
+      a.cs[o] = c_new;
+      a.hs[o] = h_new;
+      if (!last) a.cm[o + int64_t(B) * H] = c_new * ndn_in;
+    }
   }
 }
 
@@ -583,10 +587,13 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_kernel(Persi
     const int64_t row0 = int64_t(t) * B;
     float* dgp_t = a.dgp + int64_t(it & 1) * 4 * gs;
     // ---- phase A: gate gradients of this CTA's 4 units (thread = batch row x unit) ----
-    if (ks == 0 && lane < rows && k0 + q < H) {
+    const bool actA = (ks == 0 && lane < rows && k0 + q < H);
+    float p_i = 0.f, p_f = 0.f, p_g = 0.f, p_o = 0.f;
+    int64_t g0 = 0;
+    if (actA) {
       const int j = k0 + q;
       const int64_t i = (row0 + lane) * H + j;
-      const int64_t g0 = (row0 + lane) * 4 * H + j;
+      g0 = (row0 + lane) * 4 * H + j;
       const float ig = a.gates[g0], fg = a.gates[g0 + H], gg = a.gates[g0 + 2 * H], og = a.gates[g0 + 3 * H];
       float dh = a.dy[i];
       float dc = 0.0f;
@@ -598,14 +605,17 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_kernel(Persi
       const float d_o = dh * tc;
       dc += dh * og * (1.0f - tc * tc);
       const float d_i = dc * gg, d_f = dc * a.cm[i], d_g = dc * ig;
-      const float p_i = d_i * ig * (1.0f - ig), p_f = d_f * fg * (1.0f - fg);
-      const float p_g = d_g * (1.0f - gg * gg), p_o = d_o * og * (1.0f - og);
-      a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o;
+      p_i = d_i * ig * (1.0f - ig); p_f = d_f * fg * (1.0f - fg);
+      p_g = d_g * (1.0f - gg * gg); p_o = d_o * og * (1.0f - og);
+      // what the other CTAs wait for: the gate-major padded copy feeding everybody's recurrent product
       const int64_t gp = int64_t(lane) * Hp + j;
       dgp_t[gp] = p_i; dgp_t[gs + gp] = p_f; dgp_t[2 * gs + gp] = p_g; dgp_t[3 * gs + gp] = p_o;
       dc_s[q][lane] = dc * fg * a.nd[row0 + lane];
     }
-    if (t == 0) break;  // uniform: no earlier step needs dh
+    if (t == 0) {  // uniform: no earlier step needs dh
+      if (actA) { a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o; }
+      break;
+    }
     __syncthreads();
     // ---- grid barrier: every CTA's gate gradients of step t are visible ----
     if (tid == 0) {
@@ -616,6 +626,8 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_kernel(Persi
         bulk_g2s(Xs + g * 32 * Hp, dgp_t + int64_t(g) * gs, xbytes, &bar[1 + g]);
       }
     }
+    // row-major copy for the weight-gradient GEMMs after the loop: off the critical path
+    if (actA) { a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o; }
     // ---- phase B: dh_raw[b, k0+c] = sum_g dgates_g[b,:] . W_hh[g*H + :, k0+c], c = 0..3 ----
     // warp = k-slice (1/16), every thread accumulates all 4 columns of its batch row
     float acc4[4] = {0.f, 0.f, 0.f, 0.f};
