@@ -403,11 +403,19 @@ def main():
     e2e_ms = max_over_ranks(t_e0.elapsed_time(t_e1)) / e2e_steps
     d2h_bytes = 4 * 4 + int(sum(1 for _ in stats["episode_returns"])) * 4
 
-    if rank != 0:
+    def finish():
+        """Leave without tearing NCCL down: destroy_process_group can hang while a captured CUDA graph still
+        references the communicator, and the process is exiting anyway."""
+        sys.stdout.flush(); sys.stderr.flush()
         if world > 1:
             import torch.distributed as dist
+            torch.cuda.synchronize()
             dist.barrier()
-            dist.destroy_process_group()
+            torch.cuda.synchronize()
+            os._exit(0)
+
+    if rank != 0:
+        finish()
         return
 
     pk = peaks()
@@ -476,10 +484,7 @@ def main():
         line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port",
                                     sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py" % (r["steps"], T, B))
     print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
+    finish()
 
 
 def vtrace_numbers(pk, T, B, A):
