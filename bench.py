@@ -414,7 +414,11 @@ def main():
             torch.cuda.synchronize()
             os._exit(0)
 
+    PSTEPS = 3
     if rank != 0:
+        if not args.no_profile:  # the profiled steps contain the gradient all-reduce: every rank takes part
+            for i in range(PSTEPS):
+                learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
         finish()
         return
 
@@ -435,7 +439,6 @@ def main():
     # ---- per-op device timing (separate steps; CUDA events around every op on its stream) ---
     if not args.no_profile:
         lib.tb_profile_enable(1)
-        PSTEPS = 3
         for i in range(PSTEPS):
             learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
         recs = _lib.profile_collect()
