@@ -185,6 +185,28 @@ def gemm_flops_table(N, A, use_lstm):
     return t
 
 
+def gemm_bytes_table(N, A, use_lstm, bf16):
+    """Algorithmic operand + result bytes of the tagged AtariNet GEMM ops (patch matrices are streamed once per
+    product) - with K of 64..576 most of these products are HBM streams, not tensor-pipe work."""
+    e = 2 if bf16 else 4
+    M1, M2, M3 = N * 400, N * 81, N * 49
+    e1 = 2 if bf16 else 1  # conv1 patch matrix: bf16 (tensor-core backend) or uint8 (fp32 backend)
+    t = {
+        "conv1_fwd": M1 * 256 * e1 + M1 * 32 * e, "conv2_fwd": M2 * 512 * e + M2 * 64 * e, "conv3_fwd": M3 * 576 * e + M3 * 64 * e,
+        "fc_fwd": N * 3136 * e + 512 * 3136 * e + N * 512 * 4,
+        "conv1_wgrad": M1 * 256 * e1 + M1 * 32 * e, "conv2_wgrad": M2 * 512 * e + M2 * 64 * e, "conv3_wgrad": M3 * 576 * e + M3 * 64 * e,
+        "fc_wgrad": N * 3136 * e + N * 512 * e + 512 * 3136 * 4,
+        "conv2_dgrad": M2 * 64 * e + M2 * 512 * e, "conv3_dgrad": M3 * 64 * e + M3 * 576 * e,
+        "fc_dgrad": N * 512 * e + 512 * 3136 * e + 2 * N * 3136 * e,
+    }
+    if use_lstm:
+        H = 512 + 1 + A
+        t.update({"lstm_xproj_fwd": 2 * (N * H * e + 4 * H * H * e + N * 4 * H * 4),
+                  "lstm_wgrad": 4 * (N * 4 * H * e + N * H * e + 4 * H * H * 4),
+                  "lstm_xproj_dgrad": 2 * (N * 4 * H * e + 4 * H * H * e + N * H * 4)})
+    return t
+
+
 def resnet_flops_table(N, A):
     """2*M*N*K per tagged op of the IMPALA ResNet trunk (aggregated over the 15 convs)."""
     secs = [(84, 42, 4, 16), (42, 21, 16, 32), (21, 11, 32, 32)]
@@ -450,12 +472,19 @@ def main():
         N = (T + 1) * B
         flops = gemm_flops_table(N, A, "resnet" if args.net == "resnet" else args.use_lstm)
         nbytes = hbm_bytes_table(N, T, B, A, args.use_lstm, model.flat_params.numel())
+        gbytes = gemm_bytes_table(N, A, args.use_lstm, model.precision == "bf16") if args.net == "atari" else {}
         ops = []
         for name, (tot, cnt) in agg.items():
             per_step = tot / PSTEPS
             o = dict(op=name, ms_per_step=per_step, launches_per_step=cnt / PSTEPS)
             if name in flops:
-                o.update(bound="tensor", achieved=flops[name] / (per_step * 1e-3) / 1e12, peak=pk["tensor"], unit="TFLOP/s")
+                tf = flops[name] / (per_step * 1e-3) / 1e12
+                o.update(bound="tensor", achieved=tf, peak=pk["tensor"], unit="TFLOP/s")
+                if name in gbytes:  # a GEMM whose operands stream once: report the binding roofline
+                    gb = gbytes[name] / (per_step * 1e-3) / 1e9
+                    o["tensor_frac"], o["hbm_frac"] = tf / pk["tensor"], gb / pk["hbm"]
+                    if gb / pk["hbm"] > tf / pk["tensor"]:
+                        o.update(bound="hbm", achieved=gb, peak=pk["hbm"], unit="GB/s")
             elif name in nbytes:
                 o.update(bound="hbm", achieved=nbytes[name] / (per_step * 1e-3) / 1e9, peak=pk["hbm"], unit="GB/s")
             if "achieved" in o:
