@@ -11,6 +11,7 @@
 // torch.nn.LSTM conventions: gate order i,f,g,o; weight_ih [4H,In], weight_hh [4H,H]; two biases.
 #include "lstm.cuh"
 
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "gemm_simt.cuh"
@@ -26,6 +27,9 @@ static inline int padded_h(int H) {
 }
 
 static inline int64_t ld16(int64_t n) { return (n + 7) & ~int64_t(7); }
+// row length (bf16 elements) of the tensor-core recurrence's operand tiles: K padded to 16, +8 so that a
+// row is an odd number of 16-byte chunks (conflict-free ldmatrix)
+static inline int mma_hq(int H) { return ((H + 15) & ~15) + 8; }
 
 size_t lstm_ws_bytes(int64_t T1, int64_t B, int In, int H, int layers, int precision) {
   return lstm_ws(nullptr, T1, B, In, H, layers, precision).bytes;
@@ -47,11 +51,12 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
       L.gates = takef(N * 4 * H); L.hs = takef(N * H); L.cs = takef(N * H); L.hm = takef(N * Hp);
       L.cm = takef(N * H); L.dgates = takef(N * 4 * H); L.bsum = takef(4 * H); L.w_hh_t = takef(int64_t(H + 4) * 4 * Hp);
       L.wp = takef(int64_t(4 * H + 4) * Hp);
-      L.xb = L.wihb = L.dgb = L.hmb = nullptr;
+      L.xb = L.wihb = L.dgb = L.hmb = L.hmq = L.dgq = nullptr;
       if (precision) {  // bf16 operand copies (2 bytes per element: take half the float count, rounded up)
         const int64_t in_l = (l == 0) ? In : H;
         L.xb = takef((N * ld16(in_l) + 1) / 2); L.wihb = takef((int64_t(4) * H * ld16(in_l) + 1) / 2);
         L.dgb = takef((N * ld16(4 * H) + 1) / 2); L.hmb = takef((N * ld16(H) + 1) / 2);
+        L.hmq = takef((N * mma_hq(H) + 1) / 2); L.dgq = takef((int64_t(2) * 4 * B * mma_hq(H) + 1) / 2);
       }
     } else {
       L = LstmLayerWs();
@@ -746,6 +751,367 @@ static int lstm_bwd_persistent(const LstmLayerWs& L, const LstmWs& ws, const flo
   return check_launch("lstm_bwd_persistent_kernel");
 }
 
+
+// =========================================================================================
+// Tensor-core variants of the persistent recurrence (bf16 backend): the per-step recurrent products run
+// on mma.sync.m16n8k16 (bf16 x bf16 -> fp32).  tcgen05 needs M >= 64 and smem-resident B, so for this
+// M = 32, N = 16/4, weights-in-registers product the warp-level MMA is the right tool: the CTA's W_hh
+// slice lives in REGISTERS as B fragments for all T+1 steps (nothing but the 34 KB bf16 h tile moves
+// per step), A fragments come from shared memory via ldmatrix.
+// =========================================================================================
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_ptr)));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct PersistFwdMmaArgs {
+  const float* w_hh;            // [4H, H] fp32 (converted to bf16 fragments once)
+  float* gates; float* hs; float* cs; float* cm; const float* nd;
+  __nv_bfloat16* hmq;           // [T1*B, Hq] masked recurrent inputs (hmq[0] pre-initialised)
+  unsigned* counter;
+  int T1, B, H, Hq; unsigned nctas;
+};
+
+constexpr int kMmaWarps = 8;     // warps that own k-slices of the product
+constexpr int kMaxKSteps = 6;    // ceil(ceil(H/16) / kMmaWarps) upper bound (H <= 768)
+
+__global__ void __launch_bounds__(kStepThreads) lstm_fwd_persistent_mma_kernel(PersistFwdMmaArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_b[];
+  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem_b);  // [32][Hq]
+  __shared__ float act_s[4][kStepUnits][33];
+  __shared__ float part_s[kMmaWarps][16][33];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int H = a.H, Hq = a.Hq, B = a.B;
+  const int j0 = blockIdx.x * kStepUnits;
+  const int b0 = blockIdx.y * 32;
+  const int rows = (B - b0 < 32) ? (B - b0) : 32;
+  const int ksteps = (H + 15) / 16;
+  const int kper = (ksteps + kMmaWarps - 1) / kMmaWarps;
+  const int ks0 = wrp * kper, ks1 = (ks0 + kper < ksteps) ? ks0 + kper : ksteps;
+  // B fragments of this CTA's 16 gate rows (o = gate*4 + unit), k-slice of this warp: registers for all steps
+  uint32_t bf[kMaxKSteps][2][2];
+  if (wrp < kMmaWarps) {
+#pragma unroll
+    for (int s = 0; s < kMaxKSteps; ++s) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int o = nt * 8 + (lane >> 2);
+        const int g = o >> 2, u = o & 3;
+        const bool okrow = (j0 + u < H);
+        const float* wr = a.w_hh + (int64_t(g) * H + j0 + u) * H;
+        const int k = (ks0 + s) * 16 + (lane & 3) * 2;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (okrow && ks0 + s < ks1) {
+          if (k < H) v[0] = wr[k];
+          if (k + 1 < H) v[1] = wr[k + 1];
+          if (k + 8 < H) v[2] = wr[k + 8];
+          if (k + 9 < H) v[3] = wr[k + 9];
+        }
+        bf[s][nt][0] = pack_bf16(v[0], v[1]);
+        bf[s][nt][1] = pack_bf16(v[2], v[3]);
+      }
+    }
+  }
+  const int b = b0 + lane;
+  const int oq = wrp >> 2, ou = wrp & 3;
+  const int chunks_per_row = Hq / 8;               // 16-byte chunks
+  uint4* Xs4 = reinterpret_cast<uint4*>(Xs);
+  for (int t = 0; t < a.T1; ++t) {
+    const int64_t row0 = int64_t(t) * B;
+    const bool last = (t == a.T1 - 1);
+    if (tid == 0 && t > 0) grid_wait(a.counter, unsigned(t) * a.nctas);
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(a.hmq + (row0 + b0) * Hq);
+    for (int i = tid; i < rows * chunks_per_row; i += kStepThreads) Xs4[i] = __ldcg(src + i);
+    float pre_in = 0.f, cm_in = 0.f, ndn_in = 0.f;
+    if (lane < rows && j0 + ou < H) {
+      pre_in = a.gates[(row0 + b) * 4 * H + int64_t(oq) * H + j0 + ou];
+      if (wrp < 4 && j0 + wrp < H) {
+        cm_in = a.cm[(row0 + b) * H + j0 + wrp];
+        if (!last) ndn_in = __ldg(a.nd + row0 + B + b);
+      }
+    }
+    __syncthreads();
+    if (wrp < kMmaWarps) {
+      float acc[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+      for (int s = 0; s < kMaxKSteps; ++s) {
+        if (ks0 + s < ks1) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t af[4];
+            ldmatrix_x4(af, Xs + (mt * 16 + (lane & 15)) * Hq + (ks0 + s) * 16 + (lane >> 4) * 8);
+            mma_bf16_16816(acc[mt][0], af, bf[s][0][0], bf[s][0][1]);
+            mma_bf16_16816(acc[mt][1], af, bf[s][1][0], bf[s][1][1]);
+          }
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int r = mt * 16 + (lane >> 2), c = nt * 8 + (lane & 3) * 2;
+          part_s[wrp][c][r] = acc[mt][nt][0]; part_s[wrp][c + 1][r] = acc[mt][nt][1];
+          part_s[wrp][c][r + 8] = acc[mt][nt][2]; part_s[wrp][c + 1][r + 8] = acc[mt][nt][3];
+        }
+    }
+    __syncthreads();
+    float gate_v = 0.0f;
+    if (lane < rows && j0 + ou < H) {
+      float dot = 0.f;
+#pragma unroll
+      for (int sidx = 0; sidx < kMmaWarps; ++sidx) dot += part_s[sidx][wrp][lane];
+      const float pre = pre_in + dot;
+      gate_v = (oq == 2) ? tanhf(pre) : sigmoidf_(pre);
+    }
+    act_s[oq][ou][lane] = gate_v;
+    __syncthreads();
+    float c_new = 0.f, h_new = 0.f;
+    const bool upd = (wrp < 4 && lane < rows && j0 + wrp < H);
+    if (upd) {
+      const int u = wrp;
+      const float ig = act_s[0][u][lane], fg = act_s[1][u][lane], gg = act_s[2][u][lane], og = act_s[3][u][lane];
+      c_new = fg * cm_in + ig * gg;
+      h_new = og * tanhf(c_new);
+      if (!last) a.hmq[(row0 + B + b) * Hq + j0 + u] = __float2bfloat16_rn(h_new * ndn_in);
+    }
+    __syncthreads();
+    if (tid == 0 && !last) red_release_add(a.counter, 1u);
+    if (lane < rows && j0 + ou < H) a.gates[(row0 + b) * 4 * H + int64_t(oq) * H + j0 + ou] = gate_v;
+    if (upd) {
+      const int64_t o = (row0 + b) * H + j0 + wrp;
+      a.cs[o] = c_new;
+      a.hs[o] = h_new;
+      if (!last) a.cm[o + int64_t(B) * H] = c_new * ndn_in;
+    }
+  }
+}
+
+struct PersistBwdMmaArgs {
+  const float* w_hh; const float* dy; const float* nd;
+  const float* gates; const float* cs; const float* cm;
+  float* dgates; __nv_bfloat16* dgq;   // dgq: [2][4, B, Hq]
+  unsigned* counter;
+  int T1, B, H, Hq; unsigned nctas;
+};
+
+constexpr int kMaxKStepsBwd = 12;  // ceil(4*ceil(H/16) / 16) upper bound (H <= 768)
+
+__global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(PersistBwdMmaArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_b[];
+  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem_b);  // [4 gates][32][Hq]
+  __shared__ float part16_s[16][4][33];
+  __shared__ float dh_s[4][33];
+  __shared__ float dc_s[4][33];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, q = wrp & 3, ks = wrp >> 2;
+  const int H = a.H, Hq = a.Hq, B = a.B;
+  const int k0 = blockIdx.x * 4;
+  const int rows = B < 32 ? B : 32;
+  const int kpg = (H + 15) / 16;           // k16 steps per gate
+  const int ksteps = 4 * kpg;
+  const int kper = (ksteps + 15) / 16;
+  const int ks0 = wrp * kper, ks1 = (ks0 + kper < ksteps) ? ks0 + kper : ksteps;
+  // B fragments: B[kk][n] = W_hh[g*H + j][k0 + n], kk = g*kpg*16 + j; n < 4 valid
+  uint32_t bf[kMaxKStepsBwd][2];
+#pragma unroll
+  for (int s = 0; s < kMaxKStepsBwd; ++s) {
+    const int st = ks0 + s;
+    const int g = st / kpg, j = (st % kpg) * 16 + (lane & 3) * 2;
+    const int n = lane >> 2;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (st < ks1 && n < 4 && k0 + n < H) {
+      const float* wc = a.w_hh + int64_t(g) * H * H + (k0 + n);
+      if (j < H) v[0] = wc[int64_t(j) * H];
+      if (j + 1 < H) v[1] = wc[int64_t(j + 1) * H];
+      if (j + 8 < H) v[2] = wc[int64_t(j + 8) * H];
+      if (j + 9 < H) v[3] = wc[int64_t(j + 9) * H];
+    }
+    bf[s][0] = pack_bf16(v[0], v[1]);
+    bf[s][1] = pack_bf16(v[2], v[3]);
+  }
+  if (tid < 128) { dh_s[q][lane] = 0.0f; dc_s[q][lane] = 0.0f; }
+  __syncthreads();
+  const int64_t gs = int64_t(B) * Hq;
+  const int chunks_per_row = Hq / 8;
+  uint4* Xs4 = reinterpret_cast<uint4*>(Xs);
+  int it = 0;
+  for (int t = a.T1 - 1; t >= 0; --t, ++it) {
+    const int64_t row0 = int64_t(t) * B;
+    __nv_bfloat16* dgq_t = a.dgq + int64_t(it & 1) * 4 * gs;
+    const bool actA = (ks == 0 && lane < rows && k0 + q < H);
+    float p_i = 0.f, p_f = 0.f, p_g = 0.f, p_o = 0.f;
+    int64_t g0 = 0;
+    if (actA) {
+      const int j = k0 + q;
+      const int64_t i = (row0 + lane) * H + j;
+      g0 = (row0 + lane) * 4 * H + j;
+      const float ig = a.gates[g0], fg = a.gates[g0 + H], gg = a.gates[g0 + 2 * H], og = a.gates[g0 + 3 * H];
+      float dh = a.dy[i];
+      float dc = 0.0f;
+      if (it > 0) {
+        dh += dh_s[q][lane] * a.nd[row0 + B + lane];
+        dc = dc_s[q][lane];
+      }
+      const float tc = tanhf(a.cs[i]);
+      const float d_o = dh * tc;
+      dc += dh * og * (1.0f - tc * tc);
+      const float d_i = dc * gg, d_f = dc * a.cm[i], d_g = dc * ig;
+      p_i = d_i * ig * (1.0f - ig); p_f = d_f * fg * (1.0f - fg);
+      p_g = d_g * (1.0f - gg * gg); p_o = d_o * og * (1.0f - og);
+      const int64_t gp = int64_t(lane) * Hq + j;
+      dgq_t[gp] = __float2bfloat16_rn(p_i); dgq_t[gs + gp] = __float2bfloat16_rn(p_f);
+      dgq_t[2 * gs + gp] = __float2bfloat16_rn(p_g); dgq_t[3 * gs + gp] = __float2bfloat16_rn(p_o);
+      dc_s[q][lane] = dc * fg * a.nd[row0 + lane];
+    }
+    if (t == 0) {
+      if (actA) { a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o; }
+      break;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      red_release_add(a.counter, 1u);
+      grid_wait(a.counter, unsigned(it + 1) * a.nctas);
+    }
+    if (actA) { a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o; }
+    __syncthreads();
+    // all four gate-gradient tiles of this step: [4][rows][Hq] bf16 (L2 -> smem, 16-byte chunks)
+    for (int g = 0; g < 4; ++g) {
+      const uint4* src = reinterpret_cast<const uint4*>(dgq_t + int64_t(g) * gs);
+      uint4* dst = Xs4 + int64_t(g) * 32 * chunks_per_row;
+      for (int i = tid; i < rows * chunks_per_row; i += kStepThreads) dst[i] = __ldcg(src + i);
+    }
+    __syncthreads();
+    float acc[2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[mt][e] = 0.f;
+#pragma unroll
+    for (int s = 0; s < kMaxKStepsBwd; ++s) {
+      const int st = ks0 + s;
+      if (st < ks1) {
+        const int g = st / kpg, kk = (st % kpg) * 16;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          uint32_t af[4];
+          ldmatrix_x4(af, Xs + (int64_t(g) * 32 + mt * 16 + (lane & 15)) * Hq + kk + (lane >> 4) * 8);
+          mma_bf16_16816(acc[mt], af, bf[s][0], bf[s][1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+      if (c < 4) {
+        part16_s[wrp][c][r] = acc[mt][0]; part16_s[wrp][c + 1][r] = acc[mt][1];
+        part16_s[wrp][c][r + 8] = acc[mt][2]; part16_s[wrp][c + 1][r + 8] = acc[mt][3];
+      }
+    }
+    __syncthreads();
+    if (wrp < 4) {
+      float d = 0.f;
+#pragma unroll
+      for (int sidx = 0; sidx < 16; ++sidx) d += part16_s[sidx][wrp][lane];
+      dh_s[wrp][lane] = d;
+    }
+    __syncthreads();
+  }
+}
+
+// hmq[0][b][:] = bf16(h0 * nd_0), zero padded; cm[0] = c0 * nd_0
+__global__ void lstm_init_state_q_kernel(const float* __restrict__ h0, const float* __restrict__ c0,
+                                         const float* __restrict__ nd, __nv_bfloat16* __restrict__ hmq,
+                                         float* __restrict__ cm, int B, int H, int Hq) {
+  const int64_t total = int64_t(B) * Hq;
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = int(i / Hq), k = int(i % Hq);
+  if (k < H) {
+    hmq[i] = __float2bfloat16_rn(h0[int64_t(b) * H + k] * nd[b]);
+    cm[int64_t(b) * H + k] = c0[int64_t(b) * H + k] * nd[b];
+  } else {
+    hmq[i] = __float2bfloat16_rn(0.0f);
+  }
+}
+
+template <typename Kernel>
+static int coop_fit(Kernel kernel, dim3 grid, size_t smem, size_t* attr_smem) {
+  if (*attr_smem < smem) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    *attr_smem = smem;
+  }
+  return persistent_ok((const void*)kernel, grid, smem);
+}
+
+static size_t g_fwd_mma_attr = 0, g_bwd_mma_attr = 0;
+
+// one decision for a (B, H) pair, used identically by forward and backward (the backward consumes the bf16
+// masked-h buffer only the tensor-core forward writes)
+static bool mma_recurrence_applicable(int64_t B, int H) {
+  const char* e = getenv("TB_LSTM_MMA");
+  if (e && e[0] == '0') return false;
+  if (!persistent_enabled() || B > 32 || H > 768) return false;
+  const int Hq = mma_hq(H);
+  dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
+  return coop_fit(lstm_fwd_persistent_mma_kernel, grid, size_t(32) * Hq * 2, &g_fwd_mma_attr) &&
+         coop_fit(lstm_bwd_persistent_mma_kernel, grid, size_t(4) * 32 * Hq * 2, &g_bwd_mma_attr);
+}
+
+static int lstm_fwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, float* hs, const float* notdone, int64_t T1,
+                                   int64_t B, int H, unsigned* counter, cudaStream_t st) {
+  const int Hq = mma_hq(H);
+  const size_t smem = size_t(32) * Hq * 2;
+  dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
+  if (!coop_fit(lstm_fwd_persistent_mma_kernel, grid, smem, &g_fwd_mma_attr)) return -1;
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+  TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
+  PersistFwdMmaArgs a;
+  a.w_hh = w_hh; a.gates = L.gates; a.hs = hs; a.cs = L.cs; a.cm = L.cm; a.nd = notdone;
+  a.hmq = static_cast<__nv_bfloat16*>(L.hmq); a.counter = counter;
+  a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nctas = grid.x;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)lstm_fwd_persistent_mma_kernel, grid, dim3(kStepThreads), args, smem, st);
+  TB_REQUIRE(e == cudaSuccess, "lstm_fwd_persistent_mma_kernel: %s", cudaGetErrorString(e));
+  return check_launch("lstm_fwd_persistent_mma_kernel");
+}
+
+static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, const float* dy, const float* notdone,
+                                   int64_t T1, int64_t B, int H, unsigned* counter, cudaStream_t st) {
+  const int Hq = mma_hq(H);
+  const size_t smem = size_t(4) * 32 * Hq * 2;
+  dim3 grid((H + 3) / 4, 1);
+  if (!coop_fit(lstm_bwd_persistent_mma_kernel, grid, smem, &g_bwd_mma_attr)) return -1;
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(L.dgq, 0, size_t(2) * 4 * B * Hq * 2, st);  // zero the row padding
+  TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
+  PersistBwdMmaArgs a;
+  a.w_hh = w_hh; a.dy = dy; a.nd = notdone; a.gates = L.gates; a.cs = L.cs; a.cm = L.cm; a.dgates = L.dgates;
+  a.dgq = static_cast<__nv_bfloat16*>(L.dgq); a.counter = counter;
+  a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nctas = grid.x;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)lstm_bwd_persistent_mma_kernel, grid, dim3(kStepThreads), args, smem, st);
+  TB_REQUIRE(e == cudaSuccess, "lstm_bwd_persistent_mma_kernel: %s", cudaGetErrorString(e));
+  return check_launch("lstm_bwd_persistent_mma_kernel");
+}
+
 #define TB_TRY(expr)        \
   do {                      \
     int _rc = (expr);       \
@@ -787,7 +1153,17 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
       TB_TRY(check_launch("lstm_init_state_kernel"));
     }
     ProfScope prof("lstm_recurrence_fwd", st);
-    const int prc = lstm_fwd_persistent(L, hs, notdone, T1, B, H, ws.sync, st);
+    int prc = -1;
+    if (precision && mma_recurrence_applicable(B, H)) {
+      const int Hq = mma_hq(H);
+      cudaError_t eq = cudaMemsetAsync(L.hmq, 0, size_t(N) * Hq * 2, st);
+      TB_REQUIRE(eq == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(eq));
+      lstm_init_state_q_kernel<<<(unsigned)((B * Hq + 255) / 256), 256, 0, st>>>(
+          h0 + int64_t(l) * B * H, c0 + int64_t(l) * B * H, notdone, static_cast<__nv_bfloat16*>(L.hmq), L.cm, int(B), H, Hq);
+      TB_TRY(check_launch("lstm_init_state_q_kernel"));
+      prc = lstm_fwd_persistent_mma(L, p.w_hh[l], hs, notdone, T1, B, H, ws.sync, st);
+    }
+    if (prc < 0) prc = lstm_fwd_persistent(L, hs, notdone, T1, B, H, ws.sync, st);
     if (prc > 0) return prc;
     for (int64_t t = 0; prc < 0 && t < T1; ++t) {
       StepArgs a;
@@ -840,6 +1216,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     const int in_dim = (l == 0) ? In : H;
     float* dxl = (l == 0) ? dx : ws.dx_mid;
     const int Hp = padded_h(H);
+    const bool use_mma = precision && mma_recurrence_applicable(B, H);
     {
       const int64_t tot = int64_t(H + 4) * 4 * Hp;
       lstm_pack_whh_t_kernel<<<(unsigned)((tot + 255) / 256 > 1184 ? 1184 : (tot + 255) / 256), 256, 0, st>>>(p.w_hh[l], L.w_hh_t, H, Hp);
@@ -849,7 +1226,9 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     }
     {
     ProfScope prof("lstm_recurrence_bwd", st);
-    const int prc = lstm_bwd_persistent(L, ws, dyl, notdone, T1, B, H, ws.sync + 16, st);
+    int prc = -1;
+    if (use_mma) prc = lstm_bwd_persistent_mma(L, p.w_hh[l], dyl, notdone, T1, B, H, ws.sync + 16, st);
+    if (prc < 0) prc = lstm_bwd_persistent(L, ws, dyl, notdone, T1, B, H, ws.sync + 16, st);
     if (prc > 0) return prc;
     for (int64_t t = T1 - 1; prc < 0 && t >= 0; --t) {
       BwdPointArgs a;
@@ -874,12 +1253,18 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     if (precision) {
       const int64_t lg = ld16(4 * H), lh = ld16(H), li = ld16(in_dim);
       TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st));
-      TB_TRY(f32_to_bf16(L.hm, L.hmb, N, H, padded_h(H), lh, st));
+      const void* hm_b = L.hmb;
+      int64_t hm_ld = lh;
+      if (use_mma) {  // the tensor-core forward recurrence already left the masked h in bf16
+        hm_b = L.hmq; hm_ld = mma_hq(H);
+      } else {
+        TB_TRY(f32_to_bf16(L.hm, L.hmb, N, H, padded_h(H), lh, st));
+      }
       const int64_t kb = (N + 63) / 64;
       int sp = int(kb / 8); if (sp < 1) sp = 1; if (sp > 4) sp = 4;
       TcEpilogue te; te.tag = "lstm_wgrad";
       te.C = g.w_hh[l]; te.ldc = H;      // dW_hh[4H,H] = dgates^T . hm   (both operands stored [N, .]: MN-major)
-      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.hmb, 4 * H, H, N, lg, lh, true, true, te, sp, splitk, st));
+      TB_TRY(gemm_tc_bf16_ex(L.dgb, hm_b, 4 * H, H, N, lg, hm_ld, true, true, te, sp, splitk, st));
       te.C = g.w_ih[l]; te.ldc = in_dim;  // dW_ih[4H,in] = dgates^T . x
       TB_TRY(gemm_tc_bf16_ex(L.dgb, L.xb, 4 * H, in_dim, N, lg, li, true, true, te, sp, splitk, st));
       TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));

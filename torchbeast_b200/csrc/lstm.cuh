@@ -26,6 +26,8 @@ struct LstmLayerWs {
   void* wihb;     // bf16 [4H, ld16(In)]     W_ih
   void* dgb;      // bf16 [T1*B, ld16(4H)]   gate gradients
   void* hmb;      // bf16 [T1*B, ld16(H)]    masked recurrent inputs
+  void* hmq;      // bf16 [T1*B, Hq]         masked recurrent inputs written by the tensor-core recurrence (Hq = mma_hq(H))
+  void* dgq;      // bf16 [2][4, B, Hq]      this step's gate gradients for the tensor-core backward recurrence
   float* wp;      // [4H+4, Hp]  W_hh with rows zero-padded to Hp floats (16-byte multiples for bulk copies)
   float* dgates;  // [T1*B, 4H]  backward: d pre-activations
   float* bsum;    // [4H]        b_ih + b_hh
