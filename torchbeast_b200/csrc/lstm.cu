@@ -950,33 +950,44 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
   const int chunks_per_row = Hq / 8;
   uint4* Xs4 = reinterpret_cast<uint4*>(Xs);
   int it = 0;
+  const bool actA = (ks == 0 && lane < rows && k0 + q < H);
+  // phase-A operands of the NEXT processed step are fetched one step ahead (they do not depend on the
+  // recurrence), so the pointwise phase after the grid barrier runs from registers
+  float n_ig = 0.f, n_fg = 0.f, n_gg = 0.f, n_og = 0.f, n_dy = 0.f, n_cs = 0.f, n_cm = 0.f, n_nd = 0.f, n_ndn = 0.f;
+  auto prefetch = [&](int t) {
+    if (!actA || t < 0) return;
+    const int64_t r0 = int64_t(t) * B;
+    const int64_t i = (r0 + lane) * H + k0 + q, g = (r0 + lane) * 4 * H + k0 + q;
+    n_ig = a.gates[g]; n_fg = a.gates[g + H]; n_gg = a.gates[g + 2 * H]; n_og = a.gates[g + 3 * H];
+    n_dy = a.dy[i]; n_cs = a.cs[i]; n_cm = a.cm[i]; n_nd = a.nd[r0 + lane];
+    n_ndn = (t + 1 < a.T1) ? a.nd[r0 + B + lane] : 0.f;
+  };
+  prefetch(a.T1 - 1);
   for (int t = a.T1 - 1; t >= 0; --t, ++it) {
     const int64_t row0 = int64_t(t) * B;
     __nv_bfloat16* dgq_t = a.dgq + int64_t(it & 1) * 4 * gs;
-    const bool actA = (ks == 0 && lane < rows && k0 + q < H);
     float p_i = 0.f, p_f = 0.f, p_g = 0.f, p_o = 0.f;
     int64_t g0 = 0;
     if (actA) {
       const int j = k0 + q;
-      const int64_t i = (row0 + lane) * H + j;
       g0 = (row0 + lane) * 4 * H + j;
-      const float ig = a.gates[g0], fg = a.gates[g0 + H], gg = a.gates[g0 + 2 * H], og = a.gates[g0 + 3 * H];
-      float dh = a.dy[i];
+      const float ig = n_ig, fg = n_fg, gg = n_gg, og = n_og;
+      float dh = n_dy;
       float dc = 0.0f;
       if (it > 0) {
-        dh += dh_s[q][lane] * a.nd[row0 + B + lane];
+        dh += dh_s[q][lane] * n_ndn;
         dc = dc_s[q][lane];
       }
-      const float tc = tanhf(a.cs[i]);
+      const float tc = tanhf(n_cs);
       const float d_o = dh * tc;
       dc += dh * og * (1.0f - tc * tc);
-      const float d_i = dc * gg, d_f = dc * a.cm[i], d_g = dc * ig;
+      const float d_i = dc * gg, d_f = dc * n_cm, d_g = dc * ig;
       p_i = d_i * ig * (1.0f - ig); p_f = d_f * fg * (1.0f - fg);
       p_g = d_g * (1.0f - gg * gg); p_o = d_o * og * (1.0f - og);
       const int64_t gp = int64_t(lane) * Hq + j;
       dgq_t[gp] = __float2bfloat16_rn(p_i); dgq_t[gs + gp] = __float2bfloat16_rn(p_f);
       dgq_t[2 * gs + gp] = __float2bfloat16_rn(p_g); dgq_t[3 * gs + gp] = __float2bfloat16_rn(p_o);
-      dc_s[q][lane] = dc * fg * a.nd[row0 + lane];
+      dc_s[q][lane] = dc * fg * n_nd;
     }
     if (t == 0) {
       if (actA) { a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o; }
@@ -988,6 +999,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
       grid_wait(a.counter, unsigned(it + 1) * a.nctas);
     }
     if (actA) { a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o; }
+    prefetch(t - 1);
     __syncthreads();
     // all four gate-gradient tiles of this step: [4][rows][Hq] bf16 (L2 -> smem, 16-byte chunks)
     for (int g = 0; g < 4; ++g) {
