@@ -911,48 +911,54 @@ struct PersistBwdMmaArgs {
 };
 
 constexpr int kMaxKStepsBwd = 12;  // ceil(4*ceil(H/16) / 16) upper bound (H <= 768)
+constexpr int kBwdCols = 16;       // output columns (hidden units) per CTA: 2 full n8 MMA tiles
 
+// Every CTA needs ALL gate gradients of the step (4 x [32, H] bf16 = 137 KB): with 4 columns per CTA the
+// 130 CTAs pulled 17.8 MB per step through L2 and the step was L2-bandwidth bound (measured 8 us vs 4.6 us
+// for the forward); 16 columns per CTA cut that to 4.5 MB and fill both n8 tiles of the MMA.
 __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(PersistBwdMmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem_b[];
   __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem_b);  // [4 gates][32][Hq]
-  __shared__ float part16_s[16][4][33];
-  __shared__ float dh_s[4][33];
-  __shared__ float dc_s[4][33];
-  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, q = wrp & 3, ks = wrp >> 2;
+  __shared__ float part16_s[16][kBwdCols][33];
+  __shared__ float dh_s[kBwdCols][33];
+  __shared__ float dc_s[kBwdCols][33];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int H = a.H, Hq = a.Hq, B = a.B;
-  const int k0 = blockIdx.x * 4;
+  const int k0 = blockIdx.x * kBwdCols;
   const int rows = B < 32 ? B : 32;
   const int kpg = (H + 15) / 16;           // k16 steps per gate
   const int ksteps = 4 * kpg;
   const int kper = (ksteps + 15) / 16;
   const int ks0 = wrp * kper, ks1 = (ks0 + kper < ksteps) ? ks0 + kper : ksteps;
-  // B fragments: B[kk][n] = W_hh[g*H + j][k0 + n], kk = g*kpg*16 + j; n < 4 valid
-  uint32_t bf[kMaxKStepsBwd][2];
+  // B fragments: B[kk][n] = W_hh[g*H + j][k0 + n], kk = g*kpg*16 + j
+  uint32_t bf[kMaxKStepsBwd][2][2];
 #pragma unroll
   for (int s = 0; s < kMaxKStepsBwd; ++s) {
     const int st = ks0 + s;
     const int g = st / kpg, j = (st % kpg) * 16 + (lane & 3) * 2;
-    const int n = lane >> 2;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (st < ks1 && n < 4 && k0 + n < H) {
-      const float* wc = a.w_hh + int64_t(g) * H * H + (k0 + n);
-      if (j < H) v[0] = wc[int64_t(j) * H];
-      if (j + 1 < H) v[1] = wc[int64_t(j + 1) * H];
-      if (j + 8 < H) v[2] = wc[int64_t(j + 8) * H];
-      if (j + 9 < H) v[3] = wc[int64_t(j + 9) * H];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int n = nt * 8 + (lane >> 2);
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (st < ks1 && k0 + n < H) {
+        const float* wc = a.w_hh + int64_t(g) * H * H + (k0 + n);
+        if (j < H) v[0] = wc[int64_t(j) * H];
+        if (j + 1 < H) v[1] = wc[int64_t(j + 1) * H];
+        if (j + 8 < H) v[2] = wc[int64_t(j + 8) * H];
+        if (j + 9 < H) v[3] = wc[int64_t(j + 9) * H];
+      }
+      bf[s][nt][0] = pack_bf16(v[0], v[1]);
+      bf[s][nt][1] = pack_bf16(v[2], v[3]);
     }
-    bf[s][0] = pack_bf16(v[0], v[1]);
-    bf[s][1] = pack_bf16(v[2], v[3]);
   }
-  if (tid < 128) { dh_s[q][lane] = 0.0f; dc_s[q][lane] = 0.0f; }
+  dh_s[wrp][lane] = 0.0f; dc_s[wrp][lane] = 0.0f;
   __syncthreads();
   const int64_t gs = int64_t(B) * Hq;
   const int chunks_per_row = Hq / 8;
   uint4* Xs4 = reinterpret_cast<uint4*>(Xs);
   int it = 0;
-  const bool actA = (ks == 0 && lane < rows && k0 + q < H);
-  // phase-A operands of the NEXT processed step are fetched one step ahead (they do not depend on the
-  // recurrence), so the pointwise phase after the grid barrier runs from registers
+  const int q = wrp;  // phase A: thread = (batch row lane, unit k0 + wrp)
+  const bool actA = (lane < rows && k0 + q < H);
   float n_ig = 0.f, n_fg = 0.f, n_gg = 0.f, n_og = 0.f, n_dy = 0.f, n_cs = 0.f, n_cm = 0.f, n_nd = 0.f, n_ndn = 0.f;
   auto prefetch = [&](int t) {
     if (!actA || t < 0) return;
@@ -1008,11 +1014,13 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
       for (int i = tid; i < rows * chunks_per_row; i += kStepThreads) dst[i] = __ldcg(src + i);
     }
     __syncthreads();
-    float acc[2][4];
+    float acc[2][2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[mt][e] = 0.f;
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
 #pragma unroll
     for (int s = 0; s < kMaxKStepsBwd; ++s) {
       const int st = ks0 + s;
@@ -1022,20 +1030,21 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
         for (int mt = 0; mt < 2; ++mt) {
           uint32_t af[4];
           ldmatrix_x4(af, Xs + (int64_t(g) * 32 + mt * 16 + (lane & 15)) * Hq + kk + (lane >> 4) * 8);
-          mma_bf16_16816(acc[mt], af, bf[s][0], bf[s][1]);
+          mma_bf16_16816(acc[mt][0], af, bf[s][0][0], bf[s][0][1]);
+          mma_bf16_16816(acc[mt][1], af, bf[s][1][0], bf[s][1][1]);
         }
       }
     }
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt) {
-      const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
-      if (c < 4) {
-        part16_s[wrp][c][r] = acc[mt][0]; part16_s[wrp][c + 1][r] = acc[mt][1];
-        part16_s[wrp][c][r + 8] = acc[mt][2]; part16_s[wrp][c + 1][r + 8] = acc[mt][3];
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const int r = mt * 16 + (lane >> 2), c = nt * 8 + (lane & 3) * 2;
+        part16_s[wrp][c][r] = acc[mt][nt][0]; part16_s[wrp][c + 1][r] = acc[mt][nt][1];
+        part16_s[wrp][c][r + 8] = acc[mt][nt][2]; part16_s[wrp][c + 1][r + 8] = acc[mt][nt][3];
       }
-    }
     __syncthreads();
-    if (wrp < 4) {
+    {
       float d = 0.f;
 #pragma unroll
       for (int sidx = 0; sidx < 16; ++sidx) d += part16_s[sidx][wrp][lane];
@@ -1082,9 +1091,9 @@ static bool mma_recurrence_applicable(int64_t B, int H) {
   if (e && e[0] == '0') return false;
   if (!persistent_enabled() || B > 32 || H > 768) return false;
   const int Hq = mma_hq(H);
-  dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
+  dim3 grid((H + kStepUnits - 1) / kStepUnits, 1), gridb((H + kBwdCols - 1) / kBwdCols, 1);
   return coop_fit(lstm_fwd_persistent_mma_kernel, grid, size_t(32) * Hq * 2, &g_fwd_mma_attr) &&
-         coop_fit(lstm_bwd_persistent_mma_kernel, grid, size_t(4) * 32 * Hq * 2, &g_bwd_mma_attr);
+         coop_fit(lstm_bwd_persistent_mma_kernel, gridb, size_t(4) * 32 * Hq * 2, &g_bwd_mma_attr);
 }
 
 static int lstm_fwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, float* hs, const float* notdone, int64_t T1,
@@ -1109,7 +1118,7 @@ static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, cons
                                    int64_t T1, int64_t B, int H, unsigned* counter, cudaStream_t st) {
   const int Hq = mma_hq(H);
   const size_t smem = size_t(4) * 32 * Hq * 2;
-  dim3 grid((H + 3) / 4, 1);
+  dim3 grid((H + kBwdCols - 1) / kBwdCols, 1);
   if (!coop_fit(lstm_bwd_persistent_mma_kernel, grid, smem, &g_bwd_mma_attr)) return -1;
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(L.dgq, 0, size_t(2) * 4 * B * Hq * 2, st);  // zero the row padding
