@@ -831,7 +831,20 @@ __global__ void __launch_bounds__(kStepThreads) lstm_fwd_persistent_mma_kernel(P
     if (tid == 0 && t > 0) grid_wait(a.counter, unsigned(t) * a.nctas);
     __syncthreads();
     const uint4* src = reinterpret_cast<const uint4*>(a.hmq + (row0 + b0) * Hq);
-    for (int i = tid; i < rows * chunks_per_row; i += kStepThreads) Xs4[i] = __ldcg(src + i);
+    {
+      const int nchunk = rows * chunks_per_row;  // <= 5 chunks per thread: all loads in flight, then the stores
+      uint4 v[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int i = tid + u * kStepThreads;
+        if (i < nchunk) v[u] = __ldcg(src + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int i = tid + u * kStepThreads;
+        if (i < nchunk) Xs4[i] = v[u];
+      }
+    }
     float pre_in = 0.f, cm_in = 0.f, ndn_in = 0.f;
     if (lane < rows && j0 + ou < H) {
       pre_in = a.gates[(row0 + b) * 4 * H + int64_t(oq) * H + j0 + ou];
@@ -911,11 +924,12 @@ struct PersistBwdMmaArgs {
 };
 
 constexpr int kMaxKStepsBwd = 12;  // ceil(4*ceil(H/16) / 16) upper bound (H <= 768)
-constexpr int kBwdCols = 16;       // output columns (hidden units) per CTA: 2 full n8 MMA tiles
+constexpr int kBwdCols = 8;        // output columns (hidden units) per CTA: one full n8 MMA tile
+constexpr int kBwdNT = kBwdCols / 8;
 
-// Every CTA needs ALL gate gradients of the step (4 x [32, H] bf16 = 137 KB): with 4 columns per CTA the
-// 130 CTAs pulled 17.8 MB per step through L2 and the step was L2-bandwidth bound (measured 8 us vs 4.6 us
-// for the forward); 16 columns per CTA cut that to 4.5 MB and fill both n8 tiles of the MMA.
+// Every CTA needs ALL gate gradients of the step (4 x [32, H] bf16 = 137 KB, pulled L2 -> smem with all loads
+// of a thread in flight at once); 8 columns per CTA (65 CTAs) fill the n8 MMA tile and halve the per-step L2
+// traffic against 4 columns (measured: 4 cols 8.0 us/step, 16 cols 9.8 us/step with too few SMs pulling).
 __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(PersistBwdMmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem_b[];
   __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem_b);  // [4 gates][32][Hq]
@@ -931,13 +945,13 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
   const int kper = (ksteps + 15) / 16;
   const int ks0 = wrp * kper, ks1 = (ks0 + kper < ksteps) ? ks0 + kper : ksteps;
   // B fragments: B[kk][n] = W_hh[g*H + j][k0 + n], kk = g*kpg*16 + j
-  uint32_t bf[kMaxKStepsBwd][2][2];
+  uint32_t bf[kMaxKStepsBwd][kBwdNT][2];
 #pragma unroll
   for (int s = 0; s < kMaxKStepsBwd; ++s) {
     const int st = ks0 + s;
     const int g = st / kpg, j = (st % kpg) * 16 + (lane & 3) * 2;
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt) {
+    for (int nt = 0; nt < kBwdNT; ++nt) {
       const int n = nt * 8 + (lane >> 2);
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       if (st < ks1 && k0 + n < H) {
@@ -951,14 +965,14 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
       bf[s][nt][1] = pack_bf16(v[2], v[3]);
     }
   }
-  dh_s[wrp][lane] = 0.0f; dc_s[wrp][lane] = 0.0f;
+  if (wrp < kBwdCols) { dh_s[wrp][lane] = 0.0f; dc_s[wrp][lane] = 0.0f; }
   __syncthreads();
   const int64_t gs = int64_t(B) * Hq;
   const int chunks_per_row = Hq / 8;
   uint4* Xs4 = reinterpret_cast<uint4*>(Xs);
   int it = 0;
   const int q = wrp;  // phase A: thread = (batch row lane, unit k0 + wrp)
-  const bool actA = (lane < rows && k0 + q < H);
+  const bool actA = (wrp < kBwdCols && lane < rows && k0 + q < H);
   float n_ig = 0.f, n_fg = 0.f, n_gg = 0.f, n_og = 0.f, n_dy = 0.f, n_cs = 0.f, n_cm = 0.f, n_nd = 0.f, n_ndn = 0.f;
   auto prefetch = [&](int t) {
     if (!actA || t < 0) return;
@@ -1008,17 +1022,36 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
     prefetch(t - 1);
     __syncthreads();
     // all four gate-gradient tiles of this step: [4][rows][Hq] bf16 (L2 -> smem, 16-byte chunks)
-    for (int g = 0; g < 4; ++g) {
-      const uint4* src = reinterpret_cast<const uint4*>(dgq_t + int64_t(g) * gs);
-      uint4* dst = Xs4 + int64_t(g) * 32 * chunks_per_row;
-      for (int i = tid; i < rows * chunks_per_row; i += kStepThreads) dst[i] = __ldcg(src + i);
+    {
+      // every thread first issues ALL its loads (up to 5 per gate tile), then stores: ~20 x 16 B in flight per
+      // thread instead of one (a load->store loop left the copy latency-bound at ~16 B/clk per SM)
+      const int nchunk = rows * chunks_per_row;
+      uint4 v[4][5];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint4* src = reinterpret_cast<const uint4*>(dgq_t + int64_t(g) * gs);
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int i = tid + u * kStepThreads;
+          if (i < nchunk) v[g][u] = __ldcg(src + i);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4* dst = Xs4 + int64_t(g) * 32 * chunks_per_row;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int i = tid + u * kStepThreads;
+          if (i < nchunk) dst[i] = v[g][u];
+        }
+      }
     }
     __syncthreads();
-    float acc[2][2][4];
+    float acc[2][kBwdNT][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < kBwdNT; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
 #pragma unroll
@@ -1030,21 +1063,21 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
         for (int mt = 0; mt < 2; ++mt) {
           uint32_t af[4];
           ldmatrix_x4(af, Xs + (int64_t(g) * 32 + mt * 16 + (lane & 15)) * Hq + kk + (lane >> 4) * 8);
-          mma_bf16_16816(acc[mt][0], af, bf[s][0][0], bf[s][0][1]);
-          mma_bf16_16816(acc[mt][1], af, bf[s][1][0], bf[s][1][1]);
+#pragma unroll
+          for (int nt = 0; nt < kBwdNT; ++nt) mma_bf16_16816(acc[mt][nt], af, bf[s][nt][0], bf[s][nt][1]);
         }
       }
     }
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt) {
+      for (int nt = 0; nt < kBwdNT; ++nt) {
         const int r = mt * 16 + (lane >> 2), c = nt * 8 + (lane & 3) * 2;
         part16_s[wrp][c][r] = acc[mt][nt][0]; part16_s[wrp][c + 1][r] = acc[mt][nt][1];
         part16_s[wrp][c][r + 8] = acc[mt][nt][2]; part16_s[wrp][c + 1][r + 8] = acc[mt][nt][3];
       }
     __syncthreads();
-    {
+    if (wrp < kBwdCols) {
       float d = 0.f;
 #pragma unroll
       for (int sidx = 0; sidx < 16; ++sidx) d += part16_s[sidx][wrp][lane];
@@ -1089,7 +1122,7 @@ static size_t g_fwd_mma_attr = 0, g_bwd_mma_attr = 0;
 static bool mma_recurrence_applicable(int64_t B, int H) {
   const char* e = getenv("TB_LSTM_MMA");
   if (e && e[0] == '0') return false;
-  if (!persistent_enabled() || B > 32 || H > 768) return false;
+  if (!persistent_enabled() || B > 32 || H > 624) return false;  // tile copy: <= 5 x 16 B chunks per thread
   const int Hq = mma_hq(H);
   dim3 grid((H + kStepUnits - 1) / kStepUnits, 1), gridb((H + kBwdCols - 1) / kBwdCols, 1);
   return coop_fit(lstm_fwd_persistent_mma_kernel, grid, size_t(32) * Hq * 2, &g_fwd_mma_attr) &&
