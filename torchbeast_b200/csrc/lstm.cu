@@ -936,6 +936,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
   __shared__ float part16_s[16][kBwdCols][33];
   __shared__ float dh_s[kBwdCols][33];
   __shared__ float dc_s[kBwdCols][33];
+  __shared__ __align__(16) __nv_bfloat16 stg_s[4][32][kBwdCols];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int H = a.H, Hq = a.Hq, B = a.B;
   const int k0 = blockIdx.x * kBwdCols;
@@ -1004,14 +1005,22 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
       const float d_i = dc * gg, d_f = dc * n_cm, d_g = dc * ig;
       p_i = d_i * ig * (1.0f - ig); p_f = d_f * fg * (1.0f - fg);
       p_g = d_g * (1.0f - gg * gg); p_o = d_o * og * (1.0f - og);
-      const int64_t gp = int64_t(lane) * Hq + j;
-      dgq_t[gp] = __float2bfloat16_rn(p_i); dgq_t[gs + gp] = __float2bfloat16_rn(p_f);
-      dgq_t[2 * gs + gp] = __float2bfloat16_rn(p_g); dgq_t[3 * gs + gp] = __float2bfloat16_rn(p_o);
       dc_s[q][lane] = dc * fg * n_nd;
     }
     if (t == 0) {
       if (actA) { a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o; }
       break;
+    }
+    // publish this CTA's 8 columns of the four gate-gradient tiles with 16-byte stores (staged through smem:
+    // 128 full-sector stores instead of 1024 scattered 2-byte ones ahead of the grid release)
+    if (wrp < kBwdCols) {
+      stg_s[0][lane][q] = __float2bfloat16_rn(p_i); stg_s[1][lane][q] = __float2bfloat16_rn(p_f);
+      stg_s[2][lane][q] = __float2bfloat16_rn(p_g); stg_s[3][lane][q] = __float2bfloat16_rn(p_o);
+    }
+    __syncthreads();
+    if (tid < 128 && (tid & 31) < rows) {
+      const int g = tid >> 5, bb = tid & 31;
+      *reinterpret_cast<uint4*>(dgq_t + int64_t(g) * gs + int64_t(bb) * Hq + k0) = *reinterpret_cast<const uint4*>(&stg_s[g][bb][0]);
     }
     __syncthreads();
     if (tid == 0) {
