@@ -439,8 +439,16 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) {
-  while (ld_acquire_u32(ctr) < target) {}
+  // spin on cheap relaxed loads (an acquire load per poll costs an L1 invalidation each time - ncu showed
+  // CCTL.IVALL in the loop and ~30 % of the step stalled at the barrier), then ONE acquire fence
+  while (ld_relaxed_u32(ctr) < target) {}
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
   asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other CTAs -> our bulk copies
 }
 
@@ -1035,23 +1043,26 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
       // every thread first issues ALL its loads (up to 5 per gate tile), then stores: ~20 x 16 B in flight per
       // thread instead of one (a load->store loop left the copy latency-bound at ~16 B/clk per SM)
       const int nchunk = rows * chunks_per_row;
-      uint4 v[4][5];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const uint4* src = reinterpret_cast<const uint4*>(dgq_t + int64_t(g) * gs);
+      for (int half = 0; half < 2; ++half) {  // two gate tiles (10 x 16 B per thread) per batch: fits the register budget
+        uint4 v[2][5];
 #pragma unroll
-        for (int u = 0; u < 5; ++u) {
-          const int i = tid + u * kStepThreads;
-          if (i < nchunk) v[g][u] = __ldcg(src + i);
+        for (int gg = 0; gg < 2; ++gg) {
+          const uint4* src = reinterpret_cast<const uint4*>(dgq_t + int64_t(half * 2 + gg) * gs);
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const int i = tid + u * kStepThreads;
+            if (i < nchunk) v[gg][u] = __ldcg(src + i);
+          }
         }
-      }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4* dst = Xs4 + int64_t(g) * 32 * chunks_per_row;
+        for (int gg = 0; gg < 2; ++gg) {
+          uint4* dst = Xs4 + int64_t(half * 2 + gg) * 32 * chunks_per_row;
 #pragma unroll
-        for (int u = 0; u < 5; ++u) {
-          const int i = tid + u * kStepThreads;
-          if (i < nchunk) dst[i] = v[g][u];
+          for (int u = 0; u < 5; ++u) {
+            const int i = tid + u * kStepThreads;
+            if (i < nchunk) dst[i] = v[gg][u];
+          }
         }
       }
     }
