@@ -51,12 +51,12 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
       L.gates = takef(N * 4 * H); L.hs = takef(N * H); L.cs = takef(N * H); L.hm = takef(N * Hp);
       L.cm = takef(N * H); L.dgates = takef(N * 4 * H); L.bsum = takef(4 * H); L.w_hh_t = takef(int64_t(H + 4) * 4 * Hp);
       L.wp = takef(int64_t(4 * H + 4) * Hp);
-      L.xb = L.wihb = L.dgb = L.hmb = L.hmq = L.dgq = nullptr;
+      L.xb = L.wihb = L.dgb = L.hmb = L.hmq = L.dgq = L.hq = nullptr;
       if (precision) {  // bf16 operand copies (2 bytes per element: take half the float count, rounded up)
         const int64_t in_l = (l == 0) ? In : H;
         L.xb = takef((N * ld16(in_l) + 1) / 2); L.wihb = takef((int64_t(4) * H * ld16(in_l) + 1) / 2);
         L.dgb = takef((N * ld16(4 * H) + 1) / 2); L.hmb = takef((N * ld16(H) + 1) / 2);
-        L.hmq = takef((N * mma_hq(H) + 1) / 2); L.dgq = takef((int64_t(2) * 4 * B * mma_hq(H) + 1) / 2);
+        L.hmq = takef((N * mma_hq(H) + 1) / 2); L.hq = takef(((N + B) * mma_hq(H) + 1) / 2); L.dgq = takef((int64_t(2) * 4 * B * mma_hq(H) + 1) / 2);
       }
     } else {
       L = LstmLayerWs();
@@ -923,6 +923,201 @@ __global__ void __launch_bounds__(kStepThreads) lstm_fwd_persistent_mma_kernel(P
   }
 }
 
+// ---- two stacked layers as ONE wavefront ------------------------------------------------------
+// Layer 1 at time t needs only layer 0's h at time t, so wave step s runs layer 0 at t = s and layer 1
+// at t = s-1 side by side: T1+1 grid barriers instead of 2*T1, the input projection of layer 1 rides
+// on the same tensor-core pass (its operand tile h0_{s-1} is the one layer 0's recurrence loads anyway),
+// and the hoisted layer-1 projection GEMM disappears.  Each CTA owns kStepUnits hidden units of BOTH
+// layers.  The done-mask is applied to the recurrent PRODUCT (a 0/1 row scale commutes with the GEMM),
+// so only the raw bf16 h tiles are exchanged; the masked copies (hmq) are still written for the
+// weight-gradient GEMMs.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+struct WaveFwdArgs {
+  const float* w_hh0; const float* w_ih1; const float* w_hh1; const float* bias1;
+  float* gates[2]; float* hs[2]; float* cs[2]; float* cm[2];
+  __nv_bfloat16* hq[2];    // raw h: [(T1+1)*B, Hq]; slot 0 = initial state, slot t+1 = h_t
+  __nv_bfloat16* hmq[2];   // masked recurrent inputs [T1*B, Hq] (slot 0 pre-initialised)
+  const float* nd; unsigned* counter;
+  int T1, B, H, Hq; unsigned nctas;
+};
+
+constexpr int kWaveK = 3;  // k-steps per warp, all 16 warps own a k-slice: ceil(ceil(H/16)/16) (H <= 768)
+
+__global__ void __launch_bounds__(kStepThreads) lstm2_fwd_wave_mma_kernel(WaveFwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_b[];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int H = a.H, Hq = a.Hq, B = a.B;
+  __nv_bfloat16* X0 = reinterpret_cast<__nv_bfloat16*>(smem_b);  // [32][Hq]  h0_{s-1}
+  __nv_bfloat16* X1 = X0 + 32 * Hq;                              // [32][Hq]  h1_{s-2}
+  typedef float PartT[2][16][33];
+  PartT* part = reinterpret_cast<PartT*>(smem_b + size_t(2) * 32 * Hq * 2);  // [16 warps][set][col][row]
+  __shared__ float act_s[2][4][kStepUnits][33];
+  __shared__ float nd_s[2][32];
+  const int j0 = blockIdx.x * kStepUnits;
+  const int rows = (B < 32) ? B : 32;
+  const int ksteps = (H + 15) / 16;
+  const int kper = (ksteps + 15) / 16;
+  const int ks0 = wrp * kper, ks1 = (ks0 + kper < ksteps) ? ks0 + kper : ksteps;
+  // B fragments of this CTA's 16 gate rows (o = gate*4 + unit) of the three weight matrices
+  uint32_t bf[3][kWaveK][2][2];
+  {
+    const float* wm[3] = {a.w_hh0, a.w_ih1, a.w_hh1};
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int s = 0; s < kWaveK; ++s)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int o = nt * 8 + (lane >> 2);
+          const int g = o >> 2, u = o & 3;
+          const float* wr = wm[m] + (int64_t(g) * H + j0 + u) * H;
+          const int k = (ks0 + s) * 16 + (lane & 3) * 2;
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (j0 + u < H && ks0 + s < ks1) {
+            if (k < H) v[0] = wr[k];
+            if (k + 1 < H) v[1] = wr[k + 1];
+            if (k + 8 < H) v[2] = wr[k + 8];
+            if (k + 9 < H) v[3] = wr[k + 9];
+          }
+          bf[m][s][nt][0] = pack_bf16(v[0], v[1]);
+          bf[m][s][nt][1] = pack_bf16(v[2], v[3]);
+        }
+  }
+  const int b = lane;
+  const int oq = wrp >> 2, ou = wrp & 3;           // activation role: gate column o = wrp of both layers
+  const bool colok = (lane < rows && j0 + ou < H);
+  const float bias1 = colok ? a.bias1[int64_t(oq) * H + j0 + ou] : 0.f;
+  const int ul = (wrp >> 2) & 1, uu = wrp & 3;     // update role: warps 0..3 layer 0, warps 4..7 layer 1
+  const bool updrole = (wrp < 8 && lane < rows && j0 + uu < H);
+  // per-role pointers picked once (dynamic indexing of the parameter arrays would go through local memory)
+  float* const cm_u = ul ? a.cm[1] : a.cm[0];
+  float* const cs_u = ul ? a.cs[1] : a.cs[0];
+  float* const hs_u = ul ? a.hs[1] : a.hs[0];
+  __nv_bfloat16* const hq_u = ul ? a.hq[1] : a.hq[0];
+  __nv_bfloat16* const hmq_u = ul ? a.hmq[1] : a.hmq[0];
+  const int chunks_per_row = Hq / 8;               // 16-byte chunks
+  const int nchunk = rows * chunks_per_row;
+  uint4* X04 = reinterpret_cast<uint4*>(X0);
+  uint4* X14 = reinterpret_cast<uint4*>(X1);
+  for (int s = 0; s <= a.T1; ++s) {
+    const bool act0 = (s < a.T1), act1 = (s >= 1);
+    if (tid == 0 && s > 0) grid_wait(a.counter, unsigned(s) * a.nctas);
+    __syncthreads();
+    {
+      const uint4* src0 = reinterpret_cast<const uint4*>(a.hq[0] + int64_t(s) * B * Hq);
+      const uint4* src1 = reinterpret_cast<const uint4*>(a.hq[1] + int64_t(s > 0 ? s - 1 : 0) * B * Hq);
+      // per-thread async copies (LDGSTS, L1 bypass): ten 16-byte chunks in flight without staging registers
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const int i = tid + u * kStepThreads;
+        if (i < nchunk) {
+          cp_async16(X04 + i, src0 + i);
+          if (act1) cp_async16(X14 + i, src1 + i);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (tid < 64) {
+      const int l = tid >> 5, r = tid & 31, t = s - l;
+      nd_s[l][r] = (r < rows && t >= 0 && t < a.T1) ? __ldg(a.nd + int64_t(t) * B + r) : 0.f;
+    }
+    float pre0 = 0.f, cm_in = 0.f, ndn_in = 0.f;
+    if (colok && act0) pre0 = a.gates[0][(int64_t(s) * B + b) * 4 * H + int64_t(oq) * H + j0 + ou];
+    const int tu = s - ul;                          // time step of this thread's update role
+    const bool upd = updrole && (ul ? act1 : act0);
+    if (upd) {
+      cm_in = cm_u[(int64_t(tu) * B + b) * H + j0 + uu];
+      if (tu < a.T1 - 1) ndn_in = __ldg(a.nd + int64_t(tu + 1) * B + b);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    {
+      float acc0[2][2][4], accI[2][2][4], acc1[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { acc0[mt][nt][e] = 0.f; accI[mt][nt][e] = 0.f; acc1[mt][nt][e] = 0.f; }
+#pragma unroll
+      for (int sk = 0; sk < kWaveK; ++sk) {
+        if (ks0 + sk < ks1) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t af[4];
+            const int off = (mt * 16 + (lane & 15)) * Hq + (ks0 + sk) * 16 + (lane >> 4) * 8;
+            ldmatrix_x4(af, X0 + off);
+            if (act0) {
+              mma_bf16_16816(acc0[mt][0], af, bf[0][sk][0][0], bf[0][sk][0][1]);
+              mma_bf16_16816(acc0[mt][1], af, bf[0][sk][1][0], bf[0][sk][1][1]);
+            }
+            if (act1) {
+              mma_bf16_16816(accI[mt][0], af, bf[1][sk][0][0], bf[1][sk][0][1]);
+              mma_bf16_16816(accI[mt][1], af, bf[1][sk][1][0], bf[1][sk][1][1]);
+              ldmatrix_x4(af, X1 + off);
+              mma_bf16_16816(acc1[mt][0], af, bf[2][sk][0][0], bf[2][sk][0][1]);
+              mma_bf16_16816(acc1[mt][1], af, bf[2][sk][1][0], bf[2][sk][1][1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r = mt * 16 + (lane >> 2);
+        const float m0a = nd_s[0][r], m0b = nd_s[0][r + 8], m1a = nd_s[1][r], m1b = nd_s[1][r + 8];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int c = nt * 8 + (lane & 3) * 2;
+          part[wrp][0][c][r] = acc0[mt][nt][0] * m0a; part[wrp][0][c + 1][r] = acc0[mt][nt][1] * m0a;
+          part[wrp][0][c][r + 8] = acc0[mt][nt][2] * m0b; part[wrp][0][c + 1][r + 8] = acc0[mt][nt][3] * m0b;
+          part[wrp][1][c][r] = accI[mt][nt][0] + acc1[mt][nt][0] * m1a;
+          part[wrp][1][c + 1][r] = accI[mt][nt][1] + acc1[mt][nt][1] * m1a;
+          part[wrp][1][c][r + 8] = accI[mt][nt][2] + acc1[mt][nt][2] * m1b;
+          part[wrp][1][c + 1][r + 8] = accI[mt][nt][3] + acc1[mt][nt][3] * m1b;
+        }
+      }
+    }
+    __syncthreads();
+    float gate0 = 0.f, gate1 = 0.f;
+    if (colok) {
+      float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) { d0 += part[w][0][wrp][lane]; d1 += part[w][1][wrp][lane]; }
+      if (act0) { const float pre = pre0 + d0; gate0 = (oq == 2) ? tanhf(pre) : sigmoidf_(pre); }
+      if (act1) { const float pre = bias1 + d1; gate1 = (oq == 2) ? tanhf(pre) : sigmoidf_(pre); }
+    }
+    act_s[0][oq][ou][lane] = gate0;
+    act_s[1][oq][ou][lane] = gate1;
+    __syncthreads();
+    float c_new = 0.f, h_new = 0.f;
+    if (upd) {
+      const float ig = act_s[ul][0][uu][lane], fg = act_s[ul][1][uu][lane], gg = act_s[ul][2][uu][lane],
+                  og = act_s[ul][3][uu][lane];
+      c_new = fg * cm_in + ig * gg;
+      h_new = og * tanhf(c_new);
+      hq_u[(int64_t(tu + 1) * B + b) * Hq + j0 + uu] = __float2bfloat16_rn(h_new);
+    }
+    __syncthreads();
+    if (tid == 0 && s < a.T1) red_release_add(a.counter, 1u);
+    if (colok) {
+      if (act0) a.gates[0][(int64_t(s) * B + b) * 4 * H + int64_t(oq) * H + j0 + ou] = gate0;
+      if (act1) a.gates[1][(int64_t(s - 1) * B + b) * 4 * H + int64_t(oq) * H + j0 + ou] = gate1;
+    }
+    if (upd) {
+      const int64_t o = (int64_t(tu) * B + b) * H + j0 + uu;
+      cs_u[o] = c_new;
+      hs_u[o] = h_new;
+      if (tu < a.T1 - 1) {
+        cm_u[o + int64_t(B) * H] = c_new * ndn_in;
+        hmq_u[(int64_t(tu + 1) * B + b) * Hq + j0 + uu] = __float2bfloat16_rn(h_new * ndn_in);
+      }
+    }
+  }
+}
+
 struct PersistBwdMmaArgs {
   const float* w_hh; const float* dy; const float* nd;
   const float* gates; const float* cs; const float* cm;
@@ -1110,16 +1305,19 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
 // hmq[0][b][:] = bf16(h0 * nd_0), zero padded; cm[0] = c0 * nd_0
 __global__ void lstm_init_state_q_kernel(const float* __restrict__ h0, const float* __restrict__ c0,
                                          const float* __restrict__ nd, __nv_bfloat16* __restrict__ hmq,
-                                         float* __restrict__ cm, int B, int H, int Hq) {
+                                         float* __restrict__ cm, int B, int H, int Hq,
+                                         __nv_bfloat16* __restrict__ hq_raw = nullptr) {
   const int64_t total = int64_t(B) * Hq;
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int b = int(i / Hq), k = int(i % Hq);
   if (k < H) {
     hmq[i] = __float2bfloat16_rn(h0[int64_t(b) * H + k] * nd[b]);
+    if (hq_raw) hq_raw[i] = __float2bfloat16_rn(h0[int64_t(b) * H + k]);
     cm[int64_t(b) * H + k] = c0[int64_t(b) * H + k] * nd[b];
   } else {
     hmq[i] = __float2bfloat16_rn(0.0f);
+    if (hq_raw) hq_raw[i] = __float2bfloat16_rn(0.0f);
   }
 }
 
@@ -1167,6 +1365,39 @@ static int lstm_fwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, floa
   return check_launch("lstm_fwd_persistent_mma_kernel");
 }
 
+static size_t g_fwd_wave_attr = 0;
+static size_t wave_fwd_smem(int Hq) { return size_t(2) * 32 * Hq * 2 + sizeof(float) * 16 * 2 * 16 * 33; }
+static bool wave_fwd_applicable(int64_t B, int H) {
+  const char* e = getenv("TB_LSTM_WAVE");
+  if (e && e[0] == '0') return false;
+  if (!mma_recurrence_applicable(B, H)) return false;
+  if (((H + 15) / 16 + 15) / 16 > kWaveK) return false;
+  dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
+  return coop_fit(lstm2_fwd_wave_mma_kernel, grid, wave_fwd_smem(mma_hq(H)), &g_fwd_wave_attr);
+}
+
+static int lstm2_fwd_wave(LstmWs& ws, const LstmParams& p, float* y, const float* notdone, int64_t T1, int64_t B, int H,
+                          cudaStream_t st) {
+  const int Hq = mma_hq(H);
+  const size_t smem = wave_fwd_smem(Hq);
+  dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
+  cudaError_t e = cudaMemsetAsync(ws.sync, 0, sizeof(unsigned), st);
+  TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
+  WaveFwdArgs a;
+  a.w_hh0 = p.w_hh[0]; a.w_ih1 = p.w_ih[1]; a.w_hh1 = p.w_hh[1]; a.bias1 = ws.layer[1].bsum;
+  for (int l = 0; l < 2; ++l) {
+    const LstmLayerWs& L = ws.layer[l];
+    a.gates[l] = L.gates; a.hs[l] = (l == 1) ? y : L.hs; a.cs[l] = L.cs; a.cm[l] = L.cm;
+    a.hq[l] = static_cast<__nv_bfloat16*>(L.hq); a.hmq[l] = static_cast<__nv_bfloat16*>(L.hmq);
+  }
+  a.nd = notdone; a.counter = ws.sync;
+  a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nctas = grid.x;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)lstm2_fwd_wave_mma_kernel, grid, dim3(kStepThreads), args, smem, st);
+  TB_REQUIRE(e == cudaSuccess, "lstm2_fwd_wave_mma_kernel: %s", cudaGetErrorString(e));
+  return check_launch("lstm2_fwd_wave_mma_kernel");
+}
+
 static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, const float* dy, const float* notdone,
                                    int64_t T1, int64_t B, int H, unsigned* counter, cudaStream_t st) {
   const int Hq = mma_hq(H);
@@ -1199,6 +1430,45 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
   const int64_t N = T1 * B;
   const float* xin = x;
   int in_dim = In;
+  if (precision && layers == 2 && wave_fwd_applicable(B, H)) {
+    // both layers in one wavefront kernel: only layer 0's input projection is hoisted
+    const int Hq = mma_hq(H);
+    for (int l = 0; l < 2; ++l) {
+      LstmLayerWs& L = ws.layer[l];
+      const int in_l = (l == 0) ? In : H;
+      const int64_t l16 = ld16(in_l);
+      add2_kernel<<<(4 * H + 255) / 256, 256, 0, st>>>(p.b_ih[l], p.b_hh[l], L.bsum, 4 * H);
+      TB_TRY(check_launch("add2_kernel"));
+      TB_TRY(pack_weights_bf16(p.w_ih[l], L.wihb, 4 * H, 1, in_l, l16, st));  // layer 1's is used by the backward
+      if (l == 0) {
+        TB_TRY(f32_to_bf16(x, L.xb, N, In, In, l16, st));
+        TcEpilogue te; te.C = L.gates; te.ldc = 4 * H; te.bias = L.bsum; te.tag = "lstm_xproj_fwd";
+        TB_TRY(gemm_tc_bf16(L.xb, L.wihb, N, 4 * H, In, l16, l16, te, st));
+      }
+      cudaError_t eq = cudaMemsetAsync(L.hmq, 0, size_t(N) * Hq * 2, st);
+      if (eq == cudaSuccess) eq = cudaMemsetAsync(L.hq, 0, size_t(N + B) * Hq * 2, st);
+      TB_REQUIRE(eq == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(eq));
+      lstm_init_state_q_kernel<<<(unsigned)((B * Hq + 255) / 256), 256, 0, st>>>(
+          h0 + int64_t(l) * B * H, c0 + int64_t(l) * B * H, notdone, static_cast<__nv_bfloat16*>(L.hmq), L.cm, int(B), H,
+          Hq, static_cast<__nv_bfloat16*>(L.hq));
+      TB_TRY(check_launch("lstm_init_state_q_kernel"));
+    }
+    {
+      ProfScope prof("lstm_recurrence_fwd", st);
+      TB_TRY(lstm2_fwd_wave(ws, p, y, notdone, T1, B, H, st));
+    }
+    TB_TRY(f32_to_bf16(ws.layer[0].hs, ws.layer[1].xb, N, H, H, ld16(H), st));  // layer 1's input, for its dW_ih GEMM
+    for (int l = 0; l < 2; ++l) {
+      const float* hs = (l == 1) ? y : ws.layer[0].hs;
+      cudaError_t e = cudaMemcpyAsync(hN + int64_t(l) * B * H, hs + (T1 - 1) * B * H, sizeof(float) * B * H,
+                                      cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cN + int64_t(l) * B * H, ws.layer[l].cs + (T1 - 1) * B * H, sizeof(float) * B * H,
+                            cudaMemcpyDeviceToDevice, st);
+      TB_REQUIRE(e == cudaSuccess, "lstm: state copy: %s", cudaGetErrorString(e));
+    }
+    return 0;
+  }
   for (int l = 0; l < layers; ++l) {
     LstmLayerWs& L = ws.layer[l];
     float* hs = (l == layers - 1) ? y : L.hs;
@@ -1216,7 +1486,8 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
                                                     nullptr, st)));
     }
     const int Hp = padded_h(H);
-    {
+    const bool use_mma = precision && mma_recurrence_applicable(B, H);
+    if (!use_mma) {  // operands of the fp32 recurrence kernels
       const int64_t tot = int64_t(4 * H + 4) * Hp;
       lstm_pack_whh_kernel<<<(unsigned)((tot + 255) / 256 > 1184 ? 1184 : (tot + 255) / 256), 256, 0, st>>>(p.w_hh[l], L.wp, H, Hp);
       TB_TRY(check_launch("lstm_pack_whh_kernel"));
@@ -1228,7 +1499,7 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
     }
     ProfScope prof("lstm_recurrence_fwd", st);
     int prc = -1;
-    if (precision && mma_recurrence_applicable(B, H)) {
+    if (use_mma) {
       const int Hq = mma_hq(H);
       cudaError_t eq = cudaMemsetAsync(L.hmq, 0, size_t(N) * Hq * 2, st);
       TB_REQUIRE(eq == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(eq));
@@ -1236,6 +1507,7 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
           h0 + int64_t(l) * B * H, c0 + int64_t(l) * B * H, notdone, static_cast<__nv_bfloat16*>(L.hmq), L.cm, int(B), H, Hq);
       TB_TRY(check_launch("lstm_init_state_q_kernel"));
       prc = lstm_fwd_persistent_mma(L, p.w_hh[l], hs, notdone, T1, B, H, ws.sync, st);
+      TB_REQUIRE(prc >= 0, "lstm: tensor-core recurrence kernel does not fit (B=%lld H=%d)", (long long)B, H);
     }
     if (prc < 0) prc = lstm_fwd_persistent(L, hs, notdone, T1, B, H, ws.sync, st);
     if (prc > 0) return prc;
@@ -1291,7 +1563,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     float* dxl = (l == 0) ? dx : ws.dx_mid;
     const int Hp = padded_h(H);
     const bool use_mma = precision && mma_recurrence_applicable(B, H);
-    {
+    if (!use_mma) {  // operands of the fp32 recurrence kernels
       const int64_t tot = int64_t(H + 4) * 4 * Hp;
       lstm_pack_whh_t_kernel<<<(unsigned)((tot + 255) / 256 > 1184 ? 1184 : (tot + 255) / 256), 256, 0, st>>>(p.w_hh[l], L.w_hh_t, H, Hp);
       TB_TRY(check_launch("lstm_pack_whh_t_kernel"));
@@ -1301,7 +1573,10 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     {
     ProfScope prof("lstm_recurrence_bwd", st);
     int prc = -1;
-    if (use_mma) prc = lstm_bwd_persistent_mma(L, p.w_hh[l], dyl, notdone, T1, B, H, ws.sync + 16, st);
+    if (use_mma) {
+      prc = lstm_bwd_persistent_mma(L, p.w_hh[l], dyl, notdone, T1, B, H, ws.sync + 16, st);
+      TB_REQUIRE(prc >= 0, "lstm: tensor-core recurrence kernel does not fit (B=%lld H=%d)", (long long)B, H);
+    }
     if (prc < 0) prc = lstm_bwd_persistent(L, ws, dyl, notdone, T1, B, H, ws.sync + 16, st);
     if (prc > 0) return prc;
     for (int64_t t = T1 - 1; prc < 0 && t >= 0; --t) {

@@ -27,6 +27,7 @@ struct LstmLayerWs {
   void* dgb;      // bf16 [T1*B, ld16(4H)]   gate gradients
   void* hmb;      // bf16 [T1*B, ld16(H)]    masked recurrent inputs
   void* hmq;      // bf16 [T1*B, Hq]         masked recurrent inputs written by the tensor-core recurrence (Hq = mma_hq(H))
+  void* hq;       // bf16 [(T1+1)*B, Hq]     raw h (slot 0 = initial state) exchanged by the two-layer wavefront kernel
   void* dgq;      // bf16 [2][4, B, Hq]      this step's gate gradients for the tensor-core backward recurrence
   float* wp;      // [4H+4, Hp]  W_hh with rows zero-padded to Hp floats (16-byte multiples for bulk copies)
   float* dgates;  // [T1*B, 4H]  backward: d pre-activations
