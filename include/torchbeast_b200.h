@@ -139,10 +139,8 @@ int tb_atarinet_forward(const uint8_t* frame, const float* reward, const float* 
                         float* cN, void* stream);
 /* Backward of the above (replaces the autograd graph of total_loss.backward(), monobeast.py:290):
  * grad_logits [T1,B,A], grad_baseline [T1,B] -> grads (flat, parameter layout, overwritten).
- * Must follow a tb_atarinet_forward on the same workspace, parameters and `frame` (the same device
- * buffer, unmodified: the bf16 backend gathers the conv1 weight gradient straight from the frames
- * instead of keeping a 7x larger patch matrix).                                                */
-int tb_atarinet_backward(const uint8_t* frame, const float* grad_logits, const float* grad_baseline, const float* notdone,
+ * Must follow a tb_atarinet_forward on the same workspace and parameters.                    */
+int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
                          const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
                          int precision, void* workspace, float* grads, void* stream);
 

@@ -167,8 +167,10 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
     te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act1b); te.ldc16 = G::C1; te.bias = P + pp.conv1_b;
     te.scale = 1.0f / 255.0f; te.relu = 1; te.tag = "conv1_fwd";
     if (conv_u8_implicit_applicable(G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, G::C1)) {
-      // implicit GEMM: producer warps gather the patches from the uint8 frames into the UMMA smem layout
-      TB_TRY(conv_u8_fwd_implicit(frame, w.w1b, N, G::H0, G::W0, G::S1, te, st));
+      // implicit GEMM: frames -> bf16 image once (kept in col1b for the backward), producer warps gather the
+      // patches from it into the UMMA smem layout
+      TB_TRY(frames_u8_to_bf16(frame, w.col1b, N * G::C0 * G::H0 * G::W0, st));
+      TB_TRY(conv_u8_fwd_implicit(w.col1b, w.w1b, N, G::H0, G::W0, G::S1, te, st));
     } else {
       TB_TRY(im2col_u8_nchw_bf16(frame, w.col1b, N, G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, st));
       TB_TRY(gemm_tc_bf16(w.col1b, w.w1b, M1, G::C1, G::KD1, G::KD1, G::KD1, te, st));
@@ -267,8 +269,8 @@ static int tc_wgrad(const void* dYb, int64_t ldy, const void* Xb, int64_t ldx, f
   return gemm_tc_bf16_ex(dYb, Xb, nout, kin, rows, ldy, ldx, true, true, te, tc_splits(nout, kin, rows), w.splitk, st);
 }
 
-static int atarinet_backward_trunk_bf16(const uint8_t* frame, const float* P, float* G_, const AtariParams& pp, AtariWs& w,
-                                        int64_t N, cudaStream_t st) {
+static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariParams& pp, AtariWs& w, int64_t N,
+                                        cudaStream_t st) {
   using G = AtariGeom;
   const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
   // fc: ReLU mask (fp32, in place), bias grad, bf16 copy of dY
@@ -297,7 +299,8 @@ static int atarinet_backward_trunk_bf16(const uint8_t* frame, const float* P, fl
   TB_TRY(col2im_bf16_nhwc(w.dcol2b, w.act1b, w.dact1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
   // conv1: the patch matrix holds raw pixel values, so the weight gradient carries the 1/255
   if (conv_u8_implicit_applicable(G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, G::C1)) {
-    TB_TRY(conv_u8_wgrad_implicit(w.dact1b, frame, N, G::H0, G::W0, G::S1, G_ + pp.conv1_w, 1.0f / 255.0f, w.splitk,
+    // w.col1b holds the bf16 frame image the forward left there (not a patch matrix)
+    TB_TRY(conv_u8_wgrad_implicit(w.dact1b, w.col1b, N, G::H0, G::W0, G::S1, G_ + pp.conv1_w, 1.0f / 255.0f, w.splitk,
                                   kSplitKScratchFloats, "conv1_wgrad", st));
   } else {
     TB_TRY(tc_wgrad(w.dact1b, G::C1, w.col1b, G::KD1, G_ + pp.conv1_w, M1, G::C1, G::KD1, 1, 1, 1.0f / 255.0f, w, st,
@@ -307,7 +310,7 @@ static int atarinet_backward_trunk_bf16(const uint8_t* frame, const float* P, fl
   return 0;
 }
 
-static int atarinet_backward(const uint8_t* frame, const float* grad_logits, const float* grad_baseline, const float* notdone,
+static int atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
                              const float* P, int64_t T1, int64_t B, int A, int use_lstm, int precision,
                              void* workspace, float* G_, cudaStream_t st) {
   using G = AtariGeom;
@@ -338,7 +341,7 @@ static int atarinet_backward(const uint8_t* frame, const float* grad_logits, con
     TB_TRY(lstm_backward(w.dcore_out, w.core_in, notdone, lp, lg, T1, B, pp.core, pp.core, 2, w.lstm, w.dcore_in,
                          w.splitk, w.colsum_scratch, precision, st));
   }
-  if (precision) return atarinet_backward_trunk_bf16(frame, P, G_, pp, w, N, st);
+  if (precision) return atarinet_backward_trunk_bf16(P, G_, pp, w, N, st);
   // fc: ReLU mask on the first 512 columns, wgrad (un-packed into [o, c, (h,w)]), bias, dgrad (+ReLU mask of act3)
   TB_TRY(relu_mask_inplace(w.dcore_in, w.core_in, N, G::FC_OUT, pp.core, pp.core, st));
   TB_TRY(wgrad(w.dcore_in, pp.core, w.act3, false, G::FC_IN, G_ + pp.fc_w, N, G::FC_OUT, G::FC_IN, G::H3 * G::W3,
@@ -398,13 +401,13 @@ int tb_atarinet_forward(const uint8_t* frame, const float* reward, const float* 
                           workspace, policy_logits, baseline, hN, cN, (cudaStream_t)stream);
 }
 
-int tb_atarinet_backward(const uint8_t* frame, const float* grad_logits, const float* grad_baseline, const float* notdone,
+int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
                          const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm, int precision,
                          void* workspace, float* grads, void* stream) {
   TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "atarinet_backward: bad sizes");
-  TB_REQUIRE(frame && grad_logits && grad_baseline && params && workspace && grads, "atarinet_backward: null pointer");
+  TB_REQUIRE(grad_logits && grad_baseline && params && workspace && grads, "atarinet_backward: null pointer");
   TB_REQUIRE(!use_lstm || notdone, "atarinet_backward: LSTM needs notdone");
-  return atarinet_backward(frame, grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm, precision, workspace,
+  return atarinet_backward(grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm, precision, workspace,
                            grads, (cudaStream_t)stream);
 }
 

@@ -154,7 +154,6 @@ class _AtariNetFunction(torch.autograd.Function):
         logits, baseline, hN, cN = module._launch_forward(frame, reward, notdone, last_action, h0, c0)
         ctx.module = module
         ctx.notdone = notdone
-        ctx.frame = frame.contiguous()  # the backward gathers conv1's weight gradient from the frames
         ctx.shape = frame.shape[:2]
         ctx.mark_non_differentiable(hN, cN)
         return logits, baseline, hN, cN
@@ -168,7 +167,7 @@ class _AtariNetFunction(torch.autograd.Function):
         if g_baseline is None:
             g_baseline = torch.zeros(T1, B, device=module._flat.device)
         grads = torch.empty_like(module._flat)
-        module._launch_backward(ctx.frame, g_logits.contiguous(), g_baseline.contiguous(), ctx.notdone, grads)
+        module._launch_backward(g_logits.contiguous(), g_baseline.contiguous(), ctx.notdone, grads)
         outs = tuple(grads[off:off + n].view(shape) for _, off, n, shape in module._views)
         return (None,) * 7 + outs
 
@@ -250,14 +249,13 @@ class AtariNet(FlatParamModule):
             "tb_atarinet_forward")
         return logits, baseline, hN, cN
 
-    def _launch_backward(self, frame, g_logits, g_baseline, notdone, grads_out):
+    def _launch_backward(self, g_logits, g_baseline, notdone, grads_out):
         T1, B = g_baseline.shape
-        assert frame.is_contiguous() and frame.shape[:2] == (T1, B)
         ws = self._workspace(T1, B)
         p = _lib.ptr
         _lib.check(
             _lib.lib().tb_atarinet_backward(
-                p(frame), p(g_logits), p(g_baseline), p(notdone) if self.use_lstm else None, p(self._flat), T1, B,
+                p(g_logits), p(g_baseline), p(notdone) if self.use_lstm else None, p(self._flat), T1, B,
                 self.num_actions, int(self.use_lstm), self.PRECISIONS[self.precision], p(ws), p(grads_out),
                 _lib.stream_ptr()),
             "tb_atarinet_backward")
@@ -275,14 +273,13 @@ class AtariNet(FlatParamModule):
         logits, baseline, hN, cN = self._launch_forward(
             inputs["frame"], inputs["reward"], notdone, inputs["last_action"], h0, c0)
         self._saved_notdone = notdone
-        self._saved_frame = inputs["frame"].contiguous()
         return LearnerOutputs(logits, baseline, (hN, cN) if self.use_lstm else tuple())
 
     @torch.no_grad()
     def learner_backward(self, grad_logits, grad_baseline):
         """Writes d loss / d params into flat_grad (and points every .grad at its slice)."""
         fg = self.attach_grads()
-        self._launch_backward(self._saved_frame, grad_logits, grad_baseline, self._saved_notdone, fg)
+        self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg)
         return fg
 
     # ---- reference-compatible forward ---------------------------------------------------------
