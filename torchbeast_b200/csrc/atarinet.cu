@@ -175,14 +175,26 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
       TB_TRY(im2col_u8_nchw_bf16(frame, w.col1b, N, G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, st));
       TB_TRY(gemm_tc_bf16(w.col1b, w.w1b, M1, G::C1, G::KD1, G::KD1, G::KD1, te, st));
     }
-    TB_TRY(im2col_bf16_nhwc(w.act1b, w.col2b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
+    // conv2 / conv3: implicit GEMM - TMA gathers the patches from the NHWC activation (rank-4 map with
+    // overlapping dimensions); the patch matrices col2b / col3b are only materialised for the backward
+    const bool impl2 = conv_tc_implicit_applicable(G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2);
+    const bool impl3 = conv_tc_implicit_applicable(G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3);
     te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act2b); te.ldc16 = G::C2; te.bias = P + pp.conv2_b;
     te.relu = 1; te.tag = "conv2_fwd";
-    TB_TRY(gemm_tc_bf16(w.col2b, w.w2b, M2, G::C2, G::KD2, G::KD2, G::KD2, te, st));
-    TB_TRY(im2col_bf16_nhwc(w.act2b, w.col3b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
+    if (impl2) {
+      TB_TRY(conv_tc_fwd_implicit(w.act1b, w.w2b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2, te, st));
+    } else {
+      TB_TRY(im2col_bf16_nhwc(w.act1b, w.col2b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
+      TB_TRY(gemm_tc_bf16(w.col2b, w.w2b, M2, G::C2, G::KD2, G::KD2, G::KD2, te, st));
+    }
     te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act3b); te.ldc16 = G::C3; te.bias = P + pp.conv3_b;
     te.relu = 1; te.tag = "conv3_fwd";
-    TB_TRY(gemm_tc_bf16(w.col3b, w.w3b, M3, G::C3, G::KD3, G::KD3, G::KD3, te, st));
+    if (impl3) {
+      TB_TRY(conv_tc_fwd_implicit(w.act2b, w.w3b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3, te, st));
+    } else {
+      TB_TRY(im2col_bf16_nhwc(w.act2b, w.col3b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
+      TB_TRY(gemm_tc_bf16(w.col3b, w.w3b, M3, G::C3, G::KD3, G::KD3, G::KD3, te, st));
+    }
     te = TcEpilogue(); te.C = w.core_in; te.ldc = pp.core; te.bias = P + pp.fc_b; te.relu = 1; te.tag = "fc_fwd";
     TB_TRY(gemm_tc_bf16(w.act3b, w.wfcb, N, G::FC_OUT, G::FC_IN, G::FC_IN, G::FC_IN, te, st));
   } else {
@@ -283,16 +295,26 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
   te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dact3b); te.ldc16 = G::FC_IN;
   te.mask16 = static_cast<const __nv_bfloat16*>(w.act3b); te.ldmask = G::FC_IN; te.tag = "fc_dgrad";
   TB_TRY(gemm_tc_bf16_ex(w.dfcb, w.wfcb, N, G::FC_IN, G::FC_OUT, G::FC_OUT, G::FC_IN, false, true, te, 1, nullptr, st));
-  // conv3 (dact3b viewed as [M3, 64])
-  TB_TRY(tc_wgrad(w.dact3b, G::C3, w.col3b, G::KD3, G_ + pp.conv3_w, M3, G::C3, G::KD3, G::K3 * G::K3, G::C2, 1.0f, w, st,
-                  "conv3_wgrad"));
+  // conv3 (dact3b viewed as [M3, 64]); the implicit forward did not leave a patch matrix behind
+  if (conv_tc_implicit_applicable(G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3)) {
+    TB_TRY(conv_tc_wgrad_implicit(w.dact3b, w.act2b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3, G_ + pp.conv3_w,
+                                  G::K3 * G::K3, G::C2, 1.0f, w.splitk, kSplitKScratchFloats, "conv3_wgrad", st));
+  } else {
+    TB_TRY(tc_wgrad(w.dact3b, G::C3, w.col3b, G::KD3, G_ + pp.conv3_w, M3, G::C3, G::KD3, G::K3 * G::K3, G::C2, 1.0f, w, st,
+                    "conv3_wgrad"));
+  }
   TB_TRY(colsum_bf16(w.dact3b, G_ + pp.conv3_b, M3, G::C3, G::C3, w.colsum_scratch, st));
   te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol3b); te.ldc16 = G::KD3; te.tag = "conv3_dgrad";
   TB_TRY(gemm_tc_bf16_ex(w.dact3b, w.w3b, M3, G::KD3, G::C3, G::C3, G::KD3, false, true, te, 1, nullptr, st));
   TB_TRY(col2im_bf16_nhwc(w.dcol3b, w.act2b, w.dact2b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
   // conv2
-  TB_TRY(tc_wgrad(w.dact2b, G::C2, w.col2b, G::KD2, G_ + pp.conv2_w, M2, G::C2, G::KD2, G::K2 * G::K2, G::C1, 1.0f, w, st,
-                  "conv2_wgrad"));
+  if (conv_tc_implicit_applicable(G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2)) {
+    TB_TRY(conv_tc_wgrad_implicit(w.dact2b, w.act1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2, G_ + pp.conv2_w,
+                                  G::K2 * G::K2, G::C1, 1.0f, w.splitk, kSplitKScratchFloats, "conv2_wgrad", st));
+  } else {
+    TB_TRY(tc_wgrad(w.dact2b, G::C2, w.col2b, G::KD2, G_ + pp.conv2_w, M2, G::C2, G::KD2, G::K2 * G::K2, G::C1, 1.0f, w, st,
+                    "conv2_wgrad"));
+  }
   TB_TRY(colsum_bf16(w.dact2b, G_ + pp.conv2_b, M2, G::C2, G::C2, w.colsum_scratch, st));
   te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol2b); te.ldc16 = G::KD2; te.tag = "conv2_dgrad";
   TB_TRY(gemm_tc_bf16_ex(w.dact2b, w.w2b, M2, G::KD2, G::C2, G::C2, G::KD2, false, true, te, 1, nullptr, st));

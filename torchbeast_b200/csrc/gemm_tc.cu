@@ -39,10 +39,22 @@ namespace {
 // EPI: 0 = store the accumulator as is; 1 = scale / bias / ReLU; 2 = + ReLU-mask / residual loads.
 // (compile-time so the common epilogues carry no predicated per-element loads - ncu showed the generic
 //  epilogue, not the MMA pipe, bounding the K=64 dgrad products)
-template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI>
+// IMPL (implicit-GEMM convolution, forward): the A operand is not a matrix in memory but the NHWC activation
+// itself, addressed through a rank-4 tensor map {flat frame element, ox, oy, frame} whose dimensions overlap:
+// M tile t = the `rows` = OW*OH*fpt patches of frames [t*fpt, (t+1)*fpt), k-block kb = 64 consecutive
+// (kw, c) elements of kernel row kb / kbw starting at element e0 of the frame - one TMA box per stage lands
+// as [patch][64 k] rows in the canonical SWIZZLE_128B layout, so no patch matrix is ever written.
+struct ImplicitConv {
+  int rows = 0;       // valid patch rows per M tile (<= 128)
+  int fpt = 1;        // frames per tile
+  int kbw = 1;        // k-blocks per kernel row = KW*C/64
+  int row_elems = 0;  // W*C
+};
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI, bool IMPL = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep, int M,
-               int N, int K, float* partial, int tiles_m, int tiles_n, int splits) {
+               int N, int K, float* partial, int tiles_m, int tiles_n, int splits, ImplicitConv ic = ImplicitConv()) {
   constexpr uint32_t B_BYTES = BLOCK_N * kBlockK * 2;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulator buffers (power of two)
   extern __shared__ uint8_t smem_raw[];
@@ -95,8 +107,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < num_kb; ++i) {
           const int kc = (kb0 + i) * kBlockK;
           mbar_wait(empty(stage), phase ^ 1);
-          mbar_expect_tx(full(stage), kABytes + B_BYTES);
-          if (A_MN) {  // two 64(k) x 64(m) boxes
+          mbar_expect_tx(full(stage), (IMPL ? uint32_t(ic.rows) * 128u : kABytes) + B_BYTES);
+          if (IMPL) {
+            const int kb = kb0 + i;
+            tma_load_4d(sA + stage * kABytes, &tmA, full(stage), (kb / ic.kbw) * ic.row_elems + (kb % ic.kbw) * kBlockK, 0, 0,
+                        (m0 / kBlockM) * ic.fpt);
+          } else if (A_MN) {  // two 64(k) x 64(m) boxes
             tma_load_2d(sA + stage * kABytes, &tmA, full(stage), m0, kc);
             tma_load_2d(sA + stage * kABytes + 8192, &tmA, full(stage), m0 + 64, kc);
           } else {
@@ -151,7 +167,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int ab = it & 1;
       mbar_wait(tmem_full(ab), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int64_t r = int64_t(m0) + quarter * 32 + lane;
+      const int rl = quarter * 32 + lane;
+      const int64_t r = IMPL ? int64_t(m0 / kBlockM) * ic.rows + rl : int64_t(m0) + rl;
+      const bool rvalid = r < M && (!IMPL || rl < ic.rows);
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
@@ -161,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) v[j] = 0u;  // nothing was accumulated (empty split)
         }
         if (partial) {  // split-K: raw partial tile [z][M][N]; splitk_reduce_kernel applies the epilogue
-          if (r < M) {
+          if (rvalid) {
             float* pz = partial + (int64_t(z) * M + r) * N + n0 + c0;
             if (n0 + c0 + 32 <= N && (N & 3) == 0) {
 #pragma unroll
@@ -175,7 +193,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           continue;
         }
-        if (r < M) {
+        if (rvalid) {
           const int nbase = n0 + c0;
           float o[32];
           const bool full_cols = nbase + 32 <= N;
@@ -293,7 +311,260 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int
   return launch_s<BLOCK_N, A_MN, B_MN, 4>(a, b, ep, M, N, K, splits, partial, stream);
 }
 
+
+// Implicit-GEMM convolution weight gradient: dW[o, k] = sum_patches dY[patch, o] * patch[patch, k] with the
+// patches read straight from the NHWC activation (same overlapping-dimension tensor map as the forward).
+// One stage = the `rows` patches of `fpt` whole frames: A = one 64(o) x rows box of dY (MN-major), B = two
+// 64(k) x rows boxes of patches (MN-major: the k-th 64-wide group is k-block n0/64 + j of the kernel window).
+// rows is padded to a multiple of 16 (the UMMA K step) with shared-memory rows that are zeroed once and
+// never written by TMA, so the padding contributes exact zeros.  CTAs split the frames; raw fp32 partial
+// tiles go to `partial` [z][O][K] and splitk_reduce_kernel folds them in a fixed order.
+struct ImplicitWgrad {
+  int rows = 0, rows_pad = 0, fpt = 1, kbw = 1, row_elems = 0;
+  int stages_total = 0;  // ceil(frames / fpt)
+  int per = 0;           // stages per split
+};
+
+template <int kSt>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_implicit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int O, int Kdim,
+                           float* __restrict__ partial, int tiles_n, ImplicitWgrad iw) {
+  constexpr int BLOCK_N = 128;
+  constexpr uint32_t TMEM_COLS = BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
+  const uint32_t group = uint32_t(iw.rows_pad) * 128u;  // one 64-wide group: rows_pad x 128 B (multiple of 1024)
+  const uint32_t stage_bytes = 3u * group;              // [dY group][patch group 0][patch group 1]
+  const uint32_t bars = base + kSt * stage_bytes;       // full[kSt], empty[kSt], tmem_full
+  const uint32_t tmem_slot = bars + 8 * (2 * kSt + 1);
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (kSt + s); };
+  const uint32_t tmem_full = bars + 8u * (2 * kSt);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockIdx.x % tiles_n, z = blockIdx.x / tiles_n;
+  const int n0 = nt * BLOCK_N;
+  const int s0 = z * iw.per;
+  const int s1 = (s0 + iw.per < iw.stages_total) ? s0 + iw.per : iw.stages_total;
+  const int num = s1 > s0 ? s1 - s0 : 0;
+
+  // zero the ring once: the padding rows [rows, rows_pad) of every group must read as exact zeros
+  for (uint32_t off = threadIdx.x * 16u; off < kSt * stage_bytes; off += kThreads * 16u)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(base + off), "r"(0u) : "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kSt; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int kbA = n0 / kBlockK, kbB = kbA + 1;
+      const int eA = (kbA / iw.kbw) * iw.row_elems + (kbA % iw.kbw) * kBlockK;
+      const int eB = (kbB / iw.kbw) * iw.row_elems + (kbB % iw.kbw) * kBlockK;
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < num; ++i) {
+        const int f0 = (s0 + i) * iw.fpt;
+        mbar_wait(empty(stage), phase ^ 1);
+        mbar_expect_tx(full(stage), 3u * uint32_t(iw.rows) * 128u);
+        const uint32_t st = base + stage * stage_bytes;
+        tma_load_2d(st, &tmA, full(stage), 0, f0 * (iw.rows / iw.fpt));
+        tma_load_4d(st + group, &tmB, full(stage), eA, 0, 0, f0);
+        tma_load_4d(st + 2 * group, &tmB, full(stage), eB, 0, 0, f0);
+        if (++stage == kSt) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && num > 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(BLOCK_N >> 3) << 17) |
+                                 (uint32_t(kBlockM >> 4) << 24);
+      const int ksteps = iw.rows_pad / 16;
+      int stage = 0; uint32_t phase = 0;
+      for (int i = 0; i < num; ++i) {
+        mbar_wait(full(stage), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = base + stage * stage_bytes;
+        for (int k = 0; k < ksteps; ++k)  // A's second 64-wide group aliases patch group 0: accumulator rows >= 64 are junk
+          umma_bf16(tmem_base, make_smem_desc_mn_lbo(st + k * 2048, group), make_smem_desc_mn_lbo(st + group + k * 2048, group),
+                    idesc, (i | k) != 0 ? 1u : 0u);
+        umma_commit(empty(stage));
+        if (++stage == kSt) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;  // output channel
+    if (quarter < 2) {                   // TMEM lanes 0..63
+      if (num > 0) {
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        if (num > 0) {
+          tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if (r < O) {
+          float* pz = partial + (int64_t(z) * O + r) * Kdim + n0 + c0;
+          if (n0 + c0 + 32 <= Kdim && (Kdim & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(pz + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c0 + j < Kdim) pz[j] = __uint_as_float(v[j]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int BLOCK_N>
+int launch_conv_fwd(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K,
+                    int64_t tiles_m, const ImplicitConv& ic, cudaStream_t stream) {
+  constexpr int kSt = 4;
+  constexpr size_t smem = 1024 + kSt * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kSt + 4) + 16;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, false, false, kSt, 1, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const int64_t tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t total = tiles_m * tiles_n;
+  int per_sm = int((220 * 1024) / smem);
+  if (per_sm > 512 / (2 * BLOCK_N)) per_sm = 512 / (2 * BLOCK_N);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 3) per_sm = 3;
+  int64_t grid = int64_t(kNumSMsB200) * per_sm;
+  if (grid > total) grid = total;
+  gemm_tc_kernel<BLOCK_N, false, false, kSt, 1, true><<<(unsigned)grid, kThreads, smem, stream>>>(
+      a, b, ep, int(M), int(N), int(K), nullptr, int(tiles_m), int(tiles_n), 1, ic);
+  return check_launch("gemm_tc_kernel(implicit conv)");
+}
+
 }  // namespace
+
+bool conv_tc_implicit_applicable(int H, int W, int C, int KH, int KW, int S, int O) {
+  const char* e = getenv("TB_CONV_IMPLICIT");
+  if (e && e[0] == '0') return false;
+  if (H < KH || W < KW || S < 1) return false;
+  const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
+  return (KW * C) % kBlockK == 0 && (S * C * 2) % 16 == 0 && (C % 8) == 0 && OW * OH <= kBlockM && OW <= 256 && OH <= 256 &&
+         (O == 32 || O == 64 || O % 128 == 0 || O <= 128);
+}
+
+int conv_tc_fwd_implicit(const void* act_nhwc_bf16, const void* w_packed_bf16, int64_t Nf, int H, int W, int C, int KH, int KW,
+                         int S, int O, const TcEpilogue& ep, cudaStream_t stream) {
+  TB_REQUIRE(act_nhwc_bf16 && w_packed_bf16 && (ep.C || ep.C16), "conv_tc_fwd_implicit: null pointer");
+  TB_REQUIRE(conv_tc_implicit_applicable(H, W, C, KH, KW, S, O), "conv_tc_fwd_implicit: unsupported shape");
+  if (Nf == 0) return 0;
+  ProfScope prof(ep.tag, stream);
+  const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
+  ImplicitConv ic;
+  ic.fpt = kBlockM / (OW * OH);
+  if (ic.fpt > 256) ic.fpt = 256;
+  ic.rows = OW * OH * ic.fpt;
+  ic.kbw = KW * C / kBlockK;
+  ic.row_elems = W * C;
+  const int64_t K = int64_t(KH) * KW * C, M = Nf * OH * OW;
+  const int64_t tiles_m = (Nf + ic.fpt - 1) / ic.fpt;
+  const uint64_t dims[4] = {uint64_t(H) * W * C, uint64_t(OW), uint64_t(OH), uint64_t(Nf)};
+  const uint64_t strides[3] = {uint64_t(S) * C * 2, uint64_t(S) * W * C * 2, uint64_t(H) * W * C * 2};
+  const uint32_t box[4] = {uint32_t(kBlockK), uint32_t(OW), uint32_t(OH), uint32_t(ic.fpt)};
+  CUtensorMap ma, mb;
+  int rc = make_map_nd(&ma, act_nhwc_bf16, 4, dims, strides, box);
+  if (rc) return rc;
+  const int bn = (O <= 32) ? 32 : (O <= 64 ? 64 : 128);
+  rc = make_map(&mb, w_packed_bf16, O, K, K, bn);
+  if (rc) return rc;
+  if (bn == 32) return launch_conv_fwd<32>(ma, mb, ep, M, O, K, tiles_m, ic, stream);
+  if (bn == 64) return launch_conv_fwd<64>(ma, mb, ep, M, O, K, tiles_m, ic, stream);
+  return launch_conv_fwd<128>(ma, mb, ep, M, O, K, tiles_m, ic, stream);
+}
+
+int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64_t Nf, int H, int W, int C, int KH, int KW, int S,
+                           int O, float* dW, int permP, int permQ, float scale, float* partial, int64_t partial_floats,
+                           const char* tag, cudaStream_t stream) {
+  TB_REQUIRE(dy_bf16 && act_nhwc_bf16 && dW && partial, "conv_tc_wgrad_implicit: null pointer");
+  TB_REQUIRE(conv_tc_implicit_applicable(H, W, C, KH, KW, S, O) && O <= 64 && O % 8 == 0,
+             "conv_tc_wgrad_implicit: unsupported shape");
+  if (Nf == 0) return 0;
+  ProfScope prof(tag, stream);
+  const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
+  const int64_t K = int64_t(KH) * KW * C;
+  ImplicitWgrad iw;
+  iw.fpt = kBlockM / (OW * OH);
+  if (iw.fpt > 256) iw.fpt = 256;
+  iw.rows = OW * OH * iw.fpt;
+  iw.rows_pad = (iw.rows + 15) & ~15;
+  if (iw.rows_pad % 8) iw.rows_pad = (iw.rows_pad + 7) & ~7;
+  iw.kbw = KW * C / kBlockK;
+  iw.row_elems = W * C;
+  iw.stages_total = int((Nf + iw.fpt - 1) / iw.fpt);
+  const int tiles_n = int((K + 127) / 128);
+  // the second 64-wide group of the last n tile may start past K: its kernel-row offset must still be inside the frame
+  {
+    const int kb_last = tiles_n * 2 - 1;
+    const int64_t e_last = int64_t(kb_last / iw.kbw) * iw.row_elems + int64_t(kb_last % iw.kbw) * kBlockK;
+    TB_REQUIRE(e_last + kBlockK <= int64_t(H) * W * C, "conv_tc_wgrad_implicit: window tail outside the frame");
+  }
+  int64_t splits = kNumSMsB200 / tiles_n;
+  if (splits > iw.stages_total) splits = iw.stages_total;
+  if (splits * O * K > partial_floats) splits = partial_floats / (int64_t(O) * K);
+  TB_REQUIRE(splits >= 1, "conv_tc_wgrad_implicit: partial buffer too small");
+  iw.per = int((iw.stages_total + splits - 1) / splits);
+  splits = (iw.stages_total + iw.per - 1) / iw.per;
+  CUtensorMap ma, mb;
+  // dY [patches, O]: MN-major box of 64 channels x `rows` patches
+  int rc = make_map(&ma, dy_bf16, Nf * OH * OW, O, O, iw.rows, 64);
+  if (rc) return rc;
+  const uint64_t dims[4] = {uint64_t(H) * W * C, uint64_t(OW), uint64_t(OH), uint64_t(Nf)};
+  const uint64_t strides[3] = {uint64_t(S) * C * 2, uint64_t(S) * W * C * 2, uint64_t(H) * W * C * 2};
+  const uint32_t box[4] = {uint32_t(kBlockK), uint32_t(OW), uint32_t(OH), uint32_t(iw.fpt)};
+  rc = make_map_nd(&mb, act_nhwc_bf16, 4, dims, strides, box);
+  if (rc) return rc;
+  constexpr int kSt = 4;
+  const size_t smem = 1024 + size_t(kSt) * 3 * iw.rows_pad * 128 + 8 * (2 * kSt + 1) + 16;
+  TB_REQUIRE(smem <= 227 * 1024, "conv_tc_wgrad_implicit: stage too large");
+  static size_t attr = 0;
+  if (attr < smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_implicit_kernel<kSt>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    TB_REQUIRE(e == cudaSuccess, "conv_tc_wgrad_implicit: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = smem;
+  }
+  conv_wgrad_implicit_kernel<kSt><<<(unsigned)(splits * tiles_n), kThreads, smem, stream>>>(ma, mb, O, int(K), partial, tiles_n, iw);
+  rc = check_launch("conv_wgrad_implicit_kernel");
+  if (rc) return rc;
+  GemmEpilogue rep;
+  rep.permP = permP; rep.permQ = permQ; rep.scale = scale;
+  const int64_t total = int64_t(O) * K;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;
+  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, dW, O, K, K, int(splits), rep);
+  return check_launch("splitk_reduce_kernel");
+}
 
 int gemm_tc_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                  const TcEpilogue& ep, cudaStream_t stream) {

@@ -30,6 +30,19 @@ int gemm_tc_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, 
 int gemm_tc_bf16_ex(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, bool a_mn,
                     bool b_mn, const TcEpilogue& ep, int splits, float* partial, cudaStream_t stream);
 
+// Implicit-GEMM convolution forward over a bf16 NHWC activation [Nf, H, W, C] (no patch matrix): out[Nf*OH*OW, O] =
+// epilogue(patches . Wp^T) with Wp [O, KH*KW*C] packed (kh, kw, c).  The activation is read through a rank-4
+// tensor map with overlapping dimensions.  Requires conv_tc_implicit_applicable().
+bool conv_tc_implicit_applicable(int H, int W, int C, int KH, int KW, int S, int O);
+int conv_tc_fwd_implicit(const void* act_nhwc_bf16, const void* w_packed_bf16, int64_t Nf, int H, int W, int C, int KH, int KW,
+                         int S, int O, const TcEpilogue& ep, cudaStream_t stream);
+
+// Weight gradient of the same convolution, patches again read through TMA: dW (fp32, [O, KH*KW*C] un-packed by
+// permP/permQ like the split-K reduce of gemm_tc_bf16_ex) = scale * dY^T . patches; dy_bf16 [Nf*OH*OW, O], O <= 64.
+int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64_t Nf, int H, int W, int C, int KH, int KW, int S,
+                           int O, float* dW, int permP, int permQ, float scale, float* partial, int64_t partial_floats,
+                           const char* tag, cudaStream_t stream);
+
 int f32_to_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, cudaStream_t stream);
 
 }  // namespace tb

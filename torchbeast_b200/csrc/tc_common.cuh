@@ -39,6 +39,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   // K-major, SWIZZLE_128B: start>>4 | LBO(1)<<16 | SBO(1024>>4)<<32 | version(1)<<46 | layout(2)<<61
   return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
@@ -47,6 +53,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   // MN-major, SWIZZLE_128B: LBO = 8192 B (next 64-wide mn group), SBO = 1024 B (next 8 k rows)
   return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(8192 >> 4) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+         (uint64_t(2) << 61);
+}
+__device__ __forceinline__ uint64_t make_smem_desc_mn_lbo(uint32_t saddr, uint32_t lbo_bytes) {
+  // MN-major, SWIZZLE_128B with an explicit byte distance between the 64-wide mn groups
+  return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(lbo_bytes >> 4) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
          (uint64_t(2) << 61);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
@@ -112,6 +123,28 @@ inline int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t col
   return 0;
 }
 
+
+// General rank-`rank` bf16 tensor map (dims/strides innermost first; strides in BYTES for dims 1..rank-1,
+// multiples of 16).  Dimensions may overlap in memory - that is how the implicit-GEMM convolutions express
+// "patch (ox, oy) of frame n, kernel row offset e0" as plain TMA coordinates.
+inline int make_map_nd(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  TB_REQUIRE(fn, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+  TB_REQUIRE(rank >= 2 && rank <= 5 && (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "gemm_tc: bad tensor map arguments");
+  cuuint64_t gdim[5]; cuuint64_t gstride[4]; cuuint32_t bx[5]; cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) {
+    TB_REQUIRE(strides_bytes[i] % 16 == 0, "gemm_tc: tensor map stride %d (%llu B) is not a multiple of 16", i,
+               (unsigned long long)strides_bytes[i]);
+    gstride[i] = strides_bytes[i];
+  }
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstride, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TB_REQUIRE(r == CUDA_SUCCESS, "gemm_tc: cuTensorMapEncodeTiled (rank %d) failed (%d)", rank, int(r));
+  return 0;
+}
 
 }  // namespace tcd
 }  // namespace tb
