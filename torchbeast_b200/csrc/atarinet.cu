@@ -13,6 +13,7 @@
 #include "gemm_simt.cuh"
 #include "conv_implicit.cuh"
 #include "gemm_tc.cuh"
+#include "heads.cuh"
 #include "lstm.cuh"
 #include "net_kernels.cuh"
 
@@ -232,13 +233,9 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
     TB_TRY(lstm_forward(w.core_in, notdone, h0, c0, lp, T1, B, pp.core, pp.core, 2, w.lstm, w.core_out, hN, cN,
                         w.splitk, precision, st));
   }
-  // heads
-  ep = GemmEpilogue(); ep.bias = P + pp.policy_b; ep.tag = "heads_fwd";
-  TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.policy_w, policy_logits, N, A, pp.core, pp.core,
-                                                pp.core, A, ep, 1, nullptr, st)));
-  ep = GemmEpilogue(); ep.bias = P + pp.baseline_b; ep.tag = "heads_fwd";
-  TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.baseline_w, baseline, N, 1, pp.core, pp.core,
-                                                pp.core, 1, ep, 1, nullptr, st)));
+  // heads (fused skinny kernel: one pass over core_out for all A+1 outputs)
+  TB_TRY(heads_forward(w.core_out, pp.core, P + pp.policy_w, P + pp.policy_b, P + pp.baseline_w, P + pp.baseline_b, N, pp.core,
+                       A, policy_logits, baseline, st));
   return 0;
 }
 
@@ -342,16 +339,10 @@ static int atarinet_backward(const float* grad_logits, const float* grad_baselin
   const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
   GemmEpilogue ep;
   // heads: dcore_out = dlogits . Wp + dbaseline . Wb ; dWp, dbp, dWb, dbb
-  ep = GemmEpilogue(); ep.tag = "heads_dgrad";
-  TB_TRY((gemm_simt<float, float, false, false>(grad_logits, P + pp.policy_w, w.dcore_out, N, pp.core, A, A, pp.core,
-                                                 pp.core, ep, 1, nullptr, st)));
-  ep.accumulate = 1;
-  TB_TRY((gemm_simt<float, float, false, false>(grad_baseline, P + pp.baseline_w, w.dcore_out, N, pp.core, 1, 1,
-                                                 pp.core, pp.core, ep, 1, nullptr, st)));
-  TB_TRY(wgrad(grad_logits, A, w.core_out, false, pp.core, G_ + pp.policy_w, N, A, pp.core, 1, 1, w, st, "heads_wgrad"));
-  TB_TRY(wgrad(grad_baseline, 1, w.core_out, false, pp.core, G_ + pp.baseline_w, N, 1, pp.core, 1, 1, w, st, "heads_wgrad"));
-  TB_TRY(colsum(grad_logits, G_ + pp.policy_b, N, A, A, w.colsum_scratch, st));
-  TB_TRY(colsum(grad_baseline, G_ + pp.baseline_b, N, 1, 1, w.colsum_scratch, st));
+  TB_REQUIRE(heads_scratch_floats(N, pp.core, A) <= kSplitKScratchFloats, "atarinet_backward: heads scratch too small");
+  TB_TRY(heads_backward(w.core_out, pp.core, P + pp.policy_w, P + pp.baseline_w, grad_logits, grad_baseline, N, pp.core, A,
+                        w.dcore_out, pp.core, G_ + pp.policy_w, G_ + pp.policy_b, G_ + pp.baseline_w, G_ + pp.baseline_b, w.splitk,
+                        st));
   if (use_lstm) {
     LstmParams lp; LstmGrads lg;
     for (int l = 0; l < 2; ++l) {

@@ -13,6 +13,7 @@
 
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "heads.cuh"
 #include "lstm.cuh"
 #include "net_kernels.cuh"
 #include "resnet_kernels.cuh"
@@ -265,12 +266,8 @@ struct Impl {
       TB_TRY(lstm_forward(w.core_in, notdone, h0, c0, lp, T1, B, pp.core_in, kLstmH, 1, w.lstm, w.core_out, hN, cN, w.splitk,
                           kBf16 ? 1 : 0, st));
     }
-    GemmEpilogue ep; ep.bias = P + pp.policy_b; ep.tag = "heads_fwd";
-    TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.policy_w, policy_logits, N, A, pp.core_out, pp.core_out,
-                                                  pp.core_out, A, ep, 1, nullptr, st)));
-    ep = GemmEpilogue(); ep.bias = P + pp.baseline_b; ep.tag = "heads_fwd";
-    TB_TRY((gemm_simt<float, float, false, true>(w.core_out, P + pp.baseline_w, baseline, N, 1, pp.core_out, pp.core_out,
-                                                  pp.core_out, 1, ep, 1, nullptr, st)));
+    TB_TRY(heads_forward(w.core_out, pp.core_out, P + pp.policy_w, P + pp.policy_b, P + pp.baseline_w, P + pp.baseline_b, N,
+                         pp.core_out, A, policy_logits, baseline, st));
     return 0;
   }
 
@@ -294,21 +291,10 @@ struct Impl {
     const int64_t N = T1 * B;
     const ResParams pp = res_params(A, use_lstm);
     ResWs<T> w = res_ws<T>(workspace, N, T1, B, A, use_lstm);
-    GemmEpilogue ep;
     // heads
-    ep = GemmEpilogue(); ep.tag = "heads_dgrad";
-    TB_TRY((gemm_simt<float, float, false, false>(grad_logits, P + pp.policy_w, w.dcore_out, N, pp.core_out, A, A, pp.core_out,
-                                                   pp.core_out, ep, 1, nullptr, st)));
-    ep.accumulate = 1;
-    TB_TRY((gemm_simt<float, float, false, false>(grad_baseline, P + pp.baseline_w, w.dcore_out, N, pp.core_out, 1, 1,
-                                                   pp.core_out, pp.core_out, ep, 1, nullptr, st)));
-    ep = GemmEpilogue(); ep.tag = "heads_wgrad";
-    TB_TRY((gemm_simt<float, float, true, false>(grad_logits, w.core_out, G + pp.policy_w, A, pp.core_out, N, A, pp.core_out,
-                                                  pp.core_out, ep, splits_simt(A, pp.core_out, N), w.splitk, st)));
-    TB_TRY((gemm_simt<float, float, true, false>(grad_baseline, w.core_out, G + pp.baseline_w, 1, pp.core_out, N, 1, pp.core_out,
-                                                  pp.core_out, ep, splits_simt(1, pp.core_out, N), w.splitk, st)));
-    TB_TRY(colsum(grad_logits, G + pp.policy_b, N, A, A, w.colsum_scratch, st));
-    TB_TRY(colsum(grad_baseline, G + pp.baseline_b, N, 1, 1, w.colsum_scratch, st));
+    TB_TRY(heads_backward(w.core_out, pp.core_out, P + pp.policy_w, P + pp.baseline_w, grad_logits, grad_baseline, N, pp.core_out,
+                          A, w.dcore_out, pp.core_out, G + pp.policy_w, G + pp.policy_b, G + pp.baseline_w, G + pp.baseline_b,
+                          w.splitk, st));
     if (use_lstm) {
       LstmParams lp; LstmGrads lg;
       lp.w_ih[0] = P + pp.lstm[0]; lp.w_hh[0] = P + pp.lstm[1]; lp.b_ih[0] = P + pp.lstm[2]; lp.b_hh[0] = P + pp.lstm[3];
