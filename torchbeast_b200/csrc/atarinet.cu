@@ -301,9 +301,18 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
                     "conv3_wgrad"));
   }
   TB_TRY(colsum_bf16(w.dact3b, G_ + pp.conv3_b, M3, G::C3, G::C3, w.colsum_scratch, st));
-  te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol3b); te.ldc16 = G::KD3; te.tag = "conv3_dgrad";
-  TB_TRY(gemm_tc_bf16_ex(w.dact3b, w.w3b, M3, G::KD3, G::C3, G::C3, G::KD3, false, true, te, 1, nullptr, st));
-  TB_TRY(col2im_bf16_nhwc(w.dcol3b, w.act2b, w.dact2b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
+  if (conv_tc_dgrad_implicit_applicable(G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3)) {
+    // gather-form transposed convolution on tensor cores: dY boxes through TMA (zero fill = padding), ReLU mask in the
+    // epilogue; the transposed weight pack lives in the (otherwise unused) dcol3b buffer
+    TB_TRY(pack_dgrad_weights_bf16(P + pp.conv3_w, w.dcol3b, G::C3, G::C2, G::K3, G::K3, G::S3, st));
+    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dact2b); te.ldc16 = G::C2;
+    te.mask16 = static_cast<const __nv_bfloat16*>(w.act2b); te.ldmask = G::C2; te.tag = "conv3_dgrad";
+    TB_TRY(conv_tc_dgrad_implicit(w.dact3b, w.dcol3b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3, te, st));
+  } else {
+    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol3b); te.ldc16 = G::KD3; te.tag = "conv3_dgrad";
+    TB_TRY(gemm_tc_bf16_ex(w.dact3b, w.w3b, M3, G::KD3, G::C3, G::C3, G::KD3, false, true, te, 1, nullptr, st));
+    TB_TRY(col2im_bf16_nhwc(w.dcol3b, w.act2b, w.dact2b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
+  }
   // conv2
   if (conv_tc_implicit_applicable(G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2)) {
     TB_TRY(conv_tc_wgrad_implicit(w.dact2b, w.act1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2, G_ + pp.conv2_w,
@@ -313,9 +322,16 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
                     "conv2_wgrad"));
   }
   TB_TRY(colsum_bf16(w.dact2b, G_ + pp.conv2_b, M2, G::C2, G::C2, w.colsum_scratch, st));
-  te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol2b); te.ldc16 = G::KD2; te.tag = "conv2_dgrad";
-  TB_TRY(gemm_tc_bf16_ex(w.dact2b, w.w2b, M2, G::KD2, G::C2, G::C2, G::KD2, false, true, te, 1, nullptr, st));
-  TB_TRY(col2im_bf16_nhwc(w.dcol2b, w.act1b, w.dact1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
+  if (conv_tc_dgrad_implicit_applicable(G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2)) {
+    TB_TRY(pack_dgrad_weights_bf16(P + pp.conv2_w, w.dcol2b, G::C2, G::C1, G::K2, G::K2, G::S2, st));
+    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dact1b); te.ldc16 = G::C1;
+    te.mask16 = static_cast<const __nv_bfloat16*>(w.act1b); te.ldmask = G::C1; te.tag = "conv2_dgrad";
+    TB_TRY(conv_tc_dgrad_implicit(w.dact2b, w.dcol2b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2, te, st));
+  } else {
+    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol2b); te.ldc16 = G::KD2; te.tag = "conv2_dgrad";
+    TB_TRY(gemm_tc_bf16_ex(w.dact2b, w.w2b, M2, G::KD2, G::C2, G::C2, G::KD2, false, true, te, 1, nullptr, st));
+    TB_TRY(col2im_bf16_nhwc(w.dcol2b, w.act1b, w.dact1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
+  }
   // conv1: the patch matrix holds raw pixel values, so the weight gradient carries the 1/255
   if (conv_u8_implicit_applicable(G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, G::C1)) {
     // w.col1b holds the bf16 frame image the forward left there (not a patch matrix)

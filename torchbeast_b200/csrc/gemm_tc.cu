@@ -44,11 +44,23 @@ namespace {
 // M tile t = the `rows` = OW*OH*fpt patches of frames [t*fpt, (t+1)*fpt), k-block kb = 64 consecutive
 // (kw, c) elements of kernel row kb / kbw starting at element e0 of the frame - one TMA box per stage lands
 // as [patch][64 k] rows in the canonical SWIZZLE_128B layout, so no patch matrix is ever written.
+//
+// The same machinery runs the INPUT gradient (mode 1/2) as a gather-form transposed convolution, so that
+// neither the [patches, KH*KW*C] gradient matrix nor a col2im pass exists:
+//   mode 1 (stride 1): dX[n,y,x,c] = sum_{kh,kw,o} dY[n,y-kh,x-kw,o] W[o,kh,kw,c]; the A tile of k-block (kh,kw) is
+//     the TMA box of dY at (x0,y0) = (-kw,-kh) - out-of-bounds rows/columns arrive as zeros (the "full" padding);
+//   mode 2 (stride 2, even kernel): output pixels split by parity (py,px) = (y&1, x&1): each class is a stride-1
+//     conv of dY with the (KH/2 x KW/2) sub-kernel W[o, py+2i, px+2j, c].  All classes read the SAME dY boxes, so
+//     they are the N dimension of one GEMM: B = [(py,px,c), (i,j,o)], and the epilogue scatters the 32-column
+//     chunk of class (py,px) to pixel (2u+py, 2v+px).
 struct ImplicitConv {
-  int rows = 0;       // valid patch rows per M tile (<= 128)
+  int rows = 0;       // valid rows per M tile (<= 128)
   int fpt = 1;        // frames per tile
-  int kbw = 1;        // k-blocks per kernel row = KW*C/64
-  int row_elems = 0;  // W*C
+  int kbw = 1;        // k-blocks per kernel row
+  int row_elems = 0;  // mode 0: W*C
+  int mode = 0;       // 0 forward, 1 input gradient stride 1, 2 input gradient stride 2 (parity classes)
+  int tw = 0;         // mode 2: tile width (v range) = ceil(W_in / 2)
+  int outH = 0, outW = 0;  // mode 2: input-gradient image size
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI, bool IMPL = false>
@@ -110,8 +122,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(full(stage), (IMPL ? uint32_t(ic.rows) * 128u : kABytes) + B_BYTES);
           if (IMPL) {
             const int kb = kb0 + i;
-            tma_load_4d(sA + stage * kABytes, &tmA, full(stage), (kb / ic.kbw) * ic.row_elems + (kb % ic.kbw) * kBlockK, 0, 0,
-                        (m0 / kBlockM) * ic.fpt);
+            if (ic.mode == 0)
+              tma_load_4d(sA + stage * kABytes, &tmA, full(stage), (kb / ic.kbw) * ic.row_elems + (kb % ic.kbw) * kBlockK, 0, 0,
+                          (m0 / kBlockM) * ic.fpt);
+            else
+              tma_load_4d(sA + stage * kABytes, &tmA, full(stage), 0, -(kb % ic.kbw), -(kb / ic.kbw), (m0 / kBlockM) * ic.fpt);
           } else if (A_MN) {  // two 64(k) x 64(m) boxes
             tma_load_2d(sA + stage * kABytes, &tmA, full(stage), m0, kc);
             tma_load_2d(sA + stage * kABytes + 8192, &tmA, full(stage), m0 + 64, kc);
@@ -165,11 +180,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int m0, n0, kb0, num_kb, z;
       decode(w, m0, n0, kb0, num_kb, z);
       const int ab = it & 1;
-      mbar_wait(tmem_full(ab), (it >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int rl = quarter * 32 + lane;
       const int64_t r = IMPL ? int64_t(m0 / kBlockM) * ic.rows + rl : int64_t(m0) + rl;
       const bool rvalid = r < M && (!IMPL || rl < ic.rows);
+      // where this thread's 32 values of column chunk c0 live in memory: row pr, first column pc (== r, n0 + c0
+      // except for the parity-class scatter of the stride-2 input gradient); false = nothing to store
+      auto locate = [&](int c0, int64_t& pr, int& pc) -> bool {
+        pr = r; pc = n0 + c0;
+        if (IMPL && ic.mode == 2) {
+          const int cls = (n0 + c0) >> 5, u = rl / ic.tw, v2 = rl - u * ic.tw;
+          const int y = 2 * u + (cls >> 1), x = 2 * v2 + (cls & 1);
+          if (y >= ic.outH || x >= ic.outW) return false;
+          pr = (int64_t(m0 / kBlockM) * ic.outH + y) * ic.outW + x;
+          pc = 0;
+        }
+        return true;
+      };
+      // EPI 2: pull the ReLU-mask / residual rows of the WHOLE tile into L2 before waiting for the accumulator, so
+      // their DRAM latency hides behind the MMA main loop (fetching them chunk by chunk after the wait made the
+      // stride-2 input gradient - 4 chunks, 4 k-blocks - epilogue-latency bound: 271 us)
+      if constexpr (EPI >= 2) {
+        if (rvalid) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BLOCK_N && n0 + c0 < N; c0 += 32) {
+            int64_t pr; int pc;
+            if (!locate(c0, pr, pc)) continue;
+            if (ep.mask16) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.mask16 + pr * ep.ldmask + pc));
+            if (ep.addend16) asm volatile("prefetch.global.L2 [%0];" ::"l"(ep.addend16 + pr * ep.ldadd + pc));
+          }
+        }
+      }
+      mbar_wait(tmem_full(ab), (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         uint32_t v[32];
@@ -195,6 +237,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (rvalid) {
           const int nbase = n0 + c0;
+          int64_t pr; int pc;
+          if (!locate(c0, pr, pc)) continue;
           float o[32];
           const bool full_cols = nbase + 32 <= N;
           // EPI 2: the ReLU mask / residual rows are read as four 16-byte vectors per 32 columns when aligned
@@ -203,7 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           bool vm = false, va = false;
           if constexpr (EPI >= 2) {
             if (full_cols && ep.mask16 && (ep.ldmask & 7) == 0) {
-              const __nv_bfloat16* mp = ep.mask16 + r * ep.ldmask + nbase;
+              const __nv_bfloat16* mp = ep.mask16 + pr * ep.ldmask + pc;
               if ((reinterpret_cast<uintptr_t>(mp) & 15) == 0) {
                 vm = true;
 #pragma unroll
@@ -214,7 +258,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
             if (full_cols && ep.addend16 && (ep.ldadd & 7) == 0) {
-              const __nv_bfloat16* ap = ep.addend16 + r * ep.ldadd + nbase;
+              const __nv_bfloat16* ap = ep.addend16 + pr * ep.ldadd + pc;
               if ((reinterpret_cast<uintptr_t>(ap) & 15) == 0) {
                 va = true;
 #pragma unroll
@@ -237,25 +281,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if constexpr (EPI >= 2) {
               const int n = nbase + j;
               if (full_cols || n < N) {
-                if (ep.mask) x = (ep.mask[r * ep.ldmask + n] > 0.0f) ? x : 0.0f;
+                if (ep.mask) x = (ep.mask[pr * ep.ldmask + pc + j] > 0.0f) ? x : 0.0f;
                 if (vm) {
                   const uint32_t bits = (j & 1) ? (m16[j >> 1] >> 16) : (m16[j >> 1] & 0xffffu);
                   x = (__uint_as_float(bits << 16) > 0.0f) ? x : 0.0f;
                 } else if (ep.mask16) {
-                  x = (__bfloat162float(ep.mask16[r * ep.ldmask + n]) > 0.0f) ? x : 0.0f;
+                  x = (__bfloat162float(ep.mask16[pr * ep.ldmask + pc + j]) > 0.0f) ? x : 0.0f;
                 }
                 if (va) {
                   const uint32_t bits = (j & 1) ? (a16[j >> 1] >> 16) : (a16[j >> 1] & 0xffffu);
                   x += __uint_as_float(bits << 16);
                 } else if (ep.addend16) {
-                  x += __bfloat162float(ep.addend16[r * ep.ldadd + n]);
+                  x += __bfloat162float(ep.addend16[pr * ep.ldadd + pc + j]);
                 }
               }
             }
             o[j] = x;
           }
           if (ep.C) {
-            float* c = ep.C + r * ep.ldc + nbase;
+            float* c = ep.C + pr * ep.ldc + pc;
             const bool vec = (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -269,7 +313,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
           if (ep.C16) {
-            __nv_bfloat16* c = ep.C16 + r * ep.ldc16 + nbase;
+            __nv_bfloat16* c = ep.C16 + pr * ep.ldc16 + pc;
             const bool vec = (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -477,14 +521,13 @@ conv_wgrad_implicit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 1, int kSt = 4>
 int launch_conv_fwd(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K,
                     int64_t tiles_m, const ImplicitConv& ic, cudaStream_t stream) {
-  constexpr int kSt = 4;
   constexpr size_t smem = 1024 + kSt * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kSt + 4) + 16;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, false, false, kSt, 1, true>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, false, false, kSt, EPI, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
@@ -497,7 +540,7 @@ int launch_conv_fwd(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue
   if (per_sm > 3) per_sm = 3;
   int64_t grid = int64_t(kNumSMsB200) * per_sm;
   if (grid > total) grid = total;
-  gemm_tc_kernel<BLOCK_N, false, false, kSt, 1, true><<<(unsigned)grid, kThreads, smem, stream>>>(
+  gemm_tc_kernel<BLOCK_N, false, false, kSt, EPI, true><<<(unsigned)grid, kThreads, smem, stream>>>(
       a, b, ep, int(M), int(N), int(K), nullptr, int(tiles_m), int(tiles_n), 1, ic);
   return check_launch("gemm_tc_kernel(implicit conv)");
 }
@@ -540,6 +583,58 @@ int conv_tc_fwd_implicit(const void* act_nhwc_bf16, const void* w_packed_bf16, i
   if (bn == 32) return launch_conv_fwd<32>(ma, mb, ep, M, O, K, tiles_m, ic, stream);
   if (bn == 64) return launch_conv_fwd<64>(ma, mb, ep, M, O, K, tiles_m, ic, stream);
   return launch_conv_fwd<128>(ma, mb, ep, M, O, K, tiles_m, ic, stream);
+}
+
+bool conv_tc_dgrad_implicit_applicable(int H, int W, int C, int KH, int KW, int S, int O) {
+  const char* e = getenv("TB_CONV_IMPLICIT");
+  if (e && e[0] == '0') return false;
+  if (O != 64 || H < KH || W < KW) return false;
+  const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
+  if (S == 1) return H * W <= kBlockM && (C == 32 || C == 64 || C == 128) && (OH - 1) + KH == H && (OW - 1) + KW == W;
+  if (S == 2)  // every input pixel is covered and the parity tiles are exact
+    return KH == 4 && KW == 4 && C == 32 && (H % 2) == 0 && (W % 2) == 0 && (H / 2) * (W / 2) <= kBlockM &&
+           2 * (OH - 1) + KH == H && 2 * (OW - 1) + KW == W;
+  return false;
+}
+
+// dX (ep.C16, bf16 NHWC [Nf,H,W,C], multiplied by the ReLU mask ep.mask16 = forward activation) from dY [Nf,OH,OW,64];
+// wt_bf16: stride 1: [C, (kh,kw,o)];  stride 2: [(py,px,c), (i,j,o)]   (net_kernels: pack_dgrad_weights_bf16)
+int conv_tc_dgrad_implicit(const void* dy_nhwc_bf16, const void* wt_bf16, int64_t Nf, int H, int W, int C, int KH, int KW, int S,
+                           int O, const TcEpilogue& ep, cudaStream_t stream) {
+  TB_REQUIRE(dy_nhwc_bf16 && wt_bf16 && ep.C16 && ep.ldc16 == C && (!ep.mask16 || ep.ldmask == C),
+             "conv_tc_dgrad_implicit: bad arguments");
+  TB_REQUIRE(conv_tc_dgrad_implicit_applicable(H, W, C, KH, KW, S, O), "conv_tc_dgrad_implicit: unsupported shape");
+  if (Nf == 0) return 0;
+  ProfScope prof(ep.tag, stream);
+  const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
+  ImplicitConv ic;
+  ic.fpt = 1;
+  CUtensorMap ma, mb;
+  const uint64_t dims[4] = {uint64_t(O), uint64_t(OW), uint64_t(OH), uint64_t(Nf)};
+  const uint64_t strides[3] = {uint64_t(O) * 2, uint64_t(OW) * O * 2, uint64_t(OH) * OW * O * 2};
+  int rc;
+  if (S == 1) {
+    ic.mode = 1; ic.rows = H * W; ic.kbw = KW;
+    const uint32_t box[4] = {uint32_t(kBlockK), uint32_t(W), uint32_t(H), 1u};
+    rc = make_map_nd(&ma, dy_nhwc_bf16, 4, dims, strides, box);
+    if (rc) return rc;
+    const int64_t K = int64_t(KH) * KW * O, M = Nf * ic.rows;
+    const int bn = (C <= 32) ? 32 : (C <= 64 ? 64 : 128);
+    rc = make_map(&mb, wt_bf16, C, K, K, bn);
+    if (rc) return rc;
+    if (bn == 32) return launch_conv_fwd<32, 2>(ma, mb, ep, M, C, K, Nf, ic, stream);
+    if (bn == 64) return launch_conv_fwd<64, 2>(ma, mb, ep, M, C, K, Nf, ic, stream);
+    return launch_conv_fwd<128, 2>(ma, mb, ep, M, C, K, Nf, ic, stream);
+  }
+  ic.mode = 2; ic.tw = W / 2; ic.rows = (H / 2) * (W / 2); ic.kbw = KW / 2; ic.outH = H; ic.outW = W;
+  const uint32_t box[4] = {uint32_t(kBlockK), uint32_t(W / 2), uint32_t(H / 2), 1u};
+  rc = make_map_nd(&ma, dy_nhwc_bf16, 4, dims, strides, box);
+  if (rc) return rc;
+  const int64_t K = int64_t(KH / 2) * (KW / 2) * O, M = Nf * ic.rows;
+  rc = make_map(&mb, wt_bf16, 4 * C, K, K, 128);
+  if (rc) return rc;
+  // 4 k-blocks per tile: a 2-stage ring lets two CTAs share an SM so one tile's epilogue overlaps another's loads
+  return launch_conv_fwd<128, 2, 2>(ma, mb, ep, M, 4 * C, K, Nf, ic, stream);
 }
 
 int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64_t Nf, int H, int W, int C, int KH, int KW, int S,

@@ -37,6 +37,14 @@ bool conv_tc_implicit_applicable(int H, int W, int C, int KH, int KW, int S, int
 int conv_tc_fwd_implicit(const void* act_nhwc_bf16, const void* w_packed_bf16, int64_t Nf, int H, int W, int C, int KH, int KW,
                          int S, int O, const TcEpilogue& ep, cudaStream_t stream);
 
+// Input gradient of the same convolution as a gather-form transposed convolution (no gradient patch matrix, no
+// col2im): dX (ep.C16, bf16 NHWC [Nf,H,W,C], times the ReLU mask ep.mask16) from dY [Nf,OH,OW,64].  Stride 1, or
+// stride 2 with a 4x4 kernel (output pixels split into 4 parity classes that share the dY boxes).  wt_bf16 comes
+// from pack_dgrad_weights_bf16 (net_kernels.cuh).
+bool conv_tc_dgrad_implicit_applicable(int H, int W, int C, int KH, int KW, int S, int O);
+int conv_tc_dgrad_implicit(const void* dy_nhwc_bf16, const void* wt_bf16, int64_t Nf, int H, int W, int C, int KH, int KW, int S,
+                           int O, const TcEpilogue& ep, cudaStream_t stream);
+
 // Weight gradient of the same convolution, patches again read through TMA: dW (fp32, [O, KH*KW*C] un-packed by
 // permP/permQ like the split-K reduce of gemm_tc_bf16_ex) = scale * dY^T . patches; dy_bf16 [Nf*OH*OW, O], O <= 64.
 int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64_t Nf, int H, int W, int C, int KH, int KW, int S,

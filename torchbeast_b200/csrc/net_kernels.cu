@@ -416,6 +416,35 @@ int pack_weights_bf16(const float* in, void* out, int64_t O, int P, int Q, int64
   return check_launch("pack_weights_bf16_kernel");
 }
 
+// weights [O, C, KH, KW] (fp32, reference layout) -> B operand of the implicit input-gradient GEMMs (bf16):
+//   stride 1: out[c][(kh*KW + kw)*O + o]
+//   stride 2: out[((py*2 + px)*C + c)][((i*(KW/2) + j)*O + o]  with kh = py + 2i, kw = px + 2j
+__global__ void pack_dgrad_weights_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int O, int C,
+                                               int KH, int KW, int S) {
+  const int64_t total = int64_t(O) * C * KH * KW;
+  const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int kw = int(idx % KW), kh = int((idx / KW) % KH), c = int((idx / (int64_t(KW) * KH)) % C), o = int(idx / (int64_t(KW) * KH * C));
+  const float v = in[idx];
+  int64_t dst;
+  if (S == 1) {
+    dst = int64_t(c) * (KH * KW * O) + int64_t(kh * KW + kw) * O + o;
+  } else {
+    const int py = kh & 1, i = kh >> 1, px = kw & 1, j = kw >> 1;
+    dst = (int64_t((py * 2 + px) * C + c)) * ((KH / 2) * (KW / 2) * O) + int64_t(i * (KW / 2) + j) * O + o;
+  }
+  out[dst] = __float2bfloat16_rn(v);
+}
+
+int pack_dgrad_weights_bf16(const float* in, void* out_bf16, int O, int C, int KH, int KW, int S, cudaStream_t stream) {
+  TB_REQUIRE(in && out_bf16 && (S == 1 || (S == 2 && KH % 2 == 0 && KW % 2 == 0)), "pack_dgrad_weights_bf16: bad arguments");
+  ProfScope prof("weight_pack_bf16", stream);
+  const int64_t total = int64_t(O) * C * KH * KW;
+  pack_dgrad_weights_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out_bf16), O,
+                                                                                     C, KH, KW, S);
+  return check_launch("pack_dgrad_weights_bf16_kernel");
+}
+
 __global__ void colsum_partial_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ part, int64_t M,
                                            int64_t ncols, int64_t ld, int64_t rows_per_slab) {
   __shared__ float sm[8][33];

@@ -50,6 +50,8 @@ int col2im_bf16_nhwc(const void* dcol_bf16, const void* act_bf16, void* dact_bf1
                      int KH, int KW, int S, cudaStream_t stream);
 // out_bf16[o*ld_out + p*Q + q] = in[o*P*Q + q*P + p]; columns [P*Q, ld_out) zero
 int pack_weights_bf16(const float* in, void* out_bf16, int64_t O, int P, int Q, int64_t ld_out, cudaStream_t stream);
+// weights [O,C,KH,KW] fp32 -> bf16 B operand of the implicit input-gradient GEMMs (see gemm_tc.cuh)
+int pack_dgrad_weights_bf16(const float* in, void* out_bf16, int O, int C, int KH, int KW, int S, cudaStream_t stream);
 // colsum over a bf16 matrix (bias gradients), fp32 accumulation
 int colsum_bf16(const void* X_bf16, float* out, int64_t M, int64_t ncols, int64_t ld, float* scratch, cudaStream_t stream);
 
