@@ -269,66 +269,92 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
             }
           }
+          // uniform branches around whole 32-element passes (per-element predication on the runtime flags cost ~15
+          // instructions per output and made the short-K implicit convolutions issue-bound in this epilogue)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]);
-            if constexpr (EPI >= 1) {
-              x *= ep.scale;
-              const int n = nbase + j;
-              if (ep.bias && (full_cols || n < N)) x += __ldg(ep.bias + n);
-              if (ep.relu) x = fmaxf(x, 0.0f);
+          for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+          if constexpr (EPI >= 1) {
+            if (ep.scale != 1.0f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] *= ep.scale;
             }
-            if constexpr (EPI >= 2) {
-              const int n = nbase + j;
-              if (full_cols || n < N) {
-                if (ep.mask) x = (ep.mask[pr * ep.ldmask + pc + j] > 0.0f) ? x : 0.0f;
-                if (vm) {
-                  const uint32_t bits = (j & 1) ? (m16[j >> 1] >> 16) : (m16[j >> 1] & 0xffffu);
-                  x = (__uint_as_float(bits << 16) > 0.0f) ? x : 0.0f;
-                } else if (ep.mask16) {
-                  x = (__bfloat162float(ep.mask16[pr * ep.ldmask + pc + j]) > 0.0f) ? x : 0.0f;
+            if (ep.bias) {
+              const float* bp = ep.bias + nbase;
+              if (full_cols && (reinterpret_cast<uintptr_t>(bp) & 15) == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + q);
+                  o[4 * q] += b4.x; o[4 * q + 1] += b4.y; o[4 * q + 2] += b4.z; o[4 * q + 3] += b4.w;
                 }
-                if (va) {
-                  const uint32_t bits = (j & 1) ? (a16[j >> 1] >> 16) : (a16[j >> 1] & 0xffffu);
-                  x += __uint_as_float(bits << 16);
-                } else if (ep.addend16) {
-                  x += __bfloat162float(ep.addend16[pr * ep.ldadd + pc + j]);
-                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (nbase + j < N) o[j] += __ldg(bp + j);
               }
             }
-            o[j] = x;
+            if (ep.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.0f);
+            }
+          }
+          if constexpr (EPI >= 2) {
+            if (ep.mask) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nbase + j < N) o[j] = (ep.mask[pr * ep.ldmask + pc + j] > 0.0f) ? o[j] : 0.0f;
+            }
+            if (vm) {  // a bf16 is positive iff its bit pattern, read as a signed 16-bit integer, is > 0
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const uint32_t m = m16[j >> 1];
+                o[j] = (int(m << 16) > 0) ? o[j] : 0.0f;
+                o[j + 1] = (int(m & 0xffff0000u) > 0) ? o[j + 1] : 0.0f;
+              }
+            } else if (ep.mask16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nbase + j < N) o[j] = (__bfloat162float(ep.mask16[pr * ep.ldmask + pc + j]) > 0.0f) ? o[j] : 0.0f;
+            }
+            if (va) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const uint32_t m = a16[j >> 1];
+                o[j] += __uint_as_float(m << 16);
+                o[j + 1] += __uint_as_float(m & 0xffff0000u);
+              }
+            } else if (ep.addend16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nbase + j < N) o[j] += __bfloat162float(ep.addend16[pr * ep.ldadd + pc + j]);
+            }
           }
           if (ep.C) {
             float* c = ep.C + pr * ep.ldc + pc;
-            const bool vec = (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
+            if (full_cols && (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (vec && nbase + j + 4 <= N) {
-                *reinterpret_cast<float4*>(c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-              } else {
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            } else {
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                  if (nbase + j + jj < N) c[j + jj] = o[j + jj];
-              }
+              for (int j = 0; j < 32; ++j)
+                if (nbase + j < N) c[j] = o[j];
             }
           }
           if (ep.C16) {
             __nv_bfloat16* c = ep.C16 + pr * ep.ldc16 + pc;
-            const bool vec = (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
+            if (full_cols && (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (vec && nbase + j + 8 <= N) {
+              for (int j = 0; j < 32; j += 8) {
                 uint4 pk;
                 __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
                 __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
                 pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
                 pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
                 *reinterpret_cast<uint4*>(c + j) = pk;
-              } else {
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
-                  if (nbase + j + jj < N) c[j + jj] = __float2bfloat16_rn(o[j + jj]);
               }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nbase + j < N) c[j] = __float2bfloat16_rn(o[j]);
             }
           }
         }

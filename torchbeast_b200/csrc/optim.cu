@@ -16,9 +16,11 @@ __global__ void grad_sumsq_kernel(const float* __restrict__ g, int64_t n, float*
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   const int64_t n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
+  // squares of one 16-byte vector are summed in fp32 (4 terms), the running sum in fp64; 4 loads in flight
+#pragma unroll 4
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = __ldg(g4 + i);
-    s += double(v.x) * v.x + double(v.y) * v.y + double(v.z) * v.z + double(v.w) * v.w;
+    s += double(fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))));
   }
   for (int64_t i = n4 * 4 + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     s += double(g[i]) * g[i];
@@ -38,7 +40,24 @@ __global__ void clip_rmsprop_kernel(float* __restrict__ p, float* __restrict__ g
   const float lr = lr_dev ? lr_dev[0] : lr_host;
   if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) norm_out[0] = norm;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+  int64_t done = 0;
+  if (!mom && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(sq)) & 15) == 0) {
+    // 128-bit path (no momentum buffer: the learner's configuration)
+    const int64_t n4 = n / 4;
+    float4* p4 = reinterpret_cast<float4*>(p); float4* g4 = reinterpret_cast<float4*>(g); float4* s4 = reinterpret_cast<float4*>(sq);
+#pragma unroll 2
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      float4 gv = g4[i], sv = s4[i], pv = p4[i];
+      gv.x *= coef; gv.y *= coef; gv.z *= coef; gv.w *= coef;
+      sv.x = alpha * sv.x + (1.0f - alpha) * gv.x * gv.x; sv.y = alpha * sv.y + (1.0f - alpha) * gv.y * gv.y;
+      sv.z = alpha * sv.z + (1.0f - alpha) * gv.z * gv.z; sv.w = alpha * sv.w + (1.0f - alpha) * gv.w * gv.w;
+      pv.x -= lr * (gv.x / (sqrtf(sv.x) + eps)); pv.y -= lr * (gv.y / (sqrtf(sv.y) + eps));
+      pv.z -= lr * (gv.z / (sqrtf(sv.z) + eps)); pv.w -= lr * (gv.w / (sqrtf(sv.w) + eps));
+      g4[i] = gv; s4[i] = sv; p4[i] = pv;
+    }
+    done = n4 * 4;
+  }
+  for (int64_t i = done + int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float gi = g[i] * coef;
     g[i] = gi;
     const float s = alpha * sq[i] + (1.0f - alpha) * gi * gi;
