@@ -85,15 +85,27 @@ __device__ __forceinline__ bool grid_sum3(double s0, double s1, double s2, void*
       __threadfence();
       unsigned ticket = atomicAdd(counter, 1u);
       is_last = (ticket == nblocks - 1);
-      if (is_last) {
-        __threadfence();
-        double x = 0, y = 0, z = 0;
-        for (unsigned i = 0; i < nblocks; ++i) {
-          x += __ldcg(&partials[i * 4 + 0]); y += __ldcg(&partials[i * 4 + 1]); z += __ldcg(&partials[i * 4 + 2]);
-        }
-        tot[0] = x; tot[1] = y; tot[2] = z;
-        *counter = 0u;
-      }
+    }
+  }
+  __syncthreads();
+  if (is_last && nblocks > 1) {
+    // the last CTA folds the partials with ALL its threads: thread t takes CTAs t, t + nthreads, ... and the
+    // per-thread sums are combined warp by warp - a fixed pattern, independent of which CTA arrived last
+    // (one thread walking 592 partials with dependent fp64 adds took 40 us in grad_sumsq_kernel)
+    __threadfence();
+    double x = 0, y = 0, z = 0;
+    for (unsigned i = tid; i < nblocks; i += nthreads) {
+      x += __ldcg(&partials[i * 4 + 0]); y += __ldcg(&partials[i * 4 + 1]); z += __ldcg(&partials[i * 4 + 2]);
+    }
+    x = warp_sum(x); y = warp_sum(y); z = warp_sum(z);
+    __syncthreads();
+    if (lane == 0) { sm[warp][0] = x; sm[warp][1] = y; sm[warp][2] = z; }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0, b = 0, c = 0;
+      for (int w = 0; w < nwarps; ++w) { a += sm[w][0]; b += sm[w][1]; c += sm[w][2]; }
+      tot[0] = a; tot[1] = b; tot[2] = c;
+      *counter = 0u;
     }
   }
   __syncthreads();

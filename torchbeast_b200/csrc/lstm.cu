@@ -1121,7 +1121,9 @@ __global__ void __launch_bounds__(kStepThreads) lstm2_fwd_wave_mma_kernel(WaveFw
 struct PersistBwdMmaArgs {
   const float* w_hh; const float* dy; const float* nd;
   const float* gates; const float* cs; const float* cm;
-  float* dgates; __nv_bfloat16* dgq;   // dgq: [2][4, B, Hq]
+  __nv_bfloat16* dgb; int lg;          // gate gradients of all steps, bf16 [T1*B, lg] (operand of the hoisted GEMMs)
+  float* db;                           // [4H] bias gradient = sum over steps and rows of the gate gradients
+  __nv_bfloat16* dgq;                  // dgq: [2][4, B, Hq]
   unsigned* counter;
   int T1, B, H, Hq; unsigned nctas;
 };
@@ -1187,14 +1189,17 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
     n_ndn = (t + 1 < a.T1) ? a.nd[r0 + B + lane] : 0.f;
   };
   prefetch(a.T1 - 1);
+  float bs_i = 0.f, bs_f = 0.f, bs_g = 0.f, bs_o = 0.f;  // bias gradients: this thread's (row, unit) summed over time
+  auto store_dg = [&](int64_t row, float p_i, float p_f, float p_g, float p_o) {
+    __nv_bfloat16* d = a.dgb + row * a.lg + k0 + q;
+    d[0] = __float2bfloat16_rn(p_i); d[H] = __float2bfloat16_rn(p_f);
+    d[2 * H] = __float2bfloat16_rn(p_g); d[3 * H] = __float2bfloat16_rn(p_o);
+  };
   for (int t = a.T1 - 1; t >= 0; --t, ++it) {
     const int64_t row0 = int64_t(t) * B;
     __nv_bfloat16* dgq_t = a.dgq + int64_t(it & 1) * 4 * gs;
     float p_i = 0.f, p_f = 0.f, p_g = 0.f, p_o = 0.f;
-    int64_t g0 = 0;
     if (actA) {
-      const int j = k0 + q;
-      g0 = (row0 + lane) * 4 * H + j;
       const float ig = n_ig, fg = n_fg, gg = n_gg, og = n_og;
       float dh = n_dy;
       float dc = 0.0f;
@@ -1209,9 +1214,10 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
       p_i = d_i * ig * (1.0f - ig); p_f = d_f * fg * (1.0f - fg);
       p_g = d_g * (1.0f - gg * gg); p_o = d_o * og * (1.0f - og);
       dc_s[q][lane] = dc * fg * n_nd;
+      bs_i += p_i; bs_f += p_f; bs_g += p_g; bs_o += p_o;
     }
     if (t == 0) {
-      if (actA) { a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o; }
+      if (actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
       break;
     }
     // publish this CTA's 8 columns of the four gate-gradient tiles with 16-byte stores (staged through smem:
@@ -1230,36 +1236,25 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
       red_release_add(a.counter, 1u);
       grid_wait(a.counter, unsigned(it + 1) * a.nctas);
     }
-    if (actA) { a.dgates[g0] = p_i; a.dgates[g0 + H] = p_f; a.dgates[g0 + 2 * H] = p_g; a.dgates[g0 + 3 * H] = p_o; }
+    if (actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
     prefetch(t - 1);
     __syncthreads();
-    // all four gate-gradient tiles of this step: [4][rows][Hq] bf16 (L2 -> smem, 16-byte chunks)
+    // all four gate-gradient tiles of this step: [4][rows][Hq] bf16, L2 -> smem as per-thread async 16-byte copies
+    // (up to 20 in flight per thread, no staging registers)
     {
-      // every thread first issues ALL its loads (up to 5 per gate tile), then stores: ~20 x 16 B in flight per
-      // thread instead of one (a load->store loop left the copy latency-bound at ~16 B/clk per SM)
       const int nchunk = rows * chunks_per_row;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {  // two gate tiles (10 x 16 B per thread) per batch: fits the register budget
-        uint4 v[2][5];
+      for (int gg = 0; gg < 4; ++gg) {
+        const uint4* src = reinterpret_cast<const uint4*>(dgq_t + int64_t(gg) * gs);
+        uint4* dst = Xs4 + int64_t(gg) * 32 * chunks_per_row;
 #pragma unroll
-        for (int gg = 0; gg < 2; ++gg) {
-          const uint4* src = reinterpret_cast<const uint4*>(dgq_t + int64_t(half * 2 + gg) * gs);
-#pragma unroll
-          for (int u = 0; u < 5; ++u) {
-            const int i = tid + u * kStepThreads;
-            if (i < nchunk) v[gg][u] = __ldcg(src + i);
-          }
-        }
-#pragma unroll
-        for (int gg = 0; gg < 2; ++gg) {
-          uint4* dst = Xs4 + int64_t(half * 2 + gg) * 32 * chunks_per_row;
-#pragma unroll
-          for (int u = 0; u < 5; ++u) {
-            const int i = tid + u * kStepThreads;
-            if (i < nchunk) dst[i] = v[gg][u];
-          }
+        for (int u = 0; u < 5; ++u) {
+          const int i = tid + u * kStepThreads;
+          if (i < nchunk) cp_async16(dst + i, src + i);
         }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     float acc[2][kBwdNT][4];
@@ -1299,6 +1294,13 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
       dh_s[wrp][lane] = d;
     }
     __syncthreads();
+  }
+  // bias gradients: fold the 32 batch rows of each unit (fixed order: time inside the thread, rows by shuffles)
+  if (wrp < kBwdCols) {
+    bs_i = warp_sum(bs_i); bs_f = warp_sum(bs_f); bs_g = warp_sum(bs_g); bs_o = warp_sum(bs_o);
+    if (lane == 0 && k0 + q < H) {
+      a.db[k0 + q] = bs_i; a.db[H + k0 + q] = bs_f; a.db[2 * H + k0 + q] = bs_g; a.db[3 * H + k0 + q] = bs_o;
+    }
   }
 }
 
@@ -1399,7 +1401,7 @@ static int lstm2_fwd_wave(LstmWs& ws, const LstmParams& p, float* y, const float
 }
 
 static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, const float* dy, const float* notdone,
-                                   int64_t T1, int64_t B, int H, unsigned* counter, cudaStream_t st) {
+                                   int64_t T1, int64_t B, int H, float* db, unsigned* counter, cudaStream_t st) {
   const int Hq = mma_hq(H);
   const size_t smem = size_t(4) * 32 * Hq * 2;
   dim3 grid((H + kBwdCols - 1) / kBwdCols, 1);
@@ -1408,7 +1410,8 @@ static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, cons
   if (e == cudaSuccess) e = cudaMemsetAsync(L.dgq, 0, size_t(2) * 4 * B * Hq * 2, st);  // zero the row padding
   TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
   PersistBwdMmaArgs a;
-  a.w_hh = w_hh; a.dy = dy; a.nd = notdone; a.gates = L.gates; a.cs = L.cs; a.cm = L.cm; a.dgates = L.dgates;
+  a.w_hh = w_hh; a.dy = dy; a.nd = notdone; a.gates = L.gates; a.cs = L.cs; a.cm = L.cm;
+  a.dgb = static_cast<__nv_bfloat16*>(L.dgb); a.lg = int(ld16(4 * H)); a.db = db;
   a.dgq = static_cast<__nv_bfloat16*>(L.dgq); a.counter = counter;
   a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nctas = grid.x;
   void* args[] = {&a};
@@ -1574,7 +1577,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     ProfScope prof("lstm_recurrence_bwd", st);
     int prc = -1;
     if (use_mma) {
-      prc = lstm_bwd_persistent_mma(L, p.w_hh[l], dyl, notdone, T1, B, H, ws.sync + 16, st);
+      prc = lstm_bwd_persistent_mma(L, p.w_hh[l], dyl, notdone, T1, B, H, g.b_ih[l], ws.sync + 16, st);
       TB_REQUIRE(prc >= 0, "lstm: tensor-core recurrence kernel does not fit (B=%lld H=%d)", (long long)B, H);
     }
     if (prc < 0) prc = lstm_bwd_persistent(L, ws, dyl, notdone, T1, B, H, ws.sync + 16, st);
@@ -1601,7 +1604,8 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     // parameter gradients over all steps at once
     if (precision) {
       const int64_t lg = ld16(4 * H), lh = ld16(H), li = ld16(in_dim);
-      TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st));
+      // the tensor-core recurrence wrote the gate gradients in bf16 and summed the bias gradients itself
+      if (!use_mma) TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st));
       const void* hm_b = L.hmb;
       int64_t hm_ld = lh;
       if (use_mma) {  // the tensor-core forward recurrence already left the masked h in bf16
@@ -1616,7 +1620,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       TB_TRY(gemm_tc_bf16_ex(L.dgb, hm_b, 4 * H, H, N, lg, hm_ld, true, true, te, sp, splitk, st));
       te.C = g.w_ih[l]; te.ldc = in_dim;  // dW_ih[4H,in] = dgates^T . x
       TB_TRY(gemm_tc_bf16_ex(L.dgb, L.xb, 4 * H, in_dim, N, lg, li, true, true, te, sp, splitk, st));
-      TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));
+      if (!use_mma) TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));
       cudaError_t e = cudaMemcpyAsync(g.b_hh[l], g.b_ih[l], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st);
       TB_REQUIRE(e == cudaSuccess, "lstm: bias grad copy: %s", cudaGetErrorString(e));
       // dx[N,in] = dgates[N,4H] . W_ih[4H,in]   (W_ih as stored: reduction index is its row index)
