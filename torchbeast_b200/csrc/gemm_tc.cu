@@ -393,6 +393,7 @@ int launch_e(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, i
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 3) per_sm = 3;
   int64_t grid = int64_t(kNumSMsB200) * per_sm;
+  if (ep.max_ctas > 0 && grid > ep.max_ctas) grid = ep.max_ctas;
   if (grid > total) grid = total;
   gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages, EPI><<<(unsigned)grid, kThreads, smem, stream>>>(
       a, b, ep, int(M), int(N), int(K), partial, int(tiles_m), int(tiles_n), splits);

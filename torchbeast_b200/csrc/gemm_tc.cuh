@@ -16,6 +16,7 @@ struct TcEpilogue {
   const __nv_bfloat16* mask16 = nullptr;             // same, mask stored in bf16 (uses ldmask)
   const __nv_bfloat16* addend16 = nullptr; int64_t ldadd = 0;  // out += addend (residual connection), applied last
   int permP = 1, permQ = 1;                          // (split-K reduce only) weight-grad column un-pack
+  int max_ctas = 0;                                  // > 0: cap the persistent grid (GEMMs running beside a cooperative kernel)
   const char* tag = "gemm_tc";
 };
 

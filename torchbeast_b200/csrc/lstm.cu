@@ -1420,6 +1420,31 @@ static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, cons
   return check_launch("lstm_bwd_persistent_mma_kernel");
 }
 
+// Side stream for work that can run beside a recurrence kernel (which occupies only H/8 = 65 of the 148 SMs):
+// forked from / joined into the caller's stream with events, so it is captured into the learner's CUDA graph.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream* side_stream() {
+  static thread_local SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& s = per_dev[dev];
+  if (!s.stream) {
+    const char* e = getenv("TB_LSTM_OVERLAP");
+    if (e && e[0] == '0') return nullptr;
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      s.stream = nullptr;
+      return nullptr;
+    }
+  }
+  return &s;
+}
+
 #define TB_TRY(expr)        \
   do {                      \
     int _rc = (expr);       \
@@ -1559,6 +1584,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
   const int64_t N = T1 * B;
   const int64_t scratch = int64_t(8) << 20;  // == kSplitKScratchFloats (atarinet.cu)
   const float* dyl = dy;
+  bool forked = false;
   for (int l = layers - 1; l >= 0; --l) {
     LstmLayerWs& L = ws.layer[l];
     const float* xin = (l == 0) ? x : ws.layer[l - 1].hs;
@@ -1604,6 +1630,11 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     // parameter gradients over all steps at once
     if (precision) {
       const int64_t lg = ld16(4 * H), lh = ld16(H), li = ld16(in_dim);
+      if (forked) {  // the upper layer's side-stream GEMMs used the split-K scratch: join before reusing it
+        cudaError_t ej = cudaStreamWaitEvent(st, side_stream()->join, 0);
+        TB_REQUIRE(ej == cudaSuccess, "lstm: side stream join: %s", cudaGetErrorString(ej));
+        forked = false;
+      }
       // the tensor-core recurrence wrote the gate gradients in bf16 and summed the bias gradients itself
       if (!use_mma) TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st));
       const void* hm_b = L.hmb;
@@ -1615,14 +1646,31 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       }
       const int64_t kb = (N + 63) / 64;
       int sp = int(kb / 8); if (sp < 1) sp = 1; if (sp > 4) sp = 4;
+      // The weight-gradient GEMMs of the UPPER layer do not feed the lower layer's recurrence (only dx does), and that
+      // recurrence occupies 65 SMs: run them on a side stream with a grid capped to the idle SMs and join before the
+      // split-K scratch is needed again.
+      SideStream* side = (use_mma && l == 1 && layers == 2) ? side_stream() : nullptr;
+      cudaStream_t gs = st;
       TcEpilogue te; te.tag = "lstm_wgrad";
+      if (side) {
+        cudaError_t ee = cudaEventRecord(side->fork, st);
+        if (ee == cudaSuccess) ee = cudaStreamWaitEvent(side->stream, side->fork, 0);
+        TB_REQUIRE(ee == cudaSuccess, "lstm: side stream fork: %s", cudaGetErrorString(ee));
+        gs = side->stream;
+        te.max_ctas = kNumSMsB200 - int((H + kBwdCols - 1) / kBwdCols) - 2;
+        forked = true;
+      }
       te.C = g.w_hh[l]; te.ldc = H;      // dW_hh[4H,H] = dgates^T . hm   (both operands stored [N, .]: MN-major)
-      TB_TRY(gemm_tc_bf16_ex(L.dgb, hm_b, 4 * H, H, N, lg, hm_ld, true, true, te, sp, splitk, st));
+      TB_TRY(gemm_tc_bf16_ex(L.dgb, hm_b, 4 * H, H, N, lg, hm_ld, true, true, te, sp, splitk, gs));
       te.C = g.w_ih[l]; te.ldc = in_dim;  // dW_ih[4H,in] = dgates^T . x
-      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.xb, 4 * H, in_dim, N, lg, li, true, true, te, sp, splitk, st));
+      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.xb, 4 * H, in_dim, N, lg, li, true, true, te, sp, splitk, gs));
       if (!use_mma) TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));
-      cudaError_t e = cudaMemcpyAsync(g.b_hh[l], g.b_ih[l], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, st);
+      cudaError_t e = cudaMemcpyAsync(g.b_hh[l], g.b_ih[l], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, gs);
       TB_REQUIRE(e == cudaSuccess, "lstm: bias grad copy: %s", cudaGetErrorString(e));
+      if (side) {
+        e = cudaEventRecord(side->join, side->stream);
+        TB_REQUIRE(e == cudaSuccess, "lstm: side stream join: %s", cudaGetErrorString(e));
+      }
       // dx[N,in] = dgates[N,4H] . W_ih[4H,in]   (W_ih as stored: reduction index is its row index)
       TcEpilogue td; td.tag = "lstm_xproj_dgrad"; td.C = dxl; td.ldc = in_dim;
       TB_TRY(gemm_tc_bf16_ex(L.dgb, L.wihb, N, in_dim, 4 * H, lg, li, false, true, td, 1, nullptr, st));
