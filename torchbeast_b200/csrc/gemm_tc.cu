@@ -334,9 +334,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
             } else {
+              const bool vec = (ep.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nbase + j < N) c[j] = o[j];
+              for (int j = 0; j < 32; j += 4) {
+                if (vec && nbase + j + 4 <= N) {
+                  *reinterpret_cast<float4*>(c + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj)
+                    if (nbase + j + jj < N) c[j + jj] = o[j + jj];
+                }
+              }
             }
           }
           if (ep.C16) {
@@ -351,10 +359,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
                 *reinterpret_cast<uint4*>(c + j) = pk;
               }
-            } else {
+            } else {  // column tail (N = 144, 288, ...): still 16-byte stores for the complete groups of 8
+              const bool vec = (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nbase + j < N) c[j] = __float2bfloat16_rn(o[j]);
+              for (int j = 0; j < 32; j += 8) {
+                if (vec && nbase + j + 8 <= N) {
+                  uint4 pk;
+                  __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+                  __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                  *reinterpret_cast<uint4*>(c + j) = pk;
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj)
+                    if (nbase + j + jj < N) c[j + jj] = __float2bfloat16_rn(o[j + jj]);
+                }
+              }
             }
           }
         }
