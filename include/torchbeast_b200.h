@@ -189,7 +189,7 @@ int tb_gemm_bf16_tn(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N
 /* General operand layouts of the same kernel: a_mn / b_mn != 0 mark an operand stored with the
  * REDUCTION index as its row index (A as [K,M], B as [K,N], row-major) - the dgrad (b_mn) and wgrad
  * (a_mn and b_mn) forms, so no transposed copies are needed.  splits > 1 reduces K over grid.z through
- * `partial` (splits*M*N floats) with a fixed-order second pass.  C fp32 [M,N] (ldc).            */
+ * `partial` (splits*M*roundup(N,32) floats: rows padded so the tiles store 16 bytes) with a fixed-order second pass.  C fp32 [M,N] (ldc).            */
 int tb_gemm_bf16_ex(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, int64_t lda,
                     int64_t ldb, int a_mn, int b_mn, float* C, int64_t ldc, int splits, float* partial,
                     void* stream);

@@ -75,7 +75,7 @@ def test_gemm_tc_mn_major_operands(M, N, K, mode):
     B = torch.randn(K, N, device="cuda", generator=g).to(torch.bfloat16)
     C = torch.full((M, N), float("nan"), device="cuda")
     splits = 7 if mode == "wgrad_splitk" else 1
-    part = torch.empty(splits * M * N, device="cuda") if splits > 1 else None
+    part = torch.empty(splits * M * ((N + 31) // 32 * 32), device="cuda") if splits > 1 else None  # rows padded to 32 floats
     p = _lib.ptr
     rc = _lib.lib().tb_gemm_bf16_ex(p(A), p(B), M, N, K, A.shape[1], N, int(a_mn), 1, p(C), N, splits, p(part), _lib.stream_ptr())
     _lib.check(rc, "tb_gemm_bf16_ex")

@@ -265,7 +265,8 @@ static int tc_splits(int64_t M, int64_t N, int64_t K) {
   const int64_t kb = (K + 63) / 64;
   int64_t s = (2 * kNumSMsB200 + tiles - 1) / tiles;
   if (s > kb / 4) s = kb / 4;
-  if (s * M * N > kSplitKScratchFloats) s = kSplitKScratchFloats / (M * N);
+  const int64_t Np = (N + 31) & ~int64_t(31);  // partial rows are padded to 32 floats (gemm_tc.cu)
+  if (s * M * Np > kSplitKScratchFloats) s = kSplitKScratchFloats / (M * Np);
   if (s > 148) s = 148;
   if (s < 1) s = 1;
   return int(s);

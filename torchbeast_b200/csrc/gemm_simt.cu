@@ -4,14 +4,17 @@
 namespace tb {
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int64_t M, int64_t N,
-                                     int64_t ldc, int splits, GemmEpilogue ep) {
+                                     int64_t ldc, int splits, GemmEpilogue ep, int64_t ldp) {
   const int64_t total = M * N;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int64_t slice = M * ldp;  // partial rows are ldp floats apart (ldp >= N: padded so the GEMM stores 16 bytes)
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    float v = 0.0f;
-    for (int z = 0; z < splits; ++z) v += partial[int64_t(z) * total + i];
-    v *= ep.scale;
     const int64_t m = i / N, n = i % N;
+    const float* p = partial + m * ldp + n;
+    float v = 0.0f;
+#pragma unroll 4
+    for (int z = 0; z < splits; ++z) v += __ldg(p + int64_t(z) * slice);
+    v *= ep.scale;
     if (ep.bias) v += ep.bias[n];
     if (ep.relu) v = fmaxf(v, 0.0f);
     int64_t nd = n;
@@ -58,7 +61,7 @@ int gemm_simt(const AT* A, const BT* B, float* C, int64_t M, int64_t N, int64_t 
     const int64_t total = M * N;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(splitk_scratch, C, M, N, ldc, splits, ep);
+    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(splitk_scratch, C, M, N, ldc, splits, ep, N);
     rc = check_launch("splitk_reduce_kernel");
   }
   return rc;

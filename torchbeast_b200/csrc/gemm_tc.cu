@@ -66,7 +66,8 @@ struct ImplicitConv {
 template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI, bool IMPL = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep, int M,
-               int N, int K, float* partial, int tiles_m, int tiles_n, int splits, ImplicitConv ic = ImplicitConv()) {
+               int N, int K, float* partial, int tiles_m, int tiles_n, int splits, int ldp = 0,
+               ImplicitConv ic = ImplicitConv()) {
   constexpr uint32_t B_BYTES = BLOCK_N * kBlockK * 2;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulator buffers (power of two)
   extern __shared__ uint8_t smem_raw[];
@@ -222,13 +223,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (partial) {  // split-K: raw partial tile [z][M][N]; splitk_reduce_kernel applies the epilogue
           if (rvalid) {
-            float* pz = partial + (int64_t(z) * M + r) * N + n0 + c0;
-            if (n0 + c0 + 32 <= N && (N & 3) == 0) {
+            // rows of the partial tiles are ldp floats apart, ldp = N rounded up to 32: every chunk that starts
+            // inside a row is stored whole with 16-byte stores (the columns past N hold exact zeros from the TMA
+            // fill).  With the natural stride an odd N (519) forced 4-byte stores: 6x write amplification in L2.
+            float* pz = partial + (int64_t(z) * M + r) * ldp + n0 + c0;
+            if (n0 + c0 + 32 <= ldp) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
                 *reinterpret_cast<float4*>(pz + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            } else {
+            } else if (n0 + c0 < ldp) {
               for (int j = 0; j < 32; ++j)
                 if (n0 + c0 + j < N) pz[j] = __uint_as_float(v[j]);
             }
@@ -417,7 +421,7 @@ int launch_e(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, i
   if (ep.max_ctas > 0 && grid > ep.max_ctas) grid = ep.max_ctas;
   if (grid > total) grid = total;
   gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages, EPI><<<(unsigned)grid, kThreads, smem, stream>>>(
-      a, b, ep, int(M), int(N), int(K), partial, int(tiles_m), int(tiles_n), splits);
+      a, b, ep, int(M), int(N), int(K), partial, int(tiles_m), int(tiles_n), splits, int((N + 31) & ~int64_t(31)));
   return check_launch("gemm_tc_kernel");
 }
 
@@ -589,7 +593,7 @@ int launch_conv_fwd(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue
   int64_t grid = int64_t(kNumSMsB200) * per_sm;
   if (grid > total) grid = total;
   gemm_tc_kernel<BLOCK_N, false, false, kSt, EPI, true><<<(unsigned)grid, kThreads, smem, stream>>>(
-      a, b, ep, int(M), int(N), int(K), nullptr, int(tiles_m), int(tiles_n), 1, ic);
+      a, b, ep, int(M), int(N), int(K), nullptr, int(tiles_m), int(tiles_n), 1, 0, ic);
   return check_launch("gemm_tc_kernel(implicit conv)");
 }
 
@@ -743,7 +747,7 @@ int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64
   const int64_t total = int64_t(O) * K;
   int64_t blocks = (total + 255) / 256;
   if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;
-  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, dW, O, K, K, int(splits), rep);
+  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, dW, O, K, K, int(splits), rep, K);
   return check_launch("splitk_reduce_kernel");
 }
 
@@ -792,7 +796,7 @@ int gemm_tc_bf16_ex(const void* A, const void* B, int64_t M, int64_t N, int64_t 
   const int64_t total = M * N;
   int64_t blocks = (total + 255) / 256;
   if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;
-  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(part, ep.C, M, N, ep.ldc, splits, rep);
+  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(part, ep.C, M, N, ep.ldc, splits, rep, (N + 31) & ~int64_t(31));
   return check_launch("splitk_reduce_kernel");
 }
 

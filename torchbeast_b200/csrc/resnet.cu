@@ -147,7 +147,8 @@ int splits_tc(int64_t M, int64_t N, int64_t K) {
   int64_t s = (2 * kNumSMsB200 + tiles - 1) / tiles;
   const int64_t kb = (K + 63) / 64;
   if (s > kb / 4) s = kb / 4;
-  if (s * M * N > kScratchFloats) s = kScratchFloats / (M * N);
+  const int64_t Np = (N + 31) & ~int64_t(31);  // partial rows are padded to 32 floats (gemm_tc.cu)
+  if (s * M * Np > kScratchFloats) s = kScratchFloats / (M * Np);
   if (s > 148) s = 148;
   return int(s < 1 ? 1 : s);
 }
