@@ -489,9 +489,7 @@ int conv_u8_wgrad_implicit(const void* dy_bf16, const void* frame_bf16, int64_t 
   if (rc) return rc;
   GemmEpilogue rep;
   rep.scale = scale;
-  const int64_t total = int64_t(kO) * kC * 64;
-  splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, dW, kO, kC * 64, kC * 64, int(grid), rep, kC * 64);
-  return check_launch("splitk_reduce_kernel");
+  return launch_splitk_reduce(partial, dW, kO, kC * 64, kC * 64, int(grid), rep, kC * 64, stream);
 }
 
 }  // namespace tb

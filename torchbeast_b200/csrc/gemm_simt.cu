@@ -3,28 +3,37 @@
 
 namespace tb {
 
+// grid (ceil(N / 256), rows): one output row per blockIdx.y (grid-stride over rows), one column per thread - no
+// 64-bit div/mod per element, the split loop unrolled so `splits` loads are in flight.
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int64_t M, int64_t N,
                                      int64_t ldc, int splits, GemmEpilogue ep, int64_t ldp) {
-  const int64_t total = M * N;
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
   const int64_t slice = M * ldp;  // partial rows are ldp floats apart (ldp >= N: padded so the GEMM stores 16 bytes)
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int64_t m = i / N, n = i % N;
+  int nd = n;
+  if (ep.permP > 1 || ep.permQ > 1) {
+    const int p = n / ep.permQ, q = n - p * ep.permQ;
+    nd = q * ep.permP + p;
+  }
+  const float b = ep.bias ? __ldg(ep.bias + n) : 0.0f;
+  for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
     const float* p = partial + m * ldp + n;
     float v = 0.0f;
 #pragma unroll 4
     for (int z = 0; z < splits; ++z) v += __ldg(p + int64_t(z) * slice);
-    v *= ep.scale;
-    if (ep.bias) v += ep.bias[n];
+    v = v * ep.scale + b;
     if (ep.relu) v = fmaxf(v, 0.0f);
-    int64_t nd = n;
-    if (ep.permP > 1 || ep.permQ > 1) {
-      const int64_t p = n / ep.permQ, q = n % ep.permQ;
-      nd = q * ep.permP + p;
-    }
     float* c = C + m * ldc + nd;
     *c = ep.accumulate ? (*c + v) : v;
   }
+}
+
+int launch_splitk_reduce(const float* partial, float* C, int64_t M, int64_t N, int64_t ldc, int splits, const GemmEpilogue& ep,
+                         int64_t ldp, cudaStream_t stream) {
+  if (M == 0 || N == 0) return 0;
+  dim3 grid((unsigned)((N + 255) / 256), (unsigned)(M < 65535 ? M : 65535));
+  splitk_reduce_kernel<<<grid, 256, 0, stream>>>(partial, C, M, N, ldc, splits, ep, ldp);
+  return check_launch("splitk_reduce_kernel");
 }
 
 template <typename AT, typename BT, bool TA, bool TB, int BM, int BN>
@@ -61,8 +70,7 @@ int gemm_simt(const AT* A, const BT* B, float* C, int64_t M, int64_t N, int64_t 
     const int64_t total = M * N;
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(splitk_scratch, C, M, N, ldc, splits, ep, N);
-    rc = check_launch("splitk_reduce_kernel");
+    rc = launch_splitk_reduce(splitk_scratch, C, M, N, ldc, splits, ep, N, stream);
   }
   return rc;
 }

@@ -184,6 +184,8 @@ __global__ void __launch_bounds__(kGemmThreads) gemm_simt_kernel(GemmArgs g) {
 // out[m, perm(n)] (+)= sum_z partial[z][m][n] (+bias, relu) - fixed summation order.
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int64_t M, int64_t N,
                                      int64_t ldc, int splits, GemmEpilogue ep, int64_t ldp);
+int launch_splitk_reduce(const float* partial, float* C, int64_t M, int64_t N, int64_t ldc, int splits, const GemmEpilogue& ep,
+                         int64_t ldp, cudaStream_t stream);
 
 // Host launcher.  `splitk_scratch` must hold splits*M*N floats when splits > 1.
 template <typename AT, typename BT, bool TA, bool TB>

@@ -744,11 +744,7 @@ int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64
   if (rc) return rc;
   GemmEpilogue rep;
   rep.permP = permP; rep.permQ = permQ; rep.scale = scale;
-  const int64_t total = int64_t(O) * K;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;
-  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(partial, dW, O, K, K, int(splits), rep, K);
-  return check_launch("splitk_reduce_kernel");
+  return launch_splitk_reduce(partial, dW, O, K, K, int(splits), rep, K, stream);
 }
 
 int gemm_tc_bf16(const void* A, const void* B, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
@@ -793,11 +789,7 @@ int gemm_tc_bf16_ex(const void* A, const void* B, int64_t M, int64_t N, int64_t 
   TB_REQUIRE(ep.C, "gemm_tc: split-K reduce needs an fp32 output");
   GemmEpilogue rep;
   rep.bias = ep.bias; rep.relu = ep.relu; rep.permP = ep.permP; rep.permQ = ep.permQ; rep.scale = ep.scale;
-  const int64_t total = M * N;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > kNumSMsB200 * 8) blocks = kNumSMsB200 * 8;
-  splitk_reduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(part, ep.C, M, N, ep.ldc, splits, rep, (N + 31) & ~int64_t(31));
-  return check_launch("splitk_reduce_kernel");
+  return launch_splitk_reduce(part, ep.C, M, N, ep.ldc, splits, rep, (N + 31) & ~int64_t(31), stream);
 }
 
 // fp32 [rows, cols] (ld) -> bf16 [rows, cols16] (ld16), optional ReLU-free straight convert
