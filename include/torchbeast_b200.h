@@ -193,6 +193,24 @@ int tb_gemm_bf16_tn(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N
 int tb_gemm_bf16_ex(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N, int64_t K, int64_t lda,
                     int64_t ldb, int a_mn, int b_mn, float* C, int64_t ldc, int splits, float* partial,
                     void* stream);
+/* ---- implicit-GEMM convolutions (bf16 tensor-core backend) -------------------------------------------
+ * The nn.Conv2d layers of AtariNet (monobeast.py:560-562: 8x8/4, 4x4/2, 3x3/1, no padding) as tcgen05 GEMMs whose
+ * patch operand is read by TMA straight from the bf16 NHWC activation [Nf,H,W,C] (conv2/conv3) or gathered from a
+ * bf16 image of the uint8 NCHW frames (conv1) - no patch matrix is materialised.  weight / dweight are fp32 in the
+ * reference layout [O,C,KH,KW]; outputs bf16 NHWC.  *_scratch buffers are caller-owned device memory:
+ * pack_scratch_bf16 >= max(O,4*C)*KH*KW*max(C,O) bf16, partial >= 148*O*KH*KW*C floats, image_bf16 = N*4*H*W bf16. */
+int tb_conv_nhwc_bf16_fwd(const void* act_bf16, const float* weight, const float* bias, int64_t Nf, int H, int W, int C,
+                          int KH, int KW, int S, int O, int relu, void* out_bf16, void* pack_scratch_bf16, void* stream);
+/* dx = conv_transpose(dy, weight) * (act > 0)   (act_bf16 nullable: no ReLU mask); O must be 64, stride 1 or 2 (4x4) */
+int tb_conv_nhwc_bf16_dgrad(const void* dy_bf16, const float* weight, const void* act_bf16, int64_t Nf, int H, int W, int C,
+                            int KH, int KW, int S, int O, void* dx_bf16, void* pack_scratch_bf16, void* stream);
+int tb_conv_nhwc_bf16_wgrad(const void* dy_bf16, const void* act_bf16, int64_t Nf, int H, int W, int C, int KH, int KW, int S,
+                            int O, float* dweight, float* partial, int64_t partial_floats, void* stream);
+/* conv1: frame u8 [N,4,H,W] -> relu(conv(frame/255) + b) bf16 [N,OH,OW,32]; leaves the bf16 image for the wgrad */
+int tb_conv1_u8_fwd(const uint8_t* frame, const float* weight, const float* bias, int64_t N, int H, int W, int S, int relu,
+                    void* out_bf16, void* image_bf16, void* pack_scratch_bf16, void* stream);
+int tb_conv1_u8_wgrad(const void* dy_bf16, const void* image_bf16, int64_t N, int H, int W, int S, float* dweight,
+                      float* partial, int64_t partial_floats, void* stream);
 /* out_bf16[r, c] = bf16(in[r*ld + c]) for c < cols, 0 for cols <= c < ld16 (operand staging). */
 int tb_f32_to_bf16(const float* in, void* out_bf16, int64_t rows, int64_t cols, int64_t ld, int64_t ld16,
                    void* stream);

@@ -89,7 +89,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // global-load latency is exposed per tile, not per stage.
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep,
-                            ConvGeom g, int tiles_m, int dbg) {
+                            ConvGeom g, int tiles_m) {
   constexpr uint32_t B_BYTES = kO * kBlockK * 2;  // 4 KB per k-block
   constexpr uint32_t TMEM_COLS = 64;              // two 32-column accumulator buffers
   extern __shared__ uint8_t smem_raw[];
@@ -165,7 +165,7 @@ conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __gri
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty(ab));  // values are in registers: free the accumulator early
-      if (r < g.M && !(dbg & 2)) {
+      if (r < g.M) {
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -204,7 +204,7 @@ conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __gri
         const uint32_t dst = sA + stage * kTileBytes + c * kABytes + row_off;
         const __nv_bfloat16* src = src0 + int64_t(c) * g.H * g.W;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (!(dbg & 1)) copy8(dst + (uint32_t(j ^ rr) << 4), src + j * g.W);
+        for (int j = 0; j < 8; ++j) copy8(dst + (uint32_t(j ^ rr) << 4), src + j * g.W);
       }
       cp_commit();
       if (++stage == kStagesF) { stage = 0; phase ^= 1; }
@@ -238,7 +238,7 @@ conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __gri
 // gathered boxes (one per channel).  Gather thread p owns patch row p & 63 of channel p >> 6.
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_u8_wgrad_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __grid_constant__ CUtensorMap tmA, ConvGeom g,
-                              float* __restrict__ partial, int total_kb, int per, int dbg) {
+                              float* __restrict__ partial, int total_kb, int per) {
   constexpr uint32_t B_BYTES = kC * 8192;  // 32 KB
   constexpr uint32_t TMEM_COLS = 256;
   extern __shared__ uint8_t smem_raw[];
@@ -344,7 +344,6 @@ conv_u8_wgrad_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __g
       const uint32_t dst = sB + stage * B_BYTES + row_off;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        if (dbg & 1) continue;
         copy8(dst + (uint32_t(j ^ rr) << 4), srcA + j * g.W);
         copy8(dst + 2048u + (uint32_t(j ^ rr) << 4), srcB + j * g.W);  // row + 16: two 8-row groups further
       }
@@ -457,7 +456,7 @@ int conv_u8_fwd_implicit(const void* frame_bf16, const void* w_bf16, int64_t N, 
   const int64_t tiles = (g.M + kBlockM - 1) / kBlockM;
   TB_REQUIRE(tiles < (int64_t(1) << 31), "conv_u8_fwd_implicit: too many tiles");
   const int64_t grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
-  conv_u8_fwd_implicit_kernel<<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, mb, ep, g, int(tiles), getenv("TB_CONV_DBG") ? atoi(getenv("TB_CONV_DBG")) : 0);
+  conv_u8_fwd_implicit_kernel<<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, mb, ep, g, int(tiles));
   return check_launch("conv_u8_fwd_implicit_kernel");
 }
 
@@ -484,7 +483,7 @@ int conv_u8_wgrad_implicit(const void* dy_bf16, const void* frame_bf16, int64_t 
     TB_REQUIRE(e == cudaSuccess, "conv_u8_wgrad_implicit: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
   }
-  conv_u8_wgrad_implicit_kernel<<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, ma, g, partial, int(total_kb), int(per), getenv("TB_CONV_DBG") ? atoi(getenv("TB_CONV_DBG")) : 0);
+  conv_u8_wgrad_implicit_kernel<<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, ma, g, partial, int(total_kb), int(per));
   rc = check_launch("conv_u8_wgrad_implicit_kernel");
   if (rc) return rc;
   GemmEpilogue rep;
