@@ -445,10 +445,13 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   return v;
 }
 __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) {
-  // spin on cheap relaxed loads (an acquire load per poll costs an L1 invalidation each time - ncu showed
-  // CCTL.IVALL in the loop and ~30 % of the step stalled at the barrier), then ONE acquire fence
+  // Spin on cheap relaxed loads, then ONE acquire load: it reads a value written by the last red.release of the
+  // arrivals (or a later one in the same release sequence), which is what synchronizes this thread with every
+  // arriving CTA.  History: acquire loads in the spin cost an L1 invalidation per poll (30 % of the step at the
+  // barrier); relaxed spin + fence.acq_rel.gpu fixed that but the fence is a full MEMBAR.ALL.GPU - ncu showed the
+  // waiting thread spending as long in it (1.3 us) as in the release fence of the arrive.
   while (ld_relaxed_u32(ctr) < target) {}
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  (void)ld_acquire_u32(ctr);
   asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of other CTAs -> our bulk copies
 }
 
