@@ -199,6 +199,12 @@ def gemm_bytes_table(N, A, use_lstm, bf16):
         "conv2_dgrad": M2 * 64 * e + M2 * 512 * e, "conv3_dgrad": M3 * 64 * e + M3 * 576 * e,
         "fc_dgrad": N * 512 * e + 512 * 3136 * e + 2 * N * 3136 * e,
     }
+    if bf16:  # implicit-GEMM convolutions: the activation (or the bf16 frame image) is the operand - read once, no patch matrix
+        img = N * 28224 * 2
+        t.update({"conv1_fwd": img + M1 * 32 * 2, "conv1_wgrad": img + M1 * 32 * 2,
+                  "conv2_fwd": M1 * 32 * 2 + M2 * 64 * 2, "conv2_wgrad": M1 * 32 * 2 + M2 * 64 * 2,
+                  "conv3_fwd": M2 * 64 * 2 + M3 * 64 * 2, "conv3_wgrad": M2 * 64 * 2 + M3 * 64 * 2,
+                  "conv2_dgrad": M2 * 64 * 2 + 2 * M1 * 32 * 2, "conv3_dgrad": M3 * 64 * 2 + 2 * M2 * 64 * 2})  # dY + mask + dX
     if use_lstm:
         H = 512 + 1 + A
         t.update({"lstm_xproj_fwd": 2 * (N * H * e + 4 * H * H * e + N * 4 * H * 4),
@@ -503,8 +509,9 @@ def main():
                                     unit=dom["unit"], frac=dom["frac"],
                                     traffic=(traffic_tab.get(dom["op"], {}).get("dram_bytes_per_launch")),
                                     launches_per_step=dom["launches_per_step"], peak_source=pk["source"],
-                                    note=("latency-bound fp32 recurrence (grid barrier per time step), flops of the recurrent "
-                                          "products against the sustained bf16 tensor peak" if dom["op"].startswith("lstm_recurrence")
+                                    note=("latency-bound recurrence: T+1 dependent time steps, each a grid barrier + L2 tile fetch + bf16 "
+                                          "mma.sync product (~5 us per step); neither roofline is approached - the recurrent-product "
+                                          "flops are reported against the sustained bf16 tensor peak" if dom["op"].startswith("lstm_recurrence")
                                           else ("bf16 tcgen05 GEMM" if model.precision == "bf16" else "fp32 SIMT GEMM backend") +
                                           " against the sustained bf16 tensor-core peak"))
         # the V-trace kernels on their own (BASELINE.json metric: V-trace GB/s vs HBM peak)
