@@ -1307,6 +1307,226 @@ __global__ void __launch_bounds__(kStepThreads) lstm_bwd_persistent_mma_kernel(P
   }
 }
 
+// ---- two stacked layers, backward, as ONE wavefront -------------------------------------------
+// The lower layer at time t needs dL/d(its output)[t] = dgates_upper[t] . W_ih_upper, and the upper layer's CTAs
+// already hold the tile dgates_upper[t] in shared memory for their own recurrent product.  So the grid is
+// role-split: CTAs [0, nc) run the UPPER layer's recurrence (as lstm_bwd_persistent_mma_kernel) and, from the same
+// tile, ALSO produce their 8 columns of dL/dh_lower[t] (W_ih_upper^T fragments staged in shared memory);
+// CTAs [nc, 2nc) run the LOWER layer's recurrence two wave steps behind (the product for time t is written after
+// barrier s and must be visible before it is prefetched).  T+2 grid barriers instead of 2T, no hoisted
+// input-gradient GEMM for the upper layer, and 130 instead of 65 SMs busy.
+struct WaveBwdArgs {
+  const float* w_hh_up; const float* w_hh_lo; const float* w_ih_up;
+  const float* dy;                  // dL/d(upper output) [T1*B, H]
+  const float* nd;
+  const float* gates_up; const float* cs_up; const float* cm_up;
+  const float* gates_lo; const float* cs_lo; const float* cm_lo;
+  __nv_bfloat16* dgb_up; __nv_bfloat16* dgb_lo; int lg;
+  float* db_up; float* db_lo;
+  __nv_bfloat16* dgq_up; __nv_bfloat16* dgq_lo;   // each [2][4, B, Hq]
+  float* dxm;                       // [T1*B, H] dL/d(lower output): written by the upper role, read by the lower
+  unsigned* counter;
+  int T1, B, H, Hq; unsigned nc;    // nc = CTAs per role
+};
+
+__global__ void __launch_bounds__(kStepThreads) lstm2_bwd_wave_mma_kernel(WaveBwdArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_b[];
+  __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem_b);  // [4 gates][32][Hq]
+  __shared__ float part16_s[16][kBwdCols][33];
+  __shared__ float dh_s[kBwdCols][33];
+  __shared__ float dc_s[kBwdCols][33];
+  __shared__ __align__(16) __nv_bfloat16 stg_s[4][32][kBwdCols];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int H = a.H, Hq = a.Hq, B = a.B;
+  const bool upper = blockIdx.x < a.nc;
+  const int k0 = int(upper ? blockIdx.x : blockIdx.x - a.nc) * kBwdCols;
+  const int rows = B < 32 ? B : 32;
+  const int kpg = (H + 15) / 16;           // k16 steps per gate
+  const int ksteps = 4 * kpg;
+  const int kper = (ksteps + 15) / 16;
+  const int ks0 = wrp * kper, ks1 = (ks0 + kper < ksteps) ? ks0 + kper : ksteps;
+  uint2* Wih_s = reinterpret_cast<uint2*>(smem_b + size_t(4) * 32 * Hq * 2);  // [16 warps][kper][32 lanes] fragments
+  const float* const w_hh = upper ? a.w_hh_up : a.w_hh_lo;
+  const float* const gates = upper ? a.gates_up : a.gates_lo;
+  const float* const cs = upper ? a.cs_up : a.cs_lo;
+  const float* const cm = upper ? a.cm_up : a.cm_lo;
+  __nv_bfloat16* const dgb = upper ? a.dgb_up : a.dgb_lo;
+  __nv_bfloat16* const dgq = upper ? a.dgq_up : a.dgq_lo;
+  // B fragments: B[kk][n] = W[g*H + j][k0 + n], kk = g*kpg*16 + j  (W = this role's W_hh; the upper role also
+  // stages the same fragments of W_ih_upper in shared memory)
+  auto load_frag = [&](const float* w, int st, uint32_t& f0, uint32_t& f1) {
+    const int g = st / kpg, j = (st % kpg) * 16 + (lane & 3) * 2;
+    const int n = lane >> 2;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (st < ks1 && k0 + n < H) {
+      const float* wc = w + int64_t(g) * H * H + (k0 + n);
+      if (j < H) v[0] = wc[int64_t(j) * H];
+      if (j + 1 < H) v[1] = wc[int64_t(j + 1) * H];
+      if (j + 8 < H) v[2] = wc[int64_t(j + 8) * H];
+      if (j + 9 < H) v[3] = wc[int64_t(j + 9) * H];
+    }
+    f0 = pack_bf16(v[0], v[1]);
+    f1 = pack_bf16(v[2], v[3]);
+  };
+  uint32_t bf[kMaxKStepsBwd][2];
+#pragma unroll
+  for (int s = 0; s < kMaxKStepsBwd; ++s) load_frag(w_hh, ks0 + s, bf[s][0], bf[s][1]);
+  if (upper) {
+    for (int s = 0; s < kper; ++s) {
+      uint32_t f0, f1;
+      load_frag(a.w_ih_up, ks0 + s, f0, f1);
+      Wih_s[(wrp * kper + s) * 32 + lane] = make_uint2(f0, f1);
+    }
+  }
+  if (wrp < kBwdCols) { dh_s[wrp][lane] = 0.0f; dc_s[wrp][lane] = 0.0f; }
+  __syncthreads();
+  const int64_t gs = int64_t(B) * Hq;
+  const int chunks_per_row = Hq / 8;
+  uint4* Xs4 = reinterpret_cast<uint4*>(Xs);
+  const int q = wrp;  // pointwise role: thread = (batch row lane, unit k0 + wrp)
+  const bool actA = (wrp < kBwdCols && lane < rows && k0 + q < H);
+  // role time line: the upper layer handles t = T1-1-s at wave step s, the lower layer t = T1+1-s
+  auto time_of = [&](int s) { return upper ? a.T1 - 1 - s : a.T1 + 1 - s; };
+  float n_ig = 0.f, n_fg = 0.f, n_gg = 0.f, n_og = 0.f, n_dy = 0.f, n_cs = 0.f, n_cm = 0.f, n_nd = 0.f, n_ndn = 0.f;
+  auto prefetch = [&](int t) {
+    if (!actA || t < 0 || t >= a.T1) return;
+    const int64_t r0 = int64_t(t) * B;
+    const int64_t i = (r0 + lane) * H + k0 + q, g = (r0 + lane) * 4 * H + k0 + q;
+    n_ig = gates[g]; n_fg = gates[g + H]; n_gg = gates[g + 2 * H]; n_og = gates[g + 3 * H];
+    if (upper) n_dy = a.dy[i];  // the lower role's dy comes from the upper role: fetched AFTER the barrier (fetch_dxm)
+    n_cs = cs[i]; n_cm = cm[i]; n_nd = a.nd[r0 + lane];
+    n_ndn = (t + 1 < a.T1) ? a.nd[r0 + B + lane] : 0.f;
+  };
+  auto fetch_dxm = [&](int t) {
+    if (upper || !actA || t < 0 || t >= a.T1) return;
+    n_dy = __ldcg(a.dxm + (int64_t(t) * B + lane) * H + k0 + q);
+  };
+  if (upper) prefetch(a.T1 - 1);
+  float bs_i = 0.f, bs_f = 0.f, bs_g = 0.f, bs_o = 0.f;
+  auto store_dg = [&](int64_t row, float p_i, float p_f, float p_g, float p_o) {
+    __nv_bfloat16* d = dgb + row * a.lg + k0 + q;
+    d[0] = __float2bfloat16_rn(p_i); d[H] = __float2bfloat16_rn(p_f);
+    d[2 * H] = __float2bfloat16_rn(p_g); d[3 * H] = __float2bfloat16_rn(p_o);
+  };
+  const int last_s = a.T1 + 1;
+  int it = 0;  // this role's active-step counter
+  for (int s = 0; s <= last_s; ++s) {
+    const int t = time_of(s);
+    const bool active = (t >= 0 && t < a.T1);
+    const int64_t row0 = int64_t(active ? t : 0) * B;
+    __nv_bfloat16* dgq_t = dgq + int64_t(it & 1) * 4 * gs;
+    float p_i = 0.f, p_f = 0.f, p_g = 0.f, p_o = 0.f;
+    if (active) {
+      if (actA) {
+        const float ig = n_ig, fg = n_fg, gg = n_gg, og = n_og;
+        float dh = n_dy;
+        float dc = 0.0f;
+        if (it > 0) {
+          dh += dh_s[q][lane] * n_ndn;
+          dc = dc_s[q][lane];
+        }
+        const float tc = tanhf(n_cs);
+        const float d_o = dh * tc;
+        dc += dh * og * (1.0f - tc * tc);
+        const float d_i = dc * gg, d_f = dc * n_cm, d_g = dc * ig;
+        p_i = d_i * ig * (1.0f - ig); p_f = d_f * fg * (1.0f - fg);
+        p_g = d_g * (1.0f - gg * gg); p_o = d_o * og * (1.0f - og);
+        dc_s[q][lane] = dc * fg * n_nd;
+        bs_i += p_i; bs_f += p_f; bs_g += p_g; bs_o += p_o;
+      }
+      // publish this CTA's 8 columns of the four gate-gradient tiles (16-byte stores staged through smem)
+      if (wrp < kBwdCols) {
+        stg_s[0][lane][q] = __float2bfloat16_rn(p_i); stg_s[1][lane][q] = __float2bfloat16_rn(p_f);
+        stg_s[2][lane][q] = __float2bfloat16_rn(p_g); stg_s[3][lane][q] = __float2bfloat16_rn(p_o);
+      }
+      __syncthreads();
+      if (tid < 128 && (tid & 31) < rows) {
+        const int g = tid >> 5, bb = tid & 31;
+        *reinterpret_cast<uint4*>(dgq_t + int64_t(g) * gs + int64_t(bb) * Hq + k0) = *reinterpret_cast<const uint4*>(&stg_s[g][bb][0]);
+      }
+    }
+    if (s == last_s) {
+      if (active && actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
+      break;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      red_release_add(a.counter, 1u);
+      grid_wait(a.counter, unsigned(s + 1) * 2u * a.nc);
+    }
+    if (active && actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
+    prefetch(time_of(s + 1));  // forward-pass operands only: overlaps the barrier wait
+    __syncthreads();
+    fetch_dxm(time_of(s + 1));  // written by the upper role before it arrived at this barrier
+    // post-barrier products from the tile this role published at this wave step: the recurrent carry for time t-1,
+    // and (upper role) dL/dh_lower[t]
+    const bool need_rec = active && t > 0;
+    const bool need_dx = active && upper;
+    if (need_rec || need_dx) {
+      const int nchunk = rows * chunks_per_row;
+#pragma unroll
+      for (int gg = 0; gg < 4; ++gg) {
+        const uint4* src = reinterpret_cast<const uint4*>(dgq_t + int64_t(gg) * gs);
+        uint4* dst = Xs4 + int64_t(gg) * 32 * chunks_per_row;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+          const int i = tid + u * kStepThreads;
+          if (i < nchunk) cp_async16(dst + i, src + i);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 0 ? !need_rec : !need_dx) continue;
+        float acc[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[mt][e] = 0.f;
+#pragma unroll
+        for (int sk = 0; sk < kMaxKStepsBwd; ++sk) {
+          const int st = ks0 + sk;
+          if (st < ks1) {
+            const int g = st / kpg, kk = (st % kpg) * 16;
+            uint32_t f0 = bf[sk][0], f1 = bf[sk][1];
+            if (pass == 1) { const uint2 w = Wih_s[(wrp * kper + sk) * 32 + lane]; f0 = w.x; f1 = w.y; }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              uint32_t af[4];
+              ldmatrix_x4(af, Xs + (int64_t(g) * 32 + mt * 16 + (lane & 15)) * Hq + kk + (lane >> 4) * 8);
+              mma_bf16_16816(acc[mt], af, f0, f1);
+            }
+          }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+          part16_s[wrp][c][r] = acc[mt][0]; part16_s[wrp][c + 1][r] = acc[mt][1];
+          part16_s[wrp][c][r + 8] = acc[mt][2]; part16_s[wrp][c + 1][r + 8] = acc[mt][3];
+        }
+        __syncthreads();
+        if (wrp < kBwdCols) {
+          float d = 0.f;
+#pragma unroll
+          for (int sidx = 0; sidx < 16; ++sidx) d += part16_s[sidx][wrp][lane];
+          if (pass == 0) dh_s[wrp][lane] = d;
+          else if (lane < rows && k0 + wrp < H) a.dxm[(row0 + lane) * H + k0 + wrp] = d;
+        }
+        __syncthreads();
+      }
+    }
+    if (active) ++it;
+  }
+  if (wrp < kBwdCols) {
+    bs_i = warp_sum(bs_i); bs_f = warp_sum(bs_f); bs_g = warp_sum(bs_g); bs_o = warp_sum(bs_o);
+    float* db = upper ? a.db_up : a.db_lo;
+    if (lane == 0 && k0 + q < H) {
+      db[k0 + q] = bs_i; db[H + k0 + q] = bs_f; db[2 * H + k0 + q] = bs_g; db[3 * H + k0 + q] = bs_o;
+    }
+  }
+}
+
 // hmq[0][b][:] = bf16(h0 * nd_0), zero padded; cm[0] = c0 * nd_0
 __global__ void lstm_init_state_q_kernel(const float* __restrict__ h0, const float* __restrict__ c0,
                                          const float* __restrict__ nd, __nv_bfloat16* __restrict__ hmq,
@@ -1421,6 +1641,49 @@ static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, cons
   e = cudaLaunchCooperativeKernel((const void*)lstm_bwd_persistent_mma_kernel, grid, dim3(kStepThreads), args, smem, st);
   TB_REQUIRE(e == cudaSuccess, "lstm_bwd_persistent_mma_kernel: %s", cudaGetErrorString(e));
   return check_launch("lstm_bwd_persistent_mma_kernel");
+}
+
+static size_t g_bwd_wave_attr = 0;
+static size_t wave_bwd_smem(int H) {
+  const int kper = (4 * ((H + 15) / 16) + 15) / 16;
+  return size_t(4) * 32 * mma_hq(H) * 2 + size_t(16) * kper * 32 * 8;
+}
+static bool wave_bwd_applicable(int64_t B, int H) {
+  const char* e = getenv("TB_LSTM_WAVE_BWD");
+  if (e && e[0] == '0') return false;
+  if (!mma_recurrence_applicable(B, H)) return false;
+  dim3 grid(2 * ((H + kBwdCols - 1) / kBwdCols), 1);
+  return coop_fit(lstm2_bwd_wave_mma_kernel, grid, wave_bwd_smem(H), &g_bwd_wave_attr);
+}
+
+// both layers' backward recurrences in one launch; leaves dgb / bias gradients of both layers and
+// ws.dx_mid = dL/d(lower layer output)
+static int lstm2_bwd_wave(LstmWs& ws, const LstmParams& p, const LstmGrads& g, const float* dy, const float* notdone, int64_t T1,
+                          int64_t B, int H, cudaStream_t st) {
+  const int Hq = mma_hq(H);
+  const unsigned nc = unsigned((H + kBwdCols - 1) / kBwdCols);
+  const LstmLayerWs& U = ws.layer[1];
+  const LstmLayerWs& L = ws.layer[0];
+  unsigned* counter = ws.sync + 32;
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(U.dgq, 0, size_t(2) * 4 * B * Hq * 2, st);  // zero the row padding
+  if (e == cudaSuccess) e = cudaMemsetAsync(L.dgq, 0, size_t(2) * 4 * B * Hq * 2, st);
+  TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
+  WaveBwdArgs a;
+  a.w_hh_up = p.w_hh[1]; a.w_hh_lo = p.w_hh[0]; a.w_ih_up = p.w_ih[1];
+  a.dy = dy; a.nd = notdone;
+  a.gates_up = U.gates; a.cs_up = U.cs; a.cm_up = U.cm;
+  a.gates_lo = L.gates; a.cs_lo = L.cs; a.cm_lo = L.cm;
+  a.dgb_up = static_cast<__nv_bfloat16*>(U.dgb); a.dgb_lo = static_cast<__nv_bfloat16*>(L.dgb); a.lg = int(ld16(4 * H));
+  a.db_up = g.b_ih[1]; a.db_lo = g.b_ih[0];
+  a.dgq_up = static_cast<__nv_bfloat16*>(U.dgq); a.dgq_lo = static_cast<__nv_bfloat16*>(L.dgq);
+  a.dxm = ws.dx_mid; a.counter = counter;
+  a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nc = nc;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)lstm2_bwd_wave_mma_kernel, dim3(2 * nc), dim3(kStepThreads), args,
+                                  wave_bwd_smem(H), st);
+  TB_REQUIRE(e == cudaSuccess, "lstm2_bwd_wave_mma_kernel: %s", cudaGetErrorString(e));
+  return check_launch("lstm2_bwd_wave_mma_kernel");
 }
 
 // Side stream for work that can run beside a recurrence kernel (which occupies only H/8 = 65 of the 148 SMs):
@@ -1588,6 +1851,14 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
   const int64_t scratch = int64_t(8) << 20;  // == kSplitKScratchFloats (atarinet.cu)
   const float* dyl = dy;
   bool forked = false;
+  // two layers on the tensor-core backend: ONE wavefront kernel runs both recurrences (and the upper layer's
+  // input-gradient product); only the hoisted weight-gradient GEMMs and the lower layer's dx remain per layer
+  bool wave_done = false;
+  if (precision && layers == 2 && In <= H && wave_bwd_applicable(B, H)) {
+    ProfScope prof("lstm_recurrence_bwd", st);
+    TB_TRY(lstm2_bwd_wave(ws, p, g, dy, notdone, T1, B, H, st));
+    wave_done = true;
+  }
   for (int l = layers - 1; l >= 0; --l) {
     LstmLayerWs& L = ws.layer[l];
     const float* xin = (l == 0) ? x : ws.layer[l - 1].hs;
@@ -1602,7 +1873,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       cudaError_t em = cudaMemsetAsync(ws.dgp, 0, sizeof(float) * 4 * B * Hp, st);  // zero the row padding
       TB_REQUIRE(em == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(em));
     }
-    {
+    if (!wave_done) {
     ProfScope prof("lstm_recurrence_bwd", st);
     int prc = -1;
     if (use_mma) {
@@ -1652,7 +1923,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       // The weight-gradient GEMMs of the UPPER layer do not feed the lower layer's recurrence (only dx does), and that
       // recurrence occupies 65 SMs: run them on a side stream with a grid capped to the idle SMs and join before the
       // split-K scratch is needed again.
-      SideStream* side = (use_mma && l == 1 && layers == 2) ? side_stream() : nullptr;
+      SideStream* side = (use_mma && l == 1 && layers == 2 && !wave_done) ? side_stream() : nullptr;
       cudaStream_t gs = st;
       TcEpilogue te; te.tag = "lstm_wgrad";
       if (side) {
@@ -1675,8 +1946,10 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
         TB_REQUIRE(e == cudaSuccess, "lstm: side stream join: %s", cudaGetErrorString(e));
       }
       // dx[N,in] = dgates[N,4H] . W_ih[4H,in]   (W_ih as stored: reduction index is its row index)
-      TcEpilogue td; td.tag = "lstm_xproj_dgrad"; td.C = dxl; td.ldc = in_dim;
-      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.wihb, N, in_dim, 4 * H, lg, li, false, true, td, 1, nullptr, st));
+      if (!(wave_done && l == 1)) {  // the wavefront kernel already produced the upper layer's dx (= ws.dx_mid)
+        TcEpilogue td; td.tag = "lstm_xproj_dgrad"; td.C = dxl; td.ldc = in_dim;
+        TB_TRY(gemm_tc_bf16_ex(L.dgb, L.wihb, N, in_dim, 4 * H, lg, li, false, true, td, 1, nullptr, st));
+      }
     } else {
     GemmEpilogue ep; ep.tag = "lstm_wgrad";
     int s = splits_for(4 * H, H, N, scratch);
