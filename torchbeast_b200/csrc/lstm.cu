@@ -1333,6 +1333,7 @@ __global__ void __launch_bounds__(kStepThreads) lstm2_bwd_wave_mma_kernel(WaveBw
   extern __shared__ __align__(128) unsigned char smem_b[];
   __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(smem_b);  // [4 gates][32][Hq]
   __shared__ float part16_s[16][kBwdCols][33];
+  __shared__ float part16b_s[16][kBwdCols][33];
   __shared__ float dh_s[kBwdCols][33];
   __shared__ float dc_s[kBwdCols][33];
   __shared__ __align__(16) __nv_bfloat16 stg_s[4][32][kBwdCols];
@@ -1477,44 +1478,53 @@ __global__ void __launch_bounds__(kStepThreads) lstm2_bwd_wave_mma_kernel(WaveBw
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncthreads();
-      for (int pass = 0; pass < 2; ++pass) {
-        if (pass == 0 ? !need_rec : !need_dx) continue;
-        float acc[2][4];
+      // one sweep over the tile feeds both products (the A fragments are loaded once): acc0 with this role's W_hh^T
+      // fragments (registers) -> recurrent carry, acc1 with W_ih_upper^T fragments (shared memory) -> dL/dh_lower
+      float acc0[2][4], acc1[2][4];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[mt][e] = 0.f;
+        for (int e = 0; e < 4; ++e) { acc0[mt][e] = 0.f; acc1[mt][e] = 0.f; }
 #pragma unroll
-        for (int sk = 0; sk < kMaxKStepsBwd; ++sk) {
-          const int st = ks0 + sk;
-          if (st < ks1) {
-            const int g = st / kpg, kk = (st % kpg) * 16;
-            uint32_t f0 = bf[sk][0], f1 = bf[sk][1];
-            if (pass == 1) { const uint2 w = Wih_s[(wrp * kper + sk) * 32 + lane]; f0 = w.x; f1 = w.y; }
+      for (int sk = 0; sk < kMaxKStepsBwd; ++sk) {
+        const int st = ks0 + sk;
+        if (st < ks1) {
+          const int g = st / kpg, kk = (st % kpg) * 16;
+          uint2 w = make_uint2(0u, 0u);
+          if (need_dx) w = Wih_s[(wrp * kper + sk) * 32 + lane];
 #pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-              uint32_t af[4];
-              ldmatrix_x4(af, Xs + (int64_t(g) * 32 + mt * 16 + (lane & 15)) * Hq + kk + (lane >> 4) * 8);
-              mma_bf16_16816(acc[mt], af, f0, f1);
-            }
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t af[4];
+            ldmatrix_x4(af, Xs + (int64_t(g) * 32 + mt * 16 + (lane & 15)) * Hq + kk + (lane >> 4) * 8);
+            if (need_rec) mma_bf16_16816(acc0[mt], af, bf[sk][0], bf[sk][1]);
+            if (need_dx) mma_bf16_16816(acc1[mt], af, w.x, w.y);
           }
         }
+      }
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-          const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
-          part16_s[wrp][c][r] = acc[mt][0]; part16_s[wrp][c + 1][r] = acc[mt][1];
-          part16_s[wrp][c][r + 8] = acc[mt][2]; part16_s[wrp][c + 1][r + 8] = acc[mt][3];
-        }
-        __syncthreads();
-        if (wrp < kBwdCols) {
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+        part16_s[wrp][c][r] = acc0[mt][0]; part16_s[wrp][c + 1][r] = acc0[mt][1];
+        part16_s[wrp][c][r + 8] = acc0[mt][2]; part16_s[wrp][c + 1][r + 8] = acc0[mt][3];
+        part16b_s[wrp][c][r] = acc1[mt][0]; part16b_s[wrp][c + 1][r] = acc1[mt][1];
+        part16b_s[wrp][c][r + 8] = acc1[mt][2]; part16b_s[wrp][c + 1][r + 8] = acc1[mt][3];
+      }
+      __syncthreads();
+      if (wrp < kBwdCols) {            // warps 0..7: recurrent carry
+        if (need_rec) {
           float d = 0.f;
 #pragma unroll
           for (int sidx = 0; sidx < 16; ++sidx) d += part16_s[sidx][wrp][lane];
-          if (pass == 0) dh_s[wrp][lane] = d;
-          else if (lane < rows && k0 + wrp < H) a.dxm[(row0 + lane) * H + k0 + wrp] = d;
+          dh_s[wrp][lane] = d;
         }
-        __syncthreads();
+      } else if (need_dx) {            // warps 8..15: dL/dh_lower[t], this CTA's 8 columns
+        const int cw = wrp - kBwdCols;
+        float d = 0.f;
+#pragma unroll
+        for (int sidx = 0; sidx < 16; ++sidx) d += part16b_s[sidx][cw][lane];
+        if (lane < rows && k0 + cw < H) a.dxm[(row0 + lane) * H + k0 + cw] = d;
       }
+      __syncthreads();
     }
     if (active) ++it;
   }
