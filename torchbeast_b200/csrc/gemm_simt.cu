@@ -3,36 +3,58 @@
 
 namespace tb {
 
-// grid (ceil(N / 256), rows): one output row per blockIdx.y (grid-stride over rows), one column per thread - no
-// 64-bit div/mod per element, the split loop unrolled so `splits` loads are in flight.
+// Thread = 4 consecutive columns of one output row (one 16-byte load per split when the partial rows are
+// 16-byte aligned), block = 128 threads x 4 rows; no 64-bit div/mod, the split loop keeps `splits` loads in flight.
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* __restrict__ C, int64_t M, int64_t N,
                                      int64_t ldc, int splits, GemmEpilogue ep, int64_t ldp) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  const int n0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (n0 >= N) return;
   const int64_t slice = M * ldp;  // partial rows are ldp floats apart (ldp >= N: padded so the GEMM stores 16 bytes)
-  int nd = n;
-  if (ep.permP > 1 || ep.permQ > 1) {
-    const int p = n / ep.permQ, q = n - p * ep.permQ;
-    nd = q * ep.permP + p;
+  const bool vec = (ldp & 3) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0 && n0 + 4 <= ldp;
+  const int nv = (N - n0 < 4) ? int(N - n0) : 4;
+  int nd[4]; float bias[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + j;
+    nd[j] = n;
+    if ((ep.permP > 1 || ep.permQ > 1) && j < nv) {
+      const int p = n / ep.permQ, q = n - p * ep.permQ;
+      nd[j] = q * ep.permP + p;
+    }
+    bias[j] = (ep.bias && j < nv) ? __ldg(ep.bias + n) : 0.0f;
   }
-  const float b = ep.bias ? __ldg(ep.bias + n) : 0.0f;
-  for (int64_t m = blockIdx.y; m < M; m += gridDim.y) {
-    const float* p = partial + m * ldp + n;
-    float v = 0.0f;
+  for (int64_t m = int64_t(blockIdx.y) * blockDim.y + threadIdx.y; m < M; m += int64_t(gridDim.y) * blockDim.y) {
+    const float* p = partial + m * ldp + n0;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (vec) {
 #pragma unroll 4
-    for (int z = 0; z < splits; ++z) v += __ldg(p + int64_t(z) * slice);
-    v = v * ep.scale + b;
-    if (ep.relu) v = fmaxf(v, 0.0f);
-    float* c = C + m * ldc + nd;
-    *c = ep.accumulate ? (*c + v) : v;
+      for (int z = 0; z < splits; ++z) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p + int64_t(z) * slice));
+        v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+      }
+    } else {
+      for (int z = 0; z < splits; ++z)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j < nv) v[j] += __ldg(p + int64_t(z) * slice + j);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j >= nv) break;
+      float x = v[j] * ep.scale + bias[j];
+      if (ep.relu) x = fmaxf(x, 0.0f);
+      float* c = C + m * ldc + nd[j];
+      *c = ep.accumulate ? (*c + x) : x;
+    }
   }
 }
 
 int launch_splitk_reduce(const float* partial, float* C, int64_t M, int64_t N, int64_t ldc, int splits, const GemmEpilogue& ep,
                          int64_t ldp, cudaStream_t stream) {
   if (M == 0 || N == 0) return 0;
-  dim3 grid((unsigned)((N + 255) / 256), (unsigned)(M < 65535 ? M : 65535));
-  splitk_reduce_kernel<<<grid, 256, 0, stream>>>(partial, C, M, N, ldc, splits, ep, ldp);
+  const int64_t gy = (M + 3) / 4;
+  dim3 grid((unsigned)((N + 511) / 512), (unsigned)(gy < 65535 ? gy : 65535));
+  splitk_reduce_kernel<<<grid, dim3(128, 4), 0, stream>>>(partial, C, M, N, ldc, splits, ep, ldp);
   return check_launch("splitk_reduce_kernel");
 }
 
