@@ -371,7 +371,10 @@ static int atarinet_backward(const float* grad_logits, const float* grad_baselin
     TB_TRY(lstm_backward(w.dcore_out, w.core_in, notdone, lp, lg, T1, B, pp.core, pp.core, 2, w.lstm, w.dcore_in,
                          w.splitk, w.colsum_scratch, precision, st));
   }
-  if (precision) return atarinet_backward_trunk_bf16(P, G_, pp, w, N, st);
+  if (precision) {
+    TB_TRY(atarinet_backward_trunk_bf16(P, G_, pp, w, N, st));
+    return lstm_backward_join(st);  // the LSTM weight-gradient GEMMs ran beside the trunk backward
+  }
   // fc: ReLU mask on the first 512 columns, wgrad (un-packed into [o, c, (h,w)]), bias, dgrad (+ReLU mask of act3)
   TB_TRY(relu_mask_inplace(w.dcore_in, w.core_in, N, G::FC_OUT, pp.core, pp.core, st));
   TB_TRY(wgrad(w.dcore_in, pp.core, w.act3, false, G::FC_IN, G_ + pp.fc_w, N, G::FC_OUT, G::FC_IN, G::H3 * G::W3,

@@ -64,6 +64,7 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
   }
   w.dh = takef(B * H); w.dc = takef(B * H);
   w.dx_mid = takef(N * (H > In ? H : In));
+  w.wg_scratch = (precision && layers == 2) ? takef(int64_t(4) * 4 * H * (((H > In ? H : In) + 31) & ~31)) : nullptr;
   w.dgp = takef(int64_t(2) * 4 * B * padded_h(H));
   w.sync = reinterpret_cast<unsigned*>(takef(64));
   w.Hp = padded_h(H);
@@ -1854,6 +1855,16 @@ static int splits_for(int64_t M, int64_t N, int64_t K, int64_t scratch_floats) {
   return int(s);
 }
 
+static thread_local SideStream* g_pending_join = nullptr;
+
+int lstm_backward_join(cudaStream_t st) {
+  if (!g_pending_join) return 0;
+  cudaError_t e = cudaStreamWaitEvent(st, g_pending_join->join, 0);
+  g_pending_join = nullptr;
+  TB_REQUIRE(e == cudaSuccess, "lstm: side stream join: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int lstm_backward(const float* dy, const float* x, const float* notdone, const LstmParams& p, const LstmGrads& g,
                   int64_t T1, int64_t B, int In, int H, int layers, LstmWs& ws, float* dx, float* splitk,
                   float* colsum_scratch, int precision, cudaStream_t st) {
@@ -1868,6 +1879,16 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     ProfScope prof("lstm_recurrence_bwd", st);
     TB_TRY(lstm2_bwd_wave(ws, p, g, dy, notdone, T1, B, H, st));
     wave_done = true;
+  }
+  // After the wavefront kernel only the hoisted weight-gradient GEMMs of both layers (and the lower layer's dx) remain.
+  // The GEMMs feed nothing downstream in this backward pass: fork them onto the side stream (own split-K scratch, grid
+  // capped so the caller's critical path keeps most SMs); the caller joins with lstm_backward_join().
+  SideStream* tail = (wave_done && ws.wg_scratch) ? side_stream() : nullptr;
+  if (tail) {
+    TB_TRY(lstm_backward_join(st));  // a previous call's fork must be joined before its event is reused
+    cudaError_t ee = cudaEventRecord(tail->fork, st);
+    if (ee == cudaSuccess) ee = cudaStreamWaitEvent(tail->stream, tail->fork, 0);
+    TB_REQUIRE(ee == cudaSuccess, "lstm: side stream fork: %s", cudaGetErrorString(ee));
   }
   for (int l = layers - 1; l >= 0; --l) {
     LstmLayerWs& L = ws.layer[l];
@@ -1935,7 +1956,9 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       // split-K scratch is needed again.
       SideStream* side = (use_mma && l == 1 && layers == 2 && !wave_done) ? side_stream() : nullptr;
       cudaStream_t gs = st;
+      float* wscr = splitk;
       TcEpilogue te; te.tag = "lstm_wgrad";
+      if (tail) { gs = tail->stream; wscr = ws.wg_scratch; te.max_ctas = 64; }
       if (side) {
         cudaError_t ee = cudaEventRecord(side->fork, st);
         if (ee == cudaSuccess) ee = cudaStreamWaitEvent(side->stream, side->fork, 0);
@@ -1945,9 +1968,9 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
         forked = true;
       }
       te.C = g.w_hh[l]; te.ldc = H;      // dW_hh[4H,H] = dgates^T . hm   (both operands stored [N, .]: MN-major)
-      TB_TRY(gemm_tc_bf16_ex(L.dgb, hm_b, 4 * H, H, N, lg, hm_ld, true, true, te, sp, splitk, gs));
+      TB_TRY(gemm_tc_bf16_ex(L.dgb, hm_b, 4 * H, H, N, lg, hm_ld, true, true, te, sp, wscr, gs));
       te.C = g.w_ih[l]; te.ldc = in_dim;  // dW_ih[4H,in] = dgates^T . x
-      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.xb, 4 * H, in_dim, N, lg, li, true, true, te, sp, splitk, gs));
+      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.xb, 4 * H, in_dim, N, lg, li, true, true, te, sp, wscr, gs));
       if (!use_mma) TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));
       cudaError_t e = cudaMemcpyAsync(g.b_hh[l], g.b_ih[l], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, gs);
       TB_REQUIRE(e == cudaSuccess, "lstm: bias grad copy: %s", cudaGetErrorString(e));
@@ -1977,6 +2000,11 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
                                                    nullptr, st)));
     }
     dyl = dxl;
+  }
+  if (tail) {
+    cudaError_t e = cudaEventRecord(tail->join, tail->stream);
+    TB_REQUIRE(e == cudaSuccess, "lstm: side stream join: %s", cudaGetErrorString(e));
+    g_pending_join = tail;
   }
   return 0;
 }

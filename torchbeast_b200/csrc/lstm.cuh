@@ -41,6 +41,8 @@ struct LstmWs {
   float* dc;      // [B, H] carry
   float* dx_mid;  // [T1*B, H] gradient w.r.t. the output of layer 0 (input of layer 1)
   unsigned* sync; // [64] grid-barrier counters of the persistent recurrence kernels (zeroed per launch)
+  float* wg_scratch;  // split-K scratch private to the weight-gradient GEMMs (two layers, bf16 backend): lets them run on a
+                      // side stream beside the caller's trunk backward, which uses the caller's scratch
   float* dgp;     // [2][4, B, Hp] (double-buffered for the persistent backward)
   //               this step's gate gradients, gate-major and zero padded (recurrent product operand)
   int Hp = 0;     // padded row length of hm / wp
@@ -59,6 +61,10 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
                  float* splitk, int precision, cudaStream_t stream);
 
 // dy [T1*B, H] -> dx [T1*B, In]; parameter gradients written (overwritten) into g.
+// Joins the side stream lstm_backward may have forked (weight-gradient GEMMs overlapping the caller's own backward):
+// call on the same stream after the work that may overlap, before anything consumes the LSTM parameter gradients.
+int lstm_backward_join(cudaStream_t stream);
+
 int lstm_backward(const float* dy, const float* x, const float* notdone, const LstmParams& p, const LstmGrads& g,
                   int64_t T1, int64_t B, int In, int H, int layers, LstmWs& ws, float* dx, float* splitk,
                   float* colsum_scratch, int precision, cudaStream_t stream);
