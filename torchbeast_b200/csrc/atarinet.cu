@@ -34,6 +34,21 @@ struct AtariGeom {
   static constexpr int KD3 = K3 * K3 * C2;  // 576
 };
 
+// Which convolutions run as implicit GEMMs (bf16 backend).  Decided ONCE per process (the environment switches are
+// read at the first call): the workspace layout depends on it - without patch matrices the conv-side buffers shrink
+// from 1.5 GB to 0.35 GB at N = 2592 - so forward, backward and tb_atarinet_workspace_bytes must agree.
+struct ImplicitPlan { bool conv1, conv2, conv3, dgrad2, dgrad3; };
+static const ImplicitPlan& implicit_plan() {
+  using G = AtariGeom;
+  static const ImplicitPlan p = {
+      conv_u8_implicit_applicable(G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, G::C1),
+      conv_tc_implicit_applicable(G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2),
+      conv_tc_implicit_applicable(G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3),
+      conv_tc_dgrad_implicit_applicable(G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2),
+      conv_tc_dgrad_implicit_applicable(G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3)};
+  return p;
+}
+
 struct AtariParams {  // offsets (in floats) into the flat parameter / gradient buffers
   int64_t conv1_w, conv1_b, conv2_w, conv2_b, conv3_w, conv3_b, fc_w, fc_b;
   int64_t lstm[2][4];  // per layer: w_ih, w_hh, b_ih, b_hh
@@ -107,12 +122,18 @@ static AtariWs atari_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int
     w.dact3 = takef(N * G::FC_IN); w.dcol3 = takef(M3 * G::KD3); w.dact2 = takef(M2 * G::C2);
     w.dcol2 = takef(M2 * G::KD2); w.dact1 = takef(M1 * G::C1);
   } else {
-    w.col1b = takeh(M1 * G::KD1); w.act1b = takeh(M1 * G::C1); w.col2b = takeh(M2 * G::KD2); w.act2b = takeh(M2 * G::C2);
-    w.col3b = takeh(M3 * G::KD3); w.act3b = takeh(N * G::FC_IN);
+    const ImplicitPlan& ip = implicit_plan();
+    // col1b: the bf16 frame image (implicit conv1) or the conv1 patch matrix; col2b/col3b exist only for the patch-matrix
+    // fallback; dcol2b/dcol3b hold the transposed weight packs of the implicit input gradients or the gradient matrices
+    w.col1b = takeh(ip.conv1 ? N * G::C0 * G::H0 * G::W0 : M1 * G::KD1); w.act1b = takeh(M1 * G::C1);
+    w.col2b = takeh(ip.conv2 ? 8 : M2 * G::KD2); w.act2b = takeh(M2 * G::C2);
+    w.col3b = takeh(ip.conv3 ? 8 : M3 * G::KD3); w.act3b = takeh(N * G::FC_IN);
     w.w1b = takeh(int64_t(G::C1) * G::KD1); w.w2b = takeh(int64_t(G::C2) * G::KD2); w.w3b = takeh(int64_t(G::C3) * G::KD3);
     w.wfcb = takeh(int64_t(G::FC_OUT) * G::FC_IN);
-    w.dfcb = takeh(N * G::FC_OUT); w.dact3b = takeh(N * G::FC_IN); w.dcol3b = takeh(M3 * G::KD3);
-    w.dact2b = takeh(M2 * G::C2); w.dcol2b = takeh(M2 * G::KD2); w.dact1b = takeh(M1 * G::C1);
+    w.dfcb = takeh(N * G::FC_OUT); w.dact3b = takeh(N * G::FC_IN);
+    w.dcol3b = takeh(ip.dgrad3 ? int64_t(G::C2) * G::KD3 : M3 * G::KD3);
+    w.dact2b = takeh(M2 * G::C2); w.dcol2b = takeh(ip.dgrad2 ? int64_t(4) * G::C1 * G::KD2 : M2 * G::KD2);
+    w.dact1b = takeh(M1 * G::C1);
   }
   w.splitk = takef(kSplitKScratchFloats);
   w.colsum_scratch = takef(colsum_scratch_floats(4 * int64_t(pp.core) > 512 ? 4 * int64_t(pp.core) : 512));
@@ -167,7 +188,7 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
     TcEpilogue te;
     te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act1b); te.ldc16 = G::C1; te.bias = P + pp.conv1_b;
     te.scale = 1.0f / 255.0f; te.relu = 1; te.tag = "conv1_fwd";
-    if (conv_u8_implicit_applicable(G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, G::C1)) {
+    if (implicit_plan().conv1) {
       // implicit GEMM: frames -> bf16 image once (kept in col1b for the backward), producer warps gather the
       // patches from it into the UMMA smem layout
       TB_TRY(frames_u8_to_bf16(frame, w.col1b, N * G::C0 * G::H0 * G::W0, st));
@@ -178,8 +199,7 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
     }
     // conv2 / conv3: implicit GEMM - TMA gathers the patches from the NHWC activation (rank-4 map with
     // overlapping dimensions); the patch matrices col2b / col3b are only materialised for the backward
-    const bool impl2 = conv_tc_implicit_applicable(G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2);
-    const bool impl3 = conv_tc_implicit_applicable(G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3);
+    const bool impl2 = implicit_plan().conv2, impl3 = implicit_plan().conv3;
     te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act2b); te.ldc16 = G::C2; te.bias = P + pp.conv2_b;
     te.relu = 1; te.tag = "conv2_fwd";
     if (impl2) {
@@ -294,7 +314,7 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
   te.mask16 = static_cast<const __nv_bfloat16*>(w.act3b); te.ldmask = G::FC_IN; te.tag = "fc_dgrad";
   TB_TRY(gemm_tc_bf16_ex(w.dfcb, w.wfcb, N, G::FC_IN, G::FC_OUT, G::FC_OUT, G::FC_IN, false, true, te, 1, nullptr, st));
   // conv3 (dact3b viewed as [M3, 64]); the implicit forward did not leave a patch matrix behind
-  if (conv_tc_implicit_applicable(G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3)) {
+  if (implicit_plan().conv3) {
     TB_TRY(conv_tc_wgrad_implicit(w.dact3b, w.act2b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3, G_ + pp.conv3_w,
                                   G::K3 * G::K3, G::C2, 1.0f, w.splitk, kSplitKScratchFloats, "conv3_wgrad", st));
   } else {
@@ -302,7 +322,7 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
                     "conv3_wgrad"));
   }
   TB_TRY(colsum_bf16(w.dact3b, G_ + pp.conv3_b, M3, G::C3, G::C3, w.colsum_scratch, st));
-  if (conv_tc_dgrad_implicit_applicable(G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3)) {
+  if (implicit_plan().dgrad3) {
     // gather-form transposed convolution on tensor cores: dY boxes through TMA (zero fill = padding), ReLU mask in the
     // epilogue; the transposed weight pack lives in the (otherwise unused) dcol3b buffer
     TB_TRY(pack_dgrad_weights_bf16(P + pp.conv3_w, w.dcol3b, G::C3, G::C2, G::K3, G::K3, G::S3, st));
@@ -315,7 +335,7 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
     TB_TRY(col2im_bf16_nhwc(w.dcol3b, w.act2b, w.dact2b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
   }
   // conv2
-  if (conv_tc_implicit_applicable(G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2)) {
+  if (implicit_plan().conv2) {
     TB_TRY(conv_tc_wgrad_implicit(w.dact2b, w.act1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2, G_ + pp.conv2_w,
                                   G::K2 * G::K2, G::C1, 1.0f, w.splitk, kSplitKScratchFloats, "conv2_wgrad", st));
   } else {
@@ -323,7 +343,7 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
                     "conv2_wgrad"));
   }
   TB_TRY(colsum_bf16(w.dact2b, G_ + pp.conv2_b, M2, G::C2, G::C2, w.colsum_scratch, st));
-  if (conv_tc_dgrad_implicit_applicable(G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2)) {
+  if (implicit_plan().dgrad2) {
     TB_TRY(pack_dgrad_weights_bf16(P + pp.conv2_w, w.dcol2b, G::C2, G::C1, G::K2, G::K2, G::S2, st));
     te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dact1b); te.ldc16 = G::C1;
     te.mask16 = static_cast<const __nv_bfloat16*>(w.act1b); te.ldmask = G::C1; te.tag = "conv2_dgrad";
@@ -334,7 +354,7 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
     TB_TRY(col2im_bf16_nhwc(w.dcol2b, w.act1b, w.dact1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
   }
   // conv1: the patch matrix holds raw pixel values, so the weight gradient carries the 1/255
-  if (conv_u8_implicit_applicable(G::C0, G::H0, G::W0, G::K1, G::K1, G::S1, G::C1)) {
+  if (implicit_plan().conv1) {
     // w.col1b holds the bf16 frame image the forward left there (not a patch matrix)
     TB_TRY(conv_u8_wgrad_implicit(w.dact1b, w.col1b, N, G::H0, G::W0, G::S1, G_ + pp.conv1_w, 1.0f / 255.0f, w.splitk,
                                   kSplitKScratchFloats, "conv1_wgrad", st));
