@@ -1881,8 +1881,8 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     wave_done = true;
   }
   // After the wavefront kernel only the hoisted weight-gradient GEMMs of both layers (and the lower layer's dx) remain.
-  // The GEMMs feed nothing downstream in this backward pass: fork them onto the side stream (own split-K scratch, grid
-  // capped so the caller's critical path keeps most SMs); the caller joins with lstm_backward_join().
+  // The GEMMs feed nothing downstream in this backward pass: fork them onto the side stream (own split-K scratch); the
+  // caller joins with lstm_backward_join().
   SideStream* tail = (wave_done && ws.wg_scratch) ? side_stream() : nullptr;
   if (tail) {
     TB_TRY(lstm_backward_join(st));  // a previous call's fork must be joined before its event is reused
@@ -1958,7 +1958,10 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       cudaStream_t gs = st;
       float* wscr = splitk;
       TcEpilogue te; te.tag = "lstm_wgrad";
-      if (tail) { gs = tail->stream; wscr = ws.wg_scratch; te.max_ctas = 64; }
+      if (tail) {
+        static const int tail_ctas = [] { const char* e = getenv("TB_LSTM_TAIL_CTAS"); return e ? atoi(e) : 0; }();  // 0 = uncapped: measured best (cap 32/64/96/none: 2.13/2.11/2.09/2.08 ms)
+        gs = tail->stream; wscr = ws.wg_scratch; te.max_ctas = tail_ctas;
+      }
       if (side) {
         cudaError_t ee = cudaEventRecord(side->fork, st);
         if (ee == cudaSuccess) ee = cudaStreamWaitEvent(side->stream, side->fork, 0);
