@@ -77,9 +77,10 @@ def synthetic_host_batch(T, B, A, seed, pin):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled every 50 ms while a timed region runs (a step is ~2 ms, the default
-    timed region ~0.2 s)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons sampled every 50 ms.  Started before the warm-up (nvidia-smi needs ~0.2 s to
+    produce its first line and a step is ~2 ms) and filtered to the timed region by nvidia-smi's own timestamps; if
+    that filter leaves nothing (clock skew, parse trouble) every collected sample is used."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -97,24 +98,47 @@ class ClockSampler:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        try:
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
 
-    def stop(self):
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text, "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
+
+    def stop(self, t0=None, t1=None):
         if self.proc is None:
             return None
-        time.sleep(0.25)
-        self.proc.terminate()
-        self.thread.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        if not sm:
+        try:
+            time.sleep(0.12)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+            rows = [r for r in list(self.rows) if len(r) >= 2 and r[1].replace(".", "").isdigit()]
+            if not rows:
+                return None
+            window = []
+            if t0 is not None and t1 is not None:
+                for r in rows:
+                    ts = self._stamp(r[0])
+                    if ts is not None and t0 - 0.06 <= ts <= t1 + 0.06:
+                        window.append(r)
+            used = window if window else rows
+            sm = [float(r[1]) for r in used]
+            reasons = []
+            for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if any(len(r) > 4 + i and r[4 + i].lower().startswith("active") for r in used):
+                    reasons.append(name)
+            mx = [float(r[2]) for r in used if len(r) > 2 and r[2].replace(".", "").isdigit()]
+            return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm),
+                        in_timed_region=bool(window))
+        except Exception:
             return None
-        reasons = []
-        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
-            if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows):
-                reasons.append(name)
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 
 
 def bind_to_gpu_numa_node(index):
@@ -356,12 +380,13 @@ def main():
         return ms
 
     # ---- device-resident throughput ----------------------------------------------------
-    for i in range(args.warmup):
-        learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
     if sampler:
         sampler.start()
+    for i in range(args.warmup):
+        learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
+    barrier()
+    t_region0 = time.time()
     launches0 = lib.tb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -371,7 +396,7 @@ def main():
     barrier()
     launches = lib.tb_launch_count() - launches0
     ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_region0, time.time()) if sampler else None
     final_loss = float(out["losses"][3])
     assert np.isfinite(final_loss), "non-finite loss"
 
