@@ -141,6 +141,20 @@ class ClockSampler:
             return None
 
 
+def host_cpu_info():
+    """os.cpu_count() and the CPU model string, reported next to every CPU number."""
+    info = {"host_cpu_count": os.cpu_count()}
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    info["host_cpu_model"] = ln.split(":", 1)[1].strip()
+                    break
+    except Exception:
+        pass
+    return info
+
+
 def bind_to_gpu_numa_node(index):
     """Pin this process to the CPUs of the NUMA node the GPU hangs off, so the pinned rollout
     staging buffers are allocated next to the GPU's PCIe root (first touch) - H2D bandwidth on a
@@ -330,7 +344,8 @@ def main():
             steps=r["steps"], warmup=r["warmup"], ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak",
             vs_baseline=None, dtype="f32", data="synthetic", config=config,
             cpu_baseline=dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port",
-                              sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py on CPU" % (r["steps"], T, B)),
+                              sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py on CPU" % (r["steps"], T, B),
+                              **host_cpu_info()),
             e2e=dict(value=r["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
@@ -547,7 +562,8 @@ def main():
         os.environ.setdefault("TB_CPU_BASELINE_BUDGET_S", "20")
         r = run_reference(types.SimpleNamespace(**dict(vars(args), steps=3, warmup=1)))
         line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port",
-                                    sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py" % (r["steps"], T, B))
+                                    sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py" % (r["steps"], T, B),
+                                    **host_cpu_info())
     print(json.dumps(line))
     finish()
 
