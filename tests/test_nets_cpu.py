@@ -52,4 +52,6 @@ def test_initial_state_and_init_distribution():
     assert AtariNet((4, 84, 84), 6, False, device="cpu").initial_state(3) == tuple()
     bound = 1 / np.sqrt(3136)
     w = m.fc.weight.detach()
-    assert float(w.abs().max()) <= bound and float(w.std()) > 0.5 * bound / np.sqrt(3)
+    # |w| <= bound up to fp32 rounding of the bound itself: uniform() can return exactly -1 (probability 2^-24 per
+    # element, ~10 % over the 1.6 M weights), and float32(bound) is slightly larger than the float64 value
+    assert float(w.abs().max()) <= bound * (1 + 1e-6) and float(w.std()) > 0.5 * bound / np.sqrt(3)
