@@ -130,8 +130,9 @@ size_t tb_atarinet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int u
  * monobeast.py:607-609); h0,c0 / hN,cN f32 [2,B,519] (LSTM only).
  * -> policy_logits f32 [T1,B,A], baseline f32 [T1,B].  Activations stay in `workspace`.
  * precision: 0 = fp32 SIMT GEMMs (bit-comparable with the reference's fp32 CPU arithmetic);
- *            1 = bf16 operands on tcgen05 tensor cores with fp32 accumulation (conv/fc trunk and the
- *                LSTM projections; recurrence, heads, losses, optimizer stay fp32).              */
+ *            1 = bf16 operands with fp32 accumulation: conv/fc trunk (implicit-GEMM convolutions) and LSTM
+ *                projections on tcgen05 tensor cores, LSTM recurrence products as bf16 mma.sync; LSTM state and
+ *                gate math, heads, losses, optimizer, master weights and gradients stay fp32.             */
 int tb_atarinet_forward(const uint8_t* frame, const float* reward, const float* notdone,
                         const int64_t* last_action, const float* h0, const float* c0,
                         const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
