@@ -147,16 +147,30 @@ def _flags():
     return f
 
 
-def _record(out, model, pre_grads):
+GRAD_SAMPLES = 4096  # strided sample of every gradient / updated parameter tensor (large fixtures only)
+
+
+def sample_index(numel, k=GRAD_SAMPLES):
+    """Deterministic strided sample positions shared with the tests (tests/common.py has the same formula)."""
+    if numel <= k:
+        return np.arange(numel)
+    return (np.arange(k, dtype=np.int64) * numel) // k
+
+
+def _record(out, model, pre_grads, samples=False):
     for n, prm in model.named_parameters():
         out["grad_stats/" + n] = _stats(prm.grad)
         out["grad_head/" + n] = prm.grad.detach().flatten()[:16].numpy().copy()
+        if samples:
+            idx = torch.from_numpy(sample_index(prm.numel()))
+            out["grad_sample/" + n] = prm.grad.detach().flatten()[idx].numpy().copy()
+            out["param_sample/" + n] = prm.detach().flatten()[idx].numpy().copy()
         out["param_stats/" + n] = _stats(prm)
         out["param_head/" + n] = prm.detach().flatten()[:16].numpy().copy()
     out["clipped_grad_norm"] = np.sqrt(sum((p.grad.double() ** 2).sum().item() for p in model.parameters()))
 
 
-def make_learn(net, use_lstm, T, B, seed, fname, clip=40.0):
+def make_learn(net, use_lstm, T, B, seed, fname, clip=40.0, samples=False):
     A = 6
     torch.manual_seed(0)
     batch = LT.synthetic_batch(T, B, A, seed=seed, with_last_action=(net == "atari"))
@@ -189,6 +203,14 @@ def make_learn(net, use_lstm, T, B, seed, fname, clip=40.0):
         else:
             (_, pl, bl), _ = model(dict(frame=batch["frame"], reward=batch["reward"], done=batch["done"]), state)
             out["policy_logits"], out["baseline"] = pl.numpy(), bl.numpy()
+        # the V-trace targets learn() computes from these outputs (monobeast.py:245-262 / polybeast_learner.py:332-347),
+        # through the reference's own core.vtrace
+        rewards = torch.clamp(batch["reward"][1:], -1, 1)
+        vt = ref_vtrace.from_logits(
+            behavior_policy_logits=batch["policy_logits"][1:], target_policy_logits=torch.from_numpy(out["policy_logits"])[:-1],
+            actions=batch["action"][1:], discounts=(~batch["done"][1:]).float() * flags.discounting, rewards=rewards,
+            values=torch.from_numpy(out["baseline"])[:-1], bootstrap_value=torch.from_numpy(out["baseline"])[-1])
+        out["vs"], out["pg_advantages"] = vt.vs.numpy(), vt.pg_advantages.numpy()
     if net == "atari":
         stats = monobeast.learn(flags, actor, model, batch, state, opt, sched)
     else:
@@ -199,7 +221,7 @@ def make_learn(net, use_lstm, T, B, seed, fname, clip=40.0):
         polybeast_learner.learn(flags, q, model, actor, opt, sched, stats, mock.Mock())
     for k in ("total_loss", "pg_loss", "baseline_loss", "entropy_loss"):
         out[k] = np.float64(stats[k])
-    _record(out, model, None)
+    _record(out, model, None, samples=samples)
     out["meta"] = np.array([T, B, A, seed, int(use_lstm)])
     out["clip"] = np.float64(clip)
     np.savez_compressed(os.path.join(OUT, fname), **out)
@@ -207,8 +229,19 @@ def make_learn(net, use_lstm, T, B, seed, fname, clip=40.0):
           "clipped_norm", out["clipped_grad_norm"])
 
 
+def make_baseline_config():
+    """BASELINE.json configs[1] (T=80, B=32, AtariNet +-LSTM) and one GPU's shard of configs[3] (ResNet, T=80, B=8):
+    the sizes bench.py runs.  Inputs are regenerated from the seed; outputs carry strided samples of every gradient."""
+    make_learn("atari", True, 80, 32, 21, "learn_atari_lstm_T80_B32.npz", samples=True)
+    make_learn("atari", False, 80, 32, 22, "learn_atari_T80_B32.npz", samples=True)
+    make_learn("resnet", True, 80, 8, 23, "learn_resnet_lstm_T80_B8.npz", samples=True)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--baseline-config" in sys.argv:  # only the large cases (minutes of CPU time)
+        make_baseline_config()
+        sys.exit(0)
     make_vtrace_fixture()
     make_vtrace_random()
     make_losses()
@@ -219,4 +252,5 @@ if __name__ == "__main__":
     make_learn("atari", False, 40, 6, 17, "learn_atari_T40_B6_clip10.npz", clip=10.0)  # grad-norm clip active
     make_learn("resnet", False, 4, 2, 15, "learn_resnet_T4_B2.npz")
     make_learn("resnet", True, 4, 2, 16, "learn_resnet_lstm_T4_B2.npz")
+    make_baseline_config()
     print("golden fixtures written to", OUT)

@@ -38,3 +38,14 @@ def random_vtrace_inputs(T, B, A, seed):
 
 RANDOM_CASES = (((80, 32, 6), 1), ((20, 8, 3), 2), ((7, 2, 18), 3), ((600, 16, 6), 4))
 CLIPS = ((1.0, 1.0), (None, None), (3.7, 2.2))
+
+
+GRAD_SAMPLES = 4096
+
+
+def sample_index(numel, k=GRAD_SAMPLES):
+    """Strided sample positions of the large fixtures' grad_sample/ and param_sample/ arrays (same formula as
+    oracle/make_golden.py:sample_index)."""
+    if numel <= k:
+        return np.arange(numel)
+    return (np.arange(k, dtype=np.int64) * numel) // k

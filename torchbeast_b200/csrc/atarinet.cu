@@ -83,14 +83,21 @@ static AtariParams atari_params(int A, int use_lstm) {
 
 constexpr int64_t kSplitKScratchFloats = int64_t(8) << 20;  // 32 MB
 
+// bf16 operand buffer of the tensor-core backends; lo != 0 (precision 2, split-bf16): element offset of the lo plane
+struct HB {
+  void* p = nullptr; int64_t lo = 0;
+  operator void*() const { return p; }
+  __nv_bfloat16* h() const { return static_cast<__nv_bfloat16*>(p); }
+};
+
 struct AtariWs {  // bump-carved view of the caller's workspace
   uint8_t* col1; float *act1, *col2, *act2, *col3, *act3, *core_in, *core_out;
   float *w2p, *w3p, *wfcp;
   float *dcore_out, *dcore_in, *dact3, *dcol3, *dact2, *dcol2, *dact1;
   float *splitk, *colsum_scratch;
-  // bf16 tensor-core backend (precision 1): operands / activations in bf16
-  void *col1b, *act1b, *col2b, *act2b, *col3b, *act3b, *w1b, *w2b, *w3b, *wfcb;
-  void *dfcb, *dact3b, *dcol3b, *dact2b, *dcol2b, *dact1b;
+  // tensor-core backends (precision 1: bf16, precision 2: split-bf16 hi/lo planes): operands / activations
+  HB col1b, act1b, col2b, act2b, col3b, act3b, w1b, w2b, w3b, wfcb;
+  HB dfcb, dact3b, dcol3b, dact2b, dcol2b, dact1b;
   LstmWs lstm;
   size_t bytes;
 };
@@ -107,7 +114,14 @@ static AtariWs atari_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int
   const AtariParams pp = atari_params(A, use_lstm);
   const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
   auto takef = [&](int64_t n) { return static_cast<float*>(take(size_t(n) * sizeof(float))); };
-  auto takeh = [&](int64_t n) { return take(size_t(n) * 2); };  // bf16
+  const bool split = precision == 2;
+  auto takeh = [&](int64_t n, bool planes = true) {  // bf16 (+ the lo plane right behind it in split mode)
+    HB b;
+    const size_t plane = (size_t(n) * 2 + 255) & ~size_t(255);
+    b.p = take(planes && split ? 2 * plane : plane);
+    b.lo = planes && split ? int64_t(plane / 2) : 0;
+    return b;
+  };
   w = AtariWs();
   w.core_in = takef(N * pp.core);
   w.core_out = use_lstm ? takef(N * pp.core) : w.core_in;
@@ -125,7 +139,8 @@ static AtariWs atari_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int
     const ImplicitPlan& ip = implicit_plan();
     // col1b: the bf16 frame image (implicit conv1) or the conv1 patch matrix; col2b/col3b exist only for the patch-matrix
     // fallback; dcol2b/dcol3b hold the transposed weight packs of the implicit input gradients or the gradient matrices
-    w.col1b = takeh(ip.conv1 ? N * G::C0 * G::H0 * G::W0 : M1 * G::KD1); w.act1b = takeh(M1 * G::C1);
+    // (the frame image / conv1 patch matrix holds integers <= 255: exact in bf16, no lo plane)
+    w.col1b = takeh(ip.conv1 ? N * G::C0 * G::H0 * G::W0 : M1 * G::KD1, false); w.act1b = takeh(M1 * G::C1);
     w.col2b = takeh(ip.conv2 ? 8 : M2 * G::KD2); w.act2b = takeh(M2 * G::C2);
     w.col3b = takeh(ip.conv3 ? 8 : M3 * G::KD3); w.act3b = takeh(N * G::FC_IN);
     w.w1b = takeh(int64_t(G::C1) * G::KD1); w.w2b = takeh(int64_t(G::C2) * G::KD2); w.w3b = takeh(int64_t(G::C3) * G::KD3);
@@ -180,17 +195,21 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
   const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
   GemmEpilogue ep;
   if (precision) {
-    // ---- bf16 tensor-core trunk: tcgen05 GEMMs, bf16 activations, fp32 accumulation ----
-    TB_TRY(pack_weights_bf16(P + pp.conv1_w, w.w1b, G::C1, 1, G::KD1, G::KD1, st));
-    TB_TRY(pack_weights_bf16(P + pp.conv2_w, w.w2b, G::C2, G::K2 * G::K2, G::C1, G::KD2, st));
-    TB_TRY(pack_weights_bf16(P + pp.conv3_w, w.w3b, G::C3, G::K3 * G::K3, G::C2, G::KD3, st));
-    TB_TRY(pack_weights_bf16(P + pp.fc_w, w.wfcb, G::FC_OUT, G::H3 * G::W3, G::C3, G::FC_IN, st));
+    // ---- tensor-core trunk: tcgen05 GEMMs, bf16 (precision 1) or split-bf16 hi/lo (precision 2) activations, fp32 accumulation
+    const bool split = precision == 2;
+    TB_REQUIRE(!split || (implicit_plan().conv1 && implicit_plan().conv2 && implicit_plan().conv3),
+               "atarinet_forward: the split-bf16 backend needs the implicit-GEMM convolutions (TB_CONV*_IMPLICIT=0 set?)");
+    TB_TRY(pack_weights_bf16(P + pp.conv1_w, w.w1b, G::C1, 1, G::KD1, G::KD1, st, w.w1b.lo));
+    TB_TRY(pack_weights_bf16(P + pp.conv2_w, w.w2b, G::C2, G::K2 * G::K2, G::C1, G::KD2, st, w.w2b.lo));
+    TB_TRY(pack_weights_bf16(P + pp.conv3_w, w.w3b, G::C3, G::K3 * G::K3, G::C2, G::KD3, st, w.w3b.lo));
+    TB_TRY(pack_weights_bf16(P + pp.fc_w, w.wfcb, G::FC_OUT, G::H3 * G::W3, G::C3, G::FC_IN, st, w.wfcb.lo));
     TcEpilogue te;
-    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act1b); te.ldc16 = G::C1; te.bias = P + pp.conv1_b;
+    te = TcEpilogue(); te.C16 = w.act1b.h(); te.ldc16 = G::C1; te.c16_lo = w.act1b.lo; te.bias = P + pp.conv1_b;
     te.scale = 1.0f / 255.0f; te.relu = 1; te.tag = "conv1_fwd";
     if (implicit_plan().conv1) {
       // implicit GEMM: frames -> bf16 image once (kept in col1b for the backward), producer warps gather the
       // patches from it into the UMMA smem layout
+      te.b_lo = w.w1b.lo;  // the pixels are exact in bf16: only the weights have a lo plane
       TB_TRY(frames_u8_to_bf16(frame, w.col1b, N * G::C0 * G::H0 * G::W0, st));
       TB_TRY(conv_u8_fwd_implicit(w.col1b, w.w1b, N, G::H0, G::W0, G::S1, te, st));
     } else {
@@ -200,16 +219,16 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
     // conv2 / conv3: implicit GEMM - TMA gathers the patches from the NHWC activation (rank-4 map with
     // overlapping dimensions); the patch matrices col2b / col3b are only materialised for the backward
     const bool impl2 = implicit_plan().conv2, impl3 = implicit_plan().conv3;
-    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act2b); te.ldc16 = G::C2; te.bias = P + pp.conv2_b;
-    te.relu = 1; te.tag = "conv2_fwd";
+    te = TcEpilogue(); te.C16 = w.act2b.h(); te.ldc16 = G::C2; te.c16_lo = w.act2b.lo; te.bias = P + pp.conv2_b;
+    te.relu = 1; te.tag = "conv2_fwd"; te.a_lo = w.act1b.lo; te.b_lo = w.w2b.lo;
     if (impl2) {
       TB_TRY(conv_tc_fwd_implicit(w.act1b, w.w2b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2, te, st));
     } else {
       TB_TRY(im2col_bf16_nhwc(w.act1b, w.col2b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
       TB_TRY(gemm_tc_bf16(w.col2b, w.w2b, M2, G::C2, G::KD2, G::KD2, G::KD2, te, st));
     }
-    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.act3b); te.ldc16 = G::C3; te.bias = P + pp.conv3_b;
-    te.relu = 1; te.tag = "conv3_fwd";
+    te = TcEpilogue(); te.C16 = w.act3b.h(); te.ldc16 = G::C3; te.c16_lo = w.act3b.lo; te.bias = P + pp.conv3_b;
+    te.relu = 1; te.tag = "conv3_fwd"; te.a_lo = w.act2b.lo; te.b_lo = w.w3b.lo;
     if (impl3) {
       TB_TRY(conv_tc_fwd_implicit(w.act2b, w.w3b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3, te, st));
     } else {
@@ -217,6 +236,7 @@ static int atarinet_forward(const uint8_t* frame, const float* reward, const flo
       TB_TRY(gemm_tc_bf16(w.col3b, w.w3b, M3, G::C3, G::KD3, G::KD3, G::KD3, te, st));
     }
     te = TcEpilogue(); te.C = w.core_in; te.ldc = pp.core; te.bias = P + pp.fc_b; te.relu = 1; te.tag = "fc_fwd";
+    te.a_lo = w.act3b.lo; te.b_lo = w.wfcb.lo;
     TB_TRY(gemm_tc_bf16(w.act3b, w.wfcb, N, G::FC_OUT, G::FC_IN, G::FC_IN, G::FC_IN, te, st));
   } else {
   // weight pack: [o, c, kh, kw] -> [o, (kh,kw), c];  fc: [o, c, (h,w)] -> [o, (h,w), c]
@@ -292,10 +312,11 @@ static int tc_splits(int64_t M, int64_t N, int64_t K) {
   return int(s);
 }
 
-static int tc_wgrad(const void* dYb, int64_t ldy, const void* Xb, int64_t ldx, float* dW, int64_t rows, int64_t nout,
+static int tc_wgrad(const HB& dYb, int64_t ldy, const HB& Xb, int64_t ldx, float* dW, int64_t rows, int64_t nout,
                     int64_t kin, int permP, int permQ, float scale, AtariWs& w, cudaStream_t st, const char* tag) {
   TcEpilogue te;
   te.C = dW; te.ldc = kin; te.permP = permP; te.permQ = permQ; te.scale = scale; te.tag = tag;
+  te.a_lo = dYb.lo; te.b_lo = Xb.lo;
   return gemm_tc_bf16_ex(dYb, Xb, nout, kin, rows, ldy, ldx, true, true, te, tc_splits(nout, kin, rows), w.splitk, st);
 }
 
@@ -306,50 +327,54 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
   // fc: ReLU mask (fp32, in place), bias grad, bf16 copy of dY
   TB_TRY(relu_mask_inplace(w.dcore_in, w.core_in, N, G::FC_OUT, pp.core, pp.core, st));
   TB_TRY(colsum(w.dcore_in, G_ + pp.fc_b, N, G::FC_OUT, pp.core, w.colsum_scratch, st));
-  TB_TRY(f32_to_bf16(w.dcore_in, w.dfcb, N, G::FC_OUT, pp.core, G::FC_OUT, st));
+  TB_TRY(f32_to_bf16(w.dcore_in, w.dfcb, N, G::FC_OUT, pp.core, G::FC_OUT, st, w.dfcb.lo));
   TB_TRY(tc_wgrad(w.dfcb, G::FC_OUT, w.act3b, G::FC_IN, G_ + pp.fc_w, N, G::FC_OUT, G::FC_IN, G::H3 * G::W3, G::C3, 1.0f, w,
                   st, "fc_wgrad"));
   TcEpilogue te;
-  te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dact3b); te.ldc16 = G::FC_IN;
-  te.mask16 = static_cast<const __nv_bfloat16*>(w.act3b); te.ldmask = G::FC_IN; te.tag = "fc_dgrad";
+  te = TcEpilogue(); te.C16 = w.dact3b.h(); te.ldc16 = G::FC_IN; te.c16_lo = w.dact3b.lo;
+  te.mask16 = w.act3b.h(); te.ldmask = G::FC_IN; te.tag = "fc_dgrad"; te.a_lo = w.dfcb.lo; te.b_lo = w.wfcb.lo;
   TB_TRY(gemm_tc_bf16_ex(w.dfcb, w.wfcb, N, G::FC_IN, G::FC_OUT, G::FC_OUT, G::FC_IN, false, true, te, 1, nullptr, st));
   // conv3 (dact3b viewed as [M3, 64]); the implicit forward did not leave a patch matrix behind
   if (implicit_plan().conv3) {
     TB_TRY(conv_tc_wgrad_implicit(w.dact3b, w.act2b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3, G_ + pp.conv3_w,
-                                  G::K3 * G::K3, G::C2, 1.0f, w.splitk, kSplitKScratchFloats, "conv3_wgrad", st));
+                                  G::K3 * G::K3, G::C2, 1.0f, w.splitk, kSplitKScratchFloats, "conv3_wgrad", st, w.dact3b.lo,
+                                  w.act2b.lo));
   } else {
     TB_TRY(tc_wgrad(w.dact3b, G::C3, w.col3b, G::KD3, G_ + pp.conv3_w, M3, G::C3, G::KD3, G::K3 * G::K3, G::C2, 1.0f, w, st,
                     "conv3_wgrad"));
   }
-  TB_TRY(colsum_bf16(w.dact3b, G_ + pp.conv3_b, M3, G::C3, G::C3, w.colsum_scratch, st));
+  TB_TRY(colsum_bf16(w.dact3b, G_ + pp.conv3_b, M3, G::C3, G::C3, w.colsum_scratch, st, w.dact3b.lo));
   if (implicit_plan().dgrad3) {
     // gather-form transposed convolution on tensor cores: dY boxes through TMA (zero fill = padding), ReLU mask in the
     // epilogue; the transposed weight pack lives in the (otherwise unused) dcol3b buffer
-    TB_TRY(pack_dgrad_weights_bf16(P + pp.conv3_w, w.dcol3b, G::C3, G::C2, G::K3, G::K3, G::S3, st));
-    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dact2b); te.ldc16 = G::C2;
-    te.mask16 = static_cast<const __nv_bfloat16*>(w.act2b); te.ldmask = G::C2; te.tag = "conv3_dgrad";
+    TB_TRY(pack_dgrad_weights_bf16(P + pp.conv3_w, w.dcol3b, G::C3, G::C2, G::K3, G::K3, G::S3, st, w.dcol3b.lo));
+    te = TcEpilogue(); te.C16 = w.dact2b.h(); te.ldc16 = G::C2; te.c16_lo = w.dact2b.lo;
+    te.mask16 = w.act2b.h(); te.ldmask = G::C2; te.tag = "conv3_dgrad"; te.a_lo = w.dact3b.lo; te.b_lo = w.dcol3b.lo;
     TB_TRY(conv_tc_dgrad_implicit(w.dact3b, w.dcol3b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, G::C3, te, st));
   } else {
-    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol3b); te.ldc16 = G::KD3; te.tag = "conv3_dgrad";
+    TB_REQUIRE(!w.dact3b.lo, "atarinet_backward: split-bf16 needs the implicit input-gradient convolutions");
+    te = TcEpilogue(); te.C16 = w.dcol3b.h(); te.ldc16 = G::KD3; te.tag = "conv3_dgrad";
     TB_TRY(gemm_tc_bf16_ex(w.dact3b, w.w3b, M3, G::KD3, G::C3, G::C3, G::KD3, false, true, te, 1, nullptr, st));
     TB_TRY(col2im_bf16_nhwc(w.dcol3b, w.act2b, w.dact2b, N, G::H2, G::W2, G::C2, G::K3, G::K3, G::S3, st));
   }
   // conv2
   if (implicit_plan().conv2) {
     TB_TRY(conv_tc_wgrad_implicit(w.dact2b, w.act1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2, G_ + pp.conv2_w,
-                                  G::K2 * G::K2, G::C1, 1.0f, w.splitk, kSplitKScratchFloats, "conv2_wgrad", st));
+                                  G::K2 * G::K2, G::C1, 1.0f, w.splitk, kSplitKScratchFloats, "conv2_wgrad", st, w.dact2b.lo,
+                                  w.act1b.lo));
   } else {
     TB_TRY(tc_wgrad(w.dact2b, G::C2, w.col2b, G::KD2, G_ + pp.conv2_w, M2, G::C2, G::KD2, G::K2 * G::K2, G::C1, 1.0f, w, st,
                     "conv2_wgrad"));
   }
-  TB_TRY(colsum_bf16(w.dact2b, G_ + pp.conv2_b, M2, G::C2, G::C2, w.colsum_scratch, st));
+  TB_TRY(colsum_bf16(w.dact2b, G_ + pp.conv2_b, M2, G::C2, G::C2, w.colsum_scratch, st, w.dact2b.lo));
   if (implicit_plan().dgrad2) {
-    TB_TRY(pack_dgrad_weights_bf16(P + pp.conv2_w, w.dcol2b, G::C2, G::C1, G::K2, G::K2, G::S2, st));
-    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dact1b); te.ldc16 = G::C1;
-    te.mask16 = static_cast<const __nv_bfloat16*>(w.act1b); te.ldmask = G::C1; te.tag = "conv2_dgrad";
+    TB_TRY(pack_dgrad_weights_bf16(P + pp.conv2_w, w.dcol2b, G::C2, G::C1, G::K2, G::K2, G::S2, st, w.dcol2b.lo));
+    te = TcEpilogue(); te.C16 = w.dact1b.h(); te.ldc16 = G::C1; te.c16_lo = w.dact1b.lo;
+    te.mask16 = w.act1b.h(); te.ldmask = G::C1; te.tag = "conv2_dgrad"; te.a_lo = w.dact2b.lo; te.b_lo = w.dcol2b.lo;
     TB_TRY(conv_tc_dgrad_implicit(w.dact2b, w.dcol2b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, G::C2, te, st));
   } else {
-    te = TcEpilogue(); te.C16 = static_cast<__nv_bfloat16*>(w.dcol2b); te.ldc16 = G::KD2; te.tag = "conv2_dgrad";
+    TB_REQUIRE(!w.dact2b.lo, "atarinet_backward: split-bf16 needs the implicit input-gradient convolutions");
+    te = TcEpilogue(); te.C16 = w.dcol2b.h(); te.ldc16 = G::KD2; te.tag = "conv2_dgrad";
     TB_TRY(gemm_tc_bf16_ex(w.dact2b, w.w2b, M2, G::KD2, G::C2, G::C2, G::KD2, false, true, te, 1, nullptr, st));
     TB_TRY(col2im_bf16_nhwc(w.dcol2b, w.act1b, w.dact1b, N, G::H1, G::W1, G::C1, G::K2, G::K2, G::S2, st));
   }
@@ -357,12 +382,13 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
   if (implicit_plan().conv1) {
     // w.col1b holds the bf16 frame image the forward left there (not a patch matrix)
     TB_TRY(conv_u8_wgrad_implicit(w.dact1b, w.col1b, N, G::H0, G::W0, G::S1, G_ + pp.conv1_w, 1.0f / 255.0f, w.splitk,
-                                  kSplitKScratchFloats, "conv1_wgrad", st));
+                                  kSplitKScratchFloats, "conv1_wgrad", st, w.dact1b.lo));
   } else {
+    TB_REQUIRE(!w.dact1b.lo, "atarinet_backward: split-bf16 needs the implicit conv1");
     TB_TRY(tc_wgrad(w.dact1b, G::C1, w.col1b, G::KD1, G_ + pp.conv1_w, M1, G::C1, G::KD1, 1, 1, 1.0f / 255.0f, w, st,
                     "conv1_wgrad"));
   }
-  TB_TRY(colsum_bf16(w.dact1b, G_ + pp.conv1_b, M1, G::C1, G::C1, w.colsum_scratch, st));
+  TB_TRY(colsum_bf16(w.dact1b, G_ + pp.conv1_b, M1, G::C1, G::C1, w.colsum_scratch, st, w.dact1b.lo));
   return 0;
 }
 
@@ -449,7 +475,8 @@ int tb_atarinet_forward(const uint8_t* frame, const float* reward, const float* 
   TB_REQUIRE(frame && reward && last_action && params && workspace && policy_logits && baseline,
              "atarinet_forward: null pointer");
   TB_REQUIRE(!use_lstm || (notdone && h0 && c0 && hN && cN), "atarinet_forward: LSTM needs notdone/h0/c0/hN/cN");
-  TB_REQUIRE(precision == 0 || precision == 1, "atarinet_forward: precision must be 0 (fp32) or 1 (bf16 tensor cores)");
+  TB_REQUIRE(precision >= 0 && precision <= 2,
+             "atarinet_forward: precision must be 0 (fp32 SIMT), 1 (bf16 tensor cores) or 2 (split-bf16 tensor cores)");
   return atarinet_forward(frame, reward, notdone, last_action, h0, c0, params, T1, B, num_actions, use_lstm, precision,
                           workspace, policy_logits, baseline, hN, cN, (cudaStream_t)stream);
 }
@@ -460,6 +487,7 @@ int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, c
   TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "atarinet_backward: bad sizes");
   TB_REQUIRE(grad_logits && grad_baseline && params && workspace && grads, "atarinet_backward: null pointer");
   TB_REQUIRE(!use_lstm || notdone, "atarinet_backward: LSTM needs notdone");
+  TB_REQUIRE(precision >= 0 && precision <= 2, "atarinet_backward: precision must be 0, 1 or 2");
   return atarinet_backward(grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm, precision, workspace,
                            grads, (cudaStream_t)stream);
 }

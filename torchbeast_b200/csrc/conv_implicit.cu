@@ -87,16 +87,19 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // position runs on), filled by all 256 gather threads: thread p owns patch row p & 127 and kernel rows
 // [4*(p>>7), +4).  The next tile's 32 words are loaded before the current tile is converted, so one
 // global-load latency is exposed per tile, not per stage.
+// SPLIT (split-bf16): the pixel operand is exact in bf16, so only the weights carry a lo plane (resident next to the
+// hi plane, tmBl) - two MMAs per k-step, patch.Wlo then patch.Whi - and the output is written as hi / lo planes.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep,
-                            ConvGeom g, int tiles_m) {
+conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __grid_constant__ CUtensorMap tmB,
+                            const __grid_constant__ CUtensorMap tmBl, TcEpilogue ep, ConvGeom g, int tiles_m) {
   constexpr uint32_t B_BYTES = kO * kBlockK * 2;  // 4 KB per k-block
   constexpr uint32_t TMEM_COLS = 64;              // two 32-column accumulator buffers
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
   constexpr uint32_t kTileBytes = kC * kABytes;  // 64 KB
   const uint32_t sA = base, sB = base + kStagesF * kTileBytes;
-  const uint32_t bars = sB + kC * B_BYTES;  // full[kStagesF], empty[kStagesF], tmem_full[2], tmem_empty[2], wfull
+  const uint32_t bars = sB + (SPLIT ? 2 : 1) * kC * B_BYTES;  // full[kStagesF], empty[kStagesF], tmem_full[2], tmem_empty[2], wfull
   const uint32_t tmem_slot = bars + 8 * (2 * kStagesF + 5);
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (kStagesF + s); };
@@ -122,8 +125,10 @@ conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __gri
 
   if (warp == 0) {
     if (lane == 0) {  // the whole weight matrix [32, 256] stays resident: one box per k-block
-      mbar_expect_tx(wfull, kC * B_BYTES);
+      mbar_expect_tx(wfull, (SPLIT ? 2 : 1) * kC * B_BYTES);
       for (int c = 0; c < kC; ++c) tma_load_2d(sB + c * B_BYTES, &tmB, wfull, c * kBlockK, 0);
+      if constexpr (SPLIT)
+        for (int c = 0; c < kC; ++c) tma_load_2d(sB + (kC + c) * B_BYTES, &tmBl, wfull, c * kBlockK, 0);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -141,9 +146,15 @@ conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __gri
 #pragma unroll
         for (int c = 0; c < kC; ++c)
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_bf16(tacc, make_smem_desc(sA + stage * kTileBytes + c * kABytes + k * 32),
-                      make_smem_desc(sB + c * B_BYTES + k * 32), idesc, (c | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sA + stage * kTileBytes + c * kABytes + k * 32);
+            if constexpr (SPLIT) {
+              umma_bf16(tacc, da, make_smem_desc(sB + (kC + c) * B_BYTES + k * 32), idesc, (c | k) != 0 ? 1u : 0u);
+              umma_bf16(tacc, da, make_smem_desc(sB + c * B_BYTES + k * 32), idesc, 1u);
+            } else {
+              umma_bf16(tacc, da, make_smem_desc(sB + c * B_BYTES + k * 32), idesc, (c | k) != 0 ? 1u : 0u);
+            }
+          }
         umma_commit(empty(stage));
         umma_commit(tmem_full(ab));
         if (++stage == kStagesF) { stage = 0; phase ^= 1; }
@@ -166,18 +177,22 @@ conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty(ab));  // values are in registers: free the accumulator early
       if (r < g.M) {
-        uint32_t pk[16];
+        uint32_t pk[16], pl[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           float x0 = __uint_as_float(v[j]) * ep.scale + bias_r[j];
           float x1 = __uint_as_float(v[j + 1]) * ep.scale + bias_r[j + 1];
           if (ep.relu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
-          __nv_bfloat162 p = __floats2bfloat162_rn(x0, x1);
-          pk[j >> 1] = *reinterpret_cast<uint32_t*>(&p);
+          split_bf16x2(x0, x1, pk[j >> 1], pl[j >> 1]);
         }
         uint4* c = reinterpret_cast<uint4*>(ep.C16 + r * ep.ldc16);
 #pragma unroll
         for (int j = 0; j < 4; ++j) c[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        if (SPLIT && ep.c16_lo) {
+          uint4* cl = reinterpret_cast<uint4*>(ep.C16 + ep.c16_lo + r * ep.ldc16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+        }
       }
     }
   } else {
@@ -236,28 +251,34 @@ conv_u8_fwd_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __gri
 // D[o (padded to 128), k = 256] accumulates over this CTA's slice of 64-patch blocks; stage = A: two
 // 64(o) x 64(patch) TMA boxes of dY (columns >= 32 are out of bounds -> zero), B: four 64(patch) x 64(k)
 // gathered boxes (one per channel).  Gather thread p owns patch row p & 63 of channel p >> 6.
+// SPLIT (split-bf16): dY arrives as hi / lo planes (tmA / tmAl, two boxes per stage), the pixels are exact:
+// two MMAs per k-step, dYlo.patch then dYhi.patch.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv_u8_wgrad_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __grid_constant__ CUtensorMap tmA, ConvGeom g,
-                              float* __restrict__ partial, int total_kb, int per) {
+conv_u8_wgrad_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __grid_constant__ CUtensorMap tmA,
+                              const __grid_constant__ CUtensorMap tmAl, ConvGeom g, float* __restrict__ partial, int total_kb,
+                              int per) {
+  constexpr int kStW = SPLIT ? kStagesW - 1 : kStagesW;  // 4 x 48 KB (split) / 5 x 40 KB
   constexpr uint32_t B_BYTES = kC * 8192;  // 32 KB
   constexpr uint32_t TMEM_COLS = 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
-  constexpr uint32_t A_BYTES = 8192;  // only the first 64-wide box of dY^T is loaded: accumulator rows >= 64 read
+  constexpr uint32_t A_BOX = 8192;   // only the first 64-wide box of dY^T is loaded: accumulator rows >= 64 read
                                      // whatever follows in shared memory and are never looked at
-  const uint32_t sA = base, sB = base + kStagesW * A_BYTES;
-  const uint32_t bars = sB + kStagesW * B_BYTES;  // full[kStagesW], empty[kStagesW], tmem_full
-  const uint32_t tmem_slot = bars + 8 * (2 * kStagesW + 1);
+  constexpr uint32_t A_BYTES = (SPLIT ? 2u : 1u) * A_BOX;  // [hi][lo]
+  const uint32_t sA = base, sB = base + kStW * A_BYTES;
+  const uint32_t bars = sB + kStW * B_BYTES;  // full[kStW], empty[kStW], tmem_full
+  const uint32_t tmem_slot = bars + 8 * (2 * kStW + 1);
   auto full = [&](int s) { return bars + 8u * s; };
-  auto empty = [&](int s) { return bars + 8u * (kStagesW + s); };
-  const uint32_t tmem_full = bars + 8u * (2 * kStagesW);
+  auto empty = [&](int s) { return bars + 8u * (kStW + s); };
+  const uint32_t tmem_full = bars + 8u * (2 * kStW);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kb0 = blockIdx.x * per;
   const int kb1 = (kb0 + per < total_kb) ? kb0 + per : total_kb;
   const int num_kb = kb1 > kb0 ? kb1 - kb0 : 0;
 
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStagesW; ++s) { mbar_init(full(s), kProducers / 32 + 1); mbar_init(empty(s), 1); }
+    for (int s = 0; s < kStW; ++s) { mbar_init(full(s), kProducers / 32 + 1); mbar_init(empty(s), 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   } else if (warp == 2) {
@@ -278,7 +299,8 @@ conv_u8_wgrad_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __g
         mbar_wait(empty(stage), phase ^ 1);
         mbar_expect_tx(full(stage), A_BYTES);
         tma_load_2d(sA + stage * A_BYTES, &tmA, full(stage), 0, kc);
-        if (++stage == kStagesW) { stage = 0; phase ^= 1; }
+        if constexpr (SPLIT) tma_load_2d(sA + stage * A_BYTES + A_BOX, &tmAl, full(stage), 0, kc);
+        if (++stage == kStW) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -290,11 +312,17 @@ conv_u8_wgrad_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __g
         mbar_wait(full(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)
-          umma_bf16(tmem_base, make_smem_desc_mn(sA + stage * A_BYTES + k * 2048), make_smem_desc_mn(sB + stage * B_BYTES + k * 2048),
-                    idesc, (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t db = make_smem_desc_mn(sB + stage * B_BYTES + k * 2048);
+          if constexpr (SPLIT) {
+            umma_bf16(tmem_base, make_smem_desc_mn(sA + stage * A_BYTES + A_BOX + k * 2048), db, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_base, make_smem_desc_mn(sA + stage * A_BYTES + k * 2048), db, idesc, 1u);
+          } else {
+            umma_bf16(tmem_base, make_smem_desc_mn(sA + stage * A_BYTES + k * 2048), db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
         umma_commit(empty(stage));
-        if (++stage == kStagesW) { stage = 0; phase ^= 1; }
+        if (++stage == kStW) { stage = 0; phase ^= 1; }
       }
       umma_commit(tmem_full);
     }
@@ -348,13 +376,13 @@ conv_u8_wgrad_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __g
         copy8(dst + 2048u + (uint32_t(j ^ rr) << 4), srcB + j * g.W);  // row + 16: two 8-row groups further
       }
       cp_commit();
-      if (++stage == kStagesW) { stage = 0; phase ^= 1; }
+      if (++stage == kStW) { stage = 0; phase ^= 1; }
       if (++pending > kLag) {
         cp_wait<kLag>();
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(full(sig));
-        if (++sig == kStagesW) sig = 0;
+        if (++sig == kStW) sig = 0;
         --pending;
       }
     }
@@ -363,7 +391,7 @@ conv_u8_wgrad_implicit_kernel(const __nv_bfloat16* __restrict__ frame, const __g
     __syncwarp();
     for (; pending > 0; --pending) {
       if (lane == 0) mbar_arrive(full(sig));
-      if (++sig == kStagesW) sig = 0;
+      if (++sig == kStW) sig = 0;
     }
   }
   __syncthreads();
@@ -443,25 +471,36 @@ int conv_u8_fwd_implicit(const void* frame_bf16, const void* w_bf16, int64_t N, 
   if (N == 0) return 0;
   ProfScope prof(ep.tag, stream);
   const ConvGeom g = make_geom(N, H, W, S);
-  CUtensorMap mb;
+  CUtensorMap mb, mbl;
   int rc = make_map(&mb, w_bf16, kO, kC * 64, kC * 64, kO);
   if (rc) return rc;
-  constexpr size_t smem = 1024 + kStagesF * size_t(kC) * kABytes + kC * (kO * kBlockK * 2) + 8 * (2 * kStagesF + 5) + 16;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_u8_fwd_implicit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  mbl = mb;
+  const bool split = ep.b_lo != 0;
+  if (split) {
+    rc = make_map(&mbl, static_cast<const __nv_bfloat16*>(w_bf16) + ep.b_lo, kO, kC * 64, kC * 64, kO);
+    if (rc) return rc;
+  }
+  constexpr size_t smem = 1024 + kStagesF * size_t(kC) * kABytes + 2 * kC * (kO * kBlockK * 2) + 8 * (2 * kStagesF + 5) + 16;
+  static uint64_t attr = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr >> (dev & 63)) & 1)) {
+    cudaError_t e = cudaFuncSetAttribute(conv_u8_fwd_implicit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_u8_fwd_implicit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     TB_REQUIRE(e == cudaSuccess, "conv_u8_fwd_implicit: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr = true;
+    attr |= uint64_t(1) << (dev & 63);
   }
   const int64_t tiles = (g.M + kBlockM - 1) / kBlockM;
   TB_REQUIRE(tiles < (int64_t(1) << 31), "conv_u8_fwd_implicit: too many tiles");
   const int64_t grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
-  conv_u8_fwd_implicit_kernel<<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, mb, ep, g, int(tiles));
+  if (split) conv_u8_fwd_implicit_kernel<true><<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, mb, mbl, ep, g, int(tiles));
+  else conv_u8_fwd_implicit_kernel<false><<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, mb, mbl, ep, g, int(tiles));
   return check_launch("conv_u8_fwd_implicit_kernel");
 }
 
 int conv_u8_wgrad_implicit(const void* dy_bf16, const void* frame_bf16, int64_t N, int H, int W, int S, float* dW, float scale,
-                           float* partial, int64_t partial_floats, const char* tag, cudaStream_t stream) {
+                           float* partial, int64_t partial_floats, const char* tag, cudaStream_t stream, int64_t dy_lo) {
   const __nv_bfloat16* frame = static_cast<const __nv_bfloat16*>(frame_bf16);
   TB_REQUIRE(frame && dy_bf16 && dW && partial, "conv_u8_wgrad_implicit: null pointer");
   TB_REQUIRE((reinterpret_cast<uintptr_t>(frame) & 7) == 0, "conv_u8_wgrad_implicit: unaligned frame pointer");
@@ -473,17 +512,31 @@ int conv_u8_wgrad_implicit(const void* dy_bf16, const void* frame_bf16, int64_t 
   const int64_t per = (total_kb + grid - 1) / grid;
   grid = (total_kb + per - 1) / per;
   TB_REQUIRE(grid * kO * kC * 64 <= partial_floats, "conv_u8_wgrad_implicit: partial buffer too small");
-  CUtensorMap ma;  // dY [M, 32] with the patch index as the reduction (row) index: MN-major boxes of 64 x 64
+  CUtensorMap ma, mal;  // dY [M, 32] with the patch index as the reduction (row) index: MN-major boxes of 64 x 64
   int rc = make_map(&ma, dy_bf16, g.M, kO, kO, kBlockK, 64);
   if (rc) return rc;
-  constexpr size_t smem = 1024 + kStagesW * (8192 + size_t(kC) * 8192) + 8 * (2 * kStagesW + 1) + 16;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_u8_wgrad_implicit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    TB_REQUIRE(e == cudaSuccess, "conv_u8_wgrad_implicit: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr = true;
+  mal = ma;
+  if (dy_lo) {
+    rc = make_map(&mal, static_cast<const __nv_bfloat16*>(dy_bf16) + dy_lo, g.M, kO, kO, kBlockK, 64);
+    if (rc) return rc;
   }
-  conv_u8_wgrad_implicit_kernel<<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, ma, g, partial, int(total_kb), int(per));
+  constexpr size_t smem = 1024 + kStagesW * (8192 + size_t(kC) * 8192) + 8 * (2 * kStagesW + 1) + 16;  // >= the split ring (4 x 48 KB)
+  static_assert(smem <= 227 * 1024 && smem >= 1024 + (kStagesW - 1) * (2 * 8192 + size_t(kC) * 8192) + 8 * (2 * kStagesW + 1) + 16,
+                "conv_u8_wgrad_implicit: ring size");
+  static uint64_t attr = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!((attr >> (dev & 63)) & 1)) {
+    cudaError_t e = cudaFuncSetAttribute(conv_u8_wgrad_implicit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_u8_wgrad_implicit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    TB_REQUIRE(e == cudaSuccess, "conv_u8_wgrad_implicit: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr |= uint64_t(1) << (dev & 63);
+  }
+  if (dy_lo)
+    conv_u8_wgrad_implicit_kernel<true><<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, ma, mal, g, partial, int(total_kb), int(per));
+  else
+    conv_u8_wgrad_implicit_kernel<false><<<(unsigned)grid, kConvThreads, smem, stream>>>(frame, ma, mal, g, partial, int(total_kb), int(per));
   rc = check_launch("conv_u8_wgrad_implicit_kernel");
   if (rc) return rc;
   GemmEpilogue rep;

@@ -63,17 +63,22 @@ struct ImplicitConv {
   int outH = 0, outW = 0;  // mode 2: input-gradient image size
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI, bool IMPL = false>
+// SPLIT (split-bf16, see TcEpilogue): a stage holds the hi AND lo plane tiles of both operands (tmAl / tmBl are the
+// lo planes' tensor maps) and every k-step issues three MMAs (lo.hi, hi.lo, hi.hi) into the same accumulator; the
+// epilogue can write its bf16 output as hi / lo planes.
+template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI, bool IMPL = false, bool SPLIT = false>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcEpilogue ep, int M,
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl, TcEpilogue ep, int M,
                int N, int K, float* partial, int tiles_m, int tiles_n, int splits, int ldp = 0,
                ImplicitConv ic = ImplicitConv()) {
   constexpr uint32_t B_BYTES = BLOCK_N * kBlockK * 2;
+  constexpr uint32_t A_STAGE = (SPLIT ? 2u : 1u) * kABytes, B_STAGE = (SPLIT ? 2u : 1u) * B_BYTES;  // [hi][lo]
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // two accumulator buffers (power of two)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
-  const uint32_t sA = base, sB = base + kStages * kABytes;
-  const uint32_t bars = sB + kStages * B_BYTES;  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
+  const uint32_t sA = base, sB = base + kStages * A_STAGE;
+  const uint32_t bars = sB + kStages * B_STAGE;  // full[kStages], empty[kStages], tmem_full[2], tmem_empty[2]
   const uint32_t tmem_slot = bars + 8 * (2 * kStages + 4);
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (kStages + s); };
@@ -120,26 +125,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < num_kb; ++i) {
           const int kc = (kb0 + i) * kBlockK;
           mbar_wait(empty(stage), phase ^ 1);
-          mbar_expect_tx(full(stage), (IMPL ? uint32_t(ic.rows) * 128u : kABytes) + B_BYTES);
-          if (IMPL) {
-            const int kb = kb0 + i;
-            if (ic.mode == 0)
-              tma_load_4d(sA + stage * kABytes, &tmA, full(stage), (kb / ic.kbw) * ic.row_elems + (kb % ic.kbw) * kBlockK, 0, 0,
-                          (m0 / kBlockM) * ic.fpt);
-            else
-              tma_load_4d(sA + stage * kABytes, &tmA, full(stage), 0, -(kb % ic.kbw), -(kb / ic.kbw), (m0 / kBlockM) * ic.fpt);
-          } else if (A_MN) {  // two 64(k) x 64(m) boxes
-            tma_load_2d(sA + stage * kABytes, &tmA, full(stage), m0, kc);
-            tma_load_2d(sA + stage * kABytes + 8192, &tmA, full(stage), m0 + 64, kc);
-          } else {
-            tma_load_2d(sA + stage * kABytes, &tmA, full(stage), kc, m0);
-          }
-          if (B_MN) {
+          mbar_expect_tx(full(stage), (SPLIT ? 2u : 1u) * ((IMPL ? uint32_t(ic.rows) * 128u : kABytes) + B_BYTES));
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sB + stage * B_BYTES + j * 8192, &tmB, full(stage), n0 + 64 * j, kc);
-          } else {
-            tma_load_2d(sB + stage * B_BYTES, &tmB, full(stage), kc, n0);
+          for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {  // plane 0 = hi, plane 1 = lo
+            const CUtensorMap* mA = pl ? &tmAl : &tmA;
+            const CUtensorMap* mB = pl ? &tmBl : &tmB;
+            const uint32_t dA = sA + stage * A_STAGE + pl * kABytes, dB = sB + stage * B_STAGE + pl * B_BYTES;
+            if (IMPL) {
+              const int kb = kb0 + i;
+              if (ic.mode == 0)
+                tma_load_4d(dA, mA, full(stage), (kb / ic.kbw) * ic.row_elems + (kb % ic.kbw) * kBlockK, 0, 0,
+                            (m0 / kBlockM) * ic.fpt);
+              else
+                tma_load_4d(dA, mA, full(stage), 0, -(kb % ic.kbw), -(kb / ic.kbw), (m0 / kBlockM) * ic.fpt);
+            } else if (A_MN) {  // two 64(k) x 64(m) boxes
+              tma_load_2d(dA, mA, full(stage), m0, kc);
+              tma_load_2d(dA + 8192, mA, full(stage), m0 + 64, kc);
+            } else {
+              tma_load_2d(dA, mA, full(stage), kc, m0);
+            }
+            if (B_MN) {
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 64; ++j) tma_load_2d(dB + j * 8192, mB, full(stage), n0 + 64 * j, kc);
+            } else {
+              tma_load_2d(dB, mB, full(stage), kc, n0);
+            }
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -164,9 +174,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc_mn(sA + stage * kABytes + k * 2048) : make_smem_desc(sA + stage * kABytes + k * 32);
-            const uint64_t db = B_MN ? make_smem_desc_mn(sB + stage * B_BYTES + k * 2048) : make_smem_desc(sB + stage * B_BYTES + k * 32);
-            umma_bf16(tacc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t aA = sA + stage * A_STAGE, aB = sB + stage * B_STAGE;
+            const uint64_t da = A_MN ? make_smem_desc_mn(aA + k * 2048) : make_smem_desc(aA + k * 32);
+            const uint64_t db = B_MN ? make_smem_desc_mn(aB + k * 2048) : make_smem_desc(aB + k * 32);
+            if constexpr (SPLIT) {  // small terms first: lo.hi, hi.lo, then hi.hi
+              const uint64_t dal = A_MN ? make_smem_desc_mn(aA + kABytes + k * 2048) : make_smem_desc(aA + kABytes + k * 32);
+              const uint64_t dbl = B_MN ? make_smem_desc_mn(aB + B_BYTES + k * 2048) : make_smem_desc(aB + B_BYTES + k * 32);
+              umma_bf16(tacc, dal, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_bf16(tacc, da, dbl, idesc, 1u);
+              umma_bf16(tacc, da, db, idesc, 1u);
+            } else {
+              umma_bf16(tacc, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(empty(stage));  // slot free once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -353,32 +372,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (ep.C16) {
             __nv_bfloat16* c = ep.C16 + pr * ep.ldc16 + pc;
-            if (full_cols && (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0) {
+            const bool wlo = SPLIT && ep.c16_lo != 0;  // also write the lo plane (c16_lo is a multiple of 8 elements)
+            const bool vec = (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-                __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                *reinterpret_cast<uint4*>(c + j) = pk;
-              }
-            } else {  // column tail (N = 144, 288, ...): still 16-byte stores for the complete groups of 8
-              const bool vec = (ep.ldc16 & 7) == 0 && (reinterpret_cast<uintptr_t>(c) & 15) == 0;
+            for (int j = 0; j < 32; j += 8) {
+              // column tail (N = 144, 288, ...): still 16-byte stores for the complete groups of 8
+              if (vec && (full_cols || nbase + j + 8 <= N)) {
+                uint4 ph, pl;
+                split_bf16x2(o[j], o[j + 1], ph.x, pl.x); split_bf16x2(o[j + 2], o[j + 3], ph.y, pl.y);
+                split_bf16x2(o[j + 4], o[j + 5], ph.z, pl.z); split_bf16x2(o[j + 6], o[j + 7], ph.w, pl.w);
+                *reinterpret_cast<uint4*>(c + j) = ph;
+                if (wlo) *reinterpret_cast<uint4*>(c + ep.c16_lo + j) = pl;
+              } else {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (vec && nbase + j + 8 <= N) {
-                  uint4 pk;
-                  __nv_bfloat162 p0 = __floats2bfloat162_rn(o[j], o[j + 1]), p1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
-                  __nv_bfloat162 p2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), p3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
-                  pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                  pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                  *reinterpret_cast<uint4*>(c + j) = pk;
-                } else {
-#pragma unroll
-                  for (int jj = 0; jj < 8; ++jj)
-                    if (nbase + j + jj < N) c[j + jj] = __float2bfloat16_rn(o[j + jj]);
-                }
+                for (int jj = 0; jj < 8; ++jj)
+                  if (nbase + j + jj < N) {
+                    const __nv_bfloat16 h = __float2bfloat16_rn(o[j + jj]);
+                    c[j + jj] = h;
+                    if (wlo) c[ep.c16_lo + j + jj] = bf16_lo_of(o[j + jj], h);
+                  }
               }
             }
           }
@@ -397,16 +409,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI>
-int launch_e(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
+struct TcMaps { CUtensorMap a, b, al, bl; };  // operand maps (+ lo planes in split mode; copies of a / b otherwise)
+
+// cudaFuncSetAttribute is per device: remember which devices have had it applied for this instantiation
+static inline bool attr_done(uint64_t* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = uint64_t(1) << (dev & 63);
+  if (*mask & bit) return true;
+  *mask |= bit;
+  return false;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, int EPI, bool SPLIT>
+int launch_e(const TcMaps& mp, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
              float* partial, cudaStream_t stream) {
-  constexpr size_t smem = 1024 + kStages * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kStages + 4) + 16;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages, EPI>,
+  constexpr size_t smem = 1024 + kStages * (SPLIT ? 2 : 1) * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kStages + 4) + 16;
+  static_assert(smem <= 227 * 1024, "gemm_tc: stage ring exceeds shared memory");
+  static uint64_t attr = 0;
+  if (!attr_done(&attr)) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages, EPI, false, SPLIT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr = true;
   }
   const int64_t tiles_m = (M + kBlockM - 1) / kBlockM, tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int64_t total = tiles_m * tiles_n * splits;
@@ -420,29 +444,36 @@ int launch_e(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, i
   int64_t grid = int64_t(kNumSMsB200) * per_sm;
   if (ep.max_ctas > 0 && grid > ep.max_ctas) grid = ep.max_ctas;
   if (grid > total) grid = total;
-  gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages, EPI><<<(unsigned)grid, kThreads, smem, stream>>>(
-      a, b, ep, int(M), int(N), int(K), partial, int(tiles_m), int(tiles_n), splits, int((N + 31) & ~int64_t(31)));
+  gemm_tc_kernel<BLOCK_N, A_MN, B_MN, kStages, EPI, false, SPLIT><<<(unsigned)grid, kThreads, smem, stream>>>(
+      mp.a, mp.b, mp.al, mp.bl, ep, int(M), int(N), int(K), partial, int(tiles_m), int(tiles_n), splits,
+      int((N + 31) & ~int64_t(31)));
   return check_launch("gemm_tc_kernel");
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int kStages>
-int launch_s(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
+template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, bool SPLIT>
+int launch_s(const TcMaps& mp, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
              float* partial, cudaStream_t stream) {
   const bool loads = ep.mask || ep.mask16 || ep.addend16;
   const bool arith = ep.bias || ep.relu || ep.scale != 1.0f;
-  if (loads) return launch_e<BLOCK_N, A_MN, B_MN, kStages, 2>(a, b, ep, M, N, K, splits, partial, stream);
-  if (arith && !partial) return launch_e<BLOCK_N, A_MN, B_MN, kStages, 1>(a, b, ep, M, N, K, splits, partial, stream);
-  return launch_e<BLOCK_N, A_MN, B_MN, kStages, 0>(a, b, ep, M, N, K, splits, partial, stream);
+  if (loads) return launch_e<BLOCK_N, A_MN, B_MN, kStages, 2, SPLIT>(mp, ep, M, N, K, splits, partial, stream);
+  if (arith && !partial) return launch_e<BLOCK_N, A_MN, B_MN, kStages, 1, SPLIT>(mp, ep, M, N, K, splits, partial, stream);
+  return launch_e<BLOCK_N, A_MN, B_MN, kStages, 0, SPLIT>(mp, ep, M, N, K, splits, partial, stream);
 }
 
 // Few k-blocks per CTA (dgrad: K = 64 channels): a 2-stage ring keeps 3 CTAs resident per SM so the
 // per-CTA prologue (TMEM alloc, barrier init) of one tile overlaps the epilogue of another.
+// Split mode doubles the stage (hi + lo planes): 3 stages of 64 KB for 128-wide tiles, 4 otherwise.
 template <int BLOCK_N, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
+int launch(const TcMaps& mp, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
            float* partial, cudaStream_t stream) {
   const int64_t kb_per_cta = ((K + kBlockK - 1) / kBlockK + splits - 1) / splits;
-  if (kb_per_cta <= 2) return launch_s<BLOCK_N, A_MN, B_MN, 2>(a, b, ep, M, N, K, splits, partial, stream);
-  return launch_s<BLOCK_N, A_MN, B_MN, 4>(a, b, ep, M, N, K, splits, partial, stream);
+  const bool split = ep.a_lo != 0;
+  if (split) {
+    if (kb_per_cta <= 2) return launch_s<BLOCK_N, A_MN, B_MN, 2, true>(mp, ep, M, N, K, splits, partial, stream);
+    return launch_s<BLOCK_N, A_MN, B_MN, (BLOCK_N >= 128 ? 3 : 4), true>(mp, ep, M, N, K, splits, partial, stream);
+  }
+  if (kb_per_cta <= 2) return launch_s<BLOCK_N, A_MN, B_MN, 2, false>(mp, ep, M, N, K, splits, partial, stream);
+  return launch_s<BLOCK_N, A_MN, B_MN, 4, false>(mp, ep, M, N, K, splits, partial, stream);
 }
 
 
@@ -459,16 +490,20 @@ struct ImplicitWgrad {
   int per = 0;           // stages per split
 };
 
-template <int kSt>
+// SPLIT (split-bf16): the stage also carries the lo planes, [dY hi][dY lo][patch0 hi][patch1 hi][patch0 lo][patch1 lo],
+// and every k-step issues dYlo.Phi, dYhi.Plo, dYhi.Phi.
+template <int kSt, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_wgrad_implicit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int O, int Kdim,
+conv_wgrad_implicit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmAl, const __grid_constant__ CUtensorMap tmBl, int O, int Kdim,
                            float* __restrict__ partial, int tiles_n, ImplicitWgrad iw) {
   constexpr int BLOCK_N = 128;
   constexpr uint32_t TMEM_COLS = BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_addr(smem_raw) + 1023u) & ~1023u;
   const uint32_t group = uint32_t(iw.rows_pad) * 128u;  // one 64-wide group: rows_pad x 128 B (multiple of 1024)
-  const uint32_t stage_bytes = 3u * group;              // [dY group][patch group 0][patch group 1]
+  const uint32_t stage_bytes = (SPLIT ? 6u : 3u) * group;  // [dY group][patch group 0][patch group 1]
+  const uint32_t offB = (SPLIT ? 2u : 1u) * group;         // first patch group
   const uint32_t bars = base + kSt * stage_bytes;       // full[kSt], empty[kSt], tmem_full
   const uint32_t tmem_slot = bars + 8 * (2 * kSt + 1);
   auto full = [&](int s) { return bars + 8u * s; };
@@ -508,11 +543,16 @@ conv_wgrad_implicit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
       for (int i = 0; i < num; ++i) {
         const int f0 = (s0 + i) * iw.fpt;
         mbar_wait(empty(stage), phase ^ 1);
-        mbar_expect_tx(full(stage), 3u * uint32_t(iw.rows) * 128u);
+        mbar_expect_tx(full(stage), (SPLIT ? 6u : 3u) * uint32_t(iw.rows) * 128u);
         const uint32_t st = base + stage * stage_bytes;
         tma_load_2d(st, &tmA, full(stage), 0, f0 * (iw.rows / iw.fpt));
-        tma_load_4d(st + group, &tmB, full(stage), eA, 0, 0, f0);
-        tma_load_4d(st + 2 * group, &tmB, full(stage), eB, 0, 0, f0);
+        tma_load_4d(st + offB, &tmB, full(stage), eA, 0, 0, f0);
+        tma_load_4d(st + offB + group, &tmB, full(stage), eB, 0, 0, f0);
+        if constexpr (SPLIT) {
+          tma_load_2d(st + group, &tmAl, full(stage), 0, f0 * (iw.rows / iw.fpt));
+          tma_load_4d(st + 4 * group, &tmBl, full(stage), eA, 0, 0, f0);
+          tma_load_4d(st + 5 * group, &tmBl, full(stage), eB, 0, 0, f0);
+        }
         if (++stage == kSt) { stage = 0; phase ^= 1; }
       }
     }
@@ -526,9 +566,17 @@ conv_wgrad_implicit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
         mbar_wait(full(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t st = base + stage * stage_bytes;
-        for (int k = 0; k < ksteps; ++k)  // A's second 64-wide group aliases patch group 0: accumulator rows >= 64 are junk
-          umma_bf16(tmem_base, make_smem_desc_mn_lbo(st + k * 2048, group), make_smem_desc_mn_lbo(st + group + k * 2048, group),
-                    idesc, (i | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < ksteps; ++k) {  // A's second 64-wide group aliases the next group: accumulator rows >= 64 are junk
+          const uint64_t da = make_smem_desc_mn_lbo(st + k * 2048, group);
+          const uint64_t db = make_smem_desc_mn_lbo(st + offB + k * 2048, group);
+          if constexpr (SPLIT) {
+            umma_bf16(tmem_base, make_smem_desc_mn_lbo(st + group + k * 2048, group), db, idesc, (i | k) != 0 ? 1u : 0u);
+            umma_bf16(tmem_base, da, make_smem_desc_mn_lbo(st + 4 * group + k * 2048, group), idesc, 1u);
+            umma_bf16(tmem_base, da, db, idesc, 1u);
+          } else {
+            umma_bf16(tmem_base, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
         umma_commit(empty(stage));
         if (++stage == kSt) { stage = 0; phase ^= 1; }
       }
@@ -573,16 +621,16 @@ conv_wgrad_implicit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
   }
 }
 
-template <int BLOCK_N, int EPI = 1, int kSt = 4>
-int launch_conv_fwd(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K,
-                    int64_t tiles_m, const ImplicitConv& ic, cudaStream_t stream) {
-  constexpr size_t smem = 1024 + kSt * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kSt + 4) + 16;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, false, false, kSt, EPI, true>,
+template <int BLOCK_N, int EPI, int kSt, bool SPLIT>
+int launch_conv_fwd_s(const TcMaps& mp, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K,
+                      int64_t tiles_m, const ImplicitConv& ic, cudaStream_t stream) {
+  constexpr size_t smem = 1024 + kSt * (SPLIT ? 2 : 1) * (kABytes + size_t(BLOCK_N) * kBlockK * 2) + 8 * (2 * kSt + 4) + 16;
+  static_assert(smem <= 227 * 1024, "gemm_tc: stage ring exceeds shared memory");
+  static uint64_t attr = 0;
+  if (!attr_done(&attr)) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, false, false, kSt, EPI, true, SPLIT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     TB_REQUIRE(e == cudaSuccess, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr = true;
   }
   const int64_t tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
   const int64_t total = tiles_m * tiles_n;
@@ -592,9 +640,17 @@ int launch_conv_fwd(const CUtensorMap& a, const CUtensorMap& b, const TcEpilogue
   if (per_sm > 3) per_sm = 3;
   int64_t grid = int64_t(kNumSMsB200) * per_sm;
   if (grid > total) grid = total;
-  gemm_tc_kernel<BLOCK_N, false, false, kSt, EPI, true><<<(unsigned)grid, kThreads, smem, stream>>>(
-      a, b, ep, int(M), int(N), int(K), nullptr, int(tiles_m), int(tiles_n), 1, 0, ic);
+  gemm_tc_kernel<BLOCK_N, false, false, kSt, EPI, true, SPLIT><<<(unsigned)grid, kThreads, smem, stream>>>(
+      mp.a, mp.b, mp.al, mp.bl, ep, int(M), int(N), int(K), nullptr, int(tiles_m), int(tiles_n), 1, 0, ic);
   return check_launch("gemm_tc_kernel(implicit conv)");
+}
+
+template <int BLOCK_N, int EPI = 1, int kSt = 4>
+int launch_conv_fwd(const TcMaps& mp, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int64_t tiles_m,
+                    const ImplicitConv& ic, cudaStream_t stream) {
+  if (ep.a_lo != 0)  // split: 64 KB stages for 128-wide tiles
+    return launch_conv_fwd_s<BLOCK_N, EPI, (BLOCK_N >= 128 && kSt > 3 ? 3 : kSt), true>(mp, ep, M, N, K, tiles_m, ic, stream);
+  return launch_conv_fwd_s<BLOCK_N, EPI, kSt, false>(mp, ep, M, N, K, tiles_m, ic, stream);
 }
 
 }  // namespace
@@ -626,15 +682,23 @@ int conv_tc_fwd_implicit(const void* act_nhwc_bf16, const void* w_packed_bf16, i
   const uint64_t dims[4] = {uint64_t(H) * W * C, uint64_t(OW), uint64_t(OH), uint64_t(Nf)};
   const uint64_t strides[3] = {uint64_t(S) * C * 2, uint64_t(S) * W * C * 2, uint64_t(H) * W * C * 2};
   const uint32_t box[4] = {uint32_t(kBlockK), uint32_t(OW), uint32_t(OH), uint32_t(ic.fpt)};
-  CUtensorMap ma, mb;
-  int rc = make_map_nd(&ma, act_nhwc_bf16, 4, dims, strides, box);
+  TB_REQUIRE((ep.a_lo != 0) == (ep.b_lo != 0), "conv_tc_fwd_implicit: split mode needs both lo planes");
+  TcMaps mp;
+  int rc = make_map_nd(&mp.a, act_nhwc_bf16, 4, dims, strides, box);
   if (rc) return rc;
   const int bn = (O <= 32) ? 32 : (O <= 64 ? 64 : 128);
-  rc = make_map(&mb, w_packed_bf16, O, K, K, bn);
+  rc = make_map(&mp.b, w_packed_bf16, O, K, K, bn);
   if (rc) return rc;
-  if (bn == 32) return launch_conv_fwd<32>(ma, mb, ep, M, O, K, tiles_m, ic, stream);
-  if (bn == 64) return launch_conv_fwd<64>(ma, mb, ep, M, O, K, tiles_m, ic, stream);
-  return launch_conv_fwd<128>(ma, mb, ep, M, O, K, tiles_m, ic, stream);
+  mp.al = mp.a; mp.bl = mp.b;
+  if (ep.a_lo) {
+    rc = make_map_nd(&mp.al, static_cast<const __nv_bfloat16*>(act_nhwc_bf16) + ep.a_lo, 4, dims, strides, box);
+    if (rc) return rc;
+    rc = make_map(&mp.bl, static_cast<const __nv_bfloat16*>(w_packed_bf16) + ep.b_lo, O, K, K, bn);
+    if (rc) return rc;
+  }
+  if (bn == 32) return launch_conv_fwd<32>(mp, ep, M, O, K, tiles_m, ic, stream);
+  if (bn == 64) return launch_conv_fwd<64>(mp, ep, M, O, K, tiles_m, ic, stream);
+  return launch_conv_fwd<128>(mp, ep, M, O, K, tiles_m, ic, stream);
 }
 
 bool conv_tc_dgrad_implicit_applicable(int H, int W, int C, int KH, int KW, int S, int O) {
@@ -661,37 +725,72 @@ int conv_tc_dgrad_implicit(const void* dy_nhwc_bf16, const void* wt_bf16, int64_
   const int OH = (H - KH) / S + 1, OW = (W - KW) / S + 1;
   ImplicitConv ic;
   ic.fpt = 1;
-  CUtensorMap ma, mb;
+  TB_REQUIRE((ep.a_lo != 0) == (ep.b_lo != 0), "conv_tc_dgrad_implicit: split mode needs both lo planes");
+  TcMaps mp;
+  const __nv_bfloat16* dy_lo = static_cast<const __nv_bfloat16*>(dy_nhwc_bf16) + ep.a_lo;
+  const __nv_bfloat16* wt_lo = static_cast<const __nv_bfloat16*>(wt_bf16) + ep.b_lo;
   const uint64_t dims[4] = {uint64_t(O), uint64_t(OW), uint64_t(OH), uint64_t(Nf)};
   const uint64_t strides[3] = {uint64_t(O) * 2, uint64_t(OW) * O * 2, uint64_t(OH) * OW * O * 2};
   int rc;
   if (S == 1) {
     ic.mode = 1; ic.rows = H * W; ic.kbw = KW;
     const uint32_t box[4] = {uint32_t(kBlockK), uint32_t(W), uint32_t(H), 1u};
-    rc = make_map_nd(&ma, dy_nhwc_bf16, 4, dims, strides, box);
+    rc = make_map_nd(&mp.a, dy_nhwc_bf16, 4, dims, strides, box);
     if (rc) return rc;
     const int64_t K = int64_t(KH) * KW * O, M = Nf * ic.rows;
     const int bn = (C <= 32) ? 32 : (C <= 64 ? 64 : 128);
-    rc = make_map(&mb, wt_bf16, C, K, K, bn);
+    rc = make_map(&mp.b, wt_bf16, C, K, K, bn);
     if (rc) return rc;
-    if (bn == 32) return launch_conv_fwd<32, 2>(ma, mb, ep, M, C, K, Nf, ic, stream);
-    if (bn == 64) return launch_conv_fwd<64, 2>(ma, mb, ep, M, C, K, Nf, ic, stream);
-    return launch_conv_fwd<128, 2>(ma, mb, ep, M, C, K, Nf, ic, stream);
+    mp.al = mp.a; mp.bl = mp.b;
+    if (ep.a_lo) {
+      rc = make_map_nd(&mp.al, dy_lo, 4, dims, strides, box);
+      if (rc) return rc;
+      rc = make_map(&mp.bl, wt_lo, C, K, K, bn);
+      if (rc) return rc;
+    }
+    if (bn == 32) return launch_conv_fwd<32, 2>(mp, ep, M, C, K, Nf, ic, stream);
+    if (bn == 64) return launch_conv_fwd<64, 2>(mp, ep, M, C, K, Nf, ic, stream);
+    return launch_conv_fwd<128, 2>(mp, ep, M, C, K, Nf, ic, stream);
   }
   ic.mode = 2; ic.tw = W / 2; ic.rows = (H / 2) * (W / 2); ic.kbw = KW / 2; ic.outH = H; ic.outW = W;
   const uint32_t box[4] = {uint32_t(kBlockK), uint32_t(W / 2), uint32_t(H / 2), 1u};
-  rc = make_map_nd(&ma, dy_nhwc_bf16, 4, dims, strides, box);
+  rc = make_map_nd(&mp.a, dy_nhwc_bf16, 4, dims, strides, box);
   if (rc) return rc;
   const int64_t K = int64_t(KH / 2) * (KW / 2) * O, M = Nf * ic.rows;
-  rc = make_map(&mb, wt_bf16, 4 * C, K, K, 128);
+  rc = make_map(&mp.b, wt_bf16, 4 * C, K, K, 128);
   if (rc) return rc;
+  mp.al = mp.a; mp.bl = mp.b;
+  if (ep.a_lo) {
+    rc = make_map_nd(&mp.al, dy_lo, 4, dims, strides, box);
+    if (rc) return rc;
+    rc = make_map(&mp.bl, wt_lo, 4 * C, K, K, 128);
+    if (rc) return rc;
+  }
   // 4 k-blocks per tile: a 2-stage ring lets two CTAs share an SM so one tile's epilogue overlaps another's loads
-  return launch_conv_fwd<128, 2, 2>(ma, mb, ep, M, 4 * C, K, Nf, ic, stream);
+  return launch_conv_fwd<128, 2, 2>(mp, ep, M, 4 * C, K, Nf, ic, stream);
+}
+
+template <int kSt, bool SPLIT>
+static int launch_conv_wgrad(const TcMaps& mp, int O, int64_t K, float* partial, int tiles_n, int64_t splits,
+                             const ImplicitWgrad& iw, cudaStream_t stream) {
+  const size_t smem = 1024 + size_t(kSt) * (SPLIT ? 6 : 3) * iw.rows_pad * 128 + 8 * (2 * kSt + 1) + 16;
+  TB_REQUIRE(smem <= 227 * 1024, "conv_tc_wgrad_implicit: stage too large");
+  static size_t attr[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr[dev & 63] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_implicit_kernel<kSt, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    TB_REQUIRE(e == cudaSuccess, "conv_tc_wgrad_implicit: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr[dev & 63] = smem;
+  }
+  conv_wgrad_implicit_kernel<kSt, SPLIT><<<(unsigned)(splits * tiles_n), kThreads, smem, stream>>>(mp.a, mp.b, mp.al, mp.bl, O, int(K),
+                                                                                                 partial, tiles_n, iw);
+  return check_launch("conv_wgrad_implicit_kernel");
 }
 
 int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64_t Nf, int H, int W, int C, int KH, int KW, int S,
                            int O, float* dW, int permP, int permQ, float scale, float* partial, int64_t partial_floats,
-                           const char* tag, cudaStream_t stream) {
+                           const char* tag, cudaStream_t stream, int64_t dy_lo, int64_t act_lo) {
   TB_REQUIRE(dy_bf16 && act_nhwc_bf16 && dW && partial, "conv_tc_wgrad_implicit: null pointer");
   TB_REQUIRE(conv_tc_implicit_applicable(H, W, C, KH, KW, S, O) && O <= 64 && O % 8 == 0,
              "conv_tc_wgrad_implicit: unsupported shape");
@@ -721,26 +820,28 @@ int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64
   TB_REQUIRE(splits >= 1, "conv_tc_wgrad_implicit: partial buffer too small");
   iw.per = int((iw.stages_total + splits - 1) / splits);
   splits = (iw.stages_total + iw.per - 1) / iw.per;
-  CUtensorMap ma, mb;
+  TB_REQUIRE((dy_lo != 0) == (act_lo != 0), "conv_tc_wgrad_implicit: split mode needs both lo planes");
+  TcMaps mp;
   // dY [patches, O]: MN-major box of 64 channels x `rows` patches
-  int rc = make_map(&ma, dy_bf16, Nf * OH * OW, O, O, iw.rows, 64);
+  int rc = make_map(&mp.a, dy_bf16, Nf * OH * OW, O, O, iw.rows, 64);
   if (rc) return rc;
   const uint64_t dims[4] = {uint64_t(H) * W * C, uint64_t(OW), uint64_t(OH), uint64_t(Nf)};
   const uint64_t strides[3] = {uint64_t(S) * C * 2, uint64_t(S) * W * C * 2, uint64_t(H) * W * C * 2};
   const uint32_t box[4] = {uint32_t(kBlockK), uint32_t(OW), uint32_t(OH), uint32_t(iw.fpt)};
-  rc = make_map_nd(&mb, act_nhwc_bf16, 4, dims, strides, box);
+  rc = make_map_nd(&mp.b, act_nhwc_bf16, 4, dims, strides, box);
   if (rc) return rc;
-  constexpr int kSt = 4;
-  const size_t smem = 1024 + size_t(kSt) * 3 * iw.rows_pad * 128 + 8 * (2 * kSt + 1) + 16;
-  TB_REQUIRE(smem <= 227 * 1024, "conv_tc_wgrad_implicit: stage too large");
-  static size_t attr = 0;
-  if (attr < smem) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_implicit_kernel<kSt>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    TB_REQUIRE(e == cudaSuccess, "conv_tc_wgrad_implicit: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr = smem;
+  mp.al = mp.a; mp.bl = mp.b;
+  if (dy_lo) {
+    rc = make_map(&mp.al, static_cast<const __nv_bfloat16*>(dy_bf16) + dy_lo, Nf * OH * OW, O, O, iw.rows, 64);
+    if (rc) return rc;
+    rc = make_map_nd(&mp.bl, static_cast<const __nv_bfloat16*>(act_nhwc_bf16) + act_lo, 4, dims, strides, box);
+    if (rc) return rc;
+    // 6 groups per stage: as many stages as fit (2 for the 98-patch conv3 tiles, 3 for the 81-patch conv2 tiles)
+    if (size_t(3) * 6 * iw.rows_pad * 128 + 2048 <= 227 * 1024) rc = launch_conv_wgrad<3, true>(mp, O, K, partial, tiles_n, splits, iw, stream);
+    else rc = launch_conv_wgrad<2, true>(mp, O, K, partial, tiles_n, splits, iw, stream);
+  } else {
+    rc = launch_conv_wgrad<4, false>(mp, O, K, partial, tiles_n, splits, iw, stream);
   }
-  conv_wgrad_implicit_kernel<kSt><<<(unsigned)(splits * tiles_n), kThreads, smem, stream>>>(ma, mb, O, int(K), partial, tiles_n, iw);
-  rc = check_launch("conv_wgrad_implicit_kernel");
   if (rc) return rc;
   GemmEpilogue rep;
   rep.permP = permP; rep.permQ = permQ; rep.scale = scale;
@@ -764,15 +865,25 @@ int gemm_tc_bf16_ex(const void* A, const void* B, int64_t M, int64_t N, int64_t 
   ProfScope prof(ep.tag, stream);
   int bn = (N <= 32) ? 32 : (N <= 64 ? 64 : 128);
   if (b_mn && bn < 64) bn = 64;  // MN-major tiles are built from 64-wide boxes
-  CUtensorMap ma, mb;
+  TB_REQUIRE((ep.a_lo != 0) == (ep.b_lo != 0), "gemm_tc: split mode needs the lo planes of both operands");
+  TcMaps mp;
   // K-major operand [rows = mn, cols = k]: box {64 k, mn rows}.  MN-major operand [rows = k, cols = mn]: box {64 mn, 64 k}.
-  int rc = a_mn ? make_map(&ma, A, K, M, lda, kBlockK, 64) : make_map(&ma, A, M, K, lda, kBlockM);
+  int rc = a_mn ? make_map(&mp.a, A, K, M, lda, kBlockK, 64) : make_map(&mp.a, A, M, K, lda, kBlockM);
   if (rc) return rc;
-  rc = b_mn ? make_map(&mb, B, K, N, ldb, kBlockK, 64) : make_map(&mb, B, N, K, ldb, bn);
+  rc = b_mn ? make_map(&mp.b, B, K, N, ldb, kBlockK, 64) : make_map(&mp.b, B, N, K, ldb, bn);
   if (rc) return rc;
+  mp.al = mp.a; mp.bl = mp.b;
+  if (ep.a_lo) {
+    const __nv_bfloat16* Al = static_cast<const __nv_bfloat16*>(A) + ep.a_lo;
+    const __nv_bfloat16* Bl = static_cast<const __nv_bfloat16*>(B) + ep.b_lo;
+    rc = a_mn ? make_map(&mp.al, Al, K, M, lda, kBlockK, 64) : make_map(&mp.al, Al, M, K, lda, kBlockM);
+    if (rc) return rc;
+    rc = b_mn ? make_map(&mp.bl, Bl, K, N, ldb, kBlockK, 64) : make_map(&mp.bl, Bl, N, K, ldb, bn);
+    if (rc) return rc;
+  }
   float* part = splits > 1 || partial ? partial : nullptr;
   if (splits == 1 && !(ep.permP > 1 || ep.permQ > 1)) part = nullptr;
-#define TB_TC_LAUNCH(BN, AM, BM) rc = launch<BN, AM, BM>(ma, mb, ep, M, N, K, splits, part, stream)
+#define TB_TC_LAUNCH(BN, AM, BM) rc = launch<BN, AM, BM>(mp, ep, M, N, K, splits, part, stream)
   if (!a_mn && !b_mn) {
     if (bn == 32) TB_TC_LAUNCH(32, false, false);
     else if (bn == 64) TB_TC_LAUNCH(64, false, false);
@@ -794,22 +905,26 @@ int gemm_tc_bf16_ex(const void* A, const void* B, int64_t M, int64_t N, int64_t 
 
 // fp32 [rows, cols] (ld) -> bf16 [rows, cols16] (ld16), optional ReLU-free straight convert
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t rows,
-                                   int64_t cols, int64_t ld, int64_t ld16) {
+                                   int64_t cols, int64_t ld, int64_t ld16, int64_t lo_off) {
   const int64_t total = rows * ld16;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int64_t r = i / ld16, c = i % ld16;
-    out[i] = __float2bfloat16_rn(c < cols ? in[r * ld + c] : 0.0f);
+    const float x = c < cols ? in[r * ld + c] : 0.0f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    out[i] = h;
+    if (lo_off) out[lo_off + i] = bf16_lo_of(x, h);
   }
 }
 
-int f32_to_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, cudaStream_t stream) {
+int f32_to_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, cudaStream_t stream,
+                int64_t lo_off) {
   const int64_t total = rows * ld16;
   if (total == 0) return 0;
   ProfScope prof("f32_to_bf16", stream);
   int64_t blocks = (total + 255) / 256;
   if (blocks > kNumSMsB200 * 16) blocks = kNumSMsB200 * 16;
-  f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), rows, cols, ld, ld16);
+  f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), rows, cols, ld, ld16, lo_off);
   return check_launch("f32_to_bf16_kernel");
 }
 
@@ -837,7 +952,7 @@ int tb_gemm_bf16_ex(const void* A_bf16, const void* B_bf16, int64_t M, int64_t N
 
 int tb_f32_to_bf16(const float* in, void* out_bf16, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, void* stream) {
   TB_REQUIRE(in && out_bf16, "tb_f32_to_bf16: null pointer");
-  return f32_to_bf16(in, out_bf16, rows, cols, ld, ld16, (cudaStream_t)stream);
+  return f32_to_bf16(in, out_bf16, rows, cols, ld, ld16, (cudaStream_t)stream, 0);
 }
 
 }  // extern "C"

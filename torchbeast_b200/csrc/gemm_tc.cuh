@@ -9,6 +9,12 @@ namespace tb {
 struct TcEpilogue {
   float* C = nullptr; int64_t ldc = 0;               // fp32 output (nullable)
   __nv_bfloat16* C16 = nullptr; int64_t ldc16 = 0;   // bf16 output (nullable) - next GEMM's operand
+  // Split-bf16 ("bf16x3") mode: every operand x is stored as TWO bf16 planes, hi = bf16(x) and lo = bf16(x - hi)
+  // (16-17 significant bits together), and the product is accumulated as hi.hi + hi.lo + lo.hi in the same fp32
+  // TMEM accumulator - fp32-grade results (relative error ~2^-17 per product instead of 2^-9) at 3 MMAs per k-step.
+  // a_lo / b_lo: element offsets from the operand base pointers to their lo planes (both non-zero = split product,
+  // both zero = plain bf16); c16_lo: element offset from C16 to the lo plane of the bf16 output (0 = hi only).
+  int64_t a_lo = 0, b_lo = 0, c16_lo = 0;
   const float* bias = nullptr;                       // [N]
   float scale = 1.0f;                                // applied to the accumulator first (1/255 for uint8 frames)
   int relu = 0;
@@ -50,8 +56,10 @@ int conv_tc_dgrad_implicit(const void* dy_nhwc_bf16, const void* wt_bf16, int64_
 // permP/permQ like the split-K reduce of gemm_tc_bf16_ex) = scale * dY^T . patches; dy_bf16 [Nf*OH*OW, O], O <= 64.
 int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64_t Nf, int H, int W, int C, int KH, int KW, int S,
                            int O, float* dW, int permP, int permQ, float scale, float* partial, int64_t partial_floats,
-                           const char* tag, cudaStream_t stream);
+                           const char* tag, cudaStream_t stream, int64_t dy_lo = 0, int64_t act_lo = 0);
 
-int f32_to_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, cudaStream_t stream);
+// lo_off != 0: also write the lo plane bf16(x - hi) at out + lo_off elements (split-bf16 operands)
+int f32_to_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, cudaStream_t stream,
+                int64_t lo_off = 0);
 
 }  // namespace tb

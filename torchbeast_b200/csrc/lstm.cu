@@ -52,10 +52,18 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
       L.cm = takef(N * H); L.dgates = takef(N * 4 * H); L.bsum = takef(4 * H); L.w_hh_t = takef(int64_t(H + 4) * 4 * Hp);
       L.wp = takef(int64_t(4 * H + 4) * Hp);
       L.xb = L.wihb = L.dgb = L.hmb = L.hmq = L.dgq = L.hq = nullptr;
+      L.xb_lo = L.wihb_lo = L.dgb_lo = L.hmb_lo = 0;
       if (precision) {  // bf16 operand copies (2 bytes per element: take half the float count, rounded up)
         const int64_t in_l = (l == 0) ? In : H;
-        L.xb = takef((N * ld16(in_l) + 1) / 2); L.wihb = takef((int64_t(4) * H * ld16(in_l) + 1) / 2);
-        L.dgb = takef((N * ld16(4 * H) + 1) / 2); L.hmb = takef((N * ld16(H) + 1) / 2);
+        // precision 2 (split-bf16): every GEMM operand also has a lo plane right behind its hi plane
+        auto takeh = [&](int64_t n, int64_t* lo) {
+          const int64_t plane = ((n * 2 + 255) & ~int64_t(255)) / 2;  // elements, 256-byte multiple
+          void* ptr = takef(((precision == 2 ? 2 * plane : plane) + 1) / 2);
+          *lo = precision == 2 ? plane : 0;
+          return ptr;
+        };
+        L.xb = takeh(N * ld16(in_l), &L.xb_lo); L.wihb = takeh(int64_t(4) * H * ld16(in_l), &L.wihb_lo);
+        L.dgb = takeh(N * ld16(4 * H), &L.dgb_lo); L.hmb = takeh(N * ld16(H), &L.hmb_lo);
         L.hmq = takef((N * mma_hq(H) + 1) / 2); L.hq = takef(((N + B) * mma_hq(H) + 1) / 2); L.dgq = takef((int64_t(2) * 4 * B * mma_hq(H) + 1) / 2);
       }
     } else {
@@ -1735,7 +1743,7 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
   const int64_t N = T1 * B;
   const float* xin = x;
   int in_dim = In;
-  if (precision && layers == 2 && wave_fwd_applicable(B, H)) {
+  if (precision == 1 && layers == 2 && wave_fwd_applicable(B, H)) {
     // both layers in one wavefront kernel: only layer 0's input projection is hoisted
     const int Hq = mma_hq(H);
     for (int l = 0; l < 2; ++l) {
@@ -1781,9 +1789,10 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
     TB_TRY(check_launch("add2_kernel"));
     if (precision) {
       const int64_t l16 = ld16(in_dim);
-      TB_TRY(f32_to_bf16(xin, L.xb, N, in_dim, in_dim, l16, st));
-      TB_TRY(pack_weights_bf16(p.w_ih[l], L.wihb, 4 * H, 1, in_dim, l16, st));
+      TB_TRY(f32_to_bf16(xin, L.xb, N, in_dim, in_dim, l16, st, L.xb_lo));
+      TB_TRY(pack_weights_bf16(p.w_ih[l], L.wihb, 4 * H, 1, in_dim, l16, st, L.wihb_lo));
       TcEpilogue te; te.C = L.gates; te.ldc = 4 * H; te.bias = L.bsum; te.tag = "lstm_xproj_fwd";
+      te.a_lo = L.xb_lo; te.b_lo = L.wihb_lo;
       TB_TRY(gemm_tc_bf16(L.xb, L.wihb, N, 4 * H, in_dim, l16, l16, te, st));
     } else {
       GemmEpilogue ep; ep.bias = L.bsum; ep.tag = "lstm_xproj_fwd";
@@ -1791,7 +1800,8 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
                                                     nullptr, st)));
     }
     const int Hp = padded_h(H);
-    const bool use_mma = precision && mma_recurrence_applicable(B, H);
+    // precision 2 (split-bf16 GEMMs) keeps the recurrence itself in exact fp32 (lstm_*_persistent_kernel)
+    const bool use_mma = precision == 1 && mma_recurrence_applicable(B, H);
     if (!use_mma) {  // operands of the fp32 recurrence kernels
       const int64_t tot = int64_t(4 * H + 4) * Hp;
       lstm_pack_whh_kernel<<<(unsigned)((tot + 255) / 256 > 1184 ? 1184 : (tot + 255) / 256), 256, 0, st>>>(p.w_hh[l], L.wp, H, Hp);
@@ -1875,7 +1885,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
   // two layers on the tensor-core backend: ONE wavefront kernel runs both recurrences (and the upper layer's
   // input-gradient product); only the hoisted weight-gradient GEMMs and the lower layer's dx remain per layer
   bool wave_done = false;
-  if (precision && layers == 2 && In <= H && wave_bwd_applicable(B, H)) {
+  if (precision == 1 && layers == 2 && In <= H && wave_bwd_applicable(B, H)) {
     ProfScope prof("lstm_recurrence_bwd", st);
     TB_TRY(lstm2_bwd_wave(ws, p, g, dy, notdone, T1, B, H, st));
     wave_done = true;
@@ -1896,7 +1906,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     const int in_dim = (l == 0) ? In : H;
     float* dxl = (l == 0) ? dx : ws.dx_mid;
     const int Hp = padded_h(H);
-    const bool use_mma = precision && mma_recurrence_applicable(B, H);
+    const bool use_mma = precision == 1 && mma_recurrence_applicable(B, H);
     if (!use_mma) {  // operands of the fp32 recurrence kernels
       const int64_t tot = int64_t(H + 4) * 4 * Hp;
       lstm_pack_whh_t_kernel<<<(unsigned)((tot + 255) / 256 > 1184 ? 1184 : (tot + 255) / 256), 256, 0, st>>>(p.w_hh[l], L.w_hh_t, H, Hp);
@@ -1941,13 +1951,13 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
         forked = false;
       }
       // the tensor-core recurrence wrote the gate gradients in bf16 and summed the bias gradients itself
-      if (!use_mma) TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st));
+      if (!use_mma) TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st, L.dgb_lo));
       const void* hm_b = L.hmb;
-      int64_t hm_ld = lh;
+      int64_t hm_ld = lh, hm_lo = L.hmb_lo;
       if (use_mma) {  // the tensor-core forward recurrence already left the masked h in bf16
-        hm_b = L.hmq; hm_ld = mma_hq(H);
+        hm_b = L.hmq; hm_ld = mma_hq(H); hm_lo = 0;
       } else {
-        TB_TRY(f32_to_bf16(L.hm, L.hmb, N, H, padded_h(H), lh, st));
+        TB_TRY(f32_to_bf16(L.hm, L.hmb, N, H, padded_h(H), lh, st, L.hmb_lo));
       }
       const int64_t kb = (N + 63) / 64;
       int sp = int(kb / 8); if (sp < 1) sp = 1; if (sp > 4) sp = 4;
@@ -1971,8 +1981,10 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
         forked = true;
       }
       te.C = g.w_hh[l]; te.ldc = H;      // dW_hh[4H,H] = dgates^T . hm   (both operands stored [N, .]: MN-major)
+      te.a_lo = L.dgb_lo; te.b_lo = hm_lo;
       TB_TRY(gemm_tc_bf16_ex(L.dgb, hm_b, 4 * H, H, N, lg, hm_ld, true, true, te, sp, wscr, gs));
       te.C = g.w_ih[l]; te.ldc = in_dim;  // dW_ih[4H,in] = dgates^T . x
+      te.b_lo = L.xb_lo;
       TB_TRY(gemm_tc_bf16_ex(L.dgb, L.xb, 4 * H, in_dim, N, lg, li, true, true, te, sp, wscr, gs));
       if (!use_mma) TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));
       cudaError_t e = cudaMemcpyAsync(g.b_hh[l], g.b_ih[l], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, gs);
@@ -1984,6 +1996,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       // dx[N,in] = dgates[N,4H] . W_ih[4H,in]   (W_ih as stored: reduction index is its row index)
       if (!(wave_done && l == 1)) {  // the wavefront kernel already produced the upper layer's dx (= ws.dx_mid)
         TcEpilogue td; td.tag = "lstm_xproj_dgrad"; td.C = dxl; td.ldc = in_dim;
+        td.a_lo = L.dgb_lo; td.b_lo = L.wihb_lo;
         TB_TRY(gemm_tc_bf16_ex(L.dgb, L.wihb, N, in_dim, 4 * H, lg, li, false, true, td, 1, nullptr, st));
       }
     } else {

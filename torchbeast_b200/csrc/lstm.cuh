@@ -26,6 +26,7 @@ struct LstmLayerWs {
   void* wihb;     // bf16 [4H, ld16(In)]     W_ih
   void* dgb;      // bf16 [T1*B, ld16(4H)]   gate gradients
   void* hmb;      // bf16 [T1*B, ld16(H)]    masked recurrent inputs
+  int64_t xb_lo = 0, wihb_lo = 0, dgb_lo = 0, hmb_lo = 0;  // precision 2 (split-bf16): element offsets of the lo planes
   void* hmq;      // bf16 [T1*B, Hq]         masked recurrent inputs written by the tensor-core recurrence (Hq = mma_hq(H))
   void* hq;       // bf16 [(T1+1)*B, Hq]     raw h (slot 0 = initial state) exchanged by the two-layer wavefront kernel
   void* dgq;      // bf16 [2][4, B, Hq]      this step's gate gradients for the tensor-core backward recurrence
@@ -52,8 +53,9 @@ struct LstmWs {
 size_t lstm_ws_bytes(int64_t T1, int64_t B, int In, int H, int layers, int precision);
 LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int precision);
 
-// precision: 0 = fp32 SIMT GEMMs, 1 = bf16 tcgen05 GEMMs for the hoisted projections (the recurrence
-// itself is fp32 either way).
+// precision: 0 = fp32 SIMT GEMMs; 1 = bf16 tcgen05 GEMMs for the hoisted projections and bf16 mma.sync operands in
+// the recurrence; 2 = split-bf16 (hi/lo planes, 3 MMAs) tcgen05 GEMMs with the recurrence in exact fp32.  State, gate
+// activations and accumulation are fp32 in every mode.
 // x [T1*B, In] -> y [T1*B, H]; h0/c0/hN/cN [layers, B, H]; notdone [T1*B] (float, multiplies the state
 // before each step).  splitk: GEMM scratch (kSplitKScratchFloats).
 int lstm_forward(const float* x, const float* notdone, const float* h0, const float* c0, const LstmParams& p,

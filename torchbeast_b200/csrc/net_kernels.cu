@@ -393,7 +393,7 @@ int col2im_bf16_nhwc(const void* dcol, const void* act, void* dact, int64_t N, i
 }
 
 __global__ void pack_weights_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int64_t O, int P,
-                                         int Q, int64_t ld) {
+                                         int Q, int64_t ld, int64_t lo_off) {
   const int64_t total = O * ld;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -404,15 +404,17 @@ __global__ void pack_weights_bf16_kernel(const float* __restrict__ in, __nv_bflo
       const int pp = int(r / Q), q = int(r % Q);
       v = __ldg(in + o * P * Q + int64_t(q) * P + pp);
     }
-    out[i] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = h;
+    if (lo_off) out[lo_off + i] = __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
 
-int pack_weights_bf16(const float* in, void* out, int64_t O, int P, int Q, int64_t ld_out, cudaStream_t stream) {
+int pack_weights_bf16(const float* in, void* out, int64_t O, int P, int Q, int64_t ld_out, cudaStream_t stream, int64_t lo_off) {
   ProfScope prof("weight_pack_bf16", stream);
   const int64_t total = O * ld_out;
   if (total == 0) return 0;
-  pack_weights_bf16_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), O, P, Q, ld_out);
+  pack_weights_bf16_kernel<<<grid_for(total, 256), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), O, P, Q, ld_out, lo_off);
   return check_launch("pack_weights_bf16_kernel");
 }
 
@@ -420,7 +422,7 @@ int pack_weights_bf16(const float* in, void* out, int64_t O, int P, int Q, int64
 //   stride 1: out[c][(kh*KW + kw)*O + o]
 //   stride 2: out[((py*2 + px)*C + c)][((i*(KW/2) + j)*O + o]  with kh = py + 2i, kw = px + 2j
 __global__ void pack_dgrad_weights_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int O, int C,
-                                               int KH, int KW, int S) {
+                                               int KH, int KW, int S, int64_t lo_off) {
   const int64_t total = int64_t(O) * C * KH * KW;
   const int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -433,20 +435,23 @@ __global__ void pack_dgrad_weights_bf16_kernel(const float* __restrict__ in, __n
     const int py = kh & 1, i = kh >> 1, px = kw & 1, j = kw >> 1;
     dst = (int64_t((py * 2 + px) * C + c)) * ((KH / 2) * (KW / 2) * O) + int64_t(i * (KW / 2) + j) * O + o;
   }
-  out[dst] = __float2bfloat16_rn(v);
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  out[dst] = h;
+  if (lo_off) out[lo_off + dst] = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-int pack_dgrad_weights_bf16(const float* in, void* out_bf16, int O, int C, int KH, int KW, int S, cudaStream_t stream) {
+int pack_dgrad_weights_bf16(const float* in, void* out_bf16, int O, int C, int KH, int KW, int S, cudaStream_t stream,
+                            int64_t lo_off) {
   TB_REQUIRE(in && out_bf16 && (S == 1 || (S == 2 && KH % 2 == 0 && KW % 2 == 0)), "pack_dgrad_weights_bf16: bad arguments");
   ProfScope prof("weight_pack_bf16", stream);
   const int64_t total = int64_t(O) * C * KH * KW;
   pack_dgrad_weights_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out_bf16), O,
-                                                                                     C, KH, KW, S);
+                                                                                     C, KH, KW, S, lo_off);
   return check_launch("pack_dgrad_weights_bf16_kernel");
 }
 
 __global__ void colsum_partial_bf16_kernel(const __nv_bfloat16* __restrict__ X, float* __restrict__ part, int64_t M,
-                                           int64_t ncols, int64_t ld, int64_t rows_per_slab) {
+                                           int64_t ncols, int64_t ld, int64_t rows_per_slab, int64_t lo_off) {
   __shared__ float sm[8][33];
   const int64_t n = int64_t(blockIdx.x) * 32 + threadIdx.x;
   const int64_t r0 = int64_t(blockIdx.y) * rows_per_slab;
@@ -454,7 +459,10 @@ __global__ void colsum_partial_bf16_kernel(const __nv_bfloat16* __restrict__ X, 
   if (r1 > M) r1 = M;
   float s = 0.0f;
   if (n < ncols)
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += __bfloat162float(X[r * ld + n]);
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+      s += __bfloat162float(X[r * ld + n]);
+      if (lo_off) s += __bfloat162float(X[lo_off + r * ld + n]);
+    }
   sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && n < ncols) {
@@ -468,12 +476,16 @@ __global__ void colsum_partial_bf16_kernel(const __nv_bfloat16* __restrict__ X, 
 // Dense [M, ncols] bf16 with ncols in {8,16,32,64}: every thread streams 16-byte vectors whose column
 // group never changes (the grid stride is a multiple of the row length), so the kernel is a plain
 // coalesced read of the whole matrix followed by a small shared-memory fold.
-__global__ void colsum_dense_bf16_kernel(const uint4* __restrict__ X, float* __restrict__ part, int64_t nvec, int cg) {
+__global__ void colsum_dense_bf16_kernel(const uint4* __restrict__ X, float* __restrict__ part, int64_t nvec, int cg,
+                                         int64_t lo_vec) {
   __shared__ float sm[256][9];
   float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;  // multiple of cg (cg | 256)
 #pragma unroll 4
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) acc_bf16x8(__ldg(X + i), s);
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    acc_bf16x8(__ldg(X + i), s);
+    if (lo_vec) acc_bf16x8(__ldg(X + lo_vec + i), s);  // split-bf16 gradient: hi + lo planes
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) sm[threadIdx.x][j] = s[j];
   __syncthreads();
@@ -485,15 +497,16 @@ __global__ void colsum_dense_bf16_kernel(const uint4* __restrict__ X, float* __r
   }
 }
 
-int colsum_bf16(const void* X, float* out, int64_t M, int64_t ncols, int64_t ld, float* scratch, cudaStream_t stream) {
+int colsum_bf16(const void* X, float* out, int64_t M, int64_t ncols, int64_t ld, float* scratch, cudaStream_t stream,
+                int64_t lo_off) {
   ProfScope prof("bias_grad_colsum", stream);
   if (ncols == 0) return 0;
   TB_REQUIRE(X && out && scratch, "colsum_bf16: null pointer");
   if (ld == ncols && (ncols == 8 || ncols == 16 || ncols == 32 || ncols == 64) && M >= 4096 &&
-      (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+      (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (lo_off & 7) == 0) {
     const int cg = int(ncols / 8);
     const int blocks = kColsumSlabs;  // partials [blocks][ncols] fit the caller's scratch
-    colsum_dense_bf16_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(X), scratch, M * cg, cg);
+    colsum_dense_bf16_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(X), scratch, M * cg, cg, lo_off / 8);
     int rc = check_launch("colsum_dense_bf16_kernel");
     if (rc) return rc;
     colsum_final_kernel<<<(unsigned)((ncols + 31) / 32), dim3(32, 8), 0, stream>>>(scratch, out, ncols, blocks);
@@ -505,7 +518,7 @@ int colsum_bf16(const void* X, float* out, int64_t M, int64_t ncols, int64_t ld,
   const int64_t rows_per_slab = (M + slabs - 1) / slabs;
   dim3 grid((unsigned)((ncols + 31) / 32), (unsigned)slabs);
   colsum_partial_bf16_kernel<<<grid, dim3(32, 8), 0, stream>>>(static_cast<const __nv_bfloat16*>(X), scratch, M, ncols, ld,
-                                                                rows_per_slab);
+                                                                rows_per_slab, lo_off);
   int rc = check_launch("colsum_partial_bf16_kernel");
   if (rc) return rc;
   colsum_final_kernel<<<(unsigned)((ncols + 31) / 32), dim3(32, 8), 0, stream>>>(scratch, out, ncols, slabs);

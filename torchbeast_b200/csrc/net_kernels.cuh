@@ -49,10 +49,14 @@ int im2col_bf16_nhwc(const void* act_bf16, void* col_bf16, int64_t N, int H, int
 int col2im_bf16_nhwc(const void* dcol_bf16, const void* act_bf16, void* dact_bf16, int64_t N, int H, int W, int C,
                      int KH, int KW, int S, cudaStream_t stream);
 // out_bf16[o*ld_out + p*Q + q] = in[o*P*Q + q*P + p]; columns [P*Q, ld_out) zero
-int pack_weights_bf16(const float* in, void* out_bf16, int64_t O, int P, int Q, int64_t ld_out, cudaStream_t stream);
+// lo_off != 0 (all three below): split-bf16 - also write / read the lo plane at +lo_off elements
+int pack_weights_bf16(const float* in, void* out_bf16, int64_t O, int P, int Q, int64_t ld_out, cudaStream_t stream,
+                      int64_t lo_off = 0);
 // weights [O,C,KH,KW] fp32 -> bf16 B operand of the implicit input-gradient GEMMs (see gemm_tc.cuh)
-int pack_dgrad_weights_bf16(const float* in, void* out_bf16, int O, int C, int KH, int KW, int S, cudaStream_t stream);
+int pack_dgrad_weights_bf16(const float* in, void* out_bf16, int O, int C, int KH, int KW, int S, cudaStream_t stream,
+                            int64_t lo_off = 0);
 // colsum over a bf16 matrix (bias gradients), fp32 accumulation
-int colsum_bf16(const void* X_bf16, float* out, int64_t M, int64_t ncols, int64_t ld, float* scratch, cudaStream_t stream);
+int colsum_bf16(const void* X_bf16, float* out, int64_t M, int64_t ncols, int64_t ld, float* scratch, cudaStream_t stream,
+                int64_t lo_off = 0);
 
 }  // namespace tb

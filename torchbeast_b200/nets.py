@@ -176,7 +176,13 @@ class AtariNet(FlatParamModule):
     """CUDA AtariNet (reference monobeast.py:545-635).  conv 8/4 -> 4/2 -> 3/1 -> fc 512 ->
     cat[reward, one-hot last action] -> optional 2-layer LSTM(519) -> policy / baseline heads."""
 
-    PRECISIONS = {"fp32": 0, "bf16": 1}
+    # "bf16x3" (default): every dense product on tcgen05 tensor cores with SPLIT bf16 operands - x = hi + lo, two bf16
+    #     planes, accumulated as hi.hi + hi.lo + lo.hi in fp32 (3 MMAs, ~2^-17 relative per product): holds the
+    #     reference's fp32 results to the 1e-4 parity contract (tests/test_learner_baseline_gpu.py);
+    # "bf16": single-plane bf16 operands (1 MMA, 2^-9): fastest, mixed-precision tolerances only;
+    # "fp32": exact fp32 FFMA (SIMT) GEMMs - the slow parity anchor.
+    PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2}
+    DEFAULT_PRECISION = "bf16x3"
 
     def __init__(self, observation_shape, num_actions, use_lstm=False, device=None, precision=None):
         super().__init__()
@@ -195,12 +201,10 @@ class AtariNet(FlatParamModule):
             self.core.num_layers = 2
             self.core.hidden_size = self.core_size
             self.core.input_size = self.core_size
-        # "bf16": conv/fc/LSTM-projection GEMMs on tcgen05 tensor cores (bf16 operands, fp32
-        # accumulation, fp32 master weights/gradients); "fp32": exact SIMT GEMMs (parity anchor).
         import os
-        self.precision = precision or os.environ.get("TB_PRECISION", "bf16")
+        self.precision = precision or os.environ.get("TB_PRECISION", self.DEFAULT_PRECISION)
         if self.precision not in self.PRECISIONS:
-            raise _lib.TorchBeastB200Error("precision must be 'fp32' or 'bf16'")
+            raise _lib.TorchBeastB200Error("precision must be one of %s" % sorted(self.PRECISIONS))
         self._ws = None
         self._ws_key = None
         count = _lib.lib().tb_atarinet_param_count(num_actions, int(use_lstm))
@@ -368,9 +372,10 @@ class ResNet(FlatParamModule):
         self.reset_parameters_like_torch()
         if use_lstm:
             self.core.num_layers, self.core.hidden_size, self.core.input_size = 1, 256, 257
-        self.precision = precision or os.environ.get("TB_PRECISION", "bf16")
+        # the ResNet trunk still runs on patch-matrix GEMMs: fp32 (parity, default) or single-plane bf16
+        self.precision = precision or os.environ.get("TB_RESNET_PRECISION", "fp32")
         if self.precision not in self.PRECISIONS:
-            raise _lib.TorchBeastB200Error("precision must be 'fp32' or 'bf16'")
+            raise _lib.TorchBeastB200Error("ResNet precision must be 'fp32' or 'bf16'")
         self._ws = None
         self._ws_key = None
         count = _lib.lib().tb_resnet_param_count(num_actions, int(use_lstm))
