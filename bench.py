@@ -45,12 +45,21 @@ def parse():
     ap.add_argument("--use_lstm", type=int, default=1)
     ap.add_argument("--net", default="atari", choices=["atari", "resnet"],
                     help="atari: monobeast AtariNet (BASELINE configs[1]); resnet: polybeast IMPALA ResNet (configs[3])")
-    ap.add_argument("--precision", default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=None, choices=["fp32", "bf16", "bf16x3"],
+                    help="GEMM backend (default: the package default, bf16x3 = split-bf16 tensor-core products, parity-green)")
     ap.add_argument("--num_actions", type=int, default=6)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_profile", action="store_true")
     ap.add_argument("--graph", type=int, default=1, help="e2e path: replay the step as one CUDA graph (falls back to eager)")
     return ap.parse_args()
+
+
+# what the arithmetic is, per backend (the line's `dtype`)
+DTYPE_NAMES = {
+    "bf16x3": "bf16x3 (split-bf16 hi+lo operands, 3 tcgen05 MMAs per product, fp32 accumulate; fp32 state/loss/optimizer)",
+    "bf16": "bf16 (single-plane bf16 operands, fp32 accumulate)",
+    "fp32": "f32",
+}
 
 
 def flags_ns(T, B):
@@ -496,7 +505,7 @@ def main():
     line = dict(
         metric="learner_frames_per_sec", value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=args.steps,
         warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
-        dtype=("bf16" if model.precision == "bf16" else "f32"),
+        dtype=DTYPE_NAMES.get(model.precision, model.precision),
         data="synthetic", config=dict(config, l2="4 rotating input batches per rank (%.0f MB) > 126 MB L2; ~2.3 GB of "
                                       "activations written per step" % (NROT * h2d_bytes / 1e6)),
         e2e=dict(value=frames / (e2e_ms * 1e-3), unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes,
@@ -519,7 +528,7 @@ def main():
         N = (T + 1) * B
         flops = gemm_flops_table(N, A, "resnet" if args.net == "resnet" else args.use_lstm)
         nbytes = hbm_bytes_table(N, T, B, A, args.use_lstm, model.flat_params.numel())
-        gbytes = gemm_bytes_table(N, A, args.use_lstm, model.precision == "bf16") if args.net == "atari" else {}
+        gbytes = gemm_bytes_table(N, A, args.use_lstm, model.precision != "fp32") if args.net == "atari" else {}
         ops = []
         for name, (tot, cnt) in agg.items():
             per_step = tot / PSTEPS

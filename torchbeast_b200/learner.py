@@ -184,7 +184,8 @@ class GraphedLearner:
         optimizer.lr_from_device = True
         optimizer.sync_lr_to_device()
         # warm up on a side stream (allocations, one-time attribute calls), then capture
-        snapshot = (model.flat_params.clone(), optimizer.square_avg.clone())
+        snapshot = (model.flat_params.clone(), optimizer.square_avg.clone(),
+                    None if optimizer.momentum_buffer is None else optimizer.momentum_buffer.clone(), optimizer._steps)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -201,6 +202,9 @@ class GraphedLearner:
         # undo the warm-up / capture-time updates so training starts from the caller's weights
         model.flat_params.copy_(snapshot[0])
         optimizer.square_avg.copy_(snapshot[1])
+        if snapshot[2] is not None:
+            optimizer.momentum_buffer.copy_(snapshot[2])
+        optimizer._steps = snapshot[3]
         if actor_model is not None and hasattr(actor_model, "copy_params_from"):
             actor_model.copy_params_from(model)
 

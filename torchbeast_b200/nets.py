@@ -7,6 +7,7 @@ gradients into one flat gradient buffer): that is what the C-ABI kernels, the fu
 clip+RMSprop step and the single NCCL all-reduce operate on.
 """
 import collections
+import weakref
 
 import torch
 from torch import nn
@@ -51,6 +52,10 @@ def _numel(shape):
 class FlatParamModule(nn.Module):
     """nn.Module whose Parameters alias one flat fp32 buffer (`flat_params`) in spec order."""
 
+    # flat buffer address -> module: lets load_state_dict() recognise a sibling's state_dict (whose tensors alias that
+    # sibling's flat buffer) and take the one-copy path without hanging anything on the dict itself
+    _flat_owners = weakref.WeakValueDictionary()
+
     def _build_flat(self, spec, device):
         self._spec = list(spec)
         total = sum(_numel(s) for _, s in self._spec)
@@ -71,6 +76,7 @@ class FlatParamModule(nn.Module):
             self._views.append((p, off, n, shape))
             off += n
         self._total = total
+        FlatParamModule._flat_owners[self._flat.data_ptr()] = self
 
     # keep the aliasing across .to()/.cuda()/.float(): move the flat buffer, re-point the views
     def _apply(self, fn, recurse=True):
@@ -78,6 +84,7 @@ class FlatParamModule(nn.Module):
         if new_flat.dtype != torch.float32:
             raise _lib.TorchBeastB200Error("torchbeast_b200 networks are float32 only")
         self._flat = new_flat.contiguous()
+        FlatParamModule._flat_owners[self._flat.data_ptr()] = self
         self._flat_grad = None
         for p, off, n, shape in self._views:
             p.data = self._flat[off:off + n].view(shape)
@@ -99,9 +106,15 @@ class FlatParamModule(nn.Module):
         return self._flat_grad
 
     def attach_grads(self):
+        """Point every Parameter's .grad at its slice of the flat gradient buffer.  A gradient that lives elsewhere
+        (autograd wrote it: model(...) -> loss.backward()) is COPIED into its slice first, so the fused optimizer
+        steps on it instead of silently discarding it."""
         fg = self.flat_grad
         for p, off, n, shape in self._views:
-            if p.grad is None or p.grad.data_ptr() != fg.data_ptr() + 4 * off:
+            if p.grad is None:
+                p.grad = fg[off:off + n].view(shape)
+            elif p.grad.data_ptr() != fg.data_ptr() + 4 * off:
+                fg[off:off + n].copy_(p.grad.detach().reshape(-1))
                 p.grad = fg[off:off + n].view(shape)
         return fg
 
@@ -109,18 +122,35 @@ class FlatParamModule(nn.Module):
         """actor_model.load_state_dict(model.state_dict()) as ONE device copy (monobeast.py:295)."""
         self._flat.copy_(other._flat, non_blocking=True)
 
+    def _aliased_sibling(self, state_dict):
+        """The FlatParamModule whose live flat buffer EVERY tensor of `state_dict` aliases at this module's own
+        offsets (i.e. `sibling.state_dict()` as returned, unedited), or None."""
+        names = [n for n, _ in self._spec]
+        if len(state_dict) != len(names):
+            return None
+        first = state_dict.get(names[0])
+        if not isinstance(first, torch.Tensor):
+            return None
+        src = FlatParamModule._flat_owners.get(first.data_ptr())
+        if src is None or src is self or src._total != self._total or list(src._spec) != list(self._spec):
+            return None
+        base = src._flat.data_ptr()
+        for (name, shape), (_, off, n, _s) in zip(self._spec, self._views):
+            t = state_dict.get(name)
+            if not isinstance(t, torch.Tensor) or t.data_ptr() != base + 4 * off or tuple(t.shape) != tuple(shape) \
+                    or t.dtype != torch.float32 or not t.is_contiguous():
+                return None
+        return src
+
     def load_state_dict(self, state_dict, strict=True, assign=False):
-        src = getattr(state_dict, "_tb_flat_source", None)
-        if src is not None and src._total == self._total and [s for s in src._spec] == [s for s in self._spec]:
+        """Reference checkpoints / state_dicts load key by key; `actor.load_state_dict(model.state_dict())`
+        (monobeast.py:295) is recognised by aliasing and becomes ONE device copy.  The dict itself carries nothing
+        but tensors, so torch.save / torch.load(weights_only=True) / copy.deepcopy behave as for any nn.Module."""
+        src = self._aliased_sibling(state_dict)
+        if src is not None:
             self.copy_params_from(src)
             return torch.nn.modules.module._IncompatibleKeys([], [])
         return super().load_state_dict(state_dict, strict=strict)
-
-    def state_dict(self, *args, **kwargs):
-        sd = super().state_dict(*args, **kwargs)
-        if not args and not kwargs.get("prefix"):
-            sd._tb_flat_source = self  # lets a sibling FlatParamModule take the one-copy path
-        return sd
 
     def reset_parameters_like_torch(self, seed=None):
         """Same init distributions as the reference modules (nn.Conv2d / nn.Linear / nn.LSTM

@@ -29,13 +29,46 @@ class RMSprop(torch.optim.Optimizer):
         # learning rate as a device scalar: lets a captured CUDA graph see scheduler updates
         self._lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=flat.device)
         self.lr_from_device = False
-        # per-parameter views so state_dict() looks like torch.optim.RMSprop's
-        for p, off, n, shape in model._views:
+        self._point_state_at_flat()
+
+    def _point_state_at_flat(self, step=None):
+        """Per-parameter views of the flat buffers so state_dict() looks like torch.optim.RMSprop's."""
+        for p, off, n, shape in self.model._views:
             st = self.state[p]
-            st["step"] = torch.tensor(0.0)
+            if step is not None or "step" not in st:
+                st["step"] = torch.tensor(float(step or 0.0))
             st["square_avg"] = self.square_avg[off:off + n].view(shape)
             if self.momentum_buffer is not None:
                 st["momentum_buffer"] = self.momentum_buffer[off:off + n].view(shape)
+
+    def load_state_dict(self, state_dict):
+        """Resume like the reference does (`optimizer.load_state_dict(checkpoint["optimizer_state_dict"])`,
+        polybeast_learner.py:535-548): torch replaces the per-parameter state tensors with copies, so the loaded
+        values are copied INTO the flat buffers the fused kernel reads and the per-parameter entries are re-pointed
+        at them.  Accepts state_dicts of torch.optim.RMSprop (same per-parameter keys) and of this class."""
+        self._loading = True  # torch calls __setstate__ with the loaded copies: keep them until they are in the flat buffers
+        try:
+            super().load_state_dict(state_dict)
+        finally:
+            self._loading = False
+        steps = 0
+        with torch.no_grad():
+            for p, off, n, shape in self.model._views:
+                st = self.state.get(p, {})
+                if "square_avg" in st:
+                    self.square_avg[off:off + n].copy_(st["square_avg"].reshape(-1))
+                if self.momentum_buffer is not None and st.get("momentum_buffer") is not None:
+                    self.momentum_buffer[off:off + n].copy_(st["momentum_buffer"].reshape(-1))
+                if "step" in st:
+                    steps = max(steps, int(float(st["step"])))
+        self._steps = steps
+        self._point_state_at_flat(step=steps)
+        self._lr_dev.fill_(float(self.param_groups[0]["lr"]))
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        if hasattr(self, "model") and not getattr(self, "_loading", False):
+            self._point_state_at_flat()
 
     @torch.no_grad()
     def step(self, closure=None, max_grad_norm=None):
@@ -58,6 +91,11 @@ class RMSprop(torch.optim.Optimizer):
             "tb_clip_rmsprop_step_f32")
         self._steps += 1
         return None
+
+    def state_dict(self):
+        for st in self.state.values():  # torch.optim.RMSprop keeps a per-parameter step count in its state_dict
+            st["step"] = torch.tensor(float(self._steps))
+        return super().state_dict()
 
     def sync_lr_to_device(self):
         """Publish param_groups[0]['lr'] to the device scalar a captured graph reads (async fill)."""
