@@ -67,7 +67,7 @@ def test_learn_step_matches_reference(fname, precision):
         np.testing.assert_allclose(float(gr.double().norm()), float(g["grad_stats/" + n][2]), rtol=2e-3, atol=1e-6, err_msg=n)
         np.testing.assert_allclose(p.detach().cpu().flatten()[idx].numpy(), g["param_sample/" + n], rtol=1e-4, atol=5e-4,
                                    err_msg=n)
-        np.testing.assert_allclose(float(p.detach().double().norm()), float(g["param_stats/" + n][2]), rtol=1e-4, err_msg=n)
+        np.testing.assert_allclose(float(p.detach().double().norm()), float(g["param_stats/" + n][2]), rtol=1e-3, err_msg=n)
     np.testing.assert_allclose(np.sqrt(total), float(g["clipped_grad_norm"]), rtol=1e-4)
     for (n, a), (_, b) in zip(actor.named_parameters(), model.named_parameters()):
         assert torch.equal(a, b), n

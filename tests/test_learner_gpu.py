@@ -1,8 +1,8 @@
 """GPU parity of the network + full learn() step (torchbeast_b200.monobeast) against
  (a) golden fixtures produced by the reference's own monobeast.learn (tests/golden/learn_*.npz),
  (b) the torch-CPU oracle (oracle/learner_torch.py) tensor by tensor.
-All cases here run the fp32 backend (precision="fp32"); the bf16 tensor-core backend has its own file
-(test_learner_bf16_gpu.py).  Tolerances (fp32 backend): forward outputs rtol 1e-4 / atol 1e-4 (north_star 1e-4 fp32); scalar
+Every case runs on BOTH parity-grade backends: "bf16x3" (the default: split-bf16 tensor-core products) and "fp32"
+(SIMT anchor); the single-plane bf16 backend has its own file (test_learner_bf16_gpu.py).  Tolerances (both backends): forward outputs rtol 1e-4 / atol 1e-4 (north_star 1e-4 fp32); scalar
 losses rtol 2e-5; gradients rtol 2e-3 with an absolute floor of 2e-4 x the tensor's norm (different
 summation order over up to 1e6-term reductions)."""
 import types
@@ -54,9 +54,13 @@ def to_cuda(batch):
     return {k: v.cuda() for k, v in batch.items()}
 
 
+PARITY_BACKENDS = ["bf16x3", "fp32"]
+
+
+@pytest.mark.parametrize("precision", PARITY_BACKENDS)
 @pytest.mark.parametrize("fname", ATARI_CASES + LSTM_CASES)
-def test_forward_matches_reference_and_oracle(fname):
-    g, model, actor, batch, params, state, opt, sched = build_case(fname)
+def test_forward_matches_reference_and_oracle(fname, precision):
+    g, model, actor, batch, params, state, opt, sched = build_case(fname, precision)
     model.eval()
     with torch.no_grad():
         out, new_state = model(to_cuda(batch), tuple(s.cuda() for s in state))
@@ -72,10 +76,11 @@ def test_forward_matches_reference_and_oracle(fname):
         np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("precision", PARITY_BACKENDS)
 @pytest.mark.parametrize("fname", ATARI_CASES + LSTM_CASES)
-def test_learn_step_matches_reference(fname):
+def test_learn_step_matches_reference(fname, precision):
     from torchbeast_b200 import monobeast
-    g, model, actor, batch, params, state, opt, sched = build_case(fname)
+    g, model, actor, batch, params, state, opt, sched = build_case(fname, precision)
     flags = flags_for(g)
     stats = monobeast.learn(flags, actor, model, to_cuda(batch), tuple(s.cuda() for s in state), opt, sched)
     for k in ("total_loss", "pg_loss", "baseline_loss", "entropy_loss"):
@@ -101,11 +106,12 @@ def test_learn_step_matches_reference(fname):
         assert torch.equal(a, b), n
 
 
+@pytest.mark.parametrize("precision", PARITY_BACKENDS)
 @pytest.mark.parametrize("fname", ["learn_atari_T4_B2.npz", "learn_atari_T20_B4.npz", "learn_atari_lstm_T4_B2.npz"])
-def test_full_gradients_vs_oracle(fname):
-    """Every gradient element against oracle autograd (fp64 oracle -> tight bound on our fp32)."""
+def test_full_gradients_vs_oracle(fname, precision):
+    """Every gradient element against oracle autograd (fp64 oracle -> tight bound on our fp32 / split-bf16)."""
     from torchbeast_b200 import learner
-    g, model, actor, batch, params, state, opt, sched = build_case(fname)
+    g, model, actor, batch, params, state, opt, sched = build_case(fname, precision)
     p64 = {k: v.double() for k, v in params.items()}
     o = LT.learner_step(p64, batch, tuple(s.double() for s in state), net="atari", update=False)
     cb = to_cuda(batch)
@@ -118,7 +124,9 @@ def test_full_gradients_vs_oracle(fname):
     for n, p in model.named_parameters():
         ref = o["grads"][n].numpy()
         got = p.grad.cpu().numpy()
-        tol = 1e-4 * max(np.abs(ref).max(), 1e-6)
+        # fp32 backend: 1e-4 x the tensor's largest gradient; split-bf16: 3e-3 x (its ~2^-17 products move the handful of
+        # ReLU pre-activations that sit at the rounding threshold, measured 1.2e-3 on conv1 at T=20,B=4)
+        tol = (1e-4 if precision == "fp32" else 3e-3) * max(np.abs(ref).max(), 1e-6)
         np.testing.assert_allclose(got, ref, rtol=1e-3, atol=tol, err_msg=n)
 
 

@@ -52,7 +52,7 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
       L.cm = takef(N * H); L.dgates = takef(N * 4 * H); L.bsum = takef(4 * H); L.w_hh_t = takef(int64_t(H + 4) * 4 * Hp);
       L.wp = takef(int64_t(4 * H + 4) * Hp);
       L.xb = L.wihb = L.dgb = L.hmb = L.hmq = L.dgq = L.hq = nullptr;
-      L.xb_lo = L.wihb_lo = L.dgb_lo = L.hmb_lo = 0;
+      L.xb_lo = L.wihb_lo = L.dgb_lo = L.hmb_lo = L.hq_lo = L.hmq_lo = L.dgq_lo = 0;
       if (precision) {  // bf16 operand copies (2 bytes per element: take half the float count, rounded up)
         const int64_t in_l = (l == 0) ? In : H;
         // precision 2 (split-bf16): every GEMM operand also has a lo plane right behind its hi plane
@@ -64,7 +64,8 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
         };
         L.xb = takeh(N * ld16(in_l), &L.xb_lo); L.wihb = takeh(int64_t(4) * H * ld16(in_l), &L.wihb_lo);
         L.dgb = takeh(N * ld16(4 * H), &L.dgb_lo); L.hmb = takeh(N * ld16(H), &L.hmb_lo);
-        L.hmq = takef((N * mma_hq(H) + 1) / 2); L.hq = takef(((N + B) * mma_hq(H) + 1) / 2); L.dgq = takef((int64_t(2) * 4 * B * mma_hq(H) + 1) / 2);
+        L.hmq = takeh(N * mma_hq(H), &L.hmq_lo); L.hq = takeh((N + B) * mma_hq(H), &L.hq_lo);
+        L.dgq = takeh(int64_t(2) * 4 * B * mma_hq(H), &L.dgq_lo);
       }
     } else {
       L = LstmLayerWs();
@@ -75,6 +76,7 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
   w.wg_scratch = (precision && layers == 2) ? takef(int64_t(4) * 4 * H * (((H > In ? H : In) + 31) & ~31)) : nullptr;
   w.dgp = takef(int64_t(2) * 4 * B * padded_h(H));
   w.sync = reinterpret_cast<unsigned*>(takef(64));
+  w.flags = reinterpret_cast<unsigned*>(takef(1024));
   w.Hp = padded_h(H);
   w.bytes = off;
   return w;
@@ -1565,6 +1567,292 @@ __global__ void lstm_init_state_q_kernel(const float* __restrict__ h0, const flo
   }
 }
 
+
+// =========================================================================================
+// Split-precision ("bf16x3") recurrence, forward, two stacked layers as one wavefront (precision 2).
+//
+// Same wavefront as lstm2_fwd_wave_mma_kernel (layer 0 at t = s, layer 1 at t = s-1 per wave step, the
+// layer-1 input projection riding on the pass), but every MMA operand is a hi/lo bf16 PAIR (x = hi + lo,
+// hi.hi + hi.lo + lo.hi in fp32: ~2^-17 relative per product, fp32-grade) so that the recurrence holds the
+// 1e-4 parity contract the bf16 kernel cannot.  What changed with the 3x MMA count (measured,
+// profiles/ubench_lstm_r2.txt: mma.sync.m16n8k16 runs at 2.0 cycles / MMA / SM = 2036 flop/clk/SM):
+//   * 11 MMA warps x 3 k16-steps cover K = 528 exactly (33 k-steps): no padded k-steps, weights of all three
+//     matrices as hi AND lo B fragments in registers (72 per thread) for all steps;
+//   * h is exchanged as two bf16 planes (hq: raw h, slot t+1 = h_t) written with 8-byte stores (4 units x
+//     bf16 of one row and plane) and pulled as 4 x 34 KB tiles per step with cp.async (77 B/clk/SM measured);
+//   * the cell state lives in a register of the thread that owns (layer, unit, row) for all steps;
+//   * the grid barrier is per-CTA FLAGS instead of one contended counter: producer = stores, bar.sync,
+//     fence.acq_rel.gpu (600 cycles measured), st flag[cta] = step; consumers = one thread per producer
+//     spinning on its flag with relaxed loads, one acquire load, bar.sync.
+// CTA = kStepUnits hidden units x 4 gates of BOTH layers, B <= 32 rows, ceil(H/16) <= 33.
+// =========================================================================================
+constexpr int kSplitWarps = 11;
+constexpr int kSplitThreads = kSplitWarps * 32;
+constexpr int kSplitK = 3;  // k16 steps per warp
+
+struct WaveFwdSplitArgs {
+  const float* w_hh0; const float* w_ih1; const float* w_hh1; const float* bias1;
+  const float* c0;          // [2, B, H] initial cell state
+  float* gates[2]; float* hs[2]; float* cs[2]; float* cm[2];
+  __nv_bfloat16* hq[2];     // raw h planes [(T1+1)*B, Hq] (+ hq_lo): slot 0 = initial state, slot t+1 = h_t
+  __nv_bfloat16* hmq[2];    // masked recurrent inputs [T1*B, Hq] (+ hmq_lo): operand of the weight-gradient GEMMs
+  int64_t hq_lo, hmq_lo;
+  const float* nd; unsigned* flags;
+  int T1, B, H, Hq; unsigned nctas;
+};
+
+__device__ __forceinline__ void split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - hf.x, v1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void st_relaxed_u32(unsigned* p, unsigned v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// hi.hi + hi.lo + lo.hi (small terms first) of one m16n8k16 tile product
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
+                                     uint32_t bl0, uint32_t bl1) {
+  mma_bf16_16816(c, al, bh0, bh1);
+  mma_bf16_16816(c, ah, bl0, bl1);
+  mma_bf16_16816(c, ah, bh0, bh1);
+}
+
+__global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(WaveFwdSplitArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_b[];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int H = a.H, Hq = a.Hq, B = a.B;
+  // tiles: [0] h0 hi, [1] h0 lo, [2] h1 hi, [3] h1 lo; each [32][Hq]
+  __nv_bfloat16* X = reinterpret_cast<__nv_bfloat16*>(smem_b);
+  const int tile = 32 * Hq;
+  typedef float PartT[2][16][33];
+  PartT* part = reinterpret_cast<PartT*>(smem_b + size_t(4) * tile * 2);  // [11 warps][set][col][row]
+  __shared__ float act_s[2][4][kStepUnits][33];
+  __shared__ float nd_s[2][32];
+  const int j0 = blockIdx.x * kStepUnits;
+  const int rows = (B < 32) ? B : 32;
+  const int ksteps = (H + 15) / 16;
+  const int ks0 = wrp * kSplitK;
+  // B fragments (hi, lo) of this CTA's 16 gate rows (o = gate*4 + unit) of the three weight matrices, this warp's k-steps
+  uint32_t bh[3][kSplitK][2][2], bl[3][kSplitK][2][2];
+  {
+    const float* wm[3] = {a.w_hh0, a.w_ih1, a.w_hh1};
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int sk = 0; sk < kSplitK; ++sk)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int o = nt * 8 + (lane >> 2);
+          const int g = o >> 2, u = o & 3;
+          const float* wr = wm[m] + (int64_t(g) * H + j0 + u) * H;
+          const int k = (ks0 + sk) * 16 + (lane & 3) * 2;
+          float v[4] = {0.f, 0.f, 0.f, 0.f};
+          if (j0 + u < H && ks0 + sk < ksteps) {
+            if (k < H) v[0] = wr[k];
+            if (k + 1 < H) v[1] = wr[k + 1];
+            if (k + 8 < H) v[2] = wr[k + 8];
+            if (k + 9 < H) v[3] = wr[k + 9];
+          }
+          split_pack(v[0], v[1], bh[m][sk][nt][0], bl[m][sk][nt][0]);
+          split_pack(v[2], v[3], bh[m][sk][nt][1], bl[m][sk][nt][1]);
+        }
+  }
+  // activation role (warps 0..7): gate columns c0 = wrp and c1 = wrp + 8 of both layers, row = lane
+  const bool actrole = wrp < 8;
+  const int cA = wrp, cB = wrp + 8;                     // col = gate*4 + unit
+  const bool okA = actrole && lane < rows && j0 + (cA & 3) < H, okB = actrole && lane < rows && j0 + (cB & 3) < H;
+  const int64_t gA = int64_t(cA >> 2) * H + j0 + (cA & 3), gB = int64_t(cB >> 2) * H + j0 + (cB & 3);
+  const float bias1A = okA ? a.bias1[gA] : 0.f, bias1B = okB ? a.bias1[gB] : 0.f;
+  // update role (threads 0..255): layer ul, row ur, unit uu - the 4 units of a row sit in 4 adjacent lanes
+  const bool updthread = tid < 256;
+  const int ul = tid >> 7, ur = (tid & 127) >> 2, uu = tid & 3;
+  const bool updrole = updthread && ur < rows && j0 + uu < H;
+  float* const cm_u = ul ? a.cm[1] : a.cm[0];
+  float* const cs_u = ul ? a.cs[1] : a.cs[0];
+  float* const hs_u = ul ? a.hs[1] : a.hs[0];
+  __nv_bfloat16* const hq_u = ul ? a.hq[1] : a.hq[0];
+  __nv_bfloat16* const hmq_u = ul ? a.hmq[1] : a.hmq[0];
+  float c_state = updrole ? a.c0[(int64_t(ul) * B + ur) * H + j0 + uu] : 0.f;  // c_{t-1} of this (layer, row, unit)
+  const int chunks_per_row = (ksteps * 16) / 8;          // 16-byte chunks the MMAs read (the row padding is never touched)
+  const int nchunk = rows * chunks_per_row;
+  for (int s = 0; s <= a.T1; ++s) {
+    const bool act0 = (s < a.T1), act1 = (s >= 1);
+    // inputs that do not depend on other CTAs: issued before the wait
+    float preA = 0.f, preB = 0.f;
+    if (act0) {
+      if (okA) preA = a.gates[0][(int64_t(s) * B + lane) * 4 * H + gA];
+      if (okB) preB = a.gates[0][(int64_t(s) * B + lane) * 4 * H + gB];
+    }
+    const int tu = s - ul;                                 // time step of this thread's update role
+    const bool upd = updrole && (ul ? act1 : act0);
+    float nd_t = 0.f, nd_n = 0.f;
+    if (upd) {
+      nd_t = __ldg(a.nd + int64_t(tu) * B + ur);
+      if (tu < a.T1 - 1) nd_n = __ldg(a.nd + int64_t(tu + 1) * B + ur);
+    }
+    if (s > 0) {  // every CTA has published wave step s-1
+      if (tid < int(a.nctas)) {
+        while (ld_relaxed_u32(a.flags + tid) < unsigned(s)) {}
+        (void)ld_acquire_u32(a.flags + tid);
+      }
+    }
+    __syncthreads();
+    {
+      const __nv_bfloat16* src0 = a.hq[0] + int64_t(s) * B * Hq;
+      const __nv_bfloat16* src1 = a.hq[1] + int64_t(s > 0 ? s - 1 : 0) * B * Hq;
+      for (int i = tid; i < nchunk; i += kSplitThreads) {
+        const int r = i / chunks_per_row, c = i - r * chunks_per_row;
+        const int off = r * Hq + c * 8;
+        cp_async16(X + off, src0 + off);
+        cp_async16(X + tile + off, src0 + a.hq_lo + off);
+        if (act1) {
+          cp_async16(X + 2 * tile + off, src1 + off);
+          cp_async16(X + 3 * tile + off, src1 + a.hq_lo + off);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (tid < 64) {
+      const int l = tid >> 5, r = tid & 31, t = s - l;
+      nd_s[l][r] = (r < rows && t >= 0 && t < a.T1) ? __ldg(a.nd + int64_t(t) * B + r) : 0.f;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    {
+      float acc0[2][2][4], accI[2][2][4], acc1[2][2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { acc0[mt][nt][e] = 0.f; accI[mt][nt][e] = 0.f; acc1[mt][nt][e] = 0.f; }
+#pragma unroll
+      for (int sk = 0; sk < kSplitK; ++sk) {
+        if (ks0 + sk < ksteps) {
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) {
+            uint32_t ah[4], al[4];
+            const int off = (mt * 16 + (lane & 15)) * Hq + (ks0 + sk) * 16 + (lane >> 4) * 8;
+            ldmatrix_x4(ah, X + off);
+            ldmatrix_x4(al, X + tile + off);
+            if (act0) {
+              mma3(acc0[mt][0], ah, al, bh[0][sk][0][0], bh[0][sk][0][1], bl[0][sk][0][0], bl[0][sk][0][1]);
+              mma3(acc0[mt][1], ah, al, bh[0][sk][1][0], bh[0][sk][1][1], bl[0][sk][1][0], bl[0][sk][1][1]);
+            }
+            if (act1) {
+              mma3(accI[mt][0], ah, al, bh[1][sk][0][0], bh[1][sk][0][1], bl[1][sk][0][0], bl[1][sk][0][1]);
+              mma3(accI[mt][1], ah, al, bh[1][sk][1][0], bh[1][sk][1][1], bl[1][sk][1][0], bl[1][sk][1][1]);
+              ldmatrix_x4(ah, X + 2 * tile + off);
+              ldmatrix_x4(al, X + 3 * tile + off);
+              mma3(acc1[mt][0], ah, al, bh[2][sk][0][0], bh[2][sk][0][1], bl[2][sk][0][0], bl[2][sk][0][1]);
+              mma3(acc1[mt][1], ah, al, bh[2][sk][1][0], bh[2][sk][1][1], bl[2][sk][1][0], bl[2][sk][1][1]);
+            }
+          }
+        }
+      }
+      // the done-mask is a 0/1 row scale: applied to the recurrent PRODUCTS (raw h tiles are exchanged)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r = mt * 16 + (lane >> 2);
+        const float m0a = nd_s[0][r], m0b = nd_s[0][r + 8], m1a = nd_s[1][r], m1b = nd_s[1][r + 8];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int c = nt * 8 + (lane & 3) * 2;
+          part[wrp][0][c][r] = acc0[mt][nt][0] * m0a; part[wrp][0][c + 1][r] = acc0[mt][nt][1] * m0a;
+          part[wrp][0][c][r + 8] = acc0[mt][nt][2] * m0b; part[wrp][0][c + 1][r + 8] = acc0[mt][nt][3] * m0b;
+          part[wrp][1][c][r] = accI[mt][nt][0] + acc1[mt][nt][0] * m1a;
+          part[wrp][1][c + 1][r] = accI[mt][nt][1] + acc1[mt][nt][1] * m1a;
+          part[wrp][1][c][r + 8] = accI[mt][nt][2] + acc1[mt][nt][2] * m1b;
+          part[wrp][1][c + 1][r + 8] = accI[mt][nt][3] + acc1[mt][nt][3] * m1b;
+        }
+      }
+    }
+    __syncthreads();
+    float g0A = 0.f, g0B = 0.f, g1A = 0.f, g1B = 0.f;
+    if (actrole) {
+      float d0A = 0.f, d0B = 0.f, d1A = 0.f, d1B = 0.f;
+#pragma unroll
+      for (int w = 0; w < kSplitWarps; ++w) {  // fixed order: deterministic
+        d0A += part[w][0][cA][lane]; d0B += part[w][0][cB][lane];
+        d1A += part[w][1][cA][lane]; d1B += part[w][1][cB][lane];
+      }
+      const bool tanhA = (cA >> 2) == 2, tanhB = (cB >> 2) == 2;
+      if (act0) {
+        if (okA) { const float p = preA + d0A; g0A = tanhA ? tanhf(p) : sigmoidf_(p); }
+        if (okB) { const float p = preB + d0B; g0B = tanhB ? tanhf(p) : sigmoidf_(p); }
+      }
+      if (act1) {
+        if (okA) { const float p = bias1A + d1A; g1A = tanhA ? tanhf(p) : sigmoidf_(p); }
+        if (okB) { const float p = bias1B + d1B; g1B = tanhB ? tanhf(p) : sigmoidf_(p); }
+      }
+      act_s[0][cA >> 2][cA & 3][lane] = g0A; act_s[0][cB >> 2][cB & 3][lane] = g0B;
+      act_s[1][cA >> 2][cA & 3][lane] = g1A; act_s[1][cB >> 2][cB & 3][lane] = g1B;
+    }
+    __syncthreads();
+    float c_new = 0.f, h_new = 0.f, cm_in = 0.f;
+    if (updthread) {
+      if (upd) {
+        const float ig = act_s[ul][0][uu][ur], fg = act_s[ul][1][uu][ur], gg = act_s[ul][2][uu][ur], og = act_s[ul][3][uu][ur];
+        cm_in = c_state * nd_t;      // state *= notdone_t before the step (monobeast.py:603-606)
+        c_new = fg * cm_in + ig * gg;
+        h_new = og * tanhf(c_new);
+        c_state = c_new;
+      }
+      // publish raw h_t: the 4 units of a row sit in 4 adjacent lanes -> one 8-byte store per (row, plane)
+      const bool live = (ul ? act1 : act0);
+      const __nv_bfloat16 hh = __float2bfloat16_rn(h_new);
+      const __nv_bfloat16 hl = __float2bfloat16_rn(h_new - __bfloat162float(hh));
+      const uint32_t vh = uint32_t(__bfloat16_as_ushort(hh)), vl = uint32_t(__bfloat16_as_ushort(hl));
+      const uint32_t ph = vh | (__shfl_down_sync(0xffffffffu, vh, 1) << 16), pl = vl | (__shfl_down_sync(0xffffffffu, vl, 1) << 16);
+      const uint32_t ph2 = __shfl_down_sync(0xffffffffu, ph, 2), pl2 = __shfl_down_sync(0xffffffffu, pl, 2);
+      if (live && uu == 0 && ur < rows) {
+        __nv_bfloat16* d = hq_u + (int64_t(tu + 1) * B + ur) * Hq + j0;
+        *reinterpret_cast<uint2*>(d) = make_uint2(ph, ph2);
+        *reinterpret_cast<uint2*>(d + a.hq_lo) = make_uint2(pl, pl2);
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && s < a.T1) {
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      st_relaxed_u32(a.flags + blockIdx.x, unsigned(s + 1));
+    }
+    // ---- everything below is consumed by this CTA or after the kernel: off the critical path ----
+    if (actrole) {
+      if (act0) {
+        if (okA) a.gates[0][(int64_t(s) * B + lane) * 4 * H + gA] = g0A;
+        if (okB) a.gates[0][(int64_t(s) * B + lane) * 4 * H + gB] = g0B;
+      }
+      if (act1) {
+        if (okA) a.gates[1][(int64_t(s - 1) * B + lane) * 4 * H + gA] = g1A;
+        if (okB) a.gates[1][(int64_t(s - 1) * B + lane) * 4 * H + gB] = g1B;
+      }
+    }
+    if (updthread) {
+      // masked recurrent input of the NEXT step (h_t * notdone_{t+1}) for the weight-gradient GEMMs, as hi / lo planes
+      const float hm = h_new * nd_n;
+      const __nv_bfloat16 mh = __float2bfloat16_rn(hm);
+      const __nv_bfloat16 ml = __float2bfloat16_rn(hm - __bfloat162float(mh));
+      const uint32_t vh = uint32_t(__bfloat16_as_ushort(mh)), vl = uint32_t(__bfloat16_as_ushort(ml));
+      const uint32_t ph = vh | (__shfl_down_sync(0xffffffffu, vh, 1) << 16), pl = vl | (__shfl_down_sync(0xffffffffu, vl, 1) << 16);
+      const uint32_t ph2 = __shfl_down_sync(0xffffffffu, ph, 2), pl2 = __shfl_down_sync(0xffffffffu, pl, 2);
+      const bool live = (ul ? act1 : act0) && tu < a.T1 - 1;
+      if (live && uu == 0 && ur < rows) {
+        __nv_bfloat16* d = hmq_u + (int64_t(tu + 1) * B + ur) * Hq + j0;
+        *reinterpret_cast<uint2*>(d) = make_uint2(ph, ph2);
+        *reinterpret_cast<uint2*>(d + a.hmq_lo) = make_uint2(pl, pl2);
+      }
+      if (upd) {
+        const int64_t o = (int64_t(tu) * B + ur) * H + j0 + uu;
+        cs_u[o] = c_new;
+        hs_u[o] = h_new;
+        cm_u[o] = cm_in;
+      }
+    }
+  }
+}
+
 template <typename Kernel>
 static int coop_fit(Kernel kernel, dim3 grid, size_t smem, size_t* attr_smem) {
   if (*attr_smem < smem) {
@@ -1640,6 +1928,74 @@ static int lstm2_fwd_wave(LstmWs& ws, const LstmParams& p, float* y, const float
   e = cudaLaunchCooperativeKernel((const void*)lstm2_fwd_wave_mma_kernel, grid, dim3(kStepThreads), args, smem, st);
   TB_REQUIRE(e == cudaSuccess, "lstm2_fwd_wave_mma_kernel: %s", cudaGetErrorString(e));
   return check_launch("lstm2_fwd_wave_mma_kernel");
+}
+
+// slot 0 of the split recurrence's planes: hq = split(h0) (raw), hmq = split(h0 * nd_0); row padding zero
+__global__ void lstm_init_state_split_kernel(const float* __restrict__ h0, const float* __restrict__ nd,
+                                             __nv_bfloat16* __restrict__ hq, int64_t hq_lo, __nv_bfloat16* __restrict__ hmq,
+                                             int64_t hmq_lo, int B, int H, int Hq) {
+  const int64_t total = int64_t(B) * Hq;
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = int(i / Hq), k = int(i % Hq);
+  const float h = k < H ? h0[int64_t(b) * H + k] : 0.f;
+  const float hm = h * nd[b];
+  const __nv_bfloat16 a = __float2bfloat16_rn(h), m = __float2bfloat16_rn(hm);
+  hq[i] = a; hq[hq_lo + i] = __float2bfloat16_rn(h - __bfloat162float(a));
+  hmq[i] = m; hmq[hmq_lo + i] = __float2bfloat16_rn(hm - __bfloat162float(m));
+}
+
+static size_t g_fwd_split_attr = 0;
+static size_t wave_fwd_split_smem(int Hq) { return size_t(4) * 32 * Hq * 2 + sizeof(float) * kSplitWarps * 2 * 16 * 33; }
+// precision 2, two layers: the split-bf16 wavefront kernel (TB_LSTM_SPLIT=0 keeps the exact-fp32 recurrence kernels)
+static bool wave_fwd_split_applicable(int64_t B, int In, int H) {
+  const char* e = getenv("TB_LSTM_SPLIT");
+  if (e && e[0] == '0') return false;
+  if (!persistent_enabled() || B > 32 || In != H || (H + 15) / 16 > kSplitWarps * kSplitK) return false;
+  dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
+  if (int(grid.x) > kSplitThreads || grid.x > 512) return false;
+  if (g_fwd_split_attr < wave_fwd_split_smem(mma_hq(H))) {
+    if (cudaFuncSetAttribute(lstm2_fwd_wave_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             int(wave_fwd_split_smem(mma_hq(H)))) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    g_fwd_split_attr = wave_fwd_split_smem(mma_hq(H));
+  }
+  int dev = 0, sms = 0, coop = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm2_fwd_wave_split_kernel, kSplitThreads,
+                                                             wave_fwd_split_smem(mma_hq(H))) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return int64_t(per_sm) * sms >= int64_t(grid.x);
+}
+
+static int lstm2_fwd_wave_split(LstmWs& ws, const LstmParams& p, float* y, const float* notdone, const float* c0, int64_t T1,
+                                int64_t B, int H, cudaStream_t st) {
+  const int Hq = mma_hq(H);
+  dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
+  cudaError_t e = cudaMemsetAsync(ws.flags, 0, sizeof(unsigned) * 512, st);
+  TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
+  WaveFwdSplitArgs a;
+  a.w_hh0 = p.w_hh[0]; a.w_ih1 = p.w_ih[1]; a.w_hh1 = p.w_hh[1]; a.bias1 = ws.layer[1].bsum; a.c0 = c0;
+  for (int l = 0; l < 2; ++l) {
+    const LstmLayerWs& L = ws.layer[l];
+    a.gates[l] = L.gates; a.hs[l] = (l == 1) ? y : L.hs; a.cs[l] = L.cs; a.cm[l] = L.cm;
+    a.hq[l] = static_cast<__nv_bfloat16*>(L.hq); a.hmq[l] = static_cast<__nv_bfloat16*>(L.hmq);
+  }
+  a.hq_lo = ws.layer[0].hq_lo; a.hmq_lo = ws.layer[0].hmq_lo;
+  TB_REQUIRE(ws.layer[1].hq_lo == a.hq_lo && ws.layer[1].hmq_lo == a.hmq_lo && a.hq_lo > 0, "lstm: split planes missing");
+  a.nd = notdone; a.flags = ws.flags;
+  a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nctas = grid.x;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)lstm2_fwd_wave_split_kernel, grid, dim3(kSplitThreads), args,
+                                  wave_fwd_split_smem(Hq), st);
+  TB_REQUIRE(e == cudaSuccess, "lstm2_fwd_wave_split_kernel: %s", cudaGetErrorString(e));
+  return check_launch("lstm2_fwd_wave_split_kernel");
 }
 
 static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, const float* dy, const float* notdone,
@@ -1782,6 +2138,46 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
     }
     return 0;
   }
+  if (precision == 2 && layers == 2 && wave_fwd_split_applicable(B, In, H)) {
+    // split-bf16 wavefront: layer 0's input projection is one split tcgen05 GEMM, everything sequential is ONE kernel
+    const int Hq = mma_hq(H);
+    for (int l = 0; l < 2; ++l) {
+      LstmLayerWs& L = ws.layer[l];
+      const int in_l = (l == 0) ? In : H;
+      const int64_t l16 = ld16(in_l);
+      add2_kernel<<<(4 * H + 255) / 256, 256, 0, st>>>(p.b_ih[l], p.b_hh[l], L.bsum, 4 * H);
+      TB_TRY(check_launch("add2_kernel"));
+      TB_TRY(pack_weights_bf16(p.w_ih[l], L.wihb, 4 * H, 1, in_l, l16, st, L.wihb_lo));  // layer 1's: backward (dx)
+      if (l == 0) {
+        TB_TRY(f32_to_bf16(x, L.xb, N, In, In, l16, st, L.xb_lo));
+        TcEpilogue te; te.C = L.gates; te.ldc = 4 * H; te.bias = L.bsum; te.tag = "lstm_xproj_fwd";
+        te.a_lo = L.xb_lo; te.b_lo = L.wihb_lo;
+        TB_TRY(gemm_tc_bf16(L.xb, L.wihb, N, 4 * H, In, l16, l16, te, st));
+      }
+      // zero the row padding (columns [H, Hq)) of every slot of both planes; the kernels only write [0, 4*ceil(H/4))
+      cudaError_t eq = cudaMemsetAsync(L.hmq, 0, size_t(L.hmq_lo + N * Hq) * 2, st);
+      if (eq == cudaSuccess) eq = cudaMemsetAsync(L.hq, 0, size_t(L.hq_lo + (N + B) * Hq) * 2, st);
+      TB_REQUIRE(eq == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(eq));
+      lstm_init_state_split_kernel<<<(unsigned)((B * Hq + 255) / 256), 256, 0, st>>>(
+          h0 + int64_t(l) * B * H, notdone, static_cast<__nv_bfloat16*>(L.hq), L.hq_lo, static_cast<__nv_bfloat16*>(L.hmq), L.hmq_lo,
+          int(B), H, Hq);
+      TB_TRY(check_launch("lstm_init_state_split_kernel"));
+    }
+    {
+      ProfScope prof("lstm_recurrence_fwd", st);
+      TB_TRY(lstm2_fwd_wave_split(ws, p, y, notdone, c0, T1, B, H, st));
+    }
+    for (int l = 0; l < 2; ++l) {
+      const float* hs = (l == 1) ? y : ws.layer[0].hs;
+      cudaError_t e = cudaMemcpyAsync(hN + int64_t(l) * B * H, hs + (T1 - 1) * B * H, sizeof(float) * B * H,
+                                      cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess)
+        e = cudaMemcpyAsync(cN + int64_t(l) * B * H, ws.layer[l].cs + (T1 - 1) * B * H, sizeof(float) * B * H,
+                            cudaMemcpyDeviceToDevice, st);
+      TB_REQUIRE(e == cudaSuccess, "lstm: state copy: %s", cudaGetErrorString(e));
+    }
+    return 0;
+  }
   for (int l = 0; l < layers; ++l) {
     LstmLayerWs& L = ws.layer[l];
     float* hs = (l == layers - 1) ? y : L.hs;
@@ -1885,6 +2281,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
   // two layers on the tensor-core backend: ONE wavefront kernel runs both recurrences (and the upper layer's
   // input-gradient product); only the hoisted weight-gradient GEMMs and the lower layer's dx remain per layer
   bool wave_done = false;
+  const bool split_fwd = precision == 2 && layers == 2 && wave_fwd_split_applicable(B, In, H);  // same predicate as the forward
   if (precision == 1 && layers == 2 && In <= H && wave_bwd_applicable(B, H)) {
     ProfScope prof("lstm_recurrence_bwd", st);
     TB_TRY(lstm2_bwd_wave(ws, p, g, dy, notdone, T1, B, H, st));
@@ -1954,8 +2351,17 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       if (!use_mma) TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st, L.dgb_lo));
       const void* hm_b = L.hmb;
       int64_t hm_ld = lh, hm_lo = L.hmb_lo;
+      const void* x_b = L.xb;
+      int64_t x_ld = li, x_lo = L.xb_lo;
       if (use_mma) {  // the tensor-core forward recurrence already left the masked h in bf16
         hm_b = L.hmq; hm_ld = mma_hq(H); hm_lo = 0;
+      } else if (split_fwd) {
+        // the split wavefront forward left the masked h as hi / lo planes, and layer 1's input (= layer 0's raw h_t) is
+        // slot t+1 of layer 0's exchange planes
+        hm_b = L.hmq; hm_ld = mma_hq(H); hm_lo = L.hmq_lo;
+        if (l == 1) {
+          x_b = static_cast<const __nv_bfloat16*>(ws.layer[0].hq) + B * mma_hq(H); x_ld = mma_hq(H); x_lo = ws.layer[0].hq_lo;
+        }
       } else {
         TB_TRY(f32_to_bf16(L.hm, L.hmb, N, H, padded_h(H), lh, st, L.hmb_lo));
       }
@@ -1984,8 +2390,8 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       te.a_lo = L.dgb_lo; te.b_lo = hm_lo;
       TB_TRY(gemm_tc_bf16_ex(L.dgb, hm_b, 4 * H, H, N, lg, hm_ld, true, true, te, sp, wscr, gs));
       te.C = g.w_ih[l]; te.ldc = in_dim;  // dW_ih[4H,in] = dgates^T . x
-      te.b_lo = L.xb_lo;
-      TB_TRY(gemm_tc_bf16_ex(L.dgb, L.xb, 4 * H, in_dim, N, lg, li, true, true, te, sp, wscr, gs));
+      te.b_lo = x_lo;
+      TB_TRY(gemm_tc_bf16_ex(L.dgb, x_b, 4 * H, in_dim, N, lg, x_ld, true, true, te, sp, wscr, gs));
       if (!use_mma) TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));
       cudaError_t e = cudaMemcpyAsync(g.b_hh[l], g.b_ih[l], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, gs);
       TB_REQUIRE(e == cudaSuccess, "lstm: bias grad copy: %s", cudaGetErrorString(e));

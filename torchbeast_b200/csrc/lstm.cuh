@@ -27,6 +27,7 @@ struct LstmLayerWs {
   void* dgb;      // bf16 [T1*B, ld16(4H)]   gate gradients
   void* hmb;      // bf16 [T1*B, ld16(H)]    masked recurrent inputs
   int64_t xb_lo = 0, wihb_lo = 0, dgb_lo = 0, hmb_lo = 0;  // precision 2 (split-bf16): element offsets of the lo planes
+  int64_t hq_lo = 0, hmq_lo = 0, dgq_lo = 0;               // same for the recurrence kernels' exchange / masked-h planes
   void* hmq;      // bf16 [T1*B, Hq]         masked recurrent inputs written by the tensor-core recurrence (Hq = mma_hq(H))
   void* hq;       // bf16 [(T1+1)*B, Hq]     raw h (slot 0 = initial state) exchanged by the two-layer wavefront kernel
   void* dgq;      // bf16 [2][4, B, Hq]      this step's gate gradients for the tensor-core backward recurrence
@@ -42,6 +43,7 @@ struct LstmWs {
   float* dc;      // [B, H] carry
   float* dx_mid;  // [T1*B, H] gradient w.r.t. the output of layer 0 (input of layer 1)
   unsigned* sync; // [64] grid-barrier counters of the persistent recurrence kernels (zeroed per launch)
+  unsigned* flags; // [1024] per-CTA step flags of the split-precision recurrence kernels (forward [0,512), backward [512,1024))
   float* wg_scratch;  // split-K scratch private to the weight-gradient GEMMs (two layers, bf16 backend): lets them run on a
                       // side stream beside the caller's trunk backward, which uses the caller's scratch
   float* dgp;     // [2][4, B, Hp] (double-buffered for the persistent backward)
