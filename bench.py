@@ -50,7 +50,10 @@ def parse():
     ap.add_argument("--num_actions", type=int, default=6)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_profile", action="store_true")
-    ap.add_argument("--graph", type=int, default=1, help="e2e path: replay the step as one CUDA graph (falls back to eager)")
+    ap.add_argument("--graph", type=int, default=1, help="replay the step as one CUDA graph (falls back to eager)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --B columns per GPU (default, the driver's scaling run); strong: --B columns in total, B/N per GPU")
+    ap.add_argument("--no_dp_check", action="store_true", help="skip the multi-GPU gradient / replica check before the timed runs")
     return ap.parse_args()
 
 
@@ -233,10 +236,12 @@ def gemm_flops_table(N, A, use_lstm):
     return t
 
 
-def gemm_bytes_table(N, A, use_lstm, bf16):
-    """Algorithmic operand + result bytes of the tagged AtariNet GEMM ops (patch matrices are streamed once per
-    product) - with K of 64..576 most of these products are HBM streams, not tensor-pipe work."""
-    e = 2 if bf16 else 4
+def gemm_bytes_table(N, A, use_lstm, precision):
+    """ALGORITHMIC operand + result bytes of the tagged AtariNet GEMM ops - with K of 64..576 most of these products
+    are HBM streams, not tensor-pipe work.  Activations count 2 B (bf16), 4 B (bf16x3: hi + lo plane, or fp32); conv1's
+    input counts as the 1-byte uint8 frames (the bf16 image the kernels stage is an implementation cost, not algorithmic)."""
+    bf16 = precision != "fp32"
+    e = {"bf16": 2, "bf16x3": 4}.get(precision, 4)
     M1, M2, M3 = N * 400, N * 81, N * 49
     e1 = 2 if bf16 else 1  # conv1 patch matrix: bf16 (tensor-core backend) or uint8 (fp32 backend)
     t = {
@@ -247,12 +252,12 @@ def gemm_bytes_table(N, A, use_lstm, bf16):
         "conv2_dgrad": M2 * 64 * e + M2 * 512 * e, "conv3_dgrad": M3 * 64 * e + M3 * 576 * e,
         "fc_dgrad": N * 512 * e + 512 * 3136 * e + 2 * N * 3136 * e,
     }
-    if bf16:  # implicit-GEMM convolutions: the activation (or the bf16 frame image) is the operand - read once, no patch matrix
-        img = N * 28224 * 2
-        t.update({"conv1_fwd": img + M1 * 32 * 2, "conv1_wgrad": img + M1 * 32 * 2,
-                  "conv2_fwd": M1 * 32 * 2 + M2 * 64 * 2, "conv2_wgrad": M1 * 32 * 2 + M2 * 64 * 2,
-                  "conv3_fwd": M2 * 64 * 2 + M3 * 64 * 2, "conv3_wgrad": M2 * 64 * 2 + M3 * 64 * 2,
-                  "conv2_dgrad": M2 * 64 * 2 + 2 * M1 * 32 * 2, "conv3_dgrad": M3 * 64 * 2 + 2 * M2 * 64 * 2})  # dY + mask + dX
+    if bf16:  # implicit-GEMM convolutions: the activation (or the frames) is the operand - read once, no patch matrix
+        img = N * 28224  # uint8 frames
+        t.update({"conv1_fwd": img + M1 * 32 * e, "conv1_wgrad": img + M1 * 32 * e,
+                  "conv2_fwd": M1 * 32 * e + M2 * 64 * e, "conv2_wgrad": M1 * 32 * e + M2 * 64 * e,
+                  "conv3_fwd": M2 * 64 * e + M3 * 64 * e, "conv3_wgrad": M2 * 64 * e + M3 * 64 * e,
+                  "conv2_dgrad": M2 * 64 * e + M1 * 32 * 2 + M1 * 32 * e, "conv3_dgrad": M3 * 64 * e + M2 * 64 * 2 + M2 * 64 * e})  # dY + mask + dX
     if use_lstm:
         H = 512 + 1 + A
         t.update({"lstm_xproj_fwd": 2 * (N * H * e + 4 * H * H * e + N * 4 * H * 4),
@@ -284,11 +289,16 @@ def hbm_bytes_table(N, T, B, A, use_lstm, nparams):
     }
 
 
-def run_reference(args):
-    """CPU arm: the oracle port of the reference's learn step on the host cores."""
+def run_reference(args, world=1):
+    """CPU arm: the oracle port of the reference's learn step on the host cores (the reference itself is PyTorch-on-CPU
+    code that cannot travel to the box; the port is pinned to the reference's outputs by tests/test_oracle_golden.py).
+    Honours --steps / --warmup.  Each step trains on the job's GLOBAL batch (B per GPU x N columns) unless that would
+    exceed the time budget (TB_CPU_BASELINE_BUDGET_S, default 240 s for the whole run): then every step is a bounded
+    sample of `cols` batch columns of the same rollout shape - frames/s is per column, so the sample does not bias it."""
     from oracle import learner_torch as LT
     T, B, A = args.T, args.B, args.num_actions
-    budget_s = float(os.environ.get("TB_CPU_BASELINE_BUDGET_S", "60"))
+    Bg = B * world if args.scaling == "weak" else B
+    budget_s = float(os.environ.get("TB_CPU_BASELINE_BUDGET_S", "240"))
     net = getattr(args, "net", "atari")
     shapes = (LT.resnet_param_shapes if net == "resnet" else LT.atarinet_param_shapes)(A, bool(args.use_lstm))
     p = LT.random_params(shapes, seed=0)
@@ -311,22 +321,99 @@ def run_reference(args):
         if dt > 4 * best[0]:
             break
     torch.set_num_threads(best[1])
-    batch = synthetic_host_batch(T, B, A, seed=1, pin=False)
-    state = tuple(torch.zeros(*st_shape(B)) for _ in range(2)) if args.use_lstm else ()
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    # size the per-step sample: time one step on min(Bg, 8) columns, extrapolate linearly in columns
+    probe_cols = min(Bg, 8)
+    pb = synthetic_host_batch(T, probe_cols, A, seed=1, pin=False)
+    ps = tuple(torch.zeros(*st_shape(probe_cols)) for _ in range(2)) if args.use_lstm else ()
+    t0 = time.perf_counter()
+    LT.learner_step(p, pb, ps, net=net, num_actions=A)
+    per_col = (time.perf_counter() - t0) / probe_cols
+    cols = int(max(1, min(Bg, budget_s / max(per_col * (steps + warm), 1e-9))))
+    batch = synthetic_host_batch(T, cols, A, seed=1, pin=False)
+    state = tuple(torch.zeros(*st_shape(cols)) for _ in range(2)) if args.use_lstm else ()
     sq = None
-    steps, warm = max(1, min(args.steps, 10)), 1
-    tw = time.perf_counter()
     for _ in range(warm):
         o = LT.learner_step(p, batch, state, net=net, square_avg=sq, num_actions=A)
         p, sq = o["params"], o["square_avg"]
-    tw = time.perf_counter() - tw
-    steps = max(1, min(steps, int(budget_s / max(tw, 1e-3))))  # bounded sample: ~budget_s of CPU work
     t0 = time.perf_counter()
     for _ in range(steps):
         o = LT.learner_step(p, batch, state, net=net, square_avg=sq, num_actions=A)
         p, sq = o["params"], o["square_avg"]
     dt = (time.perf_counter() - t0) / steps
-    return dict(value=T * B / dt, ms_per_step=dt * 1e3, steps=steps, warmup=warm, cores=torch.get_num_threads())
+    return dict(value=T * cols / dt, ms_per_step=dt * 1e3 * (Bg / cols), steps=steps, warmup=warm, cores=torch.get_num_threads(),
+                cols=cols, global_cols=Bg,
+                sample="%d timed + %d warm-up learn steps of oracle/learner_torch.py (port of monobeast.learn) on %d of the %d "
+                       "batch columns of the global T=%d rollout per step" % (steps, warm, cols, Bg, T))
+
+
+def make_config(args, world):
+    T, B, A = args.T, args.B, args.num_actions
+    per_gpu = B if args.scaling == "weak" else B // max(world, 1)
+    if args.net == "resnet":
+        workload = "IMPALA ResNet(84x84x4 u8)%s + V-trace learner step, T=%d B=%d per GPU, synthetic frames" % (
+            "+LSTM(257->256)" if args.use_lstm else "", T, per_gpu)
+    else:
+        workload = "AtariNet(84x84x4 u8)%s + V-trace learner step, T=%d B=%d per GPU, synthetic frames" % (
+            "+LSTM(2x519)" if args.use_lstm else "", T, per_gpu)
+    return dict(workload=workload, T=T, B_per_gpu=per_gpu, global_batch=per_gpu * max(world, 1), num_actions=A,
+                use_lstm=bool(args.use_lstm), scaling=args.scaling,
+                parallelism="dp%d over batch columns, one SUM all-reduce of the flat gradient (two buckets, the LSTM + heads "
+                            "bucket overlapped with the trunk backward)" % world)
+
+
+def dp_check(args, world, rank, dev, A):
+    """Multi-GPU correctness on the hardware: one step on a full global batch by rank 0 alone vs the
+    same batch column-sharded over all ranks + the SUM all-reduce -> flat gradient difference; then every rank steps and
+    the replicas' parameters must be BIT-identical."""
+    import torch.distributed as dist
+    from torchbeast_b200 import learner, monobeast, optim
+    T = args.T
+    Bg = max(world, (args.B // world) * world)
+    flags = flags_ns(T, Bg)
+    full = {k: v.to(dev) for k, v in synthetic_host_batch(T, Bg, A, seed=4242, pin=False).items()}
+
+    def fresh():
+        m = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm), precision=args.precision)
+        m.reset_parameters_like_torch(seed=7)
+        return m
+
+    def grads(m, batch, state, reduce):
+        out = m.learner_forward(batch, state)
+        loss = learner.impala_loss_fwd_bwd(batch["policy_logits"][1:], out.policy_logits[:-1], batch["action"][1:], batch["reward"][1:],
+                                           batch["done"][1:], out.baseline[:-1], out.baseline[-1])
+        if reduce:
+            fg = learner._backward_with_overlapped_all_reduce(m, loss.grad_logits, loss.grad_values)
+        else:
+            fg = m.learner_backward(loss.grad_logits, loss.grad_values)
+        return fg, loss.losses
+
+    m = fresh()
+    st_full = m.initial_state(Bg)
+    shard, st = learner.shard_rollout(full, st_full, rank, world)
+    g_dp, l_dp = grads(m, shard, st, True)
+    g_dp = g_dp.clone()
+    l_sum = l_dp.clone()
+    dist.all_reduce(l_sum)
+    res = {}
+    if rank == 0:
+        m1 = fresh()
+        g_full, l_full = grads(m1, full, m1.initial_state(Bg), False)
+        d = (g_dp.double() - g_full.double())
+        res["grad_rel_l2"] = float(d.norm() / g_full.double().norm())
+        res["grad_max_over_max"] = float(d.abs().max() / g_full.abs().max())
+        res["loss_rel"] = float((l_sum[3] - l_full[3]).abs() / l_full[3].abs())
+    opt = optim.RMSprop(m, lr=0.00048, momentum=0, eps=0.01, alpha=0.99)
+    opt.step(max_grad_norm=flags.grad_norm_clipping)
+    torch.cuda.synchronize()
+    bits = m.flat_params.view(torch.int32).to(torch.int64)
+    sig = torch.stack([bits.sum(), (bits * torch.arange(1, bits.numel() + 1, device=dev) % 1000003).sum()])
+    sigs = [torch.zeros_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig)
+    res["replicas_bit_identical"] = bool(all(torch.equal(sigs[0], x) for x in sigs))
+    res["global_batch"] = Bg
+    res["cols_per_rank"] = Bg // world
+    return res
 
 
 def main():
@@ -334,27 +421,24 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    T, B, A = args.T, args.B, args.num_actions
-    if args.net == "resnet":
-        workload = "IMPALA ResNet(84x84x4 u8)%s + V-trace learner step, T=%d B=%d per GPU, synthetic frames" % (
-            "+LSTM(257->256)" if args.use_lstm else "", T, B)
-    else:
-        workload = "AtariNet(84x84x4 u8)%s + V-trace learner step, T=%d B=%d per GPU, synthetic frames" % (
-            "+LSTM(2x519)" if args.use_lstm else "", T, B)
-    config = dict(workload=workload, T=T, B_per_gpu=B, global_batch=B * max(world, 1), num_actions=A,
-                  use_lstm=bool(args.use_lstm), parallelism="dp%d over batch columns, one NCCL all-reduce of the flat gradient" % world)
+    T, A = args.T, args.num_actions
+    config = make_config(args, world)
+    B = config["B_per_gpu"]
+    if args.scaling == "strong" and args.B % max(world, 1):
+        raise SystemExit("--scaling strong needs --B divisible by the number of GPUs")
 
     if args.impl == "reference":
         if rank != 0:
             return
-        r = run_reference(args)
+        r = run_reference(args, world)
         line = dict(
             impl="reference", metric="learner_frames_per_sec", value=r["value"], unit="frames/s", n_gpus=args.gpus,
-            steps=r["steps"], warmup=r["warmup"], ms_per_step=r["ms_per_step"], higher_is_better=True, scaling="weak",
+            steps=r["steps"], warmup=r["warmup"], ms_per_step=r["ms_per_step"], higher_is_better=True, scaling=args.scaling,
             vs_baseline=None, dtype="f32", data="synthetic", config=config,
-            cpu_baseline=dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port",
-                              sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py on CPU" % (r["steps"], T, B),
-                              **host_cpu_info()),
+            cpu_baseline=dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"],
+                              note="port of the reference's learn step, pinned to reference-generated fixtures "
+                                   "(tests/test_oracle_golden.py); functional torch ops at the best of several thread counts - a "
+                                   "generous baseline", **host_cpu_info()),
             e2e=dict(value=r["value"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
@@ -365,7 +449,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from torchbeast_b200 import _lib, learner, monobeast, optim
+    from torchbeast_b200 import _lib, learner, monobeast, optim, staging
 
     dev = torch.device("cuda", local_rank)
     if args.net == "resnet":
@@ -375,19 +459,32 @@ def main():
     else:
         model = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm), precision=args.precision)
         actor = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm), precision=args.precision)
+    lib = _lib.lib()
+    dp = None
+    if world > 1 and args.net == "atari" and not args.no_dp_check:
+        dp = dp_check(args, world, rank, dev, A)
     model.reset_parameters_like_torch(seed=0)  # identical replicas on every rank
     actor.copy_params_from(model)
     opt = optim.RMSprop(model, lr=0.00048, momentum=0, eps=0.01, alpha=0.99)
     total_steps = 30_000_000
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 1 - min(e * T * B * world, total_steps) / total_steps)
     flags = flags_ns(T, B)
+    flags.cuda_graph = bool(args.graph)
     state = model.initial_state(B)
     NROT = 4  # distinct input batches: 4 x 73 MB > 126 MB L2
-    host = [synthetic_host_batch(T, B, A, seed=1000 * rank + i, pin=True) for i in range(NROT)]
+    # N1: the rollouts live in the pinned slots of the package's RolloutStager (what the actors would write in place)
+    example = synthetic_host_batch(T, B, A, seed=1000 * rank, pin=False)
+    stager = staging.RolloutStager(staging.spec_like(example), dev, depth=NROT)
+    stager._key = tuple((k, tuple(v.shape), v.dtype) for k, v in example.items())
+    model._tb_stager = stager
+    for i in range(NROT):
+        hb = example if i == 0 else synthetic_host_batch(T, B, A, seed=1000 * rank + i, pin=False)
+        for k, v in hb.items():
+            stager.host[i][k].copy_(v)
+    host = stager.host
     devb = [{k: v.to(dev) for k, v in hb.items()} for hb in host]
-    h2d_bytes = sum(v.numel() * v.element_size() for v in host[0].values())
+    h2d_bytes = stager.h2d_bytes
     h2d_gbs = measure_h2d_gbs(dev)
-    lib = _lib.lib()
 
     def barrier():
         if world > 1:
@@ -404,18 +501,35 @@ def main():
         return ms
 
     # ---- device-resident throughput ----------------------------------------------------
+    graphed = None
+    if args.graph:
+        try:
+            graphed = learner.GraphedLearner(flags, model, actor, opt, devb[0], state)
+            model.__dict__.setdefault("_tb_graphs", {})[
+                (tuple((k, tuple(v.shape)) for k, v in devb[0].items() if k in learner.GraphedLearner.KEYS), id(opt), id(actor))] = graphed
+        except Exception as exc:  # capture not possible on this setup: report and run eagerly
+            sys.stderr.write("CUDA graph capture failed (%s); running eagerly\n" % (exc,))
+            graphed = None
+            opt.lr_from_device = False
+            flags.cuda_graph = False
+
+    def device_step(i):
+        if graphed is not None:
+            return graphed.step(devb[i % NROT], state, sched)
+        return learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     for i in range(args.warmup):
-        learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
+        device_step(i)
     barrier()
     t_region0 = time.time()
     launches0 = lib.tb_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        out = learner.learn_step(flags, model, actor, devb[i % NROT], state, opt, sched, stats_sync=False)
+        out = device_step(i)
     e1.record()
     barrier()
     launches = lib.tb_launch_count() - launches0
@@ -423,54 +537,45 @@ def main():
     clocks = sampler.stop(t_region0, time.time()) if sampler else None
     final_loss = float(out["losses"][3])
     assert np.isfinite(final_loss), "non-finite loss"
+    if graphed is not None:  # launches per step: count one eager step (a graph replay launches the same kernels)
+        l0 = lib.tb_launch_count()
+        learner.learn_step(flags, model, actor, devb[0], state, opt, None, stats_sync=False)
+        torch.cuda.synchronize()
+        launches = (lib.tb_launch_count() - l0) * args.steps
 
-    # ---- end to end: pinned host buffers -> H2D -> learn() -> stats D2H, every step ------
-    copy_stream = torch.cuda.Stream()
-    slots = [{k: torch.empty_like(v, device=dev) for k, v in host[0].items()} for _ in range(2)]
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    freed = [torch.cuda.Event(), torch.cuda.Event()]
+    # ---- end to end THROUGH THE PLUGIN CALL: monobeast.learn(host rollout) from two learner threads ----------
+    # (the reference's own thread structure, polybeast_learner.py:62,505-521: the host->device copy of one thread overlaps
+    #  the other thread's step; monobeast.learn stages the pinned rollout through the RolloutStager, takes the lock,
+    #  replays the graphed step and reads the stats back - every step, inside the timed region)
+    lock = threading.Lock()
+    last_stats = [None]
 
-    def stage(i):
-        s = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[s])
-            for k, v in host[i % NROT].items():
-                slots[s][k].copy_(v, non_blocking=True)
-            ready[s].record(copy_stream)
-
-    graphed = None
-    if args.graph:
-        try:
-            graphed = learner.GraphedLearner(flags, model, actor, opt, slots[0], state)
-        except Exception as exc:  # capture not possible on this setup: report and run eagerly
-            sys.stderr.write("CUDA graph capture failed (%s); e2e runs eagerly\n" % (exc,))
-            graphed = None
-            opt.lr_from_device = False
     def e2e_loop(nsteps):
-        """nsteps learner steps, each with its own H2D copy (prefetched one step ahead on the copy
-        stream) and its own blocking stats read-back."""
-        for s in range(2):
-            freed[s].record()
-        stage(0)
-        out_stats = None
-        for i in range(nsteps):
-            t0 = time.perf_counter()
-            if i + 1 < nsteps:
-                stage(i + 1)  # prefetch the next rollout while this one trains
-            s = i % 2
-            torch.cuda.current_stream().wait_event(ready[s])
-            if graphed is not None:
-                graphed.step(slots[s], state, sched)
-                freed[s].record()  # inputs were copied into the graph's static buffers
-                out_stats = graphed.stats()  # the step's blocking stats read-back
-            else:
-                out_stats = monobeast.learn(flags, actor, model, slots[s], state, opt, sched)  # incl. stats read-back
-                freed[s].record()
-            if os.environ.get("TB_BENCH_DEBUG"):
-                sys.stderr.write("e2e step %d: %.2f ms\n" % (i, (time.perf_counter() - t0) * 1e3))
-        return out_stats
+        nthreads = 2
+        errs = []
 
-    e2e_loop(max(args.warmup, 1))  # untimed warm-up: first-use kernel loads, graph upload, pinned-page first touch
+        def body(k):
+            try:
+                torch.cuda.set_device(local_rank)
+                for i in range(k, nsteps, nthreads):
+                    last_stats[0] = monobeast.learn(flags, actor, model, host[i % NROT], state, opt, sched, lock) \
+                        if args.net == "atari" else learner.learn(flags, model, actor, host[i % NROT], state, opt, sched, lock)
+            except Exception as exc:  # surfaced below
+                errs.append(exc)
+
+        if world > 1:  # collectives inside the step must be issued in the same order on every rank: one learner thread
+            body_threads = [threading.Thread(target=lambda: [body(0), body(1)])]
+        else:
+            body_threads = [threading.Thread(target=body, args=(k,)) for k in range(nthreads)]
+        for t in body_threads:
+            t.start()
+        for t in body_threads:
+            t.join()
+        if errs:
+            raise errs[0]
+        return last_stats[0]
+
+    e2e_loop(max(args.warmup, 2))  # untimed warm-up: first-use kernel loads, graph upload, pinned-page first touch
     barrier()
     e2e_steps = args.steps
     t_e0, t_e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -504,15 +609,24 @@ def main():
     frames = T * B * world
     line = dict(
         metric="learner_frames_per_sec", value=frames / (ms * 1e-3), unit="frames/s", n_gpus=world, steps=args.steps,
-        warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None,
+        warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling=args.scaling, vs_baseline=None,
         dtype=DTYPE_NAMES.get(model.precision, model.precision),
-        data="synthetic", config=dict(config, l2="4 rotating input batches per rank (%.0f MB) > 126 MB L2; ~2.3 GB of "
-                                      "activations written per step" % (NROT * h2d_bytes / 1e6)),
+        data="synthetic", config=config,
+        l2_policy="4 rotating input batches per rank (%.0f MB) > 126 MB L2; ~2.3 GB of activations written per step" % (
+            NROT * h2d_bytes / 1e6),
         e2e=dict(value=frames / (e2e_ms * 1e-3), unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes,
-                 d2h_bytes_per_step=d2h_bytes, h2d_gbs_measured=h2d_gbs, numa_node=numa, cuda_graph=graphed is not None, note="pinned host rollout -> async H2D (double-buffered, overlapped with "
-                 "the previous step) -> monobeast.learn -> stats read-back, all inside the timed region"),
+                 d2h_bytes_per_step=d2h_bytes, h2d_gbs_measured=h2d_gbs, numa_node=numa, cuda_graph=graphed is not None,
+                 learner_threads=1 if world > 1 else 2,
+                 note="every step: monobeast.learn(flags, actor, model, PINNED HOST rollout, ...) -> RolloutStager (one async "
+                      "H2D copy of the slot on the copy stream, issued outside the lock so it overlaps the other learner "
+                      "thread's step) -> lock -> %s -> stats read-back; all inside the timed region" % (
+                          "one CUDA-graph replay of the step" if graphed is not None else "eager step")),
         gpu_launches=int(launches), clocks=clocks, final_total_loss=final_loss,
+        parity="default backend %s: tests/test_learner_baseline_gpu.py holds it to reference-generated T=80,B=32 fixtures "
+               "(outputs, vs, pg_advantages, losses <= 1e-5)" % model.precision if args.net == "atari" else None,
     )
+    if dp is not None:
+        line["dp_check"] = dp
 
     # ---- per-op device timing (separate steps; CUDA events around every op on its stream) ---
     if not args.no_profile:
@@ -559,19 +673,19 @@ def main():
                                     unit=dom["unit"], frac=dom["frac"],
                                     traffic=(traffic_tab.get(dom["op"], {}).get("dram_bytes_per_launch")),
                                     launches_per_step=dom["launches_per_step"], peak_source=pk["source"],
-                                    note=("latency-bound recurrence: T+1 dependent time steps, each a grid barrier + L2 tile fetch + bf16 "
-                                          "mma.sync product (~5 us per step); neither roofline is approached - the recurrent-product "
-                                          "flops are reported against the sustained bf16 tensor peak" if dom["op"].startswith("lstm_recurrence")
-                                          else ("bf16 tcgen05 GEMM" if model.precision == "bf16" else "fp32 SIMT GEMM backend") +
-                                          " against the sustained bf16 tensor-core peak"))
+                                    note=("latency-bound recurrence: T+1 dependent time steps, each a hand-off through L2 + tile "
+                                          "all-gather + mma.sync products; neither roofline is approached - the algorithmic "
+                                          "recurrent-product flops (2*M*N*K, not x3 for the split planes) are reported against the "
+                                          "sustained bf16 tensor peak" if dom["op"].startswith("lstm_recurrence")
+                                          else "%s backend against the sustained bf16 tensor-core peak (algorithmic flops: the 3 MMAs of "
+                                               "a split product count once)" % model.precision))
         # the V-trace kernels on their own (BASELINE.json metric: V-trace GB/s vs HBM peak)
         line["vtrace"] = vtrace_numbers(pk, T, B, A)
 
     if not args.no_cpu_baseline and world == 1:
         os.environ.setdefault("TB_CPU_BASELINE_BUDGET_S", "20")
-        r = run_reference(types.SimpleNamespace(**dict(vars(args), steps=3, warmup=1)))
-        line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port",
-                                    sample="%d full learn steps (T=%d,B=%d) of oracle/learner_torch.py" % (r["steps"], T, B),
+        r = run_reference(types.SimpleNamespace(**dict(vars(args), steps=3, warmup=1)), 1)
+        line["cpu_baseline"] = dict(value=r["value"], unit="frames/s", cores=r["cores"], kind="port", sample=r["sample"],
                                     **host_cpu_info())
     print(json.dumps(line))
     finish()

@@ -145,6 +145,16 @@ int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, c
                          const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
                          int precision, void* workspace, float* grads, void* stream);
 
+/* The same backward in two calls, for data-parallel learners (the reference has a single learner device,
+ * polybeast_learner.py:402-405; SURVEY 8(e) G1 "bucket order = reverse of forward"): phase 1 = policy/baseline heads +
+ * LSTM, phase 2 = conv/fc trunk.  After phase 2 everything is final; after phase 1 the slice
+ * [tb_atarinet_grad_split(), param_count) of `grads` (LSTM + heads: 17 of 24 MB) is final when the LSTM weight-gradient
+ * GEMMs ran on the caller's stream (precision 0 and 2), so its all-reduce can overlap phase 2.                      */
+int64_t tb_atarinet_grad_split(int num_actions, int use_lstm);
+int tb_atarinet_backward_phase(const float* grad_logits, const float* grad_baseline, const float* notdone,
+                               const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
+                               int precision, void* workspace, float* grads, int phase, void* stream);
+
 /* ---- IMPALA ResNet (polybeast_learner.py:134-266 `Net`) forward / backward ------------------------- */
 
 /* Flat parameter layout = the reference's state_dict order: feat_convs.{0,1,2}.0.{weight,bias}

@@ -46,6 +46,23 @@ def _worker(rank, world, port, use_lstm, ret):
         losses = torch.stack([o["pg_loss"], o["baseline_loss"], o["entropy_loss"]])
         assert learner._all_reduce_grads(flat) is True
         learner._all_reduce_grads(losses)
+        # the two-bucket overlapped path (LSTM + heads slice reduced between the backward phases, trunk slice after):
+        # same result as the single all-reduce, every element reduced exactly once
+        local = _flat_grads(o, names)
+        split = local.numel() // 3
+
+        class TwoPhase:
+            flat_params = local
+            def grad_split(self):
+                return split
+            def learner_backward(self, gl, gv, between=None):
+                fg = torch.zeros_like(local)
+                fg[split:] = local[split:]          # phase 1: heads + LSTM slice final
+                between(fg, split)
+                fg[:split] = local[:split]          # phase 2: trunk slice
+                return fg
+        two = learner._backward_with_overlapped_all_reduce(TwoPhase(), None, None)
+        assert torch.equal(two, flat), float((two - flat).abs().max())
         if rank == 0:
             full = LT.learner_step(p, batch, state, net="atari", update=False)
             ref = _flat_grads(full, names)

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "tb_grad_sumsq_f32": ([_vp, _i64, _vp, _vp, _vp], _int),
     "tb_clip_rmsprop_step_f32": ([_vp] * 4 + [_i64, _vp, _f32, _vp, _f32, _f32, _f32, _f32, _vp, _vp], _int),
     "tb_atarinet_backward": ([_vp] * 4 + [_i64, _i64, _int, _int, _int, _vp, _vp, _vp], _int),
+    "tb_atarinet_grad_split": ([_int, _int], _i64),
+    "tb_atarinet_backward_phase": ([_vp] * 4 + [_i64, _i64, _int, _int, _int, _vp, _vp, _int, _vp], _int),
 }
 
 _lib = None

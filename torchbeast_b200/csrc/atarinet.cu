@@ -392,21 +392,27 @@ static int atarinet_backward_trunk_bf16(const float* P, float* G_, const AtariPa
   return 0;
 }
 
+// phases: bit 0 = heads + LSTM (after it the gradient slice [tb_atarinet_grad_split, total) is final unless the LSTM
+// weight-gradient GEMMs were forked onto the side stream - then it is final after phase 2's join), bit 1 = conv/fc trunk
+// (slice [0, split)).  3 = the whole backward.  The split lets a data-parallel learner start the all-reduce of the
+// LSTM + heads slice (17 of 24 MB) while the trunk backward is still running (bucket order = reverse of forward).
 static int atarinet_backward(const float* grad_logits, const float* grad_baseline, const float* notdone,
                              const float* P, int64_t T1, int64_t B, int A, int use_lstm, int precision,
-                             void* workspace, float* G_, cudaStream_t st) {
+                             void* workspace, float* G_, cudaStream_t st, int phases = 3) {
   using G = AtariGeom;
   const int64_t N = T1 * B;
   const AtariParams pp = atari_params(A, use_lstm);
   AtariWs w = atari_ws(workspace, N, T1, B, A, use_lstm, precision);
   const int64_t M1 = N * G::H1 * G::W1, M2 = N * G::H2 * G::W2, M3 = N * G::H3 * G::W3;
   GemmEpilogue ep;
+  if (phases & 1) {
   // heads: dcore_out = dlogits . Wp + dbaseline . Wb ; dWp, dbp, dWb, dbb
   TB_REQUIRE(heads_scratch_floats(N, pp.core, A) <= kSplitKScratchFloats, "atarinet_backward: heads scratch too small");
   TB_TRY(heads_backward(w.core_out, pp.core, P + pp.policy_w, P + pp.baseline_w, grad_logits, grad_baseline, N, pp.core, A,
                         w.dcore_out, pp.core, G_ + pp.policy_w, G_ + pp.policy_b, G_ + pp.baseline_w, G_ + pp.baseline_b, w.splitk,
                         st));
-  if (use_lstm) {
+  }
+  if (use_lstm && (phases & 1)) {
     LstmParams lp; LstmGrads lg;
     for (int l = 0; l < 2; ++l) {
       lp.w_ih[l] = P + pp.lstm[l][0]; lp.w_hh[l] = P + pp.lstm[l][1];
@@ -417,6 +423,7 @@ static int atarinet_backward(const float* grad_logits, const float* grad_baselin
     TB_TRY(lstm_backward(w.dcore_out, w.core_in, notdone, lp, lg, T1, B, pp.core, pp.core, 2, w.lstm, w.dcore_in,
                          w.splitk, w.colsum_scratch, precision, st));
   }
+  if (!(phases & 2)) return 0;
   if (precision) {
     TB_TRY(atarinet_backward_trunk_bf16(P, G_, pp, w, N, st));
     return lstm_backward_join(st);  // the LSTM weight-gradient GEMMs ran beside the trunk backward
@@ -460,6 +467,23 @@ extern "C" {
 
 int64_t tb_atarinet_param_count(int num_actions, int use_lstm) {
   return atari_params(num_actions, use_lstm).total;
+}
+
+int64_t tb_atarinet_grad_split(int num_actions, int use_lstm) {
+  const AtariParams pp = atari_params(num_actions, use_lstm);
+  return use_lstm ? pp.lstm[0][0] : pp.policy_w;  // first parameter after fc.bias
+}
+
+int tb_atarinet_backward_phase(const float* grad_logits, const float* grad_baseline, const float* notdone,
+                               const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm, int precision,
+                               void* workspace, float* grads, int phase, void* stream) {
+  TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "atarinet_backward_phase: bad sizes");
+  TB_REQUIRE(grad_logits && grad_baseline && params && workspace && grads, "atarinet_backward_phase: null pointer");
+  TB_REQUIRE(!use_lstm || notdone, "atarinet_backward_phase: LSTM needs notdone");
+  TB_REQUIRE(precision >= 0 && precision <= 2, "atarinet_backward_phase: precision must be 0, 1 or 2");
+  TB_REQUIRE(phase == 1 || phase == 2, "atarinet_backward_phase: phase must be 1 (heads + LSTM) or 2 (conv/fc trunk)");
+  return atarinet_backward(grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm, precision, workspace,
+                           grads, (cudaStream_t)stream, phase);
 }
 
 size_t tb_atarinet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm, int precision) {

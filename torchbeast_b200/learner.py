@@ -1,5 +1,6 @@
 """Fused pieces of the learner step shared by monobeast.learn and polybeast_learner.learn."""
 import collections
+import os
 
 import torch
 
@@ -73,16 +74,70 @@ def impala_loss_fwd_bwd(
     return ImpalaLoss(vs, pg, lr, blp, tlp, losses, gl, gv)
 
 
+def _dp_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size()
+    return 1
+
+
 def _all_reduce_grads(flat_grad):
     """Batch-column data parallelism: losses are sums over (t, b), so one
     SUM all-reduce of the flat gradient over NCCL/NVLink reproduces the single-GPU gradient;
     every rank then clips and steps on the reduced gradient and replicas stay identical."""
     import torch.distributed as dist
 
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if _dp_world() > 1:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM)
         return True
     return False
+
+
+_ar_streams = {}
+
+
+def _backward_with_overlapped_all_reduce(model, grad_logits, grad_values):
+    """Network backward + the gradient SUM all-reduce, still one logical SUM per parameter, in two buckets in reverse
+    forward order: the LSTM + heads slice (17 of 24 MB; final after backward phase 1) is reduced on a
+    side stream WHILE the conv/fc trunk backward runs, the trunk slice right after it.  Fork / join are events, so the
+    whole thing is captured into the learner's CUDA graph.  Falls back to one all-reduce after the backward when the
+    model has no two-phase backward."""
+    import torch.distributed as dist
+    if _dp_world() <= 1:
+        return model.learner_backward(grad_logits, grad_values)
+    if not hasattr(model, "grad_split") or os.environ.get("TB_AR_OVERLAP", "1") == "0":
+        fg = model.learner_backward(grad_logits, grad_values)
+        dist.all_reduce(fg, op=dist.ReduceOp.SUM)
+        return fg
+    dev = model.flat_params.device
+    on_gpu = dev.type == "cuda"   # (the gloo / CPU path of tests/test_dist_cpu.py runs the same bucket logic without streams)
+    side = main = None
+    if on_gpu:
+        side = _ar_streams.get(dev)
+        if side is None:
+            side = _ar_streams[dev] = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+    state = {"split": 0}
+
+    def between(fg, split):
+        state["split"] = split
+        if split > 0:
+            if on_gpu:
+                side.wait_stream(main)        # phase 1 (heads + LSTM gradients) is enqueued on main
+                with torch.cuda.stream(side):
+                    dist.all_reduce(fg[split:], op=dist.ReduceOp.SUM)
+            else:
+                dist.all_reduce(fg[split:], op=dist.ReduceOp.SUM)
+
+    fg = model.learner_backward(grad_logits, grad_values, between=between)
+    split = state["split"]
+    if split > 0:
+        dist.all_reduce(fg[:split], op=dist.ReduceOp.SUM)
+        if on_gpu:
+            main.wait_stream(side)
+    else:
+        dist.all_reduce(fg, op=dist.ReduceOp.SUM)
+    return fg
 
 
 def optimizer_step(model, optimizer, max_grad_norm):
@@ -112,8 +167,7 @@ def learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer,
         out.baseline[:-1], out.baseline[-1],
         discounting=flags.discounting, baseline_cost=flags.baseline_cost, entropy_cost=flags.entropy_cost,
         reward_clipping=flags.reward_clipping)
-    flat_grad = model.learner_backward(loss.grad_logits, loss.grad_values)
-    _all_reduce_grads(flat_grad)
+    _backward_with_overlapped_all_reduce(model, loss.grad_logits, loss.grad_values)
     optimizer_step(model, optimizer, flags.grad_norm_clipping)
     if scheduler is not None:
         scheduler.step()
@@ -136,6 +190,71 @@ def learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer,
         "baseline_loss": host[1].item(),
         "entropy_loss": host[2].item(),
     }
+
+
+def _graph_enabled(flags):
+    """The graphed step is opt-in: flags.cuda_graph (or TB_CUDA_GRAPH=1).  Capture costs four throw-away steps and pins the
+    batch shape; a training loop that calls learn() thousands of times with one shape wants it, a unit test does not."""
+    import os
+    v = getattr(flags, "cuda_graph", None)
+    if v is None:
+        v = os.environ.get("TB_CUDA_GRAPH", "0") not in ("0", "", "false")
+    return bool(v)
+
+
+def _is_host(batch):
+    t = batch["frame"] if isinstance(batch, dict) else batch[0]
+    return not t.is_cuda
+
+
+def learn(flags, model, actor_model, batch, initial_agent_state, optimizer, scheduler, lock=None):
+    """What monobeast.learn / polybeast_learner.learn run per rollout batch.
+
+    * `batch` may live on the HOST (the reference's learner-queue nest / monobeast buffers): it is staged through the
+      model's RolloutStager (pinned slot -> one async H2D copy on the copy stream) OUTSIDE `lock`, exactly where the
+      reference does its `.to(device)` (polybeast_learner.py:307 - so with two learner threads the copy of one thread
+      overlaps the other thread's step), then consumed under the lock.
+    * with flags.cuda_graph (or TB_CUDA_GRAPH=1) the device side is ONE CUDA-graph replay (GraphedLearner, created on first
+      use per batch shape); otherwise the eager launch sequence of learn_step.
+    Returns the reference's stats dict."""
+    import contextlib
+    from torchbeast_b200 import staging
+    slot = None
+    stager = None
+    if _is_host(batch):
+        stager = getattr(model, "_tb_stager", None)
+        key = tuple((k, tuple(v.shape), v.dtype) for k, v in batch.items())
+        if stager is None or getattr(stager, "_key", None) != key:
+            stager = staging.RolloutStager(staging.spec_like(batch), model.flat_params.device, depth=3)
+            stager._key = key
+            model._tb_stager = stager
+        slot = stager.put(batch)
+        initial_agent_state = tuple(t.to(model.flat_params.device, non_blocking=True) for t in initial_agent_state)
+    with (lock if lock is not None else contextlib.nullcontext()):
+        if stager is not None:
+            # this thread's own slot: wait for ITS copy (slots complete in submission order per thread)
+            torch.cuda.current_stream().wait_event(stager._ready[slot])
+            with stager._lock:
+                if slot in stager._submitted:
+                    stager._submitted.remove(slot)
+            batch = stager.dev[slot]
+        try:
+            if _graph_enabled(flags):
+                graphs = model.__dict__.setdefault("_tb_graphs", {})
+                gkey = (tuple((k, tuple(v.shape)) for k, v in batch.items() if k in GraphedLearner.KEYS), id(optimizer),
+                        id(actor_model))
+                gl = graphs.get(gkey)
+                if gl is None:
+                    gl = graphs[gkey] = GraphedLearner(flags, model, actor_model, optimizer, batch, initial_agent_state)
+                gl.step(batch, initial_agent_state, scheduler)
+                if stager is not None:
+                    stager.release(slot)  # the inputs now live in the graph's static buffers
+                    slot = None
+                return gl.stats()
+            return learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer, scheduler)
+        finally:
+            if stager is not None and slot is not None:
+                stager.release(slot)
 
 
 def shard_rollout(batch, initial_agent_state, rank, world_size):

@@ -34,7 +34,8 @@ def learn(
 ):
     """Performs a learning (optimization) step - reference monobeast.py:226-296.
 
-    Same arguments and returned stats dict.  `model` is a torchbeast_b200 network, `batch`
-    the dict of [T+1, B, ...] CUDA tensors get_batch() produces (monobeast.py:194-223)."""
-    with lock:
-        return _learner.learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer, scheduler)
+    Same arguments and returned stats dict.  `model` is a torchbeast_b200 network, `batch` the dict of
+    [T+1, B, ...] tensors get_batch() produces (monobeast.py:194-223): CUDA tensors as in the reference, or HOST
+    tensors (the buffers themselves) - those are staged through the pinned RolloutStager outside the lock.
+    flags.cuda_graph / TB_CUDA_GRAPH=1 replays the whole device side as one CUDA graph (learner.learn)."""
+    return _learner.learn(flags, model, actor_model, batch, initial_agent_state, optimizer, scheduler, lock)

@@ -283,16 +283,29 @@ class AtariNet(FlatParamModule):
             "tb_atarinet_forward")
         return logits, baseline, hN, cN
 
-    def _launch_backward(self, g_logits, g_baseline, notdone, grads_out):
+    def _launch_backward(self, g_logits, g_baseline, notdone, grads_out, phase=None):
         T1, B = g_baseline.shape
         ws = self._workspace(T1, B)
         p = _lib.ptr
-        _lib.check(
-            _lib.lib().tb_atarinet_backward(
-                p(g_logits), p(g_baseline), p(notdone) if self.use_lstm else None, p(self._flat), T1, B,
-                self.num_actions, int(self.use_lstm), self.PRECISIONS[self.precision], p(ws), p(grads_out),
-                _lib.stream_ptr()),
-            "tb_atarinet_backward")
+        if phase is None:
+            _lib.check(
+                _lib.lib().tb_atarinet_backward(
+                    p(g_logits), p(g_baseline), p(notdone) if self.use_lstm else None, p(self._flat), T1, B,
+                    self.num_actions, int(self.use_lstm), self.PRECISIONS[self.precision], p(ws), p(grads_out),
+                    _lib.stream_ptr()),
+                "tb_atarinet_backward")
+        else:
+            _lib.check(
+                _lib.lib().tb_atarinet_backward_phase(
+                    p(g_logits), p(g_baseline), p(notdone) if self.use_lstm else None, p(self._flat), T1, B,
+                    self.num_actions, int(self.use_lstm), self.PRECISIONS[self.precision], p(ws), p(grads_out), int(phase),
+                    _lib.stream_ptr()),
+                "tb_atarinet_backward_phase")
+
+    def grad_split(self):
+        """Flat-gradient offset where the LSTM + heads slice starts (final after backward phase 1 for precision
+        fp32 / bf16x3): what a data-parallel learner all-reduces first, overlapped with the trunk backward."""
+        return int(_lib.lib().tb_atarinet_grad_split(self.num_actions, int(self.use_lstm)))
 
     @staticmethod
     def _notdone(done):
@@ -310,10 +323,19 @@ class AtariNet(FlatParamModule):
         return LearnerOutputs(logits, baseline, (hN, cN) if self.use_lstm else tuple())
 
     @torch.no_grad()
-    def learner_backward(self, grad_logits, grad_baseline):
-        """Writes d loss / d params into flat_grad (and points every .grad at its slice)."""
+    def learner_backward(self, grad_logits, grad_baseline, between=None):
+        """Writes d loss / d params into flat_grad (and points every .grad at its slice).  `between(flat_grad, split)`:
+        called after the heads + LSTM phase, when flat_grad[split:] is final, before the conv/fc trunk phase is launched
+        (data-parallel learners start that slice's all-reduce there)."""
         fg = self.attach_grads()
-        self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg)
+        if between is None or self.precision == "bf16":  # bf16: the LSTM weight-gradient GEMMs run beside the trunk backward
+            self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg)
+            if between is not None:
+                between(fg, 0)
+            return fg
+        self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg, phase=1)
+        between(fg, self.grad_split())
+        self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg, phase=2)
         return fg
 
     # ---- reference-compatible forward ---------------------------------------------------------

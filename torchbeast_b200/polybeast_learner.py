@@ -47,27 +47,28 @@ def learn(
     ((env_outputs, actor_outputs), initial_agent_state) with [T+1, B, ...] CPU (or CUDA) leaves,
     env_outputs = (frame u8, reward, done, episode_step, episode_return), actor_outputs =
     (action, policy_logits, baseline); fills `stats` with the reference's keys and calls plogger.log."""
-    device = getattr(flags, "learner_device", None) or model.flat_params.device
     for tensors in learner_queue:
         batch, initial_agent_state = tensors
         env_outputs, actor_outputs = batch
-        env = EnvOutput._make(_to_device(t, device) for t in list(env_outputs)[:5])
-        agent = AgentOutput._make(_to_device(t, device) for t in list(actor_outputs)[:3])
-        state = tuple(_to_device(t, device) for t in initial_agent_state)
+        env = EnvOutput._make(list(env_outputs)[:5])
+        agent = AgentOutput._make(list(actor_outputs)[:3])
         rollout = dict(frame=env.frame, reward=env.rewards, done=env.done, episode_return=env.episode_return,
-                       policy_logits=agent.policy_logits, action=agent.action)
-        lock.acquire()  # only one thread learning at a time (the H2D copies above overlap the previous step)
-        try:
-            out = _learner.learn_step(flags, model, actor_model, rollout, state, optimizer, scheduler)
+                       episode_step=env.episode_step, policy_logits=agent.policy_logits, action=agent.action)
+        if hasattr(model, "num_actions") and "last_action" not in rollout and type(model).__name__ == "AtariNet":
+            rollout["last_action"] = agent.action  # AtariNet consumes the previous action; the nest's action row 0 is it
+        # host nest (what the reference's BatchingQueue yields) -> pinned slot -> async H2D, OUTSIDE the lock: with
+        # num_learner_threads = 2 (polybeast_learner.py:62,505-521) this thread's copy overlaps the other thread's step.
+        # _learner.learn takes the lock for the step itself (only one thread learning at a time, pl:313).
+        mean_step = torch.mean(env.episode_step[1:].float()).item()
+        out = _learner.learn(flags, model, actor_model, rollout, tuple(initial_agent_state), optimizer, scheduler, lock)
+        with lock:
             stats["step"] = stats.get("step", 0) + flags.unroll_length * flags.batch_size
             stats["episode_returns"] = out["episode_returns"]
             stats["mean_episode_return"] = out["mean_episode_return"]
-            stats["mean_episode_step"] = torch.mean(env.episode_step[1:].float()).item()
+            stats["mean_episode_step"] = mean_step
             for k in ("total_loss", "pg_loss", "baseline_loss", "entropy_loss"):
                 stats[k] = out[k]
             stats["learner_queue_size"] = learner_queue.size()
             plogger.log(stats)
             if not len(out["episode_returns"]):
                 stats["mean_episode_return"] = None  # hide the mean-of-empty NaN, like the reference
-        finally:
-            lock.release()
