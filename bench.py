@@ -54,6 +54,10 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --B columns per GPU (default, the driver's scaling run); strong: --B columns in total, B/N per GPU")
     ap.add_argument("--no_dp_check", action="store_true", help="skip the multi-GPU gradient / replica check before the timed runs")
+    ap.add_argument("--actors", type=int, default=0,
+                    help="BASELINE configs[2]: N synthetic host actor threads -> pinned slots -> learner queue -> "
+                         "polybeast_learner.learn on --learner_threads threads; prints the end-to-end SPS line")
+    ap.add_argument("--learner_threads", type=int, default=2)
     return ap.parse_args()
 
 
@@ -416,8 +420,70 @@ def dp_check(args, world, rank, dev, A):
     return res
 
 
+def run_actor_pipeline(args):
+    """BASELINE.json configs[2]: `--actors 48` synthetic actor threads feed pinned [T+1, B, ...] slots; full slots travel the
+    learner queue as the reference's nest into polybeast_learner.learn() on `--learner_threads` threads (2 = the reference
+    default, polybeast_learner.py:62) sharing one model, optimizer and lock.  Value = frames consumed per second end to end
+    (T*B per learn step / wall time, stats["step"] as the reference counts it, pl:372), steady state after a warm-up."""
+    from torchbeast_b200 import actors, monobeast, optim, polybeast_learner, staging
+    T, B, A = args.T, args.B, args.num_actions
+    torch.cuda.set_device(0)
+    numa = bind_to_gpu_numa_node(0)
+    dev = torch.device("cuda", 0)
+    model = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm), precision=args.precision)
+    actor_model = monobeast.AtariNet((4, 84, 84), A, bool(args.use_lstm), precision=args.precision)
+    actor_model.copy_params_from(model)
+    opt = optim.RMSprop(model, lr=0.00048, momentum=0, eps=0.01, alpha=0.99)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 1.0)
+    flags = flags_ns(T, B)
+    flags.cuda_graph = bool(args.graph)
+    stager = staging.RolloutStager(staging.spec_for(T, B, A, use_last_action=False), dev, depth=4)
+    model._tb_stager = stager
+    q = actors.LearnerQueue()
+    pool = actors.SyntheticActors(stager, args.actors, T, B, A, q, state_shape=(2, 512 + A + 1) if args.use_lstm else None)
+    stats, lock = {}, threading.Lock()
+    steps_done = [0]
+    t_mark = {}
+    total = args.warmup + args.steps
+
+    class Log:
+        def log(self, st):
+            steps_done[0] += 1
+            if steps_done[0] == args.warmup:
+                torch.cuda.synchronize(); t_mark["t0"] = time.perf_counter()
+            if steps_done[0] == total:
+                torch.cuda.synchronize(); t_mark["t1"] = time.perf_counter()
+                pool.stop()
+
+    pool.start()
+    threads = [threading.Thread(target=polybeast_learner.learn, args=(flags, q, model, actor_model, opt, sched, stats, Log(), lock))
+               for _ in range(args.learner_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+    dt = t_mark["t1"] - t_mark["t0"]
+    sps = args.steps * T * B / dt
+    line = dict(metric="end_to_end_sps", value=sps, unit="frames/s", n_gpus=1, steps=args.steps, warmup=args.warmup,
+                ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=DTYPE_NAMES.get(model.precision, model.precision), data="synthetic",
+                config=dict(workload="polybeast_learner, %d synthetic host actor threads -> pinned slots -> learner queue -> "
+                                     "%d learner threads, AtariNet%s, T=%d B=%d, 1 GPU" % (
+                                         args.actors, args.learner_threads, "+LSTM" if args.use_lstm else "", T, B),
+                            T=T, B_per_gpu=B, num_actions=A, use_lstm=bool(args.use_lstm), actors=args.actors,
+                            learner_threads=args.learner_threads),
+                e2e=dict(value=sps, unit="frames/s", h2d_bytes_per_step=stager.h2d_bytes, d2h_bytes_per_step=16,
+                         numa_node=numa, rollouts_produced=pool.rollouts, **host_cpu_info()),
+                final_total_loss=stats.get("total_loss"), learner_steps=steps_done[0])
+    print(json.dumps(line))
+    sys.stdout.flush()
+    os._exit(0)
+
+
 def main():
     args = parse()
+    if args.actors > 0 and args.impl != "reference":
+        return run_actor_pipeline(args)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -475,7 +541,6 @@ def main():
     # N1: the rollouts live in the pinned slots of the package's RolloutStager (what the actors would write in place)
     example = synthetic_host_batch(T, B, A, seed=1000 * rank, pin=False)
     stager = staging.RolloutStager(staging.spec_like(example), dev, depth=NROT)
-    stager._key = tuple((k, tuple(v.shape), v.dtype) for k, v in example.items())
     model._tb_stager = stager
     for i in range(NROT):
         hb = example if i == 0 else synthetic_host_batch(T, B, A, seed=1000 * rank + i, pin=False)

@@ -423,7 +423,7 @@ static int atarinet_backward(const float* grad_logits, const float* grad_baselin
     TB_TRY(lstm_backward(w.dcore_out, w.core_in, notdone, lp, lg, T1, B, pp.core, pp.core, 2, w.lstm, w.dcore_in,
                          w.splitk, w.colsum_scratch, precision, st));
   }
-  if (!(phases & 2)) return 0;
+  if (!(phases & 2)) return lstm_backward_join(st);  // phase 1 alone: the LSTM + heads gradient slice must be final on return
   if (precision) {
     TB_TRY(atarinet_backward_trunk_bf16(P, G_, pp, w, N, st));
     return lstm_backward_join(st);  // the LSTM weight-gradient GEMMs ran beside the trunk backward

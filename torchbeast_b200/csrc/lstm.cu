@@ -1853,6 +1853,257 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
   }
 }
 
+
+// ---- split-precision backward wavefront (precision 2) ----------------------------------------------
+// lstm2_bwd_wave_mma_kernel's role split (CTAs [0, nc): upper layer recurrence + dL/dh_lower from the same tile;
+// CTAs [nc, 2nc): lower layer two wave steps behind; 8 hidden units per CTA) with hi/lo operand planes:
+//   * the four gate-gradient tiles of a step are 4 x (hi + lo) x 34 KB = 274 KB - more than shared memory - so they
+//     stream through a 2-deep ring by gate (cp.async of gate g+1 under the MMAs of gate g);
+//   * 11 MMA warps x 3 k16-steps cover one gate's K = 528 exactly; W_hh^T (and, upper role, W_ih_upper^T) as hi AND lo
+//     B fragments in registers (96 per thread);
+//   * per-CTA flags instead of the counter barrier (see lstm2_fwd_wave_split_kernel): a CTA waits for the CTAs of its
+//     own role (they produce the tile it pulls) and, lower role, for the upper CTA that owns the same 8 columns
+//     (it produces this CTA's dL/dh_lower).
+struct WaveBwdSplitArgs {
+  const float* w_hh_up; const float* w_hh_lo; const float* w_ih_up;
+  const float* dy; const float* nd;
+  const float* gates_up; const float* cs_up; const float* cm_up;
+  const float* gates_lo; const float* cs_lo; const float* cm_lo;
+  __nv_bfloat16* dgb_up; __nv_bfloat16* dgb_lo; int lg; int64_t dgb_lo_off;   // gate gradients of all steps, hi plane (+ lo offset)
+  float* db_up; float* db_lo;
+  __nv_bfloat16* dgq_up; __nv_bfloat16* dgq_lo; int64_t dgq_lo_off;          // exchange planes: [2][4, B, Hq] (+ lo offset)
+  float* dxm;
+  unsigned* flags;                  // [2 * nc]
+  int T1, B, H, Hq; unsigned nc;
+};
+
+__global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(WaveBwdSplitArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_b[];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int H = a.H, Hq = a.Hq, B = a.B;
+  const int tile = 32 * Hq;                                      // one plane of one gate
+  __nv_bfloat16* X = reinterpret_cast<__nv_bfloat16*>(smem_b);   // ring: [2 slots][hi, lo][32][Hq]
+  typedef float PartT[2][kBwdCols][33];
+  PartT* part = reinterpret_cast<PartT*>(smem_b + size_t(4) * tile * 2);  // [11 warps][product][col][row]
+  __shared__ float dh_s[kBwdCols][33];
+  __shared__ float dc_s[kBwdCols][33];
+  __shared__ __align__(16) __nv_bfloat16 stg_s[2][4][32][kBwdCols];       // [plane][gate][row][col]
+  const bool upper = blockIdx.x < a.nc;
+  const int cidx = int(upper ? blockIdx.x : blockIdx.x - a.nc);
+  const int k0 = cidx * kBwdCols;
+  const int rows = B < 32 ? B : 32;
+  const int kpg = (H + 15) / 16;           // k16 steps per gate (<= 33)
+  const int ks0 = wrp * kSplitK;           // this warp's k-steps inside every gate
+  const float* const w_hh = upper ? a.w_hh_up : a.w_hh_lo;
+  const float* const gates = upper ? a.gates_up : a.gates_lo;
+  const float* const cs = upper ? a.cs_up : a.cs_lo;
+  const float* const cm = upper ? a.cm_up : a.cm_lo;
+  __nv_bfloat16* const dgb = upper ? a.dgb_up : a.dgb_lo;
+  __nv_bfloat16* const dgq = upper ? a.dgq_up : a.dgq_lo;
+  // B fragments: B[kk][n] = W[g*H + j][k0 + n] for kk = (gate g, j)
+  uint32_t bh[4][kSplitK][2], bl[4][kSplitK][2], ih[4][kSplitK][2], il[4][kSplitK][2];
+  {
+    const int n = lane >> 2;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int sk = 0; sk < kSplitK; ++sk) {
+        const int j = (ks0 + sk) * 16 + (lane & 3) * 2;
+        float v[4] = {0.f, 0.f, 0.f, 0.f}, u[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ks0 + sk < kpg && k0 + n < H) {
+          const float* wc = w_hh + int64_t(g) * H * H + (k0 + n);
+          const float* ic = a.w_ih_up + int64_t(g) * H * H + (k0 + n);
+          if (j < H) { v[0] = wc[int64_t(j) * H]; if (upper) u[0] = ic[int64_t(j) * H]; }
+          if (j + 1 < H) { v[1] = wc[int64_t(j + 1) * H]; if (upper) u[1] = ic[int64_t(j + 1) * H]; }
+          if (j + 8 < H) { v[2] = wc[int64_t(j + 8) * H]; if (upper) u[2] = ic[int64_t(j + 8) * H]; }
+          if (j + 9 < H) { v[3] = wc[int64_t(j + 9) * H]; if (upper) u[3] = ic[int64_t(j + 9) * H]; }
+        }
+        split_pack(v[0], v[1], bh[g][sk][0], bl[g][sk][0]);
+        split_pack(v[2], v[3], bh[g][sk][1], bl[g][sk][1]);
+        split_pack(u[0], u[1], ih[g][sk][0], il[g][sk][0]);
+        split_pack(u[2], u[3], ih[g][sk][1], il[g][sk][1]);
+      }
+  }
+  if (wrp < kBwdCols) { dh_s[wrp][lane] = 0.0f; dc_s[wrp][lane] = 0.0f; }
+  __syncthreads();
+  const int64_t gs = int64_t(B) * Hq;      // one gate of one exchange buffer
+  const int chunks_per_row = (kpg * 16) / 8;
+  const int nchunk = rows * chunks_per_row;
+  const int q = wrp;  // pointwise role: thread = (batch row lane, unit k0 + wrp), warps 0..7
+  const bool actA = (wrp < kBwdCols && lane < rows && k0 + q < H);
+  auto time_of = [&](int s) { return upper ? a.T1 - 1 - s : a.T1 + 1 - s; };
+  float n_ig = 0.f, n_fg = 0.f, n_gg = 0.f, n_og = 0.f, n_dy = 0.f, n_cs = 0.f, n_cm = 0.f, n_nd = 0.f, n_ndn = 0.f;
+  auto prefetch = [&](int t) {
+    if (!actA || t < 0 || t >= a.T1) return;
+    const int64_t r0 = int64_t(t) * B;
+    const int64_t i = (r0 + lane) * H + k0 + q, g = (r0 + lane) * 4 * H + k0 + q;
+    n_ig = gates[g]; n_fg = gates[g + H]; n_gg = gates[g + 2 * H]; n_og = gates[g + 3 * H];
+    if (upper) n_dy = a.dy[i];  // the lower role's dy comes from the upper role: fetched AFTER the wait (fetch_dxm)
+    n_cs = cs[i]; n_cm = cm[i]; n_nd = a.nd[r0 + lane];
+    n_ndn = (t + 1 < a.T1) ? a.nd[r0 + B + lane] : 0.f;
+  };
+  auto fetch_dxm = [&](int t) {
+    if (upper || !actA || t < 0 || t >= a.T1) return;
+    n_dy = __ldcg(a.dxm + (int64_t(t) * B + lane) * H + k0 + q);
+  };
+  if (upper) prefetch(a.T1 - 1);
+  float bs_i = 0.f, bs_f = 0.f, bs_g = 0.f, bs_o = 0.f;
+  auto store_dg = [&](int64_t row, float p_i, float p_f, float p_g, float p_o) {
+    __nv_bfloat16* d = dgb + row * a.lg + k0 + q;
+    const float p[4] = {p_i, p_f, p_g, p_o};
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(p[g]);
+      d[g * H] = h;
+      d[a.dgb_lo_off + g * H] = __float2bfloat16_rn(p[g] - __bfloat162float(h));
+    }
+  };
+  const int last_s = a.T1 + 1;
+  unsigned* const my_flag = a.flags + blockIdx.x;
+  const unsigned* const role_flags = a.flags + (upper ? 0 : a.nc);
+  int it = 0;  // this role's active-step counter
+  for (int s = 0; s <= last_s; ++s) {
+    const int t = time_of(s);
+    const bool active = (t >= 0 && t < a.T1);
+    const int64_t row0 = int64_t(active ? t : 0) * B;
+    __nv_bfloat16* dgq_t = dgq + int64_t(it & 1) * 4 * gs;
+    float p_i = 0.f, p_f = 0.f, p_g = 0.f, p_o = 0.f;
+    if (active) {
+      if (actA) {
+        const float ig = n_ig, fg = n_fg, gg = n_gg, og = n_og;
+        float dh = n_dy;
+        float dc = 0.0f;
+        if (it > 0) {
+          dh += dh_s[q][lane] * n_ndn;
+          dc = dc_s[q][lane];
+        }
+        const float tc = tanhf(n_cs);
+        const float d_o = dh * tc;
+        dc += dh * og * (1.0f - tc * tc);
+        const float d_i = dc * gg, d_f = dc * n_cm, d_g = dc * ig;
+        p_i = d_i * ig * (1.0f - ig); p_f = d_f * fg * (1.0f - fg);
+        p_g = d_g * (1.0f - gg * gg); p_o = d_o * og * (1.0f - og);
+        dc_s[q][lane] = dc * fg * n_nd;
+        bs_i += p_i; bs_f += p_f; bs_g += p_g; bs_o += p_o;
+      }
+      // publish this CTA's 8 columns of the four gate-gradient tiles, hi and lo planes (16-byte stores staged through smem)
+      if (wrp < kBwdCols) {
+        const float p[4] = {p_i, p_f, p_g, p_o};
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const __nv_bfloat16 h = __float2bfloat16_rn(p[g]);
+          stg_s[0][g][lane][q] = h;
+          stg_s[1][g][lane][q] = __float2bfloat16_rn(p[g] - __bfloat162float(h));
+        }
+      }
+      __syncthreads();
+      if (tid < 256 && (tid & 31) < rows) {
+        const int pl = tid >> 7, g = (tid >> 5) & 3, bb = tid & 31;
+        *reinterpret_cast<uint4*>(dgq_t + (pl ? a.dgq_lo_off : 0) + int64_t(g) * gs + int64_t(bb) * Hq + k0) =
+            *reinterpret_cast<const uint4*>(&stg_s[pl][g][bb][0]);
+      }
+    }
+    if (s == last_s) {
+      if (active && actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
+      break;
+    }
+    __syncthreads();
+    if (tid == 0) {  // this CTA's tile columns of wave step s (and, upper role, its dxm of step s-1) are out
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      st_relaxed_u32(my_flag, unsigned(s + 1));
+    }
+    if (active && actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
+    prefetch(time_of(s + 1));  // forward-pass operands only: overlaps the wait
+    // wait: every CTA of this role has published wave step s; lower role: plus the upper CTA with the same columns
+    if (tid < int(a.nc)) {
+      while (ld_relaxed_u32(role_flags + tid) < unsigned(s + 1)) {}
+      (void)ld_acquire_u32(role_flags + tid);
+    } else if (!upper && tid == int(a.nc)) {
+      while (ld_relaxed_u32(a.flags + cidx) < unsigned(s + 1)) {}
+      (void)ld_acquire_u32(a.flags + cidx);
+    }
+    __syncthreads();
+    fetch_dxm(time_of(s + 1));  // written by the upper role before it published wave step s
+    const bool need_rec = active && t > 0;
+    const bool need_dx = active && upper;
+    if (need_rec || need_dx) {
+      auto issue = [&](int g) {
+        const __nv_bfloat16* src = dgq_t + int64_t(g) * gs;
+        __nv_bfloat16* dst = X + int64_t(g & 1) * 2 * tile;
+        for (int i = tid; i < nchunk; i += kSplitThreads) {
+          const int r = i / chunks_per_row, c = i - r * chunks_per_row;
+          const int off = r * Hq + c * 8;
+          cp_async16(dst + off, src + off);
+          cp_async16(dst + tile + off, src + a.dgq_lo_off + off);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      float acc0[2][4], acc1[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc0[mt][e] = 0.f; acc1[mt][e] = 0.f; }
+      issue(0);
+      issue(1);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (g < 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const __nv_bfloat16* Xg = X + int64_t(g & 1) * 2 * tile;
+#pragma unroll
+        for (int sk = 0; sk < kSplitK; ++sk) {
+          if (ks0 + sk < kpg) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              uint32_t ah[4], al[4];
+              const int off = (mt * 16 + (lane & 15)) * Hq + (ks0 + sk) * 16 + (lane >> 4) * 8;
+              ldmatrix_x4(ah, Xg + off);
+              ldmatrix_x4(al, Xg + tile + off);
+              if (need_rec) mma3(acc0[mt], ah, al, bh[g][sk][0], bh[g][sk][1], bl[g][sk][0], bl[g][sk][1]);
+              if (need_dx) mma3(acc1[mt], ah, al, ih[g][sk][0], ih[g][sk][1], il[g][sk][0], il[g][sk][1]);
+            }
+          }
+        }
+        __syncthreads();
+        if (g + 2 < 4) issue(g + 2);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
+        part[wrp][0][c][r] = acc0[mt][0]; part[wrp][0][c + 1][r] = acc0[mt][1];
+        part[wrp][0][c][r + 8] = acc0[mt][2]; part[wrp][0][c + 1][r + 8] = acc0[mt][3];
+        part[wrp][1][c][r] = acc1[mt][0]; part[wrp][1][c + 1][r] = acc1[mt][1];
+        part[wrp][1][c][r + 8] = acc1[mt][2]; part[wrp][1][c + 1][r + 8] = acc1[mt][3];
+      }
+      __syncthreads();
+      if (wrp < kBwdCols) {            // warps 0..7: recurrent carry for time t-1 (fixed summation order)
+        if (need_rec) {
+          float d = 0.f;
+#pragma unroll
+          for (int w = 0; w < kSplitWarps; ++w) d += part[w][0][wrp][lane];
+          dh_s[wrp][lane] = d;
+        }
+        if (need_dx) {                 // dL/dh_lower[t], this CTA's 8 columns
+          float d = 0.f;
+#pragma unroll
+          for (int w = 0; w < kSplitWarps; ++w) d += part[w][1][wrp][lane];
+          if (lane < rows && k0 + wrp < H) a.dxm[(row0 + lane) * H + k0 + wrp] = d;
+        }
+      }
+      __syncthreads();
+    }
+    if (active) ++it;
+  }
+  if (wrp < kBwdCols) {
+    bs_i = warp_sum(bs_i); bs_f = warp_sum(bs_f); bs_g = warp_sum(bs_g); bs_o = warp_sum(bs_o);
+    float* db = upper ? a.db_up : a.db_lo;
+    if (lane == 0 && k0 + q < H) {
+      db[k0 + q] = bs_i; db[H + k0 + q] = bs_f; db[2 * H + k0 + q] = bs_g; db[3 * H + k0 + q] = bs_o;
+    }
+  }
+}
+
 template <typename Kernel>
 static int coop_fit(Kernel kernel, dim3 grid, size_t smem, size_t* attr_smem) {
   if (*attr_smem < smem) {
@@ -2059,6 +2310,63 @@ static int lstm2_bwd_wave(LstmWs& ws, const LstmParams& p, const LstmGrads& g, c
                                   wave_bwd_smem(H), st);
   TB_REQUIRE(e == cudaSuccess, "lstm2_bwd_wave_mma_kernel: %s", cudaGetErrorString(e));
   return check_launch("lstm2_bwd_wave_mma_kernel");
+}
+
+static size_t g_bwd_split_attr = 0;
+static size_t wave_bwd_split_smem(int Hq) { return size_t(4) * 32 * Hq * 2 + sizeof(float) * kSplitWarps * 2 * kBwdCols * 33; }
+static bool wave_bwd_split_applicable(int64_t B, int In, int H) {
+  const char* e = getenv("TB_LSTM_SPLIT_BWD");
+  if (e && e[0] == '0') return false;
+  if (!wave_fwd_split_applicable(B, In, H)) return false;  // consumes the planes the split forward leaves behind
+  dim3 grid(2 * ((H + kBwdCols - 1) / kBwdCols), 1);
+  if (int(grid.x / 2) + 1 > kSplitThreads || grid.x > 512) return false;
+  const size_t smem = wave_bwd_split_smem(mma_hq(H));
+  if (g_bwd_split_attr < smem) {
+    if (cudaFuncSetAttribute(lstm2_bwd_wave_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    g_bwd_split_attr = smem;
+  }
+  int dev = 0, sms = 0, coop = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  if (!coop || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm2_bwd_wave_split_kernel, kSplitThreads, smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return int64_t(per_sm) * sms >= int64_t(grid.x);
+}
+
+static int lstm2_bwd_wave_split(LstmWs& ws, const LstmParams& p, const LstmGrads& g, const float* dy, const float* notdone,
+                                int64_t T1, int64_t B, int H, cudaStream_t st) {
+  const int Hq = mma_hq(H);
+  const unsigned nc = unsigned((H + kBwdCols - 1) / kBwdCols);
+  const LstmLayerWs& U = ws.layer[1];
+  const LstmLayerWs& L = ws.layer[0];
+  unsigned* flags = ws.flags + 512;
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(unsigned) * 512, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(U.dgq, 0, size_t(U.dgq_lo + int64_t(2) * 4 * B * Hq) * 2, st);  // zero the row padding
+  if (e == cudaSuccess) e = cudaMemsetAsync(L.dgq, 0, size_t(L.dgq_lo + int64_t(2) * 4 * B * Hq) * 2, st);
+  TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
+  TB_REQUIRE(U.dgq_lo > 0 && U.dgq_lo == L.dgq_lo && U.dgb_lo > 0 && U.dgb_lo == L.dgb_lo, "lstm: split planes missing");
+  WaveBwdSplitArgs a;
+  a.w_hh_up = p.w_hh[1]; a.w_hh_lo = p.w_hh[0]; a.w_ih_up = p.w_ih[1];
+  a.dy = dy; a.nd = notdone;
+  a.gates_up = U.gates; a.cs_up = U.cs; a.cm_up = U.cm;
+  a.gates_lo = L.gates; a.cs_lo = L.cs; a.cm_lo = L.cm;
+  a.dgb_up = static_cast<__nv_bfloat16*>(U.dgb); a.dgb_lo = static_cast<__nv_bfloat16*>(L.dgb); a.lg = int(ld16(4 * H));
+  a.dgb_lo_off = U.dgb_lo;
+  a.db_up = g.b_ih[1]; a.db_lo = g.b_ih[0];
+  a.dgq_up = static_cast<__nv_bfloat16*>(U.dgq); a.dgq_lo = static_cast<__nv_bfloat16*>(L.dgq); a.dgq_lo_off = U.dgq_lo;
+  a.dxm = ws.dx_mid; a.flags = flags;
+  a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nc = nc;
+  void* args[] = {&a};
+  e = cudaLaunchCooperativeKernel((const void*)lstm2_bwd_wave_split_kernel, dim3(2 * nc), dim3(kSplitThreads), args,
+                                  wave_bwd_split_smem(Hq), st);
+  TB_REQUIRE(e == cudaSuccess, "lstm2_bwd_wave_split_kernel: %s", cudaGetErrorString(e));
+  return check_launch("lstm2_bwd_wave_split_kernel");
 }
 
 // Side stream for work that can run beside a recurrence kernel (which occupies only H/8 = 65 of the 148 SMs):
@@ -2282,10 +2590,18 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
   // input-gradient product); only the hoisted weight-gradient GEMMs and the lower layer's dx remain per layer
   bool wave_done = false;
   const bool split_fwd = precision == 2 && layers == 2 && wave_fwd_split_applicable(B, In, H);  // same predicate as the forward
+  bool split_bwd = false;  // the split wavefront kernel ran: gate gradients are already bf16 hi/lo planes, bias gradients summed
   if (precision == 1 && layers == 2 && In <= H && wave_bwd_applicable(B, H)) {
     ProfScope prof("lstm_recurrence_bwd", st);
     TB_TRY(lstm2_bwd_wave(ws, p, g, dy, notdone, T1, B, H, st));
     wave_done = true;
+  } else if (split_fwd && wave_bwd_split_applicable(B, In, H)) {
+    // (the 4 padding columns of the [N, ld16(4H)] gate-gradient planes are never read as data: the GEMMs' tensor maps
+    //  end at column 4H)
+    ProfScope prof("lstm_recurrence_bwd", st);
+    TB_TRY(lstm2_bwd_wave_split(ws, p, g, dy, notdone, T1, B, H, st));
+    wave_done = true;
+    split_bwd = true;
   }
   // After the wavefront kernel only the hoisted weight-gradient GEMMs of both layers (and the lower layer's dx) remain.
   // The GEMMs feed nothing downstream in this backward pass: fork them onto the side stream (own split-K scratch); the
@@ -2304,7 +2620,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
     float* dxl = (l == 0) ? dx : ws.dx_mid;
     const int Hp = padded_h(H);
     const bool use_mma = precision == 1 && mma_recurrence_applicable(B, H);
-    if (!use_mma) {  // operands of the fp32 recurrence kernels
+    if (!use_mma && !split_bwd) {  // operands of the fp32 recurrence kernels
       const int64_t tot = int64_t(H + 4) * 4 * Hp;
       lstm_pack_whh_t_kernel<<<(unsigned)((tot + 255) / 256 > 1184 ? 1184 : (tot + 255) / 256), 256, 0, st>>>(p.w_hh[l], L.w_hh_t, H, Hp);
       TB_TRY(check_launch("lstm_pack_whh_t_kernel"));
@@ -2348,7 +2664,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
         forked = false;
       }
       // the tensor-core recurrence wrote the gate gradients in bf16 and summed the bias gradients itself
-      if (!use_mma) TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st, L.dgb_lo));
+      if (!use_mma && !split_bwd) TB_TRY(f32_to_bf16(L.dgates, L.dgb, N, 4 * H, 4 * H, lg, st, L.dgb_lo));
       const void* hm_b = L.hmb;
       int64_t hm_ld = lh, hm_lo = L.hmb_lo;
       const void* x_b = L.xb;
@@ -2392,7 +2708,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       te.C = g.w_ih[l]; te.ldc = in_dim;  // dW_ih[4H,in] = dgates^T . x
       te.b_lo = x_lo;
       TB_TRY(gemm_tc_bf16_ex(L.dgb, x_b, 4 * H, in_dim, N, lg, x_ld, true, true, te, sp, wscr, gs));
-      if (!use_mma) TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));
+      if (!use_mma && !split_bwd) TB_TRY(colsum(L.dgates, g.b_ih[l], N, 4 * H, 4 * H, colsum_scratch, st));
       cudaError_t e = cudaMemcpyAsync(g.b_hh[l], g.b_ih[l], sizeof(float) * 4 * H, cudaMemcpyDeviceToDevice, gs);
       TB_REQUIRE(e == cudaSuccess, "lstm: bias grad copy: %s", cudaGetErrorString(e));
       if (side) {

@@ -223,10 +223,8 @@ def learn(flags, model, actor_model, batch, initial_agent_state, optimizer, sche
     stager = None
     if _is_host(batch):
         stager = getattr(model, "_tb_stager", None)
-        key = tuple((k, tuple(v.shape), v.dtype) for k, v in batch.items())
-        if stager is None or getattr(stager, "_key", None) != key:
+        if stager is None or not all(k in stager.spec and stager.spec[k] == (tuple(v.shape), v.dtype) for k, v in batch.items()):
             stager = staging.RolloutStager(staging.spec_like(batch), model.flat_params.device, depth=3)
-            stager._key = key
             model._tb_stager = stager
         slot = stager.put(batch)
         initial_agent_state = tuple(t.to(model.flat_params.device, non_blocking=True) for t in initial_agent_state)
@@ -238,6 +236,9 @@ def learn(flags, model, actor_model, batch, initial_agent_state, optimizer, sche
                 if slot in stager._submitted:
                     stager._submitted.remove(slot)
             batch = stager.dev[slot]
+        if "last_action" not in batch and getattr(model, "needs_last_action", False):
+            # the polybeast nest has no separate last_action leaf: row t of `action` IS the action taken before frame t
+            batch = dict(batch, last_action=batch["action"])
         try:
             if _graph_enabled(flags):
                 graphs = model.__dict__.setdefault("_tb_graphs", {})

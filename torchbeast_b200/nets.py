@@ -213,6 +213,7 @@ class AtariNet(FlatParamModule):
     # "fp32": exact fp32 FFMA (SIMT) GEMMs - the slow parity anchor.
     PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2}
     DEFAULT_PRECISION = "bf16x3"
+    needs_last_action = True  # forward consumes inputs["last_action"] (monobeast.py:593-597); polybeast's Net does not
 
     def __init__(self, observation_shape, num_actions, use_lstm=False, device=None, precision=None):
         super().__init__()

@@ -26,6 +26,42 @@ AgentOutput = collections.namedtuple("AgentOutput", "action policy_logits baseli
 Batch = collections.namedtuple("Batch", "env agent")
 
 
+def _map_nest(fn, n):
+    """nest.map for the tuple / list / dict nests the reference passes around (nest_pybind.h:61-67: vectors are tuples)."""
+    if isinstance(n, torch.Tensor):
+        return fn(n)
+    if isinstance(n, dict):
+        return {k: _map_nest(fn, v) for k, v in n.items()}
+    return tuple(_map_nest(fn, v) for v in n)
+
+
+def inference(flags, inference_batcher, model, lock=threading.Lock()):  # noqa: B008
+    """The inference thread body - reference polybeast_learner.py:269-285.
+
+    `inference_batcher` yields DynamicBatcher batches (actorpool.cc:224-340): `batch.get_inputs()` returns
+    `(batched_env_outputs, agent_state)` with [T=1, B, ...] leaves, B = 1 .. 512 actors; the forward of the SAME CUDA
+    kernels the learner uses runs under `lock` on flags.actor_device, and `batch.set_outputs(((action, policy_logits,
+    baseline), core_state))` receives CPU tensors, like the reference.  Works for polybeast's Net (ResNet) and for AtariNet
+    (whose `last_action` input is taken from batched_env_outputs[5] if the nest carries one, else zeros)."""
+    device = torch.device(getattr(flags, "actor_device", None) or model.flat_params.device)
+    with torch.no_grad():
+        for batch in inference_batcher:
+            batched_env_outputs, agent_state = batch.get_inputs()
+            frame, reward, done, *rest = batched_env_outputs
+            inputs = dict(frame=frame.to(device, non_blocking=True), reward=reward.to(device, non_blocking=True),
+                          done=done.to(device, non_blocking=True))
+            if getattr(model, "needs_last_action", False):
+                la = rest[3] if len(rest) > 3 else torch.zeros(reward.shape, dtype=torch.int64)
+                inputs["last_action"] = la.to(device, non_blocking=True)
+            agent_state = _map_nest(lambda t: t.to(device, non_blocking=True), agent_state)
+            with lock:
+                outputs = model(inputs, agent_state)
+            if isinstance(outputs[0], dict):  # AtariNet returns a dict (monobeast.py:626-632): same tuple order as Net
+                o = outputs[0]
+                outputs = ((o["action"], o["policy_logits"], o["baseline"]), outputs[1])
+            batch.set_outputs(_map_nest(lambda t: t.cpu(), outputs))
+
+
 def _to_device(t, device):
     return t.to(device, non_blocking=True) if isinstance(t, torch.Tensor) else t
 
@@ -54,8 +90,6 @@ def learn(
         agent = AgentOutput._make(list(actor_outputs)[:3])
         rollout = dict(frame=env.frame, reward=env.rewards, done=env.done, episode_return=env.episode_return,
                        episode_step=env.episode_step, policy_logits=agent.policy_logits, action=agent.action)
-        if hasattr(model, "num_actions") and "last_action" not in rollout and type(model).__name__ == "AtariNet":
-            rollout["last_action"] = agent.action  # AtariNet consumes the previous action; the nest's action row 0 is it
         # host nest (what the reference's BatchingQueue yields) -> pinned slot -> async H2D, OUTSIDE the lock: with
         # num_learner_threads = 2 (polybeast_learner.py:62,505-521) this thread's copy overlaps the other thread's step.
         # _learner.learn takes the lock for the step itself (only one thread learning at a time, pl:313).
