@@ -155,6 +155,23 @@ int tb_atarinet_backward_phase(const float* grad_logits, const float* grad_basel
                                const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
                                int precision, void* workspace, float* grads, int phase, void* stream);
 
+/* ---- stacked LSTM over the unroll with per-step done-reset -------------------------------------------
+ * Replaces the reference's loop of seq_len-1 nn.LSTM calls and its autograd graph (monobeast.py:603-611,
+ * polybeast_learner.py:241-249):   for t: state *= notdone_t;  y_t, state = LSTM(x_t, state).
+ * torch.nn.LSTM conventions: params[4*l + {0,1,2,3}] = weight_ih_l [4H, In|H], weight_hh_l [4H, H], bias_ih_l [4H],
+ * bias_hh_l [4H] (gate order i, f, g, o); 1 or 2 layers; hidden size, input size, batch and unroll are free
+ * (BASELINE configs[4]: T = 600, B = 128, H = 512).  x [T1*B, In], notdone [T1*B] (float 0/1), h0/c0/hN/cN [layers, B, H],
+ * y [T1*B, H].  precision 0 = fp32 everywhere (any shape); 1 / 2 = bf16 / split-bf16 tensor-core products for the hoisted
+ * projections.  tb_lstm_backward must follow tb_lstm_forward on the same workspace; grads[] mirrors params[] and is
+ * overwritten; dx [T1*B, In].                                                                                        */
+size_t tb_lstm_workspace_bytes(int64_t T1, int64_t B, int input_size, int hidden_size, int layers, int precision);
+int tb_lstm_forward(const float* x, const float* notdone, const float* h0, const float* c0, const float* const* params,
+                    int64_t T1, int64_t B, int input_size, int hidden_size, int layers, int precision, void* workspace,
+                    float* y, float* hN, float* cN, void* stream);
+int tb_lstm_backward(const float* dy, const float* x, const float* notdone, const float* const* params, float* const* grads,
+                     int64_t T1, int64_t B, int input_size, int hidden_size, int layers, int precision, void* workspace,
+                     float* dx, void* stream);
+
 /* ---- IMPALA ResNet (polybeast_learner.py:134-266 `Net`) forward / backward ------------------------- */
 
 /* Flat parameter layout = the reference's state_dict order: feat_convs.{0,1,2}.0.{weight,bias}

@@ -2748,3 +2748,79 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
 }
 
 }  // namespace tb
+
+// =======================================================================================
+// C ABI: the stacked LSTM on its own, hidden size / layers / batch as parameters (SURVEY 8(b) B3 tb_lstm_{fwd,bwd};
+// BASELINE configs[4]: "long-unroll stress T=600 B=128, LSTM hidden=512")
+// =======================================================================================
+using namespace tb;
+
+namespace {
+constexpr int64_t kLstmAbiSplitK = int64_t(8) << 20;  // floats, == kSplitKScratchFloats of the network entry points
+
+struct LstmAbiWs { LstmWs ws; float* splitk; float* colsum; size_t bytes; };
+
+LstmAbiWs lstm_abi_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int precision) {
+  LstmAbiWs w;
+  const size_t lbytes = lstm_ws_bytes(T1, B, In, H, layers, precision);
+  size_t off = (lbytes + 255) & ~size_t(255);
+  w.ws = lstm_ws(base, T1, B, In, H, layers, precision);
+  w.splitk = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+  off += size_t(kLstmAbiSplitK) * sizeof(float);
+  w.colsum = base ? reinterpret_cast<float*>(static_cast<char*>(base) + off) : nullptr;
+  off += size_t(colsum_scratch_floats(4 * int64_t(H) > 512 ? 4 * int64_t(H) : 512)) * sizeof(float);
+  w.bytes = off;
+  return w;
+}
+
+int lstm_abi_check(int64_t T1, int64_t B, int In, int H, int layers, int precision) {
+  TB_REQUIRE(T1 >= 1 && B >= 1 && In >= 1 && H >= 1, "tb_lstm: bad sizes T1=%lld B=%lld In=%d H=%d", (long long)T1, (long long)B, In, H);
+  TB_REQUIRE(layers >= 1 && layers <= kLstmMaxLayers, "tb_lstm: 1..%d layers", kLstmMaxLayers);
+  TB_REQUIRE(precision >= 0 && precision <= 2, "tb_lstm: precision must be 0 (fp32), 1 (bf16) or 2 (split-bf16)");
+  TB_REQUIRE(precision == 0 || ((In % 1) == 0), "tb_lstm: bad precision");
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+size_t tb_lstm_workspace_bytes(int64_t T1, int64_t B, int input_size, int hidden_size, int layers, int precision) {
+  if (T1 < 1 || B < 1 || input_size < 1 || hidden_size < 1 || layers < 1 || layers > kLstmMaxLayers) return 0;
+  return lstm_abi_ws(nullptr, T1, B, input_size, hidden_size, layers, precision).bytes;
+}
+
+int tb_lstm_forward(const float* x, const float* notdone, const float* h0, const float* c0, const float* const* params,
+                    int64_t T1, int64_t B, int input_size, int hidden_size, int layers, int precision, void* workspace,
+                    float* y, float* hN, float* cN, void* stream) {
+  if (lstm_abi_check(T1, B, input_size, hidden_size, layers, precision)) return 1;
+  TB_REQUIRE(x && notdone && h0 && c0 && params && workspace && y && hN && cN, "tb_lstm_forward: null pointer");
+  LstmParams p;
+  for (int l = 0; l < layers; ++l) {
+    p.w_ih[l] = params[4 * l]; p.w_hh[l] = params[4 * l + 1]; p.b_ih[l] = params[4 * l + 2]; p.b_hh[l] = params[4 * l + 3];
+    TB_REQUIRE(p.w_ih[l] && p.w_hh[l] && p.b_ih[l] && p.b_hh[l], "tb_lstm_forward: null parameter pointer (layer %d)", l);
+  }
+  LstmAbiWs w = lstm_abi_ws(workspace, T1, B, input_size, hidden_size, layers, precision);
+  return lstm_forward(x, notdone, h0, c0, p, T1, B, input_size, hidden_size, layers, w.ws, y, hN, cN, w.splitk, precision,
+                      (cudaStream_t)stream);
+}
+
+int tb_lstm_backward(const float* dy, const float* x, const float* notdone, const float* const* params, float* const* grads,
+                     int64_t T1, int64_t B, int input_size, int hidden_size, int layers, int precision, void* workspace,
+                     float* dx, void* stream) {
+  if (lstm_abi_check(T1, B, input_size, hidden_size, layers, precision)) return 1;
+  TB_REQUIRE(dy && x && notdone && params && grads && workspace && dx, "tb_lstm_backward: null pointer");
+  LstmParams p; LstmGrads g;
+  for (int l = 0; l < layers; ++l) {
+    p.w_ih[l] = params[4 * l]; p.w_hh[l] = params[4 * l + 1]; p.b_ih[l] = params[4 * l + 2]; p.b_hh[l] = params[4 * l + 3];
+    g.w_ih[l] = grads[4 * l]; g.w_hh[l] = grads[4 * l + 1]; g.b_ih[l] = grads[4 * l + 2]; g.b_hh[l] = grads[4 * l + 3];
+    TB_REQUIRE(p.w_ih[l] && p.w_hh[l] && g.w_ih[l] && g.w_hh[l] && g.b_ih[l] && g.b_hh[l], "tb_lstm_backward: null pointer (layer %d)", l);
+  }
+  LstmAbiWs w = lstm_abi_ws(workspace, T1, B, input_size, hidden_size, layers, precision);
+  int rc = lstm_backward(dy, x, notdone, p, g, T1, B, input_size, hidden_size, layers, w.ws, dx, w.splitk, w.colsum, precision,
+                         (cudaStream_t)stream);
+  if (rc) return rc;
+  return lstm_backward_join((cudaStream_t)stream);
+}
+
+}  // extern "C"
+
