@@ -115,3 +115,37 @@ def test_backward_vs_oracle_fixed_cotangents(fname, precision):
     lim = (1e-4, 0.999999) if precision == "fp32" else (0.2, 0.98)
     bad = {n: v for n, v in report.items() if v[0] >= lim[0] or v[1] <= lim[1]}
     assert not bad, (bad, report)
+
+
+def test_learn_step_at_one_gpu_shard_of_config4():
+    """BASELINE configs[3] (ResNet + LSTM, T=80, B=64 over 8 GPUs) -> one GPU's shard: T=80, B=8, against the fixture the
+    reference's polybeast_learner.learn produced at that size (learn_resnet_lstm_T80_B8.npz): outputs, V-trace targets,
+    losses, 4096 strided gradient samples per tensor, updated parameters.  Same tolerance structure as
+    tests/test_learner_baseline_gpu.py (fp32 backend)."""
+    from tests.common import sample_index
+    from torchbeast_b200 import learner, polybeast_learner
+    g, model, actor, batch, params, state, opt, sched, flags = build("learn_resnet_lstm_T80_B8.npz")
+    cb = {k: v.cuda() for k, v in batch.items()}
+    out = model.learner_forward(cb, tuple(s.cuda() for s in state))
+    np.testing.assert_allclose(out.policy_logits.cpu().numpy(), g["policy_logits"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(out.baseline.cpu().numpy(), g["baseline"], rtol=1e-5, atol=1e-5)
+    loss = learner.impala_loss_fwd_bwd(cb["policy_logits"][1:], out.policy_logits[:-1], cb["action"][1:], cb["reward"][1:],
+                                       cb["done"][1:], out.baseline[:-1], out.baseline[-1])
+    np.testing.assert_allclose(loss.vs.cpu().numpy(), g["vs"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(loss.pg_advantages.cpu().numpy(), g["pg_advantages"], rtol=1e-5, atol=1e-5)
+    stats = {}
+    polybeast_learner.learn(flags, queue_of(batch, state), model, actor, opt, sched, stats, mock.Mock())
+    for k in ("total_loss", "pg_loss", "baseline_loss", "entropy_loss"):
+        np.testing.assert_allclose(stats[k], float(g[k]), rtol=1e-5, atol=1e-5, err_msg=k)
+    assert stats["step"] == 80 * 8
+    for n, p in model.named_parameters():
+        gr = p.grad.detach().cpu().flatten()
+        idx = torch.from_numpy(sample_index(gr.numel()))
+        ref = torch.from_numpy(g["grad_sample/" + n]).double()
+        got = gr[idx].double()
+        rel = float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+        worst = float((got - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        assert rel < 6e-3 and worst < 1.5e-2, (n, rel, worst)
+        np.testing.assert_allclose(p.detach().cpu().flatten()[idx].numpy(), g["param_sample/" + n], rtol=1e-4, atol=5e-4, err_msg=n)
+    for (n, a), (_, b) in zip(actor.named_parameters(), model.named_parameters()):
+        assert torch.equal(a, b), n

@@ -252,3 +252,22 @@ def test_fused_loss_vs_oracle(T, B, A):
     r2 = learner.impala_loss_fwd_bwd(cu(v["behavior_policy_logits"]), cu(v["target_policy_logits"]), cu(v["actions"]),
                                      cu(rew), cu(done), cu(v["values"]), cu(v["bootstrap_value"]))
     assert torch.equal(r2.losses, r.losses) and torch.equal(r2.grad_logits, r.grad_logits)
+
+
+def test_out_of_range_action_is_loud_not_out_of_bounds(vtrace):
+    """an action index outside [0, A) (the reference raises 'Target out of bounds') must neither read out of
+    bounds nor silently pick a logit: the affected elements are NaN, everything else is untouched."""
+    logits = torch.randn(4, 3, 6, device="cuda")
+    actions = torch.randint(0, 6, (4, 3), device="cuda")
+    good = vtrace.action_log_probs(logits, actions)
+    bad_actions = actions.clone()
+    bad_actions[1, 2] = 6
+    bad_actions[3, 0] = -1
+    bad = vtrace.action_log_probs(logits, bad_actions)
+    assert torch.isnan(bad[1, 2]) and torch.isnan(bad[3, 0])
+    mask = torch.ones_like(good, dtype=torch.bool)
+    mask[1, 2] = False; mask[3, 0] = False
+    assert torch.equal(bad[mask], good[mask])
+    big = torch.randn(4, 3, 40, device="cuda")  # runtime-A path
+    ba = torch.randint(0, 40, (4, 3), device="cuda"); ba[0, 0] = 40
+    assert torch.isnan(vtrace.action_log_probs(big, ba)[0, 0])

@@ -229,6 +229,10 @@ __device__ __forceinline__ F alp_dyn(const F* __restrict__ row, int64_t A, int64
   for (int64_t j = 0; j < A; ++j) s += M<F>::exp(row[j] - m);
   const F logs = M<F>::log(s);
   if (m_out) { *m_out = m; *logs_out = logs; }
+  // an action index outside [0, A) is a caller bug (the reference's nll_loss raises "Target out of bounds"); a kernel
+  // cannot raise, so it must neither read out of bounds nor silently pick a logit: the result is NaN, which poisons the
+  // loss and is caught by the caller's finiteness checks
+  if (a < 0 || a >= A) return F(NAN);
   return (row[a] - m) - logs;
 }
 
@@ -242,6 +246,7 @@ __device__ __forceinline__ F alp_row(const F* __restrict__ row, int64_t Adyn, in
     F m, logs;
     RowOps<F, A>::lse(x, m, logs);
     if (m_out) { *m_out = m; *logs_out = logs; }
+    if (a < 0 || a >= A) return F(NAN);  // see alp_dyn
     return (RowOps<F, A>::pick(x, a) - m) - logs;
   }
 }
