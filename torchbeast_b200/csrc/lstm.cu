@@ -76,7 +76,7 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
   w.wg_scratch = (precision && layers == 2) ? takef(int64_t(4) * 4 * H * (((H > In ? H : In) + 31) & ~31)) : nullptr;
   w.dgp = takef(int64_t(2) * 4 * B * padded_h(H));
   w.sync = reinterpret_cast<unsigned*>(takef(64));
-  w.flags = reinterpret_cast<unsigned*>(takef(1024));
+  w.flags = reinterpret_cast<unsigned*>(takef(2 * 512 * 32));  // 2 x 512 flags, 128 bytes apart (kFlagStride)
   w.Hp = padded_h(H);
   w.bytes = off;
   return w;
@@ -1586,6 +1586,8 @@ __global__ void lstm_init_state_q_kernel(const float* __restrict__ h0, const flo
 //     spinning on its flag with relaxed loads, one acquire load, bar.sync.
 // CTA = kStepUnits hidden units x 4 gates of BOTH layers, B <= 32 rows, ceil(H/16) <= 33.
 // =========================================================================================
+constexpr int kFlagStride = 32;   // one flag per 128-byte line: 130 CTAs polling 130 flags packed into 5 lines made those
+                                  // lines' L2 slices the bottleneck (ncu: 36 % of the samples in the spin, loads ~3000 cycles)
 constexpr int kSplitWarps = 11;
 constexpr int kSplitThreads = kSplitWarps * 32;
 constexpr int kSplitK = 3;  // k16 steps per warp
@@ -1629,7 +1631,6 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
   typedef float PartT[2][16][33];
   PartT* part = reinterpret_cast<PartT*>(smem_b + size_t(4) * tile * 2);  // [11 warps][set][col][row]
   __shared__ float act_s[2][4][kStepUnits][33];
-  __shared__ float nd_s[2][32];
   const int j0 = blockIdx.x * kStepUnits;
   const int rows = (B < 32) ? B : 32;
   const int ksteps = (H + 15) / 16;
@@ -1675,8 +1676,6 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
   __nv_bfloat16* const hq_u = ul ? a.hq[1] : a.hq[0];
   __nv_bfloat16* const hmq_u = ul ? a.hmq[1] : a.hmq[0];
   float c_state = updrole ? a.c0[(int64_t(ul) * B + ur) * H + j0 + uu] : 0.f;  // c_{t-1} of this (layer, row, unit)
-  const int chunks_per_row = (ksteps * 16) / 8;          // 16-byte chunks the MMAs read (the row padding is never touched)
-  const int nchunk = rows * chunks_per_row;
   for (int s = 0; s <= a.T1; ++s) {
     const bool act0 = (s < a.T1), act1 = (s >= 1);
     // inputs that do not depend on other CTAs: issued before the wait
@@ -1692,34 +1691,54 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
       nd_t = __ldg(a.nd + int64_t(tu) * B + ur);
       if (tu < a.T1 - 1) nd_n = __ldg(a.nd + int64_t(tu + 1) * B + ur);
     }
-    if (s > 0) {  // every CTA has published wave step s-1
-      if (tid < int(a.nctas)) {
-        while (ld_relaxed_u32(a.flags + tid) < unsigned(s)) {}
-        (void)ld_acquire_u32(a.flags + tid);
+    // Every tile element is consumed by exactly ONE warp (K is split across the warps), so each warp waits only for the
+    // CTAs that produce ITS k-range (units [16*ks0, 16*ks0 + 48) -> 12 producer CTAs), pulls its own columns of the four
+    // tiles (cp.async, one commit group per k-step) and starts its MMAs on k-step 0 while k-steps 1, 2 are still in
+    // flight - no block-wide barrier between the hand-off and the products.  (History: 130 threads per CTA polling 130
+    // flag words - 17 k pollers chip-wide on 5 cache lines - made the L2 slices of those lines the bottleneck: ncu
+    // showed 36 % of all samples in the spin and the step at 9.8 us.)
+    if (s > 0) {
+      const int p0 = (ks0 * 16) / kStepUnits + lane;                   // producer CTA of this lane
+      const int pend = (min((ks0 + kSplitK) * 16, H) + kStepUnits - 1) / kStepUnits;
+      if (lane < 12 && p0 < pend && p0 < int(a.nctas)) {
+        while (ld_relaxed_u32(a.flags + p0 * kFlagStride) < unsigned(s)) {}
+        (void)ld_acquire_u32(a.flags + p0 * kFlagStride);
       }
+      __syncwarp();
     }
-    __syncthreads();
+    float m0[2][2], m1[2][2];   // done masks of this thread's accumulator rows (layer 0 at t = s, layer 1 at t = s-1)
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int r = mt * 16 + (lane >> 2) + hh * 8;
+        m0[mt][hh] = (r < rows && act0) ? __ldg(a.nd + int64_t(s) * B + r) : 0.f;
+        m1[mt][hh] = (r < rows && act1) ? __ldg(a.nd + int64_t(s - 1) * B + r) : 0.f;
+      }
     {
       const __nv_bfloat16* src0 = a.hq[0] + int64_t(s) * B * Hq;
       const __nv_bfloat16* src1 = a.hq[1] + int64_t(s > 0 ? s - 1 : 0) * B * Hq;
-      for (int i = tid; i < nchunk; i += kSplitThreads) {
-        const int r = i / chunks_per_row, c = i - r * chunks_per_row;
-        const int off = r * Hq + c * 8;
-        cp_async16(X + off, src0 + off);
-        cp_async16(X + tile + off, src0 + a.hq_lo + off);
-        if (act1) {
-          cp_async16(X + 2 * tile + off, src1 + off);
-          cp_async16(X + 3 * tile + off, src1 + a.hq_lo + off);
+      // this warp's 48 columns (96 contiguous bytes per row) of each plane: lanes walk (row, 16-byte chunk) with the chunk
+      // fastest - ~6 cache lines per warp instruction (a (row, half-k-step) walk touched 16 and ran the LSU 3x longer).
+      // Two commit groups: the h0 planes first, so the layer-0 / input-projection MMAs start while the h1 planes land.
+#pragma unroll
+      for (int grp = 0; grp < 2; ++grp) {
+        if (grp == 0 || act1) {
+          const __nv_bfloat16* src = (grp ? src1 : src0) + ks0 * 16;
+          __nv_bfloat16* dst = X + grp * 2 * tile + ks0 * 16;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int j = lane + 32 * i;            // 192 (row, chunk) pairs
+            const int r = j / 6, c = j - r * 6;
+            if (r < rows && (ks0 * 16 + c * 8) < ksteps * 16) {
+              cp_async16(dst + r * Hq + c * 8, src + int64_t(r) * Hq + c * 8);
+              cp_async16(dst + tile + r * Hq + c * 8, src + a.hq_lo + int64_t(r) * Hq + c * 8);
+            }
+          }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    if (tid < 64) {
-      const int l = tid >> 5, r = tid & 31, t = s - l;
-      nd_s[l][r] = (r < rows && t >= 0 && t < a.T1) ? __ldg(a.nd + int64_t(t) * B + r) : 0.f;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
     {
       float acc0[2][2][4], accI[2][2][4], acc1[2][2][4];
 #pragma unroll
@@ -1728,6 +1747,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
         for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
           for (int e = 0; e < 4; ++e) { acc0[mt][nt][e] = 0.f; accI[mt][nt][e] = 0.f; acc1[mt][nt][e] = 0.f; }
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // the h0 planes
+      __syncwarp();
 #pragma unroll
       for (int sk = 0; sk < kSplitK; ++sk) {
         if (ks0 + sk < ksteps) {
@@ -1744,6 +1765,20 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
             if (act1) {
               mma3(accI[mt][0], ah, al, bh[1][sk][0][0], bh[1][sk][0][1], bl[1][sk][0][0], bl[1][sk][0][1]);
               mma3(accI[mt][1], ah, al, bh[1][sk][1][0], bh[1][sk][1][1], bl[1][sk][1][0], bl[1][sk][1][1]);
+            }
+          }
+        }
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");   // the h1 planes
+      __syncwarp();
+      if (act1) {
+#pragma unroll
+        for (int sk = 0; sk < kSplitK; ++sk) {
+          if (ks0 + sk < ksteps) {
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+              uint32_t ah[4], al[4];
+              const int off = (mt * 16 + (lane & 15)) * Hq + (ks0 + sk) * 16 + (lane >> 4) * 8;
               ldmatrix_x4(ah, X + 2 * tile + off);
               ldmatrix_x4(al, X + 3 * tile + off);
               mma3(acc1[mt][0], ah, al, bh[2][sk][0][0], bh[2][sk][0][1], bl[2][sk][0][0], bl[2][sk][0][1]);
@@ -1752,11 +1787,10 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
           }
         }
       }
-      // the done-mask is a 0/1 row scale: applied to the recurrent PRODUCTS (raw h tiles are exchanged)
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const int r = mt * 16 + (lane >> 2);
-        const float m0a = nd_s[0][r], m0b = nd_s[0][r + 8], m1a = nd_s[1][r], m1b = nd_s[1][r + 8];
+        const float m0a = m0[mt][0], m0b = m0[mt][1], m1a = m1[mt][0], m1b = m1[mt][1];
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt) {
           const int c = nt * 8 + (lane & 3) * 2;
@@ -1816,7 +1850,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
     __syncthreads();
     if (tid == 0 && s < a.T1) {
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
-      st_relaxed_u32(a.flags + blockIdx.x, unsigned(s + 1));
+      st_relaxed_u32(a.flags + blockIdx.x * kFlagStride, unsigned(s + 1));
     }
     // ---- everything below is consumed by this CTA or after the kernel: off the critical path ----
     if (actrole) {
@@ -1881,10 +1915,15 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
   extern __shared__ __align__(128) unsigned char smem_b[];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int H = a.H, Hq = a.Hq, B = a.B;
-  const int tile = 32 * Hq;                                      // one plane of one gate
-  __nv_bfloat16* X = reinterpret_cast<__nv_bfloat16*>(smem_b);   // ring: [2 slots][hi, lo][32][Hq]
+  // Every tile element is consumed by exactly one warp (K = (gate, unit) is split across the warps: this warp owns units
+  // [16*ks0, 16*ks0 + 48) of every gate), so the tiles stream through WARP-PRIVATE 2-slot rings - slot = one gate,
+  // [hi, lo][32 rows][48 units], rows padded to 56 elements (112 B: conflict-free ldmatrix) - with no block barrier
+  // anywhere in the fetch / MMA phase.
+  constexpr int kRowE = kSplitK * 16 + 8;                        // elements per ring row
+  constexpr int kPlaneE = 32 * kRowE;                            // one plane of one slot
+  __nv_bfloat16* X = reinterpret_cast<__nv_bfloat16*>(smem_b) + int64_t(wrp) * 4 * kPlaneE;  // [2 slots][hi, lo][32][kRowE]
   typedef float PartT[2][kBwdCols][33];
-  PartT* part = reinterpret_cast<PartT*>(smem_b + size_t(4) * tile * 2);  // [11 warps][product][col][row]
+  PartT* part = reinterpret_cast<PartT*>(smem_b + size_t(kSplitWarps) * 4 * kPlaneE * 2);  // [11 warps][product][col][row]
   __shared__ float dh_s[kBwdCols][33];
   __shared__ float dc_s[kBwdCols][33];
   __shared__ __align__(16) __nv_bfloat16 stg_s[2][4][32][kBwdCols];       // [plane][gate][row][col]
@@ -1927,8 +1966,6 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
   if (wrp < kBwdCols) { dh_s[wrp][lane] = 0.0f; dc_s[wrp][lane] = 0.0f; }
   __syncthreads();
   const int64_t gs = int64_t(B) * Hq;      // one gate of one exchange buffer
-  const int chunks_per_row = (kpg * 16) / 8;
-  const int nchunk = rows * chunks_per_row;
   const int q = wrp;  // pointwise role: thread = (batch row lane, unit k0 + wrp), warps 0..7
   const bool actA = (wrp < kBwdCols && lane < rows && k0 + q < H);
   auto time_of = [&](int s) { return upper ? a.T1 - 1 - s : a.T1 + 1 - s; };
@@ -1959,8 +1996,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
     }
   };
   const int last_s = a.T1 + 1;
-  unsigned* const my_flag = a.flags + blockIdx.x;
-  const unsigned* const role_flags = a.flags + (upper ? 0 : a.nc);
+  unsigned* const my_flag = a.flags + blockIdx.x * kFlagStride;
+  const unsigned* const role_flags = a.flags + (upper ? 0 : a.nc) * kFlagStride;
   int it = 0;  // this role's active-step counter
   for (int s = 0; s <= last_s; ++s) {
     const int t = time_of(s);
@@ -2014,27 +2051,35 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
     }
     if (active && actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
     prefetch(time_of(s + 1));  // forward-pass operands only: overlaps the wait
-    // wait: every CTA of this role has published wave step s; lower role: plus the upper CTA with the same columns
-    if (tid < int(a.nc)) {
-      while (ld_relaxed_u32(role_flags + tid) < unsigned(s + 1)) {}
-      (void)ld_acquire_u32(role_flags + tid);
-    } else if (!upper && tid == int(a.nc)) {
-      while (ld_relaxed_u32(a.flags + cidx) < unsigned(s + 1)) {}
-      (void)ld_acquire_u32(a.flags + cidx);
+    // hand-off: this warp needs the tile columns of units [16*ks0, 16*ks0 + 48) -> the 6 CTAs of its own role that own
+    // them; the pointwise threads of the lower role additionally need the upper CTA with the same 8 columns (its dxm)
+    {
+      const int p0 = (ks0 * 16) / kBwdCols + lane;
+      const int pend = (min((ks0 + kSplitK) * 16, H) + kBwdCols - 1) / kBwdCols;
+      if (lane < 6 && p0 < pend && p0 < int(a.nc)) {
+        while (ld_relaxed_u32(role_flags + p0 * kFlagStride) < unsigned(s + 1)) {}
+        (void)ld_acquire_u32(role_flags + p0 * kFlagStride);
+      } else if (!upper && lane == 8 && wrp < kBwdCols) {
+        while (ld_relaxed_u32(a.flags + cidx * kFlagStride) < unsigned(s + 1)) {}
+        (void)ld_acquire_u32(a.flags + cidx * kFlagStride);
+      }
+      __syncwarp();
     }
-    __syncthreads();
     fetch_dxm(time_of(s + 1));  // written by the upper role before it published wave step s
     const bool need_rec = active && t > 0;
     const bool need_dx = active && upper;
     if (need_rec || need_dx) {
-      auto issue = [&](int g) {
-        const __nv_bfloat16* src = dgq_t + int64_t(g) * gs;
-        __nv_bfloat16* dst = X + int64_t(g & 1) * 2 * tile;
-        for (int i = tid; i < nchunk; i += kSplitThreads) {
-          const int r = i / chunks_per_row, c = i - r * chunks_per_row;
-          const int off = r * Hq + c * 8;
-          cp_async16(dst + off, src + off);
-          cp_async16(dst + tile + off, src + a.dgq_lo_off + off);
+      auto issue = [&](int g) {   // this warp's 48 columns of gate g, hi and lo plane: 32 rows x 6 chunks x 2 = 12 per lane
+        const __nv_bfloat16* src = dgq_t + int64_t(g) * gs + ks0 * 16;
+        __nv_bfloat16* dst = X + int64_t(g & 1) * 2 * kPlaneE;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int j = lane + 32 * i;            // 192 (row, chunk) pairs
+          const int r = j / 6, c = j - r * 6;
+          if (r < rows && (ks0 * 16 + c * 8) < kpg * 16) {
+            cp_async16(dst + r * kRowE + c * 8, src + int64_t(r) * Hq + c * 8);
+            cp_async16(dst + kPlaneE + r * kRowE + c * 8, src + a.dgq_lo_off + int64_t(r) * Hq + c * 8);
+          }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
       };
@@ -2049,23 +2094,23 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
       for (int g = 0; g < 4; ++g) {
         if (g < 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        const __nv_bfloat16* Xg = X + int64_t(g & 1) * 2 * tile;
+        __syncwarp();
+        const __nv_bfloat16* Xg = X + int64_t(g & 1) * 2 * kPlaneE;
 #pragma unroll
         for (int sk = 0; sk < kSplitK; ++sk) {
           if (ks0 + sk < kpg) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
               uint32_t ah[4], al[4];
-              const int off = (mt * 16 + (lane & 15)) * Hq + (ks0 + sk) * 16 + (lane >> 4) * 8;
+              const int off = (mt * 16 + (lane & 15)) * kRowE + sk * 16 + (lane >> 4) * 8;
               ldmatrix_x4(ah, Xg + off);
-              ldmatrix_x4(al, Xg + tile + off);
+              ldmatrix_x4(al, Xg + kPlaneE + off);
               if (need_rec) mma3(acc0[mt], ah, al, bh[g][sk][0], bh[g][sk][1], bl[g][sk][0], bl[g][sk][1]);
               if (need_dx) mma3(acc1[mt], ah, al, ih[g][sk][0], ih[g][sk][1], il[g][sk][0], il[g][sk][1]);
             }
           }
         }
-        __syncthreads();
+        __syncwarp();
         if (g + 2 < 4) issue(g + 2);
       }
 #pragma unroll
@@ -2229,7 +2274,7 @@ static int lstm2_fwd_wave_split(LstmWs& ws, const LstmParams& p, float* y, const
                                 int64_t B, int H, cudaStream_t st) {
   const int Hq = mma_hq(H);
   dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
-  cudaError_t e = cudaMemsetAsync(ws.flags, 0, sizeof(unsigned) * 512, st);
+  cudaError_t e = cudaMemsetAsync(ws.flags, 0, sizeof(unsigned) * 512 * kFlagStride, st);
   TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
   WaveFwdSplitArgs a;
   a.w_hh0 = p.w_hh[0]; a.w_ih1 = p.w_ih[1]; a.w_hh1 = p.w_hh[1]; a.bias1 = ws.layer[1].bsum; a.c0 = c0;
@@ -2313,7 +2358,9 @@ static int lstm2_bwd_wave(LstmWs& ws, const LstmParams& p, const LstmGrads& g, c
 }
 
 static size_t g_bwd_split_attr = 0;
-static size_t wave_bwd_split_smem(int Hq) { return size_t(4) * 32 * Hq * 2 + sizeof(float) * kSplitWarps * 2 * kBwdCols * 33; }
+static size_t wave_bwd_split_smem(int) {
+  return size_t(kSplitWarps) * 4 * 32 * (kSplitK * 16 + 8) * 2 + sizeof(float) * kSplitWarps * 2 * kBwdCols * 33;
+}
 static bool wave_bwd_split_applicable(int64_t B, int In, int H) {
   const char* e = getenv("TB_LSTM_SPLIT_BWD");
   if (e && e[0] == '0') return false;
@@ -2345,8 +2392,8 @@ static int lstm2_bwd_wave_split(LstmWs& ws, const LstmParams& p, const LstmGrads
   const unsigned nc = unsigned((H + kBwdCols - 1) / kBwdCols);
   const LstmLayerWs& U = ws.layer[1];
   const LstmLayerWs& L = ws.layer[0];
-  unsigned* flags = ws.flags + 512;
-  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(unsigned) * 512, st);
+  unsigned* flags = ws.flags + 512 * kFlagStride;
+  cudaError_t e = cudaMemsetAsync(flags, 0, sizeof(unsigned) * 512 * kFlagStride, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(U.dgq, 0, size_t(U.dgq_lo + int64_t(2) * 4 * B * Hq) * 2, st);  // zero the row padding
   if (e == cudaSuccess) e = cudaMemsetAsync(L.dgq, 0, size_t(L.dgq_lo + int64_t(2) * 4 * B * Hq) * 2, st);
   TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));

@@ -42,7 +42,7 @@ def inference(flags, inference_batcher, model, lock=threading.Lock()):  # noqa: 
     `(batched_env_outputs, agent_state)` with [T=1, B, ...] leaves, B = 1 .. 512 actors; the forward of the SAME CUDA
     kernels the learner uses runs under `lock` on flags.actor_device, and `batch.set_outputs(((action, policy_logits,
     baseline), core_state))` receives CPU tensors, like the reference.  Works for polybeast's Net (ResNet) and for AtariNet
-    (whose `last_action` input is taken from batched_env_outputs[5] if the nest carries one, else zeros)."""
+    (whose `last_action` input is batched_env_outputs[5] if the nest carries one, else zeros)."""
     device = torch.device(getattr(flags, "actor_device", None) or model.flat_params.device)
     with torch.no_grad():
         for batch in inference_batcher:
@@ -51,7 +51,7 @@ def inference(flags, inference_batcher, model, lock=threading.Lock()):  # noqa: 
             inputs = dict(frame=frame.to(device, non_blocking=True), reward=reward.to(device, non_blocking=True),
                           done=done.to(device, non_blocking=True))
             if getattr(model, "needs_last_action", False):
-                la = rest[3] if len(rest) > 3 else torch.zeros(reward.shape, dtype=torch.int64)
+                la = rest[2] if len(rest) > 2 else torch.zeros(reward.shape, dtype=torch.int64)
                 inputs["last_action"] = la.to(device, non_blocking=True)
             agent_state = _map_nest(lambda t: t.to(device, non_blocking=True), agent_state)
             with lock:
