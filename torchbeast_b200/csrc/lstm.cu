@@ -1592,6 +1592,11 @@ constexpr int kSplitWarps = 11;
 constexpr int kSplitThreads = kSplitWarps * 32;
 constexpr int kSplitK = 3;  // k16 steps per warp
 
+// Debug timeline (TB_LSTM_TRACE=<file>): thread 0 of every CTA stamps clock64() at the phase boundaries of every wave step
+// into a device buffer that the launcher dumps after the kernel (synchronising - never enabled in production runs).
+constexpr int kTracePhases = 8;
+#define TB_TRACE(ph) do { if (a.trace && tid == 0) a.trace[(int64_t(blockIdx.x) * (a.T1 + 2) + s) * kTracePhases + (ph)] = clock64(); } while (0)
+
 struct WaveFwdSplitArgs {
   const float* w_hh0; const float* w_ih1; const float* w_hh1; const float* bias1;
   const float* c0;          // [2, B, H] initial cell state
@@ -1601,6 +1606,7 @@ struct WaveFwdSplitArgs {
   int64_t hq_lo, hmq_lo;
   const float* nd; unsigned* flags;
   int T1, B, H, Hq; unsigned nctas;
+  long long* trace;
 };
 
 __device__ __forceinline__ void split_pack(float v0, float v1, uint32_t& hi, uint32_t& lo) {
@@ -1678,6 +1684,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
   float c_state = updrole ? a.c0[(int64_t(ul) * B + ur) * H + j0 + uu] : 0.f;  // c_{t-1} of this (layer, row, unit)
   for (int s = 0; s <= a.T1; ++s) {
     const bool act0 = (s < a.T1), act1 = (s >= 1);
+    TB_TRACE(0);
     // inputs that do not depend on other CTAs: issued before the wait
     float preA = 0.f, preB = 0.f;
     if (act0) {
@@ -1706,6 +1713,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
       }
       __syncwarp();
     }
+    TB_TRACE(1);
     float m0[2][2], m1[2][2];   // done masks of this thread's accumulator rows (layer 0 at t = s, layer 1 at t = s-1)
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -1749,6 +1757,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
           for (int e = 0; e < 4; ++e) { acc0[mt][nt][e] = 0.f; accI[mt][nt][e] = 0.f; acc1[mt][nt][e] = 0.f; }
       asm volatile("cp.async.wait_group 1;" ::: "memory");   // the h0 planes
       __syncwarp();
+      TB_TRACE(2);
 #pragma unroll
       for (int sk = 0; sk < kSplitK; ++sk) {
         if (ks0 + sk < ksteps) {
@@ -1771,6 +1780,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");   // the h1 planes
       __syncwarp();
+      TB_TRACE(3);
       if (act1) {
 #pragma unroll
         for (int sk = 0; sk < kSplitK; ++sk) {
@@ -1803,7 +1813,9 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
         }
       }
     }
+    TB_TRACE(4);
     __syncthreads();
+    TB_TRACE(5);
     float g0A = 0.f, g0B = 0.f, g1A = 0.f, g1B = 0.f;
     if (actrole) {
       float d0A = 0.f, d0B = 0.f, d1A = 0.f, d1B = 0.f;
@@ -1848,10 +1860,12 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
       }
     }
     __syncthreads();
+    TB_TRACE(6);
     if (tid == 0 && s < a.T1) {
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       st_relaxed_u32(a.flags + blockIdx.x * kFlagStride, unsigned(s + 1));
     }
+    TB_TRACE(7);
     // ---- everything below is consumed by this CTA or after the kernel: off the critical path ----
     if (actrole) {
       if (act0) {
@@ -1909,6 +1923,7 @@ struct WaveBwdSplitArgs {
   float* dxm;
   unsigned* flags;                  // [2 * nc]
   int T1, B, H, Hq; unsigned nc;
+  long long* trace;
 };
 
 __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(WaveBwdSplitArgs a) {
@@ -1941,6 +1956,10 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
   __nv_bfloat16* const dgq = upper ? a.dgq_up : a.dgq_lo;
   // B fragments: B[kk][n] = W[g*H + j][k0 + n] for kk = (gate g, j)
   uint32_t bh[4][kSplitK][2], bl[4][kSplitK][2], ih[4][kSplitK][2], il[4][kSplitK][2];
+  // The pointwise operands of the NEXT step (forward saves: 4 gates, c, masked c_prev, dy, 2 done masks) are prefetched
+  // into SHARED memory with 4-byte cp.async while this step's hand-off and products run: held in registers they spilled
+  // to local memory (168-register cap with the 96 fragment registers) and their load latency landed on the critical path.
+  float* const pre_s = reinterpret_cast<float*>(smem_b + size_t(kSplitWarps) * 4 * kPlaneE * 2 + sizeof(float) * kSplitWarps * 2 * kBwdCols * 33);  // [9][256]
   {
     const int n = lane >> 2;
 #pragma unroll
@@ -1969,15 +1988,20 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
   const int q = wrp;  // pointwise role: thread = (batch row lane, unit k0 + wrp), warps 0..7
   const bool actA = (wrp < kBwdCols && lane < rows && k0 + q < H);
   auto time_of = [&](int s) { return upper ? a.T1 - 1 - s : a.T1 + 1 - s; };
-  float n_ig = 0.f, n_fg = 0.f, n_gg = 0.f, n_og = 0.f, n_dy = 0.f, n_cs = 0.f, n_cm = 0.f, n_nd = 0.f, n_ndn = 0.f;
-  auto prefetch = [&](int t) {
-    if (!actA || t < 0 || t >= a.T1) return;
-    const int64_t r0 = int64_t(t) * B;
-    const int64_t i = (r0 + lane) * H + k0 + q, g = (r0 + lane) * 4 * H + k0 + q;
-    n_ig = gates[g]; n_fg = gates[g + H]; n_gg = gates[g + 2 * H]; n_og = gates[g + 3 * H];
-    if (upper) n_dy = a.dy[i];  // the lower role's dy comes from the upper role: fetched AFTER the wait (fetch_dxm)
-    n_cs = cs[i]; n_cm = cm[i]; n_nd = a.nd[r0 + lane];
-    n_ndn = (t + 1 < a.T1) ? a.nd[r0 + B + lane] : 0.f;
+  float n_dy = 0.f;
+  auto cp4 = [&](int slot, const float* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(pre_s + slot * 256 + tid)), "l"(src) : "memory");
+  };
+  auto prefetch = [&](int t) {   // (commits one cp.async group; every thread commits, only the pointwise threads copy)
+    if (actA && t >= 0 && t < a.T1) {
+      const int64_t r0 = int64_t(t) * B;
+      const int64_t i = (r0 + lane) * H + k0 + q, g = (r0 + lane) * 4 * H + k0 + q;
+      cp4(0, gates + g); cp4(1, gates + g + H); cp4(2, gates + g + 2 * H); cp4(3, gates + g + 3 * H);
+      if (upper) cp4(4, a.dy + i);  // the lower role's dy comes from the upper role: fetched AFTER the wait (fetch_dxm)
+      cp4(5, cs + i); cp4(6, cm + i); cp4(7, a.nd + r0 + lane);
+      if (t + 1 < a.T1) cp4(8, a.nd + r0 + B + lane);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
   auto fetch_dxm = [&](int t) {
     if (upper || !actA || t < 0 || t >= a.T1) return;
@@ -2005,10 +2029,14 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
     const int64_t row0 = int64_t(active ? t : 0) * B;
     __nv_bfloat16* dgq_t = dgq + int64_t(it & 1) * 4 * gs;
     float p_i = 0.f, p_f = 0.f, p_g = 0.f, p_o = 0.f;
+    TB_TRACE(0);
     if (active) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's prefetched operands (the tile groups are long done)
       if (actA) {
-        const float ig = n_ig, fg = n_fg, gg = n_gg, og = n_og;
-        float dh = n_dy;
+        const float ig = pre_s[0 * 256 + tid], fg = pre_s[1 * 256 + tid], gg = pre_s[2 * 256 + tid], og = pre_s[3 * 256 + tid];
+        const float n_cs = pre_s[5 * 256 + tid], n_cm = pre_s[6 * 256 + tid], n_nd = pre_s[7 * 256 + tid];
+        const float n_ndn = (t + 1 < a.T1) ? pre_s[8 * 256 + tid] : 0.f;
+        float dh = upper ? pre_s[4 * 256 + tid] : n_dy;
         float dc = 0.0f;
         if (it > 0) {
           dh += dh_s[q][lane] * n_ndn;
@@ -2045,10 +2073,12 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
       break;
     }
     __syncthreads();
+    TB_TRACE(1);
     if (tid == 0) {  // this CTA's tile columns of wave step s (and, upper role, its dxm of step s-1) are out
       asm volatile("fence.acq_rel.gpu;" ::: "memory");
       st_relaxed_u32(my_flag, unsigned(s + 1));
     }
+    TB_TRACE(2);
     if (active && actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
     prefetch(time_of(s + 1));  // forward-pass operands only: overlaps the wait
     // hand-off: this warp needs the tile columns of units [16*ks0, 16*ks0 + 48) -> the 6 CTAs of its own role that own
@@ -2065,6 +2095,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
       }
       __syncwarp();
     }
+    TB_TRACE(3);
     fetch_dxm(time_of(s + 1));  // written by the upper role before it published wave step s
     const bool need_rec = active && t > 0;
     const bool need_dx = active && upper;
@@ -2112,7 +2143,9 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
         }
         __syncwarp();
         if (g + 2 < 4) issue(g + 2);
+        if (g == 0) TB_TRACE(4);
       }
+      TB_TRACE(5);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const int r = mt * 16 + (lane >> 2), c = (lane & 3) * 2;
@@ -2137,6 +2170,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
         }
       }
       __syncthreads();
+      TB_TRACE(6);
     }
     if (active) ++it;
   }
@@ -2226,6 +2260,33 @@ static int lstm2_fwd_wave(LstmWs& ws, const LstmParams& p, float* y, const float
   return check_launch("lstm2_fwd_wave_mma_kernel");
 }
 
+static long long* trace_buffer(unsigned ctas, int T1) {
+  static const char* path = getenv("TB_LSTM_TRACE");
+  if (!path) return nullptr;
+  long long* p = nullptr;
+  const size_t n = size_t(ctas) * (T1 + 2) * kTracePhases;
+  if (cudaMalloc(&p, n * sizeof(long long)) != cudaSuccess) return nullptr;
+  cudaMemset(p, 0, n * sizeof(long long));
+  return p;
+}
+static void trace_dump(const char* tag, long long* dev, unsigned ctas, int T1, cudaStream_t st) {
+  if (!dev) return;
+  const size_t n = size_t(ctas) * (T1 + 2) * kTracePhases;
+  long long* h = static_cast<long long*>(malloc(n * sizeof(long long)));
+  cudaStreamSynchronize(st);
+  cudaMemcpy(h, dev, n * sizeof(long long), cudaMemcpyDeviceToHost);
+  char name[512];
+  snprintf(name, sizeof(name), "%s.%s", getenv("TB_LSTM_TRACE"), tag);
+  if (FILE* f = fopen(name, "wb")) {
+    const int hdr[4] = {int(ctas), T1 + 2, kTracePhases, 0};
+    fwrite(hdr, sizeof(hdr), 1, f);
+    fwrite(h, sizeof(long long), n, f);
+    fclose(f);
+  }
+  free(h);
+  cudaFree(dev);
+}
+
 // slot 0 of the split recurrence's planes: hq = split(h0) (raw), hmq = split(h0 * nd_0); row padding zero
 __global__ void lstm_init_state_split_kernel(const float* __restrict__ h0, const float* __restrict__ nd,
                                              __nv_bfloat16* __restrict__ hq, int64_t hq_lo, __nv_bfloat16* __restrict__ hmq,
@@ -2287,10 +2348,12 @@ static int lstm2_fwd_wave_split(LstmWs& ws, const LstmParams& p, float* y, const
   TB_REQUIRE(ws.layer[1].hq_lo == a.hq_lo && ws.layer[1].hmq_lo == a.hmq_lo && a.hq_lo > 0, "lstm: split planes missing");
   a.nd = notdone; a.flags = ws.flags;
   a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nctas = grid.x;
+  a.trace = trace_buffer(grid.x, int(T1));
   void* args[] = {&a};
   e = cudaLaunchCooperativeKernel((const void*)lstm2_fwd_wave_split_kernel, grid, dim3(kSplitThreads), args,
                                   wave_fwd_split_smem(Hq), st);
   TB_REQUIRE(e == cudaSuccess, "lstm2_fwd_wave_split_kernel: %s", cudaGetErrorString(e));
+  trace_dump("fwd", a.trace, grid.x, int(T1), st);
   return check_launch("lstm2_fwd_wave_split_kernel");
 }
 
@@ -2359,7 +2422,8 @@ static int lstm2_bwd_wave(LstmWs& ws, const LstmParams& p, const LstmGrads& g, c
 
 static size_t g_bwd_split_attr = 0;
 static size_t wave_bwd_split_smem(int) {
-  return size_t(kSplitWarps) * 4 * 32 * (kSplitK * 16 + 8) * 2 + sizeof(float) * kSplitWarps * 2 * kBwdCols * 33;
+  return size_t(kSplitWarps) * 4 * 32 * (kSplitK * 16 + 8) * 2 + sizeof(float) * kSplitWarps * 2 * kBwdCols * 33 +
+         sizeof(float) * 9 * 256;   // tile rings + partial sums + prefetched pointwise operands
 }
 static bool wave_bwd_split_applicable(int64_t B, int In, int H) {
   const char* e = getenv("TB_LSTM_SPLIT_BWD");
@@ -2409,10 +2473,12 @@ static int lstm2_bwd_wave_split(LstmWs& ws, const LstmParams& p, const LstmGrads
   a.dgq_up = static_cast<__nv_bfloat16*>(U.dgq); a.dgq_lo = static_cast<__nv_bfloat16*>(L.dgq); a.dgq_lo_off = U.dgq_lo;
   a.dxm = ws.dx_mid; a.flags = flags;
   a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nc = nc;
+  a.trace = trace_buffer(2 * nc, int(T1));
   void* args[] = {&a};
   e = cudaLaunchCooperativeKernel((const void*)lstm2_bwd_wave_split_kernel, dim3(2 * nc), dim3(kSplitThreads), args,
                                   wave_bwd_split_smem(Hq), st);
   TB_REQUIRE(e == cudaSuccess, "lstm2_bwd_wave_split_kernel: %s", cudaGetErrorString(e));
+  trace_dump("bwd", a.trace, 2 * nc, int(T1), st);
   return check_launch("lstm2_bwd_wave_split_kernel");
 }
 
