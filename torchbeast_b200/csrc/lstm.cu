@@ -53,6 +53,7 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
       L.wp = takef(int64_t(4 * H + 4) * Hp);
       L.xb = L.wihb = L.dgb = L.hmb = L.hmq = L.dgq = L.hq = nullptr;
       L.xb_lo = L.wihb_lo = L.dgb_lo = L.hmb_lo = L.hq_lo = L.hmq_lo = L.dgq_lo = 0;
+      L.gact = L.csb = nullptr;
       if (precision) {  // bf16 operand copies (2 bytes per element: take half the float count, rounded up)
         const int64_t in_l = (l == 0) ? In : H;
         // precision 2 (split-bf16): every GEMM operand also has a lo plane right behind its hi plane
@@ -66,6 +67,10 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
         L.dgb = takeh(N * ld16(4 * H), &L.dgb_lo); L.hmb = takeh(N * ld16(H), &L.hmb_lo);
         L.hmq = takeh(N * mma_hq(H), &L.hmq_lo); L.hq = takeh((N + B) * mma_hq(H), &L.hq_lo);
         L.dgq = takeh(int64_t(2) * 4 * B * mma_hq(H), &L.dgq_lo);
+        if (precision == 2) {
+          const int64_t nC4 = (H + 3) / 4;
+          L.gact = takef(T1 * nC4 * 512); L.csb = takef((T1 + 1) * nC4 * 128);
+        }
       }
     } else {
       L = LstmLayerWs();
@@ -76,6 +81,7 @@ LstmWs lstm_ws(void* base, int64_t T1, int64_t B, int In, int H, int layers, int
   w.wg_scratch = (precision && layers == 2) ? takef(int64_t(4) * 4 * H * (((H > In ? H : In) + 31) & ~31)) : nullptr;
   w.dgp = takef(int64_t(2) * 4 * B * padded_h(H));
   w.sync = reinterpret_cast<unsigned*>(takef(64));
+  w.dxb = (precision == 2 && layers == 2) ? takef(T1 * int64_t((H + 7) / 8) * 256) : nullptr;
   w.flags = reinterpret_cast<unsigned*>(takef(2 * 512 * 32));  // 2 x 512 flags, 128 bytes apart (kFlagStride)
   w.Hp = padded_h(H);
   w.bytes = off;
@@ -1600,7 +1606,14 @@ constexpr int kTracePhases = 8;
 struct WaveFwdSplitArgs {
   const float* w_hh0; const float* w_ih1; const float* w_hh1; const float* bias1;
   const float* c0;          // [2, B, H] initial cell state
-  float* gates[2]; float* hs[2]; float* cs[2]; float* cm[2];
+  const float* xproj;       // layer 0: hoisted input projection + biases [T1*B, 4H]
+  // What only the LSTM kernels themselves consume is kept in CTA-BLOCKED layouts so that every access is a coalesced
+  // run (a [T1*B, 4H] / [T1*B, H] layout makes each warp store touch 32 cache lines - the LSU time of those scattered
+  // 4-byte stores sat in front of the next step's tile fetch: ncu / clock64 trace r2):
+  float* gact[2];           // activated gates [T1][nctas][32 rows][16 = gate*4 + unit]
+  float* csb[2];            // cell state [T1+1][nctas][32 rows][4 units]: slot 0 = c0, slot t+1 = c_t
+  float* y;                 // layer-1 output [T1*B, H] (the heads' input)
+  float* hN; float* cN;     // [2, B, H] final state
   __nv_bfloat16* hq[2];     // raw h planes [(T1+1)*B, Hq] (+ hq_lo): slot 0 = initial state, slot t+1 = h_t
   __nv_bfloat16* hmq[2];    // masked recurrent inputs [T1*B, Hq] (+ hmq_lo): operand of the weight-gradient GEMMs
   int64_t hq_lo, hmq_lo;
@@ -1676,20 +1689,19 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
   const bool updthread = tid < 256;
   const int ul = tid >> 7, ur = (tid & 127) >> 2, uu = tid & 3;
   const bool updrole = updthread && ur < rows && j0 + uu < H;
-  float* const cm_u = ul ? a.cm[1] : a.cm[0];
-  float* const cs_u = ul ? a.cs[1] : a.cs[0];
-  float* const hs_u = ul ? a.hs[1] : a.hs[0];
+  float* const csb_u = ul ? a.csb[1] : a.csb[0];
   __nv_bfloat16* const hq_u = ul ? a.hq[1] : a.hq[0];
   __nv_bfloat16* const hmq_u = ul ? a.hmq[1] : a.hmq[0];
   float c_state = updrole ? a.c0[(int64_t(ul) * B + ur) * H + j0 + uu] : 0.f;  // c_{t-1} of this (layer, row, unit)
+  if (updthread) csb_u[int64_t(blockIdx.x) * 128 + (tid & 127)] = c_state;    // slot 0
   for (int s = 0; s <= a.T1; ++s) {
     const bool act0 = (s < a.T1), act1 = (s >= 1);
     TB_TRACE(0);
     // inputs that do not depend on other CTAs: issued before the wait
     float preA = 0.f, preB = 0.f;
     if (act0) {
-      if (okA) preA = a.gates[0][(int64_t(s) * B + lane) * 4 * H + gA];
-      if (okB) preB = a.gates[0][(int64_t(s) * B + lane) * 4 * H + gB];
+      if (okA) preA = __ldg(a.xproj + (int64_t(s) * B + lane) * 4 * H + gA);
+      if (okB) preB = __ldg(a.xproj + (int64_t(s) * B + lane) * 4 * H + gB);
     }
     const int tu = s - ul;                                 // time step of this thread's update role
     const bool upd = updrole && (ul ? act1 : act0);
@@ -1867,15 +1879,12 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
     }
     TB_TRACE(7);
     // ---- everything below is consumed by this CTA or after the kernel: off the critical path ----
-    if (actrole) {
-      if (act0) {
-        if (okA) a.gates[0][(int64_t(s) * B + lane) * 4 * H + gA] = g0A;
-        if (okB) a.gates[0][(int64_t(s) * B + lane) * 4 * H + gB] = g0B;
-      }
-      if (act1) {
-        if (okA) a.gates[1][(int64_t(s - 1) * B + lane) * 4 * H + gA] = g1A;
-        if (okB) a.gates[1][(int64_t(s - 1) * B + lane) * 4 * H + gB] = g1B;
-      }
+    // activated gates -> CTA-blocked [row][16] tiles, straight from act_s (rewritten only after the next step's barrier)
+    for (int idx = tid; idx < 1024; idx += kSplitThreads) {
+      const int l = idx >> 9, e = idx & 511, row = e >> 4, c = e & 15;
+      const int tl = s - l;
+      if ((l ? act1 : act0) && row < rows)
+        a.gact[l][(int64_t(tl) * a.nctas + blockIdx.x) * 512 + e] = act_s[l][c >> 2][c & 3][row];
     }
     if (updthread) {
       // masked recurrent input of the NEXT step (h_t * notdone_{t+1}) for the weight-gradient GEMMs, as hi / lo planes
@@ -1891,16 +1900,19 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
         *reinterpret_cast<uint2*>(d) = make_uint2(ph, ph2);
         *reinterpret_cast<uint2*>(d + a.hmq_lo) = make_uint2(pl, pl2);
       }
+      if ((ul ? act1 : act0) && ur < rows)   // c_t, blocked (units past H hold 0)
+        csb_u[(int64_t(tu + 1) * a.nctas + blockIdx.x) * 128 + (tid & 127)] = c_new;
       if (upd) {
         const int64_t o = (int64_t(tu) * B + ur) * H + j0 + uu;
-        cs_u[o] = c_new;
-        hs_u[o] = h_new;
-        cm_u[o] = cm_in;
+        if (ul) a.y[o] = h_new;
+        if (tu == a.T1 - 1) {
+          a.hN[(int64_t(ul) * B + ur) * H + j0 + uu] = h_new;
+          a.cN[(int64_t(ul) * B + ur) * H + j0 + uu] = c_new;
+        }
       }
     }
   }
 }
-
 
 // ---- split-precision backward wavefront (precision 2) ----------------------------------------------
 // lstm2_bwd_wave_mma_kernel's role split (CTAs [0, nc): upper layer recurrence + dL/dh_lower from the same tile;
@@ -1915,12 +1927,13 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_fwd_wave_split_kernel(
 struct WaveBwdSplitArgs {
   const float* w_hh_up; const float* w_hh_lo; const float* w_ih_up;
   const float* dy; const float* nd;
-  const float* gates_up; const float* cs_up; const float* cm_up;
-  const float* gates_lo; const float* cs_lo; const float* cm_lo;
+  const float* gact_up; const float* csb_up;   // CTA-blocked forward saves (see WaveFwdSplitArgs); nfwd = forward CTAs
+  const float* gact_lo; const float* csb_lo;
+  int nfwd;
   __nv_bfloat16* dgb_up; __nv_bfloat16* dgb_lo; int lg; int64_t dgb_lo_off;   // gate gradients of all steps, hi plane (+ lo offset)
   float* db_up; float* db_lo;
   __nv_bfloat16* dgq_up; __nv_bfloat16* dgq_lo; int64_t dgq_lo_off;          // exchange planes: [2][4, B, Hq] (+ lo offset)
-  float* dxm;
+  float* dxb;                       // dL/dh_lower, blocked [T1][nc][32 rows][8 cols]: upper role -> lower role
   unsigned* flags;                  // [2 * nc]
   int T1, B, H, Hq; unsigned nc;
   long long* trace;
@@ -1949,9 +1962,8 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
   const int kpg = (H + 15) / 16;           // k16 steps per gate (<= 33)
   const int ks0 = wrp * kSplitK;           // this warp's k-steps inside every gate
   const float* const w_hh = upper ? a.w_hh_up : a.w_hh_lo;
-  const float* const gates = upper ? a.gates_up : a.gates_lo;
-  const float* const cs = upper ? a.cs_up : a.cs_lo;
-  const float* const cm = upper ? a.cm_up : a.cm_lo;
+  const float* const gact = upper ? a.gact_up : a.gact_lo;
+  const float* const csb = upper ? a.csb_up : a.csb_lo;
   __nv_bfloat16* const dgb = upper ? a.dgb_up : a.dgb_lo;
   __nv_bfloat16* const dgq = upper ? a.dgq_up : a.dgq_lo;
   // B fragments: B[kk][n] = W[g*H + j][k0 + n] for kk = (gate g, j)
@@ -1959,7 +1971,9 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
   // The pointwise operands of the NEXT step (forward saves: 4 gates, c, masked c_prev, dy, 2 done masks) are prefetched
   // into SHARED memory with 4-byte cp.async while this step's hand-off and products run: held in registers they spilled
   // to local memory (168-register cap with the 96 fragment registers) and their load latency landed on the critical path.
-  float* const pre_s = reinterpret_cast<float*>(smem_b + size_t(kSplitWarps) * 4 * kPlaneE * 2 + sizeof(float) * kSplitWarps * 2 * kBwdCols * 33);  // [9][256]
+  // layout: [0,1024) activated gates of the two forward CTAs whose units this CTA owns ([2][32 rows][16]); [1024,1280) c_t
+  // ([2][32][4]); [1280,1536) c_{t-1}; [1536,1792) dy ([32 rows][8 cols], upper role); [1792,1856) notdone_t, notdone_{t+1}
+  float* const pre_s = reinterpret_cast<float*>(smem_b + size_t(kSplitWarps) * 4 * kPlaneE * 2 + sizeof(float) * kSplitWarps * 2 * kBwdCols * 33);
   {
     const int n = lane >> 2;
 #pragma unroll
@@ -1989,36 +2003,52 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
   const bool actA = (wrp < kBwdCols && lane < rows && k0 + q < H);
   auto time_of = [&](int s) { return upper ? a.T1 - 1 - s : a.T1 + 1 - s; };
   float n_dy = 0.f;
-  auto cp4 = [&](int slot, const float* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(pre_s + slot * 256 + tid)), "l"(src) : "memory");
-  };
-  auto prefetch = [&](int t) {   // (commits one cp.async group; every thread commits, only the pointwise threads copy)
-    if (actA && t >= 0 && t < a.T1) {
-      const int64_t r0 = int64_t(t) * B;
-      const int64_t i = (r0 + lane) * H + k0 + q, g = (r0 + lane) * 4 * H + k0 + q;
-      cp4(0, gates + g); cp4(1, gates + g + H); cp4(2, gates + g + 2 * H); cp4(3, gates + g + 3 * H);
-      if (upper) cp4(4, a.dy + i);  // the lower role's dy comes from the upper role: fetched AFTER the wait (fetch_dxm)
-      cp4(5, cs + i); cp4(6, cm + i); cp4(7, a.nd + r0 + lane);
-      if (t + 1 < a.T1) cp4(8, a.nd + r0 + B + lane);
+  auto prefetch = [&](int t) {   // every thread commits one group; all copies are coalesced runs
+    if (t >= 0 && t < a.T1) {
+      for (int idx = tid; idx < 384; idx += kSplitThreads) {
+        const float* src; float* dst;
+        if (idx < 256) {          // activated gates: 2 forward-CTA blocks x 128 chunks
+          const int blk = idx >> 7, fc = 2 * cidx + blk;
+          src = gact + (int64_t(t) * a.nfwd + fc) * 512 + (idx & 127) * 4; dst = pre_s + idx * 4;
+          if (fc >= a.nfwd) src = nullptr;
+        } else {                  // c_t (slot t+1) and c_{t-1} (slot t): 2 blocks x 32 chunks each
+          const int j = idx - 256, prev = j >> 6, blk = (j >> 5) & 1, fc = 2 * cidx + blk;
+          src = csb + (int64_t(t + 1 - prev) * a.nfwd + fc) * 128 + (j & 31) * 4; dst = pre_s + 1024 + j * 4;
+          if (fc >= a.nfwd) src = nullptr;
+        }
+        if (src) cp_async16(dst, src);
+      }
+      if (upper && tid < 256) {   // dy rows of this CTA's 8 columns
+        const int r = tid >> 3, c = tid & 7;
+        if (r < rows && k0 + c < H)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(pre_s + 1536 + tid)),
+                       "l"(a.dy + (int64_t(t) * B + r) * H + k0 + c) : "memory");
+      }
+      if (tid < 64) {
+        const int r = tid & 31, tt = t + (tid >> 5);
+        if (r < rows && tt < a.T1)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(pre_s + 1792 + tid)), "l"(a.nd + int64_t(tt) * B + r) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   auto fetch_dxm = [&](int t) {
     if (upper || !actA || t < 0 || t >= a.T1) return;
-    n_dy = __ldcg(a.dxm + (int64_t(t) * B + lane) * H + k0 + q);
+    n_dy = __ldcg(a.dxb + (int64_t(t) * a.nc + cidx) * 256 + lane * 8 + q);
   };
-  if (upper) prefetch(a.T1 - 1);
-  float bs_i = 0.f, bs_f = 0.f, bs_g = 0.f, bs_o = 0.f;
-  auto store_dg = [&](int64_t row, float p_i, float p_f, float p_g, float p_o) {
-    __nv_bfloat16* d = dgb + row * a.lg + k0 + q;
-    const float p[4] = {p_i, p_f, p_g, p_o};
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const __nv_bfloat16 h = __float2bfloat16_rn(p[g]);
-      d[g * H] = h;
-      d[a.dgb_lo_off + g * H] = __float2bfloat16_rn(p[g] - __bfloat162float(h));
+  // gate-gradient rows of all steps for the hoisted weight-gradient GEMMs ([N, lg] hi / lo planes): written from the staging
+  // tile with 8 lanes per 16-byte run (4 cache lines per warp store; one 2-byte store per lane-row touched 32)
+  auto store_dg = [&](int64_t row0s) {
+    for (int idx = tid; idx < 2048; idx += kSplitThreads) {
+      const int pl = idx >> 10, g = (idx >> 8) & 3, r = (idx >> 3) & 31, e = idx & 7;
+      if (r < rows && k0 + e < H)
+        dgb[(pl ? a.dgb_lo_off : 0) + (row0s + r) * a.lg + int64_t(g) * H + k0 + e] = stg_s[pl][g][r][e];
     }
   };
+  if (upper) prefetch(a.T1 - 1); else asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  float bs_i = 0.f, bs_f = 0.f, bs_g = 0.f, bs_o = 0.f;
   const int last_s = a.T1 + 1;
   unsigned* const my_flag = a.flags + blockIdx.x * kFlagStride;
   const unsigned* const role_flags = a.flags + (upper ? 0 : a.nc) * kFlagStride;
@@ -2031,12 +2061,13 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
     float p_i = 0.f, p_f = 0.f, p_g = 0.f, p_o = 0.f;
     TB_TRACE(0);
     if (active) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");  // this thread's prefetched operands (the tile groups are long done)
-      if (actA) {
-        const float ig = pre_s[0 * 256 + tid], fg = pre_s[1 * 256 + tid], gg = pre_s[2 * 256 + tid], og = pre_s[3 * 256 + tid];
-        const float n_cs = pre_s[5 * 256 + tid], n_cm = pre_s[6 * 256 + tid], n_nd = pre_s[7 * 256 + tid];
-        const float n_ndn = (t + 1 < a.T1) ? pre_s[8 * 256 + tid] : 0.f;
-        float dh = upper ? pre_s[4 * 256 + tid] : n_dy;
+      if (actA) {   // (the prefetched operands were waited for, and made visible by the barrier, at the end of the previous step)
+        const int gb = (q >> 2) * 512 + lane * 16 + (q & 3), cb = (q >> 2) * 128 + lane * 4 + (q & 3);
+        const float ig = pre_s[gb], fg = pre_s[gb + 4], gg = pre_s[gb + 8], og = pre_s[gb + 12];
+        const float n_nd = pre_s[1792 + lane];
+        const float n_cs = pre_s[1024 + cb], n_cm = pre_s[1280 + cb] * n_nd;   // c_{t-1} * notdone_t
+        const float n_ndn = (t + 1 < a.T1) ? pre_s[1824 + lane] : 0.f;
+        float dh = upper ? pre_s[1536 + lane * 8 + q] : n_dy;
         float dc = 0.0f;
         if (it > 0) {
           dh += dh_s[q][lane] * n_ndn;
@@ -2069,7 +2100,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
       }
     }
     if (s == last_s) {
-      if (active && actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
+      if (active) { __syncthreads(); store_dg(row0); }
       break;
     }
     __syncthreads();
@@ -2079,7 +2110,7 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
       st_relaxed_u32(my_flag, unsigned(s + 1));
     }
     TB_TRACE(2);
-    if (active && actA) store_dg(row0 + lane, p_i, p_f, p_g, p_o);
+    if (active) store_dg(row0);
     prefetch(time_of(s + 1));  // forward-pass operands only: overlaps the wait
     // hand-off: this warp needs the tile columns of units [16*ks0, 16*ks0 + 48) -> the 6 CTAs of its own role that own
     // them; the pointwise threads of the lower role additionally need the upper CTA with the same 8 columns (its dxm)
@@ -2166,12 +2197,13 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
           float d = 0.f;
 #pragma unroll
           for (int w = 0; w < kSplitWarps; ++w) d += part[w][1][wrp][lane];
-          if (lane < rows && k0 + wrp < H) a.dxm[(row0 + lane) * H + k0 + wrp] = d;
+          if (lane < rows) a.dxb[(int64_t(t) * a.nc + cidx) * 256 + lane * 8 + wrp] = d;
         }
       }
-      __syncthreads();
-      TB_TRACE(6);
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");   // next step's prefetched pointwise operands (all threads' copies)
+    __syncthreads();
+    TB_TRACE(6);
     if (active) ++it;
   }
   if (wrp < kBwdCols) {
@@ -2331,17 +2363,19 @@ static bool wave_fwd_split_applicable(int64_t B, int In, int H) {
   return int64_t(per_sm) * sms >= int64_t(grid.x);
 }
 
-static int lstm2_fwd_wave_split(LstmWs& ws, const LstmParams& p, float* y, const float* notdone, const float* c0, int64_t T1,
-                                int64_t B, int H, cudaStream_t st) {
+static int lstm2_fwd_wave_split(LstmWs& ws, const LstmParams& p, float* y, const float* notdone, const float* c0, float* hN,
+                                float* cN, int64_t T1, int64_t B, int H, cudaStream_t st) {
   const int Hq = mma_hq(H);
   dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
   cudaError_t e = cudaMemsetAsync(ws.flags, 0, sizeof(unsigned) * 512 * kFlagStride, st);
   TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
   WaveFwdSplitArgs a;
   a.w_hh0 = p.w_hh[0]; a.w_ih1 = p.w_ih[1]; a.w_hh1 = p.w_hh[1]; a.bias1 = ws.layer[1].bsum; a.c0 = c0;
+  a.xproj = ws.layer[0].gates; a.y = y; a.hN = hN; a.cN = cN;
   for (int l = 0; l < 2; ++l) {
     const LstmLayerWs& L = ws.layer[l];
-    a.gates[l] = L.gates; a.hs[l] = (l == 1) ? y : L.hs; a.cs[l] = L.cs; a.cm[l] = L.cm;
+    a.gact[l] = L.gact; a.csb[l] = L.csb;
+    TB_REQUIRE(L.gact && L.csb, "lstm: blocked save buffers missing");
     a.hq[l] = static_cast<__nv_bfloat16*>(L.hq); a.hmq[l] = static_cast<__nv_bfloat16*>(L.hmq);
   }
   a.hq_lo = ws.layer[0].hq_lo; a.hmq_lo = ws.layer[0].hmq_lo;
@@ -2426,8 +2460,6 @@ static size_t wave_bwd_split_smem(int) {
          sizeof(float) * 9 * 256;   // tile rings + partial sums + prefetched pointwise operands
 }
 static bool wave_bwd_split_applicable(int64_t B, int In, int H) {
-  const char* e = getenv("TB_LSTM_SPLIT_BWD");
-  if (e && e[0] == '0') return false;
   if (!wave_fwd_split_applicable(B, In, H)) return false;  // consumes the planes the split forward leaves behind
   dim3 grid(2 * ((H + kBwdCols - 1) / kBwdCols), 1);
   if (int(grid.x / 2) + 1 > kSplitThreads || grid.x > 512) return false;
@@ -2465,13 +2497,13 @@ static int lstm2_bwd_wave_split(LstmWs& ws, const LstmParams& p, const LstmGrads
   WaveBwdSplitArgs a;
   a.w_hh_up = p.w_hh[1]; a.w_hh_lo = p.w_hh[0]; a.w_ih_up = p.w_ih[1];
   a.dy = dy; a.nd = notdone;
-  a.gates_up = U.gates; a.cs_up = U.cs; a.cm_up = U.cm;
-  a.gates_lo = L.gates; a.cs_lo = L.cs; a.cm_lo = L.cm;
+  a.gact_up = U.gact; a.csb_up = U.csb; a.gact_lo = L.gact; a.csb_lo = L.csb; a.nfwd = (H + kStepUnits - 1) / kStepUnits;
+  TB_REQUIRE(U.gact && U.csb && L.gact && L.csb && ws.dxb, "lstm: blocked save buffers missing");
   a.dgb_up = static_cast<__nv_bfloat16*>(U.dgb); a.dgb_lo = static_cast<__nv_bfloat16*>(L.dgb); a.lg = int(ld16(4 * H));
   a.dgb_lo_off = U.dgb_lo;
   a.db_up = g.b_ih[1]; a.db_lo = g.b_ih[0];
   a.dgq_up = static_cast<__nv_bfloat16*>(U.dgq); a.dgq_lo = static_cast<__nv_bfloat16*>(L.dgq); a.dgq_lo_off = U.dgq_lo;
-  a.dxm = ws.dx_mid; a.flags = flags;
+  a.dxb = ws.dxb; a.flags = flags;
   a.T1 = int(T1); a.B = int(B); a.H = H; a.Hq = Hq; a.nc = nc;
   a.trace = trace_buffer(2 * nc, int(T1));
   void* args[] = {&a};
@@ -2559,7 +2591,8 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
     }
     return 0;
   }
-  if (precision == 2 && layers == 2 && wave_fwd_split_applicable(B, In, H)) {
+  // (forward and backward are decided together: the split backward consumes the blocked saves only the split forward writes)
+  if (precision == 2 && layers == 2 && wave_bwd_split_applicable(B, In, H)) {
     // split-bf16 wavefront: layer 0's input projection is one split tcgen05 GEMM, everything sequential is ONE kernel
     const int Hq = mma_hq(H);
     for (int l = 0; l < 2; ++l) {
@@ -2586,16 +2619,7 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
     }
     {
       ProfScope prof("lstm_recurrence_fwd", st);
-      TB_TRY(lstm2_fwd_wave_split(ws, p, y, notdone, c0, T1, B, H, st));
-    }
-    for (int l = 0; l < 2; ++l) {
-      const float* hs = (l == 1) ? y : ws.layer[0].hs;
-      cudaError_t e = cudaMemcpyAsync(hN + int64_t(l) * B * H, hs + (T1 - 1) * B * H, sizeof(float) * B * H,
-                                      cudaMemcpyDeviceToDevice, st);
-      if (e == cudaSuccess)
-        e = cudaMemcpyAsync(cN + int64_t(l) * B * H, ws.layer[l].cs + (T1 - 1) * B * H, sizeof(float) * B * H,
-                            cudaMemcpyDeviceToDevice, st);
-      TB_REQUIRE(e == cudaSuccess, "lstm: state copy: %s", cudaGetErrorString(e));
+      TB_TRY(lstm2_fwd_wave_split(ws, p, y, notdone, c0, hN, cN, T1, B, H, st));  // writes hN / cN itself
     }
     return 0;
   }
@@ -2702,13 +2726,13 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
   // two layers on the tensor-core backend: ONE wavefront kernel runs both recurrences (and the upper layer's
   // input-gradient product); only the hoisted weight-gradient GEMMs and the lower layer's dx remain per layer
   bool wave_done = false;
-  const bool split_fwd = precision == 2 && layers == 2 && wave_fwd_split_applicable(B, In, H);  // same predicate as the forward
+  const bool split_fwd = precision == 2 && layers == 2 && wave_bwd_split_applicable(B, In, H);  // same predicate as the forward
   bool split_bwd = false;  // the split wavefront kernel ran: gate gradients are already bf16 hi/lo planes, bias gradients summed
   if (precision == 1 && layers == 2 && In <= H && wave_bwd_applicable(B, H)) {
     ProfScope prof("lstm_recurrence_bwd", st);
     TB_TRY(lstm2_bwd_wave(ws, p, g, dy, notdone, T1, B, H, st));
     wave_done = true;
-  } else if (split_fwd && wave_bwd_split_applicable(B, In, H)) {
+  } else if (split_fwd) {
     // (the 4 padding columns of the [N, ld16(4H)] gate-gradient planes are never read as data: the GEMMs' tensor maps
     //  end at column 4H)
     ProfScope prof("lstm_recurrence_bwd", st);

@@ -28,6 +28,8 @@ struct LstmLayerWs {
   void* hmb;      // bf16 [T1*B, ld16(H)]    masked recurrent inputs
   int64_t xb_lo = 0, wihb_lo = 0, dgb_lo = 0, hmb_lo = 0;  // precision 2 (split-bf16): element offsets of the lo planes
   int64_t hq_lo = 0, hmq_lo = 0, dgq_lo = 0;               // same for the recurrence kernels' exchange / masked-h planes
+  float* gact = nullptr;  // (precision 2) activated gates, CTA-blocked [T1][ceil(H/4)][32][16] - see lstm2_fwd_wave_split_kernel
+  float* csb = nullptr;   // (precision 2) cell state, CTA-blocked [T1+1][ceil(H/4)][32][4]: slot 0 = c0, slot t+1 = c_t
   void* hmq;      // bf16 [T1*B, Hq]         masked recurrent inputs written by the tensor-core recurrence (Hq = mma_hq(H))
   void* hq;       // bf16 [(T1+1)*B, Hq]     raw h (slot 0 = initial state) exchanged by the two-layer wavefront kernel
   void* dgq;      // bf16 [2][4, B, Hq]      this step's gate gradients for the tensor-core backward recurrence
@@ -43,6 +45,7 @@ struct LstmWs {
   float* dc;      // [B, H] carry
   float* dx_mid;  // [T1*B, H] gradient w.r.t. the output of layer 0 (input of layer 1)
   unsigned* sync; // [64] grid-barrier counters of the persistent recurrence kernels (zeroed per launch)
+  float* dxb = nullptr;  // (precision 2) dL/dh_lower handed from the upper to the lower role, blocked [T1][ceil(H/8)][32][8]
   unsigned* flags; // [1024] per-CTA step flags of the split-precision recurrence kernels (forward [0,512), backward [512,1024))
   float* wg_scratch;  // split-K scratch private to the weight-gradient GEMMs (two layers, bf16 backend): lets them run on a
                       // side stream beside the caller's trunk backward, which uses the caller's scratch
