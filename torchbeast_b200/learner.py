@@ -228,6 +228,7 @@ def learn(flags, model, actor_model, batch, initial_agent_state, optimizer, sche
             model._tb_stager = stager
         slot = stager.put(batch)
         initial_agent_state = tuple(t.to(model.flat_params.device, non_blocking=True) for t in initial_agent_state)
+    snap = None
     with (lock if lock is not None else contextlib.nullcontext()):
         if stager is not None:
             # this thread's own slot: wait for ITS copy (slots complete in submission order per thread)
@@ -251,11 +252,16 @@ def learn(flags, model, actor_model, batch, initial_agent_state, optimizer, sche
                 if stager is not None:
                     stager.release(slot)  # the inputs now live in the graph's static buffers
                     slot = None
-                return gl.stats()
-            return learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer, scheduler)
+                snap = gl.snapshot()      # tiny device copies, still under the lock (the next replay overwrites the originals)
+            else:
+                return learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer, scheduler)
         finally:
             if stager is not None and slot is not None:
                 stager.release(slot)
+    # graphed path: the blocking stats read-back happens OUTSIDE the lock - the device work of this step is already
+    # enqueued, so another learner thread can enqueue its step right behind it (the reference holds its lock across the
+    # .item() calls, polybeast_learner.py:373-379, which idles the GPU for a host round trip per step)
+    return GraphedLearner.stats_from(snap)
 
 
 def shard_rollout(batch, initial_agent_state, rank, world_size):
@@ -338,6 +344,23 @@ class GraphedLearner:
         if scheduler is not None:
             scheduler.step()
         return self.out
+
+    def snapshot(self):
+        """Device copies of what stats() reads (the step's losses and its done / episode_return rows), enqueued on the
+        current stream: lets the caller release the learner lock BEFORE the blocking read-back, so the next learner
+        thread's replay queues up behind this one instead of waiting for a host round trip."""
+        return (self.out["losses"].clone(), self.static["done"][1:].clone(), self.static["episode_return"][1:].clone())
+
+    @staticmethod
+    def stats_from(snap):
+        losses, done, ep_ret = snap
+        ep = ep_ret[done.bool()].cpu()
+        host = losses.cpu()
+        return {
+            "episode_returns": tuple(ep.numpy()), "mean_episode_return": torch.mean(ep).item(),
+            "total_loss": host[3].item(), "pg_loss": host[0].item(), "baseline_loss": host[1].item(),
+            "entropy_loss": host[2].item(),
+        }
 
     def stats(self):
         """Same keys as monobeast.learn()'s return value; one blocking read-back."""
