@@ -628,10 +628,9 @@ def main():
             except Exception as exc:  # surfaced below
                 errs.append(exc)
 
-        if world > 1:  # collectives inside the step must be issued in the same order on every rank: one learner thread
-            body_threads = [threading.Thread(target=lambda: [body(0), body(1)])]
-        else:
-            body_threads = [threading.Thread(target=body, args=(k,)) for k in range(nthreads)]
+        # (world > 1: every replay of the step graph issues the same collective sequence, so which learner thread replays
+        #  next does not matter - the ranks only have to run the same NUMBER of steps)
+        body_threads = [threading.Thread(target=body, args=(k,)) for k in range(nthreads)]
         for t in body_threads:
             t.start()
         for t in body_threads:
@@ -681,7 +680,7 @@ def main():
             NROT * h2d_bytes / 1e6),
         e2e=dict(value=frames / (e2e_ms * 1e-3), unit="frames/s", ms_per_step=e2e_ms, h2d_bytes_per_step=h2d_bytes,
                  d2h_bytes_per_step=d2h_bytes, h2d_gbs_measured=h2d_gbs, numa_node=numa, cuda_graph=graphed is not None,
-                 learner_threads=1 if world > 1 else 2,
+                 learner_threads=2,
                  note="every step: monobeast.learn(flags, actor, model, PINNED HOST rollout, ...) -> RolloutStager (one async "
                       "H2D copy of the slot on the copy stream, issued outside the lock so it overlaps the other learner "
                       "thread's step) -> lock -> %s -> stats read-back; all inside the timed region" % (

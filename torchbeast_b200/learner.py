@@ -1,6 +1,7 @@
 """Fused pieces of the learner step shared by monobeast.learn and polybeast_learner.learn."""
 import collections
 import os
+import threading
 
 import torch
 
@@ -252,7 +253,11 @@ def learn(flags, model, actor_model, batch, initial_agent_state, optimizer, sche
                 if stager is not None:
                     stager.release(slot)  # the inputs now live in the graph's static buffers
                     slot = None
+                if os.environ.get("TB_STATS_IN_LOCK", "0") == "1":   # the reference's behaviour: read back under the lock
+                    return gl.stats()
                 snap = gl.snapshot()      # tiny device copies, still under the lock (the next replay overwrites the originals)
+                snap_event = torch.cuda.Event()
+                snap_event.record()
             else:
                 return learn_step(flags, model, actor_model, batch, initial_agent_state, optimizer, scheduler)
         finally:
@@ -261,7 +266,7 @@ def learn(flags, model, actor_model, batch, initial_agent_state, optimizer, sche
     # graphed path: the blocking stats read-back happens OUTSIDE the lock - the device work of this step is already
     # enqueued, so another learner thread can enqueue its step right behind it (the reference holds its lock across the
     # .item() calls, polybeast_learner.py:373-379, which idles the GPU for a host round trip per step)
-    return GraphedLearner.stats_from(snap)
+    return GraphedLearner.stats_from(snap, snap_event)
 
 
 def shard_rollout(batch, initial_agent_state, rank, world_size):
@@ -351,11 +356,30 @@ class GraphedLearner:
         thread's replay queues up behind this one instead of waiting for a host round trip."""
         return (self.out["losses"].clone(), self.static["done"][1:].clone(), self.static["episode_return"][1:].clone())
 
+    _tls = threading.local()
+
     @staticmethod
-    def stats_from(snap):
+    def stats_from(snap, event):
+        """Read the snapshot back on a per-thread READ-BACK stream that waits only for `event` (recorded right after the
+        snapshot): a read-back on the compute stream would queue behind the NEXT step, which another learner thread has
+        already enqueued there."""
         losses, done, ep_ret = snap
-        ep = ep_ret[done.bool()].cpu()
-        host = losses.cpu()
+        tls = GraphedLearner._tls
+        dev = losses.device
+        if getattr(tls, "stream", None) is None or tls.device != dev:
+            tls.stream, tls.device, tls.pinned = torch.cuda.Stream(device=dev), dev, {}
+        key = (tuple(done.shape), done.dtype)
+        bufs = tls.pinned.get(key)
+        if bufs is None:
+            bufs = tls.pinned[key] = (torch.empty(4, dtype=torch.float32).pin_memory(), torch.empty(done.shape, dtype=done.dtype).pin_memory(),
+                                      torch.empty(ep_ret.shape, dtype=ep_ret.dtype).pin_memory())
+        tls.stream.wait_event(event)
+        with torch.cuda.stream(tls.stream):
+            for dst, src in zip(bufs, (losses, done, ep_ret)):
+                dst.copy_(src, non_blocking=True)
+        tls.stream.synchronize()
+        host, hdone, hret = bufs
+        ep = hret[hdone.bool()].clone()
         return {
             "episode_returns": tuple(ep.numpy()), "mean_episode_return": torch.mean(ep).item(),
             "total_loss": host[3].item(), "pg_loss": host[0].item(), "baseline_loss": host[1].item(),
