@@ -149,7 +149,10 @@ int tb_atarinet_backward(const float* grad_logits, const float* grad_baseline, c
  * polybeast_learner.py:402-405; SURVEY 8(e) G1 "bucket order = reverse of forward"): phase 1 = policy/baseline heads +
  * LSTM, phase 2 = conv/fc trunk.  After phase 2 everything is final; after phase 1 the slice
  * [tb_atarinet_grad_split(), param_count) of `grads` (LSTM + heads: 17 of 24 MB) is final when the LSTM weight-gradient
- * GEMMs ran on the caller's stream (precision 0 and 2), so its all-reduce can overlap phase 2.                      */
+ * GEMMs ran on the caller's stream; when they were forked onto the side stream (tensor-core backends), the slice is
+ * final in STREAM ORDER on that side stream: pass your own with tb_set_aux_stream() (thread-local; NULL = library-owned)
+ * before phase 1, make it wait for `stream`, and enqueue the slice's all-reduce on it - it then overlaps phase 2.      */
+int tb_set_aux_stream(void* stream);
 int64_t tb_atarinet_grad_split(int num_actions, int use_lstm);
 int tb_atarinet_backward_phase(const float* grad_logits, const float* grad_baseline, const float* notdone,
                                const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,

@@ -423,7 +423,9 @@ static int atarinet_backward(const float* grad_logits, const float* grad_baselin
     TB_TRY(lstm_backward(w.dcore_out, w.core_in, notdone, lp, lg, T1, B, pp.core, pp.core, 2, w.lstm, w.dcore_in,
                          w.splitk, w.colsum_scratch, precision, st));
   }
-  if (!(phases & 2)) return lstm_backward_join(st);  // phase 1 alone: the LSTM + heads gradient slice must be final on return
+  // phase 1 alone: the heads' gradients are final in stream order on `st`; the LSTM weight gradients in stream order on the
+  // side stream their GEMMs were forked onto (the caller's aux stream, tb_set_aux_stream) - joined at the end of phase 2
+  if (!(phases & 2)) return 0;
   if (precision) {
     TB_TRY(atarinet_backward_trunk_bf16(P, G_, pp, w, N, st));
     return lstm_backward_join(st);  // the LSTM weight-gradient GEMMs ran beside the trunk backward

@@ -2520,11 +2520,26 @@ struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
+// A caller-owned side stream (tb_set_aux_stream): data-parallel learners pass the stream they will enqueue the all-reduce of
+// the LSTM gradient slice on, so that it is ordered behind the weight-gradient GEMMs forked onto it.
+static thread_local cudaStream_t g_aux_stream = nullptr;
+
 static SideStream* side_stream() {
   static thread_local SideStream per_dev[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   SideStream& s = per_dev[dev];
+  if (g_aux_stream) {
+    static thread_local SideStream aux[64];
+    SideStream& x = aux[dev];
+    x.stream = g_aux_stream;
+    if (!x.fork && (cudaEventCreateWithFlags(&x.fork, cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&x.join, cudaEventDisableTiming) != cudaSuccess)) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return &x;
+  }
   if (!s.stream) {
     const char* e = getenv("TB_LSTM_OVERLAP");
     if (e && e[0] == '0') return nullptr;
@@ -2920,6 +2935,11 @@ int lstm_abi_check(int64_t T1, int64_t B, int In, int H, int layers, int precisi
 }  // namespace
 
 extern "C" {
+
+int tb_set_aux_stream(void* stream) {
+  g_aux_stream = (cudaStream_t)stream;
+  return 0;
+}
 
 size_t tb_lstm_workspace_bytes(int64_t T1, int64_t B, int input_size, int hidden_size, int layers, int precision) {
   if (T1 < 1 || B < 1 || input_size < 1 || hidden_size < 1 || layers < 1 || layers > kLstmMaxLayers) return 0;

@@ -130,7 +130,7 @@ def _backward_with_overlapped_all_reduce(model, grad_logits, grad_values):
             else:
                 dist.all_reduce(fg[split:], op=dist.ReduceOp.SUM)
 
-    fg = model.learner_backward(grad_logits, grad_values, between=between)
+    fg = model.learner_backward(grad_logits, grad_values, between=between, **({"aux_stream": side} if on_gpu else {}))
     split = state["split"]
     if split > 0:
         dist.all_reduce(fg[:split], op=dist.ReduceOp.SUM)

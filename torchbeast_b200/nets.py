@@ -324,19 +324,28 @@ class AtariNet(FlatParamModule):
         return LearnerOutputs(logits, baseline, (hN, cN) if self.use_lstm else tuple())
 
     @torch.no_grad()
-    def learner_backward(self, grad_logits, grad_baseline, between=None):
+    def learner_backward(self, grad_logits, grad_baseline, between=None, aux_stream=None):
         """Writes d loss / d params into flat_grad (and points every .grad at its slice).  `between(flat_grad, split)`:
-        called after the heads + LSTM phase, when flat_grad[split:] is final, before the conv/fc trunk phase is launched
-        (data-parallel learners start that slice's all-reduce there)."""
+        called after the heads + LSTM phase, before the conv/fc trunk phase is launched; flat_grad[split:] is then final
+        in stream order on `aux_stream` once that stream has waited for the current one (data-parallel learners enqueue
+        that slice's all-reduce on it there)."""
         fg = self.attach_grads()
-        if between is None or self.precision == "bf16":  # bf16: the LSTM weight-gradient GEMMs run beside the trunk backward
+        if between is None:
             self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg)
-            if between is not None:
-                between(fg, 0)
             return fg
-        self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg, phase=1)
-        between(fg, self.grad_split())
-        self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg, phase=2)
+        # The tensor-core backends fork the LSTM weight-gradient GEMMs onto a side stream: make it the caller's (aux_stream)
+        # so that what `between` enqueues there is ordered behind them and overlaps the trunk backward of phase 2.
+        import ctypes
+        lib = _lib.lib()
+        if aux_stream is not None:
+            lib.tb_set_aux_stream(ctypes.c_void_p(aux_stream.cuda_stream))
+        try:
+            self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg, phase=1)
+            between(fg, self.grad_split())
+            self._launch_backward(grad_logits, grad_baseline, self._saved_notdone, fg, phase=2)
+        finally:
+            if aux_stream is not None:
+                lib.tb_set_aux_stream(None)
         return fg
 
     # ---- reference-compatible forward ---------------------------------------------------------
