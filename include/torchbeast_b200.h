@@ -194,6 +194,14 @@ int tb_resnet_backward(const uint8_t* frame, const float* grad_logits, const flo
                        const float* notdone, const float* params, int64_t T1, int64_t B, int num_actions,
                        int use_lstm, int precision, void* workspace, float* grads, void* stream);
 
+/* ---- learner-queue ingest, host side --------------------------------------------------
+ * One actor writes its [T1, ...] rollout into batch column b of a pinned [T1, B, ...] slot (replaces the per-rollout
+ * tensors + torch::cat of src/cc/actorpool.cc:49-55,493-506): leaf l of the slot starts at slot_base + leaf_offset[l], one
+ * (time step, column) row of it is row_bytes[l] bytes, src[l] is the actor's contiguous [T1, row] array (NULL = skip).
+ * Pure host memcpy on the calling thread; no CUDA call.                                                           */
+int tb_host_write_rollout_column(uint8_t* slot_base, const int64_t* leaf_offset, const int64_t* row_bytes, int num_leaves,
+                                 int64_t T1, int64_t B, int64_t b, const uint8_t* const* src);
+
 /* ---- flat-buffer optimizer step ------------------------------------------------------------ */
 
 /* out_sumsq[0] = sum(grads^2) (double accumulation, deterministic).  First half of

@@ -94,9 +94,26 @@ class SyntheticActors:
                 state = tuple(torch.zeros(layers, self.B, H) for _ in range(2))
             self.queue.put(((env, agent), state))
 
-    def _actor(self, k):
+    def _make_pool(self, k, pool=4):
+        """A few pre-generated rollouts per actor (what its environment steps would have produced): the per-rollout host work
+        that remains is the hand-over into the pinned column, as for a real actor."""
         rs = np.random.RandomState(self._seed * 1000 + k)
-        T1 = self.T + 1
+        T1, A = self.T + 1, self.A
+        out = []
+        for j in range(pool):
+            out.append(dict(
+                frame=self._frames[(k + j) % self._frames.shape[0]],
+                reward=torch.from_numpy(rs.randn(T1).astype(np.float32)),
+                done=torch.from_numpy(rs.rand(T1) < 0.01),
+                episode_return=torch.from_numpy(rs.randn(T1).astype(np.float32)),
+                episode_step=torch.from_numpy(rs.randint(0, 1000, size=T1).astype(np.int32)),
+                policy_logits=torch.from_numpy(rs.randn(T1, A).astype(np.float32)),
+                baseline=torch.from_numpy(rs.randn(T1).astype(np.float32)),
+                action=torch.from_numpy(rs.randint(0, A, size=T1).astype(np.int64))))
+        return out
+
+    def _actor(self, k):
+        pool = self._make_pool(k)
         last = None
         n = 0
         while not self._stop:
@@ -104,20 +121,12 @@ class SyntheticActors:
                 i, b = self._claim()
             except TimeoutError:
                 continue
-            col = self.stager.column(i, b)
-            col["frame"].copy_(self._frames[(k + n) % self._frames.shape[0]])
-            col["reward"].copy_(torch.from_numpy(rs.randn(T1).astype(np.float32)))
-            col["done"].copy_(torch.from_numpy(rs.rand(T1) < 0.01))
-            col["episode_return"].copy_(torch.from_numpy(rs.randn(T1).astype(np.float32)))
-            col["episode_step"].copy_(torch.from_numpy(rs.randint(0, 1000, size=T1).astype(np.int32)))
-            col["policy_logits"].copy_(torch.from_numpy(rs.randn(T1, self.A).astype(np.float32)))
-            col["baseline"].copy_(torch.from_numpy(rs.randn(T1).astype(np.float32)))
-            col["action"].copy_(torch.from_numpy(rs.randint(0, self.A, size=T1).astype(np.int64)))
-            if last is not None:  # row 0 = last row of this actor's previous rollout
-                for key, v in last.items():
-                    col[key][0].copy_(v)
-            last = {key: v[-1].clone() for key, v in col.items() if key != "frame"}
-            last["frame"] = col["frame"][-1].clone()
+            roll = pool[n % len(pool)]
+            if last is not None:  # row 0 = last row of this actor's previous rollout (actorpool.cc:443)
+                for key, v in roll.items():
+                    v[0].copy_(last[key][-1])
+            self.stager.write_column(i, b, roll)   # native, GIL-free copy of all leaves into the pinned column
+            last = roll
             n += 1
             with self._lock:
                 self.rollouts += 1

@@ -107,4 +107,24 @@ int tb_profile_collect(char* names_host, size_t names_cap, float* ms_host, int m
   return n;
 }
 
+// Host side of the learner-queue ingest: one actor hands its [T1, ...] rollout over by writing it into
+// batch column b of a pinned [T1, B, ...] slot - what actorpool.cc:493-506 + the BatchingQueue's torch::cat (actorpool.cc:
+// 49-55) do with per-rollout tensors and a concatenation.  Plain memcpy per (leaf, time step): leaf l of the slot starts
+// at slot_base + leaf_offset[l], a row (one time step of one column) is row_bytes[l] bytes, the source is the actor's
+// contiguous [T1, row] array.  No CUDA calls: runs on the calling host thread (ctypes releases the GIL for its duration,
+// which is the point - 48 Python actor threads otherwise serialise on it).
+int tb_host_write_rollout_column(uint8_t* slot_base, const int64_t* leaf_offset, const int64_t* row_bytes, int num_leaves,
+                                 int64_t T1, int64_t B, int64_t b, const uint8_t* const* src) {
+  TB_REQUIRE(slot_base && leaf_offset && row_bytes && src, "tb_host_write_rollout_column: null pointer");
+  TB_REQUIRE(num_leaves >= 1 && T1 >= 1 && B >= 1 && b >= 0 && b < B, "tb_host_write_rollout_column: bad sizes");
+  for (int l = 0; l < num_leaves; ++l) {
+    const int64_t rb = row_bytes[l];
+    if (!src[l] || rb <= 0) continue;
+    uint8_t* dst = slot_base + leaf_offset[l] + b * rb;
+    const uint8_t* s = src[l];
+    for (int64_t t = 0; t < T1; ++t) memcpy(dst + t * B * rb, s + t * rb, size_t(rb));
+  }
+  return 0;
+}
+
 }  // extern "C"

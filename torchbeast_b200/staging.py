@@ -113,6 +113,25 @@ class RolloutStager:
         """Views `[T+1, ...]` of batch column b of host slot i: what ONE actor fills (actorpool.cc:493-506 per rollout)."""
         return collections.OrderedDict((k, v[:, b]) for k, v in self.host[i].items())
 
+    def write_column(self, i, b, rollout):
+        """Native per-actor hand-over: copy `rollout` (dict leaf -> contiguous [T+1, ...] CPU tensor) into column b of pinned
+        slot i with ONE C call (tb_host_write_rollout_column) that runs without the GIL - N actor threads then copy in
+        parallel instead of serialising on the interpreter."""
+        import ctypes
+        names = [k for k in self.spec if k in rollout]
+        n = len(names)
+        offs = (ctypes.c_int64 * n)(*[self._offs[k][0] for k in names])
+        T1, B = self.spec[names[0]][0][:2]
+        rows = (ctypes.c_int64 * n)(*[self._offs[k][1] // (T1 * B) for k in names])
+        srcs = (ctypes.c_void_p * n)(*[rollout[k].data_ptr() for k in names])
+        for k in names:
+            t = rollout[k]
+            if t.is_cuda or not t.is_contiguous() or t.dtype != self.spec[k][1] or t.numel() * t.element_size() != self._offs[k][1] // B:
+                raise _lib.TorchBeastB200Error("write_column: leaf %r must be a contiguous CPU [T+1, ...] tensor of the slot's dtype" % k)
+        _lib.check(_lib.lib().tb_host_write_rollout_column(
+            ctypes.c_void_p(self._host_raw[i].data_ptr()), ctypes.cast(offs, ctypes.c_void_p), ctypes.cast(rows, ctypes.c_void_p), n,
+            T1, B, int(b), ctypes.cast(srcs, ctypes.c_void_p)), "tb_host_write_rollout_column")
+
     def submit(self, i):
         """Slot i is complete: one async H2D copy of the whole slot on the copy stream."""
         with torch.cuda.stream(self._stream):
