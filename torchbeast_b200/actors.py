@@ -110,23 +110,24 @@ class SyntheticActors:
                 policy_logits=torch.from_numpy(rs.randn(T1, A).astype(np.float32)),
                 baseline=torch.from_numpy(rs.randn(T1).astype(np.float32)),
                 action=torch.from_numpy(rs.randint(0, A, size=T1).astype(np.int64))))
-        return out
+        # row 0 of a rollout = last row of this actor's previous rollout (actorpool.cc:443): the pool is handed over cyclically,
+        # so that overlap is baked in once (own copies of the shared frame stacks: row 0 differs per actor)
+        out = [dict(r, frame=r["frame"].clone()) for r in out]
+        for j in range(pool):
+            prev = out[(j - 1) % pool]
+            for key, v in out[j].items():
+                v[0].copy_(prev[key][-1])
+        return [self.stager.prepare_rollout(r) for r in out]
 
     def _actor(self, k):
         pool = self._make_pool(k)
-        last = None
         n = 0
         while not self._stop:
             try:
                 i, b = self._claim()
             except TimeoutError:
                 continue
-            roll = pool[n % len(pool)]
-            if last is not None:  # row 0 = last row of this actor's previous rollout (actorpool.cc:443)
-                for key, v in roll.items():
-                    v[0].copy_(last[key][-1])
-            self.stager.write_column(i, b, roll)   # native, GIL-free copy of all leaves into the pinned column
-            last = roll
+            self.stager.write_prepared(i, b, pool[n % len(pool)])   # ONE native, GIL-free call copies all leaves into the column
             n += 1
             with self._lock:
                 self.rollouts += 1

@@ -113,6 +113,30 @@ class RolloutStager:
         """Views `[T+1, ...]` of batch column b of host slot i: what ONE actor fills (actorpool.cc:493-506 per rollout)."""
         return collections.OrderedDict((k, v[:, b]) for k, v in self.host[i].items())
 
+    def prepare_rollout(self, rollout):
+        """Pre-built argument block for write_column() when the same host arrays are handed over repeatedly (a fixed pool of
+        synthetic rollouts): keeps the per-rollout Python work to one C call."""
+        import ctypes
+        names = [k for k in self.spec if k in rollout]
+        n = len(names)
+        T1, B = self.spec[names[0]][0][:2]
+        for k in names:
+            t = rollout[k]
+            if t.is_cuda or not t.is_contiguous() or t.dtype != self.spec[k][1] or t.numel() * t.element_size() != self._offs[k][1] // B:
+                raise _lib.TorchBeastB200Error("prepare_rollout: leaf %r must be a contiguous CPU [T+1, ...] tensor of the slot's dtype" % k)
+        offs = (ctypes.c_int64 * n)(*[self._offs[k][0] for k in names])
+        rows = (ctypes.c_int64 * n)(*[self._offs[k][1] // (T1 * B) for k in names])
+        srcs = (ctypes.c_void_p * n)(*[rollout[k].data_ptr() for k in names])
+        return (ctypes.cast(offs, ctypes.c_void_p), ctypes.cast(rows, ctypes.c_void_p), n, T1, B, ctypes.cast(srcs, ctypes.c_void_p),
+                (offs, rows, srcs, rollout))  # keep the arrays and tensors alive
+
+    def write_prepared(self, i, b, prep):
+        import ctypes
+        offs, rows, n, T1, B, srcs, _keep = prep
+        rc = _lib.lib().tb_host_write_rollout_column(ctypes.c_void_p(self._host_raw[i].data_ptr()), offs, rows, n, T1, B, int(b), srcs)
+        if rc:
+            _lib.check(rc, "tb_host_write_rollout_column")
+
     def write_column(self, i, b, rollout):
         """Native per-actor hand-over: copy `rollout` (dict leaf -> contiguous [T+1, ...] CPU tensor) into column b of pinned
         slot i with ONE C call (tb_host_write_rollout_column) that runs without the GIL - N actor threads then copy in
