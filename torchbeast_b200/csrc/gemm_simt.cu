@@ -27,7 +27,9 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, float* _
     const float* p = partial + m * ldp + n0;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     if (vec) {
-#pragma unroll 4
+      // 16 loads in flight per thread (same summation order): with 148 splits and unroll 4 the conv1 reduce was 37 dependent
+      // L2 round trips = 26 us for a 4.8 MB read
+#pragma unroll 16
       for (int z = 0; z < splits; ++z) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(p + int64_t(z) * slice));
         v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;

@@ -505,7 +505,10 @@ int colsum_bf16(const void* X, float* out, int64_t M, int64_t ncols, int64_t ld,
   if (ld == ncols && (ncols == 8 || ncols == 16 || ncols == 32 || ncols == 64) && M >= 4096 &&
       (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (lo_off & 7) == 0) {
     const int cg = int(ncols / 8);
-    const int blocks = kColsumSlabs;  // partials [blocks][ncols] fit the caller's scratch
+    // partials [blocks][ncols] must fit the caller's scratch (colsum_scratch_floats(>= 512) = 256 * 512 floats): 6 CTAs per SM
+    // keep enough 16-byte loads in flight to stream at HBM rate (256 CTAs ran the 133 MB conv1 gradient at 2.3 TB/s)
+    int blocks = kNumSMsB200 * 6;
+    if (int64_t(blocks) * ncols > int64_t(kColsumSlabs) * 512) blocks = int(int64_t(kColsumSlabs) * 512 / ncols);
     colsum_dense_bf16_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(X), scratch, M * cg, cg, lo_off / 8);
     int rc = check_launch("colsum_dense_bf16_kernel");
     if (rc) return rc;
