@@ -729,7 +729,7 @@ def main():
         line["roofline_ops"] = [dict(o, share=o["ms_per_step"] / prof_total) for o in ops[:12]]
         dom = next((o for o in ops if "achieved" in o), None)
         try:
-            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")))
+            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")))
         except Exception:
             traffic_tab = {}
         if dom is not None:
