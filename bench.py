@@ -763,20 +763,20 @@ def vtrace_numbers(pk, T, B, A):
     out = {}
     g = torch.Generator(device="cuda").manual_seed(0)
     flush = torch.zeros(64 * 1024 * 1024, device="cuda")
-    for tag, (t, b) in (("bench_size", (T, B)), ("wide", (T, 1 << 20))):
+    for tag, (t, b) in (("bench_size", (T, B)), ("config5_T600_B128", (600, 128)), ("wide", (T, 1 << 20))):
         lr = 0.5 * torch.randn(t, b, device="cuda", generator=g)
         dc = 0.99 * (torch.rand(t, b, device="cuda", generator=g) > 0.01).float()
         rw = torch.randn(t, b, device="cuda", generator=g).clamp(-1, 1)
         va = torch.randn(t, b, device="cuda", generator=g); bs = torch.randn(b, device="cuda", generator=g)
         vs = torch.empty_like(va); pg = torch.empty_like(va)
-        reps = 20 if tag == "bench_size" else 3
+        reps = 20 if tag != "wide" else 3
 
         def launch_all():
             for _ in range(reps):
                 lib.tb_vtrace_from_importance_weights_f32(p(lr), p(dc), p(rw), p(va), p(bs), t, b, 1.0, 1.0, p(vs), p(pg), _lib.stream_ptr())
 
         graph = None
-        if tag == "bench_size":
+        if tag != "wide":
             # 20 launches replayed as ONE CUDA graph: the event pair then measures kernel time on the device
             # (launch-to-launch), not the host's ctypes launch rate
             try:

@@ -2215,6 +2215,13 @@ __global__ void __launch_bounds__(kSplitThreads, 1) lstm2_bwd_wave_split_kernel(
   }
 }
 
+// cudaFuncSetAttribute is per device: the caches below are indexed by the current device
+static inline size_t* per_device(size_t (&cache)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return &cache[dev & 63];
+}
+
 template <typename Kernel>
 static int coop_fit(Kernel kernel, dim3 grid, size_t smem, size_t* attr_smem) {
   if (*attr_smem < smem) {
@@ -2227,7 +2234,7 @@ static int coop_fit(Kernel kernel, dim3 grid, size_t smem, size_t* attr_smem) {
   return persistent_ok((const void*)kernel, grid, smem);
 }
 
-static size_t g_fwd_mma_attr = 0, g_bwd_mma_attr = 0;
+static size_t g_fwd_mma_attr_dev[64] = {0}, g_bwd_mma_attr_dev[64] = {0};
 
 // one decision for a (B, H) pair, used identically by forward and backward (the backward consumes the bf16
 // masked-h buffer only the tensor-core forward writes)
@@ -2237,8 +2244,8 @@ static bool mma_recurrence_applicable(int64_t B, int H) {
   if (!persistent_enabled() || B > 32 || H > 624) return false;  // tile copy: <= 5 x 16 B chunks per thread
   const int Hq = mma_hq(H);
   dim3 grid((H + kStepUnits - 1) / kStepUnits, 1), gridb((H + kBwdCols - 1) / kBwdCols, 1);
-  return coop_fit(lstm_fwd_persistent_mma_kernel, grid, size_t(32) * Hq * 2, &g_fwd_mma_attr) &&
-         coop_fit(lstm_bwd_persistent_mma_kernel, gridb, size_t(4) * 32 * Hq * 2, &g_bwd_mma_attr);
+  return coop_fit(lstm_fwd_persistent_mma_kernel, grid, size_t(32) * Hq * 2, per_device(g_fwd_mma_attr_dev)) &&
+         coop_fit(lstm_bwd_persistent_mma_kernel, gridb, size_t(4) * 32 * Hq * 2, per_device(g_bwd_mma_attr_dev));
 }
 
 static int lstm_fwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, float* hs, const float* notdone, int64_t T1,
@@ -2246,7 +2253,7 @@ static int lstm_fwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, floa
   const int Hq = mma_hq(H);
   const size_t smem = size_t(32) * Hq * 2;
   dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
-  if (!coop_fit(lstm_fwd_persistent_mma_kernel, grid, smem, &g_fwd_mma_attr)) return -1;
+  if (!coop_fit(lstm_fwd_persistent_mma_kernel, grid, smem, per_device(g_fwd_mma_attr_dev))) return -1;
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
   PersistFwdMmaArgs a;
@@ -2259,7 +2266,7 @@ static int lstm_fwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, floa
   return check_launch("lstm_fwd_persistent_mma_kernel");
 }
 
-static size_t g_fwd_wave_attr = 0;
+static size_t g_fwd_wave_attr_dev[64] = {0};
 static size_t wave_fwd_smem(int Hq) { return size_t(2) * 32 * Hq * 2 + sizeof(float) * 16 * 2 * 16 * 33; }
 static bool wave_fwd_applicable(int64_t B, int H) {
   const char* e = getenv("TB_LSTM_WAVE");
@@ -2267,7 +2274,7 @@ static bool wave_fwd_applicable(int64_t B, int H) {
   if (!mma_recurrence_applicable(B, H)) return false;
   if (((H + 15) / 16 + 15) / 16 > kWaveK) return false;
   dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
-  return coop_fit(lstm2_fwd_wave_mma_kernel, grid, wave_fwd_smem(mma_hq(H)), &g_fwd_wave_attr);
+  return coop_fit(lstm2_fwd_wave_mma_kernel, grid, wave_fwd_smem(mma_hq(H)), per_device(g_fwd_wave_attr_dev));
 }
 
 static int lstm2_fwd_wave(LstmWs& ws, const LstmParams& p, float* y, const float* notdone, int64_t T1, int64_t B, int H,
@@ -2334,7 +2341,7 @@ __global__ void lstm_init_state_split_kernel(const float* __restrict__ h0, const
   hmq[i] = m; hmq[hmq_lo + i] = __float2bfloat16_rn(hm - __bfloat162float(m));
 }
 
-static size_t g_fwd_split_attr = 0;
+static size_t g_fwd_split_attr_dev[64] = {0};
 static size_t wave_fwd_split_smem(int Hq) { return size_t(4) * 32 * Hq * 2 + sizeof(float) * kSplitWarps * 2 * 16 * 33; }
 // precision 2, two layers: the split-bf16 wavefront kernel (TB_LSTM_SPLIT=0 keeps the exact-fp32 recurrence kernels)
 static bool wave_fwd_split_applicable(int64_t B, int In, int H) {
@@ -2343,13 +2350,13 @@ static bool wave_fwd_split_applicable(int64_t B, int In, int H) {
   if (!persistent_enabled() || B > 32 || In != H || (H + 15) / 16 > kSplitWarps * kSplitK) return false;
   dim3 grid((H + kStepUnits - 1) / kStepUnits, 1);
   if (int(grid.x) > kSplitThreads || grid.x > 512) return false;
-  if (g_fwd_split_attr < wave_fwd_split_smem(mma_hq(H))) {
+  if (*per_device(g_fwd_split_attr_dev) < wave_fwd_split_smem(mma_hq(H))) {
     if (cudaFuncSetAttribute(lstm2_fwd_wave_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              int(wave_fwd_split_smem(mma_hq(H)))) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    g_fwd_split_attr = wave_fwd_split_smem(mma_hq(H));
+    *per_device(g_fwd_split_attr_dev) = wave_fwd_split_smem(mma_hq(H));
   }
   int dev = 0, sms = 0, coop = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
@@ -2396,7 +2403,7 @@ static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, cons
   const int Hq = mma_hq(H);
   const size_t smem = size_t(4) * 32 * Hq * 2;
   dim3 grid((H + kBwdCols - 1) / kBwdCols, 1);
-  if (!coop_fit(lstm_bwd_persistent_mma_kernel, grid, smem, &g_bwd_mma_attr)) return -1;
+  if (!coop_fit(lstm_bwd_persistent_mma_kernel, grid, smem, per_device(g_bwd_mma_attr_dev))) return -1;
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(L.dgq, 0, size_t(2) * 4 * B * Hq * 2, st);  // zero the row padding
   TB_REQUIRE(e == cudaSuccess, "lstm: memset: %s", cudaGetErrorString(e));
@@ -2411,7 +2418,7 @@ static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, cons
   return check_launch("lstm_bwd_persistent_mma_kernel");
 }
 
-static size_t g_bwd_wave_attr = 0;
+static size_t g_bwd_wave_attr_dev[64] = {0};
 static size_t wave_bwd_smem(int H) {
   const int kper = (4 * ((H + 15) / 16) + 15) / 16;
   return size_t(4) * 32 * mma_hq(H) * 2 + size_t(16) * kper * 32 * 8;
@@ -2421,7 +2428,7 @@ static bool wave_bwd_applicable(int64_t B, int H) {
   if (e && e[0] == '0') return false;
   if (!mma_recurrence_applicable(B, H)) return false;
   dim3 grid(2 * ((H + kBwdCols - 1) / kBwdCols), 1);
-  return coop_fit(lstm2_bwd_wave_mma_kernel, grid, wave_bwd_smem(H), &g_bwd_wave_attr);
+  return coop_fit(lstm2_bwd_wave_mma_kernel, grid, wave_bwd_smem(H), per_device(g_bwd_wave_attr_dev));
 }
 
 // both layers' backward recurrences in one launch; leaves dgb / bias gradients of both layers and
@@ -2454,7 +2461,7 @@ static int lstm2_bwd_wave(LstmWs& ws, const LstmParams& p, const LstmGrads& g, c
   return check_launch("lstm2_bwd_wave_mma_kernel");
 }
 
-static size_t g_bwd_split_attr = 0;
+static size_t g_bwd_split_attr_dev[64] = {0};
 static size_t wave_bwd_split_smem(int) {
   return size_t(kSplitWarps) * 4 * 32 * (kSplitK * 16 + 8) * 2 + sizeof(float) * kSplitWarps * 2 * kBwdCols * 33 +
          sizeof(float) * 9 * 256;   // tile rings + partial sums + prefetched pointwise operands
@@ -2464,12 +2471,12 @@ static bool wave_bwd_split_applicable(int64_t B, int In, int H) {
   dim3 grid(2 * ((H + kBwdCols - 1) / kBwdCols), 1);
   if (int(grid.x / 2) + 1 > kSplitThreads || grid.x > 512) return false;
   const size_t smem = wave_bwd_split_smem(mma_hq(H));
-  if (g_bwd_split_attr < smem) {
+  if (*per_device(g_bwd_split_attr_dev) < smem) {
     if (cudaFuncSetAttribute(lstm2_bwd_wave_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) {
       cudaGetLastError();
       return false;
     }
-    g_bwd_split_attr = smem;
+    *per_device(g_bwd_split_attr_dev) = smem;
   }
   int dev = 0, sms = 0, coop = 0, per_sm = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;

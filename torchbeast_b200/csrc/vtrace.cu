@@ -16,6 +16,7 @@
 // (pass 3; re-reads hit L1/L2, HBM traffic stays the algorithmic 24*T*B+4*B bytes).  When the
 // batch is wide enough to fill the chip W=1 and pass 3 alone runs (single streaming pass).
 // This kernel is HBM-/latency-bound integer-free fp32 work: no tensor cores by design.
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -163,6 +164,116 @@ __global__ void __launch_bounds__(512) vtrace_scan_kernel(ScanArgs<F> p) {
   }
 }
 
+// Long unrolls on few columns (BASELINE configs[4]: T = 600, B = 128 -> 4 column tiles): one CTA per tile leaves the unroll to
+// 16 warps x 38 dependent steps.  Here a thread-block CLUSTER of C CTAs owns the tile: 16*C warps split T (5 steps per warp at
+// T = 600, C = 8), every warp folds its chunk into an affine map (pass 1), a CTA composes its 16 maps into one, the cluster
+// exchanges the C per-CTA maps through DISTRIBUTED SHARED MEMORY (cluster.sync + map_shared_rank reads of 2 x 32 floats per later
+// CTA), and every warp replays its chunk with the right carry-in (pass 3).  Same arithmetic and summation order as the
+// single-CTA kernel within a chunk; the chunk boundaries differ, which moves results by fp32 rounding of the affine composition
+// (covered by the same tolerances: tests/test_vtrace_gpu.py).
+template <typename F, int U>
+__global__ void __launch_bounds__(512) vtrace_scan_cluster_kernel(ScanArgs<F> p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int W = blockDim.y, C = int(cluster.num_blocks()), rank = int(cluster.block_rank());
+  F* sA = reinterpret_cast<F*>(smem_raw);      // [W][32] per-warp maps
+  F* sB = sA + W * kWarp;
+  F* sCA = sB + W * kWarp;                     // [32] this CTA's composed map (read by the other CTAs of the cluster)
+  F* sCB = sCA + kWarp;
+  const int lane = threadIdx.x, w = threadIdx.y;
+  const int64_t T = p.T, B = p.B;
+  const int64_t tile = blockIdx.x / C;
+  const int64_t b = tile * kWarp + lane;
+  const bool active = b < B;
+  const int64_t chunk = (T + int64_t(W) * C - 1) / (int64_t(W) * C);
+  const int64_t gw = int64_t(rank) * W + w;    // chunk index along T (rank-major: a CTA owns W consecutive chunks)
+  const int64_t t0 = (gw * chunk < T) ? gw * chunk : T;
+  const int64_t t1 = (t0 + chunk < T) ? t0 + chunk : T;
+  // pass 1: chunk -> affine map (a, bb); the chunk's operands stay in registers for pass 3 (chunk <= U)
+  F lr[U], g[U], r[U], v[U];
+  F a = F(1), bb = F(0);
+  F v_last = F(0);
+  if (active && t1 > t0) {
+    v_last = (t1 < T) ? p.values[t1 * B + b] : p.bootstrap[b];
+    F v_next = v_last;
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t t = t1 - 1 - k;
+      if (t >= t0) {
+        const int64_t i = t * B + b;
+        lr[k] = p.log_rhos[i]; g[k] = p.discounts[i]; r[k] = p.rewards[i]; v[k] = p.values[i];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t t = t1 - 1 - k;
+      if (t >= t0) {
+        const F rho = M<F>::exp(lr[k]);
+        const F c = M<F>::min(rho, F(1));
+        const F rb = p.has_clip_rho ? M<F>::min(rho, p.clip_rho) : rho;
+        const F delta = rb * (r[k] + g[k] * v_next - v[k]);
+        const F dc = g[k] * c;
+        bb = delta + dc * bb;
+        a = dc * a;
+        v_next = v[k];
+      }
+    }
+  }
+  sA[w * kWarp + lane] = a;
+  sB[w * kWarp + lane] = bb;
+  __syncthreads();
+  if (w == 0) {  // this CTA's W maps composed (latest chunk applied first)
+    F ca = F(1), cb = F(0);
+    for (int w2 = W - 1; w2 >= 0; --w2) { cb = sB[w2 * kWarp + lane] + sA[w2 * kWarp + lane] * cb; ca = sA[w2 * kWarp + lane] * ca; }
+    sCA[lane] = ca; sCB[lane] = cb;
+  }
+  cluster.sync();
+  // carry-in: all later CTAs (through DSMEM), then the later warps of this CTA
+  F acc_in = F(0);
+  for (int r2 = C - 1; r2 > rank; --r2) {
+    const F* ra = cluster.map_shared_rank(sCA, r2);
+    const F* rb2 = cluster.map_shared_rank(sCB, r2);
+    acc_in = rb2[lane] + ra[lane] * acc_in;
+  }
+  for (int w2 = W - 1; w2 > w; --w2) acc_in = sB[w2 * kWarp + lane] + sA[w2 * kWarp + lane] * acc_in;
+  if (active && t1 > t0) {  // pass 3: replay from registers
+    F v_next = v_last;
+    F vs_next = (t1 < T) ? acc_in + v_next : v_next;
+    F acc = acc_in;
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const int64_t t = t1 - 1 - k;
+      if (t >= t0) {
+        const int64_t i = t * B + b;
+        const F rho = M<F>::exp(lr[k]);
+        const F c = M<F>::min(rho, F(1));
+        const F rb = p.has_clip_rho ? M<F>::min(rho, p.clip_rho) : rho;
+        const F rp = p.has_clip_pg ? M<F>::min(rho, p.clip_pg) : rho;
+        const F delta = rb * (r[k] + g[k] * v_next - v[k]);
+        acc = delta + (g[k] * c) * acc;
+        const F vst = acc + v[k];
+        p.pg_adv[i] = rp * (r[k] + g[k] * vs_next - v[k]);
+        p.vs[i] = vst;
+        vs_next = vst;
+        v_next = v[k];
+      }
+    }
+  }
+  cluster.sync();  // no CTA may exit while another still reads its shared memory
+}
+
+// cluster size for the T-split across CTAs: the largest power of two <= 8 that leaves >= 4 time steps per warp (0: not worth it)
+static int pick_cluster(int64_t T, int64_t tiles, int W) {
+  const char* e = getenv("TB_VTRACE_CLUSTER");
+  if (e && e[0] == '0') return 0;
+  if (W < 16 || tiles * 16 > int64_t(sm_count()) * 2) return 0;  // enough tiles to fill the chip without it
+  int c = 8;
+  while (c > 1 && (T < int64_t(16) * c * 4 || (T + int64_t(16) * c - 1) / (int64_t(16) * c) > 8)) c >>= 1;
+  if (c > 1 && (T + int64_t(16) * c - 1) / (int64_t(16) * c) > 8) return 0;  // chunk must fit the register window (U = 8)
+  return c > 1 ? c : 0;
+}
+
 template <typename F>
 static int launch_scan(const F* log_rhos, const F* discounts, const F* rewards, const F* values,
                        const F* bootstrap, int64_t T, int64_t B, F clip_rho, F clip_pg, F* vs,
@@ -189,6 +300,22 @@ static int launch_scan(const F* log_rhos, const F* discounts, const F* rewards, 
   dim3 block(kWarp, W);
   size_t smem = size_t(2) * W * kWarp * sizeof(F);
   ProfScope prof("vtrace_scan", (cudaStream_t)stream);
+  const int C = a.wide ? 0 : pick_cluster(T, tiles, W);
+  if (C > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(tiles * C));
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem + 2 * kWarp * sizeof(F);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(C); attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, vtrace_scan_cluster_kernel<F, 8>, a);
+    if (e == cudaSuccess) return check_launch("vtrace_scan_cluster_kernel");
+    cudaGetLastError();  // cluster launch not possible here: fall through to the single-CTA kernel
+  }
   vtrace_scan_kernel<F, 8><<<grid, block, smem, (cudaStream_t)stream>>>(a);
   return check_launch("vtrace_scan_kernel");
 }
