@@ -140,3 +140,26 @@ def test_c_oracle_loss_matches_numpy_oracle():
     np.testing.assert_allclose(c["losses"], [o.pg_loss, o.baseline_loss, o.entropy_loss], rtol=1e-5)
     np.testing.assert_allclose(c["grad_logits"], o.grad_logits, rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(c["grad_values"], o.grad_values, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("fname,net", [("learn_atari_lstm_T80_B32.npz", "atari"), ("learn_atari_T80_B32.npz", "atari"),
+                                       ("learn_resnet_lstm_T80_B8.npz", "resnet")])
+def test_learn_step_matches_reference_at_the_baseline_config(fname, net):
+    """The oracle port against the reference's own output AT the sizes bench.py runs (BASELINE configs[1]: T=80, B=32; one
+    GPU's shard of configs[3]: ResNet T=80, B=8): outputs, V-trace targets, losses, 4096 strided gradient samples per tensor.
+    (the learn-step fixtures stopped at T=40, B=6.)"""
+    from tests.common import sample_index
+    g, o = run_oracle_learn(fname, net)
+    np.testing.assert_allclose(o["policy_logits"].numpy(), g["policy_logits"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(o["baseline"].numpy(), g["baseline"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(o["vs"].numpy(), g["vs"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(o["pg_advantages"].numpy(), g["pg_advantages"], rtol=1e-4, atol=1e-4)
+    for k in ("total_loss", "pg_loss", "baseline_loss", "entropy_loss"):
+        np.testing.assert_allclose(float(o[k]), float(g[k]), rtol=2e-5, atol=2e-5, err_msg=k)
+    coef = min(1.0, float(g["clip"]) / (float(o["grad_norm"]) + 1e-6))
+    for n, gr in o["grads"].items():
+        idx = torch.from_numpy(sample_index(gr.numel()))
+        got = (gr * coef).flatten()[idx].double()
+        ref = torch.from_numpy(g["grad_sample/" + n]).double()
+        rel = float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+        assert rel < 6e-3, (n, rel)  # fp32 summation order moves ReLU ties at this size (see tests/test_learner_baseline_gpu.py)
