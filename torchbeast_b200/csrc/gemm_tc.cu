@@ -350,6 +350,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 32; ++j)
                 if (nbase + j < N) o[j] += __bfloat162float(ep.addend16[pr * ep.ldadd + pc + j]);
             }
+            if (ep.addend32) {
+              const float* ap = ep.addend32 + pr * ep.ldadd + pc;
+              if (full_cols && (ep.ldadd & 3) == 0 && (reinterpret_cast<uintptr_t>(ap) & 15) == 0) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 a4 = __ldg(reinterpret_cast<const float4*>(ap) + q);
+                  o[4 * q] += a4.x; o[4 * q + 1] += a4.y; o[4 * q + 2] += a4.z; o[4 * q + 3] += a4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  if (nbase + j + 4 <= N && (ep.ldadd & 3) == 0 && (reinterpret_cast<uintptr_t>(ap) & 15) == 0) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(ap + j));
+                    o[j] += a4.x; o[j + 1] += a4.y; o[j + 2] += a4.z; o[j + 3] += a4.w;
+                  } else {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                      if (nbase + j + jj < N) o[j + jj] += __ldg(ap + j + jj);
+                  }
+                }
+              }
+            }
           }
           if (ep.C) {
             float* c = ep.C + pr * ep.ldc + pc;
@@ -453,7 +475,7 @@ int launch_e(const TcMaps& mp, const TcEpilogue& ep, int64_t M, int64_t N, int64
 template <int BLOCK_N, bool A_MN, bool B_MN, int kStages, bool SPLIT>
 int launch_s(const TcMaps& mp, const TcEpilogue& ep, int64_t M, int64_t N, int64_t K, int splits,
              float* partial, cudaStream_t stream) {
-  const bool loads = ep.mask || ep.mask16 || ep.addend16;
+  const bool loads = ep.mask || ep.mask16 || ep.addend16 || ep.addend32;
   const bool arith = ep.bias || ep.relu || ep.scale != 1.0f;
   if (loads) return launch_e<BLOCK_N, A_MN, B_MN, kStages, 2, SPLIT>(mp, ep, M, N, K, splits, partial, stream);
   if (arith && !partial) return launch_e<BLOCK_N, A_MN, B_MN, kStages, 1, SPLIT>(mp, ep, M, N, K, splits, partial, stream);

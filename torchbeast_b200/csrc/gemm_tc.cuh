@@ -21,6 +21,7 @@ struct TcEpilogue {
   const float* mask = nullptr; int64_t ldmask = 0;   // out = (mask > 0) ? out : 0   (ReLU backward)
   const __nv_bfloat16* mask16 = nullptr;             // same, mask stored in bf16 (uses ldmask)
   const __nv_bfloat16* addend16 = nullptr; int64_t ldadd = 0;  // out += addend (residual connection), applied last
+  const float* addend32 = nullptr;                   // same, residual stored in fp32 (uses ldadd)
   int permP = 1, permQ = 1;                          // (split-K reduce only) weight-grad column un-pack
   int max_ctas = 0;                                  // > 0: cap the persistent grid (GEMMs running beside a cooperative kernel)
   const char* tag = "gemm_tc";

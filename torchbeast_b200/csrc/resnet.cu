@@ -72,6 +72,11 @@ struct ResWs {
   T *fcin, *dfc, *dfcin, *g[3], *col, *dcol;
   T *wfeat[kSections], *wblk[kSections][4], *wfc;
   float *core_in, *core_out, *dcore_out, *dcore_in, *splitk, *colsum_scratch;
+  // split-bf16 backend (precision 2): activations stay fp32; only the GEMM operands are bf16 hi / lo planes
+  // (lo plane = hi pointer + the *_lo element offset)
+  __nv_bfloat16 *colb = nullptr, *dyb = nullptr, *fcb = nullptr, *dfcb = nullptr;
+  __nv_bfloat16 *wb_feat[kSections] = {nullptr, nullptr, nullptr}, *wb_blk[kSections][4] = {}, *wb_fc = nullptr;
+  int64_t colb_lo = 0, dyb_lo = 0, fcb_lo = 0, dfcb_lo = 0, wb_feat_lo[kSections] = {0, 0, 0}, wb_blk_lo[kSections][4] = {}, wb_fc_lo = 0;
   LstmWs lstm;
   size_t bytes;
 };
@@ -79,7 +84,7 @@ struct ResWs {
 inline int64_t ldk_of(int cin, bool bf16) { const int64_t k = int64_t(cin) * 9; return bf16 ? ((k + 7) & ~int64_t(7)) : k; }
 
 template <typename T>
-ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lstm) {
+ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lstm, bool split = false) {
   constexpr bool kBf16 = !std::is_same<T, float>::value;
   ResWs<T> w;
   size_t off = 0;
@@ -103,7 +108,29 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
     if (a > maxcol) maxcol = a;
     if (b > maxcol) maxcol = b;
   }
-  w.col = takeT(maxcol); w.dcol = takeT(maxcol);
+  w.col = split ? nullptr : takeT(maxcol);   // (the split backend gathers into colb instead)
+  w.dcol = takeT(maxcol);
+  if (split) {
+    auto takeh = [&](int64_t n, int64_t& lo) {
+      lo = (n + 127) & ~int64_t(127);
+      return static_cast<__nv_bfloat16*>(take(size_t(2) * lo * sizeof(__nv_bfloat16)));
+    };
+    int64_t maxcol16 = 0;
+    for (int i = 0; i < kSections; ++i) {
+      const int64_t a = N * kSecS[i] * kSecS[i] * ldk_of(kSecCin[i], true), b = N * kSecSo[i] * kSecSo[i] * ldk_of(kSecCh[i], true);
+      if (a > maxcol16) maxcol16 = a;
+      if (b > maxcol16) maxcol16 = b;
+    }
+    w.colb = takeh(maxcol16, w.colb_lo);
+    w.dyb = takeh(maxact, w.dyb_lo);
+    w.fcb = takeh(N * kFcIn, w.fcb_lo);
+    w.dfcb = takeh(N * kFcOut, w.dfcb_lo);
+    for (int i = 0; i < kSections; ++i) {
+      w.wb_feat[i] = takeh(int64_t(kSecCh[i]) * ldk_of(kSecCin[i], true), w.wb_feat_lo[i]);
+      for (int j = 0; j < 4; ++j) w.wb_blk[i][j] = takeh(int64_t(kSecCh[i]) * ldk_of(kSecCh[i], true), w.wb_blk_lo[i][j]);
+    }
+    w.wb_fc = takeh(int64_t(kFcOut) * kFcIn, w.wb_fc_lo);
+  }
   for (int i = 0; i < kSections; ++i) {
     w.wfeat[i] = takeT(int64_t(kSecCh[i]) * ldk_of(kSecCin[i], kBf16));
     for (int j = 0; j < 4; ++j) w.wblk[i][j] = takeT(int64_t(kSecCh[i]) * ldk_of(kSecCh[i], kBf16));
@@ -116,8 +143,9 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
   w.splitk = takef(kScratchFloats);
   w.colsum_scratch = takef(colsum_scratch_floats(4 * kLstmH));
   if (use_lstm) {
-    const size_t lb = lstm_ws_bytes(T1, B, pp.core_in, kLstmH, 1, kBf16 ? 1 : 0);
-    w.lstm = lstm_ws(take(lb), T1, B, pp.core_in, kLstmH, 1, kBf16 ? 1 : 0);
+    const int lprec = split ? 2 : (kBf16 ? 1 : 0);
+    const size_t lb = lstm_ws_bytes(T1, B, pp.core_in, kLstmH, 1, lprec);
+    w.lstm = lstm_ws(take(lb), T1, B, pp.core_in, kLstmH, 1, lprec);
   } else {
     w.lstm = LstmWs();
   }
@@ -337,6 +365,167 @@ struct Impl {
   }
 };
 
+
+// ---- split-bf16 backend (precision 2) ----------------------------------------------------------------------
+// The fp32 data flow of Impl<float> (fp32 NHWC activations, fp32 gradients, the same pool / ReLU / col2im kernels)
+// with every GEMM on the tensor cores in split-bf16: the patch gather writes hi / lo bf16 planes, the weights are
+// packed as hi / lo planes, products are hi.hi + hi.lo + lo.hi in fp32 (~2^-17 relative per product: fp32-grade,
+// holds the 1e-4 parity contract that plain bf16 operands do not).
+struct SplitImpl {
+  using W = ResWs<float>;
+  static int gemm_fwd(const __nv_bfloat16* a, int64_t a_lo, const __nv_bfloat16* b, int64_t b_lo, float* out, int64_t M, int cout,
+                      int64_t K, int64_t ldk, const float* bias, const float* addend, float scale, int relu, int64_t ldc,
+                      const char* tag, cudaStream_t st) {
+    TcEpilogue te; te.C = out; te.ldc = ldc; te.bias = bias; te.relu = relu; te.addend32 = addend; te.ldadd = cout; te.scale = scale;
+    te.a_lo = a_lo; te.b_lo = b_lo; te.tag = tag;
+    return gemm_tc_bf16(a, b, M, cout, K, ldk, ldk, te, st);
+  }
+  // dcol[M, K] (fp32) = dY[M, cout] . W[cout, K]
+  static int gemm_dgrad(const __nv_bfloat16* dy, int64_t dy_lo, const __nv_bfloat16* wp, int64_t w_lo, float* dcol, int64_t M,
+                        int cout, int64_t K, int64_t ldk, const char* tag, cudaStream_t st) {
+    TcEpilogue te; te.C = dcol; te.ldc = K; te.a_lo = dy_lo; te.b_lo = w_lo; te.tag = tag;
+    return gemm_tc_bf16_ex(dy, wp, M, K, cout, cout, ldk, false, true, te, 1, nullptr, st);
+  }
+  // dW[cout, K] (fp32, un-packed by the split-K reduce) = scale * dY^T . col
+  static int gemm_wgrad(const __nv_bfloat16* dy, int64_t dy_lo, const __nv_bfloat16* col, int64_t col_lo, float* dW, int64_t M,
+                        int cout, int64_t K, int64_t ldk, int permP, int permQ, float scale, float* scratch, const char* tag,
+                        cudaStream_t st) {
+    TcEpilogue te; te.C = dW; te.ldc = K; te.permP = permP; te.permQ = permQ; te.scale = scale; te.a_lo = dy_lo; te.b_lo = col_lo;
+    te.tag = tag;
+    return gemm_tc_bf16_ex(dy, col, cout, K, M, cout, ldk, true, true, te, splits_tc(cout, K, M), scratch, st);
+  }
+  // the first conv's patches are uint8 pixels: exact in the hi plane, the lo plane is zero
+  static int first_patches(const uint8_t* frame, W& w, int64_t N, cudaStream_t st) {
+    const int S = kSecS[0];
+    const int64_t ldk = ldk_of(4, true);
+    TB_TRY(im2col3x3_u8_nchw<__nv_bfloat16>(frame, w.colb, N, 4, S, S, ldk, st));
+    cudaError_t e = cudaMemsetAsync(w.colb + w.colb_lo, 0, size_t(N) * S * S * ldk * sizeof(__nv_bfloat16), st);
+    TB_REQUIRE(e == cudaSuccess, "resnet: memset: %s", cudaGetErrorString(e));
+    return 0;
+  }
+
+  static int forward(const uint8_t* frame, const float* reward, const float* notdone, const float* h0, const float* c0,
+                     const float* P, int64_t T1, int64_t B, int A, int use_lstm, void* workspace, float* policy_logits,
+                     float* baseline, float* hN, float* cN, cudaStream_t st) {
+    const int64_t N = T1 * B;
+    const ResParams pp = res_params(A, use_lstm);
+    W w = res_ws<float>(workspace, N, T1, B, A, use_lstm, true);
+    TB_TRY(pack_weights_bf16(P + pp.feat[0].w, w.wb_feat[0], kSecCh[0], 1, 36, ldk_of(4, true), st, w.wb_feat_lo[0]));
+    for (int i = 0; i < kSections; ++i) {
+      if (i > 0)
+        TB_TRY(pack_weights_bf16(P + pp.feat[i].w, w.wb_feat[i], kSecCh[i], 9, kSecCin[i], ldk_of(kSecCin[i], true), st, w.wb_feat_lo[i]));
+      for (int j = 0; j < 4; ++j)
+        TB_TRY(pack_weights_bf16(P + pp.blk[i][j].w, w.wb_blk[i][j], kSecCh[i], 9, kSecCh[i], ldk_of(kSecCh[i], true), st, w.wb_blk_lo[i][j]));
+    }
+    TB_TRY(pack_weights_bf16(P + pp.fc_w, w.wb_fc, kFcOut, 121, 32, kFcIn, st, w.wb_fc_lo));
+    const float* xin = nullptr;
+    for (int i = 0; i < kSections; ++i) {
+      const int S = kSecS[i], So = kSecSo[i], ch = kSecCh[i], cin = kSecCin[i];
+      const int64_t M = N * S * S, Mo = N * So * So;
+      const int64_t ldk_in = ldk_of(cin, true), ldk = ldk_of(ch, true);
+      if (i == 0) {
+        TB_TRY(first_patches(frame, w, N, st));
+        TB_TRY(gemm_fwd(w.colb, w.colb_lo, w.wb_feat[0], w.wb_feat_lo[0], w.s[0].P, M, ch, 36, ldk_in, P + pp.feat[0].b, nullptr,
+                        1.0f / 255.0f, 0, ch, "feat_conv_fwd", st));
+      } else {
+        TB_TRY(im2col3x3_split(xin, w.colb, w.colb_lo, N, S, S, cin, ldk_in, 0, st));
+        TB_TRY(gemm_fwd(w.colb, w.colb_lo, w.wb_feat[i], w.wb_feat_lo[i], w.s[i].P, M, ch, int64_t(cin) * 9, ldk_in,
+                        P + pp.feat[i].b, nullptr, 1.0f, 0, ch, "feat_conv_fwd", st));
+      }
+      TB_TRY(maxpool3x3s2_fwd<float>(w.s[i].P, w.s[i].X0, w.s[i].arg, N, S, S, ch, st));
+      const float* ins[4] = {w.s[i].X0, w.s[i].Y1, w.s[i].X1, w.s[i].Y2};
+      float* outs[4] = {w.s[i].Y1, w.s[i].X1, w.s[i].Y2, w.s[i].X2};
+      const float* adds[4] = {nullptr, w.s[i].X0, nullptr, w.s[i].X1};
+      for (int j = 0; j < 4; ++j) {
+        TB_TRY(im2col3x3_split(ins[j], w.colb, w.colb_lo, N, So, So, ch, ldk, 1, st));
+        TB_TRY(gemm_fwd(w.colb, w.colb_lo, w.wb_blk[i][j], w.wb_blk_lo[i][j], outs[j], Mo, ch, int64_t(ch) * 9, ldk,
+                        P + pp.blk[i][j].b, adds[j], 1.0f, 0, ch, "res_conv_fwd", st));
+      }
+      xin = w.s[i].X2;
+    }
+    TB_TRY(relu_fwd<float>(w.s[2].X2, w.fcin, N * kFcIn, st));
+    TB_TRY(f32_to_bf16(w.fcin, w.fcb, N, kFcIn, kFcIn, kFcIn, st, w.fcb_lo));
+    TB_TRY(gemm_fwd(w.fcb, w.fcb_lo, w.wb_fc, w.wb_fc_lo, w.core_in, N, kFcOut, kFcIn, kFcIn, P + pp.fc_b, nullptr, 1.0f, 1,
+                    pp.core_in, "fc_fwd", st));
+    TB_TRY(core_extras(w.core_in, pp.core_in, N, kFcOut, reward, nullptr, 0, st));
+    if (use_lstm) {
+      LstmParams lp;
+      lp.w_ih[0] = P + pp.lstm[0]; lp.w_hh[0] = P + pp.lstm[1]; lp.b_ih[0] = P + pp.lstm[2]; lp.b_hh[0] = P + pp.lstm[3];
+      lp.w_ih[1] = lp.w_hh[1] = lp.b_ih[1] = lp.b_hh[1] = nullptr;
+      TB_TRY(lstm_forward(w.core_in, notdone, h0, c0, lp, T1, B, pp.core_in, kLstmH, 1, w.lstm, w.core_out, hN, cN, w.splitk, 2, st));
+    }
+    TB_TRY(heads_forward(w.core_out, pp.core_out, P + pp.policy_w, P + pp.policy_b, P + pp.baseline_w, P + pp.baseline_b, N,
+                         pp.core_out, A, policy_logits, baseline, st));
+    return 0;
+  }
+
+  static int conv_bwd(const float* x, bool relu_in, const float* dY, const __nv_bfloat16* wp, int64_t w_lo, float* dW, float* db,
+                      float* dx, const float* addend, int64_t N, int S, int cin, int cout, W& w, cudaStream_t st) {
+    const int64_t M = N * S * S, K = int64_t(cin) * 9, ldk = ldk_of(cin, true);
+    TB_TRY(colsum_t<float>(dY, db, M, cout, cout, w.colsum_scratch, st));
+    TB_TRY(f32_to_bf16(dY, w.dyb, M, cout, cout, cout, st, w.dyb_lo));
+    TB_TRY(im2col3x3_split(x, w.colb, w.colb_lo, N, S, S, cin, ldk, relu_in ? 1 : 0, st));
+    TB_TRY(gemm_wgrad(w.dyb, w.dyb_lo, w.colb, w.colb_lo, dW, M, cout, K, ldk, 9, cin, 1.0f, w.splitk, "res_conv_wgrad", st));
+    if (dx) {
+      TB_TRY(gemm_dgrad(w.dyb, w.dyb_lo, wp, w_lo, w.dcol, M, cout, K, ldk, "res_conv_dgrad", st));
+      TB_TRY(col2im3x3<float>(w.dcol, relu_in ? x : nullptr, addend, dx, N, S, S, cin, K, st));
+    }
+    return 0;
+  }
+
+  static int backward(const uint8_t* frame, const float* grad_logits, const float* grad_baseline, const float* notdone,
+                      const float* P, int64_t T1, int64_t B, int A, int use_lstm, void* workspace, float* G, cudaStream_t st) {
+    const int64_t N = T1 * B;
+    const ResParams pp = res_params(A, use_lstm);
+    W w = res_ws<float>(workspace, N, T1, B, A, use_lstm, true);
+    TB_TRY(heads_backward(w.core_out, pp.core_out, P + pp.policy_w, P + pp.baseline_w, grad_logits, grad_baseline, N, pp.core_out,
+                          A, w.dcore_out, pp.core_out, G + pp.policy_w, G + pp.policy_b, G + pp.baseline_w, G + pp.baseline_b,
+                          w.splitk, st));
+    if (use_lstm) {
+      LstmParams lp; LstmGrads lg;
+      lp.w_ih[0] = P + pp.lstm[0]; lp.w_hh[0] = P + pp.lstm[1]; lp.b_ih[0] = P + pp.lstm[2]; lp.b_hh[0] = P + pp.lstm[3];
+      lg.w_ih[0] = G + pp.lstm[0]; lg.w_hh[0] = G + pp.lstm[1]; lg.b_ih[0] = G + pp.lstm[2]; lg.b_hh[0] = G + pp.lstm[3];
+      lp.w_ih[1] = lp.w_hh[1] = lp.b_ih[1] = lp.b_hh[1] = nullptr;
+      lg.w_ih[1] = lg.w_hh[1] = lg.b_ih[1] = lg.b_hh[1] = nullptr;
+      TB_TRY(lstm_backward(w.dcore_out, w.core_in, notdone, lp, lg, T1, B, pp.core_in, kLstmH, 1, w.lstm, w.dcore_in, w.splitk,
+                           w.colsum_scratch, 2, st));
+    }
+    TB_TRY(relu_mask_inplace(w.dcore_in, w.core_in, N, kFcOut, pp.core_in, pp.core_in, st));
+    TB_TRY(colsum(w.dcore_in, G + pp.fc_b, N, kFcOut, pp.core_in, w.colsum_scratch, st));
+    TB_TRY(f32_to_bf16(w.dcore_in, w.dfcb, N, kFcOut, pp.core_in, kFcOut, st, w.dfcb_lo));
+    // (fcb still holds relu(X2) as hi / lo planes from the forward pass)
+    TB_TRY(gemm_wgrad(w.dfcb, w.dfcb_lo, w.fcb, w.fcb_lo, G + pp.fc_w, N, kFcOut, kFcIn, kFcIn, 121, 32, 1.0f, w.splitk, "fc_wgrad", st));
+    {
+      TcEpilogue te; te.C = w.dfcin; te.ldc = kFcIn; te.a_lo = w.dfcb_lo; te.b_lo = w.wb_fc_lo; te.tag = "fc_dgrad";
+      TB_TRY(gemm_tc_bf16_ex(w.dfcb, w.wb_fc, N, kFcIn, kFcOut, kFcOut, kFcIn, false, true, te, 1, nullptr, st));
+    }
+    float* g0 = w.g[0]; float* g1 = w.g[1]; float* g2 = w.g[2];
+    TB_TRY(relu_bwd<float>(w.s[2].X2, w.dfcin, g0, N * kFcIn, st));
+    for (int i = kSections - 1; i >= 0; --i) {
+      const int S = kSecS[i], So = kSecSo[i], ch = kSecCh[i], cin = kSecCin[i];
+      Sec<float>& s = w.s[i];
+      TB_TRY(conv_bwd(s.Y2, true, g0, w.wb_blk[i][3], w.wb_blk_lo[i][3], G + pp.blk[i][3].w, G + pp.blk[i][3].b, g1, nullptr, N, So, ch, ch, w, st));
+      TB_TRY(conv_bwd(s.X1, true, g1, w.wb_blk[i][2], w.wb_blk_lo[i][2], G + pp.blk[i][2].w, G + pp.blk[i][2].b, g2, g0, N, So, ch, ch, w, st));
+      TB_TRY(conv_bwd(s.Y1, true, g2, w.wb_blk[i][1], w.wb_blk_lo[i][1], G + pp.blk[i][1].w, G + pp.blk[i][1].b, g0, nullptr, N, So, ch, ch, w, st));
+      TB_TRY(conv_bwd(s.X0, true, g0, w.wb_blk[i][0], w.wb_blk_lo[i][0], G + pp.blk[i][0].w, G + pp.blk[i][0].b, g1, g2, N, So, ch, ch, w, st));
+      TB_TRY(maxpool3x3s2_bwd<float>(s.arg, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
+      const int64_t M = N * S * S;
+      if (i == 0) {
+        const int64_t ldk_in = ldk_of(4, true);
+        TB_TRY(colsum_t<float>(g2, G + pp.feat[0].b, M, ch, ch, w.colsum_scratch, st));
+        TB_TRY(f32_to_bf16(g2, w.dyb, M, ch, ch, ch, st, w.dyb_lo));
+        TB_TRY(first_patches(frame, w, N, st));
+        TB_TRY(gemm_wgrad(w.dyb, w.dyb_lo, w.colb, w.colb_lo, G + pp.feat[0].w, M, ch, 36, ldk_in, 1, 1, 1.0f / 255.0f, w.splitk,
+                          "feat_conv_wgrad", st));
+      } else {
+        TB_TRY(conv_bwd(w.s[i - 1].X2, false, g2, w.wb_feat[i], w.wb_feat_lo[i], G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S,
+                        cin, ch, w, st));
+      }
+    }
+    return 0;
+  }
+};
+
 }  // namespace
 }  // namespace tb
 
@@ -347,6 +536,7 @@ extern "C" {
 int64_t tb_resnet_param_count(int num_actions, int use_lstm) { return res_params(num_actions, use_lstm).total; }
 
 size_t tb_resnet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm, int precision) {
+  if (precision == 2) return res_ws<float>(nullptr, T1 * B, T1, B, num_actions, use_lstm, true).bytes;
   return precision ? res_ws<__nv_bfloat16>(nullptr, T1 * B, T1, B, num_actions, use_lstm).bytes
                    : res_ws<float>(nullptr, T1 * B, T1, B, num_actions, use_lstm).bytes;
 }
@@ -357,7 +547,10 @@ int tb_resnet_forward(const uint8_t* frame, const float* reward, const float* no
   TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "resnet_forward: bad sizes");
   TB_REQUIRE(frame && reward && params && workspace && policy_logits && baseline, "resnet_forward: null pointer");
   TB_REQUIRE(!use_lstm || (notdone && h0 && c0 && hN && cN), "resnet_forward: LSTM needs notdone/h0/c0/hN/cN");
-  TB_REQUIRE(precision == 0 || precision == 1, "resnet_forward: precision must be 0 or 1");
+  TB_REQUIRE(precision >= 0 && precision <= 2, "resnet_forward: precision must be 0 (fp32), 1 (bf16) or 2 (split-bf16)");
+  if (precision == 2)
+    return SplitImpl::forward(frame, reward, notdone, h0, c0, params, T1, B, num_actions, use_lstm, workspace, policy_logits,
+                              baseline, hN, cN, (cudaStream_t)stream);
   if (precision)
     return Impl<__nv_bfloat16>::forward(frame, reward, notdone, h0, c0, params, T1, B, num_actions, use_lstm, workspace,
                                         policy_logits, baseline, hN, cN, (cudaStream_t)stream);
@@ -371,6 +564,10 @@ int tb_resnet_backward(const uint8_t* frame, const float* grad_logits, const flo
   TB_REQUIRE(T1 >= 1 && B >= 1 && num_actions >= 1, "resnet_backward: bad sizes");
   TB_REQUIRE(frame && grad_logits && grad_baseline && params && workspace && grads, "resnet_backward: null pointer");
   TB_REQUIRE(!use_lstm || notdone, "resnet_backward: LSTM needs notdone");
+  TB_REQUIRE(precision >= 0 && precision <= 2, "resnet_backward: precision must be 0, 1 or 2");
+  if (precision == 2)
+    return SplitImpl::backward(frame, grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm, workspace,
+                               grads, (cudaStream_t)stream);
   if (precision)
     return Impl<__nv_bfloat16>::backward(frame, grad_logits, grad_baseline, notdone, params, T1, B, num_actions, use_lstm,
                                          workspace, grads, (cudaStream_t)stream);

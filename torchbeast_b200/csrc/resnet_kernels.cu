@@ -3,6 +3,7 @@
 
 #include "gemm_tc.cuh"
 #include "net_kernels.cuh"
+#include "tc_common.cuh"
 
 namespace tb {
 
@@ -55,6 +56,50 @@ int im2col3x3(const T* x, T* col, int64_t N, int H, int W, int C, int64_t ldk, i
 }
 template int im2col3x3<float>(const float*, float*, int64_t, int, int, int, int64_t, int, cudaStream_t);
 template int im2col3x3<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int64_t, int, int, int, int64_t, int, cudaStream_t);
+
+// fp32 activations -> split-bf16 patch matrix (hi plane at col, lo plane at col + lo_off): one thread = 8 channels of
+// one (pixel, tap), two 16-byte stores
+__global__ void im2col3x3_split_kernel(const float4* __restrict__ x, __nv_bfloat16* __restrict__ col, int64_t lo_off, int64_t N,
+                                       int H, int W, int C8, int64_t ldk, int relu_in) {
+  const int64_t total = N * H * W * 9 * C8;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int cv = int(i % C8);
+    int64_t t = i / C8;
+    const int tap = int(t % 9); t /= 9;
+    const int ox = int(t % W); t /= W;
+    const int oy = int(t % H);
+    const int64_t n = t / H;
+    const int iy = oy + tap / 3 - 1, ix = ox + tap % 3 - 1;
+    float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const float4* src = x + (((n * H + iy) * W + ix) * C8 + cv) * 2;
+      const float4 a = __ldg(src), b = __ldg(src + 1);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      if (relu_in) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.0f);
+      }
+    }
+    uint4 ph, pl;
+    tcd::split_bf16x2(f[0], f[1], ph.x, pl.x); tcd::split_bf16x2(f[2], f[3], ph.y, pl.y);
+    tcd::split_bf16x2(f[4], f[5], ph.z, pl.z); tcd::split_bf16x2(f[6], f[7], ph.w, pl.w);
+    __nv_bfloat16* dst = col + ((n * H + oy) * W + ox) * ldk + int64_t(tap) * C8 * 8 + cv * 8;
+    *reinterpret_cast<uint4*>(dst) = ph;
+    *reinterpret_cast<uint4*>(dst + lo_off) = pl;
+  }
+}
+
+int im2col3x3_split(const float* x, __nv_bfloat16* col, int64_t lo_off, int64_t N, int H, int W, int C, int64_t ldk, int relu_in,
+                    cudaStream_t stream) {
+  ProfScope prof("im2col3x3", stream);
+  TB_REQUIRE(C % 8 == 0 && ldk % 8 == 0 && lo_off % 8 == 0, "im2col3x3_split: C, ldk and the plane offset must be multiples of 8");
+  const int64_t total = N * H * W * 9 * (C / 8);
+  if (total == 0) return 0;
+  im2col3x3_split_kernel<<<rgrid(total, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), col, lo_off, N, H, W, C / 8,
+                                                               ldk, relu_in);
+  return check_launch("im2col3x3_split_kernel");
+}
 
 template <typename TOut> __device__ __forceinline__ TOut from_u8(uint8_t v);
 template <> __device__ __forceinline__ uint8_t from_u8<uint8_t>(uint8_t v) { return v; }

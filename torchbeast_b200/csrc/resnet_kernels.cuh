@@ -40,6 +40,10 @@ template <> struct Vec16<__nv_bfloat16> {
 template <typename T>
 int im2col3x3(const T* x, T* col, int64_t N, int H, int W, int C, int64_t ldk, int relu_in, cudaStream_t stream);
 
+// split-bf16 backend: fp32 activations -> patch matrix as bf16 hi / lo planes (lo plane at col + lo_off elements)
+int im2col3x3_split(const float* x, __nv_bfloat16* col, int64_t lo_off, int64_t N, int H, int W, int C, int64_t ldk, int relu_in,
+                    cudaStream_t stream);
+
 // first conv of the net: frames u8 NCHW [N,C,H,W] -> patch matrix, k = (c*3 + kh)*3 + kw (the reference
 // weight's own flattening).  TOut = uint8_t (fp32 backend: x/255 applied on read) or bf16 (exact 0..255).
 template <typename TOut>

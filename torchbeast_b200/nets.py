@@ -420,7 +420,7 @@ class ResNet(FlatParamModule):
     conv3x3 + maxpool3/2 + two residual blocks, fc 3872->256, cat[reward], optional LSTM(257->256), heads.
     forward(inputs, core_state) returns ((action, policy_logits, baseline), core_state) like the reference."""
 
-    PRECISIONS = {"fp32": 0, "bf16": 1}
+    PRECISIONS = {"fp32": 0, "bf16": 1, "bf16x3": 2}
 
     def __init__(self, num_actions, use_lstm=False, device=None, precision=None):
         super().__init__()
@@ -434,10 +434,11 @@ class ResNet(FlatParamModule):
         self.reset_parameters_like_torch()
         if use_lstm:
             self.core.num_layers, self.core.hidden_size, self.core.input_size = 1, 256, 257
-        # the ResNet trunk still runs on patch-matrix GEMMs: fp32 (parity, default) or single-plane bf16
-        self.precision = precision or os.environ.get("TB_RESNET_PRECISION", "fp32")
+        # patch-matrix GEMMs: "bf16x3" (default: split-bf16 tensor-core products over fp32 activations, parity-green),
+        # "fp32" (SIMT) or "bf16" (single-plane operands and activations, not parity-grade)
+        self.precision = precision or os.environ.get("TB_RESNET_PRECISION", "bf16x3")
         if self.precision not in self.PRECISIONS:
-            raise _lib.TorchBeastB200Error("ResNet precision must be 'fp32' or 'bf16'")
+            raise _lib.TorchBeastB200Error("ResNet precision must be 'fp32', 'bf16' or 'bf16x3'")
         self._ws = None
         self._ws_key = None
         count = _lib.lib().tb_resnet_param_count(num_actions, int(use_lstm))
