@@ -322,9 +322,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if constexpr (EPI >= 2) {
             if (ep.mask) {
+              const float* mp = ep.mask + pr * ep.ldmask + pc;
+              const bool mvec = (ep.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(mp) & 15) == 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nbase + j < N) o[j] = (ep.mask[pr * ep.ldmask + pc + j] > 0.0f) ? o[j] : 0.0f;
+              for (int j = 0; j < 32; j += 4) {
+                if (mvec && nbase + j + 4 <= N) {
+                  const float4 m4 = __ldg(reinterpret_cast<const float4*>(mp + j));
+                  o[j] = m4.x > 0.0f ? o[j] : 0.0f; o[j + 1] = m4.y > 0.0f ? o[j + 1] : 0.0f;
+                  o[j + 2] = m4.z > 0.0f ? o[j + 2] : 0.0f; o[j + 3] = m4.w > 0.0f ? o[j + 3] : 0.0f;
+                } else {
+#pragma unroll
+                  for (int jj = 0; jj < 4; ++jj)
+                    if (nbase + j + jj < N) o[j + jj] = (mp[j + jj] > 0.0f) ? o[j + jj] : 0.0f;
+                }
+              }
             }
             if (vm) {  // a bf16 is positive iff its bit pattern, read as a signed 16-bit integer, is > 0
 #pragma unroll

@@ -75,11 +75,23 @@ struct ResWs {
   // split-bf16 backend (precision 2): activations stay fp32; only the GEMM operands are bf16 hi / lo planes
   // (lo plane = hi pointer + the *_lo element offset)
   __nv_bfloat16 *colb = nullptr, *dyb = nullptr, *fcb = nullptr, *dfcb = nullptr;
+  // patch matrices of the 15 convolutions kept from the forward pass for the weight-gradient GEMMs (5.6 GB at T=80, B=8:
+  // HBM is 180 GB; TB_RESNET_KEEP_PATCHES=0 gathers them again in the backward pass instead), and the flipped /
+  // transposed weights of the input-gradient convolutions
+  __nv_bfloat16 *colk_feat[kSections] = {nullptr, nullptr, nullptr}, *colk_blk[kSections][4] = {};
+  int64_t colk_feat_lo[kSections] = {0, 0, 0}, colk_blk_lo[kSections][4] = {};
+  __nv_bfloat16 *wd_feat[kSections] = {nullptr, nullptr, nullptr}, *wd_blk[kSections][4] = {};
+  int64_t wd_feat_lo[kSections] = {0, 0, 0}, wd_blk_lo[kSections][4] = {};
   __nv_bfloat16 *wb_feat[kSections] = {nullptr, nullptr, nullptr}, *wb_blk[kSections][4] = {}, *wb_fc = nullptr;
   int64_t colb_lo = 0, dyb_lo = 0, fcb_lo = 0, dfcb_lo = 0, wb_feat_lo[kSections] = {0, 0, 0}, wb_blk_lo[kSections][4] = {}, wb_fc_lo = 0;
   LstmWs lstm;
   size_t bytes;
 };
+
+inline bool keep_patches() {
+  const char* e = getenv("TB_RESNET_KEEP_PATCHES");
+  return !(e && e[0] == '0');
+}
 
 inline int64_t ldk_of(int cin, bool bf16) { const int64_t k = int64_t(cin) * 9; return bf16 ? ((k + 7) & ~int64_t(7)) : k; }
 
@@ -118,8 +130,10 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
     int64_t maxcol16 = 0;
     for (int i = 0; i < kSections; ++i) {
       const int64_t a = N * kSecS[i] * kSecS[i] * ldk_of(kSecCin[i], true), b = N * kSecSo[i] * kSecSo[i] * ldk_of(kSecCh[i], true);
+      const int64_t c = i > 0 ? N * kSecS[i] * kSecS[i] * 9 * kSecCh[i] : 0;   // patches of dY (input gradient of the feat conv)
       if (a > maxcol16) maxcol16 = a;
       if (b > maxcol16) maxcol16 = b;
+      if (c > maxcol16) maxcol16 = c;
     }
     w.colb = takeh(maxcol16, w.colb_lo);
     w.dyb = takeh(maxact, w.dyb_lo);
@@ -130,6 +144,16 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
       for (int j = 0; j < 4; ++j) w.wb_blk[i][j] = takeh(int64_t(kSecCh[i]) * ldk_of(kSecCh[i], true), w.wb_blk_lo[i][j]);
     }
     w.wb_fc = takeh(int64_t(kFcOut) * kFcIn, w.wb_fc_lo);
+    for (int i = 0; i < kSections; ++i) {
+      if (i > 0) w.wd_feat[i] = takeh(int64_t(kSecCin[i]) * 9 * kSecCh[i], w.wd_feat_lo[i]);
+      for (int j = 0; j < 4; ++j) w.wd_blk[i][j] = takeh(int64_t(kSecCh[i]) * 9 * kSecCh[i], w.wd_blk_lo[i][j]);
+    }
+    if (keep_patches()) {
+      for (int i = 0; i < kSections; ++i) {
+        w.colk_feat[i] = takeh(N * kSecS[i] * kSecS[i] * ldk_of(kSecCin[i], true), w.colk_feat_lo[i]);
+        for (int j = 0; j < 4; ++j) w.colk_blk[i][j] = takeh(N * kSecSo[i] * kSecSo[i] * ldk_of(kSecCh[i], true), w.colk_blk_lo[i][j]);
+      }
+    }
   }
   for (int i = 0; i < kSections; ++i) {
     w.wfeat[i] = takeT(int64_t(kSecCh[i]) * ldk_of(kSecCin[i], kBf16));
@@ -380,12 +404,6 @@ struct SplitImpl {
     te.a_lo = a_lo; te.b_lo = b_lo; te.tag = tag;
     return gemm_tc_bf16(a, b, M, cout, K, ldk, ldk, te, st);
   }
-  // dcol[M, K] (fp32) = dY[M, cout] . W[cout, K]
-  static int gemm_dgrad(const __nv_bfloat16* dy, int64_t dy_lo, const __nv_bfloat16* wp, int64_t w_lo, float* dcol, int64_t M,
-                        int cout, int64_t K, int64_t ldk, const char* tag, cudaStream_t st) {
-    TcEpilogue te; te.C = dcol; te.ldc = K; te.a_lo = dy_lo; te.b_lo = w_lo; te.tag = tag;
-    return gemm_tc_bf16_ex(dy, wp, M, K, cout, cout, ldk, false, true, te, 1, nullptr, st);
-  }
   // dW[cout, K] (fp32, un-packed by the split-K reduce) = scale * dY^T . col
   static int gemm_wgrad(const __nv_bfloat16* dy, int64_t dy_lo, const __nv_bfloat16* col, int64_t col_lo, float* dW, int64_t M,
                         int cout, int64_t K, int64_t ldk, int permP, int permQ, float scale, float* scratch, const char* tag,
@@ -395,11 +413,11 @@ struct SplitImpl {
     return gemm_tc_bf16_ex(dy, col, cout, K, M, cout, ldk, true, true, te, splits_tc(cout, K, M), scratch, st);
   }
   // the first conv's patches are uint8 pixels: exact in the hi plane, the lo plane is zero
-  static int first_patches(const uint8_t* frame, W& w, int64_t N, cudaStream_t st) {
+  static int first_patches(const uint8_t* frame, __nv_bfloat16* col, int64_t col_lo, int64_t N, cudaStream_t st) {
     const int S = kSecS[0];
     const int64_t ldk = ldk_of(4, true);
-    TB_TRY(im2col3x3_u8_nchw<__nv_bfloat16>(frame, w.colb, N, 4, S, S, ldk, st));
-    cudaError_t e = cudaMemsetAsync(w.colb + w.colb_lo, 0, size_t(N) * S * S * ldk * sizeof(__nv_bfloat16), st);
+    TB_TRY(im2col3x3_u8_nchw<__nv_bfloat16>(frame, col, N, 4, S, S, ldk, st));
+    cudaError_t e = cudaMemsetAsync(col + col_lo, 0, size_t(N) * S * S * ldk * sizeof(__nv_bfloat16), st);
     TB_REQUIRE(e == cudaSuccess, "resnet: memset: %s", cudaGetErrorString(e));
     return 0;
   }
@@ -423,13 +441,15 @@ struct SplitImpl {
       const int S = kSecS[i], So = kSecSo[i], ch = kSecCh[i], cin = kSecCin[i];
       const int64_t M = N * S * S, Mo = N * So * So;
       const int64_t ldk_in = ldk_of(cin, true), ldk = ldk_of(ch, true);
+      __nv_bfloat16* cf = w.colk_feat[i] ? w.colk_feat[i] : w.colb;
+      const int64_t cf_lo = w.colk_feat[i] ? w.colk_feat_lo[i] : w.colb_lo;
       if (i == 0) {
-        TB_TRY(first_patches(frame, w, N, st));
-        TB_TRY(gemm_fwd(w.colb, w.colb_lo, w.wb_feat[0], w.wb_feat_lo[0], w.s[0].P, M, ch, 36, ldk_in, P + pp.feat[0].b, nullptr,
+        TB_TRY(first_patches(frame, cf, cf_lo, N, st));
+        TB_TRY(gemm_fwd(cf, cf_lo, w.wb_feat[0], w.wb_feat_lo[0], w.s[0].P, M, ch, 36, ldk_in, P + pp.feat[0].b, nullptr,
                         1.0f / 255.0f, 0, ch, "feat_conv_fwd", st));
       } else {
-        TB_TRY(im2col3x3_split(xin, w.colb, w.colb_lo, N, S, S, cin, ldk_in, 0, st));
-        TB_TRY(gemm_fwd(w.colb, w.colb_lo, w.wb_feat[i], w.wb_feat_lo[i], w.s[i].P, M, ch, int64_t(cin) * 9, ldk_in,
+        TB_TRY(im2col3x3_split(xin, cf, cf_lo, N, S, S, cin, ldk_in, 0, st));
+        TB_TRY(gemm_fwd(cf, cf_lo, w.wb_feat[i], w.wb_feat_lo[i], w.s[i].P, M, ch, int64_t(cin) * 9, ldk_in,
                         P + pp.feat[i].b, nullptr, 1.0f, 0, ch, "feat_conv_fwd", st));
       }
       TB_TRY(maxpool3x3s2_fwd<float>(w.s[i].P, w.s[i].X0, w.s[i].arg, N, S, S, ch, st));
@@ -437,8 +457,10 @@ struct SplitImpl {
       float* outs[4] = {w.s[i].Y1, w.s[i].X1, w.s[i].Y2, w.s[i].X2};
       const float* adds[4] = {nullptr, w.s[i].X0, nullptr, w.s[i].X1};
       for (int j = 0; j < 4; ++j) {
-        TB_TRY(im2col3x3_split(ins[j], w.colb, w.colb_lo, N, So, So, ch, ldk, 1, st));
-        TB_TRY(gemm_fwd(w.colb, w.colb_lo, w.wb_blk[i][j], w.wb_blk_lo[i][j], outs[j], Mo, ch, int64_t(ch) * 9, ldk,
+        __nv_bfloat16* cb = w.colk_blk[i][j] ? w.colk_blk[i][j] : w.colb;
+        const int64_t cb_lo = w.colk_blk[i][j] ? w.colk_blk_lo[i][j] : w.colb_lo;
+        TB_TRY(im2col3x3_split(ins[j], cb, cb_lo, N, So, So, ch, ldk, 1, st));
+        TB_TRY(gemm_fwd(cb, cb_lo, w.wb_blk[i][j], w.wb_blk_lo[i][j], outs[j], Mo, ch, int64_t(ch) * 9, ldk,
                         P + pp.blk[i][j].b, adds[j], 1.0f, 0, ch, "res_conv_fwd", st));
       }
       xin = w.s[i].X2;
@@ -459,16 +481,27 @@ struct SplitImpl {
     return 0;
   }
 
-  static int conv_bwd(const float* x, bool relu_in, const float* dY, const __nv_bfloat16* wp, int64_t w_lo, float* dW, float* db,
-                      float* dx, const float* addend, int64_t N, int S, int cin, int cout, W& w, cudaStream_t st) {
+  // one 3x3 conv backward.  Bias gradient + the bf16 planes of dY in one pass; weight gradient against the patch matrix
+  // kept from the forward pass (colk; nullptr = gather it again); input gradient as a CONVOLUTION of dY with the flipped /
+  // transposed weights (wd) - patches of dY, one GEMM with N = cin whose epilogue applies the ReLU mask of the conv's input
+  // and adds the skip gradient: no [M, 9*cin] fp32 gradient patch matrix, no col2im pass.
+  static int conv_bwd(const float* x, bool relu_in, const float* dY, const float* Wsrc, const __nv_bfloat16* colk, int64_t colk_lo,
+                      __nv_bfloat16* wd, int64_t wd_lo, float* dW, float* db, float* dx, const float* addend, int64_t N, int S,
+                      int cin, int cout, W& w, cudaStream_t st) {
     const int64_t M = N * S * S, K = int64_t(cin) * 9, ldk = ldk_of(cin, true);
-    TB_TRY(colsum_t<float>(dY, db, M, cout, cout, w.colsum_scratch, st));
-    TB_TRY(f32_to_bf16(dY, w.dyb, M, cout, cout, cout, st, w.dyb_lo));
-    TB_TRY(im2col3x3_split(x, w.colb, w.colb_lo, N, S, S, cin, ldk, relu_in ? 1 : 0, st));
-    TB_TRY(gemm_wgrad(w.dyb, w.dyb_lo, w.colb, w.colb_lo, dW, M, cout, K, ldk, 9, cin, 1.0f, w.splitk, "res_conv_wgrad", st));
+    TB_TRY(dy_split_colsum(dY, w.dyb, w.dyb_lo, M, cout, db, w.splitk, kScratchFloats, st));
+    if (!colk) {
+      TB_TRY(im2col3x3_split(x, w.colb, w.colb_lo, N, S, S, cin, ldk, relu_in ? 1 : 0, st));
+      colk = w.colb; colk_lo = w.colb_lo;
+    }
+    TB_TRY(gemm_wgrad(w.dyb, w.dyb_lo, colk, colk_lo, dW, M, cout, K, ldk, 9, cin, 1.0f, w.splitk, "res_conv_wgrad", st));
     if (dx) {
-      TB_TRY(gemm_dgrad(w.dyb, w.dyb_lo, wp, w_lo, w.dcol, M, cout, K, ldk, "res_conv_dgrad", st));
-      TB_TRY(col2im3x3<float>(w.dcol, relu_in ? x : nullptr, addend, dx, N, S, S, cin, K, st));
+      const int64_t Kd = int64_t(cout) * 9;
+      TB_TRY(pack_dgrad3x3_weights(Wsrc, wd, wd_lo, cout, cin, Kd, st));
+      TB_TRY(im2col3x3_split(dY, w.colb, w.colb_lo, N, S, S, cout, Kd, 0, st));
+      TcEpilogue te; te.C = dx; te.ldc = cin; te.addend32 = addend; te.ldadd = cin; te.mask = relu_in ? x : nullptr; te.ldmask = cin;
+      te.a_lo = w.colb_lo; te.b_lo = wd_lo; te.tag = "res_conv_dgrad";
+      TB_TRY(gemm_tc_bf16(w.colb, wd, M, cin, Kd, Kd, Kd, te, st));
     }
     return 0;
   }
@@ -504,22 +537,29 @@ struct SplitImpl {
     for (int i = kSections - 1; i >= 0; --i) {
       const int S = kSecS[i], So = kSecSo[i], ch = kSecCh[i], cin = kSecCin[i];
       Sec<float>& s = w.s[i];
-      TB_TRY(conv_bwd(s.Y2, true, g0, w.wb_blk[i][3], w.wb_blk_lo[i][3], G + pp.blk[i][3].w, G + pp.blk[i][3].b, g1, nullptr, N, So, ch, ch, w, st));
-      TB_TRY(conv_bwd(s.X1, true, g1, w.wb_blk[i][2], w.wb_blk_lo[i][2], G + pp.blk[i][2].w, G + pp.blk[i][2].b, g2, g0, N, So, ch, ch, w, st));
-      TB_TRY(conv_bwd(s.Y1, true, g2, w.wb_blk[i][1], w.wb_blk_lo[i][1], G + pp.blk[i][1].w, G + pp.blk[i][1].b, g0, nullptr, N, So, ch, ch, w, st));
-      TB_TRY(conv_bwd(s.X0, true, g0, w.wb_blk[i][0], w.wb_blk_lo[i][0], G + pp.blk[i][0].w, G + pp.blk[i][0].b, g1, g2, N, So, ch, ch, w, st));
+      const float* xs[4] = {s.X0, s.Y1, s.X1, s.Y2};
+      const float* dys[4] = {g0, g2, g1, g0};       // dL/d(conv output) of r1a, r1b, r2a, r2b
+      float* dxs[4] = {g1, g0, g2, g1};
+      const float* skip[4] = {g2, nullptr, g0, nullptr};
+      for (int j = 3; j >= 0; --j)
+        TB_TRY(conv_bwd(xs[j], true, dys[j], P + pp.blk[i][j].w, w.colk_blk[i][j], w.colk_blk_lo[i][j], w.wd_blk[i][j], w.wd_blk_lo[i][j],
+                        G + pp.blk[i][j].w, G + pp.blk[i][j].b, dxs[j], skip[j], N, So, ch, ch, w, st));
       TB_TRY(maxpool3x3s2_bwd<float>(s.arg, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
       const int64_t M = N * S * S;
       if (i == 0) {
         const int64_t ldk_in = ldk_of(4, true);
-        TB_TRY(colsum_t<float>(g2, G + pp.feat[0].b, M, ch, ch, w.colsum_scratch, st));
-        TB_TRY(f32_to_bf16(g2, w.dyb, M, ch, ch, ch, st, w.dyb_lo));
-        TB_TRY(first_patches(frame, w, N, st));
-        TB_TRY(gemm_wgrad(w.dyb, w.dyb_lo, w.colb, w.colb_lo, G + pp.feat[0].w, M, ch, 36, ldk_in, 1, 1, 1.0f / 255.0f, w.splitk,
+        TB_TRY(dy_split_colsum(g2, w.dyb, w.dyb_lo, M, ch, G + pp.feat[0].b, w.splitk, kScratchFloats, st));
+        const __nv_bfloat16* cf = w.colk_feat[0];
+        int64_t cf_lo = w.colk_feat_lo[0];
+        if (!cf) {
+          TB_TRY(first_patches(frame, w.colb, w.colb_lo, N, st));
+          cf = w.colb; cf_lo = w.colb_lo;
+        }
+        TB_TRY(gemm_wgrad(w.dyb, w.dyb_lo, cf, cf_lo, G + pp.feat[0].w, M, ch, 36, ldk_in, 1, 1, 1.0f / 255.0f, w.splitk,
                           "feat_conv_wgrad", st));
       } else {
-        TB_TRY(conv_bwd(w.s[i - 1].X2, false, g2, w.wb_feat[i], w.wb_feat_lo[i], G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S,
-                        cin, ch, w, st));
+        TB_TRY(conv_bwd(w.s[i - 1].X2, false, g2, P + pp.feat[i].w, w.colk_feat[i], w.colk_feat_lo[i], w.wd_feat[i], w.wd_feat_lo[i],
+                        G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S, cin, ch, w, st));
       }
     }
     return 0;
