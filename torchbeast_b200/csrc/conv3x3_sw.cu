@@ -1,0 +1,589 @@
+// Shifted-window implicit-GEMM 3x3 convolutions (stride 1, pad 1) of the IMPALA ResNet trunk on tcgen05
+// (reference: /root/reference/torchbeast/polybeast_learner.py:141-199, nn.Conv2d(kernel_size=3, stride=1, padding=1)).
+//
+// These convolutions have 16 / 32 channels: as GEMMs they are [pixels, 9*C] x [9*C, 16..32] - the A stream is everything.
+// A patch matrix (or a per-tap TMA box) moves every input element 9-12 times through the TMA -> shared-memory path, and
+// that path (~45-70 B/clk per SM measured), not HBM and not the tensor pipe, bounded the patch-matrix kernels (3.4-3.7 TB/s
+// aggregate).  Here the image is stored as zero-padded CHANNEL-CHUNK PLANES [frame][C/8][(H+2)*(W+2)][8] (split-bf16: hi
+// and lo planes).  A tile = 128 consecutive flattened padded pixels of one frame; its input window (128 + 2*(W+2) + 2
+// pixels of every chunk plane) is ONE contiguous 1-D bulk copy per plane.  In shared memory a chunk plane is a K-major
+// no-swizzle UMMA operand as it stands - row = pixel, 16 bytes = 8 channels, rows 16 bytes apart (canonical layout
+// ((8,n),2):((1,SBO),LBO) in 16-byte units with SBO = 8 and LBO = the chunk-plane pitch) - and the operand of tap (kh, kw)
+// is the same rows shifted by (kh*(W+2) + kw)*16 bytes: 9 descriptors over one copy of the data.  Output rows that fall on
+// padding columns / rows are computed and dropped by the epilogue (2/(W+2) of the tile).
+//
+// Split-bf16 (see gemm_tc.cuh): every product is lo.hi + hi.lo + hi.hi into the same fp32 TMEM accumulator.
+#include "conv3x3_sw.cuh"
+
+#include "tc_common.cuh"
+
+namespace tb {
+
+using namespace tcd;
+
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kSwStages = 4;
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
+// K-major, no swizzle: rows 16 B apart inside an 8-row core matrix, 8-row groups `sbo` bytes apart, the second 8-element
+// k-chunk `lbo` bytes away
+__device__ __forceinline__ uint64_t desc_k_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(lbo >> 4) << 16) | (uint64_t(sbo >> 4) << 32) | (uint64_t(1) << 46);
+}
+// MN-major, no swizzle (canonical ((1,n),(8,k)):((X,SBO),(1,LBO))): 8 consecutive k rows 16 B apart (each row = 8 mn
+// elements), the next 8 k rows `lbo` bytes away, the next 8 mn elements `sbo` bytes away
+__device__ __forceinline__ uint64_t desc_mn_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(lbo >> 4) << 16) | (uint64_t(sbo >> 4) << 32) | (uint64_t(1) << 46);
+}
+
+struct SwGeom {
+  int H, W, Wp, Hp;
+  int pin;        // pixels of the input window of one tile, multiple of 8
+  int tpf;        // tiles per frame
+  int vend;       // flattened padded pixels that can hold an output: (H-1)*Wp + W
+  int64_t plane;  // elements of one chunk plane: Hp*Wp*8
+};
+
+inline SwGeom sw_geom(int H, int W) {
+  SwGeom g;
+  g.H = H; g.W = W; g.Wp = W + 2; g.Hp = H + 2;
+  g.pin = (kTile + 2 * g.Wp + 2 + 7) & ~7;
+  g.vend = (H - 1) * g.Wp + W;
+  g.tpf = (g.vend + kTile - 1) / kTile;
+  g.plane = int64_t(g.Hp) * g.Wp * 8;
+  return g;
+}
+
+struct SwFwdArgs {
+  const __nv_bfloat16* img; int64_t img_lo;
+  const __nv_bfloat16* wk; int64_t wk_lo;
+  float* out; const float* bias; const float* mask; const float* addend;
+  int Nf; SwGeom g;
+};
+
+// persistent: CTA walks (frame, tile) work items; warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+template <int CK, int NO>
+__global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
+  constexpr int CH = CK / 8;                   // chunk planes per frame
+  constexpr int KP = CK / 16;                  // k16 steps per tap
+  constexpr uint32_t W_PLANE = 9u * CK * NO * 2u;   // bytes of one weight plane
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_addr(smem_raw) + 127u) & ~127u;
+  const uint32_t chb = uint32_t(a.g.pin) * 16u;     // bytes of one chunk plane window
+  const uint32_t stage_bytes = 2u * CH * chb;       // [plane hi / lo][chunk][pixel][16 B]
+  const uint32_t sW = base;                         // [plane][tap][kp][j][row][16 B]
+  const uint32_t sX = sW + 2u * W_PLANE;
+  const uint32_t bars = sX + kSwStages * stage_bytes;  // full[kSt], empty[kSt], tmem_full[2], tmem_empty[2], wbar
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (kSwStages + s); };
+  auto tmem_full = [&](int b) { return bars + 8u * (2 * kSwStages + b); };
+  auto tmem_empty = [&](int b) { return bars + 8u * (2 * kSwStages + 2 + b); };
+  const uint32_t wbar = bars + 8u * (2 * kSwStages + 4);
+  const uint32_t tmem_slot = wbar + 8u;
+  constexpr uint32_t TMEM_COLS = 64;   // two accumulator buffers, 32 columns apart
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_work = a.Nf * a.g.tpf;
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kSwStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(wbar, 2u * W_PLANE);
+      bulk_g2s(sW, a.wk, W_PLANE, wbar);
+      bulk_g2s(sW + W_PLANE, a.wk + a.wk_lo, W_PLANE, wbar);
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int n = w / a.g.tpf, p0 = (w - n * a.g.tpf) * kTile;
+        mbar_wait(empty(stage), phase ^ 1);
+        mbar_expect_tx(full(stage), stage_bytes);
+        const uint32_t st = sX + stage * stage_bytes;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl)
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const __nv_bfloat16* src = a.img + (pl ? a.img_lo : 0) + (int64_t(n) * CH + c) * a.g.plane + int64_t(p0) * 8;
+            bulk_g2s(st + (pl * CH + c) * chb, src, chb, full(stage));
+          }
+        if (++stage == kSwStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(NO >> 3) << 17) | (uint32_t(kTile >> 4) << 24);
+      mbar_wait(wbar, 0);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        const int ab = it & 1;
+        mbar_wait(tmem_empty(ab), ((it >> 1) & 1) ^ 1);
+        mbar_wait(full(stage), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + uint32_t(ab * 32);
+        const uint32_t st = sX + stage * stage_bytes;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t shift = uint32_t((tap / 3) * a.g.Wp + (tap % 3)) * 16u;
+#pragma unroll
+          for (int kp = 0; kp < KP; ++kp) {
+            const uint32_t xa = st + uint32_t(2 * kp) * chb + shift;
+            const uint32_t wa = sW + uint32_t((tap * KP + kp) * 2 * NO) * 16u;
+            const uint64_t dah = desc_k_noswz(xa, chb, 128u), dal = desc_k_noswz(xa + CH * chb, chb, 128u);
+            const uint64_t dbh = desc_k_noswz(wa, NO * 16u, 128u), dbl = desc_k_noswz(wa + W_PLANE, NO * 16u, 128u);
+            umma_bf16(tacc, dal, dbh, idesc, (tap | kp) != 0 ? 1u : 0u);
+            umma_bf16(tacc, dah, dbl, idesc, 1u);
+            umma_bf16(tacc, dah, dbh, idesc, 1u);
+          }
+        }
+        umma_commit(empty(stage));
+        umma_commit(tmem_full(ab));
+        if (++stage == kSwStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int rl = quarter * 32 + lane;
+    int it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const int ab = it & 1;
+      const int n = w / a.g.tpf, p = (w - n * a.g.tpf) * kTile + rl;
+      const int y = p / a.g.Wp, x = p - y * a.g.Wp;
+      const bool valid = x < a.g.W && y < a.g.H;
+      const int64_t r = (int64_t(n) * a.g.H + y) * a.g.W + x;
+      if (valid) {  // pull the mask / residual rows towards L2 while the MMAs run
+        if (a.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.mask + r * NO));
+        if (a.addend) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.addend + r * NO));
+      }
+      mbar_wait(tmem_full(ab), (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(ab * 32), v);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty(ab));   // the values are in registers: the buffer can be refilled
+      if (valid) {
+        float o[NO];
+#pragma unroll
+        for (int j = 0; j < NO; ++j) o[j] = __uint_as_float(v[j]);
+        if (a.bias) {
+#pragma unroll
+          for (int q = 0; q < NO / 4; ++q) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias) + q);
+            o[4 * q] += b4.x; o[4 * q + 1] += b4.y; o[4 * q + 2] += b4.z; o[4 * q + 3] += b4.w;
+          }
+        }
+        if (a.mask) {
+          const float4* mp = reinterpret_cast<const float4*>(a.mask + r * NO);
+#pragma unroll
+          for (int q = 0; q < NO / 4; ++q) {
+            const float4 m4 = __ldg(mp + q);
+            o[4 * q] = m4.x > 0.f ? o[4 * q] : 0.f; o[4 * q + 1] = m4.y > 0.f ? o[4 * q + 1] : 0.f;
+            o[4 * q + 2] = m4.z > 0.f ? o[4 * q + 2] : 0.f; o[4 * q + 3] = m4.w > 0.f ? o[4 * q + 3] : 0.f;
+          }
+        }
+        if (a.addend) {
+          const float4* ap = reinterpret_cast<const float4*>(a.addend + r * NO);
+#pragma unroll
+          for (int q = 0; q < NO / 4; ++q) {
+            const float4 a4 = __ldg(ap + q);
+            o[4 * q] += a4.x; o[4 * q + 1] += a4.y; o[4 * q + 2] += a4.z; o[4 * q + 3] += a4.w;
+          }
+        }
+        float4* op = reinterpret_cast<float4*>(a.out + r * NO);
+#pragma unroll
+        for (int q = 0; q < NO / 4; ++q) op[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+template <int CK, int NO>
+int launch_sw_fwd(const SwFwdArgs& a, cudaStream_t stream) {
+  const size_t smem = 128 + 2 * size_t(9) * CK * NO * 2 + size_t(kSwStages) * 2 * (CK / 8) * a.g.pin * 16 + 8 * (2 * kSwStages + 5) + 16;
+  TB_REQUIRE(smem <= 227 * 1024, "sw_conv_fwd: shared memory");
+  static size_t attr[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr[dev & 63] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(sw_conv_fwd_kernel<CK, NO>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    TB_REQUIRE(e == cudaSuccess, "sw_conv_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr[dev & 63] = smem;
+  }
+  int per_sm = int((220 * 1024) / smem);
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = int64_t(kNumSMsB200) * per_sm;
+  const int64_t total = int64_t(a.Nf) * a.g.tpf;
+  if (grid > total) grid = total;
+  sw_conv_fwd_kernel<CK, NO><<<(unsigned)grid, kThreads, smem, stream>>>(a);
+  return check_launch("sw_conv_fwd_kernel");
+}
+
+// ---- weight gradient ------------------------------------------------------------------------------------------
+// dW[o, tap, c] = sum over pixels p of dY[p, o] * x[p + shift(tap), c]: the reduction runs over PIXELS, so both operands are
+// MN-major: rows of the planar images are the k index (16 bytes = 8 mn elements per row: canonical ((1,n),(8,k)):((X,SBO),
+// (1,LBO)) with LBO = 128 B between 8-pixel groups and SBO = the chunk-plane pitch).  A = the dY tile (its padded image holds
+// zeros on padding pixels, so those contribute nothing), B = the SAME x window shifted per tap; nine accumulators
+// [o, c] live in TMEM (9*C columns) for all of the CTA's tiles, then go to partial[cta][o][tap*C + c] and are folded in CTA
+// order (deterministic).  M is 64 with the dY channels in rows [0, O): rows >= O alias whatever follows in shared memory
+// and are never read back.
+constexpr int kWgStages = 3;
+
+struct SwWgradArgs {
+  const __nv_bfloat16* dy; int64_t dy_lo;
+  const __nv_bfloat16* x; int64_t x_lo;
+  float* partial;
+  int Nf; SwGeom g;
+};
+
+template <int C, int O>
+__global__ void __launch_bounds__(kThreads, 1) sw_conv_wgrad_kernel(SwWgradArgs a) {
+  constexpr int CC = C / 8, CO = O / 8;
+  constexpr uint32_t TMEM_COLS = (9 * C <= 256) ? 256 : 512;
+  constexpr uint32_t DY_CH = kTile * 16u;            // bytes of one dY chunk plane tile
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_addr(smem_raw) + 127u) & ~127u;
+  const uint32_t chb = uint32_t(a.g.pin) * 16u;
+  const uint32_t dy_bytes = 2u * CO * DY_CH, x_bytes = 2u * CC * chb;
+  const uint32_t stage_bytes = dy_bytes + x_bytes;   // [dY hi chunks][dY lo chunks][x hi chunks][x lo chunks]
+  const uint32_t bars = base;                        // full[kSt], empty[kSt], done
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (kWgStages + s); };
+  const uint32_t done = bars + 8u * (2 * kWgStages);
+  const uint32_t tmem_slot = done + 8u;
+  const uint32_t sS = base + 128u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_work = a.Nf * a.g.tpf;
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  } else if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int n = w / a.g.tpf, p0 = (w - n * a.g.tpf) * kTile;
+        mbar_wait(empty(stage), phase ^ 1);
+        mbar_expect_tx(full(stage), stage_bytes);
+        const uint32_t st = sS + stage * stage_bytes;
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+          for (int c = 0; c < CO; ++c) {   // output pixel p is padded pixel p + Wp + 1 of the dY image
+            const __nv_bfloat16* src = a.dy + (pl ? a.dy_lo : 0) + (int64_t(n) * CO + c) * a.g.plane + int64_t(p0 + a.g.Wp + 1) * 8;
+            bulk_g2s(st + (pl * CO + c) * DY_CH, src, DY_CH, full(stage));
+          }
+#pragma unroll
+          for (int c = 0; c < CC; ++c) {
+            const __nv_bfloat16* src = a.x + (pl ? a.x_lo : 0) + (int64_t(n) * CC + c) * a.g.plane + int64_t(p0) * 8;
+            bulk_g2s(st + dy_bytes + (pl * CC + c) * chb, src, chb, full(stage));
+          }
+        }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // M = 64 (the smallest atom): the A operand is read from shared memory by every MMA (64 rows x 32 B instead of 128 x 32 B;
+      // measured ~35 cycles per M = 128 MMA here, all of it the A read - the math floor at N = 16 is 8)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(C >> 3) << 17) |
+                                 (uint32_t(64 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      bool first = true;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int n = w / a.g.tpf, p0 = (w - n * a.g.tpf) * kTile;
+        // pixels past the frame's last output row alias the next chunk plane: stop at the 16-pixel step that covers the
+        // last valid pixel (the rest of that step falls into the >= 2*Wp + 2 zero pixels that follow)
+        int ksteps = (a.g.vend - p0 + 15) / 16;
+        if (ksteps > kTile / 16) ksteps = kTile / 16;
+        mbar_wait(full(stage), phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t st = sS + stage * stage_bytes;
+        const uint32_t dyh = st, dyl = st + CO * DY_CH, xh = st + dy_bytes, xl = xh + CC * chb;
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t shift = uint32_t((tap / 3) * a.g.Wp + (tap % 3)) * 16u;
+          const uint32_t tacc = tmem_base + uint32_t(tap * C);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t ko = uint32_t(ks) * 256u;
+            const uint64_t dah = desc_mn_noswz(dyh + ko, 128u, DY_CH), dal = desc_mn_noswz(dyl + ko, 128u, DY_CH);
+            const uint64_t dbh = desc_mn_noswz(xh + shift + ko, 128u, chb), dbl = desc_mn_noswz(xl + shift + ko, 128u, chb);
+            umma_bf16(tacc, dal, dbh, idesc, (first && ks == 0) ? 0u : 1u);
+            umma_bf16(tacc, dah, dbl, idesc, 1u);
+            umma_bf16(tacc, dah, dbh, idesc, 1u);
+          }
+        }
+        first = false;
+        umma_commit(empty(stage));
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done);
+    }
+  } else {
+    const int quarter = warp & 3;
+    if (quarter * 16 < O) {   // M = 64 accumulator: row r lives in TMEM lane 32*(r / 16) + r % 16
+      mbar_wait(done, 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int o = lane < 16 ? quarter * 16 + lane : O;
+      float* dst = a.partial + (int64_t(blockIdx.x) * O + o) * (9 * C);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 9 * C; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), v);   // (the allocation covers c0 + 32 <= 9*C + 16)
+        if (o < O) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (c0 + j < 9 * C)
+              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// dW[o, c, kh, kw] = sum over CTAs (in order) of partial[cta][o][(kh*3 + kw)*C + c]
+__global__ void sw_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int ctas, int O, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= O * C * 9) return;
+  const int tap = i % 9, c = (i / 9) % C, o = i / (9 * C);
+  float s = 0.f;
+  for (int b = 0; b < ctas; ++b) s += partial[(int64_t(b) * O + o) * (9 * C) + tap * C + c];
+  dW[i] = s;
+}
+
+template <int C, int O>
+int launch_sw_wgrad(const SwWgradArgs& a, int grid, cudaStream_t stream) {
+  // + 40 KB: the junk rows of the M = 128 dY operand reach up to 16 chunk pitches (32 KB) past the tile
+  const size_t smem = 256 + size_t(kWgStages) * (2 * size_t(O / 8) * kTile * 16 + 2 * size_t(C / 8) * a.g.pin * 16) + 40 * 1024;
+  TB_REQUIRE(smem <= 227 * 1024, "sw_conv_wgrad: shared memory");
+  static size_t attr[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr[dev & 63] < smem) {
+    cudaError_t e = cudaFuncSetAttribute(sw_conv_wgrad_kernel<C, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    TB_REQUIRE(e == cudaSuccess, "sw_conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr[dev & 63] = smem;
+  }
+  sw_conv_wgrad_kernel<C, O><<<grid, kThreads, smem, stream>>>(a);
+  return check_launch("sw_conv_wgrad_kernel");
+}
+
+static inline unsigned sgrid(int64_t work, int threads) {
+  int64_t blocks = (work + threads - 1) / threads;
+  const int64_t cap = int64_t(kNumSMsB200) * 16;
+  if (blocks > cap) blocks = cap;
+  return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+// one thread = 8 channels of one padded pixel (borders written as zeros every time: the buffers are shared between images)
+template <bool COLSUM>
+__global__ void __launch_bounds__(256) sw_pad_split_kernel(const float4* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                           int64_t lo_off, int64_t Nf, int H, int W, int C8, int relu_in,
+                                                           float* __restrict__ partial) {
+  const int Hp = H + 2, Wp = W + 2;
+  const int64_t total = Nf * C8 * Hp * Wp;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // COLSUM: the grid is sized so that every thread keeps ONE chunk index for all of its pixels: index = pixel-major walk of
+  // [Nf][Hp*Wp] with the chunk taken from the thread index (blockDim % C8 == 0 and stride % C8 == 0)
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int cv = int(i % C8);
+    int64_t t = i / C8;
+    const int px = int(t % Wp); t /= Wp;
+    const int py = int(t % Hp);
+    const int64_t n = t / Hp;
+    uint4 ph = make_uint4(0u, 0u, 0u, 0u), pl = ph;
+    if (py >= 1 && py <= H && px >= 1 && px <= W) {
+      const float4* src = x + (((n * H + (py - 1)) * W + (px - 1)) * C8 + cv) * 2;
+      float4 a = __ldg(src), b = __ldg(src + 1);
+      if (relu_in) {
+        a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+        b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+      }
+      if (COLSUM) {
+        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      }
+      split_bf16x2(a.x, a.y, ph.x, pl.x); split_bf16x2(a.z, a.w, ph.y, pl.y);
+      split_bf16x2(b.x, b.y, ph.z, pl.z); split_bf16x2(b.z, b.w, ph.w, pl.w);
+    }
+    __nv_bfloat16* dst = out + ((n * C8 + cv) * int64_t(Hp) * Wp + int64_t(py) * Wp + px) * 8;
+    *reinterpret_cast<uint4*>(dst) = ph;
+    *reinterpret_cast<uint4*>(dst + lo_off) = pl;
+  }
+  if (COLSUM) {
+    __shared__ float red[256][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (int(threadIdx.x) < C8 * 8) {   // thread t holds chunk t % C8: channel c = 8*(t % C8) + j
+      const int cv = threadIdx.x / 8, j = threadIdx.x % 8;
+      float s = 0.f;
+      for (int t = cv; t < 256; t += C8) s += red[t][j];
+      partial[int64_t(blockIdx.x) * C8 * 8 + cv * 8 + j] = s;
+    }
+  }
+}
+
+__global__ void sw_colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int blocks, int C) {
+  const int c = threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += partial[int64_t(b) * C + c];
+  out[c] = s;
+}
+
+__global__ void sw_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int64_t lo_off, int O, int C,
+                                       int transpose) {
+  const int R = transpose ? C : O, K = transpose ? O : C;   // operand rows, reduction channels
+  const int64_t total = int64_t(9) * K * R;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    // i = (((tap*KP + kp)*2 + j)*R + r)*8 + e
+    const int e = int(i & 7);
+    int64_t t = i >> 3;
+    const int r = int(t % R); t /= R;
+    const int j = int(t & 1); t >>= 1;
+    const int KP = K / 16;
+    const int kp = int(t % KP);
+    const int tap = int(t / KP);
+    const int k = kp * 16 + j * 8 + e;
+    const int a = tap / 3, b = tap % 3;
+    const float v = transpose ? w[((int64_t(k) * C + r) * 3 + (2 - a)) * 3 + (2 - b)] : w[((int64_t(r) * C + k) * 3 + a) * 3 + b];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = h;
+    out[lo_off + i] = bf16_lo_of(v, h);
+  }
+}
+
+}  // namespace
+
+int64_t sw_image_elems(int64_t Nf, int H, int W, int C) {
+  const SwGeom g = sw_geom(H, W);
+  return Nf * (C / 8) * g.plane + int64_t(g.pin + 8) * 8;   // + the window overhang of the last frame's last tile
+}
+
+int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, int relu_in,
+                 cudaStream_t stream) {
+  ProfScope prof("pad_split", stream);
+  TB_REQUIRE(C % 8 == 0 && lo_off % 8 == 0, "sw_pad_split: C and the plane offset must be multiples of 8");
+  const int64_t total = Nf * (C / 8) * (H + 2) * (W + 2);
+  if (total == 0) return 0;
+  sw_pad_split_kernel<false><<<sgrid(total, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, Nf, H, W, C / 8,
+                                                                   relu_in, nullptr);
+  return check_launch("sw_pad_split_kernel");
+}
+
+int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, float* db,
+                        float* scratch, int64_t scratch_floats, cudaStream_t stream) {
+  ProfScope prof("bias_grad_colsum", stream);
+  TB_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && C <= 256 && lo_off % 8 == 0, "sw_pad_split_colsum: unsupported channel count");
+  const int64_t total = Nf * (C / 8) * (H + 2) * (W + 2);
+  if (total == 0) return 0;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > int64_t(kNumSMsB200) * 8) blocks = int64_t(kNumSMsB200) * 8;
+  TB_REQUIRE(blocks * C <= scratch_floats, "sw_pad_split_colsum: scratch too small");
+  sw_pad_split_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, Nf, H, W, C / 8, 0,
+                                                                 scratch);
+  int rc = check_launch("sw_pad_split_kernel");
+  if (rc) return rc;
+  sw_colsum_final_kernel<<<1, 256, 0, stream>>>(scratch, db, int(blocks), C);
+  return check_launch("sw_colsum_final_kernel");
+}
+
+int64_t sw_weight_elems(int O, int C) { return int64_t(9) * O * C; }
+
+int sw_pack_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream) {
+  TB_REQUIRE(O % 16 == 0 && C % 16 == 0 && lo_off % 8 == 0, "sw_pack_weights: channel counts must be multiples of 16");
+  const int64_t total = sw_weight_elems(O, C);
+  sw_pack_weights_kernel<<<sgrid(total, 256), 256, 0, stream>>>(w, out, lo_off, O, C, transpose);
+  return check_launch("sw_pack_weights_kernel");
+}
+
+bool sw_conv_applicable(int H, int W, int CK, int NO) {
+  const char* e = getenv("TB_RESNET_IMPLICIT");
+  if (e && e[0] == '0') return false;
+  return (CK == 16 || CK == 32) && (NO == 16 || NO == 32) && H >= 3 && W >= 3 && W <= 126;
+}
+
+int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* wk, int64_t wk_lo, float* out, int64_t Nf, int H, int W,
+                int CK, int NO, const SwEpilogue& ep, cudaStream_t stream) {
+  TB_REQUIRE(img && wk && out && img_lo > 0 && wk_lo > 0, "sw_conv_fwd: null pointer");
+  TB_REQUIRE(sw_conv_applicable(H, W, CK, NO), "sw_conv_fwd: unsupported shape");
+  TB_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(wk) & 15) == 0 && img_lo % 8 == 0 &&
+                 wk_lo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "sw_conv_fwd: operands must be 16-byte aligned");
+  if (Nf == 0) return 0;
+  TB_REQUIRE(Nf * sw_geom(H, W).tpf < (int64_t(1) << 31), "sw_conv_fwd: too many tiles");
+  ProfScope prof(ep.tag, stream);
+  SwFwdArgs a;
+  a.img = img; a.img_lo = img_lo; a.wk = wk; a.wk_lo = wk_lo; a.out = out; a.bias = ep.bias; a.mask = ep.mask; a.addend = ep.addend;
+  a.Nf = int(Nf); a.g = sw_geom(H, W);
+  if (CK == 16 && NO == 16) return launch_sw_fwd<16, 16>(a, stream);
+  if (CK == 16 && NO == 32) return launch_sw_fwd<16, 32>(a, stream);
+  if (CK == 32 && NO == 16) return launch_sw_fwd<32, 16>(a, stream);
+  return launch_sw_fwd<32, 32>(a, stream);
+}
+
+int sw_conv_wgrad(const __nv_bfloat16* dyimg, int64_t dy_lo, const __nv_bfloat16* ximg, int64_t x_lo, float* dW, int64_t Nf, int H,
+                  int W, int C, int O, float* partial, int64_t partial_floats, const char* tag, cudaStream_t stream) {
+  TB_REQUIRE(dyimg && ximg && dW && partial && dy_lo > 0 && x_lo > 0, "sw_conv_wgrad: null pointer");
+  TB_REQUIRE(sw_conv_applicable(H, W, C, O), "sw_conv_wgrad: unsupported shape");
+  if (Nf == 0) return 0;
+  ProfScope prof(tag, stream);
+  SwWgradArgs a;
+  a.dy = dyimg; a.dy_lo = dy_lo; a.x = ximg; a.x_lo = x_lo; a.partial = partial; a.Nf = int(Nf); a.g = sw_geom(H, W);
+  int64_t grid = kNumSMsB200;
+  const int64_t total = Nf * a.g.tpf;
+  if (grid > total) grid = total;
+  TB_REQUIRE(grid * O * 9 * C <= partial_floats, "sw_conv_wgrad: partial buffer too small");
+  int rc;
+  if (C == 16 && O == 16) rc = launch_sw_wgrad<16, 16>(a, int(grid), stream);
+  else if (C == 16 && O == 32) rc = launch_sw_wgrad<16, 32>(a, int(grid), stream);
+  else if (C == 32 && O == 16) rc = launch_sw_wgrad<32, 16>(a, int(grid), stream);
+  else rc = launch_sw_wgrad<32, 32>(a, int(grid), stream);
+  if (rc) return rc;
+  const int total_w = O * C * 9;
+  sw_wgrad_reduce_kernel<<<(total_w + 255) / 256, 256, 0, stream>>>(partial, dW, int(grid), O, C);
+  return check_launch("sw_wgrad_reduce_kernel");
+}
+
+}  // namespace tb

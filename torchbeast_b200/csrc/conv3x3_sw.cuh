@@ -1,0 +1,45 @@
+// 3x3 / stride 1 / pad 1 convolutions of the IMPALA ResNet as shifted-window implicit GEMMs (see conv3x3_sw.cu).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace tb {
+
+// Zero-padded, channel-chunk-planar split-bf16 image: [Nf][C/8][(H+2)*(W+2)][8] (hi plane; lo plane at + lo_off elements).
+// One (pixel, 8 channels) unit is 16 bytes, the pixels of a chunk plane are contiguous: 128 consecutive flattened padded
+// pixels are 128 rows of a K-major UMMA operand without swizzle (rows 16 bytes apart), and the window of tap (kh, kw) is the
+// same rows shifted by (kh*(W+2) + kw)*16 bytes - every input element reaches shared memory ONCE per tile (plus halo).
+// elements of one plane including the slack the last tile's window may run into
+int64_t sw_image_elems(int64_t Nf, int H, int W, int C);
+// fp32 NHWC [Nf, H, W, C] (optionally through ReLU) -> padded planar hi / lo image
+int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, int relu_in, cudaStream_t stream);
+// same, and also db[C] = column sums of x (bias gradient when x is dL/d(conv output)); scratch >= 148*8*C floats
+int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, float* db,
+                        float* scratch, int64_t scratch_floats, cudaStream_t stream);
+
+// weights [O, C, 3, 3] fp32 -> the shared-memory image of the B operand, hi / lo planes of sw_weight_elems(O, C) elements:
+//   transpose == 0 (forward):        rows = O, K = C:  [tap][C/16][2][O][8]
+//   transpose == 1 (input gradient): rows = C, K = O:  [tap][O/16][2][C][8] with flipped taps (W[o, c, 2-a, 2-b])
+int64_t sw_weight_elems(int O, int C);
+int sw_pack_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream);
+
+struct SwEpilogue {
+  const float* bias = nullptr;     // [NO]
+  const float* mask = nullptr;     // [M, NO] fp32: out = mask > 0 ? out : 0 (ReLU backward), applied before the addend
+  const float* addend = nullptr;   // [M, NO] fp32 residual / skip gradient, applied last
+  const char* tag = "conv3x3_sw";
+};
+
+bool sw_conv_applicable(int H, int W, int CK, int NO);
+// out fp32 [Nf*H*W, NO] = epilogue(conv3x3(image) with the packed weights); CK = channels of the image (16 / 32),
+// NO = output channels (16 / 32)
+int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* wk, int64_t wk_lo, float* out, int64_t Nf, int H, int W,
+                int CK, int NO, const SwEpilogue& ep, cudaStream_t stream);
+
+// weight gradient dW[O, C, 3, 3] (fp32, reference layout) = sum over pixels dY (x) windows(x): dyimg = padded planar image of
+// dL/d(conv output) (O channels), ximg = padded planar image of the conv's input (C channels); partial: split scratch
+int sw_conv_wgrad(const __nv_bfloat16* dyimg, int64_t dy_lo, const __nv_bfloat16* ximg, int64_t x_lo, float* dW, int64_t Nf, int H,
+                  int W, int C, int O, float* partial, int64_t partial_floats, const char* tag, cudaStream_t stream);
+
+}  // namespace tb

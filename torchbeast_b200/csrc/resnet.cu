@@ -17,6 +17,7 @@
 #include "lstm.cuh"
 #include "net_kernels.cuh"
 #include "resnet_kernels.cuh"
+#include "conv3x3_sw.cuh"
 
 namespace tb {
 
@@ -82,6 +83,13 @@ struct ResWs {
   int64_t colk_feat_lo[kSections] = {0, 0, 0}, colk_blk_lo[kSections][4] = {};
   __nv_bfloat16 *wd_feat[kSections] = {nullptr, nullptr, nullptr}, *wd_blk[kSections][4] = {};
   int64_t wd_feat_lo[kSections] = {0, 0, 0}, wd_blk_lo[kSections][4] = {};
+  // shifted-window implicit-GEMM path (conv3x3_sw.cuh; every 3x3 conv with 16 / 32 input channels): the conv's input as a
+  // zero-padded channel-chunk-planar split-bf16 image, kept for the weight gradient; the image of dY (shared); weights in
+  // the kernels' shared-memory layout
+  __nv_bfloat16 *xp_feat[kSections] = {nullptr, nullptr, nullptr}, *xp_blk[kSections][4] = {}, *dyp = nullptr;
+  int64_t xp_feat_lo[kSections] = {0, 0, 0}, xp_blk_lo[kSections][4] = {}, dyp_lo = 0;
+  __nv_bfloat16 *wi_feat[kSections] = {nullptr, nullptr, nullptr}, *wi_blk[kSections][4] = {};
+  int64_t wi_feat_lo[kSections] = {0, 0, 0}, wi_blk_lo[kSections][4] = {};
   __nv_bfloat16 *wb_feat[kSections] = {nullptr, nullptr, nullptr}, *wb_blk[kSections][4] = {}, *wb_fc = nullptr;
   int64_t colb_lo = 0, dyb_lo = 0, fcb_lo = 0, dfcb_lo = 0, wb_feat_lo[kSections] = {0, 0, 0}, wb_blk_lo[kSections][4] = {}, wb_fc_lo = 0;
   LstmWs lstm;
@@ -92,6 +100,9 @@ inline bool keep_patches() {
   const char* e = getenv("TB_RESNET_KEEP_PATCHES");
   return !(e && e[0] == '0');
 }
+
+// every 3x3 conv with 16 / 32 input channels as a shifted-window implicit GEMM (TB_RESNET_IMPLICIT=0: patch matrices)
+inline bool implicit3x3() { return sw_conv_applicable(kSecSo[0], kSecSo[0], 16, 16); }
 
 inline int64_t ldk_of(int cin, bool bf16) { const int64_t k = int64_t(cin) * 9; return bf16 ? ((k + 7) & ~int64_t(7)) : k; }
 
@@ -148,11 +159,31 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
       if (i > 0) w.wd_feat[i] = takeh(int64_t(kSecCin[i]) * 9 * kSecCh[i], w.wd_feat_lo[i]);
       for (int j = 0; j < 4; ++j) w.wd_blk[i][j] = takeh(int64_t(kSecCh[i]) * 9 * kSecCh[i], w.wd_blk_lo[i][j]);
     }
+    const bool impl = implicit3x3();
     if (keep_patches()) {
       for (int i = 0; i < kSections; ++i) {
-        w.colk_feat[i] = takeh(N * kSecS[i] * kSecS[i] * ldk_of(kSecCin[i], true), w.colk_feat_lo[i]);
-        for (int j = 0; j < 4; ++j) w.colk_blk[i][j] = takeh(N * kSecSo[i] * kSecSo[i] * ldk_of(kSecCh[i], true), w.colk_blk_lo[i][j]);
+        if (i == 0 || !impl) w.colk_feat[i] = takeh(N * kSecS[i] * kSecS[i] * ldk_of(kSecCin[i], true), w.colk_feat_lo[i]);
+        for (int j = 0; j < 4 && !impl; ++j)
+          w.colk_blk[i][j] = takeh(N * kSecSo[i] * kSecSo[i] * ldk_of(kSecCh[i], true), w.colk_blk_lo[i][j]);
       }
+    }
+    if (impl) {
+      int64_t maxp = 0;
+      for (int i = 0; i < kSections; ++i) {
+        if (i > 0) {
+          w.xp_feat[i] = takeh(sw_image_elems(N, kSecS[i], kSecS[i], kSecCin[i]), w.xp_feat_lo[i]);
+          w.wi_feat[i] = takeh(sw_weight_elems(kSecCh[i], kSecCin[i]), w.wi_feat_lo[i]);
+          const int64_t e = sw_image_elems(N, kSecS[i], kSecS[i], kSecCh[i]);
+          if (e > maxp) maxp = e;
+        }
+        for (int j = 0; j < 4; ++j) {
+          w.xp_blk[i][j] = takeh(sw_image_elems(N, kSecSo[i], kSecSo[i], kSecCh[i]), w.xp_blk_lo[i][j]);
+          w.wi_blk[i][j] = takeh(sw_weight_elems(kSecCh[i], kSecCh[i]), w.wi_blk_lo[i][j]);
+        }
+        const int64_t e = sw_image_elems(N, kSecSo[i], kSecSo[i], kSecCh[i]);
+        if (e > maxp) maxp = e;
+      }
+      w.dyp = takeh(maxp, w.dyp_lo);
     }
   }
   for (int i = 0; i < kSections; ++i) {
@@ -422,6 +453,16 @@ struct SplitImpl {
     return 0;
   }
 
+  // shifted-window implicit GEMM: x fp32 NHWC -> padded planar split-bf16 image xp (kept for the weight gradient) -> out fp32
+  static int conv_impl(const float* x, int relu_in, __nv_bfloat16* xp, int64_t xp_lo, const float* Wsrc, __nv_bfloat16* wi, int64_t wi_lo,
+                       float* out, int64_t N, int S, int cin, int cout, const float* bias, const float* addend, const char* tag,
+                       cudaStream_t st) {
+    TB_TRY(sw_pack_weights(Wsrc, wi, wi_lo, cout, cin, 0, st));
+    TB_TRY(sw_pad_split(x, xp, xp_lo, N, S, S, cin, relu_in, st));
+    SwEpilogue ep; ep.bias = bias; ep.addend = addend; ep.tag = tag;
+    return sw_conv_fwd(xp, xp_lo, wi, wi_lo, out, N, S, S, cin, cout, ep, st);
+  }
+
   static int forward(const uint8_t* frame, const float* reward, const float* notdone, const float* h0, const float* c0,
                      const float* P, int64_t T1, int64_t B, int A, int use_lstm, void* workspace, float* policy_logits,
                      float* baseline, float* hN, float* cN, cudaStream_t st) {
@@ -447,6 +488,9 @@ struct SplitImpl {
         TB_TRY(first_patches(frame, cf, cf_lo, N, st));
         TB_TRY(gemm_fwd(cf, cf_lo, w.wb_feat[0], w.wb_feat_lo[0], w.s[0].P, M, ch, 36, ldk_in, P + pp.feat[0].b, nullptr,
                         1.0f / 255.0f, 0, ch, "feat_conv_fwd", st));
+      } else if (w.xp_feat[i]) {
+        TB_TRY(conv_impl(xin, 0, w.xp_feat[i], w.xp_feat_lo[i], P + pp.feat[i].w, w.wi_feat[i], w.wi_feat_lo[i], w.s[i].P, N, S, cin, ch,
+                         P + pp.feat[i].b, nullptr, "feat_conv_fwd", st));
       } else {
         TB_TRY(im2col3x3_split(xin, cf, cf_lo, N, S, S, cin, ldk_in, 0, st));
         TB_TRY(gemm_fwd(cf, cf_lo, w.wb_feat[i], w.wb_feat_lo[i], w.s[i].P, M, ch, int64_t(cin) * 9, ldk_in,
@@ -457,6 +501,11 @@ struct SplitImpl {
       float* outs[4] = {w.s[i].Y1, w.s[i].X1, w.s[i].Y2, w.s[i].X2};
       const float* adds[4] = {nullptr, w.s[i].X0, nullptr, w.s[i].X1};
       for (int j = 0; j < 4; ++j) {
+        if (w.xp_blk[i][j]) {
+          TB_TRY(conv_impl(ins[j], 1, w.xp_blk[i][j], w.xp_blk_lo[i][j], P + pp.blk[i][j].w, w.wi_blk[i][j], w.wi_blk_lo[i][j], outs[j],
+                           N, So, ch, ch, P + pp.blk[i][j].b, adds[j], "res_conv_fwd", st));
+          continue;
+        }
         __nv_bfloat16* cb = w.colk_blk[i][j] ? w.colk_blk[i][j] : w.colb;
         const int64_t cb_lo = w.colk_blk[i][j] ? w.colk_blk_lo[i][j] : w.colb_lo;
         TB_TRY(im2col3x3_split(ins[j], cb, cb_lo, N, So, So, ch, ldk, 1, st));
@@ -478,6 +527,22 @@ struct SplitImpl {
     }
     TB_TRY(heads_forward(w.core_out, pp.core_out, P + pp.policy_w, P + pp.policy_b, P + pp.baseline_w, P + pp.baseline_b, N,
                          pp.core_out, A, policy_logits, baseline, st));
+    return 0;
+  }
+
+  // one 3x3 conv backward on the shifted-window kernels: dY -> padded planar image (+ bias gradient in the same pass);
+  // weight gradient from that image and the input image kept by the forward pass; input gradient = the SAME convolution
+  // kernel over the dY image with flipped / transposed weights, ReLU mask and skip gradient in its epilogue
+  static int conv_bwd_impl(const float* x, bool relu_in, const float* dY, const float* Wsrc, const __nv_bfloat16* xp, int64_t xp_lo,
+                           __nv_bfloat16* wd, int64_t wd_lo, float* dW, float* db, float* dx, const float* addend, int64_t N, int S,
+                           int cin, int cout, W& w, const char* wtag, cudaStream_t st) {
+    TB_TRY(sw_pad_split_colsum(dY, w.dyp, w.dyp_lo, N, S, S, cout, db, w.splitk, kScratchFloats, st));
+    TB_TRY(sw_conv_wgrad(w.dyp, w.dyp_lo, xp, xp_lo, dW, N, S, S, cin, cout, w.splitk, kScratchFloats, wtag, st));
+    if (dx) {
+      TB_TRY(sw_pack_weights(Wsrc, wd, wd_lo, cout, cin, 1, st));
+      SwEpilogue ep; ep.mask = relu_in ? x : nullptr; ep.addend = addend; ep.tag = "res_conv_dgrad";
+      TB_TRY(sw_conv_fwd(w.dyp, w.dyp_lo, wd, wd_lo, dx, N, S, S, cout, cin, ep, st));
+    }
     return 0;
   }
 
@@ -541,9 +606,15 @@ struct SplitImpl {
       const float* dys[4] = {g0, g2, g1, g0};       // dL/d(conv output) of r1a, r1b, r2a, r2b
       float* dxs[4] = {g1, g0, g2, g1};
       const float* skip[4] = {g2, nullptr, g0, nullptr};
-      for (int j = 3; j >= 0; --j)
-        TB_TRY(conv_bwd(xs[j], true, dys[j], P + pp.blk[i][j].w, w.colk_blk[i][j], w.colk_blk_lo[i][j], w.wd_blk[i][j], w.wd_blk_lo[i][j],
-                        G + pp.blk[i][j].w, G + pp.blk[i][j].b, dxs[j], skip[j], N, So, ch, ch, w, st));
+      for (int j = 3; j >= 0; --j) {
+        if (w.xp_blk[i][j])
+          TB_TRY(conv_bwd_impl(xs[j], true, dys[j], P + pp.blk[i][j].w, w.xp_blk[i][j], w.xp_blk_lo[i][j], w.wd_blk[i][j],
+                               w.wd_blk_lo[i][j], G + pp.blk[i][j].w, G + pp.blk[i][j].b, dxs[j], skip[j], N, So, ch, ch, w,
+                               "res_conv_wgrad", st));
+        else
+          TB_TRY(conv_bwd(xs[j], true, dys[j], P + pp.blk[i][j].w, w.colk_blk[i][j], w.colk_blk_lo[i][j], w.wd_blk[i][j], w.wd_blk_lo[i][j],
+                          G + pp.blk[i][j].w, G + pp.blk[i][j].b, dxs[j], skip[j], N, So, ch, ch, w, st));
+      }
       TB_TRY(maxpool3x3s2_bwd<float>(s.arg, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
       const int64_t M = N * S * S;
       if (i == 0) {
@@ -557,6 +628,9 @@ struct SplitImpl {
         }
         TB_TRY(gemm_wgrad(w.dyb, w.dyb_lo, cf, cf_lo, G + pp.feat[0].w, M, ch, 36, ldk_in, 1, 1, 1.0f / 255.0f, w.splitk,
                           "feat_conv_wgrad", st));
+      } else if (w.xp_feat[i]) {
+        TB_TRY(conv_bwd_impl(w.s[i - 1].X2, false, g2, P + pp.feat[i].w, w.xp_feat[i], w.xp_feat_lo[i], w.wd_feat[i], w.wd_feat_lo[i],
+                             G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S, cin, ch, w, "res_conv_wgrad", st));
       } else {
         TB_TRY(conv_bwd(w.s[i - 1].X2, false, g2, P + pp.feat[i].w, w.colk_feat[i], w.colk_feat_lo[i], w.wd_feat[i], w.wd_feat_lo[i],
                         G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S, cin, ch, w, st));
