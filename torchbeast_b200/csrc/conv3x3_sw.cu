@@ -243,14 +243,20 @@ int launch_sw_fwd(const SwFwdArgs& a, cudaStream_t stream) {
 }
 
 // ---- weight gradient ------------------------------------------------------------------------------------------
-// dW[o, tap, c] = sum over pixels p of dY[p, o] * x[p + shift(tap), c]: the reduction runs over PIXELS, so both operands are
-// MN-major: rows of the planar images are the k index (16 bytes = 8 mn elements per row: canonical ((1,n),(8,k)):((X,SBO),
-// (1,LBO)) with LBO = 128 B between 8-pixel groups and SBO = the chunk-plane pitch).  A = the dY tile (its padded image holds
-// zeros on padding pixels, so those contribute nothing), B = the SAME x window shifted per tap; nine accumulators
-// [o, c] live in TMEM (9*C columns) for all of the CTA's tiles, then go to partial[cta][o][tap*C + c] and are folded in CTA
-// order (deterministic).  M is 64 with the dY channels in rows [0, O): rows >= O alias whatever follows in shared memory
-// and are never read back.
+// dW[o, tap, c] = sum over pixels p of dY[p, o] * x[p + shift(tap), c]: M = O and N = C are 16..32 and the reduction runs
+// over pixels.  tcgen05 cannot run this shape: its atom is 128 rows and an SS-mode MMA costs >= 32 cycles whatever M and N
+// are (measured here: 35 cycles per M=128/64 x N=16 x K=16 MMA; 216 of them per tile = 7.7 k cycles, 267 us per conv).  The
+// warp-level mma.sync.m16n8k16 atom fits exactly (M = 16 channels of dY, N = 8 channels of x, K = 16 pixels; 2 cycles per
+// MMA per SM measured): A = dY^T and B = the x window both come straight out of the planar tiles with ldmatrix.trans (a
+// row of either tile is one pixel's 8 channels = 16 bytes, 8 consecutive pixels are one 8x8 matrix), the tap shift is a
+// 16-byte multiple in the row address, and the products are split-bf16 (lo.hi + hi.lo + hi.hi).
+// CTA = 9 MMA warps = 3 tap groups (one kernel row each) x 3 pixel groups (k16 steps kg, kg+3, kg+6 of a tile) + 1 producer
+// warp issuing the same bulk copies as the forward kernel; accumulators stay in registers over all of the CTA's tiles, are
+// folded over the pixel groups through shared memory and written to partial[cta][o][tap*C + c] (folded in CTA order by
+// sw_wgrad_reduce_kernel: deterministic).
 constexpr int kWgStages = 3;
+constexpr int kWgWarps = 9;
+constexpr int kWgThreads = (kWgWarps + 1) * 32;
 
 struct SwWgradArgs {
   const __nv_bfloat16* dy; int64_t dy_lo;
@@ -259,39 +265,39 @@ struct SwWgradArgs {
   int Nf; SwGeom g;
 };
 
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 template <int C, int O>
-__global__ void __launch_bounds__(kThreads, 1) sw_conv_wgrad_kernel(SwWgradArgs a) {
-  constexpr int CC = C / 8, CO = O / 8;
-  constexpr uint32_t TMEM_COLS = (9 * C <= 256) ? 256 : 512;
+__global__ void __launch_bounds__(kWgThreads, 1) sw_conv_wgrad_kernel(SwWgradArgs a) {
+  constexpr int CC = C / 8, CO = O / 8, MT = O / 16, NP = C / 16;   // chunk planes; m16 tiles; pairs of n8 tiles
   constexpr uint32_t DY_CH = kTile * 16u;            // bytes of one dY chunk plane tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_addr(smem_raw) + 127u) & ~127u;
   const uint32_t chb = uint32_t(a.g.pin) * 16u;
   const uint32_t dy_bytes = 2u * CO * DY_CH, x_bytes = 2u * CC * chb;
   const uint32_t stage_bytes = dy_bytes + x_bytes;   // [dY hi chunks][dY lo chunks][x hi chunks][x lo chunks]
-  const uint32_t bars = base;                        // full[kSt], empty[kSt], done
+  const uint32_t bars = base;                        // full[kSt], empty[kSt]
   auto full = [&](int s) { return bars + 8u * s; };
   auto empty = [&](int s) { return bars + 8u * (kWgStages + s); };
-  const uint32_t done = bars + 8u * (2 * kWgStages);
-  const uint32_t tmem_slot = done + 8u;
   const uint32_t sS = base + 128u;
+  float* red = reinterpret_cast<float*>(smem_raw + ((sS - smem_addr(smem_raw)) + kWgStages * stage_bytes));   // [9*C][O + 1]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_work = a.Nf * a.g.tpf;
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kWgStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
-    mbar_init(done, 1);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), kWgWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  } else if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  if (warp == 0) {
+  if (warp == kWgWarps) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
@@ -315,69 +321,91 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_wgrad_kernel(SwWgradArgs 
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // M = 64 (the smallest atom): the A operand is read from shared memory by every MMA (64 rows x 32 B instead of 128 x 32 B;
-      // measured ~35 cycles per M = 128 MMA here, all of it the A read - the math floor at N = 16 is 8)
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(C >> 3) << 17) |
-                                 (uint32_t(64 >> 4) << 24);
-      int stage = 0; uint32_t phase = 0;
-      bool first = true;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const int n = w / a.g.tpf, p0 = (w - n * a.g.tpf) * kTile;
-        // pixels past the frame's last output row alias the next chunk plane: stop at the 16-pixel step that covers the
-        // last valid pixel (the rest of that step falls into the >= 2*Wp + 2 zero pixels that follow)
-        int ksteps = (a.g.vend - p0 + 15) / 16;
-        if (ksteps > kTile / 16) ksteps = kTile / 16;
-        mbar_wait(full(stage), phase);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t st = sS + stage * stage_bytes;
-        const uint32_t dyh = st, dyl = st + CO * DY_CH, xh = st + dy_bytes, xl = xh + CC * chb;
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t shift = uint32_t((tap / 3) * a.g.Wp + (tap % 3)) * 16u;
-          const uint32_t tacc = tmem_base + uint32_t(tap * C);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint32_t ko = uint32_t(ks) * 256u;
-            const uint64_t dah = desc_mn_noswz(dyh + ko, 128u, DY_CH), dal = desc_mn_noswz(dyl + ko, 128u, DY_CH);
-            const uint64_t dbh = desc_mn_noswz(xh + shift + ko, 128u, chb), dbl = desc_mn_noswz(xl + shift + ko, 128u, chb);
-            umma_bf16(tacc, dal, dbh, idesc, (first && ks == 0) ? 0u : 1u);
-            umma_bf16(tacc, dah, dbl, idesc, 1u);
-            umma_bf16(tacc, dah, dbh, idesc, 1u);
+    // falls through to the fold below (takes no part in it)
+  }
+  const int tg = warp % 3, kg = warp / 3;      // kernel row of this warp's 3 taps; pixel group (MMA warps only)
+  float acc[3][MT][2 * NP][4];
+#pragma unroll
+  for (int t = 0; t < 3; ++t)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 2 * NP; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[t][mt][nt][e] = 0.f;
+  if (warp < kWgWarps) {
+    int stage = 0; uint32_t phase = 0;
+    // ldmatrix row addresses: lane -> (matrix = lane / 8, row = lane % 8)
+    //   A (dY^T, m16 x k16): matrices (m half, k half) = (0,0), (1,0), (0,1), (1,1): chunk plane = 2*mt + (mat & 1), pixel = 8*(mat >> 1) + row
+    //   B (x, k16 x 2 n8 tiles): matrices (n tile, k half) = (0,0), (0,1), (1,0), (1,1): chunk plane = 2*np + (mat >> 1), pixel = 8*(mat & 1) + row
+    const int mat = lane >> 3, row = lane & 7;
+    const uint32_t a_off = uint32_t(mat & 1) * DY_CH + uint32_t(8 * (mat >> 1) + row) * 16u;
+    const uint32_t b_off = uint32_t(mat >> 1) * chb + uint32_t(8 * (mat & 1) + row) * 16u;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int n = w / a.g.tpf, p0 = (w - n * a.g.tpf) * kTile;
+      // pixels past the frame's last output row alias the next chunk plane: stop at the 16-pixel step that covers the last
+      // valid pixel (the rest of that step falls into the >= 2*Wp + 2 zero pixels that follow in the dY image)
+      int ksteps = (a.g.vend - p0 + 15) / 16;
+      if (ksteps > kTile / 16) ksteps = kTile / 16;
+      mbar_wait(full(stage), phase);
+      const uint32_t st = sS + stage * stage_bytes;
+      const uint32_t dyh = st, dyl = st + CO * DY_CH, xh = st + dy_bytes, xl = xh + CC * chb;
+      for (int ks = kg; ks < ksteps; ks += 3) {
+        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          ldsm_x4_t(ah[mt], dyh + uint32_t(2 * mt) * DY_CH + uint32_t(ks) * 256u + a_off);
+          ldsm_x4_t(al[mt], dyl + uint32_t(2 * mt) * DY_CH + uint32_t(ks) * 256u + a_off);
+        }
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          const uint32_t shift = uint32_t(tg * a.g.Wp + t) * 16u + uint32_t(ks) * 256u;
+#pragma unroll
+          for (int np = 0; np < NP; ++np) {
+            uint32_t bh[4], bl[4];
+            ldsm_x4_t(bh, xh + uint32_t(2 * np) * chb + shift + b_off);
+            ldsm_x4_t(bl, xl + uint32_t(2 * np) * chb + shift + b_off);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              mma16816(acc[t][mt][2 * np], al[mt], bh[0], bh[1]);
+              mma16816(acc[t][mt][2 * np], ah[mt], bl[0], bl[1]);
+              mma16816(acc[t][mt][2 * np], ah[mt], bh[0], bh[1]);
+              mma16816(acc[t][mt][2 * np + 1], al[mt], bh[2], bh[3]);
+              mma16816(acc[t][mt][2 * np + 1], ah[mt], bl[2], bl[3]);
+              mma16816(acc[t][mt][2 * np + 1], ah[mt], bh[2], bh[3]);
+            }
           }
         }
-        first = false;
-        umma_commit(empty(stage));
-        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(done);
-    }
-  } else {
-    const int quarter = warp & 3;
-    if (quarter * 16 < O) {   // M = 64 accumulator: row r lives in TMEM lane 32*(r / 16) + r % 16
-      mbar_wait(done, 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int o = lane < 16 ? quarter * 16 + lane : O;
-      float* dst = a.partial + (int64_t(blockIdx.x) * O + o) * (9 * C);
-#pragma unroll 1
-      for (int c0 = 0; c0 < 9 * C; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), v);   // (the allocation covers c0 + 32 <= 9*C + 16)
-        if (o < O) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (c0 + j < 9 * C)
-              *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                      __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        }
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty(stage));
+      if (++stage == kWgStages) { stage = 0; phase ^= 1; }
     }
   }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  // fold the three pixel groups (fixed order kg = 0, 1, 2) into red[col = tap*C + c][o], then one coalesced store
+  constexpr int LDR = O + 1;
+  for (int g = 0; g < 3; ++g) {
+    if (warp < kWgWarps && kg == g) {
+#pragma unroll
+      for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2 * NP; ++nt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int o = mt * 16 + (lane >> 2) + (e >> 1) * 8;
+              const int col = (tg * 3 + t) * C + nt * 8 + (lane & 3) * 2 + (e & 1);
+              float* d = red + col * LDR + o;
+              *d = (g == 0) ? acc[t][mt][nt][e] : *d + acc[t][mt][nt][e];
+            }
+    }
+    __syncthreads();
+  }
+  float* dst = a.partial + int64_t(blockIdx.x) * O * (9 * C);
+  for (int i = threadIdx.x; i < O * 9 * C; i += kWgThreads) {
+    const int o = i / (9 * C), col = i - o * (9 * C);
+    dst[i] = red[col * LDR + o];
   }
 }
 
@@ -393,8 +421,8 @@ __global__ void sw_wgrad_reduce_kernel(const float* __restrict__ partial, float*
 
 template <int C, int O>
 int launch_sw_wgrad(const SwWgradArgs& a, int grid, cudaStream_t stream) {
-  // + 40 KB: the junk rows of the M = 128 dY operand reach up to 16 chunk pitches (32 KB) past the tile
-  const size_t smem = 256 + size_t(kWgStages) * (2 * size_t(O / 8) * kTile * 16 + 2 * size_t(C / 8) * a.g.pin * 16) + 40 * 1024;
+  const size_t smem = 384 + size_t(kWgStages) * (2 * size_t(O / 8) * kTile * 16 + 2 * size_t(C / 8) * a.g.pin * 16) +
+                      sizeof(float) * 9 * C * (O + 1);
   TB_REQUIRE(smem <= 227 * 1024, "sw_conv_wgrad: shared memory");
   static size_t attr[64] = {0};
   int dev = 0;
@@ -404,7 +432,7 @@ int launch_sw_wgrad(const SwWgradArgs& a, int grid, cudaStream_t stream) {
     TB_REQUIRE(e == cudaSuccess, "sw_conv_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr[dev & 63] = smem;
   }
-  sw_conv_wgrad_kernel<C, O><<<grid, kThreads, smem, stream>>>(a);
+  sw_conv_wgrad_kernel<C, O><<<grid, kWgThreads, smem, stream>>>(a);
   return check_launch("sw_conv_wgrad_kernel");
 }
 
