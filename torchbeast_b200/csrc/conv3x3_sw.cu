@@ -36,12 +36,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ uint64_t desc_k_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(lbo >> 4) << 16) | (uint64_t(sbo >> 4) << 32) | (uint64_t(1) << 46);
 }
-// MN-major, no swizzle (canonical ((1,n),(8,k)):((X,SBO),(1,LBO))): 8 consecutive k rows 16 B apart (each row = 8 mn
-// elements), the next 8 k rows `lbo` bytes away, the next 8 mn elements `sbo` bytes away
-__device__ __forceinline__ uint64_t desc_mn_noswz(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(lbo >> 4) << 16) | (uint64_t(sbo >> 4) << 32) | (uint64_t(1) << 46);
-}
-
 struct SwGeom {
   int H, W, Wp, Hp;
   int pin;        // pixels of the input window of one tile, multiple of 8
@@ -63,7 +57,7 @@ inline SwGeom sw_geom(int H, int W) {
 struct SwFwdArgs {
   const __nv_bfloat16* img; int64_t img_lo;
   const __nv_bfloat16* wk; int64_t wk_lo;
-  float* out; const float* bias; const float* mask; const float* addend;
+  float* out; const float* bias; const float* mask; const float* addend; float scale;
   int Nf; SwGeom g;
 };
 
@@ -182,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
       if (valid) {
         float o[NO];
 #pragma unroll
-        for (int j = 0; j < NO; ++j) o[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < NO; ++j) o[j] = __uint_as_float(v[j]) * a.scale;
         if (a.bias) {
 #pragma unroll
           for (int q = 0; q < NO / 4; ++q) {
@@ -410,13 +404,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) sw_conv_wgrad_kernel(SwWgradArg
 }
 
 // dW[o, c, kh, kw] = sum over CTAs (in order) of partial[cta][o][(kh*3 + kw)*C + c]
-__global__ void sw_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int ctas, int O, int C) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= O * C * 9) return;
-  const int tap = i % 9, c = (i / 9) % C, o = i / (9 * C);
+__global__ void sw_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int ctas, int O, int C, int c_real,
+                                       float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // index into dW [O, c_real, 3, 3]
+  if (i >= O * c_real * 9) return;
+  const int tap = i % 9, c = (i / 9) % c_real, o = i / (9 * c_real);
   float s = 0.f;
   for (int b = 0; b < ctas; ++b) s += partial[(int64_t(b) * O + o) * (9 * C) + tap * C + c];
-  dW[i] = s;
+  dW[i] = s * scale;
 }
 
 template <int C, int O>
@@ -492,6 +487,33 @@ __global__ void __launch_bounds__(256) sw_pad_split_kernel(const float4* __restr
   }
 }
 
+// uint8 NCHW frames -> 16-channel padded planar image: chunk 0 = the Cf frame channels (+ zeros), chunk 1 = zeros, lo = zeros
+__global__ void sw_frames_u8_kernel(const uint8_t* __restrict__ frame, __nv_bfloat16* __restrict__ out, int64_t lo_off, int64_t Nf,
+                                    int Cf, int H, int W) {
+  const int Hp = H + 2, Wp = W + 2;
+  const int64_t total = Nf * 2 * Hp * Wp;
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int px = int(i % Wp);
+    int64_t t = i / Wp;
+    const int py = int(t % Hp); t /= Hp;
+    const int cv = int(t & 1);
+    const int64_t n = t >> 1;
+    uint4 ph = make_uint4(0u, 0u, 0u, 0u);
+    if (cv == 0 && py >= 1 && py <= H && px >= 1 && px <= W) {
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < Cf; ++c) f[c] = float(__ldg(frame + ((n * Cf + c) * H + (py - 1)) * W + (px - 1)));
+      __nv_bfloat162 p0 = __floats2bfloat162_rn(f[0], f[1]), p1 = __floats2bfloat162_rn(f[2], f[3]);
+      __nv_bfloat162 p2 = __floats2bfloat162_rn(f[4], f[5]), p3 = __floats2bfloat162_rn(f[6], f[7]);
+      ph.x = *reinterpret_cast<uint32_t*>(&p0); ph.y = *reinterpret_cast<uint32_t*>(&p1);
+      ph.z = *reinterpret_cast<uint32_t*>(&p2); ph.w = *reinterpret_cast<uint32_t*>(&p3);
+    }
+    __nv_bfloat16* dst = out + i * 8;   // i already walks [n][chunk][py][px]
+    *reinterpret_cast<uint4*>(dst) = ph;
+    *reinterpret_cast<uint4*>(dst + lo_off) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 __global__ void sw_colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int blocks, int C) {
   const int c = threadIdx.x;
   if (c >= C) return;
@@ -501,7 +523,7 @@ __global__ void sw_colsum_final_kernel(const float* __restrict__ partial, float*
 }
 
 __global__ void sw_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int64_t lo_off, int O, int C,
-                                       int transpose) {
+                                       int transpose, int c_real) {
   const int R = transpose ? C : O, K = transpose ? O : C;   // operand rows, reduction channels
   const int64_t total = int64_t(9) * K * R;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
@@ -515,7 +537,9 @@ __global__ void sw_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat1
     const int tap = int(t / KP);
     const int k = kp * 16 + j * 8 + e;
     const int a = tap / 3, b = tap % 3;
-    const float v = transpose ? w[((int64_t(k) * C + r) * 3 + (2 - a)) * 3 + (2 - b)] : w[((int64_t(r) * C + k) * 3 + a) * 3 + b];
+    float v;
+    if (transpose) v = w[((int64_t(k) * C + r) * 3 + (2 - a)) * 3 + (2 - b)];
+    else v = k < c_real ? w[((int64_t(r) * c_real + k) * 3 + a) * 3 + b] : 0.0f;
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     out[i] = h;
     out[lo_off + i] = bf16_lo_of(v, h);
@@ -557,12 +581,22 @@ int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int6
   return check_launch("sw_colsum_final_kernel");
 }
 
+int sw_frames_u8(const uint8_t* frame, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int Cf, int H, int W, cudaStream_t stream) {
+  ProfScope prof("frames_to_image", stream);
+  TB_REQUIRE(Cf >= 1 && Cf <= 8 && lo_off % 8 == 0, "sw_frames_u8: at most 8 frame channels");
+  const int64_t total = Nf * 2 * (H + 2) * (W + 2);
+  if (total == 0) return 0;
+  sw_frames_u8_kernel<<<sgrid(total, 256), 256, 0, stream>>>(frame, out, lo_off, Nf, Cf, H, W);
+  return check_launch("sw_frames_u8_kernel");
+}
+
 int64_t sw_weight_elems(int O, int C) { return int64_t(9) * O * C; }
 
-int sw_pack_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream) {
+int sw_pack_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream, int c_real) {
   TB_REQUIRE(O % 16 == 0 && C % 16 == 0 && lo_off % 8 == 0, "sw_pack_weights: channel counts must be multiples of 16");
+  TB_REQUIRE(c_real == 0 || (!transpose && c_real <= C), "sw_pack_weights: c_real only for the forward operand");
   const int64_t total = sw_weight_elems(O, C);
-  sw_pack_weights_kernel<<<sgrid(total, 256), 256, 0, stream>>>(w, out, lo_off, O, C, transpose);
+  sw_pack_weights_kernel<<<sgrid(total, 256), 256, 0, stream>>>(w, out, lo_off, O, C, transpose, c_real > 0 ? c_real : C);
   return check_launch("sw_pack_weights_kernel");
 }
 
@@ -584,7 +618,7 @@ int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* w
   ProfScope prof(ep.tag, stream);
   SwFwdArgs a;
   a.img = img; a.img_lo = img_lo; a.wk = wk; a.wk_lo = wk_lo; a.out = out; a.bias = ep.bias; a.mask = ep.mask; a.addend = ep.addend;
-  a.Nf = int(Nf); a.g = sw_geom(H, W);
+  a.scale = ep.scale; a.Nf = int(Nf); a.g = sw_geom(H, W);
   if (CK == 16 && NO == 16) return launch_sw_fwd<16, 16>(a, stream);
   if (CK == 16 && NO == 32) return launch_sw_fwd<16, 32>(a, stream);
   if (CK == 32 && NO == 16) return launch_sw_fwd<32, 16>(a, stream);
@@ -592,7 +626,8 @@ int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* w
 }
 
 int sw_conv_wgrad(const __nv_bfloat16* dyimg, int64_t dy_lo, const __nv_bfloat16* ximg, int64_t x_lo, float* dW, int64_t Nf, int H,
-                  int W, int C, int O, float* partial, int64_t partial_floats, const char* tag, cudaStream_t stream) {
+                  int W, int C, int O, float* partial, int64_t partial_floats, const char* tag, cudaStream_t stream, float scale,
+                  int c_real) {
   TB_REQUIRE(dyimg && ximg && dW && partial && dy_lo > 0 && x_lo > 0, "sw_conv_wgrad: null pointer");
   TB_REQUIRE(sw_conv_applicable(H, W, C, O), "sw_conv_wgrad: unsupported shape");
   if (Nf == 0) return 0;
@@ -609,8 +644,9 @@ int sw_conv_wgrad(const __nv_bfloat16* dyimg, int64_t dy_lo, const __nv_bfloat16
   else if (C == 32 && O == 16) rc = launch_sw_wgrad<32, 16>(a, int(grid), stream);
   else rc = launch_sw_wgrad<32, 32>(a, int(grid), stream);
   if (rc) return rc;
-  const int total_w = O * C * 9;
-  sw_wgrad_reduce_kernel<<<(total_w + 255) / 256, 256, 0, stream>>>(partial, dW, int(grid), O, C);
+  if (c_real <= 0 || c_real > C) c_real = C;
+  const int total_w = O * c_real * 9;
+  sw_wgrad_reduce_kernel<<<(total_w + 255) / 256, 256, 0, stream>>>(partial, dW, int(grid), O, C, c_real, scale);
   return check_launch("sw_wgrad_reduce_kernel");
 }
 

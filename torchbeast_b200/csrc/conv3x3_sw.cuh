@@ -18,13 +18,20 @@ int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf,
 int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, float* db,
                         float* scratch, int64_t scratch_floats, cudaStream_t stream);
 
+// uint8 NCHW frames [Nf, Cf <= 8, H, W] -> padded planar image with 16 channels (channels >= Cf and the whole lo plane are
+// zero; pixel values 0..255 are exact in bf16): the first convolution of the net through the same kernels
+int sw_frames_u8(const uint8_t* frame, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int Cf, int H, int W, cudaStream_t stream);
+
 // weights [O, C, 3, 3] fp32 -> the shared-memory image of the B operand, hi / lo planes of sw_weight_elems(O, C) elements:
 //   transpose == 0 (forward):        rows = O, K = C:  [tap][C/16][2][O][8]
 //   transpose == 1 (input gradient): rows = C, K = O:  [tap][O/16][2][C][8] with flipped taps (W[o, c, 2-a, 2-b])
 int64_t sw_weight_elems(int O, int C);
-int sw_pack_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream);
+// c_real > 0 (forward only): the weight tensor has c_real < C input channels, the rest of the operand is zero
+int sw_pack_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream,
+                    int c_real = 0);
 
 struct SwEpilogue {
+  float scale = 1.0f;              // applied to the accumulator first (1/255 for uint8 frames)
   const float* bias = nullptr;     // [NO]
   const float* mask = nullptr;     // [M, NO] fp32: out = mask > 0 ? out : 0 (ReLU backward), applied before the addend
   const float* addend = nullptr;   // [M, NO] fp32 residual / skip gradient, applied last
@@ -39,7 +46,9 @@ int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* w
 
 // weight gradient dW[O, C, 3, 3] (fp32, reference layout) = sum over pixels dY (x) windows(x): dyimg = padded planar image of
 // dL/d(conv output) (O channels), ximg = padded planar image of the conv's input (C channels); partial: split scratch
+// c_real > 0: dW is [O, c_real, 3, 3] (the image's channels >= c_real are padding); scale multiplies the result
 int sw_conv_wgrad(const __nv_bfloat16* dyimg, int64_t dy_lo, const __nv_bfloat16* ximg, int64_t x_lo, float* dW, int64_t Nf, int H,
-                  int W, int C, int O, float* partial, int64_t partial_floats, const char* tag, cudaStream_t stream);
+                  int W, int C, int O, float* partial, int64_t partial_floats, const char* tag, cudaStream_t stream,
+                  float scale = 1.0f, int c_real = 0);
 
 }  // namespace tb

@@ -162,7 +162,7 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
     const bool impl = implicit3x3();
     if (keep_patches()) {
       for (int i = 0; i < kSections; ++i) {
-        if (i == 0 || !impl) w.colk_feat[i] = takeh(N * kSecS[i] * kSecS[i] * ldk_of(kSecCin[i], true), w.colk_feat_lo[i]);
+        if (!impl) w.colk_feat[i] = takeh(N * kSecS[i] * kSecS[i] * ldk_of(kSecCin[i], true), w.colk_feat_lo[i]);
         for (int j = 0; j < 4 && !impl; ++j)
           w.colk_blk[i][j] = takeh(N * kSecSo[i] * kSecSo[i] * ldk_of(kSecCh[i], true), w.colk_blk_lo[i][j]);
       }
@@ -170,9 +170,10 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
     if (impl) {
       int64_t maxp = 0;
       for (int i = 0; i < kSections; ++i) {
-        if (i > 0) {
-          w.xp_feat[i] = takeh(sw_image_elems(N, kSecS[i], kSecS[i], kSecCin[i]), w.xp_feat_lo[i]);
-          w.wi_feat[i] = takeh(sw_weight_elems(kSecCh[i], kSecCin[i]), w.wi_feat_lo[i]);
+        {   // (the 4 frame channels of the first conv are padded to 16)
+          const int cin16 = kSecCin[i] < 16 ? 16 : kSecCin[i];
+          w.xp_feat[i] = takeh(sw_image_elems(N, kSecS[i], kSecS[i], cin16), w.xp_feat_lo[i]);
+          w.wi_feat[i] = takeh(sw_weight_elems(kSecCh[i], cin16), w.wi_feat_lo[i]);
           const int64_t e = sw_image_elems(N, kSecS[i], kSecS[i], kSecCh[i]);
           if (e > maxp) maxp = e;
         }
@@ -484,7 +485,13 @@ struct SplitImpl {
       const int64_t ldk_in = ldk_of(cin, true), ldk = ldk_of(ch, true);
       __nv_bfloat16* cf = w.colk_feat[i] ? w.colk_feat[i] : w.colb;
       const int64_t cf_lo = w.colk_feat[i] ? w.colk_feat_lo[i] : w.colb_lo;
-      if (i == 0) {
+      if (i == 0 && w.xp_feat[0]) {
+        // the first conv through the same kernels: frame pixels (exact in bf16) as a 16-channel image, 1/255 in the epilogue
+        TB_TRY(sw_pack_weights(P + pp.feat[0].w, w.wi_feat[0], w.wi_feat_lo[0], ch, 16, 0, st, 4));
+        TB_TRY(sw_frames_u8(frame, w.xp_feat[0], w.xp_feat_lo[0], N, 4, S, S, st));
+        SwEpilogue ep; ep.scale = 1.0f / 255.0f; ep.bias = P + pp.feat[0].b; ep.tag = "feat_conv_fwd";
+        TB_TRY(sw_conv_fwd(w.xp_feat[0], w.xp_feat_lo[0], w.wi_feat[0], w.wi_feat_lo[0], w.s[0].P, N, S, S, 16, ch, ep, st));
+      } else if (i == 0) {
         TB_TRY(first_patches(frame, cf, cf_lo, N, st));
         TB_TRY(gemm_fwd(cf, cf_lo, w.wb_feat[0], w.wb_feat_lo[0], w.s[0].P, M, ch, 36, ldk_in, P + pp.feat[0].b, nullptr,
                         1.0f / 255.0f, 0, ch, "feat_conv_fwd", st));
@@ -617,7 +624,11 @@ struct SplitImpl {
       }
       TB_TRY(maxpool3x3s2_bwd<float>(s.arg, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
       const int64_t M = N * S * S;
-      if (i == 0) {
+      if (i == 0 && w.xp_feat[0]) {
+        TB_TRY(sw_pad_split_colsum(g2, w.dyp, w.dyp_lo, N, S, S, ch, G + pp.feat[0].b, w.splitk, kScratchFloats, st));
+        TB_TRY(sw_conv_wgrad(w.dyp, w.dyp_lo, w.xp_feat[0], w.xp_feat_lo[0], G + pp.feat[0].w, N, S, S, 16, ch, w.splitk, kScratchFloats,
+                             "feat_conv_wgrad", st, 1.0f / 255.0f, 4));
+      } else if (i == 0) {
         const int64_t ldk_in = ldk_of(4, true);
         TB_TRY(dy_split_colsum(g2, w.dyb, w.dyb_lo, M, ch, G + pp.feat[0].b, w.splitk, kScratchFloats, st));
         const __nv_bfloat16* cf = w.colk_feat[0];
