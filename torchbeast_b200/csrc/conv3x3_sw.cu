@@ -438,23 +438,20 @@ static inline unsigned sgrid(int64_t work, int threads) {
   return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
-// one thread = 8 channels of one padded pixel (borders written as zeros every time: the buffers are shared between images)
+// one thread = 8 channels of one padded pixel (borders written as zeros every time: the buffers are shared between images);
+// block = 256 / C8 consecutive padded pixels of frame blockIdx.y x all chunk planes (32-bit index arithmetic: one division).
+// COLSUM: block partial sums of the C channels -> partial[(frame * gridDim.x + blockIdx.x) * C + c]
 template <bool COLSUM>
 __global__ void __launch_bounds__(256) sw_pad_split_kernel(const float4* __restrict__ x, __nv_bfloat16* __restrict__ out,
-                                                           int64_t lo_off, int64_t Nf, int H, int W, int C8, int relu_in,
+                                                           int64_t lo_off, int H, int W, int C8, int relu_in,
                                                            float* __restrict__ partial) {
   const int Hp = H + 2, Wp = W + 2;
-  const int64_t total = Nf * C8 * Hp * Wp;
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  const int cv = threadIdx.x % C8;
+  const int p = blockIdx.x * (256 / C8) + threadIdx.x / C8;
+  const int64_t n = blockIdx.y;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  // COLSUM: the grid is sized so that every thread keeps ONE chunk index for all of its pixels: index = pixel-major walk of
-  // [Nf][Hp*Wp] with the chunk taken from the thread index (blockDim % C8 == 0 and stride % C8 == 0)
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int cv = int(i % C8);
-    int64_t t = i / C8;
-    const int px = int(t % Wp); t /= Wp;
-    const int py = int(t % Hp);
-    const int64_t n = t / Hp;
+  if (p < Hp * Wp) {
+    const int py = p / Wp, px = p - py * Wp;
     uint4 ph = make_uint4(0u, 0u, 0u, 0u), pl = ph;
     if (py >= 1 && py <= H && px >= 1 && px <= W) {
       const float4* src = x + (((n * H + (py - 1)) * W + (px - 1)) * C8 + cv) * 2;
@@ -463,13 +460,11 @@ __global__ void __launch_bounds__(256) sw_pad_split_kernel(const float4* __restr
         a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
         b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
       }
-      if (COLSUM) {
-        acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w; acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-      }
+      if (COLSUM) { acc[0] = a.x; acc[1] = a.y; acc[2] = a.z; acc[3] = a.w; acc[4] = b.x; acc[5] = b.y; acc[6] = b.z; acc[7] = b.w; }
       split_bf16x2(a.x, a.y, ph.x, pl.x); split_bf16x2(a.z, a.w, ph.y, pl.y);
       split_bf16x2(b.x, b.y, ph.z, pl.z); split_bf16x2(b.z, b.w, ph.w, pl.w);
     }
-    __nv_bfloat16* dst = out + ((n * C8 + cv) * int64_t(Hp) * Wp + int64_t(py) * Wp + px) * 8;
+    __nv_bfloat16* dst = out + ((n * C8 + cv) * int64_t(Hp) * Wp + p) * 8;
     *reinterpret_cast<uint4*>(dst) = ph;
     *reinterpret_cast<uint4*>(dst + lo_off) = pl;
   }
@@ -479,10 +474,10 @@ __global__ void __launch_bounds__(256) sw_pad_split_kernel(const float4* __restr
     for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
     __syncthreads();
     if (int(threadIdx.x) < C8 * 8) {   // thread t holds chunk t % C8: channel c = 8*(t % C8) + j
-      const int cv = threadIdx.x / 8, j = threadIdx.x % 8;
+      const int c8 = threadIdx.x / 8, j = threadIdx.x % 8;
       float s = 0.f;
-      for (int t = cv; t < 256; t += C8) s += red[t][j];
-      partial[int64_t(blockIdx.x) * C8 * 8 + cv * 8 + j] = s;
+      for (int t = c8; t < 256; t += C8) s += red[t][j];   // fixed order
+      partial[(n * gridDim.x + blockIdx.x) * (C8 * 8) + c8 * 8 + j] = s;
     }
   }
 }
@@ -514,12 +509,20 @@ __global__ void sw_frames_u8_kernel(const uint8_t* __restrict__ frame, __nv_bflo
   }
 }
 
-__global__ void sw_colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int blocks, int C) {
-  const int c = threadIdx.x;
-  if (c >= C) return;
+// out[c] = sum over the block partials, one block per channel, fixed association (deterministic)
+__global__ void __launch_bounds__(256) sw_colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                              int64_t blocks, int C) {
+  __shared__ float red[256];
+  const int c = blockIdx.x;
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += partial[int64_t(b) * C + c];
-  out[c] = s;
+  for (int64_t b = threadIdx.x; b < blocks; b += 256) s += partial[b * C + c];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if (int(threadIdx.x) < w) red[threadIdx.x] += red[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[c] = red[0];
 }
 
 __global__ void sw_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int64_t lo_off, int O, int C,
@@ -556,28 +559,28 @@ int64_t sw_image_elems(int64_t Nf, int H, int W, int C) {
 int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, int relu_in,
                  cudaStream_t stream) {
   ProfScope prof("pad_split", stream);
-  TB_REQUIRE(C % 8 == 0 && lo_off % 8 == 0, "sw_pad_split: C and the plane offset must be multiples of 8");
-  const int64_t total = Nf * (C / 8) * (H + 2) * (W + 2);
-  if (total == 0) return 0;
-  sw_pad_split_kernel<false><<<sgrid(total, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, Nf, H, W, C / 8,
-                                                                   relu_in, nullptr);
+  TB_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && lo_off % 8 == 0 && Nf < 65536, "sw_pad_split: unsupported channel / frame count");
+  if (Nf == 0) return 0;
+  const int ppb = 256 / (C / 8);
+  dim3 grid(unsigned(((H + 2) * (W + 2) + ppb - 1) / ppb), unsigned(Nf));
+  sw_pad_split_kernel<false><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, H, W, C / 8, relu_in, nullptr);
   return check_launch("sw_pad_split_kernel");
 }
 
 int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, float* db,
                         float* scratch, int64_t scratch_floats, cudaStream_t stream) {
   ProfScope prof("bias_grad_colsum", stream);
-  TB_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && C <= 256 && lo_off % 8 == 0, "sw_pad_split_colsum: unsupported channel count");
-  const int64_t total = Nf * (C / 8) * (H + 2) * (W + 2);
-  if (total == 0) return 0;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > int64_t(kNumSMsB200) * 8) blocks = int64_t(kNumSMsB200) * 8;
+  TB_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && C <= 256 && lo_off % 8 == 0 && Nf < 65536,
+             "sw_pad_split_colsum: unsupported channel / frame count");
+  if (Nf == 0) return 0;
+  const int ppb = 256 / (C / 8);
+  dim3 grid(unsigned(((H + 2) * (W + 2) + ppb - 1) / ppb), unsigned(Nf));
+  const int64_t blocks = int64_t(grid.x) * grid.y;
   TB_REQUIRE(blocks * C <= scratch_floats, "sw_pad_split_colsum: scratch too small");
-  sw_pad_split_kernel<true><<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, Nf, H, W, C / 8, 0,
-                                                                 scratch);
+  sw_pad_split_kernel<true><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, H, W, C / 8, 0, scratch);
   int rc = check_launch("sw_pad_split_kernel");
   if (rc) return rc;
-  sw_colsum_final_kernel<<<1, 256, 0, stream>>>(scratch, db, int(blocks), C);
+  sw_colsum_final_kernel<<<C, 256, 0, stream>>>(scratch, db, blocks, C);
   return check_launch("sw_colsum_final_kernel");
 }
 
