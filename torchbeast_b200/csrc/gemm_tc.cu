@@ -61,9 +61,6 @@ struct ImplicitConv {
   int mode = 0;       // 0 forward, 1 input gradient stride 1, 2 input gradient stride 2 (parity classes)
   int tw = 0;         // mode 2: tile width (v range) = ceil(W_in / 2)
   int outH = 0, outW = 0;  // mode 2: input-gradient image size
-  // mode 0 with images larger than one tile: M tile t = `rpt` whole output rows [y0, y0 + rpt) of frame t / tpf
-  // (y0 = (t % tpf) * rpt; the last block of a frame is partial: the box rows past OH arrive as zeros and are not stored)
-  int tpf = 1, rpt = 0, OH = 0, OW = 0;
 };
 
 // SPLIT (split-bf16, see TcEpilogue): a stage holds the hi AND lo plane tiles of both operands (tmAl / tmBl are the
@@ -136,10 +133,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t dA = sA + stage * A_STAGE + pl * kABytes, dB = sB + stage * B_STAGE + pl * B_BYTES;
             if (IMPL) {
               const int kb = kb0 + i;
-              if (ic.mode == 0 && ic.tpf > 1) {
-                const int t = m0 / kBlockM, n = t / ic.tpf;
-                tma_load_4d(dA, mA, full(stage), (kb / ic.kbw) * ic.row_elems + (kb % ic.kbw) * kBlockK, 0, (t - n * ic.tpf) * ic.rpt, n);
-              } else if (ic.mode == 0)
+              if (ic.mode == 0)
                 tma_load_4d(dA, mA, full(stage), (kb / ic.kbw) * ic.row_elems + (kb % ic.kbw) * kBlockK, 0, 0,
                             (m0 / kBlockM) * ic.fpt);
               else
@@ -207,14 +201,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       decode(w, m0, n0, kb0, num_kb, z);
       const int ab = it & 1;
       const int rl = quarter * 32 + lane;
-      int64_t r = IMPL ? int64_t(m0 / kBlockM) * ic.rows + rl : int64_t(m0) + rl;
-      bool rvalid = r < M && (!IMPL || rl < ic.rows);
-      if (IMPL && ic.tpf > 1) {   // row-block tile of a large image
-        const int t = m0 / kBlockM, n = t / ic.tpf, y0 = (t - n * ic.tpf) * ic.rpt;
-        const int vr = (ic.OH - y0 < ic.rpt ? ic.OH - y0 : ic.rpt) * ic.OW;
-        r = (int64_t(n) * ic.OH + y0) * ic.OW + rl;
-        rvalid = rl < vr;
-      }
+      const int64_t r = IMPL ? int64_t(m0 / kBlockM) * ic.rows + rl : int64_t(m0) + rl;
+      const bool rvalid = r < M && (!IMPL || rl < ic.rows);
       // where this thread's 32 values of column chunk c0 live in memory: row pr, first column pc (== r, n0 + c0
       // except for the parity-class scatter of the stride-2 input gradient); false = nothing to store
       auto locate = [&](int c0, int64_t& pr, int& pc) -> bool {
@@ -744,58 +732,6 @@ int conv_tc_fwd_implicit(const void* act_nhwc_bf16, const void* w_packed_bf16, i
   if (bn == 32) return launch_conv_fwd<32>(mp, ep, M, O, K, tiles_m, ic, stream);
   if (bn == 64) return launch_conv_fwd<64>(mp, ep, M, O, K, tiles_m, ic, stream);
   return launch_conv_fwd<128>(mp, ep, M, O, K, tiles_m, ic, stream);
-}
-
-// 3x3 / stride 1 / pad 1 convolution (the IMPALA ResNet's) over a zero-PADDED bf16 NHWC image [Nf, H+2, W+2, C] as hi / lo
-// planes: out (ep.C, fp32 [Nf*H*W, O]) = epilogue(patches . Wp^T).  A kernel row's 3 taps x C channels are not a multiple of
-// the 64-element k-block, so a k-block spans 64/C = 4 (C = 16) or 2 (C = 32) consecutive pixels and Wp [O, 3*4*C] is packed
-// (kh, kw4, c) with ZERO weights at kw4 = 3: the 4th pixel (a finite neighbour, or the next row / frame's first pixel) is
-// read and multiplied by zero.  Images larger than one tile are cut into blocks of 128 / W whole rows.  The buffer must
-// extend 64 elements past the last frame (the 4th pixel of the last window).
-bool conv3x3p_tc_applicable(int H, int W, int C, int O) {
-  const char* e = getenv("TB_RESNET_IMPLICIT");
-  if (e && e[0] == '0') return false;
-  return (C == 16 || C == 32) && O >= 8 && O <= 32 && O % 8 == 0 && W >= 3 && W <= kBlockM && H >= 3 && H <= 256;
-}
-
-int conv3x3p_tc_fwd(const void* actp_bf16, const void* wp_bf16, int64_t Nf, int H, int W, int C, int O, const TcEpilogue& ep,
-                    cudaStream_t stream) {
-  TB_REQUIRE(actp_bf16 && wp_bf16 && ep.C && ep.a_lo != 0 && ep.b_lo != 0, "conv3x3p_tc_fwd: bad arguments (split planes required)");
-  TB_REQUIRE(conv3x3p_tc_applicable(H, W, C, O), "conv3x3p_tc_fwd: unsupported shape");
-  if (Nf == 0) return 0;
-  ProfScope prof(ep.tag, stream);
-  const int Hp = H + 2, Wp = W + 2;
-  ImplicitConv ic;
-  ic.OH = H; ic.OW = W;
-  uint32_t box[4];
-  int64_t tiles_m;
-  if (H * W <= kBlockM) {
-    ic.fpt = kBlockM / (H * W); ic.tpf = 1; ic.rows = H * W * ic.fpt;
-    box[0] = kBlockK; box[1] = uint32_t(W); box[2] = uint32_t(H); box[3] = uint32_t(ic.fpt);
-    tiles_m = (Nf + ic.fpt - 1) / ic.fpt;
-  } else {
-    ic.rpt = kBlockM / W; ic.tpf = (H + ic.rpt - 1) / ic.rpt; ic.fpt = 1; ic.rows = ic.rpt * W;
-    box[0] = kBlockK; box[1] = uint32_t(W); box[2] = uint32_t(ic.rpt); box[3] = 1u;
-    tiles_m = Nf * ic.tpf;
-  }
-  TB_REQUIRE(tiles_m < (int64_t(1) << 24), "conv3x3p_tc_fwd: too many tiles");
-  ic.kbw = 4 * C / kBlockK;
-  ic.row_elems = Wp * C;
-  const int64_t K = int64_t(12) * C, M = Nf * H * W;
-  const uint64_t dims[4] = {uint64_t(Hp) * Wp * C, uint64_t(W), uint64_t(H), uint64_t(Nf)};
-  const uint64_t strides[3] = {uint64_t(C) * 2, uint64_t(Wp) * C * 2, uint64_t(Hp) * Wp * C * 2};
-  TcMaps mp;
-  int rc = make_map_nd(&mp.a, actp_bf16, 4, dims, strides, box);
-  if (rc) return rc;
-  rc = make_map(&mp.b, wp_bf16, O, K, K, 32);
-  if (rc) return rc;
-  rc = make_map_nd(&mp.al, static_cast<const __nv_bfloat16*>(actp_bf16) + ep.a_lo, 4, dims, strides, box);
-  if (rc) return rc;
-  rc = make_map(&mp.bl, static_cast<const __nv_bfloat16*>(wp_bf16) + ep.b_lo, O, K, K, 32);
-  if (rc) return rc;
-  const bool loads = ep.mask || ep.mask16 || ep.addend16 || ep.addend32;
-  if (loads) return launch_conv_fwd_s<32, 2, 4, true>(mp, ep, M, O, K, tiles_m, ic, stream);
-  return launch_conv_fwd_s<32, 1, 4, true>(mp, ep, M, O, K, tiles_m, ic, stream);
 }
 
 bool conv_tc_dgrad_implicit_applicable(int H, int W, int C, int KH, int KW, int S, int O) {

@@ -59,12 +59,6 @@ int conv_tc_wgrad_implicit(const void* dy_bf16, const void* act_nhwc_bf16, int64
                            int O, float* dW, int permP, int permQ, float scale, float* partial, int64_t partial_floats,
                            const char* tag, cudaStream_t stream, int64_t dy_lo = 0, int64_t act_lo = 0);
 
-// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM over a zero-padded split-bf16 image [Nf, H+2, W+2, C] (see gemm_tc.cu):
-// ep.C fp32 [Nf*H*W, O]; wp_bf16 [O, 12*C] packed (kh, kw4, c), zero at kw4 = 3; ep.a_lo / ep.b_lo = lo plane offsets.
-bool conv3x3p_tc_applicable(int H, int W, int C, int O);
-int conv3x3p_tc_fwd(const void* actp_bf16, const void* wp_bf16, int64_t Nf, int H, int W, int C, int O, const TcEpilogue& ep,
-                    cudaStream_t stream);
-
 // lo_off != 0: also write the lo plane bf16(x - hi) at out + lo_off elements (split-bf16 operands)
 int f32_to_bf16(const float* in, void* out, int64_t rows, int64_t cols, int64_t ld, int64_t ld16, cudaStream_t stream,
                 int64_t lo_off = 0);

@@ -132,7 +132,7 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
     if (b > maxcol) maxcol = b;
   }
   w.col = split ? nullptr : takeT(maxcol);   // (the split backend gathers into colb instead)
-  w.dcol = takeT(maxcol);
+  w.dcol = split ? nullptr : takeT(maxcol);   // (the split backend's input gradients are convolutions of dY: no gradient patches)
   if (split) {
     auto takeh = [&](int64_t n, int64_t& lo) {
       lo = (n + 127) & ~int64_t(127);
@@ -146,11 +146,14 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
       if (b > maxcol16) maxcol16 = b;
       if (c > maxcol16) maxcol16 = c;
     }
-    w.colb = takeh(maxcol16, w.colb_lo);
-    w.dyb = takeh(maxact, w.dyb_lo);
+    const bool patches = !implicit3x3();   // patch-matrix GEMMs only behind TB_RESNET_IMPLICIT=0
+    if (patches) {
+      w.colb = takeh(maxcol16, w.colb_lo);
+      w.dyb = takeh(maxact, w.dyb_lo);
+    }
     w.fcb = takeh(N * kFcIn, w.fcb_lo);
     w.dfcb = takeh(N * kFcOut, w.dfcb_lo);
-    for (int i = 0; i < kSections; ++i) {
+    for (int i = 0; i < kSections && patches; ++i) {
       w.wb_feat[i] = takeh(int64_t(kSecCh[i]) * ldk_of(kSecCin[i], true), w.wb_feat_lo[i]);
       for (int j = 0; j < 4; ++j) w.wb_blk[i][j] = takeh(int64_t(kSecCh[i]) * ldk_of(kSecCh[i], true), w.wb_blk_lo[i][j]);
     }
@@ -470,12 +473,14 @@ struct SplitImpl {
     const int64_t N = T1 * B;
     const ResParams pp = res_params(A, use_lstm);
     W w = res_ws<float>(workspace, N, T1, B, A, use_lstm, true);
-    TB_TRY(pack_weights_bf16(P + pp.feat[0].w, w.wb_feat[0], kSecCh[0], 1, 36, ldk_of(4, true), st, w.wb_feat_lo[0]));
-    for (int i = 0; i < kSections; ++i) {
-      if (i > 0)
-        TB_TRY(pack_weights_bf16(P + pp.feat[i].w, w.wb_feat[i], kSecCh[i], 9, kSecCin[i], ldk_of(kSecCin[i], true), st, w.wb_feat_lo[i]));
-      for (int j = 0; j < 4; ++j)
-        TB_TRY(pack_weights_bf16(P + pp.blk[i][j].w, w.wb_blk[i][j], kSecCh[i], 9, kSecCh[i], ldk_of(kSecCh[i], true), st, w.wb_blk_lo[i][j]));
+    if (w.wb_feat[0]) {   // patch-matrix fallback: K-major packed weights
+      TB_TRY(pack_weights_bf16(P + pp.feat[0].w, w.wb_feat[0], kSecCh[0], 1, 36, ldk_of(4, true), st, w.wb_feat_lo[0]));
+      for (int i = 0; i < kSections; ++i) {
+        if (i > 0)
+          TB_TRY(pack_weights_bf16(P + pp.feat[i].w, w.wb_feat[i], kSecCh[i], 9, kSecCin[i], ldk_of(kSecCin[i], true), st, w.wb_feat_lo[i]));
+        for (int j = 0; j < 4; ++j)
+          TB_TRY(pack_weights_bf16(P + pp.blk[i][j].w, w.wb_blk[i][j], kSecCh[i], 9, kSecCh[i], ldk_of(kSecCh[i], true), st, w.wb_blk_lo[i][j]));
+      }
     }
     TB_TRY(pack_weights_bf16(P + pp.fc_w, w.wb_fc, kFcOut, 121, 32, kFcIn, st, w.wb_fc_lo));
     const float* xin = nullptr;

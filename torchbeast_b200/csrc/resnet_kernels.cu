@@ -178,70 +178,6 @@ int pack_dgrad3x3_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, in
   return check_launch("pack_dgrad3x3_kernel");
 }
 
-// fp32 NHWC [N, H, W, C] -> zero-padded split-bf16 image [N, H+2, W+2, C] (hi plane at out, lo plane at out + lo_off): the
-// operand of the implicit-GEMM 3x3 convolutions (conv3x3p_tc_fwd / conv3x3p_tc_wgrad).  One thread = 8 channels of one padded
-// pixel; the border is written as zeros every time (the buffer is shared by images of different sizes).
-__global__ void pad_split_kernel(const float4* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t lo_off, int64_t N, int H,
-                                 int W, int C8, int relu_in) {
-  const int Hp = H + 2, Wp = W + 2;
-  const int64_t total = N * Hp * Wp * C8;
-  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const int cv = int(i % C8);
-    int64_t t = i / C8;
-    const int px = int(t % Wp); t /= Wp;
-    const int py = int(t % Hp);
-    const int64_t n = t / Hp;
-    uint4 ph = make_uint4(0u, 0u, 0u, 0u), pl = ph;
-    if (py >= 1 && py <= H && px >= 1 && px <= W) {
-      const float4* src = x + (((n * H + (py - 1)) * W + (px - 1)) * C8 + cv) * 2;
-      float4 a = __ldg(src), b = __ldg(src + 1);
-      if (relu_in) {
-        a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-        b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
-      }
-      tcd::split_bf16x2(a.x, a.y, ph.x, pl.x); tcd::split_bf16x2(a.z, a.w, ph.y, pl.y);
-      tcd::split_bf16x2(b.x, b.y, ph.z, pl.z); tcd::split_bf16x2(b.z, b.w, ph.w, pl.w);
-    }
-    *reinterpret_cast<uint4*>(out + i * 8) = ph;
-    *reinterpret_cast<uint4*>(out + lo_off + i * 8) = pl;
-  }
-}
-
-int pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t N, int H, int W, int C, int relu_in, cudaStream_t stream) {
-  ProfScope prof("pad_split", stream);
-  TB_REQUIRE(C % 8 == 0 && lo_off % 8 == 0, "pad_split: C and the plane offset must be multiples of 8");
-  const int64_t total = N * (H + 2) * (W + 2) * (C / 8);
-  if (total == 0) return 0;
-  pad_split_kernel<<<rgrid(total, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, N, H, W, C / 8, relu_in);
-  return check_launch("pad_split_kernel");
-}
-
-// weights [O, C, 3, 3] fp32 -> B operand of conv3x3p_tc_fwd as bf16 hi / lo planes, K = 12*X packed (row, pixel4, channel)
-// with zeros at pixel4 = 3:
-//   transpose == 0 (forward):         out[o, (kh*4 + kw)*C + c] = W[o, c, kh, kw]
-//   transpose == 1 (input gradient):  out[c, (a*4 + b)*O + o]   = W[o, c, 2-a, 2-b]   (the convolution of dY that yields dX)
-__global__ void pack_w3x4_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int64_t lo_off, int O, int C,
-                                 int transpose) {
-  const int R = transpose ? C : O, X = transpose ? O : C;   // rows of the operand, channels per pixel of a k-block
-  const int64_t total = int64_t(R) * 12 * X;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int r = int(i / (12 * X)), k = int(i % (12 * X));
-    const int tap = k / X, xc = k - tap * X;
-    const int a = tap >> 2, b = tap & 3;
-    float v = 0.f;
-    if (b < 3) v = transpose ? w[((int64_t(xc) * C + r) * 3 + (2 - a)) * 3 + (2 - b)] : w[((int64_t(r) * C + xc) * 3 + a) * 3 + b];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    out[i] = h;
-    out[lo_off + i] = tcd::bf16_lo_of(v, h);
-  }
-}
-int pack_w3x4(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream) {
-  const int64_t total = int64_t(transpose ? C : O) * 12 * (transpose ? O : C);
-  pack_w3x4_kernel<<<rgrid(total, 256), 256, 0, stream>>>(w, out, lo_off, O, C, transpose);
-  return check_launch("pack_w3x4_kernel");
-}
-
 template <typename TOut> __device__ __forceinline__ TOut from_u8(uint8_t v);
 template <> __device__ __forceinline__ uint8_t from_u8<uint8_t>(uint8_t v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_u8<__nv_bfloat16>(uint8_t v) { return __float2bfloat16_rn(float(v)); }

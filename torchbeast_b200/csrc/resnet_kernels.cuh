@@ -50,11 +50,6 @@ int dy_split_colsum(const float* dy, __nv_bfloat16* out, int64_t lo_off, int64_t
 // weights [O, C, 3, 3] -> [C, ld >= 9*O] hi / lo planes with flipped taps: the input gradient as a convolution of dY
 int pack_dgrad3x3_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int64_t ld, cudaStream_t stream);
 
-// fp32 NHWC -> zero-padded split-bf16 image [N, H+2, W+2, C] (operand of the implicit 3x3 convolutions)
-int pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t N, int H, int W, int C, int relu_in, cudaStream_t stream);
-// weights [O, C, 3, 3] -> [O, 12*C] (transpose 0) or [C, 12*O] flipped (transpose 1) hi / lo planes, zero 4th pixel
-int pack_w3x4(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream);
-
 // first conv of the net: frames u8 NCHW [N,C,H,W] -> patch matrix, k = (c*3 + kh)*3 + kw (the reference
 // weight's own flattening).  TOut = uint8_t (fp32 backend: x/255 applied on read) or bf16 (exact 0..255).
 template <typename TOut>
