@@ -281,6 +281,36 @@ def resnet_flops_table(N, A):
             "res_conv_wgrad": res + feat_d, "res_conv_dgrad": res + feat_d, "fc_fwd": fc, "fc_wgrad": fc, "fc_dgrad": fc}
 
 
+def resnet_bytes_table(N):
+    """ALGORITHMIC bytes of the tagged ResNet trunk ops on the bf16x3 backend (aggregated over the convs): every tensor moves
+    once - the conv input as a zero-padded split-bf16 image (4 B per element, (S+2)^2 pixels), outputs / gradients / ReLU
+    masks / residuals in fp32.  With 16..32 channels these products are HBM streams, not tensor-pipe work."""
+    secs = [(84, 42, 4, 16), (42, 21, 16, 32), (21, 11, 32, 32)]
+    t = dict(feat_conv_fwd=0, feat_conv_wgrad=0, res_conv_fwd=0, res_conv_wgrad=0, res_conv_dgrad=0, pad_split=0,
+             bias_grad_colsum=0, frames_to_image=0, maxpool_fwd=0, maxpool_bwd=0)
+    for i, (S, So, cin, ch) in enumerate(secs):
+        cin16 = max(cin, 16)
+        M, Mp, Mo, Mop = N * S * S, N * (S + 2) ** 2, N * So * So, N * (So + 2) ** 2
+        t["feat_conv_fwd"] += Mp * cin16 * 4 + M * ch * 4
+        wg = Mp * ch * 4 + Mp * cin16 * 4                       # dY image + input image
+        t["feat_conv_wgrad" if i == 0 else "res_conv_wgrad"] += wg
+        if i > 0:
+            t["res_conv_dgrad"] += Mp * ch * 4 + M * cin * 4    # dY image -> dX
+            t["pad_split"] += M * cin * 4 + Mp * cin * 4
+        else:
+            t["frames_to_image"] += N * 4 * S * S + Mp * 16 * 4
+        t["bias_grad_colsum"] += M * ch * 4 + Mp * ch * 4       # dY fp32 -> image (+ column sums)
+        t["maxpool_fwd"] += M * ch * 4 + Mo * ch * 5            # + argmax byte
+        t["maxpool_bwd"] += Mo * ch * 5 + M * ch * 4
+        # four block convs: image + output (+ residual on two of them); backward: dY image + dX + ReLU mask (+ skip on two)
+        t["res_conv_fwd"] += 4 * (Mop * ch * 4 + Mo * ch * 4) + 2 * Mo * ch * 4
+        t["res_conv_wgrad"] += 4 * (2 * Mop * ch * 4)
+        t["res_conv_dgrad"] += 4 * (Mop * ch * 4 + 2 * Mo * ch * 4) + 2 * Mo * ch * 4
+        t["pad_split"] += 4 * (Mo * ch * 4 + Mop * ch * 4)
+        t["bias_grad_colsum"] += 4 * (Mo * ch * 4 + Mop * ch * 4)
+    return t
+
+
 def hbm_bytes_table(N, T, B, A, use_lstm, nparams):
     """Algorithmic bytes of the bandwidth-bound ops per step."""
     M1, M2, M3 = N * 400, N * 81, N * 49
@@ -707,6 +737,9 @@ def main():
         flops = gemm_flops_table(N, A, "resnet" if args.net == "resnet" else args.use_lstm)
         nbytes = hbm_bytes_table(N, T, B, A, args.use_lstm, model.flat_params.numel())
         gbytes = gemm_bytes_table(N, A, args.use_lstm, model.precision != "fp32") if args.net == "atari" else {}
+        if args.net == "resnet" and model.precision == "bf16x3":
+            gbytes = resnet_bytes_table(N)
+            nbytes = dict(nbytes, **{k: v for k, v in gbytes.items() if k not in flops})
         ops = []
         for name, (tot, cnt) in agg.items():
             per_step = tot / PSTEPS
@@ -741,8 +774,10 @@ def main():
                                           "all-gather + mma.sync products; neither roofline is approached - the algorithmic "
                                           "recurrent-product flops (2*M*N*K, not x3 for the split planes) are reported against the "
                                           "sustained bf16 tensor peak" if dom["op"].startswith("lstm_recurrence")
-                                          else "%s backend against the sustained bf16 tensor-core peak (algorithmic flops: the 3 MMAs of "
-                                               "a split product count once)" % model.precision))
+                                          else ("algorithmic bytes (every tensor once: padded split-bf16 images, fp32 outputs / masks / "
+                                                "residuals) against the measured HBM copy bandwidth" if dom["bound"] == "hbm"
+                                                else "%s backend against the sustained bf16 tensor-core peak (algorithmic flops: the 3 MMAs "
+                                                     "of a split product count once)" % model.precision)))
         # the V-trace kernels on their own (BASELINE.json metric: V-trace GB/s vs HBM peak)
         line["vtrace"] = vtrace_numbers(pk, T, B, A)
 

@@ -56,7 +56,7 @@ inline SwGeom sw_geom(int H, int W) {
 
 struct SwFwdArgs {
   const __nv_bfloat16* img; int64_t img_lo;
-  const __nv_bfloat16* wk; int64_t wk_lo;
+  const __nv_bfloat16* wk;
   float* out; const float* bias; const float* mask; const float* addend; float scale;
   int Nf; SwGeom g;
 };
@@ -66,12 +66,12 @@ template <int CK, int NO>
 __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
   constexpr int CH = CK / 8;                   // chunk planes per frame
   constexpr int KP = CK / 16;                  // k16 steps per tap
-  constexpr uint32_t W_PLANE = 9u * CK * NO * 2u;   // bytes of one weight plane
+  constexpr uint32_t W_PLANE = 9u * CK * NO * 2u;   // bytes of one weight plane (the image interleaves hi and lo rows)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_addr(smem_raw) + 127u) & ~127u;
   const uint32_t chb = uint32_t(a.g.pin) * 16u;     // bytes of one chunk plane window
   const uint32_t stage_bytes = 2u * CH * chb;       // [plane hi / lo][chunk][pixel][16 B]
-  const uint32_t sW = base;                         // [plane][tap][kp][j][row][16 B]
+  const uint32_t sW = base;                         // [tap][kp][j][hi rows | lo rows][16 B]
   const uint32_t sX = sW + 2u * W_PLANE;
   const uint32_t bars = sX + kSwStages * stage_bytes;  // full[kSt], empty[kSt], tmem_full[2], tmem_empty[2], wbar
   auto full = [&](int s) { return bars + 8u * s; };
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
   auto tmem_empty = [&](int b) { return bars + 8u * (2 * kSwStages + 2 + b); };
   const uint32_t wbar = bars + 8u * (2 * kSwStages + 4);
   const uint32_t tmem_slot = wbar + 8u;
-  constexpr uint32_t TMEM_COLS = 64;   // two accumulator buffers, 32 columns apart
+  constexpr uint32_t TMEM_COLS = 128;  // two accumulator buffers of 2*NO <= 64 columns
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_work = a.Nf * a.g.tpf;
@@ -102,8 +102,7 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
   if (warp == 0) {
     if (lane == 0) {
       mbar_expect_tx(wbar, 2u * W_PLANE);
-      bulk_g2s(sW, a.wk, W_PLANE, wbar);
-      bulk_g2s(sW + W_PLANE, a.wk + a.wk_lo, W_PLANE, wbar);
+      bulk_g2s(sW, a.wk, 2u * W_PLANE, wbar);
       int stage = 0; uint32_t phase = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         const int n = w / a.g.tpf, p0 = (w - n * a.g.tpf) * kTile;
@@ -122,7 +121,11 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(NO >> 3) << 17) | (uint32_t(kTile >> 4) << 24);
+      // An SS-mode MMA costs >= 32 cycles of the tensor pipe for its 128 x 16 A operand whatever N is (ncu: pipe_tc 87 % busy
+      // with three N = 16 MMAs per product), so the split product is issued as TWO MMAs: x_hi . [w_hi | w_lo] (N = 2*NO, the lo
+      // half lands in columns [NO, 2*NO)) and x_lo . w_hi accumulated onto columns [0, NO); the epilogue adds the halves.
+      constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t((2 * NO) >> 3) << 17) | (uint32_t(kTile >> 4) << 24);
+      constexpr uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(NO >> 3) << 17) | (uint32_t(kTile >> 4) << 24);
       mbar_wait(wbar, 0);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
         mbar_wait(tmem_empty(ab), ((it >> 1) & 1) ^ 1);
         mbar_wait(full(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + uint32_t(ab * 32);
+        const uint32_t tacc = tmem_base + uint32_t(ab * 64);
         const uint32_t st = sX + stage * stage_bytes;
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
@@ -139,12 +142,11 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
 #pragma unroll
           for (int kp = 0; kp < KP; ++kp) {
             const uint32_t xa = st + uint32_t(2 * kp) * chb + shift;
-            const uint32_t wa = sW + uint32_t((tap * KP + kp) * 2 * NO) * 16u;
+            const uint32_t wa = sW + uint32_t((tap * KP + kp) * 2 * 2 * NO) * 16u;
             const uint64_t dah = desc_k_noswz(xa, chb, 128u), dal = desc_k_noswz(xa + CH * chb, chb, 128u);
-            const uint64_t dbh = desc_k_noswz(wa, NO * 16u, 128u), dbl = desc_k_noswz(wa + W_PLANE, NO * 16u, 128u);
-            umma_bf16(tacc, dal, dbh, idesc, (tap | kp) != 0 ? 1u : 0u);
-            umma_bf16(tacc, dah, dbl, idesc, 1u);
-            umma_bf16(tacc, dah, dbh, idesc, 1u);
+            const uint64_t dbw = desc_k_noswz(wa, 2u * NO * 16u, 128u);   // rows [0, NO) = hi, [NO, 2*NO) = lo
+            umma_bf16(tacc, dah, dbw, idesc2, (tap | kp) != 0 ? 1u : 0u);
+            umma_bf16(tacc, dal, dbw, idesc1, 1u);
           }
         }
         umma_commit(empty(stage));
@@ -168,15 +170,17 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
       }
       mbar_wait(tmem_full(ab), (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(ab * 32), v);
+      uint32_t v[32], v2[32];
+      tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(ab * 64), v);
+      if (NO == 32) tmem_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(ab * 64 + 32), v2);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty(ab));   // the values are in registers: the buffer can be refilled
       if (valid) {
         float o[NO];
 #pragma unroll
-        for (int j = 0; j < NO; ++j) o[j] = __uint_as_float(v[j]) * a.scale;
+        for (int j = 0; j < NO; ++j)   // lo.hi + hi.hi (columns [0, NO)) + hi.lo (columns [NO, 2*NO))
+          o[j] = (__uint_as_float(v[j]) + __uint_as_float(NO == 32 ? v2[j] : v[(j + NO) & 31])) * a.scale;
         if (a.bias) {
 #pragma unroll
           for (int q = 0; q < NO / 4; ++q) {
@@ -525,14 +529,15 @@ __global__ void __launch_bounds__(256) sw_colsum_final_kernel(const float* __res
   if (threadIdx.x == 0) out[c] = red[0];
 }
 
-__global__ void sw_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int64_t lo_off, int O, int C,
-                                       int transpose, int c_real) {
+__global__ void sw_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int C, int transpose,
+                                       int c_real) {
   const int R = transpose ? C : O, K = transpose ? O : C;   // operand rows, reduction channels
   const int64_t total = int64_t(9) * K * R;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    // i = (((tap*KP + kp)*2 + j)*R + r)*8 + e
+    // hi element index i = (((tap*KP + kp)*2 + j)*R + r)*8 + e; stored at row r (hi) and row R + r (lo) of a 2R-row block
     const int e = int(i & 7);
     int64_t t = i >> 3;
+    const int64_t blk = t / R;                     // ((tap*KP + kp)*2 + j)
     const int r = int(t % R); t /= R;
     const int j = int(t & 1); t >>= 1;
     const int KP = K / 16;
@@ -544,8 +549,8 @@ __global__ void sw_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat1
     if (transpose) v = w[((int64_t(k) * C + r) * 3 + (2 - a)) * 3 + (2 - b)];
     else v = k < c_real ? w[((int64_t(r) * c_real + k) * 3 + a) * 3 + b] : 0.0f;
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    out[i] = h;
-    out[lo_off + i] = bf16_lo_of(v, h);
+    out[(blk * 2 * R + r) * 8 + e] = h;
+    out[(blk * 2 * R + R + r) * 8 + e] = bf16_lo_of(v, h);
   }
 }
 
@@ -593,13 +598,13 @@ int sw_frames_u8(const uint8_t* frame, __nv_bfloat16* out, int64_t lo_off, int64
   return check_launch("sw_frames_u8_kernel");
 }
 
-int64_t sw_weight_elems(int O, int C) { return int64_t(9) * O * C; }
+int64_t sw_weight_elems(int O, int C) { return int64_t(2) * 9 * O * C; }
 
-int sw_pack_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream, int c_real) {
-  TB_REQUIRE(O % 16 == 0 && C % 16 == 0 && lo_off % 8 == 0, "sw_pack_weights: channel counts must be multiples of 16");
+int sw_pack_weights(const float* w, __nv_bfloat16* out, int O, int C, int transpose, cudaStream_t stream, int c_real) {
+  TB_REQUIRE(O % 16 == 0 && C % 16 == 0, "sw_pack_weights: channel counts must be multiples of 16");
   TB_REQUIRE(c_real == 0 || (!transpose && c_real <= C), "sw_pack_weights: c_real only for the forward operand");
-  const int64_t total = sw_weight_elems(O, C);
-  sw_pack_weights_kernel<<<sgrid(total, 256), 256, 0, stream>>>(w, out, lo_off, O, C, transpose, c_real > 0 ? c_real : C);
+  const int64_t total = int64_t(9) * O * C;
+  sw_pack_weights_kernel<<<sgrid(total, 256), 256, 0, stream>>>(w, out, O, C, transpose, c_real > 0 ? c_real : C);
   return check_launch("sw_pack_weights_kernel");
 }
 
@@ -609,18 +614,18 @@ bool sw_conv_applicable(int H, int W, int CK, int NO) {
   return (CK == 16 || CK == 32) && (NO == 16 || NO == 32) && H >= 3 && W >= 3 && W <= 126;
 }
 
-int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* wk, int64_t wk_lo, float* out, int64_t Nf, int H, int W,
-                int CK, int NO, const SwEpilogue& ep, cudaStream_t stream) {
-  TB_REQUIRE(img && wk && out && img_lo > 0 && wk_lo > 0, "sw_conv_fwd: null pointer");
+int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* wk, float* out, int64_t Nf, int H, int W, int CK, int NO,
+                const SwEpilogue& ep, cudaStream_t stream) {
+  TB_REQUIRE(img && wk && out && img_lo > 0, "sw_conv_fwd: null pointer");
   TB_REQUIRE(sw_conv_applicable(H, W, CK, NO), "sw_conv_fwd: unsupported shape");
   TB_REQUIRE((reinterpret_cast<uintptr_t>(img) & 15) == 0 && (reinterpret_cast<uintptr_t>(wk) & 15) == 0 && img_lo % 8 == 0 &&
-                 wk_lo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 (reinterpret_cast<uintptr_t>(out) & 15) == 0,
              "sw_conv_fwd: operands must be 16-byte aligned");
   if (Nf == 0) return 0;
   TB_REQUIRE(Nf * sw_geom(H, W).tpf < (int64_t(1) << 31), "sw_conv_fwd: too many tiles");
   ProfScope prof(ep.tag, stream);
   SwFwdArgs a;
-  a.img = img; a.img_lo = img_lo; a.wk = wk; a.wk_lo = wk_lo; a.out = out; a.bias = ep.bias; a.mask = ep.mask; a.addend = ep.addend;
+  a.img = img; a.img_lo = img_lo; a.wk = wk; a.out = out; a.bias = ep.bias; a.mask = ep.mask; a.addend = ep.addend;
   a.scale = ep.scale; a.Nf = int(Nf); a.g = sw_geom(H, W);
   if (CK == 16 && NO == 16) return launch_sw_fwd<16, 16>(a, stream);
   if (CK == 16 && NO == 32) return launch_sw_fwd<16, 32>(a, stream);

@@ -22,13 +22,13 @@ int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int6
 // zero; pixel values 0..255 are exact in bf16): the first convolution of the net through the same kernels
 int sw_frames_u8(const uint8_t* frame, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int Cf, int H, int W, cudaStream_t stream);
 
-// weights [O, C, 3, 3] fp32 -> the shared-memory image of the B operand, hi / lo planes of sw_weight_elems(O, C) elements:
-//   transpose == 0 (forward):        rows = O, K = C:  [tap][C/16][2][O][8]
-//   transpose == 1 (input gradient): rows = C, K = O:  [tap][O/16][2][C][8] with flipped taps (W[o, c, 2-a, 2-b])
+// weights [O, C, 3, 3] fp32 -> the shared-memory image of the B operand (sw_weight_elems(O, C) elements; R operand rows,
+// the hi rows of a block followed by its lo rows so that [w_hi | w_lo] is one 2R-row operand):
+//   transpose == 0 (forward):        R = O, K = C:  [tap][C/16][2][hi R rows | lo R rows][8]
+//   transpose == 1 (input gradient): R = C, K = O:  [tap][O/16][2][hi R rows | lo R rows][8] with flipped taps (W[o, c, 2-a, 2-b])
 int64_t sw_weight_elems(int O, int C);
 // c_real > 0 (forward only): the weight tensor has c_real < C input channels, the rest of the operand is zero
-int sw_pack_weights(const float* w, __nv_bfloat16* out, int64_t lo_off, int O, int C, int transpose, cudaStream_t stream,
-                    int c_real = 0);
+int sw_pack_weights(const float* w, __nv_bfloat16* out, int O, int C, int transpose, cudaStream_t stream, int c_real = 0);
 
 struct SwEpilogue {
   float scale = 1.0f;              // applied to the accumulator first (1/255 for uint8 frames)
@@ -41,8 +41,8 @@ struct SwEpilogue {
 bool sw_conv_applicable(int H, int W, int CK, int NO);
 // out fp32 [Nf*H*W, NO] = epilogue(conv3x3(image) with the packed weights); CK = channels of the image (16 / 32),
 // NO = output channels (16 / 32)
-int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* wk, int64_t wk_lo, float* out, int64_t Nf, int H, int W,
-                int CK, int NO, const SwEpilogue& ep, cudaStream_t stream);
+int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* wk, float* out, int64_t Nf, int H, int W, int CK, int NO,
+                const SwEpilogue& ep, cudaStream_t stream);
 
 // weight gradient dW[O, C, 3, 3] (fp32, reference layout) = sum over pixels dY (x) windows(x): dyimg = padded planar image of
 // dL/d(conv output) (O channels), ximg = padded planar image of the conv's input (C channels); partial: split scratch

@@ -176,13 +176,13 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
         {   // (the 4 frame channels of the first conv are padded to 16)
           const int cin16 = kSecCin[i] < 16 ? 16 : kSecCin[i];
           w.xp_feat[i] = takeh(sw_image_elems(N, kSecS[i], kSecS[i], cin16), w.xp_feat_lo[i]);
-          w.wi_feat[i] = takeh(sw_weight_elems(kSecCh[i], cin16), w.wi_feat_lo[i]);
+          w.wi_feat[i] = takeh(sw_weight_elems(kSecCh[i], cin16) / 2, w.wi_feat_lo[i]);
           const int64_t e = sw_image_elems(N, kSecS[i], kSecS[i], kSecCh[i]);
           if (e > maxp) maxp = e;
         }
         for (int j = 0; j < 4; ++j) {
           w.xp_blk[i][j] = takeh(sw_image_elems(N, kSecSo[i], kSecSo[i], kSecCh[i]), w.xp_blk_lo[i][j]);
-          w.wi_blk[i][j] = takeh(sw_weight_elems(kSecCh[i], kSecCh[i]), w.wi_blk_lo[i][j]);
+          w.wi_blk[i][j] = takeh(sw_weight_elems(kSecCh[i], kSecCh[i]) / 2, w.wi_blk_lo[i][j]);
         }
         const int64_t e = sw_image_elems(N, kSecSo[i], kSecSo[i], kSecCh[i]);
         if (e > maxp) maxp = e;
@@ -461,10 +461,10 @@ struct SplitImpl {
   static int conv_impl(const float* x, int relu_in, __nv_bfloat16* xp, int64_t xp_lo, const float* Wsrc, __nv_bfloat16* wi, int64_t wi_lo,
                        float* out, int64_t N, int S, int cin, int cout, const float* bias, const float* addend, const char* tag,
                        cudaStream_t st) {
-    TB_TRY(sw_pack_weights(Wsrc, wi, wi_lo, cout, cin, 0, st));
+    TB_TRY(sw_pack_weights(Wsrc, wi, cout, cin, 0, st));
     TB_TRY(sw_pad_split(x, xp, xp_lo, N, S, S, cin, relu_in, st));
     SwEpilogue ep; ep.bias = bias; ep.addend = addend; ep.tag = tag;
-    return sw_conv_fwd(xp, xp_lo, wi, wi_lo, out, N, S, S, cin, cout, ep, st);
+    return sw_conv_fwd(xp, xp_lo, wi, out, N, S, S, cin, cout, ep, st);
   }
 
   static int forward(const uint8_t* frame, const float* reward, const float* notdone, const float* h0, const float* c0,
@@ -492,10 +492,10 @@ struct SplitImpl {
       const int64_t cf_lo = w.colk_feat[i] ? w.colk_feat_lo[i] : w.colb_lo;
       if (i == 0 && w.xp_feat[0]) {
         // the first conv through the same kernels: frame pixels (exact in bf16) as a 16-channel image, 1/255 in the epilogue
-        TB_TRY(sw_pack_weights(P + pp.feat[0].w, w.wi_feat[0], w.wi_feat_lo[0], ch, 16, 0, st, 4));
+        TB_TRY(sw_pack_weights(P + pp.feat[0].w, w.wi_feat[0], ch, 16, 0, st, 4));
         TB_TRY(sw_frames_u8(frame, w.xp_feat[0], w.xp_feat_lo[0], N, 4, S, S, st));
         SwEpilogue ep; ep.scale = 1.0f / 255.0f; ep.bias = P + pp.feat[0].b; ep.tag = "feat_conv_fwd";
-        TB_TRY(sw_conv_fwd(w.xp_feat[0], w.xp_feat_lo[0], w.wi_feat[0], w.wi_feat_lo[0], w.s[0].P, N, S, S, 16, ch, ep, st));
+        TB_TRY(sw_conv_fwd(w.xp_feat[0], w.xp_feat_lo[0], w.wi_feat[0], w.s[0].P, N, S, S, 16, ch, ep, st));
       } else if (i == 0) {
         TB_TRY(first_patches(frame, cf, cf_lo, N, st));
         TB_TRY(gemm_fwd(cf, cf_lo, w.wb_feat[0], w.wb_feat_lo[0], w.s[0].P, M, ch, 36, ldk_in, P + pp.feat[0].b, nullptr,
@@ -551,9 +551,9 @@ struct SplitImpl {
     TB_TRY(sw_pad_split_colsum(dY, w.dyp, w.dyp_lo, N, S, S, cout, db, w.splitk, kScratchFloats, st));
     TB_TRY(sw_conv_wgrad(w.dyp, w.dyp_lo, xp, xp_lo, dW, N, S, S, cin, cout, w.splitk, kScratchFloats, wtag, st));
     if (dx) {
-      TB_TRY(sw_pack_weights(Wsrc, wd, wd_lo, cout, cin, 1, st));
+      TB_TRY(sw_pack_weights(Wsrc, wd, cout, cin, 1, st));
       SwEpilogue ep; ep.mask = relu_in ? x : nullptr; ep.addend = addend; ep.tag = "res_conv_dgrad";
-      TB_TRY(sw_conv_fwd(w.dyp, w.dyp_lo, wd, wd_lo, dx, N, S, S, cout, cin, ep, st));
+      TB_TRY(sw_conv_fwd(w.dyp, w.dyp_lo, wd, dx, N, S, S, cout, cin, ep, st));
     }
     return 0;
   }
