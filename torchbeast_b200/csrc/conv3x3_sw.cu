@@ -407,15 +407,28 @@ __global__ void __launch_bounds__(kWgThreads, 1) sw_conv_wgrad_kernel(SwWgradArg
   }
 }
 
-// dW[o, c, kh, kw] = sum over CTAs (in order) of partial[cta][o][(kh*3 + kw)*C + c]
-__global__ void sw_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int ctas, int O, int C, int c_real,
-                                       float scale) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // index into dW [O, c_real, 3, 3]
-  if (i >= O * c_real * 9) return;
-  const int tap = i % 9, c = (i / 9) % c_real, o = i / (9 * c_real);
+// dW[o, c, kh, kw] = scale * sum over CTAs of partial[cta][o][(kh*3 + kw)*C + c].  Block = 32 consecutive partial columns x 8
+// CTA groups (coalesced 128-byte reads; a 148-iteration per-thread loop with strided reads took 24 us per conv - more than
+// a third of the weight-gradient kernels themselves); the 8 group sums are folded in a fixed order (deterministic).
+__global__ void __launch_bounds__(256) sw_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dW, int ctas,
+                                                              int O, int C, int c_real, float scale) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int q = blockIdx.x * 32 + lane;          // column of the [O][9*C] partial matrix
+  const int total = O * 9 * C;
   float s = 0.f;
-  for (int b = 0; b < ctas; ++b) s += partial[(int64_t(b) * O + o) * (9 * C) + tap * C + c];
-  dW[i] = s * scale;
+  if (q < total)
+    for (int b = g; b < ctas; b += 8) s += partial[int64_t(b) * total + q];
+  red[g][lane] = s;
+  __syncthreads();
+  if (g == 0 && q < total) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][lane];
+    const int o = q / (9 * C), col = q - o * (9 * C);
+    const int tap = col / C, c = col - tap * C;
+    if (c < c_real) dW[(int64_t(o) * c_real + c) * 9 + tap] = t * scale;
+  }
 }
 
 template <int C, int O>
@@ -513,20 +526,37 @@ __global__ void sw_frames_u8_kernel(const uint8_t* __restrict__ frame, __nv_bflo
   }
 }
 
-// out[c] = sum over the block partials, one block per channel, fixed association (deterministic)
-__global__ void __launch_bounds__(256) sw_colsum_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                                              int64_t blocks, int C) {
+// column sums of the block partials [blocks][C] in two levels (fixed association: deterministic): level 1 = kColsumSlices
+// blocks, each folding a contiguous slice of rows with coalesced reads (thread = (row group, channel)); level 2 = one block
+constexpr int kColsumSlices = 128;
+__global__ void __launch_bounds__(256) sw_colsum_l1_kernel(const float* __restrict__ partial, float* __restrict__ part2, int64_t blocks,
+                                                           int C) {
   __shared__ float red[256];
-  const int c = blockIdx.x;
+  const int c = threadIdx.x % C, rg = threadIdx.x / C, RG = 256 / C;
+  const int64_t per = (blocks + gridDim.x - 1) / gridDim.x;
+  const int64_t b0 = int64_t(blockIdx.x) * per, b1 = (b0 + per < blocks) ? b0 + per : blocks;
   float s = 0.f;
-  for (int64_t b = threadIdx.x; b < blocks; b += 256) s += partial[b * C + c];
+  for (int64_t b = b0 + rg; b < b1; b += RG) s += partial[b * C + c];
   red[threadIdx.x] = s;
   __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
-    if (int(threadIdx.x) < w) red[threadIdx.x] += red[threadIdx.x + w];
-    __syncthreads();
+  if (rg == 0) {
+    float t = red[c];
+    for (int k = 1; k < RG; ++k) t += red[k * C + c];
+    part2[int64_t(blockIdx.x) * C + c] = t;
   }
-  if (threadIdx.x == 0) out[c] = red[0];
+}
+__global__ void __launch_bounds__(256) sw_colsum_l2_kernel(const float* __restrict__ part2, float* __restrict__ out, int slices, int C) {
+  __shared__ float red[256];
+  const int c = threadIdx.x % C, rg = threadIdx.x / C, RG = 256 / C;
+  float s = 0.f;
+  for (int b = rg; b < slices; b += RG) s += part2[int64_t(b) * C + c];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (rg == 0) {
+    float t = red[c];
+    for (int k = 1; k < RG; ++k) t += red[k * C + c];
+    out[c] = t;
+  }
 }
 
 __global__ void sw_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int C, int transpose,
@@ -575,18 +605,21 @@ int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf,
 int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, float* db,
                         float* scratch, int64_t scratch_floats, cudaStream_t stream) {
   ProfScope prof("bias_grad_colsum", stream);
-  TB_REQUIRE(C % 8 == 0 && 256 % (C / 8) == 0 && C <= 256 && lo_off % 8 == 0 && Nf < 65536,
-             "sw_pad_split_colsum: unsupported channel / frame count");
+  TB_REQUIRE(C % 8 == 0 && 256 % C == 0 && lo_off % 8 == 0 && Nf < 65536, "sw_pad_split_colsum: unsupported channel / frame count");
   if (Nf == 0) return 0;
   const int ppb = 256 / (C / 8);
   dim3 grid(unsigned(((H + 2) * (W + 2) + ppb - 1) / ppb), unsigned(Nf));
   const int64_t blocks = int64_t(grid.x) * grid.y;
-  TB_REQUIRE(blocks * C <= scratch_floats, "sw_pad_split_colsum: scratch too small");
+  TB_REQUIRE((blocks + kColsumSlices) * C <= scratch_floats, "sw_pad_split_colsum: scratch too small");
   sw_pad_split_kernel<true><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, H, W, C / 8, 0, scratch);
   int rc = check_launch("sw_pad_split_kernel");
   if (rc) return rc;
-  sw_colsum_final_kernel<<<C, 256, 0, stream>>>(scratch, db, blocks, C);
-  return check_launch("sw_colsum_final_kernel");
+  float* part2 = scratch + blocks * C;
+  sw_colsum_l1_kernel<<<kColsumSlices, 256, 0, stream>>>(scratch, part2, blocks, C);
+  rc = check_launch("sw_colsum_l1_kernel");
+  if (rc) return rc;
+  sw_colsum_l2_kernel<<<1, 256, 0, stream>>>(part2, db, kColsumSlices, C);
+  return check_launch("sw_colsum_l2_kernel");
 }
 
 int sw_frames_u8(const uint8_t* frame, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int Cf, int H, int W, cudaStream_t stream) {
@@ -653,8 +686,7 @@ int sw_conv_wgrad(const __nv_bfloat16* dyimg, int64_t dy_lo, const __nv_bfloat16
   else rc = launch_sw_wgrad<32, 32>(a, int(grid), stream);
   if (rc) return rc;
   if (c_real <= 0 || c_real > C) c_real = C;
-  const int total_w = O * c_real * 9;
-  sw_wgrad_reduce_kernel<<<(total_w + 255) / 256, 256, 0, stream>>>(partial, dW, int(grid), O, C, c_real, scale);
+  sw_wgrad_reduce_kernel<<<(O * 9 * C + 31) / 32, 256, 0, stream>>>(partial, dW, int(grid), O, C, c_real, scale);
   return check_launch("sw_wgrad_reduce_kernel");
 }
 
