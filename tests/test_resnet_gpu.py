@@ -167,3 +167,27 @@ def test_learn_step_at_one_gpu_shard_of_config4(precision):
         np.testing.assert_allclose(p.detach().cpu().flatten()[idx].numpy(), g["param_sample/" + n], rtol=1e-4, atol=5e-4, err_msg=n)
     for (n, a), (_, b) in zip(actor.named_parameters(), model.named_parameters()):
         assert torch.equal(a, b), n
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_results_do_not_depend_on_stale_workspace_contents(precision):
+    """The workspace comes from torch.empty: whatever a previous owner left there (here: all bytes 0xFF = NaN patterns in
+    fp32 and bf16) must not reach the results - every byte a kernel reads is written earlier in the same pass.  Caught a
+    real hazard: the weight-gradient kernel read 15 pixels of slack behind the last image plane, multiplied by exact
+    zeros (0 * NaN)."""
+    g, model, actor, batch, params, state, opt, sched, flags = build("learn_resnet_lstm_T4_B2.npz", precision)
+    cb = {k: v.cuda() for k, v in batch.items()}
+    st = tuple(s.cuda() for s in state)
+    rs = np.random.RandomState(1)
+    runs = []
+    for fill in (None, 255, 0):
+        if fill is not None:
+            model._ws.fill_(fill)
+        out = model.learner_forward(cb, st)
+        w1 = torch.from_numpy(rs.randn(*out.policy_logits.shape)).float().cuda() if not runs else runs[0][2]
+        w2 = torch.from_numpy(rs.randn(*out.baseline.shape)).float().cuda() if not runs else runs[0][3]
+        model.learner_backward(w1.contiguous(), w2.contiguous())
+        runs.append((out.policy_logits.clone(), model.flat_grads.clone(), w1, w2))
+    for logits, grads, _, _ in runs[1:]:
+        assert torch.isfinite(grads).all()
+        assert torch.equal(logits, runs[0][0]) and torch.equal(grads, runs[0][1])

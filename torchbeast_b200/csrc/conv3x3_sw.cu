@@ -591,6 +591,19 @@ int64_t sw_image_elems(int64_t Nf, int H, int W, int C) {
   return Nf * (C / 8) * g.plane + int64_t(g.pin + 8) * 8;   // + the window overhang of the last frame's last tile
 }
 
+// The weight-gradient kernel's last k16 step of a frame reads up to 15 pixels past the frame's last chunk plane (multiplied by
+// the zeros of the dY image's padding): for the last frame that is the slack behind the image, which must therefore hold
+// finite values - uninitialised memory can be a NaN pattern and 0 * NaN poisons the accumulator.  Zero it with the image.
+static int zero_slack(__nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, cudaStream_t stream) {
+  const SwGeom g = sw_geom(H, W);
+  const int64_t body = Nf * (C / 8) * g.plane;
+  const size_t bytes = size_t(g.pin + 8) * 8 * sizeof(__nv_bfloat16);
+  cudaError_t e = cudaMemsetAsync(out + body, 0, bytes, stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(out + lo_off + body, 0, bytes, stream);
+  TB_REQUIRE(e == cudaSuccess, "conv3x3_sw: memset: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, int relu_in,
                  cudaStream_t stream) {
   ProfScope prof("pad_split", stream);
@@ -598,6 +611,7 @@ int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf,
   if (Nf == 0) return 0;
   const int ppb = 256 / (C / 8);
   dim3 grid(unsigned(((H + 2) * (W + 2) + ppb - 1) / ppb), unsigned(Nf));
+  if (int rc = zero_slack(out, lo_off, Nf, H, W, C, stream)) return rc;
   sw_pad_split_kernel<false><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, H, W, C / 8, relu_in, nullptr);
   return check_launch("sw_pad_split_kernel");
 }
@@ -611,6 +625,7 @@ int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int6
   dim3 grid(unsigned(((H + 2) * (W + 2) + ppb - 1) / ppb), unsigned(Nf));
   const int64_t blocks = int64_t(grid.x) * grid.y;
   TB_REQUIRE((blocks + kColsumSlices) * C <= scratch_floats, "sw_pad_split_colsum: scratch too small");
+  if (int rc0 = zero_slack(out, lo_off, Nf, H, W, C, stream)) return rc0;
   sw_pad_split_kernel<true><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, H, W, C / 8, 0, scratch);
   int rc = check_launch("sw_pad_split_kernel");
   if (rc) return rc;
@@ -627,6 +642,7 @@ int sw_frames_u8(const uint8_t* frame, __nv_bfloat16* out, int64_t lo_off, int64
   TB_REQUIRE(Cf >= 1 && Cf <= 8 && lo_off % 8 == 0, "sw_frames_u8: at most 8 frame channels");
   const int64_t total = Nf * 2 * (H + 2) * (W + 2);
   if (total == 0) return 0;
+  if (int rc = zero_slack(out, lo_off, Nf, H, W, 16, stream)) return rc;
   sw_frames_u8_kernel<<<sgrid(total, 256), 256, 0, stream>>>(frame, out, lo_off, Nf, Cf, H, W);
   return check_launch("sw_frames_u8_kernel");
 }
