@@ -187,7 +187,7 @@ def test_results_do_not_depend_on_stale_workspace_contents(precision):
         w1 = torch.from_numpy(rs.randn(*out.policy_logits.shape)).float().cuda() if not runs else runs[0][2]
         w2 = torch.from_numpy(rs.randn(*out.baseline.shape)).float().cuda() if not runs else runs[0][3]
         model.learner_backward(w1.contiguous(), w2.contiguous())
-        runs.append((out.policy_logits.clone(), model.flat_grads.clone(), w1, w2))
+        runs.append((out.policy_logits.clone(), model.flat_grad.clone(), w1, w2))
     for logits, grads, _, _ in runs[1:]:
         assert torch.isfinite(grads).all()
         assert torch.equal(logits, runs[0][0]) and torch.equal(grads, runs[0][1])
