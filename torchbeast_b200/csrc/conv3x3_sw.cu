@@ -455,14 +455,26 @@ static inline unsigned sgrid(int64_t work, int threads) {
   return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
+// The weight-gradient kernel's last k16 step of a frame reads up to 15 pixels past the frame's last chunk plane (multiplied by
+// the zeros of the dY image's padding): for the last frame that is the slack behind the image, which must hold finite
+// values - stale memory can be a NaN pattern and 0 * NaN poisons the accumulator.  The first block of an image producer
+// zeroes the slack of both planes (`units` 16-byte units starting `body` elements into a plane).
+__device__ __forceinline__ void zero_slack_units(__nv_bfloat16* out, int64_t lo_off, int64_t body, int units) {
+  for (int u = threadIdx.x; u < units; u += blockDim.x) {
+    *reinterpret_cast<uint4*>(out + body + int64_t(u) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(out + lo_off + body + int64_t(u) * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // one thread = 8 channels of one padded pixel (borders written as zeros every time: the buffers are shared between images);
 // block = 256 / C8 consecutive padded pixels of frame blockIdx.y x all chunk planes (32-bit index arithmetic: one division).
 // COLSUM: block partial sums of the C channels -> partial[(frame * gridDim.x + blockIdx.x) * C + c]
 template <bool COLSUM>
 __global__ void __launch_bounds__(256) sw_pad_split_kernel(const float4* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                            int64_t lo_off, int H, int W, int C8, int relu_in,
-                                                           float* __restrict__ partial) {
+                                                           float* __restrict__ partial, int slack_units) {
   const int Hp = H + 2, Wp = W + 2;
+  if (blockIdx.x == 0 && blockIdx.y == 0) zero_slack_units(out, lo_off, int64_t(gridDim.y) * C8 * Hp * Wp * 8, slack_units);
   const int cv = threadIdx.x % C8;
   const int p = blockIdx.x * (256 / C8) + threadIdx.x / C8;
   const int64_t n = blockIdx.y;
@@ -499,11 +511,65 @@ __global__ void __launch_bounds__(256) sw_pad_split_kernel(const float4* __restr
   }
 }
 
+// Max-pool backward fused with the image producer: the gradient of the feat conv's output (dL/dP, [N, H, W, C]) is only ever
+// consumed as the dY image of that conv's backward (and its column sums = the bias gradient), so it is gathered from the
+// pooled gradient dyp [N, OH, OW, C] through the recorded argmax taps (gather form of nn.MaxPool2d(3, 2, 1) backward: pixel
+// (iy, ix) sums the <= 4 windows whose first maximum it was) straight into the padded planar hi / lo image - no fp32
+// [N, H, W, C] round trip.  Same grid / column-sum scheme as sw_pad_split_kernel<true>.
+__global__ void __launch_bounds__(256) sw_pool_bwd_image_kernel(const uint8_t* __restrict__ arg, const float4* __restrict__ dyp,
+                                                                __nv_bfloat16* __restrict__ out, int64_t lo_off, int H, int W, int OH,
+                                                                int OW, int C8, float* __restrict__ partial, int slack_units) {
+  const int Hp = H + 2, Wp = W + 2;
+  if (blockIdx.x == 0 && blockIdx.y == 0) zero_slack_units(out, lo_off, int64_t(gridDim.y) * C8 * Hp * Wp * 8, slack_units);
+  const int cv = threadIdx.x % C8;
+  const int p = blockIdx.x * (256 / C8) + threadIdx.x / C8;
+  const int64_t n = blockIdx.y;
+  float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (p < Hp * Wp) {
+    const int py = p / Wp, px = p - py * Wp;
+    uint4 ph = make_uint4(0u, 0u, 0u, 0u), pl = ph;
+    if (py >= 1 && py <= H && px >= 1 && px <= W) {
+      const int iy = py - 1, ix = px - 1;
+      for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {
+        if (oy >= OH) continue;
+        const int kh = iy - (oy * 2 - 1);
+        for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
+          if (ox >= OW) continue;
+          const uint32_t tap = uint32_t(kh * 3 + (ix - (ox * 2 - 1)));
+          const int64_t o = ((n * OH + oy) * OW + ox) * C8 + cv;            // 8-channel group of the pooled pixel
+          const float4 d0 = __ldg(dyp + o * 2), d1 = __ldg(dyp + o * 2 + 1);
+          const uint2 a = __ldg(reinterpret_cast<const uint2*>(arg) + o);   // 8 argmax bytes
+          g[0] += ((a.x) & 0xffu) == tap ? d0.x : 0.f; g[1] += ((a.x >> 8) & 0xffu) == tap ? d0.y : 0.f;
+          g[2] += ((a.x >> 16) & 0xffu) == tap ? d0.z : 0.f; g[3] += (a.x >> 24) == tap ? d0.w : 0.f;
+          g[4] += ((a.y) & 0xffu) == tap ? d1.x : 0.f; g[5] += ((a.y >> 8) & 0xffu) == tap ? d1.y : 0.f;
+          g[6] += ((a.y >> 16) & 0xffu) == tap ? d1.z : 0.f; g[7] += (a.y >> 24) == tap ? d1.w : 0.f;
+        }
+      }
+      split_bf16x2(g[0], g[1], ph.x, pl.x); split_bf16x2(g[2], g[3], ph.y, pl.y);
+      split_bf16x2(g[4], g[5], ph.z, pl.z); split_bf16x2(g[6], g[7], ph.w, pl.w);
+    }
+    __nv_bfloat16* dst = out + ((n * C8 + cv) * int64_t(Hp) * Wp + p) * 8;
+    *reinterpret_cast<uint4*>(dst) = ph;
+    *reinterpret_cast<uint4*>(dst + lo_off) = pl;
+  }
+  __shared__ float red[256][9];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = g[j];
+  __syncthreads();
+  if (int(threadIdx.x) < C8 * 8) {
+    const int c8 = threadIdx.x / 8, j = threadIdx.x % 8;
+    float t = 0.f;
+    for (int k = c8; k < 256; k += C8) t += red[k][j];   // fixed order
+    partial[(n * gridDim.x + blockIdx.x) * (C8 * 8) + c8 * 8 + j] = t;
+  }
+}
+
 // uint8 NCHW frames -> 16-channel padded planar image: chunk 0 = the Cf frame channels (+ zeros), chunk 1 = zeros, lo = zeros
 __global__ void sw_frames_u8_kernel(const uint8_t* __restrict__ frame, __nv_bfloat16* __restrict__ out, int64_t lo_off, int64_t Nf,
-                                    int Cf, int H, int W) {
+                                    int Cf, int H, int W, int slack_units) {
   const int Hp = H + 2, Wp = W + 2;
   const int64_t total = Nf * 2 * Hp * Wp;
+  if (blockIdx.x == 0) zero_slack_units(out, lo_off, total * 8, slack_units);
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
     const int px = int(i % Wp);
@@ -591,19 +657,6 @@ int64_t sw_image_elems(int64_t Nf, int H, int W, int C) {
   return Nf * (C / 8) * g.plane + int64_t(g.pin + 8) * 8;   // + the window overhang of the last frame's last tile
 }
 
-// The weight-gradient kernel's last k16 step of a frame reads up to 15 pixels past the frame's last chunk plane (multiplied by
-// the zeros of the dY image's padding): for the last frame that is the slack behind the image, which must therefore hold
-// finite values - uninitialised memory can be a NaN pattern and 0 * NaN poisons the accumulator.  Zero it with the image.
-static int zero_slack(__nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, cudaStream_t stream) {
-  const SwGeom g = sw_geom(H, W);
-  const int64_t body = Nf * (C / 8) * g.plane;
-  const size_t bytes = size_t(g.pin + 8) * 8 * sizeof(__nv_bfloat16);
-  cudaError_t e = cudaMemsetAsync(out + body, 0, bytes, stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(out + lo_off + body, 0, bytes, stream);
-  TB_REQUIRE(e == cudaSuccess, "conv3x3_sw: memset: %s", cudaGetErrorString(e));
-  return 0;
-}
-
 int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, int relu_in,
                  cudaStream_t stream) {
   ProfScope prof("pad_split", stream);
@@ -611,8 +664,8 @@ int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf,
   if (Nf == 0) return 0;
   const int ppb = 256 / (C / 8);
   dim3 grid(unsigned(((H + 2) * (W + 2) + ppb - 1) / ppb), unsigned(Nf));
-  if (int rc = zero_slack(out, lo_off, Nf, H, W, C, stream)) return rc;
-  sw_pad_split_kernel<false><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, H, W, C / 8, relu_in, nullptr);
+  sw_pad_split_kernel<false><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, H, W, C / 8, relu_in, nullptr,
+                                                       sw_geom(H, W).pin + 8);
   return check_launch("sw_pad_split_kernel");
 }
 
@@ -625,9 +678,32 @@ int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int6
   dim3 grid(unsigned(((H + 2) * (W + 2) + ppb - 1) / ppb), unsigned(Nf));
   const int64_t blocks = int64_t(grid.x) * grid.y;
   TB_REQUIRE((blocks + kColsumSlices) * C <= scratch_floats, "sw_pad_split_colsum: scratch too small");
-  if (int rc0 = zero_slack(out, lo_off, Nf, H, W, C, stream)) return rc0;
-  sw_pad_split_kernel<true><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, H, W, C / 8, 0, scratch);
+  sw_pad_split_kernel<true><<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(x), out, lo_off, H, W, C / 8, 0, scratch,
+                                                      sw_geom(H, W).pin + 8);
   int rc = check_launch("sw_pad_split_kernel");
+  if (rc) return rc;
+  float* part2 = scratch + blocks * C;
+  sw_colsum_l1_kernel<<<kColsumSlices, 256, 0, stream>>>(scratch, part2, blocks, C);
+  rc = check_launch("sw_colsum_l1_kernel");
+  if (rc) return rc;
+  sw_colsum_l2_kernel<<<1, 256, 0, stream>>>(part2, db, kColsumSlices, C);
+  return check_launch("sw_colsum_l2_kernel");
+}
+
+int sw_pool_bwd_image_colsum(const uint8_t* argmax, const float* dy_pooled, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W,
+                             int C, float* db, float* scratch, int64_t scratch_floats, cudaStream_t stream) {
+  ProfScope prof("maxpool_bwd", stream);
+  TB_REQUIRE(C % 8 == 0 && 256 % C == 0 && lo_off % 8 == 0 && Nf < 65536, "sw_pool_bwd_image_colsum: unsupported channel / frame count");
+  TB_REQUIRE((reinterpret_cast<uintptr_t>(argmax) & 7) == 0, "sw_pool_bwd_image_colsum: argmax must be 8-byte aligned");
+  if (Nf == 0) return 0;
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  const int ppb = 256 / (C / 8);
+  dim3 grid(unsigned(((H + 2) * (W + 2) + ppb - 1) / ppb), unsigned(Nf));
+  const int64_t blocks = int64_t(grid.x) * grid.y;
+  TB_REQUIRE((blocks + kColsumSlices) * C <= scratch_floats, "sw_pool_bwd_image_colsum: scratch too small");
+  sw_pool_bwd_image_kernel<<<grid, 256, 0, stream>>>(argmax, reinterpret_cast<const float4*>(dy_pooled), out, lo_off, H, W, OH, OW,
+                                                     C / 8, scratch, sw_geom(H, W).pin + 8);
+  int rc = check_launch("sw_pool_bwd_image_kernel");
   if (rc) return rc;
   float* part2 = scratch + blocks * C;
   sw_colsum_l1_kernel<<<kColsumSlices, 256, 0, stream>>>(scratch, part2, blocks, C);
@@ -642,8 +718,7 @@ int sw_frames_u8(const uint8_t* frame, __nv_bfloat16* out, int64_t lo_off, int64
   TB_REQUIRE(Cf >= 1 && Cf <= 8 && lo_off % 8 == 0, "sw_frames_u8: at most 8 frame channels");
   const int64_t total = Nf * 2 * (H + 2) * (W + 2);
   if (total == 0) return 0;
-  if (int rc = zero_slack(out, lo_off, Nf, H, W, 16, stream)) return rc;
-  sw_frames_u8_kernel<<<sgrid(total, 256), 256, 0, stream>>>(frame, out, lo_off, Nf, Cf, H, W);
+  sw_frames_u8_kernel<<<sgrid(total, 256), 256, 0, stream>>>(frame, out, lo_off, Nf, Cf, H, W, sw_geom(H, W).pin + 8);
   return check_launch("sw_frames_u8_kernel");
 }
 

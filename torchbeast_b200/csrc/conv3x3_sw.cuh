@@ -18,6 +18,11 @@ int sw_pad_split(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf,
 int sw_pad_split_colsum(const float* x, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W, int C, float* db,
                         float* scratch, int64_t scratch_floats, cudaStream_t stream);
 
+// nn.MaxPool2d(3, 2, 1) backward fused with the image producer: dy_pooled [Nf, OH, OW, C] fp32 + the forward's argmax taps ->
+// the padded planar hi / lo image of dL/d(pool input) [Nf, H, W, C] and its column sums db[C] (never materialised in fp32)
+int sw_pool_bwd_image_colsum(const uint8_t* argmax, const float* dy_pooled, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int H, int W,
+                             int C, float* db, float* scratch, int64_t scratch_floats, cudaStream_t stream);
+
 // uint8 NCHW frames [Nf, Cf <= 8, H, W] -> padded planar image with 16 channels (channels >= Cf and the whole lo plane are
 // zero; pixel values 0..255 are exact in bf16): the first convolution of the net through the same kernels
 int sw_frames_u8(const uint8_t* frame, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int Cf, int H, int W, cudaStream_t stream);

@@ -548,7 +548,7 @@ struct SplitImpl {
   static int conv_bwd_impl(const float* x, bool relu_in, const float* dY, const float* Wsrc, const __nv_bfloat16* xp, int64_t xp_lo,
                            __nv_bfloat16* wd, int64_t wd_lo, float* dW, float* db, float* dx, const float* addend, int64_t N, int S,
                            int cin, int cout, W& w, const char* wtag, cudaStream_t st) {
-    TB_TRY(sw_pad_split_colsum(dY, w.dyp, w.dyp_lo, N, S, S, cout, db, w.splitk, kScratchFloats, st));
+    if (dY) TB_TRY(sw_pad_split_colsum(dY, w.dyp, w.dyp_lo, N, S, S, cout, db, w.splitk, kScratchFloats, st));   // nullptr: w.dyp is ready
     TB_TRY(sw_conv_wgrad(w.dyp, w.dyp_lo, xp, xp_lo, dW, N, S, S, cin, cout, w.splitk, kScratchFloats, wtag, st));
     if (dx) {
       TB_TRY(sw_pack_weights(Wsrc, wd, cout, cin, 1, st));
@@ -627,10 +627,14 @@ struct SplitImpl {
           TB_TRY(conv_bwd(xs[j], true, dys[j], P + pp.blk[i][j].w, w.colk_blk[i][j], w.colk_blk_lo[i][j], w.wd_blk[i][j], w.wd_blk_lo[i][j],
                           G + pp.blk[i][j].w, G + pp.blk[i][j].b, dxs[j], skip[j], N, So, ch, ch, w, st));
       }
-      TB_TRY(maxpool3x3s2_bwd<float>(s.arg, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
+      // dL/dP (the feat conv's output gradient) is consumed only as that conv's dY image + bias gradient: with the
+      // shifted-window kernels the max-pool backward gathers straight into the image (never materialised in fp32)
+      if (w.xp_feat[i])
+        TB_TRY(sw_pool_bwd_image_colsum(s.arg, g1, w.dyp, w.dyp_lo, N, S, S, ch, G + pp.feat[i].b, w.splitk, kScratchFloats, st));
+      else
+        TB_TRY(maxpool3x3s2_bwd<float>(s.arg, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
       const int64_t M = N * S * S;
       if (i == 0 && w.xp_feat[0]) {
-        TB_TRY(sw_pad_split_colsum(g2, w.dyp, w.dyp_lo, N, S, S, ch, G + pp.feat[0].b, w.splitk, kScratchFloats, st));
         TB_TRY(sw_conv_wgrad(w.dyp, w.dyp_lo, w.xp_feat[0], w.xp_feat_lo[0], G + pp.feat[0].w, N, S, S, 16, ch, w.splitk, kScratchFloats,
                              "feat_conv_wgrad", st, 1.0f / 255.0f, 4));
       } else if (i == 0) {
@@ -645,8 +649,9 @@ struct SplitImpl {
         TB_TRY(gemm_wgrad(w.dyb, w.dyb_lo, cf, cf_lo, G + pp.feat[0].w, M, ch, 36, ldk_in, 1, 1, 1.0f / 255.0f, w.splitk,
                           "feat_conv_wgrad", st));
       } else if (w.xp_feat[i]) {
-        TB_TRY(conv_bwd_impl(w.s[i - 1].X2, false, g2, P + pp.feat[i].w, w.xp_feat[i], w.xp_feat_lo[i], w.wd_feat[i], w.wd_feat_lo[i],
-                             G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S, cin, ch, w, "res_conv_wgrad", st));
+        TB_TRY(conv_bwd_impl(w.s[i - 1].X2, false, nullptr /* image + bias gradient done above */, P + pp.feat[i].w, w.xp_feat[i],
+                             w.xp_feat_lo[i], w.wd_feat[i], w.wd_feat_lo[i], G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S, cin, ch,
+                             w, "res_conv_wgrad", st));
       } else {
         TB_TRY(conv_bwd(w.s[i - 1].X2, false, g2, P + pp.feat[i].w, w.colk_feat[i], w.colk_feat_lo[i], w.wd_feat[i], w.wd_feat_lo[i],
                         G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S, cin, ch, w, st));
