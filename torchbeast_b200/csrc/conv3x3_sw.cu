@@ -58,6 +58,10 @@ struct SwFwdArgs {
   const __nv_bfloat16* img; int64_t img_lo;
   const __nv_bfloat16* wk;
   float* out; const float* bias; const float* mask; const float* addend; float scale;
+  // optional second output: the result (through ReLU if emit_relu) as the padded planar hi / lo image of the NEXT conv (same
+  // spatial size, NO channels), borders and slack included; and per (tile, epilogue warp) column sums of the result
+  // (csum[(tile*4 + warp)*NO + c]: the bias gradient when the result is a dY)
+  __nv_bfloat16* emit; int64_t emit_lo; int emit_relu; float* csum;
   int Nf; SwGeom g;
 };
 
@@ -81,6 +85,7 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
   const uint32_t wbar = bars + 8u * (2 * kSwStages + 4);
   const uint32_t tmem_slot = wbar + 8u;
   constexpr uint32_t TMEM_COLS = 128;  // two accumulator buffers of 2*NO <= 64 columns
+  __shared__ float csum_s[4][32][NO + 1];   // column-sum staging of the four epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_work = a.Nf * a.g.tpf;
@@ -176,8 +181,10 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty(ab));   // the values are in registers: the buffer can be refilled
+      float o[NO];
+#pragma unroll
+      for (int j = 0; j < NO; ++j) o[j] = 0.f;
       if (valid) {
-        float o[NO];
 #pragma unroll
         for (int j = 0; j < NO; ++j)   // lo.hi + hi.hi (columns [0, NO)) + hi.lo (columns [NO, 2*NO))
           o[j] = (__uint_as_float(v[j]) + __uint_as_float(NO == 32 ? v2[j] : v[(j + NO) & 31])) * a.scale;
@@ -209,6 +216,62 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
 #pragma unroll
         for (int q = 0; q < NO / 4; ++q) op[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
       }
+      if (a.emit) {
+        // Tile row p (an output pixel or a padding position of the flattened grid) is pixel p + Wp + 1 of the next image:
+        // valid rows carry the result, the others are exactly that image's side borders; the top border, what the last
+        // tile does not reach of the bottom border, and the slack behind the image are zeroed by the first / last tile.
+        const int hpwp = a.g.Hp * a.g.Wp, t = w - n * a.g.tpf;
+        const int64_t fbase = int64_t(n) * (NO / 8) * hpwp;
+        auto put = [&](int q, int c, uint4 ph, uint4 pl) {
+          __nv_bfloat16* dst = a.emit + (fbase + int64_t(c) * hpwp + q) * 8;
+          *reinterpret_cast<uint4*>(dst) = ph;
+          *reinterpret_cast<uint4*>(dst + a.emit_lo) = pl;
+        };
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        const int q = p + a.g.Wp + 1;
+        if (q < hpwp) {
+#pragma unroll
+          for (int c = 0; c < NO / 8; ++c) {
+            uint4 ph, pl;
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) e[j] = a.emit_relu ? fmaxf(o[8 * c + j], 0.f) : o[8 * c + j];
+            split_bf16x2(e[0], e[1], ph.x, pl.x); split_bf16x2(e[2], e[3], ph.y, pl.y);
+            split_bf16x2(e[4], e[5], ph.z, pl.z); split_bf16x2(e[6], e[7], ph.w, pl.w);
+            put(q, c, ph, pl);
+          }
+        }
+        if (t == 0 && rl < a.g.Wp + 1) {
+#pragma unroll
+          for (int c = 0; c < NO / 8; ++c) put(rl, c, z, z);
+        }
+        if (t == a.g.tpf - 1) {
+          const int q2 = a.g.tpf * kTile + a.g.Wp + 1 + rl;
+          if (q2 < hpwp) {
+#pragma unroll
+            for (int c = 0; c < NO / 8; ++c) put(q2, c, z, z);
+          }
+        }
+        if (w == 0) {   // slack behind the last frame (see zero_slack_units)
+          const int64_t body = int64_t(a.Nf) * (NO / 8) * hpwp * 8;
+          for (int u = rl; u < a.g.pin + 8; u += 128) {
+            *reinterpret_cast<uint4*>(a.emit + body + int64_t(u) * 8) = z;
+            *reinterpret_cast<uint4*>(a.emit + a.emit_lo + body + int64_t(u) * 8) = z;
+          }
+        }
+      }
+      if (a.csum) {   // per (tile, warp) column sums in a fixed order: rows of padding positions hold zeros
+#pragma unroll
+        for (int j = 0; j < NO; ++j) csum_s[quarter][lane][j] = o[j];
+        __syncwarp();
+        if (lane < NO) {
+          float sum = 0.f;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) sum += csum_s[quarter][rr][lane];
+          a.csum[(int64_t(w) * 4 + quarter) * NO + lane] = sum;
+        }
+        __syncwarp();
+      }
     }
   }
   __syncthreads();
@@ -230,7 +293,7 @@ int launch_sw_fwd(const SwFwdArgs& a, cudaStream_t stream) {
     TB_REQUIRE(e == cudaSuccess, "sw_conv_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr[dev & 63] = smem;
   }
-  int per_sm = int((220 * 1024) / smem);
+  int per_sm = int((224 * 1024) / (smem + sizeof(float) * 4 * 32 * (NO + 1) + 1024));   // + the static column-sum staging
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = int64_t(kNumSMsB200) * per_sm;
@@ -713,6 +776,19 @@ int sw_pool_bwd_image_colsum(const uint8_t* argmax, const float* dy_pooled, __nv
   return check_launch("sw_colsum_l2_kernel");
 }
 
+int64_t sw_csum_rows(int64_t Nf, int H, int W) { return Nf * sw_geom(H, W).tpf * 4; }
+
+int sw_csum_reduce(float* csum, int64_t rows, int C, float* db, cudaStream_t stream) {
+  ProfScope prof("bias_grad_colsum", stream);
+  TB_REQUIRE(256 % C == 0, "sw_csum_reduce: unsupported channel count");
+  float* part2 = csum + rows * C;
+  sw_colsum_l1_kernel<<<kColsumSlices, 256, 0, stream>>>(csum, part2, rows, C);
+  int rc = check_launch("sw_colsum_l1_kernel");
+  if (rc) return rc;
+  sw_colsum_l2_kernel<<<1, 256, 0, stream>>>(part2, db, kColsumSlices, C);
+  return check_launch("sw_colsum_l2_kernel");
+}
+
 int sw_frames_u8(const uint8_t* frame, __nv_bfloat16* out, int64_t lo_off, int64_t Nf, int Cf, int H, int W, cudaStream_t stream) {
   ProfScope prof("frames_to_image", stream);
   TB_REQUIRE(Cf >= 1 && Cf <= 8 && lo_off % 8 == 0, "sw_frames_u8: at most 8 frame channels");
@@ -751,6 +827,9 @@ int sw_conv_fwd(const __nv_bfloat16* img, int64_t img_lo, const __nv_bfloat16* w
   SwFwdArgs a;
   a.img = img; a.img_lo = img_lo; a.wk = wk; a.out = out; a.bias = ep.bias; a.mask = ep.mask; a.addend = ep.addend;
   a.scale = ep.scale; a.Nf = int(Nf); a.g = sw_geom(H, W);
+  a.emit = ep.emit; a.emit_lo = ep.emit_lo; a.emit_relu = ep.emit_relu; a.csum = ep.csum;
+  TB_REQUIRE(!ep.emit || (ep.emit_lo > 0 && ep.emit_lo % 8 == 0 && (reinterpret_cast<uintptr_t>(ep.emit) & 15) == 0),
+             "sw_conv_fwd: the emitted image needs a 16-byte aligned base and a lo plane");
   if (CK == 16 && NO == 16) return launch_sw_fwd<16, 16>(a, stream);
   if (CK == 16 && NO == 32) return launch_sw_fwd<16, 32>(a, stream);
   if (CK == 32 && NO == 16) return launch_sw_fwd<32, 16>(a, stream);

@@ -40,8 +40,18 @@ struct SwEpilogue {
   const float* bias = nullptr;     // [NO]
   const float* mask = nullptr;     // [M, NO] fp32: out = mask > 0 ? out : 0 (ReLU backward), applied before the addend
   const float* addend = nullptr;   // [M, NO] fp32 residual / skip gradient, applied last
+  // optional: also write the result (through ReLU if emit_relu) as the complete padded planar hi / lo image of the next conv
+  // (same H x W, NO channels; sw_image_elems(Nf, H, W, NO) elements per plane, lo plane at + emit_lo) - no separate
+  // sw_pad_split pass over the fp32 result
+  __nv_bfloat16* emit = nullptr; int64_t emit_lo = 0; int emit_relu = 0;
+  // optional: column sums of the result per (tile, epilogue warp): csum[sw_csum_rows(Nf, H, W)][NO] (+ 128*NO floats of
+  // scratch behind it for sw_csum_reduce) - the bias gradient of the next conv when the result is its dY
+  float* csum = nullptr;
   const char* tag = "conv3x3_sw";
 };
+int64_t sw_csum_rows(int64_t Nf, int H, int W);
+// db[C] = column sums of csum[rows][C] in a fixed order (uses csum[rows*C .. rows*C + 128*C) as scratch)
+int sw_csum_reduce(float* csum, int64_t rows, int C, float* db, cudaStream_t stream);
 
 bool sw_conv_applicable(int H, int W, int CK, int NO);
 // out fp32 [Nf*H*W, NO] = epilogue(conv3x3(image) with the packed weights); CK = channels of the image (16 / 32),

@@ -86,8 +86,8 @@ struct ResWs {
   // shifted-window implicit-GEMM path (conv3x3_sw.cuh; every 3x3 conv with 16 / 32 input channels): the conv's input as a
   // zero-padded channel-chunk-planar split-bf16 image, kept for the weight gradient; the image of dY (shared); weights in
   // the kernels' shared-memory layout
-  __nv_bfloat16 *xp_feat[kSections] = {nullptr, nullptr, nullptr}, *xp_blk[kSections][4] = {}, *dyp = nullptr;
-  int64_t xp_feat_lo[kSections] = {0, 0, 0}, xp_blk_lo[kSections][4] = {}, dyp_lo = 0;
+  __nv_bfloat16 *xp_feat[kSections] = {nullptr, nullptr, nullptr}, *xp_blk[kSections][4] = {}, *dyp = nullptr, *dyp2 = nullptr;
+  int64_t xp_feat_lo[kSections] = {0, 0, 0}, xp_blk_lo[kSections][4] = {}, dyp_lo = 0, dyp2_lo = 0;
   __nv_bfloat16 *wi_feat[kSections] = {nullptr, nullptr, nullptr}, *wi_blk[kSections][4] = {};
   int64_t wi_feat_lo[kSections] = {0, 0, 0}, wi_blk_lo[kSections][4] = {};
   __nv_bfloat16 *wb_feat[kSections] = {nullptr, nullptr, nullptr}, *wb_blk[kSections][4] = {}, *wb_fc = nullptr;
@@ -187,7 +187,8 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
         const int64_t e = sw_image_elems(N, kSecSo[i], kSecSo[i], kSecCh[i]);
         if (e > maxp) maxp = e;
       }
-      w.dyp = takeh(maxp, w.dyp_lo);
+      w.dyp = takeh(maxp, w.dyp_lo);     // dY images ping-pong: a conv's input-gradient epilogue writes the next conv's dY image
+      w.dyp2 = takeh(maxp, w.dyp2_lo);
     }
   }
   for (int i = 0; i < kSections; ++i) {
@@ -458,12 +459,14 @@ struct SplitImpl {
   }
 
   // shifted-window implicit GEMM: x fp32 NHWC -> padded planar split-bf16 image xp (kept for the weight gradient) -> out fp32
+  // x == nullptr: the previous conv's epilogue already wrote this conv's input image into xp.  emit: the NEXT conv's input
+  // image (this conv's output, through ReLU if emit_relu), written by the epilogue.
   static int conv_impl(const float* x, int relu_in, __nv_bfloat16* xp, int64_t xp_lo, const float* Wsrc, __nv_bfloat16* wi, int64_t wi_lo,
-                       float* out, int64_t N, int S, int cin, int cout, const float* bias, const float* addend, const char* tag,
-                       cudaStream_t st) {
+                       float* out, int64_t N, int S, int cin, int cout, const float* bias, const float* addend, __nv_bfloat16* emit,
+                       int64_t emit_lo, int emit_relu, const char* tag, cudaStream_t st) {
     TB_TRY(sw_pack_weights(Wsrc, wi, cout, cin, 0, st));
-    TB_TRY(sw_pad_split(x, xp, xp_lo, N, S, S, cin, relu_in, st));
-    SwEpilogue ep; ep.bias = bias; ep.addend = addend; ep.tag = tag;
+    if (x) TB_TRY(sw_pad_split(x, xp, xp_lo, N, S, S, cin, relu_in, st));
+    SwEpilogue ep; ep.bias = bias; ep.addend = addend; ep.emit = emit; ep.emit_lo = emit_lo; ep.emit_relu = emit_relu; ep.tag = tag;
     return sw_conv_fwd(xp, xp_lo, wi, out, N, S, S, cin, cout, ep, st);
   }
 
@@ -501,8 +504,9 @@ struct SplitImpl {
         TB_TRY(gemm_fwd(cf, cf_lo, w.wb_feat[0], w.wb_feat_lo[0], w.s[0].P, M, ch, 36, ldk_in, P + pp.feat[0].b, nullptr,
                         1.0f / 255.0f, 0, ch, "feat_conv_fwd", st));
       } else if (w.xp_feat[i]) {
-        TB_TRY(conv_impl(xin, 0, w.xp_feat[i], w.xp_feat_lo[i], P + pp.feat[i].w, w.wi_feat[i], w.wi_feat_lo[i], w.s[i].P, N, S, cin, ch,
-                         P + pp.feat[i].b, nullptr, "feat_conv_fwd", st));
+        // (its input image was written by the epilogue of the previous section's last conv)
+        TB_TRY(conv_impl(nullptr, 0, w.xp_feat[i], w.xp_feat_lo[i], P + pp.feat[i].w, w.wi_feat[i], w.wi_feat_lo[i], w.s[i].P, N, S, cin, ch,
+                         P + pp.feat[i].b, nullptr, nullptr, 0, 0, "feat_conv_fwd", st));
       } else {
         TB_TRY(im2col3x3_split(xin, cf, cf_lo, N, S, S, cin, ldk_in, 0, st));
         TB_TRY(gemm_fwd(cf, cf_lo, w.wb_feat[i], w.wb_feat_lo[i], w.s[i].P, M, ch, int64_t(cin) * 9, ldk_in,
@@ -514,8 +518,13 @@ struct SplitImpl {
       const float* adds[4] = {nullptr, w.s[i].X0, nullptr, w.s[i].X1};
       for (int j = 0; j < 4; ++j) {
         if (w.xp_blk[i][j]) {
-          TB_TRY(conv_impl(ins[j], 1, w.xp_blk[i][j], w.xp_blk_lo[i][j], P + pp.blk[i][j].w, w.wi_blk[i][j], w.wi_blk_lo[i][j], outs[j],
-                           N, So, ch, ch, P + pp.blk[i][j].b, adds[j], "res_conv_fwd", st));
+          // conv j's epilogue writes relu(output) as conv j+1's input image; the section's last conv writes the next
+          // section's feat-conv input (no ReLU there)
+          __nv_bfloat16* emit = j < 3 ? w.xp_blk[i][j + 1] : (i + 1 < kSections ? w.xp_feat[i + 1] : nullptr);
+          const int64_t emit_lo = j < 3 ? w.xp_blk_lo[i][j + 1] : (i + 1 < kSections ? w.xp_feat_lo[i + 1] : 0);
+          TB_TRY(conv_impl(j == 0 ? ins[0] : nullptr, 1, w.xp_blk[i][j], w.xp_blk_lo[i][j], P + pp.blk[i][j].w, w.wi_blk[i][j],
+                           w.wi_blk_lo[i][j], outs[j], N, So, ch, ch, P + pp.blk[i][j].b, adds[j], emit, emit_lo, j < 3 ? 1 : 0,
+                           "res_conv_fwd", st));
           continue;
         }
         __nv_bfloat16* cb = w.colk_blk[i][j] ? w.colk_blk[i][j] : w.colb;
@@ -545,15 +554,25 @@ struct SplitImpl {
   // one 3x3 conv backward on the shifted-window kernels: dY -> padded planar image (+ bias gradient in the same pass);
   // weight gradient from that image and the input image kept by the forward pass; input gradient = the SAME convolution
   // kernel over the dY image with flipped / transposed weights, ReLU mask and skip gradient in its epilogue
-  static int conv_bwd_impl(const float* x, bool relu_in, const float* dY, const float* Wsrc, const __nv_bfloat16* xp, int64_t xp_lo,
-                           __nv_bfloat16* wd, int64_t wd_lo, float* dW, float* db, float* dx, const float* addend, int64_t N, int S,
-                           int cin, int cout, W& w, const char* wtag, cudaStream_t st) {
-    if (dY) TB_TRY(sw_pad_split_colsum(dY, w.dyp, w.dyp_lo, N, S, S, cout, db, w.splitk, kScratchFloats, st));   // nullptr: w.dyp is ready
-    TB_TRY(sw_conv_wgrad(w.dyp, w.dyp_lo, xp, xp_lo, dW, N, S, S, cin, cout, w.splitk, kScratchFloats, wtag, st));
+  static int conv_bwd_impl(const float* x, bool relu_in, const float* dY, __nv_bfloat16* dyimg, int64_t dyimg_lo, const float* Wsrc,
+                           const __nv_bfloat16* xp, int64_t xp_lo, __nv_bfloat16* wd, int64_t wd_lo, float* dW, float* db, float* dx,
+                           const float* addend, __nv_bfloat16* emit, int64_t emit_lo, float* emit_db, int64_t N, int S, int cin, int cout,
+                           W& w, const char* wtag, cudaStream_t st) {
+    // dY == nullptr: dyimg (and db) were already produced by the previous kernel's epilogue / the fused max-pool backward
+    if (dY) TB_TRY(sw_pad_split_colsum(dY, dyimg, dyimg_lo, N, S, S, cout, db, w.splitk, kScratchFloats, st));
+    TB_TRY(sw_conv_wgrad(dyimg, dyimg_lo, xp, xp_lo, dW, N, S, S, cin, cout, w.splitk, kScratchFloats, wtag, st));
     if (dx) {
       TB_TRY(sw_pack_weights(Wsrc, wd, cout, cin, 1, st));
       SwEpilogue ep; ep.mask = relu_in ? x : nullptr; ep.addend = addend; ep.tag = "res_conv_dgrad";
-      TB_TRY(sw_conv_fwd(w.dyp, w.dyp_lo, wd, dx, N, S, S, cout, cin, ep, st));
+      // emit: dx is the dY of the conv that runs next in this backward pass - its image and (through the column sums) its
+      // bias gradient come out of this epilogue
+      const int64_t rows = sw_csum_rows(N, S, S);
+      if (emit) {
+        TB_REQUIRE((rows + 128) * cin <= kScratchFloats, "resnet: column-sum scratch too small");
+        ep.emit = emit; ep.emit_lo = emit_lo; ep.csum = w.splitk;
+      }
+      TB_TRY(sw_conv_fwd(dyimg, dyimg_lo, wd, dx, N, S, S, cout, cin, ep, st));
+      if (emit) TB_TRY(sw_csum_reduce(w.splitk, rows, cin, emit_db, st));
     }
     return 0;
   }
@@ -611,6 +630,9 @@ struct SplitImpl {
     }
     float* g0 = w.g[0]; float* g1 = w.g[1]; float* g2 = w.g[2];
     TB_TRY(relu_bwd<float>(w.s[2].X2, w.dfcin, g0, N * kFcIn, st));
+    __nv_bfloat16* dyi[2] = {w.dyp, w.dyp2};   // dY images (shifted-window path): dyi[dsel] is the one the next kernel reads
+    const int64_t dyi_lo[2] = {w.dyp_lo, w.dyp2_lo};
+    int dsel = 0;
     for (int i = kSections - 1; i >= 0; --i) {
       const int S = kSecS[i], So = kSecSo[i], ch = kSecCh[i], cin = kSecCin[i];
       Sec<float>& s = w.s[i];
@@ -619,24 +641,30 @@ struct SplitImpl {
       float* dxs[4] = {g1, g0, g2, g1};
       const float* skip[4] = {g2, nullptr, g0, nullptr};
       for (int j = 3; j >= 0; --j) {
-        if (w.xp_blk[i][j])
-          TB_TRY(conv_bwd_impl(xs[j], true, dys[j], P + pp.blk[i][j].w, w.xp_blk[i][j], w.xp_blk_lo[i][j], w.wd_blk[i][j],
-                               w.wd_blk_lo[i][j], G + pp.blk[i][j].w, G + pp.blk[i][j].b, dxs[j], skip[j], N, So, ch, ch, w,
-                               "res_conv_wgrad", st));
-        else
+        if (w.xp_blk[i][j]) {
+          // the dY image of conv j: written by the previous kernel's epilogue, except for the very first conv of the pass
+          const bool ready = !(i == kSections - 1 && j == 3);
+          __nv_bfloat16* cur = dyi[dsel]; const int64_t cur_lo = dyi_lo[dsel];
+          __nv_bfloat16* nxt = j > 0 ? dyi[dsel ^ 1] : nullptr;   // conv j's dx is conv j-1's dY (j = 0: feeds the max-pool backward)
+          TB_TRY(conv_bwd_impl(xs[j], true, ready ? nullptr : dys[j], cur, cur_lo, P + pp.blk[i][j].w, w.xp_blk[i][j], w.xp_blk_lo[i][j],
+                               w.wd_blk[i][j], w.wd_blk_lo[i][j], G + pp.blk[i][j].w, G + pp.blk[i][j].b, dxs[j], skip[j], nxt,
+                               dyi_lo[dsel ^ 1], j > 0 ? G + pp.blk[i][j - 1].b : nullptr, N, So, ch, ch, w, "res_conv_wgrad", st));
+          if (nxt) dsel ^= 1;
+        } else {
           TB_TRY(conv_bwd(xs[j], true, dys[j], P + pp.blk[i][j].w, w.colk_blk[i][j], w.colk_blk_lo[i][j], w.wd_blk[i][j], w.wd_blk_lo[i][j],
                           G + pp.blk[i][j].w, G + pp.blk[i][j].b, dxs[j], skip[j], N, So, ch, ch, w, st));
+        }
       }
       // dL/dP (the feat conv's output gradient) is consumed only as that conv's dY image + bias gradient: with the
       // shifted-window kernels the max-pool backward gathers straight into the image (never materialised in fp32)
       if (w.xp_feat[i])
-        TB_TRY(sw_pool_bwd_image_colsum(s.arg, g1, w.dyp, w.dyp_lo, N, S, S, ch, G + pp.feat[i].b, w.splitk, kScratchFloats, st));
+        TB_TRY(sw_pool_bwd_image_colsum(s.arg, g1, dyi[dsel], dyi_lo[dsel], N, S, S, ch, G + pp.feat[i].b, w.splitk, kScratchFloats, st));
       else
         TB_TRY(maxpool3x3s2_bwd<float>(s.arg, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
       const int64_t M = N * S * S;
       if (i == 0 && w.xp_feat[0]) {
-        TB_TRY(sw_conv_wgrad(w.dyp, w.dyp_lo, w.xp_feat[0], w.xp_feat_lo[0], G + pp.feat[0].w, N, S, S, 16, ch, w.splitk, kScratchFloats,
-                             "feat_conv_wgrad", st, 1.0f / 255.0f, 4));
+        TB_TRY(sw_conv_wgrad(dyi[dsel], dyi_lo[dsel], w.xp_feat[0], w.xp_feat_lo[0], G + pp.feat[0].w, N, S, S, 16, ch, w.splitk,
+                             kScratchFloats, "feat_conv_wgrad", st, 1.0f / 255.0f, 4));
       } else if (i == 0) {
         const int64_t ldk_in = ldk_of(4, true);
         TB_TRY(dy_split_colsum(g2, w.dyb, w.dyb_lo, M, ch, G + pp.feat[0].b, w.splitk, kScratchFloats, st));
@@ -649,9 +677,12 @@ struct SplitImpl {
         TB_TRY(gemm_wgrad(w.dyb, w.dyb_lo, cf, cf_lo, G + pp.feat[0].w, M, ch, 36, ldk_in, 1, 1, 1.0f / 255.0f, w.splitk,
                           "feat_conv_wgrad", st));
       } else if (w.xp_feat[i]) {
-        TB_TRY(conv_bwd_impl(w.s[i - 1].X2, false, nullptr /* image + bias gradient done above */, P + pp.feat[i].w, w.xp_feat[i],
-                             w.xp_feat_lo[i], w.wd_feat[i], w.wd_feat_lo[i], G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S, cin, ch,
-                             w, "res_conv_wgrad", st));
+        // (image + bias gradient done by the fused max-pool backward above); its dx = dL/dX2 of section i-1 = the dY of that
+        // section's last conv: emitted as the image + bias gradient that conv's backward starts from
+        TB_TRY(conv_bwd_impl(w.s[i - 1].X2, false, nullptr, dyi[dsel], dyi_lo[dsel], P + pp.feat[i].w, w.xp_feat[i], w.xp_feat_lo[i],
+                             w.wd_feat[i], w.wd_feat_lo[i], G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, dyi[dsel ^ 1], dyi_lo[dsel ^ 1],
+                             G + pp.blk[i - 1][3].b, N, S, cin, ch, w, "res_conv_wgrad", st));
+        dsel ^= 1;
       } else {
         TB_TRY(conv_bwd(w.s[i - 1].X2, false, g2, P + pp.feat[i].w, w.colk_feat[i], w.colk_feat_lo[i], w.wd_feat[i], w.wd_feat_lo[i],
                         G + pp.feat[i].w, G + pp.feat[i].b, g0, nullptr, N, S, cin, ch, w, st));
