@@ -65,9 +65,13 @@ struct SwFwdArgs {
   int Nf; SwGeom g;
 };
 
-// persistent: CTA walks (frame, tile) work items; warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..5 = epilogue
+// persistent: CTA walks (frame, tile) work items; warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..9 = two epilogue
+// groups of four warps (one per TMEM lane quarter), group g owning accumulator buffer g = the CTA's even / odd tiles: with the
+// image and column-sum outputs the epilogue of a tile (global loads of mask / residual, ~10 16-byte stores per row) takes
+// longer than its 18 MMAs, and one group made the kernels epilogue-bound
+constexpr int kSwThreads = 64 + 8 * 32;
 template <int CK, int NO>
-__global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
+__global__ void __launch_bounds__(kSwThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
   constexpr int CH = CK / 8;                   // chunk planes per frame
   constexpr int KP = CK / 16;                  // k16 steps per tap
   constexpr uint32_t W_PLANE = 9u * CK * NO * 2u;   // bytes of one weight plane (the image interleaves hi and lo rows)
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
   const uint32_t wbar = bars + 8u * (2 * kSwStages + 4);
   const uint32_t tmem_slot = wbar + 8u;
   constexpr uint32_t TMEM_COLS = 128;  // two accumulator buffers of 2*NO <= 64 columns
-  __shared__ float csum_s[4][32][NO + 1];   // column-sum staging of the four epilogue warps
+  __shared__ float csum_s[8][32][NO + 1];   // column-sum staging of the eight epilogue warps
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_work = a.Nf * a.g.tpf;
@@ -160,10 +164,9 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
       }
     }
   } else {
-    const int quarter = warp & 3;
+    const int quarter = warp & 3, ew = warp - 2, grp = ew >> 2;
     const int rl = quarter * 32 + lane;
-    int it = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+    for (int w = blockIdx.x + grp * gridDim.x, it = grp; w < total_work; w += 2 * gridDim.x, it += 2) {
       const int ab = it & 1;
       const int n = w / a.g.tpf, p = (w - n * a.g.tpf) * kTile + rl;
       const int y = p / a.g.Wp, x = p - y * a.g.Wp;
@@ -262,12 +265,12 @@ __global__ void __launch_bounds__(kThreads, 1) sw_conv_fwd_kernel(SwFwdArgs a) {
       }
       if (a.csum) {   // per (tile, warp) column sums in a fixed order: rows of padding positions hold zeros
 #pragma unroll
-        for (int j = 0; j < NO; ++j) csum_s[quarter][lane][j] = o[j];
+        for (int j = 0; j < NO; ++j) csum_s[ew][lane][j] = o[j];
         __syncwarp();
         if (lane < NO) {
           float sum = 0.f;
 #pragma unroll 8
-          for (int rr = 0; rr < 32; ++rr) sum += csum_s[quarter][rr][lane];
+          for (int rr = 0; rr < 32; ++rr) sum += csum_s[ew][rr][lane];
           a.csum[(int64_t(w) * 4 + quarter) * NO + lane] = sum;
         }
         __syncwarp();
@@ -293,13 +296,13 @@ int launch_sw_fwd(const SwFwdArgs& a, cudaStream_t stream) {
     TB_REQUIRE(e == cudaSuccess, "sw_conv_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr[dev & 63] = smem;
   }
-  int per_sm = int((224 * 1024) / (smem + sizeof(float) * 4 * 32 * (NO + 1) + 1024));   // + the static column-sum staging
+  int per_sm = int((224 * 1024) / (smem + sizeof(float) * 8 * 32 * (NO + 1) + 1024));   // + the static column-sum staging
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
   int64_t grid = int64_t(kNumSMsB200) * per_sm;
   const int64_t total = int64_t(a.Nf) * a.g.tpf;
   if (grid > total) grid = total;
-  sw_conv_fwd_kernel<CK, NO><<<(unsigned)grid, kThreads, smem, stream>>>(a);
+  sw_conv_fwd_kernel<CK, NO><<<(unsigned)grid, kSwThreads, smem, stream>>>(a);
   return check_launch("sw_conv_fwd_kernel");
 }
 
