@@ -283,8 +283,9 @@ def resnet_flops_table(N, A):
 
 def resnet_bytes_table(N):
     """ALGORITHMIC bytes of the tagged ResNet trunk ops on the bf16x3 backend (aggregated over the convs): every tensor moves
-    once - the conv input as a zero-padded split-bf16 image (4 B per element, (S+2)^2 pixels), outputs / gradients / ReLU
-    masks / residuals in fp32.  With 16..32 channels these products are HBM streams, not tensor-pipe work."""
+    once - conv inputs as zero-padded split-bf16 images (4 B per element, (S+2)^2 pixels; written by the previous conv's
+    epilogue where there is one), outputs / gradients / ReLU masks / residuals in fp32.  With 16..32 channels these products
+    are HBM streams, not tensor-pipe work."""
     secs = [(84, 42, 4, 16), (42, 21, 16, 32), (21, 11, 32, 32)]
     t = dict(feat_conv_fwd=0, feat_conv_wgrad=0, res_conv_fwd=0, res_conv_wgrad=0, res_conv_dgrad=0, pad_split=0,
              bias_grad_colsum=0, frames_to_image=0, maxpool_fwd=0, maxpool_bwd=0)
@@ -295,19 +296,19 @@ def resnet_bytes_table(N):
         wg = Mp * ch * 4 + Mp * cin16 * 4                       # dY image + input image
         t["feat_conv_wgrad" if i == 0 else "res_conv_wgrad"] += wg
         if i > 0:
-            t["res_conv_dgrad"] += Mp * ch * 4 + M * cin * 4    # dY image -> dX
-            t["pad_split"] += M * cin * 4 + Mp * cin * 4
+            t["res_conv_dgrad"] += Mp * ch * 4 + M * cin * 4 + Mp * cin * 4   # dY image -> dX fp32 + the previous section's dY image
         else:
             t["frames_to_image"] += N * 4 * S * S + Mp * 16 * 4
-        t["bias_grad_colsum"] += M * ch * 4 + Mp * ch * 4       # dY fp32 -> image (+ column sums)
         t["maxpool_fwd"] += M * ch * 4 + Mo * ch * 5            # + argmax byte
-        t["maxpool_bwd"] += Mo * ch * 5 + M * ch * 4
-        # four block convs: image + output (+ residual on two of them); backward: dY image + dX + ReLU mask (+ skip on two)
-        t["res_conv_fwd"] += 4 * (Mop * ch * 4 + Mo * ch * 4) + 2 * Mo * ch * 4
+        t["maxpool_bwd"] += Mo * ch * 5 + Mp * ch * 4           # pooled gradient + argmax -> the feat conv's dY image
+        t["pad_split"] += Mo * ch * 4 + Mop * ch * 4            # relu(X0) of the first block conv
+        # four block convs: image + output (+ residual on two of them) + the next conv's image from the epilogue;
+        # backward: dY image + dX + ReLU mask (+ skip on two) + the next dY image on three
+        t["res_conv_fwd"] += 4 * (Mop * ch * 4 + Mo * ch * 4) + 2 * Mo * ch * 4 + (4 if i < 2 else 3) * Mop * ch * 4
         t["res_conv_wgrad"] += 4 * (2 * Mop * ch * 4)
-        t["res_conv_dgrad"] += 4 * (Mop * ch * 4 + 2 * Mo * ch * 4) + 2 * Mo * ch * 4
-        t["pad_split"] += 4 * (Mo * ch * 4 + Mop * ch * 4)
-        t["bias_grad_colsum"] += 4 * (Mo * ch * 4 + Mop * ch * 4)
+        t["res_conv_dgrad"] += 4 * (Mop * ch * 4 + 2 * Mo * ch * 4) + 2 * Mo * ch * 4 + 3 * Mop * ch * 4
+    So, ch = secs[2][1], secs[2][3]
+    t["bias_grad_colsum"] = N * So * So * ch * 4 + N * (So + 2) ** 2 * ch * 4   # only the first conv of the backward pass
     return t
 
 

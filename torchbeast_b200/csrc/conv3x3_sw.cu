@@ -532,6 +532,15 @@ __device__ __forceinline__ void zero_slack_units(__nv_bfloat16* out, int64_t lo_
   }
 }
 
+// q / d for 0 <= q < 2^22 and d < 2^10 without the integer-division sequence (ncu: these index kernels were instruction-issue
+// bound with the XU pipe saturated by 32-bit divisions): one float multiply + a fix-up
+__device__ __forceinline__ int fast_div(int q, int d, float inv_d) {
+  int r = __float2int_rd((float(q) + 0.5f) * inv_d);
+  r -= (r * d > q);
+  r += ((r + 1) * d <= q);
+  return r;
+}
+
 // one thread = 8 channels of one padded pixel (borders written as zeros every time: the buffers are shared between images);
 // block = 256 / C8 consecutive padded pixels of frame blockIdx.y x all chunk planes (32-bit index arithmetic: one division).
 // COLSUM: block partial sums of the C channels -> partial[(frame * gridDim.x + blockIdx.x) * C + c]
@@ -541,12 +550,13 @@ __global__ void __launch_bounds__(256) sw_pad_split_kernel(const float4* __restr
                                                            float* __restrict__ partial, int slack_units) {
   const int Hp = H + 2, Wp = W + 2;
   if (blockIdx.x == 0 && blockIdx.y == 0) zero_slack_units(out, lo_off, int64_t(gridDim.y) * C8 * Hp * Wp * 8, slack_units);
-  const int cv = threadIdx.x % C8;
-  const int p = blockIdx.x * (256 / C8) + threadIdx.x / C8;
+  const int lc = (C8 == 4) ? 2 : (C8 == 2 ? 1 : 0);      // C8 is 1, 2 or 4
+  const int cv = threadIdx.x & (C8 - 1);
+  const int p = blockIdx.x * (256 >> lc) + (threadIdx.x >> lc);
   const int64_t n = blockIdx.y;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (p < Hp * Wp) {
-    const int py = p / Wp, px = p - py * Wp;
+    const int py = fast_div(p, Wp, 1.0f / float(Wp)), px = p - py * Wp;
     uint4 ph = make_uint4(0u, 0u, 0u, 0u), pl = ph;
     if (py >= 1 && py <= H && px >= 1 && px <= W) {
       const float4* src = x + (((n * H + (py - 1)) * W + (px - 1)) * C8 + cv) * 2;
@@ -587,28 +597,37 @@ __global__ void __launch_bounds__(256) sw_pool_bwd_image_kernel(const uint8_t* _
                                                                 int OW, int C8, float* __restrict__ partial, int slack_units) {
   const int Hp = H + 2, Wp = W + 2;
   if (blockIdx.x == 0 && blockIdx.y == 0) zero_slack_units(out, lo_off, int64_t(gridDim.y) * C8 * Hp * Wp * 8, slack_units);
-  const int cv = threadIdx.x % C8;
-  const int p = blockIdx.x * (256 / C8) + threadIdx.x / C8;
+  const int lc = (C8 == 4) ? 2 : (C8 == 2 ? 1 : 0);
+  const int cv = threadIdx.x & (C8 - 1);
+  const int p = blockIdx.x * (256 >> lc) + (threadIdx.x >> lc);
   const int64_t n = blockIdx.y;
   float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (p < Hp * Wp) {
-    const int py = p / Wp, px = p - py * Wp;
+    const int py = fast_div(p, Wp, 1.0f / float(Wp)), px = p - py * Wp;
     uint4 ph = make_uint4(0u, 0u, 0u, 0u), pl = ph;
     if (py >= 1 && py <= H && px >= 1 && px <= W) {
       const int iy = py - 1, ix = px - 1;
-      for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {
-        if (oy >= OH) continue;
+      // the <= 4 windows (oy, ox) in {iy/2, (iy+1)/2} x {ix/2, (ix+1)/2} (same order as maxpool_bwd_kernel: bit-identical sums);
+      // all loads first, then byte-wise compares of the 8 recorded taps against this pixel's tap
+      const int oy0 = iy >> 1, ox0 = ix >> 1;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const int oy = oy0 + a;
+        if ((a == 1 && (iy & 1) == 0) || oy >= OH) continue;     // even iy: (iy+1)/2 == iy/2
         const int kh = iy - (oy * 2 - 1);
-        for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
-          if (ox >= OW) continue;
-          const uint32_t tap = uint32_t(kh * 3 + (ix - (ox * 2 - 1)));
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int ox = ox0 + b;
+          if ((b == 1 && (ix & 1) == 0) || ox >= OW) continue;
+          const uint32_t tapv = uint32_t(kh * 3 + (ix - (ox * 2 - 1))) * 0x01010101u;
           const int64_t o = ((n * OH + oy) * OW + ox) * C8 + cv;            // 8-channel group of the pooled pixel
           const float4 d0 = __ldg(dyp + o * 2), d1 = __ldg(dyp + o * 2 + 1);
-          const uint2 a = __ldg(reinterpret_cast<const uint2*>(arg) + o);   // 8 argmax bytes
-          g[0] += ((a.x) & 0xffu) == tap ? d0.x : 0.f; g[1] += ((a.x >> 8) & 0xffu) == tap ? d0.y : 0.f;
-          g[2] += ((a.x >> 16) & 0xffu) == tap ? d0.z : 0.f; g[3] += (a.x >> 24) == tap ? d0.w : 0.f;
-          g[4] += ((a.y) & 0xffu) == tap ? d1.x : 0.f; g[5] += ((a.y >> 8) & 0xffu) == tap ? d1.y : 0.f;
-          g[6] += ((a.y >> 16) & 0xffu) == tap ? d1.z : 0.f; g[7] += (a.y >> 24) == tap ? d1.w : 0.f;
+          const uint2 am = __ldg(reinterpret_cast<const uint2*>(arg) + o);  // 8 argmax bytes
+          const uint32_t m0 = __vcmpeq4(am.x, tapv), m1 = __vcmpeq4(am.y, tapv);
+          g[0] += (m0 & 0x000000ffu) ? d0.x : 0.f; g[1] += (m0 & 0x0000ff00u) ? d0.y : 0.f;
+          g[2] += (m0 & 0x00ff0000u) ? d0.z : 0.f; g[3] += (m0 & 0xff000000u) ? d0.w : 0.f;
+          g[4] += (m1 & 0x000000ffu) ? d1.x : 0.f; g[5] += (m1 & 0x0000ff00u) ? d1.y : 0.f;
+          g[6] += (m1 & 0x00ff0000u) ? d1.z : 0.f; g[7] += (m1 & 0xff000000u) ? d1.w : 0.f;
         }
       }
       split_bf16x2(g[0], g[1], ph.x, pl.x); split_bf16x2(g[2], g[3], ph.y, pl.y);
