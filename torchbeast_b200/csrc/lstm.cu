@@ -11,6 +11,7 @@
 // torch.nn.LSTM conventions: gate order i,f,g,o; weight_ih [4H,In], weight_hh [4H,H]; two biases.
 #include "lstm.cuh"
 
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -2398,6 +2399,377 @@ static int lstm2_fwd_wave_split(LstmWs& ws, const LstmParams& p, float* y, const
   return check_launch("lstm2_fwd_wave_split_kernel");
 }
 
+// =========================================================================================
+// Single-layer recurrence on ONE thread-block cluster (precision 2, H = 256: the IMPALA ResNet's LSTM).
+// The cooperative kernels above pay 2-3 us per step for a grid-wide barrier through L2 although a [B, 256] x [256, 1024]
+// product is ~0.1 us of tensor-core time.  Here the 16 CTAs of one cluster own 16 hidden units x 4 gates each (64 gate
+// rows of W_hh as hi / lo mma.sync B fragments in registers for all steps), h is exchanged through DISTRIBUTED SHARED
+// MEMORY (every CTA stores its 16 units of h_t - bf16 hi / lo - into the A tile of all 16 CTAs) and the step barrier is the
+// hardware cluster barrier.  Warp w multiplies k16 steps {2w, 2w+1} for all 8 n8 tiles (A is read once per CTA), partial
+// sums meet in shared memory; thread (row, unit) finishes the four gates, keeps c in a register.
+// Same buffers as lstm_fwd_persistent_kernel: gates (pre-activations in, activated out), hs, cs, cm / hm rows t+1.
+// =========================================================================================
+namespace cg = cooperative_groups;
+constexpr int kClN = 16;            // CTAs per cluster
+constexpr int kClH = 256;
+constexpr int kClU = kClH / kClN;   // hidden units per CTA
+constexpr int kClHq = kClH + 8;     // A tile row pitch (bf16): 528 B, conflict-free ldmatrix
+constexpr int kClThreads = 256;
+
+struct ClusterFwdArgs {
+  const float* w_hh; float* gates; float* hs; float* cs; float* hm; float* cm; const float* nd;
+  int T1, B, Hp;
+};
+
+template <int MT>   // m16 tiles of batch rows (B <= 16*MT)
+__global__ void __launch_bounds__(kClThreads, 1) lstm_fwd_cluster_kernel(ClusterFwdArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = int(cluster.block_rank());
+  constexpr int R = MT * 16;
+  extern __shared__ __align__(128) unsigned char cl_smem[];
+  typedef __nv_bfloat16 ATile[2][R][kClHq];                        // [hi / lo][row][k]
+  ATile* A_s = reinterpret_cast<ATile*>(cl_smem);                  // [2 buffers]
+  typedef float PartT[R][65];                                      // [row][gate*16 + unit]
+  PartT* part = reinterpret_cast<PartT*>(cl_smem + 2 * sizeof(ATile));   // [8 warps]
+  typedef __nv_bfloat16 StageT[R][kClU];                           // this CTA's h_t as hi / lo, before the broadcast
+  StageT* stage = reinterpret_cast<StageT*>(cl_smem + 2 * sizeof(ATile) + 8 * sizeof(PartT));
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int B = a.B, H = kClH;
+  // B fragments: n tile nt = local gate rows [8 nt, 8 nt + 8), local row lr = gate*16 + unit -> W_hh row gate*H + 16*rank + unit
+  uint32_t bh[2][8][2], bl[2][8][2];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int lr = nt * 8 + (lane >> 2);
+      const float* wr = a.w_hh + (int64_t(lr >> 4) * H + rank * kClU + (lr & 15)) * H;
+      const int k = (2 * wrp + ks) * 16 + (lane & 3) * 2;
+      split_pack(wr[k], wr[k + 1], bh[ks][nt][0], bl[ks][nt][0]);
+      split_pack(wr[k + 8], wr[k + 9], bh[ks][nt][1], bl[ks][nt][1]);
+    }
+  // initial masked state: every CTA loads the whole h tile (rows >= B are zero)
+  for (int i = tid; i < R * H; i += kClThreads) {
+    const int r = i / H, k = i - r * H;
+    const float v = r < B ? a.hm[int64_t(r) * a.Hp + k] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    A_s[0][0][r][k] = h;
+    A_s[0][1][r][k] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+  // pointwise role: RP rows per thread, unit u
+  constexpr int RP = R / 16;
+  const int u = tid & 15, r0 = tid >> 4;
+  const int ug = rank * kClU + u;
+  float c_prev[RP];
+#pragma unroll
+  for (int q = 0; q < RP; ++q) { const int r = r0 + 16 * q; c_prev[q] = r < B ? a.cm[int64_t(r) * H + ug] : 0.f; }
+  // inputs of the pointwise phase that do not depend on the recurrence (input projection, next step's notdone) are loaded one
+  // step ahead, right before the cluster barrier, so their L2 / HBM latency hides behind it
+  float pre[RP][4], ndn[RP];
+  auto load_inputs = [&](int t) {
+#pragma unroll
+    for (int q = 0; q < RP; ++q) {
+      const int r = r0 + 16 * q;
+      ndn[q] = (r < B && t + 1 < a.T1) ? __ldg(a.nd + int64_t(t + 1) * B + r) : 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pre[q][g] = (r < B && t < a.T1) ? __ldcg(a.gates + (int64_t(t) * B + r) * 4 * H + g * H + ug) : 0.f;
+    }
+  };
+  load_inputs(0);
+  cluster.sync();
+  for (int t = 0; t < a.T1; ++t) {
+    const int cur = t & 1;
+    const bool last = (t == a.T1 - 1);
+    float acc[MT][8][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        uint32_t ah[4], al[4];
+        const __nv_bfloat16* ap = &A_s[cur][0][mt * 16 + (lane & 15)][(2 * wrp + ks) * 16 + (lane >> 4) * 8];
+        ldmatrix_x4(ah, ap);
+        ldmatrix_x4(al, ap + R * kClHq);
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) mma3(acc[mt][nt], ah, al, bh[ks][nt][0], bh[ks][nt][1], bl[ks][nt][0], bl[ks][nt][1]);
+      }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int r = mt * 16 + (lane >> 2), c = nt * 8 + (lane & 3) * 2;
+        part[wrp][r][c] = acc[mt][nt][0]; part[wrp][r][c + 1] = acc[mt][nt][1];
+        part[wrp][r + 8][c] = acc[mt][nt][2]; part[wrp][r + 8][c + 1] = acc[mt][nt][3];
+      }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RP; ++q) {
+      const int r = r0 + 16 * q;
+      float gv[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float d = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) d += part[w][r][g * 16 + u];   // fixed order
+        const float x = pre[q][g] + d;
+        gv[g] = (g == 2) ? tanhf(x) : sigmoidf_(x);
+      }
+      const float c_new = gv[1] * c_prev[q] + gv[0] * gv[2];
+      const float h_new = gv[3] * tanhf(c_new);
+      const float hm_next = h_new * ndn[q];
+      c_prev[q] = c_new * ndn[q];
+      const __nv_bfloat16 hh = __float2bfloat16_rn(hm_next);
+      stage[0][r][u] = hh;
+      stage[1][r][u] = __float2bfloat16_rn(hm_next - __bfloat162float(hh));
+      if (r < B) {   // saved for the backward pass / the weight-gradient GEMMs: off the critical path
+        const int64_t row = int64_t(t) * B + r;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) a.gates[row * 4 * H + g * H + ug] = gv[g];
+        a.cs[row * H + ug] = c_new;
+        a.hs[row * H + ug] = h_new;
+        if (!last) {
+          a.cm[(row + B) * H + ug] = c_prev[q];
+          a.hm[(row + B) * a.Hp + ug] = hm_next;
+        }
+      }
+    }
+    __syncthreads();
+    if (!last) {
+      // broadcast this CTA's 16 units (32 B per row and plane) into the next A tile of every CTA: thread (row, d) serves CTA d
+#pragma unroll
+      for (int q = 0; q < RP; ++q) {
+        const int r = r0 + 16 * q;
+        __nv_bfloat16* dst0 = cluster.map_shared_rank(&A_s[cur ^ 1][0][r][rank * kClU], u);
+        __nv_bfloat16* dst1 = cluster.map_shared_rank(&A_s[cur ^ 1][1][r][rank * kClU], u);
+        const uint4* s0 = reinterpret_cast<const uint4*>(&stage[0][r][0]);
+        const uint4* s1 = reinterpret_cast<const uint4*>(&stage[1][r][0]);
+        reinterpret_cast<uint4*>(dst0)[0] = s0[0]; reinterpret_cast<uint4*>(dst0)[1] = s0[1];
+        reinterpret_cast<uint4*>(dst1)[0] = s1[0]; reinterpret_cast<uint4*>(dst1)[1] = s1[1];
+      }
+    }
+    load_inputs(t + 1);
+    cluster.sync();   // release / acquire at cluster scope: every CTA's tile of step t+1 is complete and visible
+  }
+}
+
+static size_t cluster_fwd_smem(int MT) {
+  const size_t R = size_t(MT) * 16;
+  return 2 * (2 * R * kClHq * 2) + 8 * (R * 65 * 4) + 2 * R * kClU * 2;
+}
+
+static int lstm_fwd_cluster(const LstmLayerWs& L, const float* w_hh, float* hs, const float* notdone, int64_t T1, int64_t B, int H,
+                            cudaStream_t st) {
+  const char* env = getenv("TB_LSTM_CLUSTER");
+  if ((env && env[0] == '0') || H != kClH || B > 32 || B < 1) return -1;
+  static int attr_ok[64] = {0};   // per device: 0 unknown, 1 ok, -1 unavailable
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_ok[dev & 63] == 0) {
+    cudaError_t e1 = cudaFuncSetAttribute(lstm_fwd_cluster_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e2 = cudaFuncSetAttribute(lstm_fwd_cluster_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(lstm_fwd_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cluster_fwd_smem(1)));
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(lstm_fwd_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cluster_fwd_smem(2)));
+    attr_ok[dev & 63] = (e1 == cudaSuccess && e2 == cudaSuccess) ? 1 : -1;
+    if (attr_ok[dev & 63] < 0) cudaGetLastError();
+  }
+  if (attr_ok[dev & 63] < 0) return -1;
+  ClusterFwdArgs a;
+  a.w_hh = w_hh; a.gates = L.gates; a.hs = hs; a.cs = L.cs; a.hm = L.hm; a.cm = L.cm; a.nd = notdone;
+  a.T1 = int(T1); a.B = int(B); a.Hp = padded_h(H);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kClN);
+  cfg.blockDim = dim3(kClThreads);
+  cfg.dynamicSmemBytes = cluster_fwd_smem(B <= 16 ? 1 : 2);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kClN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = (B <= 16) ? cudaLaunchKernelEx(&cfg, lstm_fwd_cluster_kernel<1>, a) : cudaLaunchKernelEx(&cfg, lstm_fwd_cluster_kernel<2>, a);
+  if (e != cudaSuccess) {   // a 16-CTA cluster cannot be placed here: the cooperative kernel takes over
+    cudaGetLastError();
+    return -1;
+  }
+  return check_launch("lstm_fwd_cluster_kernel");
+}
+
+// ---- backward on the same cluster ---------------------------------------------------------------------------------
+// dL/dh_t needs dgates_{t+1} . W_hh over ALL 1024 gate rows.  Broadcasting the gate gradients (64 KB per CTA and step) would sit
+// on the DSMEM links (17-21 B/clk per SM measured); instead every CTA multiplies ITS 64 gate gradients (local, bf16 hi / lo
+// in shared memory) with ITS 64 rows of W_hh (B fragments in registers) into a partial dh[rows, 256], and the partials are
+// reduce-scattered: the 16 columns of destination CTA d go into slot [source] of d's receive buffer (16 KB per CTA and
+// step), summed by d in source order (deterministic) at the start of the next step.  Buffers as lstm_bwd_persistent_kernel:
+// reads dy / gates (activated) / cs / cm / nd, writes dgates [N, 4H] fp32 for the weight-gradient GEMMs.
+struct ClusterBwdArgs {
+  const float* w_hh; const float* dy; const float* nd; const float* gates; const float* cs; const float* cm; float* dgates;
+  int T1, B;
+};
+
+template <int MT>
+__global__ void __launch_bounds__(kClThreads, 1) lstm_bwd_cluster_kernel(ClusterBwdArgs a) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = int(cluster.block_rank());
+  constexpr int R = MT * 16, PQ = 64 + 8;
+  extern __shared__ __align__(128) unsigned char cl_smem[];
+  typedef __nv_bfloat16 PTile[R][PQ];                              // gate gradients of this CTA [row][gate*16 + unit]
+  PTile* P_s = reinterpret_cast<PTile*>(cl_smem);                  // [hi / lo]
+  typedef float RecvT[kClN][R][kClU];                              // [source CTA][row][unit]
+  RecvT* recv = reinterpret_cast<RecvT*>(cl_smem + 2 * sizeof(PTile));   // [2 buffers]
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int B = a.B, H = kClH;
+  // B fragments: reduction index = local gate row lg (k16 steps 0..3), n = output column (hidden unit) 32*wrp + 8*ntl + lane/4
+  uint32_t bh[4][4][2], bl[4][4][2];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int ntl = 0; ntl < 4; ++ntl) {
+      const int n = wrp * 32 + ntl * 8 + (lane >> 2);
+      const int lg = ks * 16 + (lane & 3) * 2;
+      auto wv = [&](int l) { return a.w_hh[(int64_t(l >> 4) * H + rank * kClU + (l & 15)) * H + n]; };
+      split_pack(wv(lg), wv(lg + 1), bh[ks][ntl][0], bl[ks][ntl][0]);
+      split_pack(wv(lg + 8), wv(lg + 9), bh[ks][ntl][1], bl[ks][ntl][1]);
+    }
+  constexpr int RP = R / 16;
+  const int u = tid & 15, r0 = tid >> 4;
+  const int ug = rank * kClU + u;
+  float dc_carry[RP];
+#pragma unroll
+  for (int q = 0; q < RP; ++q) dc_carry[q] = 0.f;
+  // per-step inputs, loaded one step ahead (before the cluster barrier)
+  float in_dy[RP], in_g[RP][4], in_cs[RP], in_cm[RP], in_nd[RP], in_ndn[RP];
+  auto load_inputs = [&](int t) {
+#pragma unroll
+    for (int q = 0; q < RP; ++q) {
+      const int r = r0 + 16 * q;
+      const bool ok = r < B && t >= 0;
+      const int64_t row = int64_t(t) * B + r;
+      in_dy[q] = ok ? __ldg(a.dy + row * H + ug) : 0.f;
+      in_cs[q] = ok ? __ldg(a.cs + row * H + ug) : 0.f;
+      in_cm[q] = ok ? __ldg(a.cm + row * H + ug) : 0.f;
+      in_nd[q] = ok ? __ldg(a.nd + row) : 0.f;
+      in_ndn[q] = (ok && t + 1 < a.T1) ? __ldg(a.nd + row + B) : 0.f;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) in_g[q][g] = ok ? __ldg(a.gates + row * 4 * H + g * H + ug) : 0.f;
+    }
+  };
+  load_inputs(a.T1 - 1);
+  cluster.sync();
+  int buf = 0;
+  for (int t = a.T1 - 1, it = 0; t >= 0; --t, ++it) {
+#pragma unroll
+    for (int q = 0; q < RP; ++q) {
+      const int r = r0 + 16 * q;
+      float dh = in_dy[q], dc = 0.f;
+      if (it > 0) {
+        float rec = 0.f;
+#pragma unroll
+        for (int sidx = 0; sidx < kClN; ++sidx) rec += recv[buf][sidx][r][u];   // fixed order
+        dh += rec * in_ndn[q];
+        dc = dc_carry[q];
+      }
+      const float ig = in_g[q][0], fg = in_g[q][1], gg = in_g[q][2], og = in_g[q][3];
+      const float tc = tanhf(in_cs[q]);
+      const float d_o = dh * tc;
+      dc += dh * og * (1.0f - tc * tc);
+      const float d_i = dc * gg, d_f = dc * in_cm[q], d_g = dc * ig;
+      float pv[4];
+      pv[0] = d_i * ig * (1.0f - ig); pv[1] = d_f * fg * (1.0f - fg);
+      pv[2] = d_g * (1.0f - gg * gg); pv[3] = d_o * og * (1.0f - og);
+      dc_carry[q] = dc * fg * in_nd[q];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const __nv_bfloat16 hh = __float2bfloat16_rn(pv[g]);
+        P_s[0][r][g * 16 + u] = hh;
+        P_s[1][r][g * 16 + u] = __float2bfloat16_rn(pv[g] - __bfloat162float(hh));
+        if (r < B) a.dgates[(int64_t(t) * B + r) * 4 * H + g * H + ug] = pv[g];
+      }
+    }
+    if (t == 0) break;   // uniform: no earlier step needs dh
+    __syncthreads();
+    float acc[MT][4][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int ntl = 0; ntl < 4; ++ntl)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[mt][ntl][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        uint32_t ah[4], al[4];
+        const __nv_bfloat16* ap = &P_s[0][mt * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8];
+        ldmatrix_x4(ah, ap);
+        ldmatrix_x4(al, ap + R * PQ);
+#pragma unroll
+        for (int ntl = 0; ntl < 4; ++ntl) mma3(acc[mt][ntl], ah, al, bh[ks][ntl][0], bh[ks][ntl][1], bl[ks][ntl][0], bl[ks][ntl][1]);
+      }
+    // reduce-scatter: this warp's 32 columns belong to CTAs 2*wrp (n tiles 0, 1) and 2*wrp + 1 (n tiles 2, 3)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int ntl = 0; ntl < 4; ++ntl) {
+        const int dest = 2 * wrp + (ntl >> 1);
+        const int col = (ntl & 1) * 8 + (lane & 3) * 2, row = mt * 16 + (lane >> 2);
+        float* d0 = cluster.map_shared_rank(&recv[buf ^ 1][rank][row][col], dest);
+        float* d1 = cluster.map_shared_rank(&recv[buf ^ 1][rank][row + 8][col], dest);
+        *reinterpret_cast<float2*>(d0) = make_float2(acc[mt][ntl][0], acc[mt][ntl][1]);
+        *reinterpret_cast<float2*>(d1) = make_float2(acc[mt][ntl][2], acc[mt][ntl][3]);
+      }
+    load_inputs(t - 1);
+    cluster.sync();
+    buf ^= 1;
+  }
+  cluster.sync();   // nobody leaves while a peer may still address its shared memory
+}
+
+static size_t cluster_bwd_smem(int MT) {
+  const size_t R = size_t(MT) * 16;
+  return 2 * (R * 72 * 2) + 2 * (size_t(kClN) * R * kClU * 4);
+}
+
+static int lstm_bwd_cluster(const LstmLayerWs& L, const float* w_hh, const float* dy, const float* notdone, int64_t T1, int64_t B,
+                            int H, cudaStream_t st) {
+  const char* env = getenv("TB_LSTM_CLUSTER");
+  if ((env && env[0] == '0') || H != kClH || B > 32 || B < 1) return -1;
+  static int attr_ok[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (attr_ok[dev & 63] == 0) {
+    cudaError_t e1 = cudaFuncSetAttribute(lstm_bwd_cluster_kernel<1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaError_t e2 = cudaFuncSetAttribute(lstm_bwd_cluster_kernel<2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(lstm_bwd_cluster_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cluster_bwd_smem(1)));
+    if (e2 == cudaSuccess) e2 = cudaFuncSetAttribute(lstm_bwd_cluster_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cluster_bwd_smem(2)));
+    attr_ok[dev & 63] = (e1 == cudaSuccess && e2 == cudaSuccess) ? 1 : -1;
+    if (attr_ok[dev & 63] < 0) cudaGetLastError();
+  }
+  if (attr_ok[dev & 63] < 0) return -1;
+  ClusterBwdArgs a;
+  a.w_hh = w_hh; a.dy = dy; a.nd = notdone; a.gates = L.gates; a.cs = L.cs; a.cm = L.cm; a.dgates = L.dgates;
+  a.T1 = int(T1); a.B = int(B);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kClN);
+  cfg.blockDim = dim3(kClThreads);
+  cfg.dynamicSmemBytes = cluster_bwd_smem(B <= 16 ? 1 : 2);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kClN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = (B <= 16) ? cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel<1>, a) : cudaLaunchKernelEx(&cfg, lstm_bwd_cluster_kernel<2>, a);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return check_launch("lstm_bwd_cluster_kernel");
+}
+
 static int lstm_bwd_persistent_mma(const LstmLayerWs& L, const float* w_hh, const float* dy, const float* notdone,
                                    int64_t T1, int64_t B, int H, float* db, unsigned* counter, cudaStream_t st) {
   const int Hq = mma_hq(H);
@@ -2687,6 +3059,7 @@ int lstm_forward(const float* x, const float* notdone, const float* h0, const fl
       prc = lstm_fwd_persistent_mma(L, p.w_hh[l], hs, notdone, T1, B, H, ws.sync, st);
       TB_REQUIRE(prc >= 0, "lstm: tensor-core recurrence kernel does not fit (B=%lld H=%d)", (long long)B, H);
     }
+    if (prc < 0 && precision == 2) prc = lstm_fwd_cluster(L, p.w_hh[l], hs, notdone, T1, B, H, st);   // H = 256, B <= 32
     if (prc < 0) prc = lstm_fwd_persistent(L, hs, notdone, T1, B, H, ws.sync, st);
     if (prc > 0) return prc;
     for (int64_t t = 0; prc < 0 && t < T1; ++t) {
@@ -2793,6 +3166,7 @@ int lstm_backward(const float* dy, const float* x, const float* notdone, const L
       prc = lstm_bwd_persistent_mma(L, p.w_hh[l], dyl, notdone, T1, B, H, g.b_ih[l], ws.sync + 16, st);
       TB_REQUIRE(prc >= 0, "lstm: tensor-core recurrence kernel does not fit (B=%lld H=%d)", (long long)B, H);
     }
+    if (prc < 0 && precision == 2 && layers == 1) prc = lstm_bwd_cluster(L, p.w_hh[l], dyl, notdone, T1, B, H, st);   // H = 256, B <= 32
     if (prc < 0) prc = lstm_bwd_persistent(L, ws, dyl, notdone, T1, B, H, ws.sync + 16, st);
     if (prc > 0) return prc;
     for (int64_t t = T1 - 1; prc < 0 && t >= 0; --t) {
