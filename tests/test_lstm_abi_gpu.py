@@ -29,6 +29,9 @@ def torch_reference(ref, x, notdone, h0, c0, dy):
     (9, 5, 519, 519, 2, "bf16x3"),
     (7, 40, 257, 256, 1, "fp32"),
     (7, 40, 257, 256, 1, "bf16x3"),
+    (81, 8, 257, 256, 1, "bf16x3"),      # the IMPALA ResNet's LSTM at one GPU's shard of configs[3]: 16-CTA cluster kernels, B <= 16
+    (33, 27, 257, 256, 1, "bf16x3"),     # same, two m16 row tiles (16 < B <= 32)
+    (12, 3, 257, 256, 2, "bf16x3"),      # two layers of H = 256: cluster forward per layer, cooperative backward
     (601, 128, 512, 512, 1, "fp32"),     # BASELINE configs[4]
 ])
 def test_lstm_abi_vs_torch(T1, B, In, H, layers, precision):
