@@ -184,12 +184,16 @@ int tb_lstm_backward(const float* dy, const float* x, const float* notdone, cons
 int64_t tb_resnet_param_count(int num_actions, int use_lstm);
 size_t tb_resnet_workspace_bytes(int64_t T1, int64_t B, int num_actions, int use_lstm, int precision);
 /* polybeast_learner.py:214-266 Net.forward without the action sampling: frame u8 [T1,B,4,84,84], reward f32
- * [T1,B], notdone f32 [T1,B] and h0,c0/hN,cN f32 [1,B,256] (LSTM only) -> policy_logits [T1,B,A], baseline [T1,B]. */
+ * [T1,B], notdone f32 [T1,B] and h0,c0/hN,cN f32 [1,B,256] (LSTM only) -> policy_logits [T1,B,A], baseline [T1,B].
+ * precision: 0 = fp32 SIMT patch-matrix GEMMs; 1 = bf16 activations + patch-matrix tcgen05 GEMMs (not parity-grade);
+ * 2 = split-bf16 (the Python default): fp32 activations, every 3x3 conv as a shifted-window implicit GEMM over padded
+ * channel-chunk-planar hi/lo images (csrc/conv3x3_sw.cu), the H=256 LSTM on one thread-block cluster.  T1*B < 65536.
+ * The same precision and workspace must be used for forward and backward.                                            */
 int tb_resnet_forward(const uint8_t* frame, const float* reward, const float* notdone, const float* h0,
                       const float* c0, const float* params, int64_t T1, int64_t B, int num_actions, int use_lstm,
                       int precision, void* workspace, float* policy_logits, float* baseline, float* hN, float* cN,
                       void* stream);
-/* Backward (patch matrices are recomputed from `frame` and the stored activations). */
+/* Backward of the forward pass that last ran on `workspace` (it keeps the conv input images / activations it needs). */
 int tb_resnet_backward(const uint8_t* frame, const float* grad_logits, const float* grad_baseline,
                        const float* notdone, const float* params, int64_t T1, int64_t B, int num_actions,
                        int use_lstm, int precision, void* workspace, float* grads, void* stream);

@@ -12,7 +12,12 @@
 // is the same rows shifted by (kh*(W+2) + kw)*16 bytes: 9 descriptors over one copy of the data.  Output rows that fall on
 // padding columns / rows are computed and dropped by the epilogue (2/(W+2) of the tile).
 //
-// Split-bf16 (see gemm_tc.cuh): every product is lo.hi + hi.lo + hi.hi into the same fp32 TMEM accumulator.
+// Split-bf16 (see gemm_tc.cuh): x = hi + lo per operand, products x_hi.w_hi + x_hi.w_lo + x_lo.w_hi in fp32.  On tcgen05 the
+// weight rows are stored [w_hi | w_lo] so that x_hi.[w_hi | w_lo] is ONE MMA with N = 2*NO (an SS-mode MMA costs >= 32 cycles
+// for its A operand whatever N is); x_lo.w_hi accumulates onto the first half and the epilogue adds the halves.
+// The epilogue can also write the NEXT conv's padded image (and per-tile column sums = its bias gradient in the backward
+// pass), so most fp32 -> image passes do not exist.  Weight gradients (M = 16..32 output channels: a shape the 128-row tcgen05
+// atom cannot fill) run on mma.sync.m16n8k16 from the same planar tiles (sw_conv_wgrad_kernel).
 #include "conv3x3_sw.cuh"
 
 #include "tc_common.cuh"
