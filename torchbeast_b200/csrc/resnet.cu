@@ -73,6 +73,7 @@ struct ResWs {
   T *fcin, *dfc, *dfcin, *g[3], *col, *dcol;
   T *wfeat[kSections], *wblk[kSections][4], *wfc;
   float *core_in, *core_out, *dcore_out, *dcore_in, *splitk, *colsum_scratch;
+  int64_t splitk_floats = 0;   // >= kScratchFloats; the split backend's per-tile column-sum partials grow with the frame count
   // split-bf16 backend (precision 2): activations stay fp32; only the GEMM operands are bf16 hi / lo planes
   // (lo plane = hi pointer + the *_lo element offset)
   __nv_bfloat16 *colb = nullptr, *dyb = nullptr, *fcb = nullptr, *dfcb = nullptr;
@@ -200,7 +201,11 @@ ResWs<T> res_ws(void* base, int64_t N, int64_t T1, int64_t B, int A, int use_lst
   w.core_out = use_lstm ? takef(N * pp.core_out) : w.core_in;
   w.dcore_out = takef(N * (pp.core_in > pp.core_out ? pp.core_in : pp.core_out));
   w.dcore_in = use_lstm ? takef(N * pp.core_in) : w.dcore_out;
-  w.splitk = takef(kScratchFloats);
+  // split-K partials need kScratchFloats; the split backend's fixed-order column-sum partials need up to ~1000 floats per frame
+  // (one row of C floats per 128-pixel block / per tile and epilogue warp of the largest image)
+  w.splitk_floats = kScratchFloats;
+  if (split && N * 1056 + 8192 > w.splitk_floats) w.splitk_floats = N * 1056 + 8192;
+  w.splitk = takef(w.splitk_floats);
   w.colsum_scratch = takef(colsum_scratch_floats(4 * kLstmH));
   if (use_lstm) {
     const int lprec = split ? 2 : (kBf16 ? 1 : 0);
@@ -559,8 +564,8 @@ struct SplitImpl {
                            const float* addend, __nv_bfloat16* emit, int64_t emit_lo, float* emit_db, int64_t N, int S, int cin, int cout,
                            W& w, const char* wtag, cudaStream_t st) {
     // dY == nullptr: dyimg (and db) were already produced by the previous kernel's epilogue / the fused max-pool backward
-    if (dY) TB_TRY(sw_pad_split_colsum(dY, dyimg, dyimg_lo, N, S, S, cout, db, w.splitk, kScratchFloats, st));
-    TB_TRY(sw_conv_wgrad(dyimg, dyimg_lo, xp, xp_lo, dW, N, S, S, cin, cout, w.splitk, kScratchFloats, wtag, st));
+    if (dY) TB_TRY(sw_pad_split_colsum(dY, dyimg, dyimg_lo, N, S, S, cout, db, w.splitk, w.splitk_floats, st));
+    TB_TRY(sw_conv_wgrad(dyimg, dyimg_lo, xp, xp_lo, dW, N, S, S, cin, cout, w.splitk, w.splitk_floats, wtag, st));
     if (dx) {
       TB_TRY(sw_pack_weights(Wsrc, wd, cout, cin, 1, st));
       SwEpilogue ep; ep.mask = relu_in ? x : nullptr; ep.addend = addend; ep.tag = "res_conv_dgrad";
@@ -568,7 +573,7 @@ struct SplitImpl {
       // bias gradient come out of this epilogue
       const int64_t rows = sw_csum_rows(N, S, S);
       if (emit) {
-        TB_REQUIRE((rows + 128) * cin <= kScratchFloats, "resnet: column-sum scratch too small");
+        TB_REQUIRE((rows + 128) * cin <= w.splitk_floats, "resnet: column-sum scratch too small");
         ep.emit = emit; ep.emit_lo = emit_lo; ep.csum = w.splitk;
       }
       TB_TRY(sw_conv_fwd(dyimg, dyimg_lo, wd, dx, N, S, S, cout, cin, ep, st));
@@ -658,13 +663,13 @@ struct SplitImpl {
       // dL/dP (the feat conv's output gradient) is consumed only as that conv's dY image + bias gradient: with the
       // shifted-window kernels the max-pool backward gathers straight into the image (never materialised in fp32)
       if (w.xp_feat[i])
-        TB_TRY(sw_pool_bwd_image_colsum(s.arg, g1, dyi[dsel], dyi_lo[dsel], N, S, S, ch, G + pp.feat[i].b, w.splitk, kScratchFloats, st));
+        TB_TRY(sw_pool_bwd_image_colsum(s.arg, g1, dyi[dsel], dyi_lo[dsel], N, S, S, ch, G + pp.feat[i].b, w.splitk, w.splitk_floats, st));
       else
         TB_TRY(maxpool3x3s2_bwd<float>(s.arg, g1, g2, N, S, S, ch, st));   // g2 = dL/dP
       const int64_t M = N * S * S;
       if (i == 0 && w.xp_feat[0]) {
         TB_TRY(sw_conv_wgrad(dyi[dsel], dyi_lo[dsel], w.xp_feat[0], w.xp_feat_lo[0], G + pp.feat[0].w, N, S, S, 16, ch, w.splitk,
-                             kScratchFloats, "feat_conv_wgrad", st, 1.0f / 255.0f, 4));
+                             w.splitk_floats, "feat_conv_wgrad", st, 1.0f / 255.0f, 4));
       } else if (i == 0) {
         const int64_t ldk_in = ldk_of(4, true);
         TB_TRY(dy_split_colsum(g2, w.dyb, w.dyb_lo, M, ch, G + pp.feat[0].b, w.splitk, kScratchFloats, st));
