@@ -717,7 +717,10 @@ def main():
                           "one CUDA-graph replay of the step" if graphed is not None else "eager step")),
         gpu_launches=int(launches), clocks=clocks, final_total_loss=final_loss,
         parity="default backend %s: tests/test_learner_baseline_gpu.py holds it to reference-generated T=80,B=32 fixtures "
-               "(outputs, vs, pg_advantages, losses <= 1e-5)" % model.precision if args.net == "atari" else None,
+               "(outputs, vs, pg_advantages, losses <= 1e-5)" % model.precision if args.net == "atari" else
+               ("backend %s: tests/test_resnet_gpu.py holds it to the reference-generated T=80,B=8 fixture (one GPU's shard of "
+                "configs[3]): outputs, vs, pg_advantages, losses <= 1e-5; gradients relative L2 < 6e-3 per tensor "
+                "(profiles/parity_r2_resnet.txt)" % model.precision),
     )
     if dp is not None:
         line["dp_check"] = dp
